@@ -1,0 +1,174 @@
+"""The oracle (oracle/uam_oracle.py) against golden vectors produced by the reference's own code.
+
+Pins the CPU restatement before anything is compared with it (no GPU needed)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import uam_oracle as orc
+from conftest import full_paths
+
+RTOL = 1e-13   # oracle vs reference float64 (observed ~1e-15; summation-order noise only)
+
+
+@pytest.fixture(scope='module')
+def omap(fixture_spec):
+    return orc.OMap(fixture_spec)
+
+
+def test_survey_appendix_b_values(golden, golden_meta):
+    # SURVEY.md App. B.1 numbers reproduce from the reference run here
+    assert golden['arc_N80_cost'][0] == pytest.approx(2497.8684368774984, rel=1e-14)
+    assert golden['arc_N80_cost'][2] == pytest.approx(2565.281618963959, rel=1e-14)
+    assert golden['arc_N62_cost'][3] == pytest.approx(2278.261899104732, rel=1e-14)
+    assert golden_meta['survey_jitter_cost'] == pytest.approx(2660.2542351510133, rel=1e-14)
+    assert golden['arc_N80_collide'].sum(axis=1).tolist() == [0, 0, 22, 34, 34]
+    assert golden['arc_N80_g'].shape == (5, 650)
+
+
+@pytest.mark.parametrize('N', [80, 62, 64, 5])
+def test_arcs(omap, fixture_spec, golden, N):
+    f = fixture_spec
+    for i, d in enumerate(golden['arc_disp']):
+        x = orc.create_x_init(f['x_start'], f['x_goal'], N, float(d))
+        np.testing.assert_allclose(x, golden[f'arc_N{N}_x'][i], rtol=1e-15, atol=1e-15)
+    X = golden[f'arc_N{N}_x']
+    Z = full_paths(f, X)
+    cost = orc.get_cost(omap, Z, N, f['weights'], f['enlargement'], f['options'])
+    np.testing.assert_allclose(cost, golden[f'arc_N{N}_cost'], rtol=RTOL)
+    g = orc.get_nonlincon(omap, Z, N, f['maxratio'], f['maxalpha'], f['options'])
+    G = golden[f'arc_N{N}_g']
+    np.testing.assert_allclose(g, G, rtol=1e-9, atol=1e-13)
+    # zero pattern of the obstacle block is bit-exact (fp64, same op order)
+    assert np.array_equal(g[:, 3 * N:] == 0, G[:, 3 * N:] == 0)
+    np.testing.assert_allclose(orc.length_of(omap, X, N, False), golden[f'arc_N{N}_length'], rtol=RTOL)
+    np.testing.assert_allclose(orc.length_of(omap, X, N, True), golden[f'arc_N{N}_length_smooth'], rtol=RTOL)
+    col = omap.collides(Z.reshape(-1, 2)).reshape(Z.shape[0], N + 2)
+    assert np.array_equal(col, golden[f'arc_N{N}_collide'])
+    assert np.array_equal(orc.path_collides(omap, Z, N), golden[f'arc_N{N}_collide'].any(axis=1))
+
+
+def test_jittered_paths(omap, fixture_spec, golden, golden_meta):
+    f = fixture_spec
+    N = 62
+    Z = full_paths(f, golden['jit_x'])
+    np.testing.assert_allclose(orc.get_cost(omap, Z, N, f['weights'], 0.0, f['options']), golden['jit_cost'], rtol=RTOL)
+    g = orc.get_nonlincon(omap, Z, N, f['maxratio'], f['maxalpha'], f['options'])
+    np.testing.assert_allclose(g, golden['jit_g'], rtol=1e-9, atol=1e-13)
+    assert np.array_equal(g == 0, golden['jit_g'] == 0)
+    col = omap.collides(Z.reshape(-1, 2)).reshape(-1, N + 2)
+    assert np.array_equal(col, golden['jit_collide'])
+    zs = full_paths(f, golden['survey_jitter_x'])
+    c = orc.get_cost(omap, zs, N, f['weights'], 0.0, f['options'])
+    assert c[0] == pytest.approx(golden_meta['survey_jitter_cost'], rel=RTOL)
+    gs = orc.get_nonlincon(omap, zs, N, f['maxratio'], f['maxalpha'], f['options'])[0]
+    np.testing.assert_allclose(gs, golden['survey_jitter_g'], rtol=1e-9, atol=1e-13)
+    assert gs[2] == pytest.approx(0.037299322077608, rel=1e-9)
+
+
+def test_variants(omap, fixture_spec, golden, golden_meta):
+    f = fixture_spec
+    N = 80
+    z = full_paths(f, orc.create_x_init(f['x_start'], f['x_goal'], N, 0.0))
+    v = golden_meta['variants_straight_N80']
+    o = f['options']
+    assert orc.get_cost(omap, z, N, f['weights'], 1.0, o)[0] == pytest.approx(v['enlargement1'], rel=RTOL)
+    assert orc.get_cost(omap, z, N, f['weights'], -0.25, o)[0] == pytest.approx(v['enlargement_neg'], rel=RTOL)
+    assert orc.get_cost(omap, z, N, f['weights'], 0.0, dict(o, length_smooth=False))[0] == pytest.approx(v['length_nonsmooth'], rel=RTOL)
+    assert orc.get_cost(omap, z, N, [100, 7500, 13500], 0.0, o)[0] == pytest.approx(v['weights_alt'], rel=RTOL)
+    assert math.isnan(v['penalty_nonsmooth'])                        # quirk Q4
+    assert math.isnan(orc.get_cost(omap, z, N, f['weights'], 0.0, dict(o, penalty_smooth=False))[0])
+    za = full_paths(f, golden['var_x'])
+    g1 = orc.get_nonlincon(omap, za, N, f['maxratio'], f['maxalpha'], dict(o, obstacle_smooth=False))[0]
+    np.testing.assert_allclose(g1, golden['var_g_obstacle_nonsmooth'], rtol=1e-9, atol=1e-13)
+    g2 = orc.get_nonlincon(omap, za, N, f['maxratio'], f['maxalpha'], dict(o, maxratio_smooth=True))[0]
+    np.testing.assert_allclose(g2, golden['var_g_maxratio_smooth'], rtol=1e-9, atol=1e-13)
+
+
+def test_point_queries(omap, fixture_spec, golden):
+    f = fixture_spec
+    Q = golden['pt_x']
+    np.testing.assert_allclose(orc.total_penalty(omap, Q, f['weights'], 0.0, True), golden['pt_total_penalty'], rtol=RTOL, atol=0)
+    for l, ((name, shapes), w) in enumerate(zip(omap.regions, f['weights'])):
+        np.testing.assert_allclose(orc.region_penalty(shapes, Q, w, True, 0.0), golden['pt_region_penalty'][:, l], rtol=RTOL)
+    np.testing.assert_allclose(orc.obstacle_penalty(omap, Q, 0.0, True), golden['pt_obstacle_penalty'], rtol=RTOL)
+    assert np.array_equal(omap.collides(Q), golden['pt_collides'])
+    assert np.array_equal(golden['pt_collides'], golden['pt_getitem'])
+    # SURVEY B.2 spot values
+    assert golden['pt_total_penalty'][0] == pytest.approx(29616.583973980643, rel=1e-14)
+    assert golden['pt_obstacle_penalty'][6] == pytest.approx(0.9555804225026664, rel=1e-14)
+
+
+def test_inequalities_bit_exact(omap, golden):
+    """h_i(x) of every shape at 64 points: identical bits -> same edge order, sign and op order."""
+    shapes = list(omap.obstacles) + [s for _, ss in omap.regions for s in ss]
+    off = golden['h_offsets']
+    P = golden['h_points']
+    for k, s in enumerate(shapes):
+        H = s.h(P)
+        assert H.shape[0] == off[k + 1] - off[k]
+        assert np.array_equal(H, golden['h_values'][off[k]:off[k + 1]]), k
+        np.testing.assert_array_equal(s.center, golden['shape_centers'][k])
+        assert s.area == pytest.approx(golden['shape_areas'][k], rel=1e-14)
+        assert s.psi(s.center.reshape(1, 2))[0] == pytest.approx(golden['shape_psi_center'][k], rel=RTOL)
+    sp = orc.make_polygon(golden['shuffled_poly_verts'])
+    assert np.array_equal(sp.h(P), golden['shuffled_poly_h'])
+    np.testing.assert_array_equal(sp.center, golden['shuffled_poly_center'])
+
+
+def test_constructors(golden_meta):
+    c = golden_meta['constructors']
+    sq = orc.make_square([1, 1], 0.5)
+    bl = orc.make_ball([1, 1], 2, 1)
+    assert bool(sq.contains([1.2, 0.9])[0]) == c['square_contains_1.2_0.9']
+    assert bool(sq.contains([1.6, 1.0])[0]) == c['square_contains_1.6_1']
+    assert sq.psi([1.2, 0.9])[0] == pytest.approx(c['square_psi_1.2_0.9'], rel=1e-15)
+    assert bool(bl.contains([2.9, 1.0])[0]) == c['ball_contains_2.9_1']
+    assert bool(bl.contains([1.0, 2.1])[0]) == c['ball_contains_1_2.1']
+    us = orc.make_polygon([[0., 0.], [1., 0.], [1., 1.], [0., 1.]])
+    assert bool(us.contains([1 + 1e-15, .5])[0]) == c['unit_square_edge_1e-15'] is True
+    assert bool(us.contains([1 + 1e-13, .5])[0]) == c['unit_square_edge_1e-13'] is False
+    for name, pts in {'two_vertices': [[0., 0.], [1., 1.]], 'aligned': [[0., 0.], [1., 0.], [2., 0.], [1., 1.]],
+                      'nonconvex': [[0., 0.], [2., 0.], [0.5, 0.5], [0., 2.]]}.items():
+        with pytest.raises(ValueError) as ei:
+            orc.make_polygon(pts)
+        assert str(ei.value) == c['errors'][name][1]
+    with pytest.raises(ValueError) as ei:
+        orc.create_x_init([0, 0], [1, 1], 10, 1.5)
+    assert str(ei.value) == c['errors']['x_init_1.5'][1]
+
+
+def test_testscript_config1():
+    """tests/test_path_generation.py inline problem at its own initial guess."""
+    z0, zN = np.array([35.590685, -27.711422]), np.array([26.478673, 9.564082])
+    c = np.array([31.034679, -9.07367])
+    z = np.linspace(z0, zN, 6)[1:-1]
+    dist, pen, tot = orc.testscript_cost(z, z0, zN, c)
+    assert dist == pytest.approx(294.498392228432, rel=1e-13)
+    assert pen == 0 and tot == pytest.approx(294.498392228432, rel=1e-13)
+    assert np.all(orc.testscript_constraints(z, z0, zN) < 1e-12) and len(orc.testscript_constraints(z, z0, zN)) == 9
+    z2 = z.copy()
+    z2[2] = c + 0.5
+    assert orc.testscript_cost(z2, z0, zN, c)[1] == pytest.approx(2.25, rel=1e-12)
+
+
+def test_raster_reduces_to_analytic(omap, fixture_spec, golden):
+    """Raster waypoint mode ~ analytic reference cost (discretisation only): the tie of the
+    build-defined raster formulation back to the reference (7e-5 @ 62.5 m cells)."""
+    f = fixture_spec
+    H = W = 512
+    x0, y0, dx = 8.0, -42.0, 64.0 / W
+    layers = orc.rasterize_layers(omap, H, W, x0, dx, y0, dx, 0.0)
+    occ = orc.rasterize_occupancy(omap, H, W, x0, dx, y0, dx)
+    N = 62
+    Z = full_paths(f, golden['jit_x'])
+    cost, col, ns = orc.score_paths_raster(layers, occ, (x0, dx, y0, dx), Z, f['weights'], 0.0, True, f['x_start'])
+    ref = golden['jit_cost']
+    assert np.max(np.abs(cost - ref) / ref) < 1e-2          # 125 m cells (observed 3.5e-3)
+    assert np.all(ns == N + 2)
+    # cell-step integral mode is a refinement of the same functional: stays close, uses more samples
+    cost2, col2, ns2 = orc.score_paths_raster(layers, occ, (x0, dx, y0, dx), Z[:4], f['weights'], 1.0, True, f['x_start'])
+    assert np.all(ns2 > ns[:4])
+    assert np.max(np.abs(cost2 - ref[:4]) / ref[:4]) < 0.2
+    assert np.all(col2 >= col[:4])
