@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- candidate-path segment evaluations / s (cost + collision) on an 8192^2 multi-layer raster.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], SURVEY.md 8d "C3"): synthetic 8192^2 raster with L = 3 float32 cost layers
+(fractal terrain with the real DEM's statistics, building heights, noise field) + uint8 occupancy, and candidate
+paths of 64 waypoints (N = 62) from the "scatter" distribution (start/goal uniform in the raster, straight line +
+N(0, 2 cells) jitter).  One step = one pass of the raster path scorer over this rank's batch of paths in integral
+mode (samples_per_cell = 1: every segment is sampled once per cell it crosses) followed by the best-path
+reduction (device argmin key, min-all-reduce over NCCL when N > 1).  Paths shard over the ranks, the map is
+replicated; per-GPU work is fixed (weak scaling).  `value` counts segment evaluations (63 per path).
+
+Timing: device-resident inputs, CUDA events on the launching stream, barrier + synchronize on both sides, max over
+ranks.  The raster (1 GiB of texels) and the path batch (1 KiB per path) are both larger than L2, so no explicit L2
+flush is needed between steps.  `e2e` times the same step through the host-buffer entry point of the C-ABI
+(uam_score_paths_raster_host: pinned numpy in, numpy out, H2D/D2H inside).  `cpu_baseline` / `--impl reference`
+time the float64 numpy oracle (oracle/uam_oracle.py -- the CPU restatement of the reference's arithmetic; the
+reference itself has no raster path and cannot be installed: it needs casadi/opengen/cargo) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RASTER = 8192
+WP = 64                 # waypoints per path (N = 62 free + start + goal)
+KM = 64.0               # raster spans 64 km
+WEIGHTS = [200.0, 15000.0, 27000.0]       # path_generation/main.py:145
+SPC = 1.0               # samples per cell (integral mode)
+METRIC = 'candidate-path segment evaluations/s (cost+collision), 8192^2 3-layer raster, integral mode'
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ---------------------------------------------------------------------------------------------------------------
+def make_raster(torch, device, n=RASTER, seed=20260102):
+    """(layers (3,n,n) f32, occupancy (n,n) u8, geo).  Same seed -> same map on every rank (map replicated)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    # terrain: 1/f^2 fractal, rescaled to the DEM statistics of merge_test.tif.aux.xml (min -12, max 557.5), 47 % sea
+    f = torch.fft.fftfreq(n, device=device)
+    k2 = f[:, None] ** 2 + f[None, :] ** 2
+    k2[0, 0] = 1.0
+    spec = torch.randn((n, n), device=device, generator=g, dtype=torch.float32) + 1j * torch.randn(
+        (n, n), device=device, generator=g, dtype=torch.float32)
+    t = torch.fft.ifft2(spec / k2).real
+    del spec, k2
+    q = torch.quantile(t.flatten()[:: max(1, t.numel() // (1 << 22))], 0.47)
+    t = t - q
+    land = t > 0
+    terrain = torch.where(land, -12.0 + t / t.max() * 569.5, torch.zeros_like(t)).clamp_(min=0.0)
+    # building height: random axis-aligned footprints x U(5,150) m
+    bld = torch.zeros((n, n), device=device)
+    R = torch.rand((4096, 5), generator=g, device=device).cpu().numpy()
+    for r in R:
+        i0, j0 = int(r[0] * (n - 64)), int(r[1] * (n - 64))
+        bld[i0:i0 + 8 + int(r[2] * 56), j0:j0 + 8 + int(r[3] * 56)] = 5.0 + 145.0 * float(r[4])
+    bld = bld * land
+    # noise: 64 Gaussian sources (separable -> one rank-64 product)
+    S = torch.rand((64, 4), generator=g, device=device)
+    ax = torch.arange(n, device=device, dtype=torch.float32)[None, :]
+    sig = (50.0 + 400.0 * S[:, 2:3]) * (n / 8192.0)
+    gx = torch.exp(-(ax - S[:, 0:1] * n) ** 2 / (2 * sig ** 2))
+    gy = torch.exp(-(ax - S[:, 1:2] * n) ** 2 / (2 * sig ** 2)) * (40.0 + 40.0 * S[:, 3:4])
+    noise = gy.t() @ gx
+    # normalise each layer to O(1) so the three weighted terms are comparable
+    layers = torch.stack([terrain / 557.5, bld / 150.0, noise / noise.max()]).contiguous()
+    occ = ((terrain + bld) > 300.0).to(torch.uint8)          # altitude band at 300 m
+    dx = KM / n
+    return layers, occ, (0.0, dx, 0.0, dx)
+
+
+def make_paths(torch, device, B, seed, n=RASTER):
+    """Scatter distribution: start/goal uniform in the raster, straight line + N(0, 2 cells) jitter."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    cell = KM / n
+    s = torch.rand((B, 1, 2), device=device, generator=g, dtype=torch.float64) * KM
+    e = torch.rand((B, 1, 2), device=device, generator=g, dtype=torch.float64) * KM
+    t = torch.linspace(0, 1, WP, device=device, dtype=torch.float64).reshape(1, WP, 1)
+    Z = s + t * (e - s)
+    Z = Z + torch.randn((B, WP, 2), device=device, generator=g, dtype=torch.float64) * (2.0 * cell)
+    return Z.reshape(B, 2 * WP).contiguous()
+
+
+def algorithmic_bytes(total_samples, B, L=3):
+    """per segment 16 B (one new float64 waypoint) + S * (L * 4 texels * 4 B + 1 B occupancy),
+    + per path 16 B (first point) + 5 B (float32 cost + uint8 flag).  total_samples includes the goal sample."""
+    return (WP - 1) * B * 16 + total_samples * (L * 16 + 1) + B * (16 + 5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the float64 numpy oracle on a bounded sample
+# ---------------------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_worker(args):
+    lo, hi = args
+    from oracle import uam_oracle as orc
+    t0 = time.perf_counter()
+    orc.score_paths_raster(_CPU['layers'], _CPU['occ'], _CPU['geo'], _CPU['Z'][lo:hi], WEIGHTS, SPC, True, None)
+    return time.perf_counter() - t0
+
+
+def cpu_oracle_rate(layers, occ, geo, Z, procs):
+    """segments/s of the oracle over the paths Z split across `procs` forked workers (wall clock)."""
+    import multiprocessing as mp
+    _CPU.update(layers=layers, occ=occ, geo=geo, Z=Z)
+    B = Z.shape[0]
+    if procs <= 1:
+        dt = _cpu_worker((0, B))
+    else:
+        cuts = np.linspace(0, B, procs + 1).astype(int)
+        ctx = mp.get_context('fork')
+        t0 = time.perf_counter()
+        with ctx.Pool(procs) as pool:
+            pool.map(_cpu_worker, [(int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a])
+        dt = time.perf_counter() - t0
+    return B * (WP - 1) / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores.  Rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    n = args.raster
+    torch.manual_seed(0)
+    layers, occ, geo = make_raster(torch, 'cpu', n)
+    layers, occ = layers.numpy(), occ.numpy()
+    per_step = args.cpu_paths * cores
+    Z = make_paths(torch, 'cpu', per_step * (args.steps + args.warmup), 2, n).numpy()
+    times = []
+    for s in range(args.warmup + args.steps):
+        rate, dt = cpu_oracle_rate(layers, occ, geo, Z[s * per_step:(s + 1) * per_step], cores)
+        if s >= args.warmup:
+            times.append(dt)
+    T = float(np.sum(times))
+    value = per_step * (WP - 1) * args.steps / T
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'segment-evals/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * T / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args, per_step),
+            'cpu_baseline': {'value': value, 'unit': 'segment-evals/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{per_step} paths/step ({args.cpu_paths} per worker x {cores} forked workers), '
+                                       'float64 numpy oracle (oracle/uam_oracle.py), integral mode'},
+            'e2e': {'value': value, 'unit': 'segment-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, paths_per_step):
+    return {'workload': f'C3: {args.raster}^2 raster, L=3 float32 layers + uint8 occupancy, scatter paths x {WP} waypoints, '
+                        f'integral mode samples_per_cell={SPC}',
+            'raster': args.raster, 'layers': 3, 'waypoints': WP, 'paths_per_gpu_per_step': paths_per_step,
+            'samples_per_cell': SPC, 'sharding': 'paths sharded contiguously over ranks, map replicated',
+            'l2': 'inputs larger than L2 (texels 1 GiB, paths 1 KiB each); no explicit flush'}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import uam_path_planning_b200 as uam
+    from uam_path_planning_b200 import distributed as udist
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = f'cuda:{local}'
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+
+    n, B = args.raster, args.paths
+    layers, occ, geo = make_raster(torch, dev, n)
+    rm = uam.RasterMap.from_arrays(layers, geo, occ, device=local)
+    eng = rm.engine
+    Z = make_paths(torch, dev, B, 2000 + rank, n)
+    cost = torch.empty(B, dtype=torch.float32, device=dev)
+    col = torch.empty(B, dtype=torch.uint8, device=dev)
+    offset = rank * B
+
+    def step():
+        rm.score_paths(Z, WEIGHTS, SPC, True, None, out=(cost, col))
+        key = eng.best(cost, offset)
+        if world > 1:
+            dist.all_reduce(key, op=dist.ReduceOp.MIN)
+        return key
+
+    # sample counts -> algorithmic bytes (one extra untimed call)
+    _, _, ns = rm.score_paths(Z, WEIGHTS, SPC, True, None, want_nsamples=True)
+    total_samples = int(ns.sum().item())
+    del ns
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_start.record()
+    for s in range(args.steps):
+        k_ev[s][0].record()
+        rm.score_paths(Z, WEIGHTS, SPC, True, None, out=(cost, col))
+        k_ev[s][1].record()
+        key = eng.best(cost, offset)
+        if world > 1:
+            dist.all_reduce(key, op=dist.ReduceOp.MIN)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = eng.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = t_start.elapsed_time(t_end)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    best_cost, best_idx = udist.decode_key(int(key.item()))
+
+    # ---- e2e: host buffers through the C-ABI host entry point ------------------------------------------------
+    Zh = torch.empty((B, 2 * WP), dtype=torch.float64).pin_memory()
+    Zh.copy_(Z)
+    Zh_np = Zh.numpy()
+    cost_h = torch.empty(B, dtype=torch.float32).pin_memory().numpy()
+    col_h = torch.empty(B, dtype=torch.uint8).pin_memory().numpy()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        rm.score_paths(Zh_np, WEIGHTS, SPC, True, None, out=(cost_h, col_h))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rm.score_paths(Zh_np, WEIGHTS, SPC, True, None, out=(cost_h, col_h))
+        kh = udist.host_best_key(cost_h, offset)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    assert np.array_equal(cost_h, cost.cpu().numpy()), 'host entry point disagrees with the device entry point'
+
+    # ---- max over ranks -----------------------------------------------------------------------------------------
+    stats = torch.tensor([ms_total, k_ms, e2e_ms, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms_total, k_ms_max, e2e_ms_max, _ = [float(v) for v in stats.tolist()]
+
+    if rank == 0:
+        segs = B * (WP - 1)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        abytes = algorithmic_bytes(total_samples, B)
+        achieved = abytes / (k_ms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': segs * world * args.steps / (ms_total * 1e-3), 'unit': 'segment-evals/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (fp64 coordinates)',
+            'data': 'synthetic', 'config': workload_config(args, B),
+            'samples_per_step_per_gpu': total_samples,
+            'samples_per_s': total_samples * world * args.steps / (ms_total * 1e-3),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'kernel': 'uam_k_score_raster_int<4>', 'kernel_ms': k_ms,
+                         'algorithmic_bytes_per_launch': abytes,
+                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'},
+            'e2e': {'value': segs * world / (e2e_ms_max * 1e-3), 'unit': 'segment-evals/s',
+                    'h2d_bytes_per_step': B * 2 * WP * 8, 'd2h_bytes_per_step': B * 5, 'ms_per_step': e2e_ms_max,
+                    'api': 'RasterMap.score_paths(numpy) -> uam_score_paths_raster_host', 'steps': e2e_steps},
+            'gpu_launches': launches, 'clocks': clk,
+            'best': {'cost': best_cost, 'index': best_idx},
+        }
+        if world == 1 and not args.no_cpu:
+            cores = 1
+            nb = args.cpu_paths
+            Lh, Oh = layers.cpu().numpy(), occ.cpu().numpy()
+            Zs = Z[:nb].cpu().numpy()
+            rate, dt = cpu_oracle_rate(Lh, Oh, geo, Zs, cores)
+            c_ref, col_ref, _ = __import__('oracle.uam_oracle', fromlist=['x']).score_paths_raster(
+                Lh, Oh, geo, Zs[:64], WEIGHTS, SPC, True, None)
+            err = float(np.max(np.abs(cost[:64].cpu().numpy() - c_ref) / np.abs(c_ref)))
+            line['cpu_baseline'] = {'value': rate, 'unit': 'segment-evals/s', 'cores': cores, 'kind': 'port',
+                                    'sample': f'first {nb} paths of the same batch, float64 numpy oracle, integral mode, {dt:.1f} s',
+                                    'max_rel_err_gpu_vs_oracle_64_paths': err,
+                                    'collide_equal': bool(np.array_equal(col[:64].cpu().numpy().astype(bool), col_ref))}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--raster', type=int, default=RASTER)
+    ap.add_argument('--paths', type=int, default=125000, help='candidate paths per GPU per step (C3: 1M over 8 GPUs)')
+    ap.add_argument('--cpu-paths', type=int, default=192, help='paths per CPU worker per step for the CPU arm')
+    ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

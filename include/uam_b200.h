@@ -1,0 +1,193 @@
+/*
+ * uam_b200.h -- C-ABI of the B200-native path scorer for nomaporon/uam_path_planning.
+ *
+ * The reference has no FFI of its own (it is pure Python); this header is the boundary a
+ * maintainer binds with ctypes from the reference's Python classes.  Each
+ * entry point names the reference interface it replaces; file:line are relative to
+ * geo_simulation_project/ in the reference tree.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, doubles.  No C++ / torch types.
+ *   - every call returns int: 0 = UAM_OK, negative = error; never throws, never aborts.
+ *     uam_last_error(ctx) gives the message of the last failing call on that ctx.
+ *   - pointers named d_* are DEVICE pointers owned by the caller (e.g. torch tensor data_ptr());
+ *     pointers named h_* (and all small parameter tables) are HOST pointers.
+ *   - `stream` is the caller's cudaStream_t passed as void* (NULL = CUDA's default stream, as in
+ *     every CUDA API).  Device-pointer calls are asynchronous and stream-ordered; host-buffer
+ *     calls (*_host) run on the ctx's own streams and return when the results are in the
+ *     caller's host buffers.
+ *   - a ctx is bound to one GPU and is not thread-safe.  No global state.  There is no CPU
+ *     fallback: without a CUDA device uam_ctx_create fails with UAM_ERR_CUDA.
+ *
+ * Layouts (kept from the reference)
+ *   paths   z_  : (B, 2*(N+2)) float64, C-contiguous, interleaved [xs,ys,x1,y1,...,xN,yN,xg,yg]
+ *                 = start + N free waypoints + goal      (path_generation/solver.py:59-66)
+ *   params  p   : [ms_x, ms_y, mg_x, mg_y, maxratio, maxalpha, enlargement, w_0 .. w_{R-1}]
+ *                 (solver.py:60-68; p[0:4] = map.x_start / map.x_goal as used by
+ *                 Problem.length_of, problem.py:137-140; weights in region insertion order)
+ *   rasters     : (L, H, W) float32 C-order, row <-> y, col <-> x, affine (x0, dx, y0, dy),
+ *                 cell centre (x0 + (j+1/2) dx, y0 + (i+1/2) dy); occupancy (H, W) uint8
+ *                 (rasterio band layout as read at map_generation/data_manager.py:13)
+ */
+#ifndef UAM_B200_H
+#define UAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct uam_ctx uam_ctx;
+
+enum {
+    UAM_OK = 0,
+    UAM_ERR_INVALID = -1,      /* bad argument */
+    UAM_ERR_CUDA = -2,         /* CUDA runtime error (message in uam_last_error) */
+    UAM_ERR_NOMEM = -3,
+    UAM_ERR_STATE = -4,        /* required map state missing (no shapes / no raster uploaded) */
+    UAM_ERR_UNSUPPORTED = -5
+};
+
+/* option flags = Problem.options (path_generation/problem.py:12-17) */
+enum {
+    UAM_LENGTH_SMOOTH   = 1 << 0,
+    UAM_PENALTY_SMOOTH  = 1 << 1,
+    UAM_OBSTACLE_SMOOTH = 1 << 2,
+    UAM_MAXRATIO_SMOOTH = 1 << 3,
+    /* the length term's first pair is (map.x_start, z_0) (problem.py:137-145).  With this flag the
+     * scorer uses each path's own z_0 instead of p[0:2], i.e. the term is 0 -- for batches of
+     * independent start/goal queries. */
+    UAM_OWN_START       = 1 << 4
+};
+
+/* inequality record kinds of uam_map_set_shapes: 8 doubles per record, rec[0] = kind */
+enum {
+    UAM_EDGE_LINE = 0,     /* rec = {0, Ax, Ay, Bx-Ax, By-Ay, sgn, 0, 0}   h = -sgn*((By-Ay)(x-Ax) - (Bx-Ax)(y-Ay))
+                              path_generation/polygon.py:69-71,98 */
+    UAM_EDGE_ELLIPSE = 1,  /* rec = {1, cx, cy, r1, r2, 0, 0, 0}           h = ((x-cx)/r1)^2 + ((y-cy)/r2)^2 - 1
+                              path_generation/ball.py:33-37 */
+    UAM_EDGE_BOX = 2       /* rec = {2, axis, sign, c, r, 0, 0, 0}         h = sign>0 ? x_d - c - r : -x_d + c - r
+                              path_generation/square.py:29-51 */
+};
+
+/* ---- context ------------------------------------------------------------------------------- */
+int uam_ctx_create(int device, uam_ctx** ctx);
+int uam_ctx_destroy(uam_ctx* ctx);
+const char* uam_last_error(const uam_ctx* ctx);
+const char* uam_version(void);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int uam_launch_count(const uam_ctx* ctx, uint64_t* n);
+/* wait for the ctx's own streams */
+int uam_sync(uam_ctx* ctx);
+
+/* ---- map: shape tables ------------------------------------------------------------------------
+ * Replaces the object graph RegionMap / Map / QuadraticObstacle / Function
+ * (path_generation/region_map.py:8-61, map.py:7-43, quadratic_obstacle.py:8-39, function.py:119).
+ *   h_edges        n_edges x 8 doubles, inequality records in reference order
+ *   h_shape_off    n_shapes+1 prefix into h_edges
+ *   h_shape_region n_shapes: -1 = hard obstacle (map.obstacles), else region index (insertion order)
+ *   h_shape_center n_shapes x 2: QuadraticObstacle.center; NaN = none (penalty not normalised,
+ *                  problem.py:76-77)
+ * Obstacles keep insertion order among themselves (it is the order of get_nonlincon's blocks). */
+int uam_map_set_shapes(uam_ctx* ctx, const double* h_edges, int n_edges, const int32_t* h_shape_off,
+                       const int32_t* h_shape_region, const double* h_shape_center, int n_shapes,
+                       int n_regions);
+
+/* ---- map: rasters -------------------------------------------------------------------------------
+ * Upload L float32 cost layers + uint8 occupancy; the library re-lays them out on the device
+ * (texel-interleaved).  L in [1,3].  Host and device-pointer forms. */
+int uam_map_set_raster(uam_ctx* ctx, const float* h_layers, int L, int H, int W, double x0, double dx,
+                       double y0, double dy, const uint8_t* h_occupancy);
+int uam_map_set_raster_device(uam_ctx* ctx, const float* d_layers, int L, int H, int W, double x0,
+                              double dx, double y0, double dy, const uint8_t* d_occupancy, void* stream);
+
+/* ---- path scoring: analytic shapes -------------------------------------------------------------
+ * Replaces, batched over B paths:
+ *   d_cost[b]    = Problem.get_cost(z_)                      path_generation/problem.py:38-44
+ *                  (length term incl. the dropped-last-segment behaviour of problem.py:39,140-145)
+ *   d_collide[b] = any_j Map.collides(z_j)                   map.py:41-43, quadratic_obstacle.py:89-94
+ *   d_g[b,:]     = Problem.get_nonlincon(z_)  (nullable)     problem.py:84-114, length 3N + n_obs(N+2)
+ * All fp64 in the reference's operation order (no FMA contraction): inequalities, collision flags
+ * and the zero pattern of g are bit-exact; costs differ from the reference only through the order
+ * in which the per-waypoint terms are summed (warp-shuffle tree), ~1e-15 relative.
+ * uam_analytic_g_len gives the row length of d_g for this map and N. */
+int uam_score_paths_analytic(uam_ctx* ctx, const double* d_z, int64_t B, int N, const double* h_p,
+                             int n_p, int flags, double* d_cost, uint8_t* d_collide, double* d_g,
+                             void* stream);
+int uam_score_paths_analytic_host(uam_ctx* ctx, const double* h_z, int64_t B, int N, const double* h_p,
+                                  int n_p, int flags, double* h_cost, uint8_t* h_collide, double* h_g);
+int uam_analytic_g_len(const uam_ctx* ctx, int N, int64_t* len);
+
+/* Problem.length_of(x, smooth) (problem.py:130-146) for B rows of M points each (x is (B, 2M) float64):
+ * y = [map.x_start; x; map.x_goal], out = sum of nrm(y_{k+1} - y_k) over the FIRST N+1 pairs (N <= M).
+ * M = N reproduces Solver.solve's call (solver.py:49), M = N+2 the call inside get_cost (problem.py:39).
+ * h_ends = [x_start(2), x_goal(2)]. */
+int uam_length_of(uam_ctx* ctx, const double* d_x, int64_t B, int M, int N, const double* h_ends, int smooth,
+                  double* d_out, void* stream);
+int uam_length_of_host(uam_ctx* ctx, const double* h_x, int64_t B, int M, int N, const double* h_ends,
+                       int smooth, double* h_out);
+
+/* ---- path scoring: rasters ----------------------------------------------------------------------
+ * Same cost functional with P(x) = sum_l w_l * bilinear(layer_l, x) and collision = occupancy of
+ * the nearest cell.  samples_per_cell == 0: one sample per waypoint (the reference's sampling,
+ * problem.py:42-43).  > 0: every segment is sampled S_k = max(1, ceil(|dz_k|_cells * samples_per_cell))
+ * times (left-endpoint rule, mean per segment; S_k capped at 2^20) -- build-defined line-integral
+ * extension.  p[7:] are the L layer weights.  World->pixel coordinates, S_k and sample positions are
+ * fp64 (same cells and sample counts as the oracle, bit for bit); texel arithmetic and the penalty
+ * sum are fp32; the length term is fp64; d_cost is float32.  d_nsamples (nullable, int64 per path)
+ * receives the number of raster samples taken for the path. */
+int uam_score_paths_raster(uam_ctx* ctx, const double* d_z, int64_t B, int N, const double* h_p, int n_p,
+                           int flags, double samples_per_cell, float* d_cost, uint8_t* d_collide,
+                           int64_t* d_nsamples, void* stream);
+int uam_score_paths_raster_host(uam_ctx* ctx, const double* h_z, int64_t B, int N, const double* h_p,
+                                int n_p, int flags, double samples_per_cell, float* h_cost,
+                                uint8_t* h_collide);
+
+/* ---- point queries --------------------------------------------------------------------------------
+ * Replaces Problem.get_penalty_function(region)(x) (problem.py:59-82), get_total_penalty_function
+ * (:49-56) and Map.collides(x) (map.py:41-43) for M points x (M,2) float64.  Outputs nullable:
+ *   d_region_pen (M, R) float64 weighted per-region penalties; d_obst_pen (M) float64 =
+ *   get_penalty_function(None)(x); d_collide (M) uint8.  All fp64 (this is the exact path). */
+int uam_eval_points(uam_ctx* ctx, const double* d_x, int64_t M, const double* h_p, int n_p, int flags,
+                    double* d_region_pen, double* d_obst_pen, uint8_t* d_collide, void* stream);
+int uam_eval_points_host(uam_ctx* ctx, const double* h_x, int64_t M, const double* h_p, int n_p, int flags,
+                         double* h_region_pen, double* h_obst_pen, uint8_t* h_collide);
+
+/* Function.__call__ (function.py:119-120): h_i(x_m) of n_rec raw inequality records (8 doubles each, the
+ * record kinds above) at M points, h_out[i*M + m]; fp64, bit-exact with the reference's closures
+ * (polygon.py:69-71,98; ball.py:33-37; square.py:29-51). */
+int uam_eval_inequalities_host(uam_ctx* ctx, const double* h_records, int n_rec, const double* h_x, int64_t M,
+                               double* h_out);
+
+/* ---- best candidate --------------------------------------------------------------------------------
+ * Replaces the running min of path_generation/main.py:162-180.  *d_key = min over b of
+ * (float32 bits of cost[b] << 32) | (global_offset + b); costs are >= 0 so the bit pattern orders
+ * like the value, ties resolve to the smaller index (the `<` of main.py:175).  The caller min-reduces
+ * the 8-byte key across ranks (NCCL).  d_key must be pre-set (e.g. to UINT64_MAX) by the caller or
+ * by passing reset != 0.  d_cost is float32 (raster scorer) or float64 (analytic scorer, rounded to
+ * float32 for the key) according to cost_is_f64. */
+int uam_best(uam_ctx* ctx, const void* d_cost, int cost_is_f64, int64_t B, int64_t global_offset,
+             uint64_t* d_key, int reset, void* stream);
+
+/* ---- map rebuild (map_generation) --------------------------------------------------------------------
+ * uam_dem_mask: mask = image > threshold, or image == -9999 when threshold == -9999
+ *               (map_generation/data_manager.py:14-17).
+ * uam_rasterize_occupancy: occ[i,j] = Map.collides(cell centre)  (map.py:41-43), fp64, bit-exact.
+ * uam_rasterize_layers: layer[l,i,j] = float32(sum_{s in region l} psi_s(xc;e)/psi_s(c_s;e)), unweighted
+ *               (problem.py:72-80 without w; quadratic_obstacle.py:33-35).
+ * uam_edt: exact squared Euclidean distance (cells) to the nearest occupied cell and clearance =
+ *               sqrt(d2)*cell (build-defined extension; no reference counterpart). */
+int uam_dem_mask(uam_ctx* ctx, const float* d_image, int64_t n, float threshold, uint8_t* d_mask,
+                 void* stream);
+int uam_rasterize_occupancy(uam_ctx* ctx, int H, int W, double x0, double dx, double y0, double dy,
+                            uint8_t* d_occ, void* stream);
+int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, double dx, double y0, double dy,
+                         double enlargement, float* d_layers, void* stream);
+int uam_edt(uam_ctx* ctx, const uint8_t* d_occ, int H, int W, double cell, int32_t* d_dist2,
+            float* d_clearance, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAM_B200_H */

@@ -43,3 +43,37 @@ def full_paths(spec, X):
     s = np.broadcast_to(np.asarray(spec['x_start'], dtype=np.float64), (X.shape[0], 2))
     g = np.broadcast_to(np.asarray(spec['x_goal'], dtype=np.float64), (X.shape[0], 2))
     return np.concatenate([s, X, g], axis=1)
+
+
+def build_product_map(spec):
+    """fixture spec -> the product's RegionMap + Problem (through the reference-named constructors)."""
+    import uam_path_planning_b200 as uam
+    mk = {'polygon': lambda s: uam.polygon(*s['verts']),
+          'ball': lambda s: uam.ball(s['center'], s.get('r1'), s.get('r2')),
+          'square': lambda s: uam.square(s['center'], s['r1'], s.get('r2'))}
+    m = uam.RegionMap()
+    m.add_obstacles(*[mk[s['kind']](s) for s in spec['obstacles']])
+    for name, shapes in spec['regions']:
+        m.new_region(name, 'red')
+        m.add_shapes_to_region(name, *[mk[s['kind']](s) for s in shapes])
+    m.x_start, m.x_goal = spec['x_start'], spec['x_goal']
+    return m
+
+
+def build_product_problem(spec, N, options=None, weights=None, enlargement=None):
+    import uam_path_planning_b200 as uam
+    m = build_product_map(spec)
+    prob = uam.Problem(m, N, dict(spec['options'], **(options or {})))
+    prob.params.update(maxratio=spec['maxratio'], maxalpha=spec['maxalpha'],
+                       enlargement=spec['enlargement'] if enlargement is None else enlargement)
+    for (name, _), w in zip(spec['regions'], weights or spec['weights']):
+        prob.set_weight(name, w)
+    return prob
+
+
+def have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False

@@ -1,0 +1,405 @@
+"""Parity of the CUDA path (through the C-ABI, via the reference-named Python entry points) against the
+golden vectors produced by the reference's own code and against the float64 oracle.
+
+Bars: bit-exact for inequalities h_i(x), collision flags, occupancy cells, sample counts, EDT distances and the
+zero pattern of g; analytic costs (fp64 on the device) within 1e-12 relative of the reference; raster costs
+(fp32 texel arithmetic and penalty sum) within 1e-5 relative of the float64 oracle.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import build_product_map, build_product_problem, full_paths
+from oracle import uam_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL_ANALYTIC = 1e-12     # fp64 device path vs reference float64 (summation order only)
+RTOL_RASTER = 1e-5        # fp32 accumulation vs float64 oracle (BASELINE.json north_star tolerance)
+
+
+@pytest.fixture(scope='module')
+def uam():
+    import uam_path_planning_b200 as u
+    return u
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch as t
+    assert t.cuda.is_available()
+    return t
+
+
+@pytest.fixture(scope='module')
+def omap(fixture_spec):
+    return orc.OMap(fixture_spec)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# analytic path: golden vectors of the reference
+# ------------------------------------------------------------------------------------------------------------
+def test_inequalities_bit_exact_on_device(uam, fixture_spec, golden):
+    m = build_product_map(fixture_spec)
+    shapes = list(m.obstacles) + [s for r in m._region_lists() for s in r]
+    R = np.concatenate([s.records() for s in shapes])
+    H = uam.default_engine().eval_inequalities(R, golden['h_points'])
+    assert np.array_equal(H, golden['h_values'])
+    # Function.__call__ surface on one inequality, one point
+    assert shapes[0].inequalities[0](golden['h_points'][3]) == golden['h_values'][0, 3]
+
+
+@pytest.mark.parametrize('N', [80, 62, 64, 5])
+def test_arcs_cost_constraints_collisions(uam, fixture_spec, golden, N):
+    f = fixture_spec
+    prob = build_product_problem(f, N)
+    Z = full_paths(f, golden[f'arc_N{N}_x'])
+    cost, col, g = prob.score(Z, want_g=True)
+    np.testing.assert_allclose(cost, golden[f'arc_N{N}_cost'], rtol=RTOL_ANALYTIC)
+    G = golden[f'arc_N{N}_g']
+    assert g.shape == G.shape
+    np.testing.assert_allclose(g, G, rtol=1e-9, atol=1e-13)
+    assert np.array_equal(g[:, 3 * N:] == 0, G[:, 3 * N:] == 0)          # obstacle block: exact zero pattern
+    assert np.array_equal(col.astype(bool), golden[f'arc_N{N}_collide'].any(axis=1))
+    per_wp = prob.map.collides(Z.reshape(-1, 2)).reshape(Z.shape[0], N + 2)
+    assert np.array_equal(per_wp, golden[f'arc_N{N}_collide'])
+    X = np.ascontiguousarray(golden[f'arc_N{N}_x'])
+    np.testing.assert_allclose(prob.length_of(X, False), golden[f'arc_N{N}_length'], rtol=1e-13)
+    np.testing.assert_allclose(prob.length_of(X, True), golden[f'arc_N{N}_length_smooth'], rtol=1e-13)
+    # single-path call signatures return scalars / vectors like the reference
+    c0 = prob.get_cost(Z[2])
+    assert isinstance(c0, float) and c0 == pytest.approx(golden[f'arc_N{N}_cost'][2], rel=RTOL_ANALYTIC)
+    g0 = prob.get_nonlincon(Z[2])
+    assert g0.shape == (3 * N + 5 * (N + 2),)
+    assert prob.length_of(X[1]) == pytest.approx(golden[f'arc_N{N}_length'][1], rel=1e-13)
+
+
+def test_jittered_paths(uam, fixture_spec, golden, golden_meta):
+    f = fixture_spec
+    N = 62
+    prob = build_product_problem(f, N)
+    Z = full_paths(f, golden['jit_x'])
+    cost, col, g = prob.score(Z, want_g=True)
+    np.testing.assert_allclose(cost, golden['jit_cost'], rtol=RTOL_ANALYTIC)
+    np.testing.assert_allclose(g, golden['jit_g'], rtol=1e-9, atol=1e-13)
+    assert np.array_equal(g == 0, golden['jit_g'] == 0)
+    assert np.array_equal(col.astype(bool), golden['jit_collide'].any(axis=1))
+    zs = full_paths(f, golden['survey_jitter_x'])
+    assert prob.get_cost(zs)[0] == pytest.approx(golden_meta['survey_jitter_cost'], rel=RTOL_ANALYTIC)
+    np.testing.assert_allclose(prob.get_nonlincon(zs)[0], golden['survey_jitter_g'], rtol=1e-9, atol=1e-13)
+
+
+def test_variants(uam, fixture_spec, golden, golden_meta):
+    f = fixture_spec
+    N = 80
+    v = golden_meta['variants_straight_N80']
+    sol = uam.Solver(build_product_problem(f, N), {})
+    z = sol.full_path(sol.create_x_init(0.0))
+    assert build_product_problem(f, N, enlargement=1.0).get_cost(z)[0] == pytest.approx(v['enlargement1'], rel=RTOL_ANALYTIC)
+    assert build_product_problem(f, N, enlargement=-0.25).get_cost(z)[0] == pytest.approx(v['enlargement_neg'], rel=RTOL_ANALYTIC)
+    assert build_product_problem(f, N, options={'length_smooth': False}).get_cost(z)[0] == pytest.approx(v['length_nonsmooth'], rel=RTOL_ANALYTIC)
+    assert build_product_problem(f, N, weights=[100, 7500, 13500]).get_cost(z)[0] == pytest.approx(v['weights_alt'], rel=RTOL_ANALYTIC)
+    assert math.isnan(build_product_problem(f, N, options={'penalty_smooth': False}).get_cost(z)[0])   # quirk Q4
+    za = full_paths(f, golden['var_x'])
+    g1 = build_product_problem(f, N, options={'obstacle_smooth': False}).get_nonlincon(za)[0]
+    np.testing.assert_allclose(g1, golden['var_g_obstacle_nonsmooth'], rtol=1e-9, atol=1e-13)
+    g2 = build_product_problem(f, N, options={'maxratio_smooth': True}).get_nonlincon(za)[0]
+    np.testing.assert_allclose(g2, golden['var_g_maxratio_smooth'], rtol=1e-9, atol=1e-13)
+
+
+def test_point_queries(uam, fixture_spec, golden):
+    f = fixture_spec
+    prob = build_product_problem(f, 80)
+    Q = golden['pt_x']
+    np.testing.assert_allclose(prob.get_total_penalty_function()(Q), golden['pt_total_penalty'], rtol=1e-13, atol=0)
+    for l, (name, _) in enumerate(f['regions']):
+        np.testing.assert_allclose(prob.get_penalty_function(name)(Q), golden['pt_region_penalty'][:, l], rtol=1e-13)
+    np.testing.assert_allclose(prob.get_penalty_function(None)(Q), golden['pt_obstacle_penalty'], rtol=1e-13)
+    assert np.array_equal(prob.map.collides(Q), golden['pt_collides'])
+    assert prob.map[(float(Q[3, 0]), float(Q[3, 1]))] == bool(golden['pt_getitem'][3])
+    assert prob.get_total_penalty_function()(Q[0]) == pytest.approx(29616.583973980643, rel=1e-13)
+    assert prob.map.collides(np.array([38.66652661075855, -9.203164091309498])) is True
+
+
+def test_constructors_on_device(uam, golden_meta):
+    c = golden_meta['constructors']
+    sq, bl = uam.square([1, 1], 0.5), uam.ball([1, 1], 2, 1)
+    assert sq.contains([1.2, 0.9]) == c['square_contains_1.2_0.9'] and sq.contains([1.6, 1.0]) == c['square_contains_1.6_1']
+    assert sq.penalty_function(True, 0)([1.2, 0.9]) == pytest.approx(c['square_psi_1.2_0.9'], rel=1e-15)
+    assert bl.contains([2.9, 1.0]) == c['ball_contains_2.9_1'] and bl.contains([1.0, 2.1]) == c['ball_contains_1_2.1']
+    us = uam.polygon([0., 0.], [1., 0.], [1., 1.], [0., 1.])
+    assert us.contains([1 + 1e-15, .5]) is True and us.contains([1 + 1e-13, .5]) is False   # quirk Q6
+    assert uam.QuadraticObstacle().contains([5.0, 5.0]) is True      # no inequalities: all([]) is True
+
+
+def test_random_shapes_vs_oracle(uam):
+    """Random convex polygons / ellipses / boxes, random paths, all option combinations -- vs the oracle."""
+    rng = np.random.default_rng(11)
+    specs_obs, specs_reg = [], [('A', []), ('B', [])]
+
+    def rand_shape():
+        k = rng.integers(3)
+        c = rng.uniform(-20, 20, 2)
+        if k == 0:
+            ang = np.sort(rng.uniform(0, 2 * np.pi, rng.integers(3, 8)))
+            r = rng.uniform(2, 6)
+            V = np.stack([c[0] + r * np.cos(ang), c[1] + 0.7 * r * np.sin(ang)], 1)
+            return {'kind': 'polygon', 'verts': V[rng.permutation(len(V))].tolist()}
+        if k == 1:
+            return {'kind': 'ball', 'center': c.tolist(), 'r1': float(rng.uniform(1, 5)), 'r2': float(rng.uniform(1, 5))}
+        return {'kind': 'square', 'center': c.tolist(), 'r1': float(rng.uniform(1, 5)), 'r2': float(rng.uniform(1, 5))}
+
+    for _ in range(7):
+        specs_obs.append(rand_shape())
+    for _ in range(40):
+        specs_reg[rng.integers(2)][1].append(rand_shape())
+    spec = {'obstacles': specs_obs, 'regions': specs_reg, 'x_start': [-18.0, -17.0], 'x_goal': [19.0, 16.0],
+            'options': {}, 'maxratio': 1.3, 'maxalpha': 0.3, 'enlargement': 0.2, 'weights': [3.0, 70.0]}
+    om = orc.OMap(spec)
+    N = 37
+    base = orc.create_x_init(spec['x_start'], spec['x_goal'], N, 0.3)
+    Z = full_paths(spec, base + rng.normal(0, 1.5, (200, 2 * N)))
+    for opts in [{'length_smooth': ls, 'penalty_smooth': True, 'obstacle_smooth': os_, 'maxratio_smooth': ms}
+                 for ls in (False, True) for os_ in (False, True) for ms in (False, True)]:
+        prob = build_product_problem(spec, N, options=opts)
+        cost, col, g = prob.score(Z, want_g=True)
+        np.testing.assert_allclose(cost, orc.get_cost(om, Z, N, spec['weights'], 0.2, opts), rtol=RTOL_ANALYTIC)
+        G = orc.get_nonlincon(om, Z, N, 1.3, 0.3, opts)
+        np.testing.assert_allclose(g, G, rtol=1e-9, atol=1e-13)
+        assert np.array_equal(g[:, 3 * N:], G[:, 3 * N:])                 # obstacle block: same bits
+        assert np.array_equal(col.astype(bool), orc.path_collides(om, Z, N))
+    assert col.any() and not col.all()
+
+
+def test_device_tensor_path_equals_host_path(uam, torch, fixture_spec, golden):
+    f = fixture_spec
+    prob = build_product_problem(f, 62)
+    Z = full_paths(f, golden['jit_x'])
+    c1, k1, g1 = prob.score(Z, want_g=True)
+    Zt = torch.from_numpy(Z).cuda()
+    c2, k2, g2 = prob.score(Zt, want_g=True)
+    assert np.array_equal(c1, c2.cpu().numpy()) and np.array_equal(k1, k2.cpu().numpy())
+    assert np.array_equal(g1, g2.cpu().numpy())
+    key = prob.map.engine().best(c2, global_offset=1000)
+    from uam_path_planning_b200 import distributed as ud
+    assert int(key.item()) == ud.host_best_key(c1.astype(np.float32), 1000)
+    assert ud.global_best(key) == (float(np.float32(c1.min())), 1000 + int(np.argmin(c1.astype(np.float32))))
+    ev = uam.Solver(prob, {}).evaluate_candidates(Z)
+    assert ev['min_fval_index'] == int(np.argmin(golden['jit_cost']))
+    assert ev['min_fval'] == pytest.approx(math.sqrt(golden['jit_cost'].min()), rel=1e-12)
+
+
+def test_empty_and_error_cases(uam, fixture_spec):
+    prob = build_product_problem(fixture_spec, 10)
+    c, k, g = prob.score(np.zeros((0, 24)), want_g=True)
+    assert c.shape == (0,) and k.shape == (0,) and g.shape == (0, 3 * 10 + 5 * 12)
+    with pytest.raises(ValueError):
+        prob.score(np.zeros((3, 20)))
+    eng = uam.Engine()
+    with pytest.raises(uam.UamError) as ei:
+        eng.score_analytic(np.zeros((1, 24)), 10, np.zeros(7), 0)
+    assert ei.value.code == -4                     # UAM_ERR_STATE: no shape table
+    with pytest.raises(uam.UamError) as ei:
+        eng.score_raster(np.zeros((1, 24)), 10, np.zeros(8), 0)
+    assert ei.value.code == -4                     # no raster
+    eng.set_raster(np.zeros((2, 4, 4), dtype=np.float32), (0, 1, 0, 1))
+    with pytest.raises(uam.UamError) as ei:
+        eng.score_raster(np.zeros((1, 24)), 10, np.zeros(8), 0)      # 1 weight for 2 layers
+    assert ei.value.code == -1
+    with pytest.raises(uam.UamError):
+        eng.set_raster(np.zeros((4, 4, 4), dtype=np.float32), (0, 1, 0, 1))   # L = 4 unsupported
+    m = build_product_map(fixture_spec)
+    p_bad = np.zeros(7 + 2)
+    with pytest.raises(uam.UamError):
+        m.engine().score_analytic(np.zeros((1, 24)), 10, p_bad, 0)   # 2 weights for 3 regions
+
+
+# ------------------------------------------------------------------------------------------------------------
+# map rebuild: occupancy / layers / DEM mask / EDT
+# ------------------------------------------------------------------------------------------------------------
+GEOS = [(384, 320, (8.0, 64.0 / 320, -42.0, 64.0 / 384)),        # non-square cells
+        (130, 203, (8.0, 0.31, 22.0, -0.49))]                    # north-up raster (dy < 0), ragged tile edges
+
+
+@pytest.mark.parametrize('H,W,geo', GEOS)
+def test_rasterize_occupancy_and_layers(uam, omap, fixture_spec, H, W, geo):
+    rm = uam.RasterMap.from_map(build_product_map(fixture_spec), H, W, geo, clearance=True)
+    occ_ref = orc.rasterize_occupancy(omap, H, W, *geo)
+    assert occ_ref.any()
+    assert np.array_equal(rm.occupancy.cpu().numpy(), occ_ref)                 # bit-exact cells
+    lay_ref = orc.rasterize_layers(omap, H, W, *geo, 0.0)
+    lay = rm.layers.cpu().numpy()
+    assert lay.shape == lay_ref.shape == (3, H, W)
+    assert np.array_equal(lay == 0, lay_ref == 0)                             # same support
+    np.testing.assert_allclose(lay, lay_ref, rtol=2e-7, atol=0)               # float32 rounding of a float64 sum
+    assert np.mean(lay == lay_ref) > 0.999
+    d2 = rm.dist2.cpu().numpy()
+    assert np.array_equal(d2, orc.edt_sq(occ_ref))
+    np.testing.assert_allclose(rm.clearance.cpu().numpy(), np.sqrt(d2.astype(np.float64)) * abs(geo[1]), rtol=1e-6)
+
+
+def test_rasterize_layers_enlargement_and_many_shapes(uam, torch):
+    """1500 random rectangles (integer-metre footprints like data_processor.py:67-71, here in km) in one region +
+    300 obstacle discs: exercises list batching (> 1024 shapes per region) and tile culling."""
+    rng = np.random.default_rng(5)
+    m = uam.RegionMap()
+    spec = {'obstacles': [], 'regions': [('Bld', [])]}
+    m.new_region('Bld', 'r')
+    for _ in range(1500):
+        c, a = rng.uniform(0, 32, 2), rng.uniform(0, np.pi)
+        hw, hh = rng.uniform(0.05, 0.6, 2)
+        R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        V = np.round((c + (np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]]) @ R.T)) * 1000) / 1000
+        m.add_shape_to_region('Bld', uam.polygon(*V.tolist()))
+        spec['regions'][0][1].append({'kind': 'polygon', 'verts': V.tolist()})
+    for _ in range(300):
+        c, r = rng.uniform(0, 32, 2), rng.uniform(0.1, 0.8)
+        m.add_obstacle(uam.ball(c.tolist(), float(r)))
+        spec['obstacles'].append({'kind': 'ball', 'center': c.tolist(), 'r1': float(r), 'r2': float(r)})
+    om = orc.OMap(spec)
+    H, W, geo = 96, 160, (0.0, 0.2, 0.0, 1.0 / 3)
+    eng = m.engine()
+    occ = eng.rasterize_occupancy(H, W, geo).cpu().numpy()
+    assert np.array_equal(occ, orc.rasterize_occupancy(om, H, W, *geo))
+    for e in (0.0, 0.05):
+        lay = eng.rasterize_layers(H, W, geo, e).cpu().numpy()
+        ref = orc.rasterize_layers(om, H, W, *geo, e)
+        assert np.array_equal(lay == 0, ref == 0)
+        np.testing.assert_allclose(lay, ref, rtol=2e-7)
+
+
+def test_dem_mask(uam, torch):
+    rng = np.random.default_rng(3)
+    eng = uam.Engine()
+    for n in [(257, 131), (64, 64), (1, 7)]:
+        img = rng.normal(129.5, 112.6, n).astype(np.float32)
+        img[rng.uniform(size=n) < 0.47] = -9999.0
+        img[0, 0] = 0.0
+        t = torch.from_numpy(img).cuda()
+        for thr in (0.0, 35.5, -9999.0):
+            assert np.array_equal(eng.dem_mask(t, thr).cpu().numpy().astype(bool), orc.dem_mask(img, thr))
+        assert np.array_equal(uam.load_dem_mask(img, 0.0, eng), img > 0)
+        assert np.array_equal(eng.dem_mask(t.flatten()[1:], 0.0).cpu().numpy().astype(bool), img.ravel()[1:] > 0)  # unaligned
+
+
+@pytest.mark.parametrize('H,W,density', [(97, 131, 0.01), (64, 300, 0.3), (200, 50, 0.0005), (33, 33, 1.0), (40, 40, 0.0)])
+def test_edt_exact(uam, torch, H, W, density):
+    rng = np.random.default_rng(H * 1000 + W)
+    occ = (rng.uniform(size=(H, W)) < density).astype(np.uint8)
+    if density == 0.0005:
+        occ[:] = 0
+        occ[H // 3, W - 2] = 1                   # a single seed: pure parabola envelope
+    d2, cl = uam.Engine().edt(torch.from_numpy(occ).cuda(), 0.25)
+    ref = orc.edt_sq(occ)
+    assert np.array_equal(d2.cpu().numpy().astype(np.int64), ref)
+    if occ.any():
+        np.testing.assert_allclose(cl.cpu().numpy(), np.sqrt(ref) * 0.25, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# raster path scorer vs the oracle
+# ------------------------------------------------------------------------------------------------------------
+def _random_raster(rng, L, H, W):
+    yy, xx = np.mgrid[0:H, 0:W]
+    lay = np.stack([(rng.uniform(0.2, 2.0) * np.exp(-((xx - rng.uniform(0, W)) ** 2 + (yy - rng.uniform(0, H)) ** 2) /
+                                                    (2 * rng.uniform(8, 40) ** 2)) + 0.05 * rng.uniform(size=(H, W)))
+                    for _ in range(L)]).astype(np.float32)
+    occ = np.zeros((H, W), dtype=np.uint8)
+    for _ in range(6):
+        ci, cj, r = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(2, 9)
+        occ |= (((yy - ci) ** 2 + (xx - cj) ** 2) < r * r).astype(np.uint8)
+    return lay, occ
+
+
+def _random_paths(rng, B, Wp, geo, H, W, spill=0.0):
+    x0, dx, y0, dy = geo
+    lo = np.array([x0, y0]) - spill * np.array([dx * W, dy * H])
+    hi = np.array([x0 + dx * W, y0 + dy * H]) + spill * np.array([dx * W, dy * H])
+    s = lo + rng.uniform(size=(B, 1, 2)) * (hi - lo)
+    g = lo + rng.uniform(size=(B, 1, 2)) * (hi - lo)
+    t = np.linspace(0, 1, Wp).reshape(1, Wp, 1)
+    P = s + t * (g - s) + rng.normal(0, 2.0 * abs(dx), (B, Wp, 2))
+    return np.ascontiguousarray(P.reshape(B, 2 * Wp))
+
+
+@pytest.mark.parametrize('L', [1, 2, 3])
+@pytest.mark.parametrize('spc', [0.0, 1.0, 0.37, 2.5])
+def test_score_paths_raster_vs_oracle(uam, torch, L, spc):
+    rng = np.random.default_rng(100 + L)
+    H, W, geo = 150, 230, (3.0, 0.25, 40.0, -0.2)
+    lay, occ = _random_raster(rng, L, H, W)
+    rm = uam.RasterMap.from_arrays(lay, geo, occ)
+    w = [200.0, 15000.0, 27000.0][:L]
+    for Wp, spill, x_start in [(64, 0.0, None), (7, 0.15, [4.0, 39.0]), (3, 0.0, None), (130, 0.05, [0.0, 0.0])]:
+        Z = _random_paths(rng, 96, Wp, geo, H, W, spill)
+        for ls in (True, False):
+            c_ref, col_ref, ns_ref = orc.score_paths_raster(lay, occ, geo, Z, w, spc, ls, x_start)
+            Zt = torch.from_numpy(Z).cuda()
+            c, col, ns = rm.score_paths(Zt, w, spc, ls, x_start, want_nsamples=True)
+            np.testing.assert_allclose(c.cpu().numpy(), c_ref, rtol=RTOL_RASTER)
+            assert np.array_equal(col.cpu().numpy().astype(bool), col_ref)         # collision flags: exact
+            assert np.array_equal(ns.cpu().numpy(), ns_ref)                         # same sample counts
+            ch, colh = rm.score_paths(Z, w, spc, ls, x_start)                       # host-buffer entry point
+            assert np.array_equal(ch, c.cpu().numpy()) and np.array_equal(colh, col.cpu().numpy())
+    assert col_ref.any() and not col_ref.all()
+
+
+def test_raster_reduces_to_analytic_reference(uam, fixture_spec, golden):
+    """The raster formulation tied back to the reference: rasterise the main.py map on the GPU, score the jittered
+    golden paths in waypoint mode, compare with the reference's analytic get_cost (discretisation error only:
+    SURVEY section 6 measured 5e-6 at 4096^2; the GPU rasteriser makes that size cheap)."""
+    f = fixture_spec
+    H = W = 4096
+    geo = (8.0, 64.0 / W, -42.0, 64.0 / H)
+    rm = uam.RasterMap.from_map(build_product_map(f), H, W, geo)
+    Z = full_paths(f, golden['jit_x'])
+    cost, col = rm.score_paths(Z, f['weights'], 0.0, True, f['x_start'])
+    ref = golden['jit_cost']
+    assert np.max(np.abs(cost - ref) / ref) < 5e-5
+    # occupancy lookup agrees with the analytic collision test except within one cell of an obstacle boundary
+    assert np.mean(col.astype(bool) == golden['jit_collide'].any(axis=1)) > 0.9
+
+
+def test_raster_scorer_full_size_properties(uam, torch):
+    """BASELINE config 2 size (4096^2 raster, 10k paths x 64 waypoints) through size-independent properties."""
+    dev = 'cuda'
+    H = W = 4096
+    geo = (0.0, 64.0 / W, 0.0, 64.0 / H)
+    g = torch.Generator(device=dev).manual_seed(20260101)
+    lay = torch.rand((1, H, W), device=dev, generator=g)
+    occ = (torch.rand((H, W), device=dev, generator=g) < 0.001).to(torch.uint8)
+    B, Wp = 10000, 64
+    s = torch.rand((B, 1, 2), device=dev, generator=g, dtype=torch.float64) * 64
+    e = torch.rand((B, 1, 2), device=dev, generator=g, dtype=torch.float64) * 64
+    t = torch.linspace(0, 1, Wp, device=dev, dtype=torch.float64).reshape(1, Wp, 1)
+    Z = (s + t * (e - s) + torch.randn((B, Wp, 2), device=dev, generator=g, dtype=torch.float64) * 0.03).reshape(B, 2 * Wp).contiguous()
+    rm = uam.RasterMap.from_arrays(lay, geo, occ)
+    for spc in (0.0, 1.0):
+        c1, k1, n1 = rm.score_paths(Z, [1.0], spc, want_nsamples=True)
+        c3, _ = rm.score_paths(Z, [3.0], spc)
+        c0, _ = rm.score_paths(Z, [0.0], spc)            # pure length term
+        # linearity in the weight: cost(w) = len + w * pen
+        # (float32 outputs near 1e4 carry ~5e-4 absolute rounding each)
+        torch.testing.assert_close((c3 - c0).double(), 3 * (c1 - c0).double(), rtol=1e-4, atol=8e-3)
+        # sharding invariance: two halves == whole, bit for bit
+        ca, ka = rm.score_paths(Z[:B // 2].contiguous(), [1.0], spc)
+        cb, kb = rm.score_paths(Z[B // 2:].contiguous(), [1.0], spc)
+        assert torch.equal(torch.cat([ca, cb]), c1) and torch.equal(torch.cat([ka, kb]), k1)
+        # host-buffer entry point == device entry point
+        ch, kh = rm.score_paths(Z.cpu().numpy(), [1.0], spc)
+        assert np.array_equal(ch, c1.cpu().numpy()) and np.array_equal(kh, k1.cpu().numpy())
+        # the length term against a float64 torch restatement
+        P = Z.reshape(B, Wp, 2)
+        d = P[:, 1:Wp - 1] - P[:, 0:Wp - 2]
+        Lref = (Wp - 1) * (d ** 2).sum(dim=(1, 2))
+        torch.testing.assert_close(c0.double(), Lref, rtol=1e-6, atol=0)
+        assert (n1 >= Wp).all() and ((n1 == Wp).all() if spc == 0 else (n1 > Wp).any())
+    # constant raster: penalty = w * c * (N+2)/N exactly representable checks the sample weights sum to 1 per segment
+    rm2 = uam.RasterMap.from_arrays(torch.full((1, H, W), 0.5, device=dev), geo, torch.ones((H, W), device=dev, dtype=torch.uint8))
+    for spc in (0.0, 1.0):
+        c, k = rm2.score_paths(Z, [8.0], spc)
+        c0, _ = rm2.score_paths(Z, [0.0], spc)
+        torch.testing.assert_close((c - c0).double(), torch.full((B,), 8.0 * 0.5 * Wp / (Wp - 2), device=dev, dtype=torch.float64),
+                                   rtol=1e-4, atol=8e-3)
+        assert bool(k.all())

@@ -1,0 +1,221 @@
+"""CPU-side tests: host logic of the product (shape tables, candidates, map file reader, sharding, key
+packing), the C-ABI export list, and the no-CPU-fallback behaviour.  No kernel runs here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import uam_path_planning_b200 as uam
+from uam_path_planning_b200 import _lib, distributed as udist
+from uam_path_planning_b200.shapes import flatten_shapes
+from oracle import uam_oracle as orc
+from conftest import ROOT, build_product_map, have_gpu
+
+
+def _h_from_records(R, P):
+    """Evaluate inequality records with the ORACLE's formulas (checker only)."""
+    out = np.empty((R.shape[0], P.shape[0]))
+    for i, r in enumerate(R):
+        k = int(r[0])
+        if k == _lib.UAM_EDGE_LINE:
+            e = ('line', r[1], r[2], r[1] + r[3], r[2] + r[4], r[5])
+            # the record stores Bx-Ax / By-Ay exactly; rebuild the oracle's op order from them
+            line = r[4] * (P[:, 0] - r[1]) - r[3] * (P[:, 1] - r[2])
+            out[i] = -r[5] * line
+        elif k == _lib.UAM_EDGE_ELLIPSE:
+            out[i] = orc.OShape('b', [('ellipse', r[1], r[2], r[3], r[4])], None, 0).h(P)[0]
+        else:
+            out[i] = orc.OShape('s', [('box', int(r[1]), r[2], r[3], r[4])], None, 0).h(P)[0]
+    return out
+
+
+def test_shape_tables_match_reference(fixture_spec, golden):
+    """Edge order, signs and coefficients of every shape of the main.py map: evaluating the product's records
+    reproduces the reference's h_i(x) bit for bit; centers and areas match."""
+    m = build_product_map(fixture_spec)
+    shapes = list(m.obstacles) + [s for r in m._region_lists() for s in r]
+    off, P = golden['h_offsets'], golden['h_points']
+    assert len(shapes) == len(off) - 1
+    for k, s in enumerate(shapes):
+        R = s.records()
+        assert R.shape == (off[k + 1] - off[k], 8)
+        assert np.array_equal(_h_from_records(R, P), golden['h_values'][off[k]:off[k + 1]]), k
+        np.testing.assert_array_equal(np.asarray(s.center, dtype=float), golden['shape_centers'][k])
+        assert s.area == pytest.approx(golden['shape_areas'][k], rel=1e-14)
+    sp = uam.polygon(*golden['shuffled_poly_verts'].tolist())
+    assert np.array_equal(_h_from_records(sp.records(), P), golden['shuffled_poly_h'])
+    np.testing.assert_array_equal(sp.center, golden['shuffled_poly_center'])
+
+
+def test_flatten_orders_obstacles_then_regions(fixture_spec):
+    m = build_product_map(fixture_spec)
+    edges, off, reg, cen = flatten_shapes(m.obstacles, m._region_lists())
+    assert edges.shape == (143, 8) and off[0] == 0 and off[-1] == 143
+    assert reg.tolist() == [-1] * 5 + [0] * 4 + [1] * 29 + [2]
+    assert cen.shape == (39, 2) and not np.isnan(cen).any()
+    bare = uam.QuadraticObstacle(*m.obstacles[0].inequalities)
+    assert np.isnan(bare.center_or_nan()).all()
+
+
+def test_constructor_errors(golden_meta):
+    c = golden_meta['constructors']['errors']
+    cases = {'two_vertices': [[0., 0.], [1., 1.]], 'aligned': [[0., 0.], [1., 0.], [2., 0.], [1., 1.]],
+             'nonconvex': [[0., 0.], [2., 0.], [0.5, 0.5], [0., 2.]]}
+    for name, pts in cases.items():
+        with pytest.raises(ValueError) as ei:
+            uam.polygon(*pts)
+        assert str(ei.value) == c[name][1]
+    with pytest.raises(Exception):              # integer first vertex + float vertices: numpy casting error (Q6)
+        uam.polygon([0, 0], [1.5, 0.], [1., 1.])
+    sq = uam.square([1, 1], 0.5)
+    assert sq.area == 1.0 and len(sq.inequalities) == 4
+    bl = uam.ball([1, 1], 2, 1)
+    assert bl.area == pytest.approx(golden_meta['constructors']['ball_area'])
+    assert uam.ball(3.0).records()[0].tolist() == [1, 0, 0, 3, 3, 0, 0, 0]
+
+
+@pytest.mark.parametrize('N', [80, 62, 64, 5])
+def test_create_x_init(fixture_spec, golden, golden_meta, N):
+    m = build_product_map(fixture_spec)
+    sol = uam.Solver(uam.Problem(m, N), {})
+    for i, d in enumerate(golden['arc_disp']):
+        np.testing.assert_allclose(sol.create_x_init(float(d)), golden[f'arc_N{N}_x'][i], rtol=1e-15, atol=1e-15)
+    with pytest.raises(ValueError) as ei:
+        sol.create_x_init(1.5)
+    assert str(ei.value) == golden_meta['constructors']['errors']['x_init_1.5'][1]
+    Z = sol.candidates([-0.5, 0.0, 0.5])
+    assert Z.shape == (3, 2 * (N + 2)) and Z.flags.c_contiguous
+    np.testing.assert_array_equal(Z[:, :2], np.tile(fixture_spec['x_start'], (3, 1)))
+    np.testing.assert_array_equal(Z[:, -2:], np.tile(fixture_spec['x_goal'], (3, 1)))
+    with pytest.raises(NotImplementedError):
+        sol.solve(None, None)
+
+
+def test_region_map_container():
+    m = uam.RegionMap()
+    m.new_region('A', 'Red')
+    with pytest.raises(ValueError) as ei:
+        m.new_region('A', 'b')
+    assert str(ei.value) == "Name 'A' already in use for areas"
+    with pytest.raises(ValueError) as ei:
+        m.add_shape_to_region('B', uam.ball(1.0))
+    assert 'Unknown type' in str(ei.value)
+    m.add_shapes_to_region('A', uam.ball(1.0), uam.square([0, 0], 1))
+    m.add_obstacle(uam.ball([3, 3], 1))
+    assert m.region_names() == ['A'] and len(m) == 1 and m.regions['A']['color'] == [1, 0, 0]
+    assert m[0:1] == m.obstacles
+    with pytest.raises(TypeError):
+        m['x']
+    prob = uam.Problem(m, 4)
+    assert prob.weights == {'A': 1} and prob.options['penalty_smooth'] and not prob.options['length_smooth']
+    prob.params.update(maxratio=1.1, maxalpha=0.1, enlargement=0.5)
+    prob.set_weight('A', 7)
+    np.testing.assert_array_equal(prob.parameter_vector(), [0, 0, 0, 0, 1.1, 0.1, 0.5, 7])
+    assert prob.flags() == _lib.UAM_PENALTY_SMOOTH
+    prob.params['enlargement'] = None
+    with pytest.raises(TypeError):
+        prob.parameter_vector()
+
+
+def test_map_file_reader(tmp_path):
+    txt = ('vertices = [polygon([16.0, 11.0], [11.5, -6.25], [30.25, -30.5], [32.0, -16.0], [28.5, 1.0]),\n'
+           'polygon([0, 0], [2, 0], [2, 1], [0, 1]),\nball([1.0, -2.0], 3),\nsquare([1, 1], 0.5, 2)]\n')
+    f = tmp_path / 'area.txt'
+    f.write_text(txt)
+    shapes = uam.get_var_from_file(str(f), 'vertices')
+    assert [s.kind for s in shapes] == ['polygon', 'polygon', 'ball', 'square']
+    assert len(shapes[0].inequalities) == 5 and shapes[1].area == 2.0
+    o = orc.make_polygon([[16.0, 11.0], [11.5, -6.25], [30.25, -30.5], [32.0, -16.0], [28.5, 1.0]])
+    P = np.random.default_rng(0).uniform(-40, 40, (32, 2))
+    assert np.array_equal(_h_from_records(shapes[0].records(), P), o.h(P))
+    for bad in ['import os\nvertices = []', 'vertices = [__import__("os").system("true")]',
+                'vertices = [polygon([1, 2], [3, open("x")], [5, 6])]', 'vertices = 3']:
+        with pytest.raises((ValueError, SyntaxError)):
+            uam.parse_shapes(bad)
+    with pytest.raises(KeyError):
+        uam.parse_shapes('other = []')
+
+
+def test_shard_range_and_keys():
+    for total, world in [(1_000_000, 8), (10, 3), (5, 8), (0, 2)]:
+        spans = [udist.shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        udist.shard_range(10, 3, 3)
+    cost = np.array([5.0, 2.5, 2.5, 9.0], dtype=np.float32)
+    k = udist.host_best_key(cost, 100)
+    assert udist.decode_key(k) == (2.5, 101)          # tie -> smaller index
+    assert udist.encode_key(2.5, 101) == k and 0 <= k < 2 ** 63
+    assert udist.host_best_key(np.zeros(0)) == udist.KEY_EMPTY
+    assert udist.global_best(k) == (2.5, 101)          # no process group: identity
+
+
+_GLOO_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from uam_path_planning_b200 import distributed as ud
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:' + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+rng = np.random.default_rng(7)
+cost = rng.uniform(1, 100, 1001).astype(np.float32)      # the same global vector on both ranks
+cost[[17, 700]] = 0.5                                     # tie across the two shards
+b, e = ud.shard_range(cost.size, rank, 2)
+key = torch.tensor([ud.host_best_key(cost[b:e], b)], dtype=torch.int64)
+c, i = ud.global_best(key)
+full = ud.gather_costs(torch.from_numpy(np.pad(cost[b:e], (0, 501 - (e - b)))))
+assert (c, i) == (0.5, 17), (c, i)
+assert full.numel() == 1002
+print('ok', rank)
+'''
+
+
+def test_global_best_two_ranks_gloo(tmp_path):
+    """world_size 2 over gloo: shard a cost vector, min-reduce the packed key, same answer on both ranks."""
+    import socket
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = str(s.getsockname()[1])
+    s.close()
+    script = tmp_path / 'w.py'
+    script.write_text(_GLOO_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f'ok {r}' in o, o
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from uam_path_planning_b200 import build
+    build.build()
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, 'include', 'uam_b200.h')).read()
+    declared = set(re.findall(r'\b(uam_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b'sm_100a' in lib.uam_version()
+
+
+@pytest.mark.skipif(have_gpu(), reason='checks the behaviour WITHOUT a CUDA device')
+def test_no_cpu_fallback():
+    """Without a GPU the product refuses to work: ctx creation fails and every evaluation raises."""
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.uam_ctx_create(0, ctypes.byref(h)) == -2 and not h.value
+    with pytest.raises(uam.UamError):
+        uam.Engine()
+    with pytest.raises(uam.UamError):
+        uam.ball(1.0).contains([0.0, 0.0])
+    m = uam.RegionMap()
+    with pytest.raises(uam.UamError):
+        m.collides([0.0, 0.0])

@@ -1,0 +1,323 @@
+// Context, error handling, map uploads (shape tables and rasters) of libuam_b200.so.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "uam_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// errors / small helpers
+// ---------------------------------------------------------------------------------------------------
+int uam_fail(uam_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+int uam_cuda_fail(uam_ctx* ctx, cudaError_t e, const char* what) {
+    return uam_fail(ctx, e == cudaErrorMemoryAllocation ? UAM_ERR_NOMEM : UAM_ERR_CUDA, "%s: %s (%s)", what,
+                    cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+int uam_reserve(uam_ctx* ctx, void** ptr, size_t* cur, size_t need) {
+    if (*cur >= need && *ptr) return UAM_OK;
+    if (*ptr) {
+        UAM_CUDA(ctx, cudaFree(*ptr));
+        *ptr = nullptr;
+        *cur = 0;
+    }
+    size_t cap = need + need / 4 + 256;
+    UAM_CUDA(ctx, cudaMalloc(ptr, cap));
+    *cur = cap;
+    return UAM_OK;
+}
+
+int uam_reserve_pinned(uam_ctx* ctx, void** ptr, size_t* cur, size_t need) {
+    if (*cur >= need && *ptr) return UAM_OK;
+    if (*ptr) {
+        UAM_CUDA(ctx, cudaFreeHost(*ptr));
+        *ptr = nullptr;
+        *cur = 0;
+    }
+    size_t cap = need + need / 4 + 256;
+    UAM_CUDA(ctx, cudaMallocHost(ptr, cap));
+    *cur = cap;
+    return UAM_OK;
+}
+
+// `stream` is the caller's cudaStream_t; NULL is CUDA's (legacy) default stream, as everywhere in CUDA
+cudaStream_t uam_pick_stream(uam_ctx* ctx, void* stream) {
+    (void)ctx;
+    return reinterpret_cast<cudaStream_t>(stream);
+}
+
+// p = [ms_x, ms_y, mg_x, mg_y, maxratio, maxalpha, enlargement, w_0..w_{R-1}]   (solver.py:60-68)
+int uam_make_params(uam_ctx* ctx, const double* h_p, int n_p, int flags, UamParams* out) {
+    if (!h_p) return uam_fail(ctx, UAM_ERR_INVALID, "parameter vector p is NULL");
+    if (n_p < 7) return uam_fail(ctx, UAM_ERR_INVALID, "parameter vector p needs >= 7 entries, got %d", n_p);
+    const int R = n_p - 7;
+    if (R > UAM_MAX_REGIONS)
+        return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "%d region weights given, at most %d supported", R, UAM_MAX_REGIONS);
+    memset(out, 0, sizeof *out);
+    out->ms_x = h_p[0];
+    out->ms_y = h_p[1];
+    out->maxratio = h_p[4];
+    out->mincos = std::cos(h_p[5]);     // cs.cos(maxalpha), problem.py:98
+    out->e = h_p[6];
+    for (int r = 0; r < R; ++r) out->w[r] = h_p[7 + r];
+    out->flags = flags;
+    out->n_regions = R;
+    return UAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+extern "C" const char* uam_version(void) { return "uam_b200 0.1 (sm_100a)"; }
+
+extern "C" int uam_ctx_create(int device, uam_ctx** out) {
+    if (!out) return UAM_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return UAM_ERR_CUDA;  // no CPU fallback
+    uam_ctx* ctx = new (std::nothrow) uam_ctx();
+    if (!ctx) return UAM_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return UAM_ERR_CUDA; }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return UAM_ERR_CUDA; }
+    for (int i = 0; i < UAM_HOST_PIPE_DEPTH; ++i) {
+        if (cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->pipe_event[i], cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return UAM_ERR_CUDA;
+        }
+    }
+    *out = ctx;
+    return UAM_OK;
+}
+
+extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
+    if (!ctx) return UAM_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_edges);
+    cudaFree(ctx->d_shapes);
+    cudaFree(ctx->d_psic);
+    cudaFree(ctx->d_tex);
+    cudaFree(ctx->d_scratch);
+    for (int i = 0; i < UAM_HOST_PIPE_DEPTH; ++i) {
+        cudaFree(ctx->d_stage_in[i]);
+        cudaFree(ctx->d_stage_out[i]);
+        cudaFreeHost(ctx->h_stage_out[i]);
+        if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
+        if (ctx->pipe_event[i]) cudaEventDestroy(ctx->pipe_event[i]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return UAM_OK;
+}
+
+extern "C" const char* uam_last_error(const uam_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+extern "C" int uam_launch_count(const uam_ctx* ctx, uint64_t* n) {
+    if (!ctx || !n) return UAM_ERR_INVALID;
+    *n = ctx->launches;
+    return UAM_OK;
+}
+
+extern "C" int uam_sync(uam_ctx* ctx) {
+    if (!ctx) return UAM_ERR_INVALID;
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < UAM_HOST_PIPE_DEPTH; ++i) UAM_CUDA(ctx, cudaStreamSynchronize(ctx->pipe_stream[i]));
+    return UAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shape tables
+// ---------------------------------------------------------------------------------------------------
+extern "C" int uam_map_set_shapes(uam_ctx* ctx, const double* h_edges, int n_edges, const int32_t* h_shape_off,
+                                  const int32_t* h_shape_region, const double* h_shape_center, int n_shapes,
+                                  int n_regions) {
+    if (!ctx) return UAM_ERR_INVALID;
+    if (n_shapes < 0 || n_edges < 0 || n_regions < 0) return uam_fail(ctx, UAM_ERR_INVALID, "negative table size");
+    if (n_regions > UAM_MAX_REGIONS)
+        return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "%d regions, at most %d supported", n_regions, UAM_MAX_REGIONS);
+    if (n_shapes > 0 && (!h_shape_off || !h_shape_region || !h_shape_center || (n_edges > 0 && !h_edges)))
+        return uam_fail(ctx, UAM_ERR_INVALID, "NULL shape table");
+    if (n_shapes > 0 && (h_shape_off[0] != 0 || h_shape_off[n_shapes] != n_edges))
+        return uam_fail(ctx, UAM_ERR_INVALID, "shape offsets must run from 0 to n_edges");
+    for (int s = 0; s < n_shapes; ++s) {
+        if (h_shape_off[s + 1] < h_shape_off[s]) return uam_fail(ctx, UAM_ERR_INVALID, "shape offsets not monotone");
+        if (h_shape_region[s] < -1 || h_shape_region[s] >= n_regions)
+            return uam_fail(ctx, UAM_ERR_INVALID, "shape %d: region %d out of range", s, h_shape_region[s]);
+    }
+    for (int i = 0; i < n_edges; ++i) {
+        const int k = (int)h_edges[8 * (size_t)i];
+        if (k != UAM_EDGE_LINE && k != UAM_EDGE_ELLIPSE && k != UAM_EDGE_BOX)
+            return uam_fail(ctx, UAM_ERR_INVALID, "inequality %d: unknown kind %d", i, k);
+    }
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    // device order: obstacles (insertion order), then regions 0..R-1 (insertion order inside each)
+    std::vector<UamEdge> edges;
+    std::vector<UamShape> shapes;
+    edges.reserve(n_edges);
+    shapes.reserve(n_shapes);
+    int n_obs = 0;
+    for (int pass = -1; pass < n_regions; ++pass) {
+        if (pass >= 0) ctx->region_begin[pass] = (int)shapes.size();
+        for (int s = 0; s < n_shapes; ++s) {
+            if (h_shape_region[s] != pass) continue;
+            UamShape sh;
+            sh.cx = h_shape_center[2 * s];
+            sh.cy = h_shape_center[2 * s + 1];
+            sh.has_center = !(std::isnan(sh.cx) || std::isnan(sh.cy));   // np.isnan(obs.center).any(), problem.py:76
+            sh.region = pass;
+            sh.e0 = (int)edges.size();
+            for (int i = h_shape_off[s]; i < h_shape_off[s + 1]; ++i) {
+                UamEdge r;
+                memcpy(&r, h_edges + 8 * (size_t)i, sizeof r);
+                edges.push_back(r);
+            }
+            sh.e1 = (int)edges.size();
+            shapes.push_back(sh);
+            if (pass < 0) ++n_obs;
+        }
+    }
+    ctx->region_begin[n_regions] = (int)shapes.size();
+
+    cudaFree(ctx->d_edges);  ctx->d_edges = nullptr;
+    cudaFree(ctx->d_shapes); ctx->d_shapes = nullptr;
+    cudaFree(ctx->d_psic);   ctx->d_psic = nullptr;
+    UAM_CUDA(ctx, cudaMalloc(&ctx->d_edges, sizeof(UamEdge) * (edges.size() + 1)));
+    UAM_CUDA(ctx, cudaMalloc(&ctx->d_shapes, sizeof(UamShape) * (shapes.size() + 1)));
+    UAM_CUDA(ctx, cudaMalloc(&ctx->d_psic, sizeof(double) * (shapes.size() + 1)));
+    if (!edges.empty())
+        UAM_CUDA(ctx, cudaMemcpy(ctx->d_edges, edges.data(), sizeof(UamEdge) * edges.size(), cudaMemcpyHostToDevice));
+    if (!shapes.empty())
+        UAM_CUDA(ctx, cudaMemcpy(ctx->d_shapes, shapes.data(), sizeof(UamShape) * shapes.size(), cudaMemcpyHostToDevice));
+    ctx->n_shapes = (int)shapes.size();
+    ctx->n_edges = (int)edges.size();
+    ctx->n_regions = n_regions;
+    ctx->n_obs = n_obs;
+    ctx->has_shapes = true;
+    ctx->psic_valid = false;
+    return UAM_OK;
+}
+
+// psi_s(center_s; e) per shape (problem.py:79), recomputed only when e / smooth flags change
+__global__ void uam_k_shape_norm(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, int n_shapes,
+                                 int flags, double e, double* __restrict__ psic) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_shapes) return;
+    const UamShape sh = shapes[s];
+    if (!sh.has_center) { psic[s] = 1.0; return; }
+    // hard obstacles: obstacle_smooth, enlargement = params['enlargement'] (get_penalty_function(None))
+    const bool smooth = sh.region < 0 ? (flags & UAM_OBSTACLE_SMOOTH) != 0 : (flags & UAM_PENALTY_SMOOTH) != 0;
+    psic[s] = uam_psi(edges, sh.e0, sh.e1, sh.cx, sh.cy, smooth, e, nullptr);
+}
+
+int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st) {
+    const int key = prm.flags & (UAM_PENALTY_SMOOTH | UAM_OBSTACLE_SMOOTH);
+    if (ctx->psic_valid && ctx->psic_e == prm.e && ctx->psic_flags == key) return UAM_OK;
+    if (ctx->n_shapes > 0) {
+        // all streams that may still read the old table must be done before it is overwritten
+        UAM_CUDA(ctx, cudaDeviceSynchronize());
+        uam_k_shape_norm<<<(ctx->n_shapes + 127) / 128, 128, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->n_shapes,
+                                                                       prm.flags, prm.e, ctx->d_psic);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_shape_norm");
+        UAM_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    ctx->psic_valid = true;
+    ctx->psic_e = prm.e;
+    ctx->psic_flags = key;
+    return UAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rasters: planar (L,H,W) float32 + (H,W) uint8  ->  interleaved texels (layer values + occupancy)
+// ---------------------------------------------------------------------------------------------------
+template <int TF>
+__global__ void uam_k_pack_texels(const float* __restrict__ layers, const uint8_t* __restrict__ occ, int L,
+                                  size_t n_cells, float* __restrict__ tex) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += stride) {
+        const float o = (occ && occ[c]) ? 1.0f : 0.0f;
+        if (TF == 2) {
+            reinterpret_cast<float2*>(tex)[c] = make_float2(layers[c], o);
+        } else {
+            const float l0 = layers[c];
+            const float l1 = L > 1 ? layers[n_cells + c] : 0.0f;
+            const float l2 = L > 2 ? layers[2 * n_cells + c] : 0.0f;
+            reinterpret_cast<float4*>(tex)[c] = make_float4(l0, l1, l2, o);
+        }
+    }
+}
+
+static int uam_check_raster_args(uam_ctx* ctx, const void* layers, int L, int H, int W, double dx, double dy) {
+    if (!ctx) return UAM_ERR_INVALID;
+    if (!layers) return uam_fail(ctx, UAM_ERR_INVALID, "layers is NULL");
+    if (L < 1 || L > 3) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "L = %d cost layers, supported: 1..3", L);
+    if (H < 2 || W < 2) return uam_fail(ctx, UAM_ERR_INVALID, "raster must be at least 2 x 2, got %d x %d", H, W);
+    if (!(dx != 0.0) || !(dy != 0.0) || std::isnan(dx) || std::isnan(dy))
+        return uam_fail(ctx, UAM_ERR_INVALID, "cell size must be non-zero");
+    return UAM_OK;
+}
+
+extern "C" int uam_map_set_raster_device(uam_ctx* ctx, const float* d_layers, int L, int H, int W, double x0, double dx,
+                                         double y0, double dy, const uint8_t* d_occupancy, void* stream) {
+    UAM_TRY(uam_check_raster_args(ctx, d_layers, L, H, W, dx, dy));
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = uam_pick_stream(ctx, stream);
+    const int tf = (L == 1) ? 2 : 4;
+    const size_t n_cells = (size_t)H * W;
+    // the old texels may still be read by kernels queued on other streams
+    UAM_CUDA(ctx, cudaDeviceSynchronize());
+    UAM_TRY(uam_reserve(ctx, &ctx->d_tex, &ctx->tex_bytes, n_cells * tf * sizeof(float)));
+    const int grid = ctx->sm_count * 8;
+    if (tf == 2)
+        uam_k_pack_texels<2><<<grid, 256, 0, st>>>(d_layers, d_occupancy, L, n_cells, (float*)ctx->d_tex);
+    else
+        uam_k_pack_texels<4><<<grid, 256, 0, st>>>(d_layers, d_occupancy, L, n_cells, (float*)ctx->d_tex);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_pack_texels");
+    ctx->geo.x0 = x0; ctx->geo.dx = dx; ctx->geo.y0 = y0; ctx->geo.dy = dy;
+    ctx->geo.H = H; ctx->geo.W = W; ctx->geo.L = L; ctx->geo.texel_floats = tf;
+    ctx->has_raster = true;
+    return UAM_OK;
+}
+
+extern "C" int uam_map_set_raster(uam_ctx* ctx, const float* h_layers, int L, int H, int W, double x0, double dx,
+                                  double y0, double dy, const uint8_t* h_occupancy) {
+    UAM_TRY(uam_check_raster_args(ctx, h_layers, L, H, W, dx, dy));
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n_cells = (size_t)H * W;
+    float* d_layers = nullptr;
+    uint8_t* d_occ = nullptr;
+    UAM_CUDA(ctx, cudaMalloc(&d_layers, n_cells * L * sizeof(float)));
+    cudaError_t e = cudaMemcpy(d_layers, h_layers, n_cells * L * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && h_occupancy) {
+        e = cudaMalloc(&d_occ, n_cells);
+        if (e == cudaSuccess) e = cudaMemcpy(d_occ, h_occupancy, n_cells, cudaMemcpyHostToDevice);
+    }
+    int rc = UAM_OK;
+    if (e != cudaSuccess) rc = uam_cuda_fail(ctx, e, "raster upload");
+    if (rc == UAM_OK) rc = uam_map_set_raster_device(ctx, d_layers, L, H, W, x0, dx, y0, dy, d_occ, nullptr);
+    if (rc == UAM_OK) {
+        cudaError_t e2 = cudaStreamSynchronize(nullptr);
+        if (e2 != cudaSuccess) rc = uam_cuda_fail(ctx, e2, "raster pack");
+    }
+    cudaFree(d_layers);
+    cudaFree(d_occ);
+    return rc;
+}

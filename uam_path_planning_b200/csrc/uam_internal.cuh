@@ -1,0 +1,176 @@
+// Internal declarations shared by the translation units of libuam_b200.so (sm_100a).
+// Public surface: include/uam_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "uam_b200.h"
+
+#define UAM_MAX_REGIONS 16
+#define UAM_WARPS_PER_CTA 8
+#define UAM_CTA_THREADS (UAM_WARPS_PER_CTA * 32)
+#define UAM_HOST_PIPE_DEPTH 3
+
+// ---- device table records ---------------------------------------------------------------------
+// Inequality record, same 8-double layout as the C-ABI (rec[0] = kind).
+struct __align__(16) UamEdge {
+    double kind, p0, p1, p2, p3, p4, p5, p6;
+};
+
+// One shape = a run of inequality records.  Device order: hard obstacles first (insertion order),
+// then region shapes, region-major in insertion order.
+struct __align__(16) UamShape {
+    double cx, cy;            // QuadraticObstacle.center (NaN = none)
+    int e0, e1;               // edge range [e0, e1)
+    int region;               // -1 = hard obstacle
+    int has_center;
+};
+
+struct UamParams {
+    double ms_x, ms_y;        // map.x_start (first pair of the length term, problem.py:137-145)
+    double maxratio, mincos, e;
+    double w[UAM_MAX_REGIONS];
+    int flags;
+    int n_regions;
+};
+
+struct UamRasterGeo {
+    double x0, dx, y0, dy;
+    int H, W, L;
+    int texel_floats;         // 2 (L == 1: layer, occupancy) or 4 (L in 2..3: l0, l1, l2, occupancy)
+};
+
+// ---- context --------------------------------------------------------------------------------------
+struct uam_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;                       // own stream
+    cudaStream_t pipe_stream[UAM_HOST_PIPE_DEPTH] = {};  // host-buffer pipeline
+    cudaEvent_t pipe_event[UAM_HOST_PIPE_DEPTH] = {};
+    std::string err;
+    uint64_t launches = 0;
+
+    // device shape tables
+    UamEdge* d_edges = nullptr;
+    UamShape* d_shapes = nullptr;
+    double* d_psic = nullptr;           // psi_s(center_s; e) per shape, made by uam_k_shape_norm
+    int n_shapes = 0, n_edges = 0, n_regions = 0, n_obs = 0;
+    int region_begin[UAM_MAX_REGIONS + 1] = {};  // shape index range of each region
+    bool has_shapes = false;
+    bool psic_valid = false;
+    double psic_e = 0.0;
+    int psic_flags = -1;
+
+    // raster
+    void* d_tex = nullptr;              // float2 / float4 texels, row-major (H, W)
+    size_t tex_bytes = 0;
+    UamRasterGeo geo = {};
+    bool has_raster = false;
+
+    // staging for the *_host entry points
+    void* d_stage_in[UAM_HOST_PIPE_DEPTH] = {};
+    size_t stage_in_bytes[UAM_HOST_PIPE_DEPTH] = {};
+    void* d_stage_out[UAM_HOST_PIPE_DEPTH] = {};
+    size_t stage_out_bytes[UAM_HOST_PIPE_DEPTH] = {};
+    void* h_stage_out[UAM_HOST_PIPE_DEPTH] = {};   // pinned
+    size_t h_stage_out_bytes[UAM_HOST_PIPE_DEPTH] = {};
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+int uam_fail(uam_ctx* ctx, int code, const char* fmt, ...);
+int uam_cuda_fail(uam_ctx* ctx, cudaError_t e, const char* what);
+int uam_reserve(uam_ctx* ctx, void** ptr, size_t* cur, size_t need);
+int uam_reserve_pinned(uam_ctx* ctx, void** ptr, size_t* cur, size_t need);
+int uam_make_params(uam_ctx* ctx, const double* h_p, int n_p, int flags, UamParams* out);
+int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st);
+cudaStream_t uam_pick_stream(uam_ctx* ctx, void* stream);
+
+#define UAM_CUDA(ctx, call)                                             \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return uam_cuda_fail((ctx), _e, #call);  \
+    } while (0)
+
+#define UAM_CHECK_LAUNCH(ctx, name)                                     \
+    do {                                                                \
+        cudaError_t _e = cudaGetLastError();                            \
+        if (_e != cudaSuccess) return uam_cuda_fail((ctx), _e, name);   \
+        (ctx)->launches++;                                              \
+    } while (0)
+
+#define UAM_TRY(expr)                 \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != UAM_OK) return _rc; \
+    } while (0)
+
+#ifdef __CUDACC__
+// ---- device helpers: exact fp64 inequality evaluation ----------------------------------------------
+// Explicit round-to-nearest intrinsics keep nvcc from contracting a*b+c into an FMA, so the result
+// has the same bits as the reference's numpy float64 arithmetic.
+__device__ __forceinline__ double uam_h_exact(const UamEdge& r, double x, double y) {
+    const int kind = (int)r.kind;
+    if (kind == UAM_EDGE_LINE) {
+        // -sgn * ((By-Ay)*(x-Ax) - (Bx-Ax)*(y-Ay))      polygon.py:69-71,98
+        const double t1 = __dmul_rn(r.p3, __dsub_rn(x, r.p0));
+        const double t2 = __dmul_rn(r.p2, __dsub_rn(y, r.p1));
+        return __dmul_rn(-r.p4, __dsub_rn(t1, t2));
+    } else if (kind == UAM_EDGE_ELLIPSE) {
+        // ((x-cx)/r1)^2 + ((y-cy)/r2)^2 - 1             ball.py:33-37
+        const double a = __ddiv_rn(__dsub_rn(x, r.p0), r.p2);
+        const double b = __ddiv_rn(__dsub_rn(y, r.p1), r.p3);
+        return __dsub_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), 1.0);
+    } else {
+        // x_d - c - r   |   -x_d + c - r                square.py:29-51
+        const double xd = ((int)r.p0 == 0) ? x : y;
+        if (r.p1 > 0) return __dsub_rn(__dsub_rn(xd, r.p2), r.p3);
+        return __dsub_rn(__dadd_rn(-xd, r.p2), r.p3);
+    }
+}
+
+__device__ __forceinline__ UamEdge uam_load_edge(const UamEdge* __restrict__ p) {
+    // 4 x 16-byte read-only loads; every lane reads the same record (broadcast, L1-resident)
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    UamEdge r;
+    r.kind = a.x; r.p0 = a.y; r.p1 = b.x; r.p2 = b.y; r.p3 = c.x; r.p4 = c.y; r.p5 = d.x; r.p6 = d.y;
+    return r;
+}
+
+// psi_s(x; e) = prod_i min(h_i - e, 0)^2 (smooth) | prod_i min(e - h_i, 0)   quadratic_obstacle.py:27-39
+// `inside` (nullable) gets all_i h_i <= 1e-14                                  quadratic_obstacle.py:89-94
+__device__ __forceinline__ double uam_psi(const UamEdge* __restrict__ edges, int e0, int e1, double x,
+                                          double y, bool smooth, double e, bool* inside) {
+    double res = 1.0;
+    bool in = true;
+    for (int i = e0; i < e1; ++i) {
+        const UamEdge r = uam_load_edge(edges + i);
+        const double h = uam_h_exact(r, x, y);
+        in = in && (h <= 1e-14);
+        if (smooth) {
+            const double m = fmin(__dsub_rn(h, e), 0.0);
+            res = __dmul_rn(res, __dmul_rn(m, m));
+        } else {
+            res = __dmul_rn(res, fmin(__dsub_rn(e, h), 0.0));
+        }
+    }
+    if (inside) *inside = in;
+    return res;
+}
+
+__device__ __forceinline__ float uam_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double uam_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif

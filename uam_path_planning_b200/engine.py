@@ -1,0 +1,328 @@
+"""Engine: one ``uam_ctx`` (one GPU) behind numpy-in / numpy-out and tensor-in / tensor-out calls.
+
+numpy arrays go through the ``*_host`` entry points of the C-ABI (host<->device copies inside the library);
+torch CUDA tensors are passed as raw device pointers on torch's current stream (torch is only the allocator).
+Nothing here computes on the CPU: without libuam_b200.so or without a CUDA device every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import UamError
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64c(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _is_tensor(x) -> bool:
+    return type(x).__module__.startswith('torch') and hasattr(x, 'data_ptr')
+
+
+def _cur_stream(device_index: int):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+class Engine:
+    def __init__(self, device: Optional[int] = None):
+        self._lib = _lib.load()
+        if device is None:
+            device = 0
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    device = torch.cuda.current_device()
+            except ImportError:      # torch is optional for the numpy path
+                pass
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self._lib.uam_ctx_create(self.device, C.byref(h))
+        if rc != _lib.UAM_OK:
+            raise UamError(rc, f'uam_ctx_create(device={self.device}) failed: no usable CUDA device '
+                               '(this framework has no CPU fallback)')
+        self._h = h
+        self.n_regions = 0
+        self.n_obstacles = 0
+        self.raster_shape = None
+
+    # ---- plumbing -------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.uam_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != _lib.UAM_OK:
+            raise UamError(rc, self._lib.uam_last_error(self._h).decode())
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self._check(self._lib.uam_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def sync(self):
+        self._check(self._lib.uam_sync(self._h))
+
+    def _tensor_args(self, *tensors):
+        import torch
+        for t in tensors:
+            if t is None:
+                continue
+            if not t.is_cuda or t.device.index != self.device:
+                raise ValueError(f'tensor on {t.device}, engine on cuda:{self.device}')
+            if not t.is_contiguous():
+                raise ValueError('tensors must be contiguous')
+        return _cur_stream(self.device)
+
+    # ---- map ------------------------------------------------------------------------------------------------
+    def set_shapes(self, obstacles: Sequence, regions: Sequence[Sequence]):
+        from .shapes import flatten_shapes
+        edges, off, reg, cen = flatten_shapes(obstacles, regions)
+        self._check(self._lib.uam_map_set_shapes(self._h, _np_ptr(edges), edges.shape[0], _np_ptr(off), _np_ptr(reg),
+                                                 _np_ptr(cen), reg.shape[0], len(regions)))
+        self.n_regions = len(regions)
+        self.n_obstacles = len(obstacles)
+
+    def set_raster(self, layers, geo, occupancy=None):
+        """layers (L,H,W) float32, geo = (x0, dx, y0, dy), occupancy (H,W) uint8 or None."""
+        x0, dx, y0, dy = [float(v) for v in geo]
+        if _is_tensor(layers):
+            import torch
+            assert layers.dtype == torch.float32 and layers.dim() == 3
+            assert occupancy is None or (occupancy.dtype == torch.uint8 and tuple(occupancy.shape) == tuple(layers.shape[1:]))
+            st = self._tensor_args(layers, occupancy)
+            L, H, W = layers.shape
+            self._check(self._lib.uam_map_set_raster_device(
+                self._h, C.c_void_p(layers.data_ptr()), L, H, W, x0, dx, y0, dy,
+                C.c_void_p(occupancy.data_ptr()) if occupancy is not None else None, st))
+        else:
+            layers = np.ascontiguousarray(layers, dtype=np.float32)
+            assert layers.ndim == 3
+            L, H, W = layers.shape
+            occ = None if occupancy is None else np.ascontiguousarray(occupancy, dtype=np.uint8)
+            assert occ is None or occ.shape == (H, W)
+            self._check(self._lib.uam_map_set_raster(self._h, _np_ptr(layers), L, H, W, x0, dx, y0, dy, _np_ptr(occ)))
+        self.raster_shape = (int(L), int(H), int(W))
+
+    # ---- scoring ---------------------------------------------------------------------------------------------
+    def g_len(self, N: int) -> int:
+        n = C.c_int64()
+        self._check(self._lib.uam_analytic_g_len(self._h, int(N), C.byref(n)))
+        return int(n.value)
+
+    def score_analytic(self, Z, N: int, p, flags: int, want_g: bool = False):
+        """Z (B, 2(N+2)) float64 -> (cost f64 (B,), collide u8 (B,), g f64 (B, glen) | None)."""
+        p = _f64c(p)
+        N = int(N)
+        if _is_tensor(Z):
+            import torch
+            assert Z.dtype == torch.float64 and Z.dim() == 2 and Z.shape[1] == 2 * (N + 2)
+            st = self._tensor_args(Z)
+            B = Z.shape[0]
+            cost = torch.empty(B, dtype=torch.float64, device=Z.device)
+            col = torch.empty(B, dtype=torch.uint8, device=Z.device)
+            g = torch.empty((B, self.g_len(N)), dtype=torch.float64, device=Z.device) if want_g else None
+            self._check(self._lib.uam_score_paths_analytic(
+                self._h, C.c_void_p(Z.data_ptr()), B, N, _np_ptr(p), p.size, flags, C.c_void_p(cost.data_ptr()),
+                C.c_void_p(col.data_ptr()), C.c_void_p(g.data_ptr()) if want_g else None, st))
+            return cost, col, g
+        Z = _f64c(Z)
+        if Z.ndim != 2 or Z.shape[1] != 2 * (N + 2):
+            raise ValueError(f'paths must be (B, {2 * (N + 2)}) for N = {N}, got {Z.shape}')
+        B = Z.shape[0]
+        cost = np.empty(B, dtype=np.float64)
+        col = np.empty(B, dtype=np.uint8)
+        g = np.empty((B, self.g_len(N)), dtype=np.float64) if want_g else None
+        self._check(self._lib.uam_score_paths_analytic_host(self._h, _np_ptr(Z), B, N, _np_ptr(p), p.size, flags,
+                                                            _np_ptr(cost), _np_ptr(col), _np_ptr(g)))
+        return cost, col, g
+
+    def score_raster(self, Z, N: int, p, flags: int, samples_per_cell: float = 0.0, want_nsamples: bool = False,
+                     out=None):
+        """Z (B, 2(N+2)) float64 -> (cost f32 (B,), collide u8 (B,)[, nsamples i64 (B,)]).
+        `out` = (cost, collide) preallocated buffers of the same kind as Z (optional)."""
+        p = _f64c(p)
+        N = int(N)
+        if _is_tensor(Z):
+            import torch
+            assert Z.dtype == torch.float64 and Z.dim() == 2 and Z.shape[1] == 2 * (N + 2)
+            B = Z.shape[0]
+            cost, col = out if out is not None else (torch.empty(B, dtype=torch.float32, device=Z.device),
+                                                     torch.empty(B, dtype=torch.uint8, device=Z.device))
+            ns = torch.empty(B, dtype=torch.int64, device=Z.device) if want_nsamples else None
+            st = self._tensor_args(Z, cost, col)
+            self._check(self._lib.uam_score_paths_raster(
+                self._h, C.c_void_p(Z.data_ptr()), B, N, _np_ptr(p), p.size, flags, float(samples_per_cell),
+                C.c_void_p(cost.data_ptr()), C.c_void_p(col.data_ptr()), C.c_void_p(ns.data_ptr()) if want_nsamples else None,
+                st))
+            return (cost, col, ns) if want_nsamples else (cost, col)
+        if want_nsamples:
+            raise ValueError('nsamples is only available on the device-tensor path')
+        if not (isinstance(Z, np.ndarray) and Z.dtype == np.float64 and Z.flags.c_contiguous):
+            Z = _f64c(Z)
+        if Z.ndim != 2 or Z.shape[1] != 2 * (N + 2):
+            raise ValueError(f'paths must be (B, {2 * (N + 2)}) for N = {N}, got {Z.shape}')
+        B = Z.shape[0]
+        cost, col = out if out is not None else (np.empty(B, dtype=np.float32), np.empty(B, dtype=np.uint8))
+        self._check(self._lib.uam_score_paths_raster_host(self._h, _np_ptr(Z), B, N, _np_ptr(p), p.size, flags,
+                                                          float(samples_per_cell), _np_ptr(cost), _np_ptr(col)))
+        return cost, col
+
+    def eval_points(self, X, p, flags: int, want=('region', 'obstacle', 'collide')):
+        """X (M,2) float64 -> dict(region=(M,R) weighted penalties, obstacle=(M,), collide=(M,) u8)."""
+        p = _f64c(p)
+        R = self.n_regions
+        if _is_tensor(X):
+            import torch
+            assert X.dtype == torch.float64 and X.dim() == 2 and X.shape[1] == 2
+            st = self._tensor_args(X)
+            M = X.shape[0]
+            out = {}
+            if 'region' in want:
+                out['region'] = torch.empty((M, R), dtype=torch.float64, device=X.device)
+            if 'obstacle' in want:
+                out['obstacle'] = torch.empty(M, dtype=torch.float64, device=X.device)
+            if 'collide' in want:
+                out['collide'] = torch.empty(M, dtype=torch.uint8, device=X.device)
+            ptr = lambda k: C.c_void_p(out[k].data_ptr()) if k in out else None
+            self._check(self._lib.uam_eval_points(self._h, C.c_void_p(X.data_ptr()), M, _np_ptr(p), p.size, flags,
+                                                  ptr('region'), ptr('obstacle'), ptr('collide'), st))
+            return out
+        X = _f64c(X).reshape(-1, 2)
+        M = X.shape[0]
+        out = {}
+        if 'region' in want:
+            out['region'] = np.empty((M, R), dtype=np.float64)
+        if 'obstacle' in want:
+            out['obstacle'] = np.empty(M, dtype=np.float64)
+        if 'collide' in want:
+            out['collide'] = np.empty(M, dtype=np.uint8)
+        self._check(self._lib.uam_eval_points_host(self._h, _np_ptr(X), M, _np_ptr(p), p.size, flags,
+                                                   _np_ptr(out.get('region')), _np_ptr(out.get('obstacle')),
+                                                   _np_ptr(out.get('collide'))))
+        return out
+
+    def length_of(self, X, N: int, x_start, x_goal, smooth: bool):
+        """Problem.length_of for rows X (B, 2M) float64."""
+        ends = _f64c(np.concatenate([np.ravel(x_start), np.ravel(x_goal)]))
+        assert ends.size == 4
+        if _is_tensor(X):
+            import torch
+            assert X.dtype == torch.float64 and X.dim() == 2 and X.shape[1] % 2 == 0
+            st = self._tensor_args(X)
+            out = torch.empty(X.shape[0], dtype=torch.float64, device=X.device)
+            self._check(self._lib.uam_length_of(self._h, C.c_void_p(X.data_ptr()), X.shape[0], X.shape[1] // 2, int(N),
+                                                _np_ptr(ends), int(bool(smooth)), C.c_void_p(out.data_ptr()), st))
+            return out
+        X = _f64c(X)
+        assert X.ndim == 2 and X.shape[1] % 2 == 0
+        out = np.empty(X.shape[0], dtype=np.float64)
+        self._check(self._lib.uam_length_of_host(self._h, _np_ptr(X), X.shape[0], X.shape[1] // 2, int(N), _np_ptr(ends),
+                                                 int(bool(smooth)), _np_ptr(out)))
+        return out
+
+    def best(self, cost, global_offset: int = 0, key=None):
+        """min over b of (float32 bits of cost[b] << 32 | global_offset + b) as a 1-element int64 CUDA tensor
+        (costs >= 0, so the key is a non-negative int64 and orders like (cost, index))."""
+        import torch
+        assert _is_tensor(cost) and cost.dtype in (torch.float32, torch.float64)
+        reset = key is None
+        if key is None:
+            key = torch.empty(1, dtype=torch.int64, device=cost.device)
+        st = self._tensor_args(cost, key)
+        self._check(self._lib.uam_best(self._h, C.c_void_p(cost.data_ptr()), int(cost.dtype == torch.float64),
+                                       cost.numel(), int(global_offset), C.c_void_p(key.data_ptr()), int(reset), st))
+        return key
+
+    # ---- map rebuild ---------------------------------------------------------------------------------------------
+    def dem_mask(self, image, threshold: float = 0.0):
+        """image > threshold (image == -9999 when threshold == -9999) on a float32 CUDA tensor -> uint8."""
+        import torch
+        assert _is_tensor(image) and image.dtype == torch.float32
+        st = self._tensor_args(image)
+        mask = torch.empty(image.shape, dtype=torch.uint8, device=image.device)
+        self._check(self._lib.uam_dem_mask(self._h, C.c_void_p(image.data_ptr()), image.numel(), float(threshold),
+                                           C.c_void_p(mask.data_ptr()), st))
+        return mask
+
+    def rasterize_occupancy(self, H: int, W: int, geo):
+        import torch
+        x0, dx, y0, dy = [float(v) for v in geo]
+        occ = torch.empty((H, W), dtype=torch.uint8, device=f'cuda:{self.device}')
+        self._check(self._lib.uam_rasterize_occupancy(self._h, H, W, x0, dx, y0, dy, C.c_void_p(occ.data_ptr()),
+                                                      _cur_stream(self.device)))
+        return occ
+
+    def rasterize_layers(self, H: int, W: int, geo, enlargement: float = 0.0):
+        import torch
+        x0, dx, y0, dy = [float(v) for v in geo]
+        lay = torch.empty((self.n_regions, H, W), dtype=torch.float32, device=f'cuda:{self.device}')
+        self._check(self._lib.uam_rasterize_layers(self._h, H, W, x0, dx, y0, dy, float(enlargement),
+                                                   C.c_void_p(lay.data_ptr()), _cur_stream(self.device)))
+        return lay
+
+    def edt(self, occ, cell: float = 1.0, want_clearance: bool = True):
+        """Exact squared distance (cells, int32) to the nearest occupied cell + clearance = sqrt(d2)*cell."""
+        import torch
+        assert _is_tensor(occ) and occ.dtype == torch.uint8 and occ.dim() == 2
+        st = self._tensor_args(occ)
+        H, W = occ.shape
+        d2 = torch.empty((H, W), dtype=torch.int32, device=occ.device)
+        cl = torch.empty((H, W), dtype=torch.float32, device=occ.device) if want_clearance else None
+        self._check(self._lib.uam_edt(self._h, C.c_void_p(occ.data_ptr()), H, W, float(cell), C.c_void_p(d2.data_ptr()),
+                                      C.c_void_p(cl.data_ptr()) if cl is not None else None, st))
+        return d2, cl
+
+    # ---- single-shape queries (QuadraticObstacle.contains / penalty_function, Function.__call__) -----------------
+    def _scratch(self) -> 'Engine':
+        if getattr(self, '_scratch_engine', None) is None:
+            self._scratch_engine = Engine(self.device)
+        return self._scratch_engine
+
+    def eval_single_shape(self, shape, x, want: str, smooth: bool = True, enlargement: float = 0.0):
+        """contains -> bool array; psi -> unnormalised penalty prod_i min(h_i - e, 0)^2 (or the non-smooth form)."""
+        from .shapes import QuadraticObstacle
+        X = _f64c(x).reshape(-1, 2)
+        eng = self._scratch()
+        bare = QuadraticObstacle(*shape.inequalities)     # center = NaN -> no normalisation (problem.py:76-77)
+        p = np.array([0, 0, 0, 0, 1.0, 0.0, float(enlargement), 1.0])
+        if want == 'contains':
+            eng.set_shapes([bare], [[]])
+            return eng.eval_points(X, p, 0, want=('collide',))['collide'].astype(bool)
+        eng.set_shapes([], [[bare]])
+        flags = _lib.UAM_PENALTY_SMOOTH if smooth else 0
+        return eng.eval_points(X, p, flags, want=('region',))['region'][:, 0]
+
+    def eval_inequalities(self, records, x) -> np.ndarray:
+        """h_i(x_m) for raw inequality records (n,8) at points (M,2) -> (n, M) float64 (Function.__call__)."""
+        R = _f64c(records).reshape(-1, 8)
+        X = _f64c(x).reshape(-1, 2)
+        out = np.empty((R.shape[0], X.shape[0]), dtype=np.float64)
+        self._check(self._lib.uam_eval_inequalities_host(self._h, _np_ptr(R), R.shape[0], _np_ptr(X), X.shape[0],
+                                                         _np_ptr(out)))
+        return out
+
+
+_default: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default
+    if _default is None:
+        _default = Engine()
+    return _default
