@@ -80,6 +80,13 @@ const char* uam_version(void);
 int uam_launch_count(const uam_ctx* ctx, uint64_t* n);
 /* wait for the ctx's own streams */
 int uam_sync(uam_ctx* ctx);
+/* tuning knobs (defaults are the measured-best settings) */
+enum {
+    UAM_OPT_RASTER_LAYOUT = 1,        /* texel layout used by the next uam_map_set_raster*: 0 row-major, 1 tiled */
+    UAM_OPT_INTEGRAL_VARIANT = 2,     /* integral-mode kernel: 0 one lane per sample, 1 lane pair per sample */
+    UAM_OPT_L2_FETCH_GRANULARITY = 3  /* cudaLimitMaxL2FetchGranularity for this device: 32, 64 or 128 bytes */
+};
+int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value);
 
 /* ---- map: shape tables ------------------------------------------------------------------------
  * Replaces the object graph RegionMap / Map / QuadraticObstacle / Function

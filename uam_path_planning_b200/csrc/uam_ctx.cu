@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -102,8 +103,33 @@ extern "C" int uam_ctx_create(int device, uam_ctx** out) {
             return UAM_ERR_CUDA;
         }
     }
+    // tuning knobs from the environment (bench A/B runs); uam_ctx_set_option overrides
+    if (const char* e = getenv("UAM_RASTER_LAYOUT")) ctx->raster_layout = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("UAM_L2_FETCH_GRANULARITY")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
     *out = ctx;
     return UAM_OK;
+}
+
+extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
+    if (!ctx) return UAM_ERR_INVALID;
+    switch (option) {
+        case UAM_OPT_RASTER_LAYOUT:
+            if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "raster layout must be 0 or 1");
+            ctx->raster_layout = (int)value;
+            return UAM_OK;
+        case UAM_OPT_INTEGRAL_VARIANT:
+            if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "integral variant must be 0 or 1");
+            ctx->int_variant = (int)value;
+            return UAM_OK;
+        case UAM_OPT_L2_FETCH_GRANULARITY:
+            if (value != 32 && value != 64 && value != 128) return uam_fail(ctx, UAM_ERR_INVALID, "L2 fetch granularity must be 32, 64 or 128");
+            UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+            UAM_CUDA(ctx, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+            return UAM_OK;
+        default:
+            return uam_fail(ctx, UAM_ERR_INVALID, "unknown option %d", option);
+    }
 }
 
 extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
@@ -248,19 +274,38 @@ int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------
 // rasters: planar (L,H,W) float32 + (H,W) uint8  ->  interleaved texels (layer values + occupancy)
 // ---------------------------------------------------------------------------------------------------
-template <int TF>
-__global__ void uam_k_pack_texels(const float* __restrict__ layers, const uint8_t* __restrict__ occ, int L,
-                                  size_t n_cells, float* __restrict__ tex) {
+// One thread per OUTPUT texel (coalesced writes); tiled layouts are padded to whole tiles with zero texels.
+template <int TF, int LAYOUT>
+__global__ void uam_k_pack_texels(const float* __restrict__ layers, const uint8_t* __restrict__ occ, int L, int H, int W,
+                                  int tiles_x, size_t n_out, float* __restrict__ tex) {
+    const size_t n_cells = (size_t)H * W;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += stride) {
-        const float o = (occ && occ[c]) ? 1.0f : 0.0f;
-        if (TF == 2) {
-            reinterpret_cast<float2*>(tex)[c] = make_float2(layers[c], o);
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += stride) {
+        int i, j;
+        if (LAYOUT == 0) {
+            i = (int)(o / W);
+            j = (int)(o - (size_t)i * W);
+        } else if (TF == 4) {
+            const size_t tile = o >> 3;
+            const int w = (int)(o & 7), ty = (int)(tile / tiles_x), tx = (int)(tile - (size_t)ty * tiles_x);
+            i = ty * 2 + ((w >> 1) & 1);
+            j = tx * 4 + ((w >> 2) & 1) * 2 + (w & 1);
         } else {
-            const float l0 = layers[c];
-            const float l1 = L > 1 ? layers[n_cells + c] : 0.0f;
-            const float l2 = L > 2 ? layers[2 * n_cells + c] : 0.0f;
-            reinterpret_cast<float4*>(tex)[c] = make_float4(l0, l1, l2, o);
+            const size_t tile = o >> 4;
+            const int w = (int)(o & 15), ty = (int)(tile / tiles_x), tx = (int)(tile - (size_t)ty * tiles_x);
+            i = ty * 4 + ((w >> 3) & 1) * 2 + ((w >> 1) & 1);
+            j = tx * 4 + ((w >> 2) & 1) * 2 + (w & 1);
+        }
+        const bool in = i < H && j < W;
+        const size_t c = (size_t)i * W + j;
+        const float ov = (in && occ && occ[c]) ? 1.0f : 0.0f;
+        if (TF == 2) {
+            reinterpret_cast<float2*>(tex)[o] = make_float2(in ? layers[c] : 0.0f, ov);
+        } else {
+            const float l0 = in ? layers[c] : 0.0f;
+            const float l1 = (in && L > 1) ? layers[n_cells + c] : 0.0f;
+            const float l2 = (in && L > 2) ? layers[2 * n_cells + c] : 0.0f;
+            reinterpret_cast<float4*>(tex)[o] = make_float4(l0, l1, l2, ov);
         }
     }
 }
@@ -281,18 +326,23 @@ extern "C" int uam_map_set_raster_device(uam_ctx* ctx, const float* d_layers, in
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = uam_pick_stream(ctx, stream);
     const int tf = (L == 1) ? 2 : 4;
-    const size_t n_cells = (size_t)H * W;
+    const int layout = ctx->raster_layout;
+    const int tile_h = (tf == 4) ? 2 : 4;
+    const int tiles_x = (W + 3) / 4, tiles_y = (H + tile_h - 1) / tile_h;
+    const size_t n_out = layout ? (size_t)tiles_x * tiles_y * 4 * tile_h : (size_t)H * W;
     // the old texels may still be read by kernels queued on other streams
     UAM_CUDA(ctx, cudaDeviceSynchronize());
-    UAM_TRY(uam_reserve(ctx, &ctx->d_tex, &ctx->tex_bytes, n_cells * tf * sizeof(float)));
+    UAM_TRY(uam_reserve(ctx, &ctx->d_tex, &ctx->tex_bytes, n_out * tf * sizeof(float)));
     const int grid = ctx->sm_count * 8;
-    if (tf == 2)
-        uam_k_pack_texels<2><<<grid, 256, 0, st>>>(d_layers, d_occupancy, L, n_cells, (float*)ctx->d_tex);
-    else
-        uam_k_pack_texels<4><<<grid, 256, 0, st>>>(d_layers, d_occupancy, L, n_cells, (float*)ctx->d_tex);
+    float* tex = (float*)ctx->d_tex;
+    if (tf == 2 && layout) uam_k_pack_texels<2, 1><<<grid, 256, 0, st>>>(d_layers, d_occupancy, L, H, W, tiles_x, n_out, tex);
+    else if (tf == 2) uam_k_pack_texels<2, 0><<<grid, 256, 0, st>>>(d_layers, d_occupancy, L, H, W, tiles_x, n_out, tex);
+    else if (layout) uam_k_pack_texels<4, 1><<<grid, 256, 0, st>>>(d_layers, d_occupancy, L, H, W, tiles_x, n_out, tex);
+    else uam_k_pack_texels<4, 0><<<grid, 256, 0, st>>>(d_layers, d_occupancy, L, H, W, tiles_x, n_out, tex);
     UAM_CHECK_LAUNCH(ctx, "uam_k_pack_texels");
     ctx->geo.x0 = x0; ctx->geo.dx = dx; ctx->geo.y0 = y0; ctx->geo.dy = dy;
     ctx->geo.H = H; ctx->geo.W = W; ctx->geo.L = L; ctx->geo.texel_floats = tf;
+    ctx->geo.layout = layout; ctx->geo.tiles_x = tiles_x; ctx->geo.tiles_y = tiles_y;
     ctx->has_raster = true;
     return UAM_OK;
 }

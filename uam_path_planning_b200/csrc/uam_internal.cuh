@@ -42,6 +42,9 @@ struct UamRasterGeo {
     double x0, dx, y0, dy;
     int H, W, L;
     int texel_floats;         // 2 (L == 1: layer, occupancy) or 4 (L in 2..3: l0, l1, l2, occupancy)
+    int layout;               // 0 = row-major texels, 1 = tiled (see uam_tex_index)
+    int tiles_x;              // tiled: tiles per tile-row (tile = 4 x 2 texels for float4, 4 x 4 for float2)
+    int tiles_y;
 };
 
 // ---- context --------------------------------------------------------------------------------------
@@ -53,6 +56,9 @@ struct uam_ctx {
     cudaEvent_t pipe_event[UAM_HOST_PIPE_DEPTH] = {};
     std::string err;
     uint64_t launches = 0;
+    // tuning knobs (uam_ctx_set_option / environment at ctx creation)
+    int raster_layout = 1;    // layout used by the next uam_map_set_raster*
+    int int_variant = 1;      // integral kernel: 0 = one lane per sample, 1 = lane pair per sample
 
     // device shape tables
     UamEdge* d_edges = nullptr;

@@ -26,6 +26,7 @@ struct UamRasterParams {
     double ms_x, ms_y;
     double spc;
     int H, W;
+    int tiles_x;          // tiled layout: tiles per tile-row
     float w0, w1, w2;
     int flags;
 };
@@ -33,6 +34,19 @@ struct UamRasterParams {
 template <int TF> struct UamTexel;
 template <> struct UamTexel<2> { typedef float2 T; };
 template <> struct UamTexel<4> { typedef float4 T; };
+
+// Texel address.  LAYOUT 0: row-major (H, W).  LAYOUT 1: tiled so that one 128-byte line is a compact 2-D block
+// and every 32-byte sector a 2 x 1 (float4) / 2 x 2 (float2) block -- a polyline crossing the raster in any
+// direction then touches ~1/3 fewer lines per warp instruction than with 8-texel-wide row-major lines, and the
+// 64-byte DRAM fetch granule is a 2 x 2 (float4) / 4 x 2 (float2) block instead of a 4 x 1 / 8 x 1 strip.
+//   float4: line = 4 wide x 2 tall:  ((i>>1) * tiles_x + (j>>2)) * 8  + ((j>>1)&1)*4 + (i&1)*2 + (j&1)
+//   float2: line = 4 wide x 4 tall:  ((i>>2) * tiles_x + (j>>2)) * 16 + ((i>>1)&1)*8 + ((j>>1)&1)*4 + (i&1)*2 + (j&1)
+template <int TF, int LAYOUT>
+__device__ __forceinline__ size_t uam_tex_index(int i, int j, int W, int tiles_x) {
+    if (LAYOUT == 0) return (size_t)i * W + j;
+    if (TF == 4) return ((size_t)(i >> 1) * tiles_x + (j >> 2)) * 8 + (((j >> 1) & 1) << 2) + ((i & 1) << 1) + (j & 1);
+    return ((size_t)(i >> 2) * tiles_x + (j >> 2)) * 16 + (((i >> 1) & 1) << 3) + (((j >> 1) & 1) << 2) + ((i & 1) << 1) + (j & 1);
+}
 
 // pixel coordinate of a world coordinate: (x - x0)/dx - 1/2 with a true division (oracle: pixel_coords)
 __device__ __forceinline__ double uam_pix(double x, double x0, double dx) {
@@ -49,30 +63,39 @@ __device__ __forceinline__ float uam_lerp2(float t00, float t01, float t10, floa
     return top + fy * (bot - top);
 }
 
-// Weighted bilinear penalty + nearest-cell occupancy at pixel coordinates (u, v) (unclamped on entry).
-template <int TF>
-__device__ __forceinline__ void uam_sample(const typename UamTexel<TF>::T* __restrict__ tex, const UamRasterParams& rp,
-                                           double u, double v, float& pen, bool& occ) {
-    typedef typename UamTexel<TF>::T T;
+// clamp pixel coordinates, split into cell + fp32 fraction (identical bits to the oracle's sample_uv)
+__device__ __forceinline__ void uam_cell_frac(const UamRasterParams& rp, double u, double v, int& i0, int& j0, float& fx,
+                                              float& fy) {
     u = fmin(fmax(u, 0.0), (double)(rp.W - 1));
     v = fmin(fmax(v, 0.0), (double)(rp.H - 1));
-    const int j0 = min((int)u, rp.W - 2);
-    const int i0 = min((int)v, rp.H - 2);
-    const float fx = (float)__dsub_rn(u, (double)j0);
-    const float fy = (float)__dsub_rn(v, (double)i0);
-    const T* r0 = tex + (size_t)i0 * rp.W + j0;
-    const T* r1 = r0 + rp.W;
-    const T t00 = __ldg(r0), t01 = __ldg(r0 + 1), t10 = __ldg(r1), t11 = __ldg(r1 + 1);
+    j0 = min((int)u, rp.W - 2);
+    i0 = min((int)v, rp.H - 2);
+    fx = (float)__dsub_rn(u, (double)j0);
+    fy = (float)__dsub_rn(v, (double)i0);
+}
+
+// Weighted bilinear penalty + nearest-cell occupancy at pixel coordinates (u, v): one lane fetches all 4 texels.
+template <int TF, int LAYOUT>
+__device__ __forceinline__ void uam_sample(const typename UamTexel<TF>::T* __restrict__ tex, const UamRasterParams& rp,
+                                           double u, double v, float& pen, bool& occ) {
+    int i0, j0;
+    float fx, fy;
+    uam_cell_frac(rp, u, v, i0, j0, fx, fy);
     const bool right = fx >= 0.5f, down = fy >= 0.5f;
-    if (TF == 2) {
-        const float2 a = *reinterpret_cast<const float2*>(&t00), b = *reinterpret_cast<const float2*>(&t01);
-        const float2 c = *reinterpret_cast<const float2*>(&t10), d = *reinterpret_cast<const float2*>(&t11);
+    if constexpr (TF == 2) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0, j0, rp.W, rp.tiles_x));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0, j0 + 1, rp.W, rp.tiles_x));
+        const float2 c = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0 + 1, j0, rp.W, rp.tiles_x));
+        const float2 d = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0 + 1, j0 + 1, rp.W, rp.tiles_x));
         pen = rp.w0 * uam_lerp2(a.x, b.x, c.x, d.x, fx, fy);
         const float o = down ? (right ? d.y : c.y) : (right ? b.y : a.y);
         occ = o != 0.0f;
     } else {
-        const float4 a = *reinterpret_cast<const float4*>(&t00), b = *reinterpret_cast<const float4*>(&t01);
-        const float4 c = *reinterpret_cast<const float4*>(&t10), d = *reinterpret_cast<const float4*>(&t11);
+        const float4* t4 = reinterpret_cast<const float4*>(tex);
+        const float4 a = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0, j0, rp.W, rp.tiles_x));
+        const float4 b = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0, j0 + 1, rp.W, rp.tiles_x));
+        const float4 c = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0 + 1, j0, rp.W, rp.tiles_x));
+        const float4 d = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0 + 1, j0 + 1, rp.W, rp.tiles_x));
         pen = rp.w0 * uam_lerp2(a.x, b.x, c.x, d.x, fx, fy) + rp.w1 * uam_lerp2(a.y, b.y, c.y, d.y, fx, fy) +
               rp.w2 * uam_lerp2(a.z, b.z, c.z, d.z, fx, fy);
         const float o = down ? (right ? d.w : c.w) : (right ? b.w : a.w);
@@ -80,8 +103,70 @@ __device__ __forceinline__ void uam_sample(const typename UamTexel<TF>::T* __res
     }
 }
 
+// Lane-pair form: the two lanes of a pair work on the SAME sample; lane `side` (0 = left, 1 = right) fetches the
+// texel column j0 + side (rows i0 and i0 + 1), lerps it in y, and the pair exchanges the column results with one
+// shuffle per layer.  The two lanes' loads of a row sit in the same 32-byte sector / 128-byte line, so each warp
+// load instruction touches half as many lines as when every lane fetches its own 2 x 2 footprint.
+// Must be called by all 32 lanes (shuffles); `active` masks lanes past the end.  pen is valid on both lanes.
+template <int TF, int LAYOUT>
+__device__ __forceinline__ void uam_sample_pair(const typename UamTexel<TF>::T* __restrict__ tex,
+                                                const UamRasterParams& rp, double u, double v, int side, bool active,
+                                                float& pen, bool& occ) {
+    int i0 = 0, j0 = 0;
+    float fx = 0.0f, fy = 0.0f;
+    float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, o = 0.0f;
+    if (active) {
+        uam_cell_frac(rp, u, v, i0, j0, fx, fy);
+        const bool down = fy >= 0.5f;
+        if constexpr (TF == 2) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0, j0 + side, rp.W, rp.tiles_x));
+            const float2 b = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0 + 1, j0 + side, rp.W, rp.tiles_x));
+            c0 = a.x + fy * (b.x - a.x);
+            o = down ? b.y : a.y;
+        } else {
+            const float4* t4 = reinterpret_cast<const float4*>(tex);
+            const float4 a = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0, j0 + side, rp.W, rp.tiles_x));
+            const float4 b = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0 + 1, j0 + side, rp.W, rp.tiles_x));
+            c0 = a.x + fy * (b.x - a.x);
+            c1 = a.y + fy * (b.y - a.y);
+            c2 = a.z + fy * (b.z - a.z);
+            o = down ? b.w : a.w;
+        }
+    }
+    const float p0 = __shfl_xor_sync(0xffffffffu, c0, 1);
+    // after the exchange: (left, right) = side ? (p, c) : (c, p)
+    float val = rp.w0 * (side ? p0 + fx * (c0 - p0) : c0 + fx * (p0 - c0));
+    if constexpr (TF == 4) {
+        const float p1 = __shfl_xor_sync(0xffffffffu, c1, 1);
+        const float p2 = __shfl_xor_sync(0xffffffffu, c2, 1);
+        val += rp.w1 * (side ? p1 + fx * (c1 - p1) : c1 + fx * (p1 - c1));
+        val += rp.w2 * (side ? p2 + fx * (c2 - p2) : c2 + fx * (p2 - c2));
+    }
+    pen = val;
+    // nearest cell column = j0 + (fx >= 0.5): only the lane holding that column reports occupancy
+    occ = active && ((fx >= 0.5f) == (side != 0)) && (o != 0.0f);
+}
+
+// ---- shared pieces of the path kernels -----------------------------------------------------------------------
+// length term of one waypoint j (reference quirk: segments 0..N-1 only + |z_0 - map.x_start|)
+__device__ __forceinline__ double uam_len_term(const double2* __restrict__ zp, int j, int N, const double2 p,
+                                               const UamRasterParams& rp) {
+    const bool len_smooth = (rp.flags & UAM_LENGTH_SMOOTH) != 0;
+    double acc = 0.0;
+    if (j < N) {
+        const double2 q = zp[j + 1];
+        const double d = uam_norm2r(__dsub_rn(q.x, p.x), __dsub_rn(q.y, p.y));
+        acc += len_smooth ? __dmul_rn(d, d) : d;
+    }
+    if (j == 0 && !(rp.flags & UAM_OWN_START)) {
+        const double d = uam_norm2r(__dsub_rn(p.x, rp.ms_x), __dsub_rn(p.y, rp.ms_y));
+        acc += len_smooth ? __dmul_rn(d, d) : d;
+    }
+    return acc;
+}
+
 // ---- waypoint mode ----------------------------------------------------------------------------------------
-template <int TF>
+template <int TF, int LAYOUT>
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
 uam_k_score_raster_wp(const double2* __restrict__ z, long long B, int Wp, UamRasterParams rp,
                       const typename UamTexel<TF>::T* __restrict__ tex, float* __restrict__ cost,
@@ -90,7 +175,6 @@ uam_k_score_raster_wp(const double2* __restrict__ z, long long B, int Wp, UamRas
     const long long warp0 = (long long)blockIdx.x * UAM_WARPS_PER_CTA + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * UAM_WARPS_PER_CTA;
     const int N = Wp - 2;
-    const bool len_smooth = (rp.flags & UAM_LENGTH_SMOOTH) != 0;
     for (long long path = warp0; path < B; path += nwarps) {
         const double2* zp = z + path * Wp;
         float pen_sum = 0.0f;
@@ -100,18 +184,10 @@ uam_k_score_raster_wp(const double2* __restrict__ z, long long B, int Wp, UamRas
             const double2 p = zp[j];
             float pen;
             bool occ;
-            uam_sample<TF>(tex, rp, uam_pix(p.x, rp.x0, rp.dx), uam_pix(p.y, rp.y0, rp.dy), pen, occ);
+            uam_sample<TF, LAYOUT>(tex, rp, uam_pix(p.x, rp.x0, rp.dx), uam_pix(p.y, rp.y0, rp.dy), pen, occ);
             pen_sum += pen;
             col = col || occ;
-            if (j < N) {    // segments 0..N-1 only: the last one is absent from the reference's length term
-                const double2 q = zp[j + 1];
-                const double d = uam_norm2r(__dsub_rn(q.x, p.x), __dsub_rn(q.y, p.y));
-                len_sum += len_smooth ? __dmul_rn(d, d) : d;
-            }
-            if (j == 0 && !(rp.flags & UAM_OWN_START)) {
-                const double d = uam_norm2r(__dsub_rn(p.x, rp.ms_x), __dsub_rn(p.y, rp.ms_y));
-                len_sum += len_smooth ? __dmul_rn(d, d) : d;
-            }
+            len_sum += uam_len_term(zp, j, N, p, rp);
         }
         pen_sum = uam_warp_sum(pen_sum);
         len_sum = uam_warp_sum(len_sum);
@@ -131,7 +207,8 @@ __host__ __device__ inline size_t uam_int_warp_smem(int Wp) {
     return (b + 15) & ~(size_t)15;
 }
 
-template <int TF>
+// PAIR = 0: one lane per sample (4 texel loads per lane).  PAIR = 1: two lanes per sample (uam_sample_pair).
+template <int TF, int LAYOUT, int PAIR>
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
 uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRasterParams rp,
                        const typename UamTexel<TF>::T* __restrict__ tex, float* __restrict__ cost,
@@ -151,7 +228,6 @@ uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRa
     const long long warp0 = (long long)blockIdx.x * wpc + warp;
     const long long nwarps = (long long)gridDim.x * wpc;
     const int N = Wp - 2;
-    const bool len_smooth = (rp.flags & UAM_LENGTH_SMOOTH) != 0;
 
     for (long long path = warp0; path < B; path += nwarps) {
         const double2* zp = z + path * Wp;
@@ -161,15 +237,7 @@ uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRa
             const double2 p = zp[j];
             sU[j] = uam_pix(p.x, rp.x0, rp.dx);
             sV[j] = uam_pix(p.y, rp.y0, rp.dy);
-            if (j < N) {
-                const double2 q = zp[j + 1];
-                const double d = uam_norm2r(__dsub_rn(q.x, p.x), __dsub_rn(q.y, p.y));
-                len_sum += len_smooth ? __dmul_rn(d, d) : d;
-            }
-            if (j == 0 && !(rp.flags & UAM_OWN_START)) {
-                const double d = uam_norm2r(__dsub_rn(p.x, rp.ms_x), __dsub_rn(p.y, rp.ms_y));
-                len_sum += len_smooth ? __dmul_rn(d, d) : d;
-            }
+            len_sum += uam_len_term(zp, j, N, p, rp);
         }
         __syncwarp();
         // B: per-segment sample count, step and exclusive prefix; pseudo-segment Wp-1 = the goal waypoint
@@ -210,20 +278,44 @@ uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRa
         long long p0 = 0, p1 = sP[1];
         double kU = sU[0], kV = sV[0], kSU = sSU[0], kSV = sSV[0];
         float kIS = sIS[0];
-        for (long long t = lane; t < T; t += 32) {
-            if (t >= p1) {
-                do { ++k; p1 = sP[k + 1]; } while (t >= p1);
-                p0 = sP[k];
-                kU = sU[k]; kV = sV[k]; kSU = sSU[k]; kSV = sSV[k]; kIS = sIS[k];
+        if (PAIR) {
+            const int side = lane & 1;
+            for (long long tb = 0; tb < T; tb += 16) {
+                const long long t = tb + (lane >> 1);
+                const bool active = t < T;
+                double u = 0.0, v = 0.0;
+                if (active) {
+                    if (t >= p1) {
+                        do { ++k; p1 = sP[k + 1]; } while (t >= p1);
+                        p0 = sP[k];
+                        kU = sU[k]; kV = sV[k]; kSU = sSU[k]; kSV = sSV[k]; kIS = sIS[k];
+                    }
+                    const double s = (double)(t - p0);
+                    u = __dadd_rn(kU, __dmul_rn(s, kSU));
+                    v = __dadd_rn(kV, __dmul_rn(s, kSV));
+                }
+                float pen;
+                bool occ;
+                uam_sample_pair<TF, LAYOUT>(tex, rp, u, v, side, active, pen, occ);
+                if (active && side == 0) acc += pen * kIS;
+                col = col || occ;
             }
-            const double s = (double)(t - p0);
-            const double u = __dadd_rn(kU, __dmul_rn(s, kSU));
-            const double v = __dadd_rn(kV, __dmul_rn(s, kSV));
-            float pen;
-            bool occ;
-            uam_sample<TF>(tex, rp, u, v, pen, occ);
-            acc += pen * kIS;
-            col = col || occ;
+        } else {
+            for (long long t = lane; t < T; t += 32) {
+                if (t >= p1) {
+                    do { ++k; p1 = sP[k + 1]; } while (t >= p1);
+                    p0 = sP[k];
+                    kU = sU[k]; kV = sV[k]; kSU = sSU[k]; kSV = sSV[k]; kIS = sIS[k];
+                }
+                const double s = (double)(t - p0);
+                const double u = __dadd_rn(kU, __dmul_rn(s, kSU));
+                const double v = __dadd_rn(kV, __dmul_rn(s, kSV));
+                float pen;
+                bool occ;
+                uam_sample<TF, LAYOUT>(tex, rp, u, v, pen, occ);
+                acc += pen * kIS;
+                col = col || occ;
+            }
         }
         acc = uam_warp_sum(acc);
         len_sum = uam_warp_sum(len_sum);
@@ -250,6 +342,7 @@ int uam_raster_prepare(uam_ctx* ctx, int64_t B, int N, const double* h_p, int n_
     rp->ms_x = prm.ms_x; rp->ms_y = prm.ms_y;
     rp->spc = spc;
     rp->H = ctx->geo.H; rp->W = ctx->geo.W;
+    rp->tiles_x = ctx->geo.tiles_x;
     rp->w0 = (float)prm.w[0];
     rp->w1 = ctx->geo.L > 1 ? (float)prm.w[1] : 0.0f;
     rp->w2 = ctx->geo.L > 2 ? (float)prm.w[2] : 0.0f;
@@ -257,35 +350,43 @@ int uam_raster_prepare(uam_ctx* ctx, int64_t B, int N, const double* h_p, int n_
     return UAM_OK;
 }
 
-int uam_raster_launch(uam_ctx* ctx, const double* d_z, int64_t B, int N, const UamRasterParams& rp, float* d_cost,
-                      uint8_t* d_collide, long long* d_nsamp, cudaStream_t st) {
-    const int Wp = N + 2;
-    const int tf = ctx->geo.texel_floats;
-    const double2* z = reinterpret_cast<const double2*>(d_z);
+template <int TF, int LAYOUT>
+int uam_raster_launch_t(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const UamRasterParams& rp, float* d_cost,
+                        uint8_t* d_collide, long long* d_nsamp, cudaStream_t st) {
+    typedef typename UamTexel<TF>::T T;
+    const T* tex = (const T*)ctx->d_tex;
     if (rp.spc == 0.0) {
         const long long ctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
-        if (tf == 2)
-            uam_k_score_raster_wp<2><<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, (const float2*)ctx->d_tex, d_cost, d_collide, d_nsamp);
-        else
-            uam_k_score_raster_wp<4><<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, (const float4*)ctx->d_tex, d_cost, d_collide, d_nsamp);
+        uam_k_score_raster_wp<TF, LAYOUT><<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
         UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_wp");
         return UAM_OK;
     }
     const size_t per_warp = uam_int_warp_smem(Wp);
     const size_t budget = 200 * 1024;
-    if (per_warp > budget) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "N = %d waypoints per path is too many for integral mode", N);
+    if (per_warp > budget) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "N = %d waypoints per path is too many for integral mode", Wp - 2);
     const int wpc = (int)std::max<size_t>(1, std::min<size_t>(UAM_WARPS_PER_CTA, budget / per_warp));
     const size_t smem = per_warp * wpc;
     const long long ctas = std::min<long long>((B + wpc - 1) / wpc, (long long)ctx->sm_count * 16);
-    if (tf == 2) {
-        if (smem > 48 * 1024) UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_score_raster_int<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uam_k_score_raster_int<2><<<(unsigned)ctas, wpc * 32, smem, st>>>(z, B, Wp, rp, (const float2*)ctx->d_tex, d_cost, d_collide, d_nsamp);
+    if (ctx->int_variant == 0) {
+        if (smem > 48 * 1024) UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_score_raster_int<TF, LAYOUT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uam_k_score_raster_int<TF, LAYOUT, 0><<<(unsigned)ctas, wpc * 32, smem, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
     } else {
-        if (smem > 48 * 1024) UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_score_raster_int<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uam_k_score_raster_int<4><<<(unsigned)ctas, wpc * 32, smem, st>>>(z, B, Wp, rp, (const float4*)ctx->d_tex, d_cost, d_collide, d_nsamp);
+        if (smem > 48 * 1024) UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_score_raster_int<TF, LAYOUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uam_k_score_raster_int<TF, LAYOUT, 1><<<(unsigned)ctas, wpc * 32, smem, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
     }
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_int");
     return UAM_OK;
+}
+
+int uam_raster_launch(uam_ctx* ctx, const double* d_z, int64_t B, int N, const UamRasterParams& rp, float* d_cost,
+                      uint8_t* d_collide, long long* d_nsamp, cudaStream_t st) {
+    const int Wp = N + 2;
+    const double2* z = reinterpret_cast<const double2*>(d_z);
+    const int tf = ctx->geo.texel_floats, lay = ctx->geo.layout;
+    if (tf == 2) return lay ? uam_raster_launch_t<2, 1>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st)
+                            : uam_raster_launch_t<2, 0>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st);
+    return lay ? uam_raster_launch_t<4, 1>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st)
+               : uam_raster_launch_t<4, 0>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st);
 }
 
 // ---- best candidate: min over b of (float bits of cost << 32 | global index) ----------------------------------

@@ -78,6 +78,13 @@ class Engine:
     def sync(self):
         self._check(self._lib.uam_sync(self._h))
 
+    OPTIONS = {'raster_layout': 1, 'integral_variant': 2, 'l2_fetch_granularity': 3}
+
+    def set_option(self, name: str, value: int):
+        """Tuning knobs of include/uam_b200.h (UAM_OPT_*): raster_layout (0 row-major, 1 tiled; applies to the next
+        set_raster), integral_variant (0 one lane per sample, 1 lane pair), l2_fetch_granularity (32/64/128)."""
+        self._check(self._lib.uam_ctx_set_option(self._h, self.OPTIONS[name], int(value)))
+
     def _tensor_args(self, *tensors):
         import torch
         for t in tensors:

@@ -32,10 +32,13 @@ def load_dem_mask(image, threshold: float = 0.0, engine: Optional[Engine] = None
 class RasterMap:
     """Cost layers + occupancy of a ``RegionMap`` on one GPU, and the raster path scorer on top of them."""
 
-    def __init__(self, H: int, W: int, geo: Tuple[float, float, float, float], device: Optional[int] = None):
+    def __init__(self, H: int, W: int, geo: Tuple[float, float, float, float], device: Optional[int] = None,
+                 options: Optional[dict] = None):
         self.H, self.W = int(H), int(W)
         self.geo = tuple(float(v) for v in geo)
         self.engine = Engine(device)
+        for k, v in (options or {}).items():
+            self.engine.set_option(k, v)
         self.layers = None        # (L,H,W) float32 CUDA tensor
         self.occupancy = None     # (H,W) uint8 CUDA tensor
         self.clearance = None     # (H,W) float32 CUDA tensor (distance to the nearest occupied cell)
@@ -44,9 +47,9 @@ class RasterMap:
     # ---- build ---------------------------------------------------------------------------------------------
     @classmethod
     def from_map(cls, m: RegionMap, H: int, W: int, geo, enlargement: float = 0.0, device: Optional[int] = None,
-                 clearance: bool = False) -> 'RasterMap':
+                 clearance: bool = False, options: Optional[dict] = None) -> 'RasterMap':
         """Rasterise the map's regions and obstacles at the cell centres (map rebuild, config 4)."""
-        rm = cls(H, W, geo, device)
+        rm = cls(H, W, geo, device, options)
         eng = rm.engine
         eng.set_shapes(m.obstacles, m._region_lists())
         rm.occupancy = eng.rasterize_occupancy(rm.H, rm.W, rm.geo)
@@ -57,10 +60,11 @@ class RasterMap:
         return rm
 
     @classmethod
-    def from_arrays(cls, layers, geo, occupancy=None, device: Optional[int] = None) -> 'RasterMap':
+    def from_arrays(cls, layers, geo, occupancy=None, device: Optional[int] = None,
+                    options: Optional[dict] = None) -> 'RasterMap':
         """Adopt existing rasters (numpy or CUDA tensors)."""
         L, H, W = layers.shape
-        rm = cls(H, W, geo, device)
+        rm = cls(H, W, geo, device, options)
         rm.engine.set_raster(layers, rm.geo, occupancy)
         if _is_tensor(layers):
             rm.layers, rm.occupancy = layers, occupancy
