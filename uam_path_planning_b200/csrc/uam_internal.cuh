@@ -58,7 +58,7 @@ struct uam_ctx {
     uint64_t launches = 0;
     // tuning knobs (uam_ctx_set_option / environment at ctx creation)
     int raster_layout = 1;    // layout used by the next uam_map_set_raster*
-    int int_variant = 1;      // integral kernel: 0 = one lane per sample, 1 = lane pair per sample
+    int int_variant = 0;      // integral kernel: 0 = one lane per sample (measured best), 1 = lane pair per sample
 
     // device shape tables
     UamEdge* d_edges = nullptr;
