@@ -83,7 +83,9 @@ int uam_sync(uam_ctx* ctx);
 /* tuning knobs (defaults are the measured-best settings) */
 enum {
     UAM_OPT_RASTER_LAYOUT = 1,        /* texel layout used by the next uam_map_set_raster*: 0 row-major, 1 tiled */
-    UAM_OPT_INTEGRAL_VARIANT = 2,     /* integral-mode kernel: 0 one lane per sample, 1 lane pair per sample */
+    UAM_OPT_INTEGRAL_VARIANT = 2,     /* integral mode: -1 auto (default: 2 for batches of >= 2^18 segments, else 0),
+                                         0 warp per path / lane per sample, 1 lane pair per sample,
+                                         2 segments binned by raster tile, warp per 32 sorted segments */
     UAM_OPT_L2_FETCH_GRANULARITY = 3  /* cudaLimitMaxL2FetchGranularity for this device: 32, 64 or 128 bytes */
 };
 int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value);

@@ -329,7 +329,7 @@ def _random_paths(rng, B, Wp, geo, H, W, spill=0.0):
 
 @pytest.mark.parametrize('L', [1, 2, 3])
 @pytest.mark.parametrize('spc', [0.0, 1.0, 0.37, 2.5])
-@pytest.mark.parametrize('layout,variant', [(1, 1), (0, 0), (1, 0), (0, 1)])
+@pytest.mark.parametrize('layout,variant', [(1, 1), (0, 0), (1, 0), (0, 1), (1, 2), (0, 2)])
 def test_score_paths_raster_vs_oracle(uam, torch, L, spc, layout, variant):
     """Every texel layout (row-major / tiled; H, W not multiples of the tile) and integral-kernel variant (one lane or
     a lane pair per sample) against the oracle."""

@@ -1,4 +1,5 @@
 // Context, error handling, map uploads (shape tables and rasters) of libuam_b200.so.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -105,7 +106,7 @@ extern "C" int uam_ctx_create(int device, uam_ctx** out) {
     }
     // tuning knobs from the environment (bench A/B runs); uam_ctx_set_option overrides
     if (const char* e = getenv("UAM_RASTER_LAYOUT")) ctx->raster_layout = atoi(e) ? 1 : 0;
-    if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = std::min(2, std::max(-1, atoi(e)));
     if (const char* e = getenv("UAM_L2_FETCH_GRANULARITY")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
     *out = ctx;
     return UAM_OK;
@@ -119,7 +120,7 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             ctx->raster_layout = (int)value;
             return UAM_OK;
         case UAM_OPT_INTEGRAL_VARIANT:
-            if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "integral variant must be 0 or 1");
+            if (value < -1 || value > 2) return uam_fail(ctx, UAM_ERR_INVALID, "integral variant must be -1 (auto), 0, 1 or 2");
             ctx->int_variant = (int)value;
             return UAM_OK;
         case UAM_OPT_L2_FETCH_GRANULARITY:
@@ -141,6 +142,7 @@ extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
     cudaFree(ctx->d_psic);
     cudaFree(ctx->d_tex);
     cudaFree(ctx->d_scratch);
+    for (int i = 0; i <= UAM_HOST_PIPE_DEPTH; ++i) cudaFree(ctx->d_bin_scratch[i]);
     for (int i = 0; i < UAM_HOST_PIPE_DEPTH; ++i) {
         cudaFree(ctx->d_stage_in[i]);
         cudaFree(ctx->d_stage_out[i]);
@@ -330,6 +332,7 @@ extern "C" int uam_map_set_raster_device(uam_ctx* ctx, const float* d_layers, in
     const int tile_h = (tf == 4) ? 2 : 4;
     const int tiles_x = (W + 3) / 4, tiles_y = (H + tile_h - 1) / tile_h;
     const size_t n_out = layout ? (size_t)tiles_x * tiles_y * 4 * tile_h : (size_t)H * W;
+    if (n_out >= 0xffffffffull) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "raster has 2^32 or more texels");
     // the old texels may still be read by kernels queued on other streams
     UAM_CUDA(ctx, cudaDeviceSynchronize());
     UAM_TRY(uam_reserve(ctx, &ctx->d_tex, &ctx->tex_bytes, n_out * tf * sizeof(float)));

@@ -58,7 +58,8 @@ struct uam_ctx {
     uint64_t launches = 0;
     // tuning knobs (uam_ctx_set_option / environment at ctx creation)
     int raster_layout = 1;    // layout used by the next uam_map_set_raster*
-    int int_variant = 0;      // integral kernel: 0 = one lane per sample (measured best), 1 = lane pair per sample
+    int int_variant = -1;     // integral mode: -1 = auto (2 for large batches, else 0); 0 = warp per path, lane per sample; 1 = lane pair per sample;
+                              // 2 = segments binned by raster tile, warp per segment (L2-resident raster)
 
     // device shape tables
     UamEdge* d_edges = nullptr;
@@ -84,8 +85,10 @@ struct uam_ctx {
     size_t stage_out_bytes[UAM_HOST_PIPE_DEPTH] = {};
     void* h_stage_out[UAM_HOST_PIPE_DEPTH] = {};   // pinned
     size_t h_stage_out_bytes[UAM_HOST_PIPE_DEPTH] = {};
-    void* d_scratch = nullptr;
+    void* d_scratch = nullptr;          // EDT
     size_t scratch_bytes = 0;
+    void* d_bin_scratch[UAM_HOST_PIPE_DEPTH + 1] = {};   // binned raster scorer: [0] caller stream, [1..] pipeline stages
+    size_t bin_scratch_bytes[UAM_HOST_PIPE_DEPTH + 1] = {};
 };
 
 int uam_fail(uam_ctx* ctx, int code, const char* fmt, ...);

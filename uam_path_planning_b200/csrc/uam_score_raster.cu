@@ -1,18 +1,24 @@
 // Raster path scorer: the reference's cost functional (problem.py:38-44,130-146) with the analytic penalty
 // replaced by a bilinear lookup in the cost rasters, and Map.collides replaced by nearest-cell occupancy.
 //
-// HBM layout: one texel per cell, layers interleaved with the occupancy flag (float2 for L = 1, float4 for
-// L = 2..3), row-major (H, W): one bilinear tap = two 2-texel runs (2 x 16 B or 2 x 32 B) instead of
-// 4 x (L + 1) scattered words.
+// HBM layout: one texel per cell, the L cost layers interleaved with the occupancy flag (float2 for L = 1, float4
+// for L = 2..3), either row-major or tiled (uam_tex_row / uam_tex_col): one bilinear tap = 4 texel loads of 8/16 B.
 //
-// One warp per candidate path.
-//   waypoint mode  (samples_per_cell == 0): lanes stride the N+2 waypoints -- the reference's sampling.
-//   integral mode  (samples_per_cell  > 0): every segment k gets S_k = max(1, ceil(|dz_k|_cells * spc))
-//       left-endpoint samples; the path's samples are flattened and lanes stride the flat sample index, so 32
-//       consecutive samples of one polyline (a compact footprint in the raster) are fetched together.
-// World -> pixel coordinates, S_k and the sample positions are fp64 in a fixed operation order (identical bits
-// to the oracle: same cells, same occupancy lookups, same sample counts); bilinear weights, texel arithmetic and
-// the penalty sum are fp32; the length term is fp64.  Per-path sums finish with warp-shuffle reductions.
+// Sampling modes
+//   waypoint mode  (samples_per_cell == 0): one sample per waypoint -- the reference's sampling; warp per path,
+//                  lanes stride the N+2 waypoints.
+//   integral mode  (samples_per_cell  > 0): segment k gets S_k = max(1, ceil(|dz_k|_cells * spc)) left-endpoint
+//                  samples (mean per segment).  Three kernels, selected by UAM_OPT_INTEGRAL_VARIANT:
+//       0  warp per path; the path's samples are flattened, lanes stride the flat sample index
+//       1  as 0 with a lane PAIR per sample (kept for comparison; slower)
+//       2  binned: the batch's segments are counting-sorted by raster bin, a warp scores 32 consecutive sorted
+//          segments with the same flat loop, a last kernel adds the per-segment partials per path.  The warps in
+//          flight then sample the same few bins and the raster streams through L2 about once per batch instead of
+//          once per path corridor.
+// World -> pixel coordinates, S_k and the sample positions are fp64 in a fixed operation order (identical bits to
+// the oracle: same cells, same occupancy lookups, same sample counts); bilinear weights, texel arithmetic and the
+// penalty sums are fp32; the length term is fp64.  Sums finish with warp-shuffle reductions in a fixed order
+// (bit-reproducible; no floating-point atomics).
 #include <algorithm>
 
 #include "uam_internal.cuh"
@@ -26,7 +32,7 @@ struct UamRasterParams {
     double ms_x, ms_y;
     double spc;
     int H, W;
-    int tiles_x;          // tiled layout: tiles per tile-row
+    unsigned row_stride;  // tiled layout: texels per tile-row (tiles_x * texels per tile); row-major: W
     float w0, w1, w2;
     int flags;
 };
@@ -35,17 +41,23 @@ template <int TF> struct UamTexel;
 template <> struct UamTexel<2> { typedef float2 T; };
 template <> struct UamTexel<4> { typedef float4 T; };
 
-// Texel address.  LAYOUT 0: row-major (H, W).  LAYOUT 1: tiled so that one 128-byte line is a compact 2-D block
-// and every 32-byte sector a 2 x 1 (float4) / 2 x 2 (float2) block -- a polyline crossing the raster in any
-// direction then touches ~1/3 fewer lines per warp instruction than with 8-texel-wide row-major lines, and the
-// 64-byte DRAM fetch granule is a 2 x 2 (float4) / 4 x 2 (float2) block instead of a 4 x 1 / 8 x 1 strip.
+// Texel address = uam_tex_row(i) + uam_tex_col(j)  (both layouts are separable).
+// LAYOUT 0: row-major (H, W).  LAYOUT 1: tiled so that one 128-byte line is a compact 2-D block and every 32-byte
+// sector a 2 x 1 (float4) / 2 x 2 (float2) block:
 //   float4: line = 4 wide x 2 tall:  ((i>>1) * tiles_x + (j>>2)) * 8  + ((j>>1)&1)*4 + (i&1)*2 + (j&1)
 //   float2: line = 4 wide x 4 tall:  ((i>>2) * tiles_x + (j>>2)) * 16 + ((i>>1)&1)*8 + ((j>>1)&1)*4 + (i&1)*2 + (j&1)
+// Texel indices are 32-bit (uam_map_set_raster refuses rasters with 2^32 or more texels).
 template <int TF, int LAYOUT>
-__device__ __forceinline__ size_t uam_tex_index(int i, int j, int W, int tiles_x) {
-    if (LAYOUT == 0) return (size_t)i * W + j;
-    if (TF == 4) return ((size_t)(i >> 1) * tiles_x + (j >> 2)) * 8 + (((j >> 1) & 1) << 2) + ((i & 1) << 1) + (j & 1);
-    return ((size_t)(i >> 2) * tiles_x + (j >> 2)) * 16 + (((i >> 1) & 1) << 3) + (((j >> 1) & 1) << 2) + ((i & 1) << 1) + (j & 1);
+__device__ __forceinline__ unsigned uam_tex_row(unsigned i, unsigned row_stride) {
+    if (LAYOUT == 0) return i * row_stride;
+    if (TF == 4) return (i >> 1) * row_stride + ((i & 1u) << 1);
+    return (i >> 2) * row_stride + ((i & 2u) << 2) + ((i & 1u) << 1);
+}
+template <int TF, int LAYOUT>
+__device__ __forceinline__ unsigned uam_tex_col(unsigned j) {
+    if (LAYOUT == 0) return j;
+    if (TF == 4) return 2u * j - (j & 1u);                  // (j>>2)*8 + ((j>>1)&1)*4 + (j&1)
+    return ((j >> 2) << 4) + ((j & 2u) << 1) + (j & 1u);
 }
 
 // pixel coordinate of a world coordinate: (x - x0)/dx - 1/2 with a true division (oracle: pixel_coords)
@@ -63,15 +75,56 @@ __device__ __forceinline__ float uam_lerp2(float t00, float t01, float t10, floa
     return top + fy * (bot - top);
 }
 
-// clamp pixel coordinates, split into cell + fp32 fraction (identical bits to the oracle's sample_uv)
-__device__ __forceinline__ void uam_cell_frac(const UamRasterParams& rp, double u, double v, int& i0, int& j0, float& fx,
-                                              float& fy) {
-    u = fmin(fmax(u, 0.0), (double)(rp.W - 1));
-    v = fmin(fmax(v, 0.0), (double)(rp.H - 1));
-    j0 = min((int)u, rp.W - 2);
-    i0 = min((int)v, rp.H - 2);
-    fx = (float)__dsub_rn(u, (double)j0);
-    fy = (float)__dsub_rn(v, (double)i0);
+// fp64 -> fp32 with clamping to [0, 1] in one conversion
+__device__ __forceinline__ float uam_sat_f32(double x) {
+    float r;
+    asm("cvt.rn.sat.f32.f64 %0, %1;" : "=f"(r) : "d"(x));
+    return r;
+}
+
+// Cell + fp32 fraction of a pixel coordinate.  Same result as the oracle's clamp(u, 0, n-1); j0 = min(floor(u),
+// n-2); f = float32(u - j0): for u < 0 the cell clamps to 0 and the saturating conversion gives f = 0, for
+// u > n-1 the cell clamps to n-2 and f saturates to 1.
+__device__ __forceinline__ void uam_cell_frac1(double u, int n, int& j0, float& f) {
+    j0 = min(max(__double2int_rd(u), 0), n - 2);
+    f = uam_sat_f32(__dsub_rn(u, (double)j0));
+}
+
+// A bilinear tap split into its load half and its arithmetic half, so that a loop can issue the loads of several
+// samples before it consumes the first one.
+template <int TF>
+struct UamTap {
+    typename UamTexel<TF>::T a, b, c, d;   // (i0,j0) (i0,j0+1) (i0+1,j0) (i0+1,j0+1)
+    float fx, fy;
+};
+
+template <int TF, int LAYOUT>
+__device__ __forceinline__ void uam_tap_load(const typename UamTexel<TF>::T* __restrict__ tex, const UamRasterParams& rp,
+                                             double u, double v, UamTap<TF>& t) {
+    int i0, j0;
+    uam_cell_frac1(u, rp.W, j0, t.fx);
+    uam_cell_frac1(v, rp.H, i0, t.fy);
+    const unsigned r0 = uam_tex_row<TF, LAYOUT>(i0, rp.row_stride), r1 = uam_tex_row<TF, LAYOUT>(i0 + 1, rp.row_stride);
+    const unsigned c0 = uam_tex_col<TF, LAYOUT>(j0), c1 = uam_tex_col<TF, LAYOUT>(j0 + 1);
+    t.a = __ldg(tex + (r0 + c0));
+    t.b = __ldg(tex + (r0 + c1));
+    t.c = __ldg(tex + (r1 + c0));
+    t.d = __ldg(tex + (r1 + c1));
+}
+
+template <int TF>
+__device__ __forceinline__ void uam_tap_eval(const UamRasterParams& rp, const UamTap<TF>& t, float& pen, bool& occ) {
+    const bool right = t.fx >= 0.5f, down = t.fy >= 0.5f;
+    if constexpr (TF == 2) {
+        pen = rp.w0 * uam_lerp2(t.a.x, t.b.x, t.c.x, t.d.x, t.fx, t.fy);
+        const float o = down ? (right ? t.d.y : t.c.y) : (right ? t.b.y : t.a.y);
+        occ = o != 0.0f;
+    } else {
+        pen = rp.w0 * uam_lerp2(t.a.x, t.b.x, t.c.x, t.d.x, t.fx, t.fy) + rp.w1 * uam_lerp2(t.a.y, t.b.y, t.c.y, t.d.y, t.fx, t.fy) +
+              rp.w2 * uam_lerp2(t.a.z, t.b.z, t.c.z, t.d.z, t.fx, t.fy);
+        const float o = down ? (right ? t.d.w : t.c.w) : (right ? t.b.w : t.a.w);
+        occ = o != 0.0f;
+    }
 }
 
 // Weighted bilinear penalty + nearest-cell occupancy at pixel coordinates (u, v): one lane fetches all 4 texels.
@@ -80,22 +133,20 @@ __device__ __forceinline__ void uam_sample(const typename UamTexel<TF>::T* __res
                                            double u, double v, float& pen, bool& occ) {
     int i0, j0;
     float fx, fy;
-    uam_cell_frac(rp, u, v, i0, j0, fx, fy);
+    uam_cell_frac1(u, rp.W, j0, fx);
+    uam_cell_frac1(v, rp.H, i0, fy);
     const bool right = fx >= 0.5f, down = fy >= 0.5f;
+    const unsigned r0 = uam_tex_row<TF, LAYOUT>(i0, rp.row_stride), r1 = uam_tex_row<TF, LAYOUT>(i0 + 1, rp.row_stride);
+    const unsigned c0 = uam_tex_col<TF, LAYOUT>(j0), c1 = uam_tex_col<TF, LAYOUT>(j0 + 1);
     if constexpr (TF == 2) {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0, j0, rp.W, rp.tiles_x));
-        const float2 b = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0, j0 + 1, rp.W, rp.tiles_x));
-        const float2 c = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0 + 1, j0, rp.W, rp.tiles_x));
-        const float2 d = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0 + 1, j0 + 1, rp.W, rp.tiles_x));
+        const float2* t2 = reinterpret_cast<const float2*>(tex);
+        const float2 a = __ldg(t2 + r0 + c0), b = __ldg(t2 + r0 + c1), c = __ldg(t2 + r1 + c0), d = __ldg(t2 + r1 + c1);
         pen = rp.w0 * uam_lerp2(a.x, b.x, c.x, d.x, fx, fy);
         const float o = down ? (right ? d.y : c.y) : (right ? b.y : a.y);
         occ = o != 0.0f;
     } else {
         const float4* t4 = reinterpret_cast<const float4*>(tex);
-        const float4 a = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0, j0, rp.W, rp.tiles_x));
-        const float4 b = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0, j0 + 1, rp.W, rp.tiles_x));
-        const float4 c = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0 + 1, j0, rp.W, rp.tiles_x));
-        const float4 d = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0 + 1, j0 + 1, rp.W, rp.tiles_x));
+        const float4 a = __ldg(t4 + r0 + c0), b = __ldg(t4 + r0 + c1), c = __ldg(t4 + r1 + c0), d = __ldg(t4 + r1 + c1);
         pen = rp.w0 * uam_lerp2(a.x, b.x, c.x, d.x, fx, fy) + rp.w1 * uam_lerp2(a.y, b.y, c.y, d.y, fx, fy) +
               rp.w2 * uam_lerp2(a.z, b.z, c.z, d.z, fx, fy);
         const float o = down ? (right ? d.w : c.w) : (right ? b.w : a.w);
@@ -105,28 +156,28 @@ __device__ __forceinline__ void uam_sample(const typename UamTexel<TF>::T* __res
 
 // Lane-pair form: the two lanes of a pair work on the SAME sample; lane `side` (0 = left, 1 = right) fetches the
 // texel column j0 + side (rows i0 and i0 + 1), lerps it in y, and the pair exchanges the column results with one
-// shuffle per layer.  The two lanes' loads of a row sit in the same 32-byte sector / 128-byte line, so each warp
-// load instruction touches half as many lines as when every lane fetches its own 2 x 2 footprint.
-// Must be called by all 32 lanes (shuffles); `active` masks lanes past the end.  pen is valid on both lanes.
+// shuffle per layer.  Must be called by all 32 lanes (shuffles); `active` masks lanes past the end.
 template <int TF, int LAYOUT>
 __device__ __forceinline__ void uam_sample_pair(const typename UamTexel<TF>::T* __restrict__ tex,
                                                 const UamRasterParams& rp, double u, double v, int side, bool active,
                                                 float& pen, bool& occ) {
-    int i0 = 0, j0 = 0;
     float fx = 0.0f, fy = 0.0f;
     float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, o = 0.0f;
     if (active) {
-        uam_cell_frac(rp, u, v, i0, j0, fx, fy);
+        int i0, j0;
+        uam_cell_frac1(u, rp.W, j0, fx);
+        uam_cell_frac1(v, rp.H, i0, fy);
         const bool down = fy >= 0.5f;
+        const unsigned r0 = uam_tex_row<TF, LAYOUT>(i0, rp.row_stride), r1 = uam_tex_row<TF, LAYOUT>(i0 + 1, rp.row_stride);
+        const unsigned cc = uam_tex_col<TF, LAYOUT>(j0 + side);
         if constexpr (TF == 2) {
-            const float2 a = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0, j0 + side, rp.W, rp.tiles_x));
-            const float2 b = __ldg(reinterpret_cast<const float2*>(tex) + uam_tex_index<TF, LAYOUT>(i0 + 1, j0 + side, rp.W, rp.tiles_x));
+            const float2* t2 = reinterpret_cast<const float2*>(tex);
+            const float2 a = __ldg(t2 + r0 + cc), b = __ldg(t2 + r1 + cc);
             c0 = a.x + fy * (b.x - a.x);
             o = down ? b.y : a.y;
         } else {
             const float4* t4 = reinterpret_cast<const float4*>(tex);
-            const float4 a = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0, j0 + side, rp.W, rp.tiles_x));
-            const float4 b = __ldg(t4 + uam_tex_index<TF, LAYOUT>(i0 + 1, j0 + side, rp.W, rp.tiles_x));
+            const float4 a = __ldg(t4 + r0 + cc), b = __ldg(t4 + r1 + cc);
             c0 = a.x + fy * (b.x - a.x);
             c1 = a.y + fy * (b.y - a.y);
             c2 = a.z + fy * (b.z - a.z);
@@ -165,6 +216,37 @@ __device__ __forceinline__ double uam_len_term(const double2* __restrict__ zp, i
     return acc;
 }
 
+// sample count of a segment with pixel-space extent (dU, dV)
+__device__ __forceinline__ double uam_seg_samples(double dU, double dV, double spc) {
+    double Sd = fmax(1.0, ceil(__dmul_rn(uam_norm2r(dU, dV), spc)));
+    if (!(Sd <= UAM_MAX_SAMPLES_PER_SEGMENT)) Sd = UAM_MAX_SAMPLES_PER_SEGMENT;
+    return Sd;
+}
+
+// Per-warp segment table in shared memory, walked by the flat sample loop.
+struct UamSegTable {
+    double* U;
+    double* V;
+    double* SU;
+    double* SV;
+    int* P;          // exclusive prefix of the sample counts, n + 1 entries
+    float* IS;       // 1 / S_k
+};
+__host__ __device__ inline size_t uam_seg_table_bytes(int n) {
+    size_t b = (size_t)n * 8 * 4 + (size_t)(n + 1) * 4 + (size_t)n * 4;
+    return (b + 15) & ~(size_t)15;
+}
+__device__ __forceinline__ UamSegTable uam_seg_table(unsigned char* base, int n) {
+    UamSegTable t;
+    t.U = reinterpret_cast<double*>(base);
+    t.V = t.U + n;
+    t.SU = t.V + n;
+    t.SV = t.SU + n;
+    t.P = reinterpret_cast<int*>(t.SV + n);
+    t.IS = reinterpret_cast<float*>(t.P + n + 1);
+    return t;
+}
+
 // ---- waypoint mode ----------------------------------------------------------------------------------------
 template <int TF, int LAYOUT>
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
@@ -200,14 +282,10 @@ uam_k_score_raster_wp(const double2* __restrict__ z, long long B, int Wp, UamRas
     }
 }
 
-// ---- integral mode ----------------------------------------------------------------------------------------
-// Per-warp shared memory: U[Wp] V[Wp] SU[Wp] SV[Wp] (double), P[Wp+1] (long long), IS[Wp] (float).
-__host__ __device__ inline size_t uam_int_warp_smem(int Wp) {
-    size_t b = (size_t)Wp * 8 * 4 + (size_t)(Wp + 1) * 8 + (size_t)Wp * 4;
-    return (b + 15) & ~(size_t)15;
-}
-
-// PAIR = 0: one lane per sample (4 texel loads per lane).  PAIR = 1: two lanes per sample (uam_sample_pair).
+// ---- integral mode, warp per path (variants 0 and 1) --------------------------------------------------------------
+// The path's samples are flattened (segment k owns flat indices [P_k, P_{k+1})), lanes stride the flat index, so 32
+// consecutive samples of one polyline -- a compact footprint in the raster -- are fetched together and no lane
+// idles on short segments.  Total samples per path are capped at 2^31 - 1 by the host-side S_k cap.
 template <int TF, int LAYOUT, int PAIR>
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
 uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRasterParams rp,
@@ -217,14 +295,7 @@ uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRa
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
-    unsigned char* base = uam_smem + (size_t)warp * uam_int_warp_smem(Wp);
-    double* sU = reinterpret_cast<double*>(base);
-    double* sV = sU + Wp;
-    double* sSU = sV + Wp;
-    double* sSV = sSU + Wp;
-    long long* sP = reinterpret_cast<long long*>(sSV + Wp);
-    float* sIS = reinterpret_cast<float*>(sP + Wp + 1);
-
+    const UamSegTable tb = uam_seg_table(uam_smem + (size_t)warp * uam_seg_table_bytes(Wp), Wp);
     const long long warp0 = (long long)blockIdx.x * wpc + warp;
     const long long nwarps = (long long)gridDim.x * wpc;
     const int N = Wp - 2;
@@ -235,64 +306,63 @@ uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRa
         // A: pixel coordinates of the waypoints
         for (int j = lane; j < Wp; j += 32) {
             const double2 p = zp[j];
-            sU[j] = uam_pix(p.x, rp.x0, rp.dx);
-            sV[j] = uam_pix(p.y, rp.y0, rp.dy);
+            tb.U[j] = uam_pix(p.x, rp.x0, rp.dx);
+            tb.V[j] = uam_pix(p.y, rp.y0, rp.dy);
             len_sum += uam_len_term(zp, j, N, p, rp);
         }
         __syncwarp();
         // B: per-segment sample count, step and exclusive prefix; pseudo-segment Wp-1 = the goal waypoint
-        long long carry = 0;
+        int carry = 0;
         for (int b0 = 0; b0 < Wp; b0 += 32) {
             const int k = b0 + lane;
-            long long S = 0;
+            int S = 0;
             if (k < Wp - 1) {
-                const double dU = __dsub_rn(sU[k + 1], sU[k]), dV = __dsub_rn(sV[k + 1], sV[k]);
-                double Sd = fmax(1.0, ceil(__dmul_rn(uam_norm2r(dU, dV), rp.spc)));
-                if (!(Sd <= UAM_MAX_SAMPLES_PER_SEGMENT)) Sd = UAM_MAX_SAMPLES_PER_SEGMENT;
-                S = (long long)Sd;
-                sSU[k] = __ddiv_rn(dU, Sd);
-                sSV[k] = __ddiv_rn(dV, Sd);
-                sIS[k] = (float)(1.0 / Sd);
+                const double dU = __dsub_rn(tb.U[k + 1], tb.U[k]), dV = __dsub_rn(tb.V[k + 1], tb.V[k]);
+                const double Sd = uam_seg_samples(dU, dV, rp.spc);
+                S = (int)Sd;
+                tb.SU[k] = __ddiv_rn(dU, Sd);
+                tb.SV[k] = __ddiv_rn(dV, Sd);
+                tb.IS[k] = (float)(1.0 / Sd);
             } else if (k == Wp - 1) {
                 S = 1;
-                sSU[k] = 0.0;
-                sSV[k] = 0.0;
-                sIS[k] = 1.0f;
+                tb.SU[k] = 0.0;
+                tb.SV[k] = 0.0;
+                tb.IS[k] = 1.0f;
             }
-            long long incl = S;
+            int incl = S;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
-            if (k < Wp) sP[k] = carry + incl - S;
+            if (k < Wp) tb.P[k] = carry + incl - S;
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 0) sP[Wp] = carry;
+        if (lane == 0) tb.P[Wp] = carry;
         __syncwarp();
         // C: flat sample loop
-        const long long T = carry;
+        const int T = carry;
         float acc = 0.0f;
         bool col = false;
-        int k = 0;
-        long long p0 = 0, p1 = sP[1];
-        double kU = sU[0], kV = sV[0], kSU = sSU[0], kSV = sSV[0];
-        float kIS = sIS[0];
+        int k = 0, p1 = tb.P[1];
+        double kU = tb.U[0], kV = tb.V[0], kSU = tb.SU[0], kSV = tb.SV[0];
+        float kIS = tb.IS[0];
         if (PAIR) {
             const int side = lane & 1;
-            for (long long tb = 0; tb < T; tb += 16) {
-                const long long t = tb + (lane >> 1);
+            double sd = (double)(lane >> 1);
+            for (int tb0 = 0; tb0 < T; tb0 += 16) {
+                const int t = tb0 + (lane >> 1);
                 const bool active = t < T;
                 double u = 0.0, v = 0.0;
                 if (active) {
                     if (t >= p1) {
-                        do { ++k; p1 = sP[k + 1]; } while (t >= p1);
-                        p0 = sP[k];
-                        kU = sU[k]; kV = sV[k]; kSU = sSU[k]; kSV = sSV[k]; kIS = sIS[k];
+                        do { ++k; p1 = tb.P[k + 1]; } while (t >= p1);
+                        sd = (double)(t - tb.P[k]);
+                        kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k]; kIS = tb.IS[k];
                     }
-                    const double s = (double)(t - p0);
-                    u = __dadd_rn(kU, __dmul_rn(s, kSU));
-                    v = __dadd_rn(kV, __dmul_rn(s, kSV));
+                    u = __dadd_rn(kU, __dmul_rn(sd, kSU));
+                    v = __dadd_rn(kV, __dmul_rn(sd, kSV));
+                    sd += 16.0;
                 }
                 float pen;
                 bool occ;
@@ -301,20 +371,45 @@ uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRa
                 col = col || occ;
             }
         } else {
-            for (long long t = lane; t < T; t += 32) {
+            // two samples per lane per trip (t and t + 32): all 8 texel loads are issued before the first lerp, which
+            // doubles the bytes each warp keeps in flight (the kernel is DRAM-latency bound on scattered paths)
+            double sd = (double)lane;
+            for (int t = lane; t < T; t += 64) {
                 if (t >= p1) {
-                    do { ++k; p1 = sP[k + 1]; } while (t >= p1);
-                    p0 = sP[k];
-                    kU = sU[k]; kV = sV[k]; kSU = sSU[k]; kSV = sSV[k]; kIS = sIS[k];
+                    do { ++k; p1 = tb.P[k + 1]; } while (t >= p1);
+                    sd = (double)(t - tb.P[k]);
+                    kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k]; kIS = tb.IS[k];
                 }
-                const double s = (double)(t - p0);
-                const double u = __dadd_rn(kU, __dmul_rn(s, kSU));
-                const double v = __dadd_rn(kV, __dmul_rn(s, kSV));
+                const double u0 = __dadd_rn(kU, __dmul_rn(sd, kSU));
+                const double v0 = __dadd_rn(kV, __dmul_rn(sd, kSV));
+                const float is0 = kIS;
+                sd += 32.0;
+                const int t2 = t + 32;
+                const bool two = t2 < T;
+                double u1 = u0, v1 = v0;
+                if (two) {
+                    if (t2 >= p1) {
+                        do { ++k; p1 = tb.P[k + 1]; } while (t2 >= p1);
+                        sd = (double)(t2 - tb.P[k]);
+                        kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k]; kIS = tb.IS[k];
+                    }
+                    u1 = __dadd_rn(kU, __dmul_rn(sd, kSU));
+                    v1 = __dadd_rn(kV, __dmul_rn(sd, kSV));
+                    sd += 32.0;
+                }
+                UamTap<TF> a, b;
+                uam_tap_load<TF, LAYOUT>(tex, rp, u0, v0, a);
+                uam_tap_load<TF, LAYOUT>(tex, rp, u1, v1, b);
                 float pen;
                 bool occ;
-                uam_sample<TF, LAYOUT>(tex, rp, u, v, pen, occ);
-                acc += pen * kIS;
+                uam_tap_eval<TF>(rp, a, pen, occ);
+                acc += pen * is0;
                 col = col || occ;
+                uam_tap_eval<TF>(rp, b, pen, occ);
+                if (two) {
+                    acc += pen * kIS;
+                    col = col || occ;
+                }
             }
         }
         acc = uam_warp_sum(acc);
@@ -329,11 +424,310 @@ uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRa
     }
 }
 
+// ---- integral mode, binned (variant 2) -------------------------------------------------------------------------
+// With candidates scattered over a raster much larger than L2 every path drags its own corridor of texels through
+// DRAM and every texel is fetched many times per batch by different paths.  The binned pipeline reorders the WORK
+// instead of the data: the batch's segments (one unit = one polyline segment, plus one pseudo-segment for the goal
+// waypoint) are counting-sorted by the raster bin (64 x 64 cells or larger, Morton order) of their midpoint; the
+// sort writes a 48-byte record per segment at its sorted position; a warp then scores 32 consecutive records with
+// the flat sample loop (per-segment partial sums in shared memory), and a last warp-per-path kernel adds the
+// per-segment partials in a fixed order.
+//   uam_k_bin_hist -> uam_k_bin_scan -> uam_k_bin_scatter -> uam_k_score_groups -> uam_k_reduce_paths
+struct UamBinGeo {
+    int shift;        // bin side = 1 << shift cells
+    int nbins;        // Morton id space (power of 4)
+};
+
+struct __align__(16) UamSegRec {
+    double U, V, SU, SV;   // first sample (pixel coordinates) and per-sample step
+    int S;                 // samples
+    float IS;              // 1 / S
+    unsigned id;           // b * Wp + k
+    unsigned pad;
+};
+
+__device__ __forceinline__ unsigned uam_part1by1(unsigned x) {
+    x &= 0x0000ffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// segment id = b * Wp + k; k < Wp-1: segment z_k -> z_{k+1}; k == Wp-1: the goal waypoint alone
+__device__ __forceinline__ UamSegRec uam_make_segment(const double2* __restrict__ z, unsigned long long id, int Wp,
+                                                      const UamRasterParams& rp) {
+    const unsigned long long b = id / (unsigned)Wp;
+    const int k = (int)(id - b * (unsigned)Wp);
+    const double2 p = z[b * Wp + k];
+    UamSegRec r;
+    r.U = uam_pix(p.x, rp.x0, rp.dx);
+    r.V = uam_pix(p.y, rp.y0, rp.dy);
+    r.SU = 0.0; r.SV = 0.0; r.S = 1; r.IS = 1.0f;
+    r.id = (unsigned)id;
+    r.pad = 0;
+    if (k < Wp - 1) {
+        const double2 q = z[b * Wp + k + 1];
+        const double dU = __dsub_rn(uam_pix(q.x, rp.x0, rp.dx), r.U), dV = __dsub_rn(uam_pix(q.y, rp.y0, rp.dy), r.V);
+        const double Sd = uam_seg_samples(dU, dV, rp.spc);
+        r.S = (int)Sd;
+        r.SU = __ddiv_rn(dU, Sd);
+        r.SV = __ddiv_rn(dV, Sd);
+        r.IS = (float)(1.0 / Sd);
+    }
+    return r;
+}
+
+__device__ __forceinline__ int uam_segment_bin(const UamSegRec& r, const UamRasterParams& rp, const UamBinGeo bg) {
+    // bin of the segment midpoint, clamped into the raster (NaN -> 0)
+    double u = r.U + 0.5 * (double)r.S * r.SU, v = r.V + 0.5 * (double)r.S * r.SV;
+    u = fmin(fmax(u, 0.0), (double)(rp.W - 1));
+    v = fmin(fmax(v, 0.0), (double)(rp.H - 1));
+    return (int)(uam_part1by1((unsigned)((int)u >> bg.shift)) | (uam_part1by1((unsigned)((int)v >> bg.shift)) << 1));
+}
+
+#define UAM_BIN_CHUNK 8192     // segments per CTA in the histogram / scatter kernels
+
+__global__ void __launch_bounds__(256)
+uam_k_bin_hist(const double2* __restrict__ z, unsigned long long n_seg, int Wp, UamRasterParams rp, UamBinGeo bg,
+               unsigned short* __restrict__ seg_bin, unsigned* __restrict__ hist) {
+    extern __shared__ int s_hist[];
+    for (int i = threadIdx.x; i < bg.nbins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const unsigned long long lo = (unsigned long long)blockIdx.x * UAM_BIN_CHUNK;
+    const unsigned long long hi = lo + UAM_BIN_CHUNK < n_seg ? lo + UAM_BIN_CHUNK : n_seg;
+    for (unsigned long long id = lo + threadIdx.x; id < hi; id += blockDim.x) {
+        const int bin = uam_segment_bin(uam_make_segment(z, id, Wp, rp), rp, bg);
+        seg_bin[id] = (unsigned short)bin;
+        atomicAdd(&s_hist[bin], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bg.nbins; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], (unsigned)s_hist[i]);
+}
+
+// exclusive prefix of hist[0..n) into cursor[0..n) (single CTA, 1024 threads)
+__global__ void __launch_bounds__(1024)
+uam_k_bin_scan(const unsigned* __restrict__ hist, int n, unsigned* __restrict__ cursor) {
+    __shared__ unsigned warp_tot[32];
+    const int per = (n + 1023) / 1024;
+    const int lo = min((int)threadIdx.x * per, n), hi = min(lo + per, n);
+    unsigned local = 0;
+    for (int i = lo; i < hi; ++i) local += hist[i];
+    unsigned incl = local;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = warp_tot[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned run = warp_tot[warp] + incl - local;
+    for (int i = lo; i < hi; ++i) {
+        const unsigned h = hist[i];
+        cursor[i] = run;
+        run += h;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+uam_k_bin_scatter(const double2* __restrict__ z, unsigned long long n_seg, int Wp, UamRasterParams rp, UamBinGeo bg,
+                  const unsigned short* __restrict__ seg_bin, unsigned* __restrict__ cursor, UamSegRec* __restrict__ recs) {
+    extern __shared__ int s_hist[];
+    for (int i = threadIdx.x; i < bg.nbins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const unsigned long long lo = (unsigned long long)blockIdx.x * UAM_BIN_CHUNK;
+    const unsigned long long hi = lo + UAM_BIN_CHUNK < n_seg ? lo + UAM_BIN_CHUNK : n_seg;
+    for (unsigned long long id = lo + threadIdx.x; id < hi; id += blockDim.x) atomicAdd(&s_hist[seg_bin[id]], 1);
+    __syncthreads();
+    // reserve this CTA's range in every bin it touches; s_hist becomes the CTA's write cursor
+    for (int i = threadIdx.x; i < bg.nbins; i += blockDim.x) {
+        const int c = s_hist[i];
+        if (c) s_hist[i] = (int)atomicAdd(&cursor[i], (unsigned)c);
+    }
+    __syncthreads();
+    for (unsigned long long id = lo + threadIdx.x; id < hi; id += blockDim.x) {
+        const unsigned pos = (unsigned)atomicAdd(&s_hist[seg_bin[id]], 1);
+        recs[pos] = uam_make_segment(z, id, Wp, rp);
+    }
+}
+
+// One warp per group of 32 consecutive sorted records: flat sample loop over the group, per-segment partial sums
+// in shared memory (row = lane, column swizzled by lane so both the per-lane flush and the per-segment reduction
+// are bank-conflict free), fixed-order reduction per segment.
+#define UAM_GROUP_SMEM (32 * 40 + 4 + 12 + 32 * 32 * 4)    // segment table (32 entries, padded to 16 B) + partials
+
+template <int TF, int LAYOUT>
+__global__ void __launch_bounds__(UAM_CTA_THREADS)
+uam_k_score_groups(unsigned long long n_seg, UamRasterParams rp, const typename UamTexel<TF>::T* __restrict__ tex,
+                   const UamSegRec* __restrict__ recs, float* __restrict__ part_pen, uint8_t* __restrict__ part_col) {
+    extern __shared__ __align__(16) unsigned char uam_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned char* base = uam_smem + (size_t)warp * UAM_GROUP_SMEM;
+    const UamSegTable tb = uam_seg_table(base, 32);
+    float* part = reinterpret_cast<float*>(base + uam_seg_table_bytes(32));
+    const unsigned long long n_groups = (n_seg + 31) >> 5;
+    const unsigned long long warp0 = (unsigned long long)blockIdx.x * UAM_WARPS_PER_CTA + warp;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * UAM_WARPS_PER_CTA;
+    for (unsigned long long g = warp0; g < n_groups; g += nwarps) {
+        const unsigned long long ridx = (g << 5) + lane;
+        const bool have = ridx < n_seg;
+        // load this lane's record (3 x 16 B, coalesced across the warp) and build the group's segment table
+        int S = 0;
+        unsigned id = 0;
+        float IS = 0.0f;
+        if (have) {
+            const double2* rp2 = reinterpret_cast<const double2*>(recs + ridx);
+            const double2 a = __ldg(rp2), b = __ldg(rp2 + 1);
+            const int4 c = __ldg(reinterpret_cast<const int4*>(rp2 + 2));
+            tb.U[lane] = a.x; tb.V[lane] = a.y; tb.SU[lane] = b.x; tb.SV[lane] = b.y;
+            S = c.x;
+            IS = __int_as_float(c.y);
+            id = (unsigned)c.z;
+        }
+        int incl = S;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        tb.P[lane] = incl - S;
+        const int T = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31) tb.P[32] = T;
+        float4* prow = reinterpret_cast<float4*>(part + lane * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) prow[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        __syncwarp();
+        // flat sample loop; acc belongs to segment k and is flushed when the lane moves on
+        float acc = 0.0f;
+        unsigned colmask = 0;
+        int k = 0, p1 = tb.P[1];
+        double kU = tb.U[0], kV = tb.V[0], kSU = tb.SU[0], kSV = tb.SV[0];
+        double sd = (double)lane;
+        for (int t = lane; t < T; t += 64) {
+            if (t >= p1) {
+                part[lane * 32 + (k ^ lane)] = acc;
+                acc = 0.0f;
+                do { ++k; p1 = tb.P[k + 1]; } while (t >= p1);
+                sd = (double)(t - tb.P[k]);
+                kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k];
+            }
+            UamTap<TF> ta, tb2;
+            uam_tap_load<TF, LAYOUT>(tex, rp, __dadd_rn(kU, __dmul_rn(sd, kSU)), __dadd_rn(kV, __dmul_rn(sd, kSV)), ta);
+            sd += 32.0;
+            const int k0 = k;
+            const int t2 = t + 32;
+            const bool two = t2 < T;
+            bool moved = false;
+            if (two && t2 >= p1) {
+                moved = true;
+                do { ++k; p1 = tb.P[k + 1]; } while (t2 >= p1);
+                sd = (double)(t2 - tb.P[k]);
+                kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k];
+            }
+            uam_tap_load<TF, LAYOUT>(tex, rp, __dadd_rn(kU, __dmul_rn(sd, kSU)), __dadd_rn(kV, __dmul_rn(sd, kSV)), tb2);
+            if (two) sd += 32.0;
+            float pen;
+            bool occ;
+            uam_tap_eval<TF>(rp, ta, pen, occ);
+            acc += pen;
+            colmask |= (occ ? 1u : 0u) << k0;
+            if (moved) {
+                part[lane * 32 + (k0 ^ lane)] = acc;
+                acc = 0.0f;
+            }
+            uam_tap_eval<TF>(rp, tb2, pen, occ);
+            if (two) {
+                acc += pen;
+                colmask |= (occ ? 1u : 0u) << k;
+            }
+        }
+        part[lane * 32 + (k ^ lane)] = acc;
+        __syncwarp();
+        // per-segment reduction: segment s = sum over lanes of part[lane][s]; lane s keeps it
+        float mine = 0.0f;
+#pragma unroll 4
+        for (int s = 0; s < 32; ++s) {
+            const float v = uam_warp_sum(part[lane * 32 + (s ^ lane)]);
+            if (lane == s) mine = v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) colmask |= __shfl_xor_sync(0xffffffffu, colmask, o);
+        if (have) {
+            part_pen[id] = mine * IS;
+            part_col[id] = (colmask >> lane) & 1u;
+        }
+        __syncwarp();
+    }
+}
+
+// one warp per path: fixed-order sum of the per-segment partials + the length term
+__global__ void __launch_bounds__(UAM_CTA_THREADS)
+uam_k_reduce_paths(const double2* __restrict__ z, long long B, int Wp, UamRasterParams rp,
+                   const float* __restrict__ part_pen, const uint8_t* __restrict__ part_col, float* __restrict__ cost,
+                   uint8_t* __restrict__ collide, long long* __restrict__ nsamp) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * UAM_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * UAM_WARPS_PER_CTA;
+    const int N = Wp - 2;
+    for (long long path = warp0; path < B; path += nwarps) {
+        const double2* zp = z + path * Wp;
+        float acc = 0.0f;
+        double len_sum = 0.0;
+        long long ns = 0;
+        bool col = false;
+        for (int j = lane; j < Wp; j += 32) {
+            const double2 p = zp[j];
+            acc += part_pen[path * Wp + j];
+            col = col || part_col[path * Wp + j];
+            len_sum += uam_len_term(zp, j, N, p, rp);
+            if (nsamp) {
+                long long S = 1;
+                if (j < Wp - 1) {
+                    const double2 q = zp[j + 1];
+                    const double dU = __dsub_rn(uam_pix(q.x, rp.x0, rp.dx), uam_pix(p.x, rp.x0, rp.dx));
+                    const double dV = __dsub_rn(uam_pix(q.y, rp.y0, rp.dy), uam_pix(p.y, rp.y0, rp.dy));
+                    S = (long long)uam_seg_samples(dU, dV, rp.spc);
+                }
+                ns += S;
+            }
+        }
+        acc = uam_warp_sum(acc);
+        len_sum = uam_warp_sum(len_sum);
+        col = __any_sync(0xffffffffu, col);
+        if (nsamp) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+        }
+        if (lane == 0) {
+            if (cost) cost[path] = (float)((double)(N + 1) * len_sum + (double)acc / (double)N);
+            if (collide) collide[path] = col ? 1 : 0;
+            if (nsamp) nsamp[path] = ns;
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
 int uam_raster_prepare(uam_ctx* ctx, int64_t B, int N, const double* h_p, int n_p, int flags, double spc,
                        UamRasterParams* rp) {
     if (B < 0 || N < 1) return uam_fail(ctx, UAM_ERR_INVALID, "need B >= 0 and N >= 1 (got B=%lld N=%d)", (long long)B, N);
     if (!ctx->has_raster) return uam_fail(ctx, UAM_ERR_STATE, "no raster: call uam_map_set_raster first");
     if (!(spc >= 0.0) || spc > 64.0) return uam_fail(ctx, UAM_ERR_INVALID, "samples_per_cell must be in [0, 64]");
+    if (spc > 0.0 && (double)(N + 2) * UAM_MAX_SAMPLES_PER_SEGMENT > 2.0e9)
+        return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "N = %d waypoints per path is too many for integral mode", N);
     UamParams prm;
     UAM_TRY(uam_make_params(ctx, h_p, n_p, flags, &prm));
     if (prm.n_regions != ctx->geo.L)
@@ -342,7 +736,8 @@ int uam_raster_prepare(uam_ctx* ctx, int64_t B, int N, const double* h_p, int n_
     rp->ms_x = prm.ms_x; rp->ms_y = prm.ms_y;
     rp->spc = spc;
     rp->H = ctx->geo.H; rp->W = ctx->geo.W;
-    rp->tiles_x = ctx->geo.tiles_x;
+    const int tile_texels = ctx->geo.texel_floats == 4 ? 8 : 16;
+    rp->row_stride = (unsigned)(ctx->geo.layout ? ctx->geo.tiles_x * tile_texels : ctx->geo.W);
     rp->w0 = (float)prm.w[0];
     rp->w1 = ctx->geo.L > 1 ? (float)prm.w[1] : 0.0f;
     rp->w2 = ctx->geo.L > 2 ? (float)prm.w[2] : 0.0f;
@@ -351,8 +746,53 @@ int uam_raster_prepare(uam_ctx* ctx, int64_t B, int N, const double* h_p, int n_
 }
 
 template <int TF, int LAYOUT>
+int uam_raster_launch_binned(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const UamRasterParams& rp, float* d_cost,
+                             uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
+    typedef typename UamTexel<TF>::T T;
+    const unsigned long long n_seg = (unsigned long long)B * Wp;
+    UamBinGeo bg;
+    bg.shift = 6;
+    const int side = std::max(rp.W, rp.H);
+    while (((side + (1 << bg.shift) - 1) >> bg.shift) > 128) ++bg.shift;       // at most 128 x 128 bins (64 KiB of smem)
+    int p2 = 1;
+    while (p2 < ((side + (1 << bg.shift) - 1) >> bg.shift)) p2 <<= 1;
+    bg.nbins = p2 * p2;
+    // scratch: recs (48 B) | part_pen (f32) | hist (u32) | cursor (u32) | seg_bin (u16) | part_col (u8)
+    const size_t need = n_seg * (sizeof(UamSegRec) + 4 + 2 + 1) + (size_t)bg.nbins * 8 + 256;
+    UAM_TRY(uam_reserve(ctx, &ctx->d_bin_scratch[slot], &ctx->bin_scratch_bytes[slot], need));
+    UamSegRec* recs = (UamSegRec*)ctx->d_bin_scratch[slot];
+    float* part_pen = (float*)(recs + n_seg);
+    unsigned* hist = (unsigned*)(part_pen + n_seg);
+    unsigned* cursor = hist + bg.nbins;
+    unsigned short* seg_bin = (unsigned short*)(cursor + bg.nbins);
+    uint8_t* part_col = (uint8_t*)(seg_bin + n_seg);
+    UAM_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)bg.nbins * 4, st));
+    const unsigned chunks = (unsigned)((n_seg + UAM_BIN_CHUNK - 1) / UAM_BIN_CHUNK);
+    const size_t hsmem = (size_t)bg.nbins * 4;
+    if (hsmem > 48 * 1024) {
+        UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+        UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+    }
+    uam_k_bin_hist<<<chunks, 256, hsmem, st>>>(z, n_seg, Wp, rp, bg, seg_bin, hist);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_bin_hist");
+    uam_k_bin_scan<<<1, 1024, 0, st>>>(hist, bg.nbins, cursor);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_bin_scan");
+    uam_k_bin_scatter<<<chunks, 256, hsmem, st>>>(z, n_seg, Wp, rp, bg, seg_bin, cursor, recs);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_bin_scatter");
+    const size_t gsmem = (size_t)UAM_GROUP_SMEM * UAM_WARPS_PER_CTA;
+    const unsigned long long n_groups = (n_seg + 31) >> 5;
+    const long long sctas = std::min<long long>((long long)((n_groups + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA), (long long)ctx->sm_count * 16);
+    uam_k_score_groups<TF, LAYOUT><<<(unsigned)sctas, UAM_CTA_THREADS, gsmem, st>>>(n_seg, rp, (const T*)ctx->d_tex, recs, part_pen, part_col);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_score_groups");
+    const long long rctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
+    uam_k_reduce_paths<<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, d_cost, d_collide, d_nsamp);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_reduce_paths");
+    return UAM_OK;
+}
+
+template <int TF, int LAYOUT>
 int uam_raster_launch_t(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const UamRasterParams& rp, float* d_cost,
-                        uint8_t* d_collide, long long* d_nsamp, cudaStream_t st) {
+                        uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
     typedef typename UamTexel<TF>::T T;
     const T* tex = (const T*)ctx->d_tex;
     if (rp.spc == 0.0) {
@@ -361,60 +801,38 @@ int uam_raster_launch_t(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const
         UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_wp");
         return UAM_OK;
     }
-    const size_t per_warp = uam_int_warp_smem(Wp);
+    // auto (-1): the binned pipeline pays off once the batch has enough segments to fill the raster bins
+    const bool binned = ctx->int_variant == 2 || (ctx->int_variant < 0 && (unsigned long long)B * Wp >= 262144ull);
+    if (binned && (unsigned long long)B * Wp < 0xffffffffull)
+        return uam_raster_launch_binned<TF, LAYOUT>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
+    const size_t per_warp = uam_seg_table_bytes(Wp);
     const size_t budget = 200 * 1024;
     if (per_warp > budget) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "N = %d waypoints per path is too many for integral mode", Wp - 2);
     const int wpc = (int)std::max<size_t>(1, std::min<size_t>(UAM_WARPS_PER_CTA, budget / per_warp));
     const size_t smem = per_warp * wpc;
     const long long ctas = std::min<long long>((B + wpc - 1) / wpc, (long long)ctx->sm_count * 16);
-    if (ctx->int_variant == 0) {
-        if (smem > 48 * 1024) UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_score_raster_int<TF, LAYOUT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uam_k_score_raster_int<TF, LAYOUT, 0><<<(unsigned)ctas, wpc * 32, smem, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
-    } else {
+    if (ctx->int_variant == 1) {
         if (smem > 48 * 1024) UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_score_raster_int<TF, LAYOUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         uam_k_score_raster_int<TF, LAYOUT, 1><<<(unsigned)ctas, wpc * 32, smem, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
+    } else {
+        if (smem > 48 * 1024) UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_score_raster_int<TF, LAYOUT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uam_k_score_raster_int<TF, LAYOUT, 0><<<(unsigned)ctas, wpc * 32, smem, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
     }
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_int");
     return UAM_OK;
 }
 
+// slot: which scratch buffer of the ctx the binned pipeline may use (0 = caller-stream calls, 1.. = host pipeline stages)
 int uam_raster_launch(uam_ctx* ctx, const double* d_z, int64_t B, int N, const UamRasterParams& rp, float* d_cost,
-                      uint8_t* d_collide, long long* d_nsamp, cudaStream_t st) {
+                      uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
     const int Wp = N + 2;
     const double2* z = reinterpret_cast<const double2*>(d_z);
     const int tf = ctx->geo.texel_floats, lay = ctx->geo.layout;
-    if (tf == 2) return lay ? uam_raster_launch_t<2, 1>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st)
-                            : uam_raster_launch_t<2, 0>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st);
-    return lay ? uam_raster_launch_t<4, 1>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st)
-               : uam_raster_launch_t<4, 0>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st);
+    if (tf == 2) return lay ? uam_raster_launch_t<2, 1>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
+                            : uam_raster_launch_t<2, 0>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
+    return lay ? uam_raster_launch_t<4, 1>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
+               : uam_raster_launch_t<4, 0>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
 }
-
-// ---- best candidate: min over b of (float bits of cost << 32 | global index) ----------------------------------
-template <typename CT>
-__global__ void __launch_bounds__(256)
-uam_k_best(const CT* __restrict__ cost, long long B, unsigned long long offset, unsigned long long* __restrict__ key) {
-    unsigned long long best = ~0ull;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
-        const float c = (float)cost[b];
-        const unsigned long long k = ((unsigned long long)__float_as_uint(c) << 32) | ((offset + (unsigned long long)b) & 0xffffffffull);
-        best = k < best ? k : best;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
-        best = t < best ? t : best;
-    }
-    __shared__ unsigned long long s[8];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) best = s[i] < best ? s[i] : best;
-        if (best != ~0ull) atomicMin(key, best);
-    }
-}
-
-__global__ void uam_k_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
 
 }  // namespace
 
@@ -427,7 +845,7 @@ extern "C" int uam_score_paths_raster(uam_ctx* ctx, const double* d_z, int64_t B
     if (B == 0) return UAM_OK;
     if (!d_z) return uam_fail(ctx, UAM_ERR_INVALID, "paths pointer is NULL");
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
-    return uam_raster_launch(ctx, d_z, B, N, rp, d_cost, d_collide, (long long*)d_nsamples, uam_pick_stream(ctx, stream));
+    return uam_raster_launch(ctx, d_z, B, N, rp, d_cost, d_collide, (long long*)d_nsamples, uam_pick_stream(ctx, stream), 0);
 }
 
 // Host buffers in, host buffers out: the batch is cut into chunks that flow through UAM_HOST_PIPE_DEPTH
@@ -456,32 +874,10 @@ extern "C" int uam_score_paths_raster_host(uam_ctx* ctx, const double* h_z, int6
         uint8_t* d_col = (uint8_t*)(d_cost + chunk);
         UAM_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in[s], (const char*)h_z + (size_t)b0 * row, (size_t)nb * row,
                                       cudaMemcpyHostToDevice, st));
-        UAM_TRY(uam_raster_launch(ctx, (const double*)ctx->d_stage_in[s], nb, N, rp, d_cost, d_col, nullptr, st));
+        UAM_TRY(uam_raster_launch(ctx, (const double*)ctx->d_stage_in[s], nb, N, rp, d_cost, d_col, nullptr, st, 1 + s));
         if (h_cost) UAM_CUDA(ctx, cudaMemcpyAsync(h_cost + b0, d_cost, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
         if (h_collide) UAM_CUDA(ctx, cudaMemcpyAsync(h_collide + b0, d_col, (size_t)nb, cudaMemcpyDeviceToHost, st));
     }
     for (int s = 0; s < UAM_HOST_PIPE_DEPTH; ++s) UAM_CUDA(ctx, cudaStreamSynchronize(ctx->pipe_stream[s]));
-    return UAM_OK;
-}
-
-extern "C" int uam_best(uam_ctx* ctx, const void* d_cost, int cost_is_f64, int64_t B, int64_t global_offset,
-                        uint64_t* d_key, int reset, void* stream) {
-    if (!ctx) return UAM_ERR_INVALID;
-    if (!d_key || B < 0 || (B > 0 && !d_cost)) return uam_fail(ctx, UAM_ERR_INVALID, "bad argument to uam_best");
-    if (global_offset < 0 || global_offset + B > 0xffffffffll)
-        return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "global path index must fit 32 bits");
-    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = uam_pick_stream(ctx, stream);
-    if (reset) {
-        uam_k_set_u64<<<1, 1, 0, st>>>((unsigned long long*)d_key, ~0ull);
-        UAM_CHECK_LAUNCH(ctx, "uam_k_set_u64");
-    }
-    if (B == 0) return UAM_OK;
-    const long long ctas = std::min<long long>((B + 255) / 256, (long long)ctx->sm_count * 4);
-    if (cost_is_f64)
-        uam_k_best<double><<<(unsigned)ctas, 256, 0, st>>>((const double*)d_cost, B, (unsigned long long)global_offset, (unsigned long long*)d_key);
-    else
-        uam_k_best<float><<<(unsigned)ctas, 256, 0, st>>>((const float*)d_cost, B, (unsigned long long)global_offset, (unsigned long long*)d_key);
-    UAM_CHECK_LAUNCH(ctx, "uam_k_best");
     return UAM_OK;
 }
