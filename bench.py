@@ -110,7 +110,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -258,7 +258,7 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     launches0 = eng.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    eng.set_option('time_kernels', 1)      # CUDA events around the dominant scoring kernel, on the launching stream
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -277,7 +277,24 @@ def run_ours(args):
     launches = eng.launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
     ms_total = t_start.elapsed_time(t_end)
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    call_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))      # whole scoring call (all its kernels)
+    k_ms = eng.get_stat('score_kernel_ms_mean')                         # the dominant kernel alone
+    assert int(eng.get_stat('score_kernel_count')) == args.steps
+    eng.set_option('time_kernels', 0)
+    variant = int(os.environ.get('UAM_INT_VARIANT', '-1'))
+    kname = {0: 'uam_k_score_raster_int<4,L,0>', 1: 'uam_k_score_raster_int<4,L,1>'}.get(variant, 'uam_k_score_groups<4,1>')
+
+    # ---- secondary: waypoint mode (the reference's sampling) on the same batch ---------------------------------
+    for _ in range(3):
+        rm.score_paths(Z, WEIGHTS, 0.0, True, None, out=(cost, col))
+    wp0, wp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wp0.record()
+    for _ in range(args.steps):
+        rm.score_paths(Z, WEIGHTS, 0.0, True, None, out=(cost, col))
+    wp1.record()
+    torch.cuda.synchronize()
+    wp_ms = wp0.elapsed_time(wp1) / args.steps
+    rm.score_paths(Z, WEIGHTS, SPC, True, None, out=(cost, col))        # restore the integral-mode costs
     best_cost, best_idx = udist.decode_key(int(key.item()))
 
     # ---- e2e: host buffers through the C-ABI host entry point ------------------------------------------------
@@ -301,10 +318,10 @@ def run_ours(args):
     assert np.array_equal(cost_h, cost.cpu().numpy()), 'host entry point disagrees with the device entry point'
 
     # ---- max over ranks -----------------------------------------------------------------------------------------
-    stats = torch.tensor([ms_total, k_ms, e2e_ms, float(launches)], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_total, k_ms, e2e_ms, float(launches), call_ms, wp_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_total, k_ms_max, e2e_ms_max, _ = [float(v) for v in stats.tolist()]
+    ms_total, k_ms, e2e_ms_max, _, call_ms, wp_ms = [float(v) for v in stats.tolist()]
 
     if rank == 0:
         segs = B * (WP - 1)
@@ -316,6 +333,15 @@ def run_ours(args):
         peak = float(peaks.get('hbm_gbs', 6650.0))
         abytes = algorithmic_bytes(total_samples, B)
         achieved = abytes / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+            for ent in tj['entries']:
+                if ent['kernel'] == kname and ent['paths'] == B and ent['raster'] == n:
+                    traffic, traffic_src = ent['dram_bytes_per_launch'], ent['source']
+        except Exception:
+            pass
+        wp_bytes = (WP - 1) * B * 16 + B * WP * 49 + B * 21
         line = {
             'metric': METRIC, 'value': segs * world * args.steps / (ms_total * 1e-3), 'unit': 'segment-evals/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
@@ -324,18 +350,24 @@ def run_ours(args):
             'samples_per_step_per_gpu': total_samples,
             'samples_per_s': total_samples * world * args.steps / (ms_total * 1e-3),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'kernel': 'uam_k_score_raster_int<4>', 'kernel_ms': k_ms,
-                         'algorithmic_bytes_per_launch': abytes,
+                         'traffic': traffic, 'traffic_source': traffic_src, 'kernel': kname, 'kernel_ms': k_ms,
+                         'scoring_call_ms': call_ms, 'algorithmic_bytes_per_launch': abytes,
+                         'note': 'achieved = SURVEY 8(d) algorithmic bytes / event-timed kernel duration; the binned kernel '
+                                 'serves most of them from L2 (raster streamed ~once per batch), so achieved may exceed traffic',
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'},
             'e2e': {'value': segs * world / (e2e_ms_max * 1e-3), 'unit': 'segment-evals/s',
                     'h2d_bytes_per_step': B * 2 * WP * 8, 'd2h_bytes_per_step': B * 5, 'ms_per_step': e2e_ms_max,
                     'api': 'RasterMap.score_paths(numpy) -> uam_score_paths_raster_host', 'steps': e2e_steps},
+            'waypoint_mode': {'ms_per_step': wp_ms, 'value': segs * world / (wp_ms * 1e-3), 'unit': 'segment-evals/s',
+                              'algorithmic_GBps': wp_bytes / (wp_ms * 1e-3) / 1e9, 'frac': wp_bytes / (wp_ms * 1e-3) / 1e9 / peak,
+                              'note': 'samples_per_cell = 0 (one sample per waypoint, the reference sampling), same batch; '
+                                      'a DRAM-latency-bound gather, reported, not the roofline claim'},
             'gpu_launches': launches, 'clocks': clk,
             'best': {'cost': best_cost, 'index': best_idx},
         }
         if world == 1 and not args.no_cpu:
             cores = 1
-            nb = args.cpu_paths
+            nb = args.cpu_sample
             Lh, Oh = layers.cpu().numpy(), occ.cpu().numpy()
             Zs = Z[:nb].cpu().numpy()
             rate, dt = cpu_oracle_rate(Lh, Oh, geo, Zs, cores)
@@ -354,12 +386,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--raster', type=int, default=RASTER)
     ap.add_argument('--paths', type=int, default=125000, help='candidate paths per GPU per step (C3: 1M over 8 GPUs)')
-    ap.add_argument('--cpu-paths', type=int, default=192, help='paths per CPU worker per step for the CPU arm')
+    ap.add_argument('--cpu-paths', type=int, default=384, help='paths per CPU worker per step for --impl reference')
+    ap.add_argument('--cpu-sample', type=int, default=4096, help='paths of the batch the 1-core cpu_baseline leg scores')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

@@ -86,8 +86,14 @@ enum {
     UAM_OPT_INTEGRAL_VARIANT = 2,     /* integral mode: -1 auto (default: 2 for batches of >= 2^18 segments, else 0),
                                          0 warp per path / lane per sample, 1 lane pair per sample,
                                          2 segments binned by raster tile, warp per 32 sorted segments */
-    UAM_OPT_L2_FETCH_GRANULARITY = 3  /* cudaLimitMaxL2FetchGranularity for this device: 32, 64 or 128 bytes */
+    UAM_OPT_L2_FETCH_GRANULARITY = 3, /* cudaLimitMaxL2FetchGranularity for this device: 32, 64 or 128 bytes */
+    UAM_OPT_TIME_KERNELS = 4          /* 1: bracket the dominant raster-scoring kernel of every device-pointer call with
+                                         CUDA events on the caller's stream (resets the statistics) */
 };
+/* statistics of UAM_OPT_TIME_KERNELS: mean device time (ms) of the dominant scoring kernel (uam_k_score_groups /
+ * uam_k_score_raster_int / uam_k_score_raster_wp) over the timed calls, and their number */
+enum { UAM_STAT_SCORE_KERNEL_MS_MEAN = 1, UAM_STAT_SCORE_KERNEL_COUNT = 2 };
+int uam_ctx_get_stat(uam_ctx* ctx, int stat, double* value);
 int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value);
 
 /* ---- map: shape tables ------------------------------------------------------------------------

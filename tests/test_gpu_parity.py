@@ -397,6 +397,10 @@ def test_raster_scorer_full_size_properties(uam, torch):
         ca, ka = rm.score_paths(Z[:B // 2].contiguous(), [1.0], spc)
         cb, kb = rm.score_paths(Z[B // 2:].contiguous(), [1.0], spc)
         assert torch.equal(torch.cat([ca, cb]), c1) and torch.equal(torch.cat([ka, kb]), k1)
+        # a path's result does not depend on what else is in the batch (binned pipeline included): shuffled subset
+        perm = torch.randperm(B, device=dev, generator=g)[:B - 1234]
+        cp, kp = rm.score_paths(Z[perm].contiguous(), [1.0], spc)
+        assert torch.equal(cp, c1[perm]) and torch.equal(kp, k1[perm])
         # host-buffer entry point == device entry point
         ch, kh = rm.score_paths(Z.cpu().numpy(), [1.0], spc)
         assert np.array_equal(ch, c1.cpu().numpy()) and np.array_equal(kh, k1.cpu().numpy())

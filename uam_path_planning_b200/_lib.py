@@ -39,6 +39,7 @@ SIGNATURES = {
     'uam_launch_count': (_i, [_vp, C.POINTER(C.c_uint64)]),
     'uam_sync': (_i, [_vp]),
     'uam_ctx_set_option': (_i, [_vp, _i, _i64]),
+    'uam_ctx_get_stat': (_i, [_vp, _i, C.POINTER(_d)]),
     'uam_map_set_shapes': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i]),
     'uam_map_set_raster': (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _vp]),
     'uam_map_set_raster_device': (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _vp, _vp]),

@@ -128,8 +128,47 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             UAM_CUDA(ctx, cudaSetDevice(ctx->device));
             UAM_CUDA(ctx, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
             return UAM_OK;
+        case UAM_OPT_TIME_KERNELS:
+            UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+            if (value && !ctx->time_ev[0]) {
+                UAM_CUDA(ctx, cudaEventCreate(&ctx->time_ev[0]));
+                UAM_CUDA(ctx, cudaEventCreate(&ctx->time_ev[1]));
+            }
+            ctx->time_kernels = value ? 1 : 0;
+            ctx->time_pending = false;
+            ctx->time_sum_ms = 0.0;
+            ctx->time_count = 0;
+            return UAM_OK;
         default:
             return uam_fail(ctx, UAM_ERR_INVALID, "unknown option %d", option);
+    }
+}
+
+// Folds the pending event pair into the running sum (waits for the kernel).  Called before the events are re-recorded.
+int uam_time_collect(uam_ctx* ctx) {
+    if (!ctx->time_pending) return UAM_OK;
+    float ms = 0.0f;
+    UAM_CUDA(ctx, cudaEventSynchronize(ctx->time_ev[1]));
+    UAM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->time_ev[0], ctx->time_ev[1]));
+    ctx->time_sum_ms += ms;
+    ctx->time_count += 1;
+    ctx->time_pending = false;
+    return UAM_OK;
+}
+
+extern "C" int uam_ctx_get_stat(uam_ctx* ctx, int stat, double* value) {
+    if (!ctx || !value) return UAM_ERR_INVALID;
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UAM_TRY(uam_time_collect(ctx));
+    switch (stat) {
+        case UAM_STAT_SCORE_KERNEL_MS_MEAN:
+            *value = ctx->time_count ? ctx->time_sum_ms / (double)ctx->time_count : 0.0;
+            return UAM_OK;
+        case UAM_STAT_SCORE_KERNEL_COUNT:
+            *value = (double)ctx->time_count;
+            return UAM_OK;
+        default:
+            return uam_fail(ctx, UAM_ERR_INVALID, "unknown stat %d", stat);
     }
 }
 
@@ -150,6 +189,8 @@ extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
         if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
         if (ctx->pipe_event[i]) cudaEventDestroy(ctx->pipe_event[i]);
     }
+    if (ctx->time_ev[0]) cudaEventDestroy(ctx->time_ev[0]);
+    if (ctx->time_ev[1]) cudaEventDestroy(ctx->time_ev[1]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return UAM_OK;

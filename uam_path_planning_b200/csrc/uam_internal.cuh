@@ -87,6 +87,12 @@ struct uam_ctx {
     size_t h_stage_out_bytes[UAM_HOST_PIPE_DEPTH] = {};
     void* d_scratch = nullptr;          // EDT
     size_t scratch_bytes = 0;
+    // optional CUDA-event timing of the dominant scoring kernel (UAM_OPT_TIME_KERNELS), read by uam_ctx_get_stat
+    int time_kernels = 0;
+    bool time_pending = false;
+    cudaEvent_t time_ev[2] = {};
+    double time_sum_ms = 0.0;
+    uint64_t time_count = 0;
     void* d_bin_scratch[UAM_HOST_PIPE_DEPTH + 1] = {};   // binned raster scorer: [0] caller stream, [1..] pipeline stages
     size_t bin_scratch_bytes[UAM_HOST_PIPE_DEPTH + 1] = {};
 };
@@ -98,6 +104,7 @@ int uam_reserve_pinned(uam_ctx* ctx, void** ptr, size_t* cur, size_t need);
 int uam_make_params(uam_ctx* ctx, const double* h_p, int n_p, int flags, UamParams* out);
 int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st);
 cudaStream_t uam_pick_stream(uam_ctx* ctx, void* stream);
+int uam_time_collect(uam_ctx* ctx);
 
 #define UAM_CUDA(ctx, call)                                             \
     do {                                                                \

@@ -35,6 +35,7 @@ struct UamRasterParams {
     unsigned row_stride;  // tiled layout: texels per tile-row (tiles_x * texels per tile); row-major: W
     float w0, w1, w2;
     int flags;
+    int variant;          // integral-mode kernel, decided once per API call from the call's whole batch
 };
 
 template <int TF> struct UamTexel;
@@ -661,7 +662,10 @@ uam_k_score_groups(unsigned long long n_seg, UamRasterParams rp, const typename 
         float mine = 0.0f;
 #pragma unroll 4
         for (int s = 0; s < 32; ++s) {
-            const float v = uam_warp_sum(part[lane * 32 + (s ^ lane)]);
+            // rows are rotated by the segment's offset so that position `lane` always holds the samples with index
+            // == lane (mod 32) of THAT segment: the sum is then independent of what else is in the group / batch
+            const int row = (lane + tb.P[s]) & 31;
+            const float v = uam_warp_sum(part[row * 32 + (s ^ row)]);
             if (lane == s) mine = v;
         }
 #pragma unroll
@@ -742,6 +746,9 @@ int uam_raster_prepare(uam_ctx* ctx, int64_t B, int N, const double* h_p, int n_
     rp->w1 = ctx->geo.L > 1 ? (float)prm.w[1] : 0.0f;
     rp->w2 = ctx->geo.L > 2 ? (float)prm.w[2] : 0.0f;
     rp->flags = flags;
+    // auto (-1): the binned pipeline pays off once the batch has enough segments to fill the raster bins.  Decided
+    // from the whole call (not per pipeline chunk), so host-buffer and device-buffer calls run the same kernels.
+    rp->variant = ctx->int_variant >= 0 ? ctx->int_variant : ((unsigned long long)B * (N + 2) >= 262144ull ? 2 : 0);
     return UAM_OK;
 }
 
@@ -782,8 +789,16 @@ int uam_raster_launch_binned(uam_ctx* ctx, const double2* z, int64_t B, int Wp, 
     const size_t gsmem = (size_t)UAM_GROUP_SMEM * UAM_WARPS_PER_CTA;
     const unsigned long long n_groups = (n_seg + 31) >> 5;
     const long long sctas = std::min<long long>((long long)((n_groups + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA), (long long)ctx->sm_count * 16);
+    if (ctx->time_kernels && slot == 0) {
+        UAM_TRY(uam_time_collect(ctx));
+        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
+    }
     uam_k_score_groups<TF, LAYOUT><<<(unsigned)sctas, UAM_CTA_THREADS, gsmem, st>>>(n_seg, rp, (const T*)ctx->d_tex, recs, part_pen, part_col);
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_groups");
+    if (ctx->time_kernels && slot == 0) {
+        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
+        ctx->time_pending = true;
+    }
     const long long rctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
     uam_k_reduce_paths<<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, d_cost, d_collide, d_nsamp);
     UAM_CHECK_LAUNCH(ctx, "uam_k_reduce_paths");
@@ -795,15 +810,22 @@ int uam_raster_launch_t(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const
                         uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
     typedef typename UamTexel<TF>::T T;
     const T* tex = (const T*)ctx->d_tex;
+    const bool timed = ctx->time_kernels && slot == 0 && !(rp.spc > 0.0 && rp.variant == 2);
+    if (timed) {
+        UAM_TRY(uam_time_collect(ctx));
+        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
+    }
     if (rp.spc == 0.0) {
         const long long ctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
         uam_k_score_raster_wp<TF, LAYOUT><<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
         UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_wp");
+        if (timed) {
+            UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
+            ctx->time_pending = true;
+        }
         return UAM_OK;
     }
-    // auto (-1): the binned pipeline pays off once the batch has enough segments to fill the raster bins
-    const bool binned = ctx->int_variant == 2 || (ctx->int_variant < 0 && (unsigned long long)B * Wp >= 262144ull);
-    if (binned && (unsigned long long)B * Wp < 0xffffffffull)
+    if (rp.variant == 2 && (unsigned long long)B * Wp < 0xffffffffull)
         return uam_raster_launch_binned<TF, LAYOUT>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
     const size_t per_warp = uam_seg_table_bytes(Wp);
     const size_t budget = 200 * 1024;
@@ -811,7 +833,7 @@ int uam_raster_launch_t(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const
     const int wpc = (int)std::max<size_t>(1, std::min<size_t>(UAM_WARPS_PER_CTA, budget / per_warp));
     const size_t smem = per_warp * wpc;
     const long long ctas = std::min<long long>((B + wpc - 1) / wpc, (long long)ctx->sm_count * 16);
-    if (ctx->int_variant == 1) {
+    if (rp.variant == 1) {
         if (smem > 48 * 1024) UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_score_raster_int<TF, LAYOUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         uam_k_score_raster_int<TF, LAYOUT, 1><<<(unsigned)ctas, wpc * 32, smem, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
     } else {
@@ -819,6 +841,10 @@ int uam_raster_launch_t(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const
         uam_k_score_raster_int<TF, LAYOUT, 0><<<(unsigned)ctas, wpc * 32, smem, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
     }
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_int");
+    if (timed) {
+        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
+        ctx->time_pending = true;
+    }
     return UAM_OK;
 }
 

@@ -78,7 +78,13 @@ class Engine:
     def sync(self):
         self._check(self._lib.uam_sync(self._h))
 
-    OPTIONS = {'raster_layout': 1, 'integral_variant': 2, 'l2_fetch_granularity': 3}
+    OPTIONS = {'raster_layout': 1, 'integral_variant': 2, 'l2_fetch_granularity': 3, 'time_kernels': 4}
+    STATS = {'score_kernel_ms_mean': 1, 'score_kernel_count': 2}
+
+    def get_stat(self, name: str) -> float:
+        v = C.c_double()
+        self._check(self._lib.uam_ctx_get_stat(self._h, self.STATS[name], C.byref(v)))
+        return float(v.value)
 
     def set_option(self, name: str, value: int):
         """Tuning knobs of include/uam_b200.h (UAM_OPT_*): raster_layout (0 row-major, 1 tiled; applies to the next
