@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Secondary measurements for the other BASELINE.json configs (one JSON line each; bench.py stays the headline):
+
+  C2  10k candidate polylines (64 waypoints) on a 4096^2 risk+obstacle raster (L = 1), corridor and scatter
+      distributions, waypoint and integral mode, plus the analytic scorer on the reference's main.py map
+  C4  map rebuild at n^2 (default 16384): DEM mask, occupancy + 3 risk layers from 4096 rectangular footprints,
+      exact EDT clearance -- Mcell/s per kernel and fraction of the HBM roofline (algorithmic bytes of SURVEY 8d)
+
+    python bench_configs.py [--c4-size 16384] [--reps 5]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def ev_time(torch, fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--c4-size', type=int, default=16384)
+    ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--skip-c4', action='store_true')
+    args = ap.parse_args()
+    import torch
+    import uam_path_planning_b200 as uam
+    assert torch.cuda.is_available()
+    dev = 'cuda'
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+    except Exception:
+        pass
+    rng = np.random.default_rng(20260101)
+
+    # ---------------- C2 ------------------------------------------------------------------------------------
+    n, KM, Wp, B = 4096, 64.0, 64, 10000
+    m = uam.RegionMap()
+    m.new_region('Risk', 'r')
+    for _ in range(192):                                    # random boxes 0.5-4 km (minAreaRect-like) ...
+        c, a = rng.uniform(2, 62, 2), rng.uniform(0, np.pi)
+        hw, hh = rng.uniform(0.25, 2.0, 2)
+        R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        m.add_shape_to_region('Risk', uam.polygon(*(c + np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]]) @ R.T).tolist()))
+    for _ in range(64):                                     # ... and discs r in [0.5, 3] km
+        m.add_shape_to_region('Risk', uam.ball(rng.uniform(2, 62, 2).tolist(), float(rng.uniform(0.5, 3))))
+    for _ in range(32):
+        m.add_obstacle(uam.ball(rng.uniform(2, 62, 2).tolist(), float(rng.uniform(0.3, 1.5))))
+    m.x_start, m.x_goal = [6.0, 7.0], [57.0, 55.0]
+    geo = (0.0, KM / n, 0.0, KM / n)
+    t0 = time.perf_counter()
+    rm = uam.RasterMap.from_map(m, n, n, geo, clearance=True)
+    torch.cuda.synchronize()
+    t_build = (time.perf_counter() - t0) * 1e3
+    prob = uam.Problem(m, Wp - 2, {'length_smooth': True, 'obstacle_smooth': True})
+    prob.params.update(maxratio=1.04, maxalpha=np.pi / 80, enlargement=0)
+    prob.set_weight('Risk', 5000.0)
+    sol = uam.Solver(prob, {})
+    cell = KM / n
+    Zc = sol.candidates(rng.uniform(-0.9, 0.9, B), jitter=0.25 * cell, rng=rng)                     # corridor
+    s, e = rng.uniform(0, KM, (B, 1, 2)), rng.uniform(0, KM, (B, 1, 2))
+    Zs = (s + np.linspace(0, 1, Wp).reshape(1, Wp, 1) * (e - s) + rng.normal(0, 2 * cell, (B, Wp, 2))).reshape(B, 2 * Wp)
+    out = {'config': 'C2: 10k polylines x 64 waypoints, 4096^2 risk+obstacle raster (L=1), 1 B200',
+           'map_rebuild_ms_4096': t_build, 'unit': 'segment-evals/s'}
+    for name, Zh in (('corridor', Zc), ('scatter', Zs)):
+        Z = torch.from_numpy(np.ascontiguousarray(Zh)).to(dev)
+        for mode, spc in (('waypoint', 0.0), ('integral', 1.0)):
+            _, _, ns = rm.score_paths(Z, [5000.0], spc, want_nsamples=True)
+            tot = int(ns.sum().item())
+            ms = ev_time(torch, lambda: rm.score_paths(Z, [5000.0], spc), 20, 3)
+            ab = (Wp - 1) * B * 16 + tot * (16 + 1) + B * 21
+            out[f'{name}_{mode}'] = {'ms': ms, 'value': B * (Wp - 1) / (ms * 1e-3), 'samples': tot,
+                                     'algorithmic_GBps': ab / (ms * 1e-3) / 1e9, 'frac_of_hbm_peak': ab / (ms * 1e-3) / 1e9 / peak}
+        # end-to-end with host buffers
+        t0 = time.perf_counter()
+        for _ in range(10):
+            rm.score_paths(Zh, [5000.0], 1.0)
+        out[f'{name}_integral_e2e_ms'] = (time.perf_counter() - t0) * 100
+    Z = torch.from_numpy(Zc).to(dev)
+    ms = ev_time(torch, lambda: prob.score(Z), 10, 2)
+    out['analytic_corridor'] = {'ms': ms, 'value': B * (Wp - 1) / (ms * 1e-3), 'shapes': 256 + 32,
+                                'note': 'fp64 analytic scorer (Problem.get_cost + collides), compute-bound'}
+    print(json.dumps(out))
+    del rm, Z
+
+    if args.skip_c4:
+        return
+    # ---------------- C4 ------------------------------------------------------------------------------------
+    n = args.c4_size
+    sys.path.insert(0, ROOT)
+    from bench import make_raster
+    layers, occ0, _ = make_raster(torch, dev, n)
+    dem = (layers[0] * 557.5).contiguous()
+    dem[dem <= 0] = -9999.0                               # sea = nodata, like merge_test.tif
+    del layers, occ0
+    eng = uam.Engine()
+    cells = n * n
+    res = {'config': f'C4: map rebuild at {n}^2, 4096 rectangular footprints (integer-metre corners)', 'unit': 'Mcell/s',
+           'hbm_peak_GBps': peak}
+    ms = ev_time(torch, lambda: eng.dem_mask(dem, 0.0), args.reps)
+    res['dem_mask'] = {'ms': ms, 'Mcell_s': cells / ms / 1e3, 'frac': cells * 5 / (ms * 1e-3) / 1e9 / peak}
+    del dem
+    KMn = 64.0 * n / 8192
+    mm = uam.RegionMap()
+    for r in ('Land', 'Population', 'Hist'):
+        mm.new_region(r, 'r')
+    for k in range(4096):
+        c, a = rng.uniform(1, KMn - 1, 2), rng.uniform(0, np.pi)
+        hw, hh = rng.uniform(0.45, 0.9, 2)                 # area > 0.78 km^2 like data_processor.py:9,32
+        R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        V = np.trunc((c + np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]]) @ R.T) * 1000) / 1000   # integer metres
+        sh = uam.polygon(*V.tolist())
+        mm.add_obstacle(sh)
+        mm.add_shape_to_region(('Land', 'Population', 'Hist')[k % 3], sh)
+    eng.set_shapes(mm.obstacles, mm._region_lists())
+    geo = (0.0, KMn / n, 0.0, KMn / n)
+    occ = eng.rasterize_occupancy(n, n, geo)
+    ms = ev_time(torch, lambda: eng.rasterize_occupancy(n, n, geo), args.reps, 1)
+    res['occupancy'] = {'ms': ms, 'Mcell_s': cells / ms / 1e3, 'frac': cells * 1 / (ms * 1e-3) / 1e9 / peak,
+                        'occupied_fraction': float(occ.float().mean().item())}
+    ms = ev_time(torch, lambda: eng.rasterize_layers(n, n, geo, 0.0), args.reps, 1)
+    res['risk_layers_x3'] = {'ms': ms, 'Mcell_s': cells / ms / 1e3, 'frac': cells * 12 / (ms * 1e-3) / 1e9 / peak}
+    ms = ev_time(torch, lambda: eng.edt(occ, KMn / n), args.reps, 1)
+    res['edt_clearance'] = {'ms': ms, 'Mcell_s': cells / ms / 1e3, 'frac': cells * (1 + 16 + 4) / (ms * 1e-3) / 1e9 / peak}
+    tot = res['dem_mask']['ms'] + res['occupancy']['ms'] + res['risk_layers_x3']['ms'] + res['edt_clearance']['ms']
+    res['total'] = {'ms': tot, 'Mcell_s': cells / tot / 1e3, 'frac': cells * 21 / (tot * 1e-3) / 1e9 / peak}
+    # CPU baseline on a crop: scipy EDT (1 core)
+    from scipy import ndimage
+    crop = occ[:2048, :2048].cpu().numpy()
+    t0 = time.perf_counter()
+    ndimage.distance_transform_edt(crop == 0)
+    res['cpu_edt_scipy_Mcell_s'] = crop.size / (time.perf_counter() - t0) / 1e6
+    print(json.dumps(res))
+
+
+if __name__ == '__main__':
+    main()
