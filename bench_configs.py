@@ -38,6 +38,7 @@ def main():
     ap.add_argument('--c4-size', type=int, default=16384)
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--skip-c4', action='store_true')
+    ap.add_argument('--c5-queries', type=int, default=16)
     args = ap.parse_args()
     import torch
     import uam_path_planning_b200 as uam
@@ -148,6 +149,28 @@ def main():
     ndimage.distance_transform_edt(crop == 0)
     res['cpu_edt_scipy_Mcell_s'] = crop.size / (time.perf_counter() - t0) / 1e6
     print(json.dumps(res))
+    del occ, mm
+
+    # ---------------- C5 ------------------------------------------------------------------------------------
+    # batched cost-to-go: 4096^2 grid, one altitude band's uint16 cost, Q queries per launch (a 1024-query job is
+    # 1024/Q launches per GPU x 8 GPUs; queries are independent, so it shards like the paths do)
+    n5, Q = 4096, args.c5_queries
+    g = torch.Generator(device=dev).manual_seed(5)
+    cost = torch.randint(1, 1000, (n5, n5), device=dev, generator=g, dtype=torch.int32).to(torch.uint16)
+    blk = (torch.rand((n5, n5), device=dev, generator=g) < 0.1).to(torch.uint8)
+    src = torch.randint(0, n5, (Q, 2), device=dev, generator=g, dtype=torch.int32)
+    blk[src[:, 0].long(), src[:, 1].long()] = 0
+    l0 = eng.launch_count()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dist, parent = eng.grid_search(cost, src, blk)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    reach = float((dist < 2 ** 62).float().mean().item())
+    print(json.dumps({'config': f'C5: cost-to-go on a {n5}^2 8-connected grid, {Q} queries per launch, 1 B200',
+                      'seconds': dt, 'queries_per_s': Q / dt, 'Mcell_per_s': Q * n5 * n5 / dt / 1e6,
+                      'kernel_launches': eng.launch_count() - l0, 'reachable_fraction': reach,
+                      'note': 'exact distances + parents (bit-identical to Dijkstra); tile label-correcting relaxation'}))
 
 
 if __name__ == '__main__':

@@ -202,6 +202,17 @@ int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, double dx, doubl
 int uam_edt(uam_ctx* ctx, const uint8_t* d_occ, int H, int W, double cell, int32_t* d_dist2,
             float* d_clearance, void* stream);
 
+/* ---- grid search / cost-to-go (build-defined extension; the reference has none: SURVEY.md section 0) ----------
+ * Q independent single-source cost-to-go sweeps on an 8-connected H x W grid with integer edge costs
+ * step(u,v) * (cost[u] + cost[v]), step = 2 (axis) / 3 (diagonal); blocked cells (nullable) are impassable.
+ * d_cost (H,W) uint16, d_sources (Q,2) int32 (row, col); outputs d_dist (Q,H,W) int64 (2^62 = unreachable) and
+ * d_parent (Q,H,W) int32 (nullable): flat index of the best predecessor, ties to the lowest neighbour slot in the
+ * order (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1); parent[source] = source, unreachable = -1.
+ * Frontier-parallel tile relaxation; results are bit-identical to Dijkstra.  Synchronises `stream` internally
+ * (the number of relaxation rounds is data dependent). */
+int uam_grid_search(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int H, int W,
+                    const int32_t* d_sources, int Q, int64_t* d_dist, int32_t* d_parent, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

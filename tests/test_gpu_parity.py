@@ -418,3 +418,74 @@ def test_raster_scorer_full_size_properties(uam, torch):
         torch.testing.assert_close((c - c0).double(), torch.full((B,), 8.0 * 0.5 * Wp / (Wp - 2), device=dev, dtype=torch.float64),
                                    rtol=1e-4, atol=8e-3)
         assert bool(k.all())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# grid search / cost-to-go (build-defined extension) vs the oracle's Dijkstra
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('H,W,wall', [(45, 70, True), (33, 32, False), (64, 97, True), (5, 3, False)])
+def test_grid_search_exact(uam, torch, H, W, wall):
+    rng = np.random.default_rng(H * 100 + W)
+    cost = rng.integers(1, 2000, (H, W)).astype(np.uint16)
+    cost[rng.uniform(size=(H, W)) < 0.05] = 65535                     # expensive cells
+    blocked = (rng.uniform(size=(H, W)) < 0.15).astype(np.uint8)
+    if wall:
+        blocked[H // 2, :] = 1
+        blocked[H // 2, W // 3] = 0                                   # one gap in a wall: long detours
+        blocked[: H // 4, W - 2] = 1                                  # sealed-off corner -> unreachable cells
+        blocked[H // 4, W - 2:] = 1
+    srcs = []
+    free = np.argwhere(blocked == 0)
+    for _ in range(3):
+        srcs.append(free[rng.integers(len(free))].tolist())
+    srcs.append(np.argwhere(blocked == 1)[0].tolist())                # a blocked source: everything unreachable
+    dist, parent = uam.Engine().grid_search(torch.from_numpy(cost).cuda(), srcs, torch.from_numpy(blocked).cuda())
+    dist, parent = dist.cpu().numpy(), parent.cpu().numpy()
+    for q, s in enumerate(srcs):
+        d_ref, p_ref = orc.grid_search(cost, tuple(s), blocked)
+        assert np.array_equal(dist[q], d_ref), q                      # bit-exact distances
+        assert np.array_equal(parent[q].astype(np.int64), p_ref), q   # bit-exact parent indices
+    assert (dist[3] == 2 ** 62).all() and (parent[3] == -1).all()
+    d2, _ = uam.Engine().grid_search(torch.from_numpy(cost).cuda(), srcs[:1], None, want_parent=False)
+    assert np.array_equal(d2[0].cpu().numpy(), orc.grid_search(cost, tuple(srcs[0]), None)[0])
+
+
+def test_grid_search_large_properties(uam, torch):
+    """1024^2 grid, 4 queries: triangle property on every edge (dist is a fixed point of the relaxation) and
+    following parents from random cells reaches the source with the recorded distance."""
+    dev = 'cuda'
+    H = W = 1024
+    g = torch.Generator(device=dev).manual_seed(5)
+    cost = torch.randint(1, 500, (H, W), device=dev, generator=g, dtype=torch.int32).to(torch.uint16)
+    blocked = (torch.rand((H, W), device=dev, generator=g) < 0.2).to(torch.uint8)
+    srcs = [[10, 10], [512, 700], [1000, 20], [300, 300]]
+    for s in srcs:
+        blocked[s[0], s[1]] = 0
+    dist, parent = uam.Engine().grid_search(cost, srcs, blocked)
+    c = cost.to(torch.int64)
+    INF = 2 ** 62
+    for (di, dj, stp) in [(0, 1, 2), (1, 0, 2), (1, 1, 3), (1, -1, 3)]:
+        a = dist[:, max(0, -di):H - max(0, di), max(0, -dj):W - max(0, dj)]
+        b = dist[:, max(0, di):H - max(0, -di), max(0, dj):W - max(0, -dj)]
+        ca = c[max(0, -di):H - max(0, di), max(0, -dj):W - max(0, dj)]
+        cb = c[max(0, di):H - max(0, -di), max(0, dj):W - max(0, -dj)]
+        w = stp * (ca + cb)
+        ok = (a >= INF) | (b >= INF) | ((a - b).abs() <= w)
+        assert bool(ok.all())
+    dist_h, par_h, cost_h = dist.cpu().numpy(), parent.cpu().numpy(), cost.cpu().numpy().astype(np.int64)
+    rng = np.random.default_rng(1)
+    for q, s in enumerate(srcs):
+        assert dist_h[q, s[0], s[1]] == 0 and par_h[q, s[0], s[1]] == s[0] * W + s[1]
+        for _ in range(20):
+            v = int(rng.integers(H * W))
+            if dist_h[q].flat[v] >= INF:
+                assert par_h[q].flat[v] == -1
+                continue
+            total, steps = 0, 0
+            while v != s[0] * W + s[1]:
+                u = int(par_h[q].flat[v])
+                diag = (abs(u // W - v // W) + abs(u % W - v % W)) == 2
+                total += (3 if diag else 2) * (cost_h.flat[u] + cost_h.flat[v])
+                assert dist_h[q].flat[u] + (3 if diag else 2) * (cost_h.flat[u] + cost_h.flat[v]) == dist_h[q].flat[v]
+                v, steps = u, steps + 1
+                assert steps < H * W

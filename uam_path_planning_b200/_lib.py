@@ -58,6 +58,7 @@ SIGNATURES = {
     'uam_rasterize_occupancy': (_i, [_vp, _i, _i, _d, _d, _d, _d, _vp, _vp]),
     'uam_rasterize_layers': (_i, [_vp, _i, _i, _d, _d, _d, _d, _d, _vp, _vp]),
     'uam_edt': (_i, [_vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
+    'uam_grid_search': (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -301,6 +301,24 @@ class Engine:
                                       C.c_void_p(cl.data_ptr()) if cl is not None else None, st))
         return d2, cl
 
+    def grid_search(self, cost, sources, blocked=None, want_parent: bool = True):
+        """Q cost-to-go sweeps on an 8-connected grid (build-defined extension, include/uam_b200.h).
+        cost (H,W) uint16 CUDA tensor, sources (Q,2) int32 (row, col), blocked (H,W) uint8 or None ->
+        (dist (Q,H,W) int64 with 2**62 = unreachable, parent (Q,H,W) int32 | None)."""
+        import torch
+        assert _is_tensor(cost) and cost.dtype == torch.uint16 and cost.dim() == 2
+        sources = torch.as_tensor(sources, dtype=torch.int32, device=cost.device).reshape(-1, 2).contiguous()
+        st = self._tensor_args(cost, sources, blocked)
+        H, W = cost.shape
+        Q = sources.shape[0]
+        dist = torch.empty((Q, H, W), dtype=torch.int64, device=cost.device)
+        parent = torch.empty((Q, H, W), dtype=torch.int32, device=cost.device) if want_parent else None
+        self._check(self._lib.uam_grid_search(
+            self._h, C.c_void_p(cost.data_ptr()), C.c_void_p(blocked.data_ptr()) if blocked is not None else None, H, W,
+            C.c_void_p(sources.data_ptr()), Q, C.c_void_p(dist.data_ptr()),
+            C.c_void_p(parent.data_ptr()) if parent is not None else None, st))
+        return dist, parent
+
     # ---- single-shape queries (QuadraticObstacle.contains / penalty_function, Function.__call__) -----------------
     def _scratch(self) -> 'Engine':
         if getattr(self, '_scratch_engine', None) is None:
