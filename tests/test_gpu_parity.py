@@ -489,3 +489,17 @@ def test_grid_search_large_properties(uam, torch):
                 assert dist_h[q].flat[u] + (3 if diag else 2) * (cost_h.flat[u] + cost_h.flat[v]) == dist_h[q].flat[v]
                 v, steps = u, steps + 1
                 assert steps < H * W
+
+
+def test_edt_mixed_fast_and_slow_rows(uam, torch):
+    """Tall raster with seeds only in the top rows: rows near the seeds finish in the outward search, rows farther
+    than its radius (1024 columns) are flagged and go through the lower-envelope path -- both in one call."""
+    H, W = 2600, 64
+    occ = np.zeros((H, W), dtype=np.uint8)
+    occ[0:3, ::5] = 1
+    occ[1, 7] = 1
+    d2, cl = uam.Engine().edt(torch.from_numpy(occ).cuda(), 2.0)
+    ref = orc.edt_sq(occ)
+    assert np.array_equal(d2.cpu().numpy().astype(np.int64), ref)
+    assert ref.max() > 1100 ** 2
+    np.testing.assert_allclose(cl.cpu().numpy(), np.sqrt(ref) * 2.0, rtol=1e-6)

@@ -181,6 +181,7 @@ extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
     cudaFree(ctx->d_psic);
     cudaFree(ctx->d_tex);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_cull_scratch);
     for (int i = 0; i <= UAM_HOST_PIPE_DEPTH; ++i) cudaFree(ctx->d_bin_scratch[i]);
     for (int i = 0; i < UAM_HOST_PIPE_DEPTH; ++i) {
         cudaFree(ctx->d_stage_in[i]);

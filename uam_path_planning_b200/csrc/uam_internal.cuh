@@ -85,7 +85,9 @@ struct uam_ctx {
     size_t stage_out_bytes[UAM_HOST_PIPE_DEPTH] = {};
     void* h_stage_out[UAM_HOST_PIPE_DEPTH] = {};   // pinned
     size_t h_stage_out_bytes[UAM_HOST_PIPE_DEPTH] = {};
-    void* d_scratch = nullptr;          // EDT
+    void* d_cull_scratch = nullptr;     // rasteriser: coarse (supertile) shape lists
+    size_t cull_scratch_bytes = 0;
+    void* d_scratch = nullptr;          // EDT, grid search
     size_t scratch_bytes = 0;
     // optional CUDA-event timing of the dominant scoring kernel (UAM_OPT_TIME_KERNELS), read by uam_ctx_get_stat
     int time_kernels = 0;

@@ -72,18 +72,21 @@ __device__ __forceinline__ bool uam_edge_excludes_tile(const UamEdge& r, double 
     return hmin > thr + 1e-9 * scale + 1e-300;
 }
 
-// Ordered compaction of the shapes [s_begin, s_end) that survive the tile test into list[0..n) (n <= CAP).
-// Returns the next shape index to continue from.  Must be called by all threads of a 256-thread CTA.
-__device__ int uam_cull_shapes(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, int s_begin,
-                               int s_end, double xa, double xb, double ya, double yb, double thr, int* list, int* n_out,
-                               int* warp_cnt) {
+// Ordered compaction of the candidates at positions [s_begin, s_end) that survive the tile test into list[0..n)
+// (n <= CAP).  A candidate is shape cand[p] (or shape p itself when cand is NULL).  Returns the next position to
+// continue from.  Must be called by all threads of a 256-thread CTA.
+__device__ int uam_cull_shapes(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes,
+                               const int* __restrict__ cand, int s_begin, int s_end, double xa, double xb, double ya,
+                               double yb, double thr, int* list, int* n_out, int* warp_cnt) {
     int n = 0;
     int s0 = s_begin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     while (s0 < s_end && n + (int)blockDim.x <= UAM_LIST_CAP) {
-        const int s = s0 + threadIdx.x;
+        const int pos = s0 + threadIdx.x;
         bool keep = false;
-        if (s < s_end) {
+        int s = 0;
+        if (pos < s_end) {
+            s = cand ? __ldg(cand + pos) : pos;
             const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
             keep = true;
             for (int i = meta.x; i < meta.y && keep; ++i) {
@@ -109,6 +112,39 @@ __device__ int uam_cull_shapes(const UamEdge* __restrict__ edges, const UamShape
     return min(s0, s_end);
 }
 
+// Coarse pass: one CTA per 256 x 256-cell supertile keeps, in shape order, the shapes of [s_begin, s_end) that can
+// matter anywhere in the supertile; the per-tile kernels then only test those (two-level culling).
+#define UAM_SUPER 256
+__global__ void __launch_bounds__(256)
+uam_k_cull_coarse(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, int s_begin, int s_end,
+                  double thr, int H, int W, double x0, double dx, double y0, double dy, int* __restrict__ out_list,
+                  int* __restrict__ out_count) {
+    __shared__ int list[UAM_LIST_CAP];
+    __shared__ int warp_cnt[8];
+    const int sup = blockIdx.y * gridDim.x + blockIdx.x;
+    const int j0 = blockIdx.x * UAM_SUPER, i0 = blockIdx.y * UAM_SUPER;
+    const int j1 = min(j0 + UAM_SUPER, W), i1 = min(i0 + UAM_SUPER, H);
+    const double xe0 = x0 + j0 * dx, xe1 = x0 + j1 * dx, ye0 = y0 + i0 * dy, ye1 = y0 + i1 * dy;
+    const double xa = fmin(xe0, xe1), xb = fmax(xe0, xe1), ya = fmin(ye0, ye1), yb = fmax(ye0, ye1);
+    int* dst = out_list + (size_t)sup * (s_end - s_begin);
+    int total = 0;
+    int s_next = s_begin;
+    while (s_next < s_end) {
+        int n;
+        s_next = uam_cull_shapes(edges, shapes, nullptr, s_next, s_end, xa, xb, ya, yb, thr, list, &n, warp_cnt);
+        for (int t = threadIdx.x; t < n; t += blockDim.x) dst[total + t] = list[t];
+        total += n;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_count[sup] = total;
+}
+
+__device__ __forceinline__ int uam_supertile_of_block() {
+    // fine tiles are 16 rows x 64 columns: 16 tile-rows x 4 tile-columns per supertile
+    const int sup_x = (gridDim.x + 3) / 4;
+    return (blockIdx.y / (UAM_SUPER / UAM_TILE_H)) * sup_x + blockIdx.x / (UAM_SUPER / UAM_TILE_W);
+}
+
 __device__ __forceinline__ double uam_cell_centre(int j, double x0, double dx) {
     return __dadd_rn(x0, __dmul_rn(__dadd_rn((double)j, 0.5), dx));     // x0 + (j + 1/2) * dx
 }
@@ -118,7 +154,8 @@ __device__ __forceinline__ double uam_cell_centre(int j, double x0, double dx) {
 // -------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 uam_k_rasterize_occupancy(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, int n_obs, int H,
-                          int W, double x0, double dx, double y0, double dy, uint8_t* __restrict__ occ) {
+                          int W, double x0, double dx, double y0, double dy, const int* __restrict__ coarse_list,
+                          const int* __restrict__ coarse_count, uint8_t* __restrict__ occ) {
     __shared__ int list[UAM_LIST_CAP];
     __shared__ int warp_cnt[8];
     const int tj0 = blockIdx.x * UAM_TILE_W, ti0 = blockIdx.y * UAM_TILE_H;
@@ -132,10 +169,13 @@ uam_k_rasterize_occupancy(const UamEdge* __restrict__ edges, const UamShape* __r
 #pragma unroll
     for (int c = 0; c < 4; ++c) x[c] = uam_cell_centre(j + c, x0, dx);
     bool in_any[4] = {false, false, false, false};
+    const int sup = uam_supertile_of_block();
+    const int* cand = coarse_list + (size_t)sup * n_obs;
+    const int n_cand = coarse_count[sup];
     int s_next = 0;
-    while (s_next < n_obs) {
+    while (s_next < n_cand) {
         int n;
-        s_next = uam_cull_shapes(edges, shapes, s_next, n_obs, xa, xb, ya, yb, 1e-14, list, &n, warp_cnt);
+        s_next = uam_cull_shapes(edges, shapes, cand, s_next, n_cand, xa, xb, ya, yb, 1e-14, list, &n, warp_cnt);
         for (int t = 0; t < n; ++t) {
             const int s = list[t];
             const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
@@ -174,7 +214,8 @@ struct UamRegionRanges2 {
 __global__ void __launch_bounds__(256)
 uam_k_rasterize_layers(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes,
                        const double* __restrict__ psic, UamRegionRanges2 rr, int n_regions, int H, int W, double x0,
-                       double dx, double y0, double dy, double e, float* __restrict__ layers) {
+                       double dx, double y0, double dy, double e, const int* __restrict__ coarse_list,
+                       const int* __restrict__ coarse_count, int n_super, float* __restrict__ layers) {
     __shared__ int list[UAM_LIST_CAP];
     __shared__ int warp_cnt[8];
     const int tj0 = blockIdx.x * UAM_TILE_W, ti0 = blockIdx.y * UAM_TILE_H;
@@ -188,14 +229,17 @@ uam_k_rasterize_layers(const UamEdge* __restrict__ edges, const UamShape* __rest
 #pragma unroll
     for (int c = 0; c < 4; ++c) x[c] = uam_cell_centre(j + c, x0, dx);
     const size_t plane = (size_t)H * W;
+    const int sup = uam_supertile_of_block();
     for (int r = 0; r < n_regions; ++r) {
         double tot[4] = {0.0, 0.0, 0.0, 0.0};
-        int s_next = rr.begin[r];
-        const int s_end = rr.begin[r + 1];
+        // region r's coarse lists start after those of regions 0..r-1: n_super * (shapes before r) entries
+        const int* cand = coarse_list + (size_t)n_super * (rr.begin[r] - rr.begin[0]) + (size_t)sup * (rr.begin[r + 1] - rr.begin[r]);
+        const int s_end = coarse_count[r * n_super + sup];
+        int s_next = 0;
         while (s_next < s_end) {
             int n;
             // psi != 0 needs h_i - e < 0 for every i: cull when some h_i > e on the whole tile
-            s_next = uam_cull_shapes(edges, shapes, s_next, s_end, xa, xb, ya, yb, e, list, &n, warp_cnt);
+            s_next = uam_cull_shapes(edges, shapes, cand, s_next, s_end, xa, xb, ya, yb, e, list, &n, warp_cnt);
             for (int t = 0; t < n; ++t) {
                 const int s = list[t];
                 const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
@@ -234,31 +278,131 @@ uam_k_rasterize_layers(const UamEdge* __restrict__ edges, const UamShape* __rest
 }
 
 // -------------------------------------------------------------------------------------------------------
-// exact EDT: column scan -> transpose -> per-row lower envelope (Meijster) -> transpose back
+// exact EDT (squared Euclidean distance to the nearest occupied cell), two separable phases:
+//   phase 1  g(i,j) = distance along column j to the nearest occupied cell.  Banded: per (256-row band, column) find
+//            the first/last occupied row, a per-column scan over the band summaries gives every band the nearest
+//            occupied row above and below it, a second banded sweep writes g.  (band x column) threads instead of
+//            one thread per column.
+//   phase 2  d2(i,u) = min_v (u-v)^2 + g(i,v)^2.
+//            fast path: one thread per cell searches outwards, delta = 1, 2, ... until delta^2 >= best (no farther
+//            column can win) -- O(distance) per cell, the row staged in shared memory.  Exact whenever it stops
+//            within UAM_EDT_R columns; otherwise the row is flagged.
+//            slow path, flagged rows only (sparse maps): transpose -> per-row lower envelope (Meijster) with an
+//            explicit stack in HBM -> transpose back.  All its kernels return at once when no row is flagged.
+// Integer arithmetic throughout: bit-exact against scipy's EDT.
 // -------------------------------------------------------------------------------------------------------
 #define UAM_GINF (1 << 20)   // "no occupied cell in this column" (> any real distance; its square fits int64)
+#define UAM_EDT_BAND 256
+#define UAM_EDT_R 1024
+#define UAM_EDT_CLIP 32768   // fast path: g clipped here (its square is 2^30 = the "none" value of d2)
 
-// thread per column: g[i][j] = distance (cells) to the nearest occupied cell in column j
 __global__ void __launch_bounds__(128)
-uam_k_edt_columns(const uint8_t* __restrict__ occ, int H, int W, int* __restrict__ g) {
+uam_k_edt_band_summary(const uint8_t* __restrict__ occ, int H, int W, int* __restrict__ band_first, int* __restrict__ band_last) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int band = blockIdx.y;
+    if (j >= W) return;
+    const int i0 = band * UAM_EDT_BAND, i1 = min(i0 + UAM_EDT_BAND, H);
+    int first = -1, last = -1;
+#pragma unroll 8
+    for (int i = i0; i < i1; ++i) {
+        if (occ[(size_t)i * W + j]) {
+            if (first < 0) first = i;
+            last = i;
+        }
+    }
+    band_first[(size_t)band * W + j] = first;
+    band_last[(size_t)band * W + j] = last;
+}
+
+// per column: nearest occupied row strictly above the band (above[band]) and below it (below[band]); -1 = none
+__global__ void __launch_bounds__(128)
+uam_k_edt_band_carry(int n_bands, int W, const int* __restrict__ band_first, const int* __restrict__ band_last,
+                     int* __restrict__ above, int* __restrict__ below) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= W) return;
-    int d = UAM_GINF;
-    for (int i = 0; i < H; ++i) {
-        d = occ[(size_t)i * W + j] ? 0 : min(d + 1, UAM_GINF);
-        g[(size_t)i * W + j] = d;
+    int run = -1;
+    for (int b = 0; b < n_bands; ++b) {
+        above[(size_t)b * W + j] = run;
+        const int l = band_last[(size_t)b * W + j];
+        if (l >= 0) run = l;
     }
-    d = UAM_GINF;
-    for (int i = H - 1; i >= 0; --i) {
+    run = -1;
+    for (int b = n_bands - 1; b >= 0; --b) {
+        below[(size_t)b * W + j] = run;
+        const int f = band_first[(size_t)b * W + j];
+        if (f >= 0) run = f;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+uam_k_edt_band_sweep(const uint8_t* __restrict__ occ, int H, int W, const int* __restrict__ above,
+                     const int* __restrict__ below, int* __restrict__ g) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int band = blockIdx.y;
+    if (j >= W) return;
+    const int i0 = band * UAM_EDT_BAND, i1 = min(i0 + UAM_EDT_BAND, H);
+    int last = above[(size_t)band * W + j];
+#pragma unroll 8
+    for (int i = i0; i < i1; ++i) {
+        if (occ[(size_t)i * W + j]) last = i;
+        g[(size_t)i * W + j] = last >= 0 ? i - last : UAM_GINF;
+    }
+    int next = below[(size_t)band * W + j];
+#pragma unroll 8
+    for (int i = i1 - 1; i >= i0; --i) {
         const int cur = g[(size_t)i * W + j];
-        d = cur == 0 ? 0 : min(d + 1, UAM_GINF);
+        if (cur == 0) next = i;
+        const int d = next >= 0 ? next - i : UAM_GINF;
         if (d < cur) g[(size_t)i * W + j] = d;
     }
 }
 
-// out[c][r] = in[r][c]   (in: R x C)
+// phase 2 fast path: block = UAM_EDT_SPAN consecutive cells of one row (4 per thread), the row segment and
+// UAM_EDT_R columns on either side staged in shared memory
+#define UAM_EDT_SPAN 1024
 __global__ void __launch_bounds__(256)
-uam_k_transpose_i32(const int* __restrict__ in, int R, int C, int* __restrict__ out) {
+uam_k_edt_rows_fast(const int* __restrict__ g, int H, int W, int* __restrict__ d2, uint8_t* __restrict__ row_flag,
+                    int* __restrict__ any_flag) {
+    __shared__ int sg[UAM_EDT_SPAN + 2 * UAM_EDT_R];
+    const int i = blockIdx.y;
+    const int u0 = blockIdx.x * UAM_EDT_SPAN;
+    const int* grow = g + (size_t)i * W;
+    for (int t = threadIdx.x; t < UAM_EDT_SPAN + 2 * UAM_EDT_R; t += 256) {
+        const int col = u0 - UAM_EDT_R + t;
+        sg[t] = (col >= 0 && col < W) ? min(grow[col], UAM_EDT_CLIP) : UAM_EDT_CLIP;
+    }
+    __syncthreads();
+    bool unresolved = false;
+#pragma unroll
+    for (int k = 0; k < UAM_EDT_SPAN / 256; ++k) {
+        const int off = k * 256 + threadIdx.x;
+        const int u = u0 + off;
+        if (u < W) {
+            const int c = UAM_EDT_R + off;
+            int best = sg[c] * sg[c];
+            int delta = 1;
+            for (; delta <= UAM_EDT_R; ++delta) {
+                const int dd = delta * delta;
+                if (dd >= best) break;
+                const int m = min(sg[c - delta], sg[c + delta]);
+                best = min(best, dd + m * m);
+            }
+            unresolved = unresolved || (delta > UAM_EDT_R && (UAM_EDT_R + 1) * (UAM_EDT_R + 1) < best);
+            d2[(size_t)i * W + u] = best;
+        }
+    }
+    if (__syncthreads_or(unresolved) && threadIdx.x == 0) {
+        row_flag[i] = 1;
+        *any_flag = 1;
+    }
+}
+
+// out[c][r] = in[r][c]   (in: R x C).  mode 0: plain; mode 1: only columns c of `in` whose flag[c] is set (forward
+// transpose of g, rows of the result = raster columns... see uam_edt); mode 2: only rows r whose flag... (see call sites)
+__global__ void __launch_bounds__(256)
+uam_k_transpose_i32(const int* __restrict__ in, int R, int C, int* __restrict__ out, const int* __restrict__ any_flag,
+                    const uint8_t* __restrict__ out_row_flag) {
+    if (any_flag && *any_flag == 0) return;
     __shared__ int tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -269,7 +413,8 @@ uam_k_transpose_i32(const int* __restrict__ in, int R, int C, int* __restrict__ 
     __syncthreads();
     for (int k = ty; k < 32; k += 8) {
         const int c = c0 + k, r = r0 + tx;
-        if (r < R && c < C) out[(size_t)c * R + r] = tile[tx][k];
+        // out_row_flag (optional) selects which rows of `out` (= columns c of `in`) are written
+        if (r < R && c < C && (!out_row_flag || out_row_flag[c])) out[(size_t)c * R + r] = tile[tx][k];
     }
 }
 
@@ -278,11 +423,13 @@ struct __align__(16) UamEdtEntry {
     long long gsq;
 };
 
-// thread per row i; gT[u][i] = g(i, u).  Stack entry q of row i lives at stack[q * H + i].
+// slow path: thread per FLAGGED row i; gT[u][i] = g(i, u).  Stack entry q of row i lives at stack[q * H + i].
 __global__ void __launch_bounds__(128)
-uam_k_edt_rows(const int* __restrict__ gT, int H, int W, UamEdtEntry* __restrict__ stack, int* __restrict__ dT) {
+uam_k_edt_rows(const int* __restrict__ gT, int H, int W, UamEdtEntry* __restrict__ stack, int* __restrict__ dT,
+               const int* __restrict__ any_flag, const uint8_t* __restrict__ row_flag) {
+    if (*any_flag == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= H) return;
+    if (i >= H || !row_flag[i]) return;
     int q = 0;
     UamEdtEntry top;
     {
@@ -365,8 +512,15 @@ extern "C" int uam_rasterize_occupancy(uam_ctx* ctx, int H, int W, double x0, do
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     dim3 grid((W + UAM_TILE_W - 1) / UAM_TILE_W, (H + UAM_TILE_H - 1) / UAM_TILE_H);
     if (grid.y > 65535) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "H too large");
-    uam_k_rasterize_occupancy<<<grid, 256, 0, uam_pick_stream(ctx, stream)>>>(ctx->d_edges, ctx->d_shapes, ctx->n_obs, H, W,
-                                                                               x0, dx, y0, dy, d_occ);
+    cudaStream_t st = uam_pick_stream(ctx, stream);
+    dim3 sgrid((W + UAM_SUPER - 1) / UAM_SUPER, (H + UAM_SUPER - 1) / UAM_SUPER);
+    const size_t n_super = (size_t)sgrid.x * sgrid.y;
+    UAM_TRY(uam_reserve(ctx, &ctx->d_cull_scratch, &ctx->cull_scratch_bytes, (n_super * (size_t)std::max(ctx->n_obs, 1) + n_super) * 4));
+    int* clist = (int*)ctx->d_cull_scratch;
+    int* ccount = clist + n_super * (size_t)std::max(ctx->n_obs, 1);
+    uam_k_cull_coarse<<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, 0, ctx->n_obs, 1e-14, H, W, x0, dx, y0, dy, clist, ccount);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_cull_coarse");
+    uam_k_rasterize_occupancy<<<grid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->n_obs, H, W, x0, dx, y0, dy, clist, ccount, d_occ);
     UAM_CHECK_LAUNCH(ctx, "uam_k_rasterize_occupancy");
     return UAM_OK;
 }
@@ -385,8 +539,20 @@ extern "C" int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, doubl
     for (int r = 0; r <= ctx->n_regions; ++r) rr.begin[r] = ctx->region_begin[r];
     dim3 grid((W + UAM_TILE_W - 1) / UAM_TILE_W, (H + UAM_TILE_H - 1) / UAM_TILE_H);
     if (grid.y > 65535) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "H too large");
+    dim3 sgrid((W + UAM_SUPER - 1) / UAM_SUPER, (H + UAM_SUPER - 1) / UAM_SUPER);
+    const size_t n_super = (size_t)sgrid.x * sgrid.y;
+    const int n_reg_shapes = rr.begin[ctx->n_regions] - rr.begin[0];
+    UAM_TRY(uam_reserve(ctx, &ctx->d_cull_scratch, &ctx->cull_scratch_bytes,
+                        (n_super * (size_t)std::max(n_reg_shapes, 1) + n_super * ctx->n_regions) * 4));
+    int* clist = (int*)ctx->d_cull_scratch;
+    int* ccount = clist + n_super * (size_t)std::max(n_reg_shapes, 1);
+    for (int r = 0; r < ctx->n_regions; ++r) {
+        uam_k_cull_coarse<<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, rr.begin[r], rr.begin[r + 1], enlargement, H, W, x0, dx,
+                                                  y0, dy, clist + n_super * (size_t)(rr.begin[r] - rr.begin[0]), ccount + (size_t)r * n_super);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_cull_coarse");
+    }
     uam_k_rasterize_layers<<<grid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
-                                                 y0, dy, enlargement, d_layers);
+                                                 y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
     UAM_CHECK_LAUNCH(ctx, "uam_k_rasterize_layers");
     return UAM_OK;
 }
@@ -399,23 +565,44 @@ extern "C" int uam_edt(uam_ctx* ctx, const uint8_t* d_occ, int H, int W, double 
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = uam_pick_stream(ctx, stream);
     const size_t n = (size_t)H * W;
-    // scratch: g (n i32) | gT (n i32) | dT (n i32) | [d2 when the caller wants only clearance] | stack (n x 16 B)
-    const size_t need = n * 4 * 4 + n * sizeof(UamEdtEntry) + 256;
+    const int n_bands = (H + UAM_EDT_BAND - 1) / UAM_EDT_BAND;
+    const size_t bw = (size_t)n_bands * W;
+    // scratch: g | gT | dT | [d2] (n i32 each) | band_first, band_last, above, below (bw i32 each) | any_flag | row_flag (H)
+    //          | stack (n x 16 B, slow path only -- allocated always so the call never has to synchronise)
+    const size_t need = n * 4 * 4 + bw * 4 * 4 + 256 + ((size_t)H + 255) + n * sizeof(UamEdtEntry) + 256;
     UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, need));
     int* g = (int*)ctx->d_scratch;
     int* gT = g + n;
     int* dT = gT + n;
     int* d2 = d_dist2 ? d_dist2 : dT + n;
-    UamEdtEntry* stack = (UamEdtEntry*)(((uintptr_t)(dT + 2 * n) + 15) & ~(uintptr_t)15);
-    uam_k_edt_columns<<<(W + 127) / 128, 128, 0, st>>>(d_occ, H, W, g);
-    UAM_CHECK_LAUNCH(ctx, "uam_k_edt_columns");
+    int* band_first = dT + 2 * n;
+    int* band_last = band_first + bw;
+    int* above = band_last + bw;
+    int* below = above + bw;
+    int* any_flag = below + bw;
+    uint8_t* row_flag = (uint8_t*)(any_flag + 16);
+    UamEdtEntry* stack = (UamEdtEntry*)(((uintptr_t)(row_flag + H) + 255) & ~(uintptr_t)255);
+    UAM_CUDA(ctx, cudaMemsetAsync(any_flag, 0, 64 + (size_t)H, st));
+    // phase 1
+    dim3 bgrid((W + 127) / 128, n_bands);
+    uam_k_edt_band_summary<<<bgrid, 128, 0, st>>>(d_occ, H, W, band_first, band_last);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_edt_band_summary");
+    uam_k_edt_band_carry<<<(W + 127) / 128, 128, 0, st>>>(n_bands, W, band_first, band_last, above, below);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_edt_band_carry");
+    uam_k_edt_band_sweep<<<bgrid, 128, 0, st>>>(d_occ, H, W, above, below, g);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_edt_band_sweep");
+    // phase 2, fast path
+    dim3 fgrid((W + UAM_EDT_SPAN - 1) / UAM_EDT_SPAN, H);
+    uam_k_edt_rows_fast<<<fgrid, 256, 0, st>>>(g, H, W, d2, row_flag, any_flag);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_edt_rows_fast");
+    // phase 2, slow path for flagged rows (every kernel returns immediately when none is flagged)
     dim3 tg((W + 31) / 32, (H + 31) / 32);
-    uam_k_transpose_i32<<<tg, 256, 0, st>>>(g, H, W, gT);
+    uam_k_transpose_i32<<<tg, 256, 0, st>>>(g, H, W, gT, any_flag, nullptr);
     UAM_CHECK_LAUNCH(ctx, "uam_k_transpose_i32");
-    uam_k_edt_rows<<<(H + 127) / 128, 128, 0, st>>>(gT, H, W, stack, dT);
+    uam_k_edt_rows<<<(H + 127) / 128, 128, 0, st>>>(gT, H, W, stack, dT, any_flag, row_flag);
     UAM_CHECK_LAUNCH(ctx, "uam_k_edt_rows");
     dim3 tg2((H + 31) / 32, (W + 31) / 32);
-    uam_k_transpose_i32<<<tg2, 256, 0, st>>>(dT, W, H, d2);
+    uam_k_transpose_i32<<<tg2, 256, 0, st>>>(dT, W, H, d2, any_flag, row_flag);
     UAM_CHECK_LAUNCH(ctx, "uam_k_transpose_i32");
     if (d_clearance) {
         uam_k_edt_clearance<<<ctx->sm_count * 8, 256, 0, st>>>(d2, (long long)n, cell, d_clearance);

@@ -263,14 +263,27 @@ uam_k_score_raster_wp(const double2* __restrict__ z, long long B, int Wp, UamRas
         float pen_sum = 0.0f;
         double len_sum = 0.0;
         bool col = false;
-        for (int j = lane; j < Wp; j += 32) {
+        // two waypoints per lane per trip: 8 texel gathers in flight before the first lerp (DRAM-latency bound)
+        for (int j = lane; j < Wp; j += 64) {
+            const int j2 = j + 32;
+            const bool two = j2 < Wp;
             const double2 p = zp[j];
+            const double2 q = zp[two ? j2 : j];
+            UamTap<TF> ta, tb;
+            uam_tap_load<TF, LAYOUT>(tex, rp, uam_pix(p.x, rp.x0, rp.dx), uam_pix(p.y, rp.y0, rp.dy), ta);
+            uam_tap_load<TF, LAYOUT>(tex, rp, uam_pix(q.x, rp.x0, rp.dx), uam_pix(q.y, rp.y0, rp.dy), tb);
+            len_sum += uam_len_term(zp, j, N, p, rp);
+            if (two) len_sum += uam_len_term(zp, j2, N, q, rp);
             float pen;
             bool occ;
-            uam_sample<TF, LAYOUT>(tex, rp, uam_pix(p.x, rp.x0, rp.dx), uam_pix(p.y, rp.y0, rp.dy), pen, occ);
+            uam_tap_eval<TF>(rp, ta, pen, occ);
             pen_sum += pen;
             col = col || occ;
-            len_sum += uam_len_term(zp, j, N, p, rp);
+            uam_tap_eval<TF>(rp, tb, pen, occ);
+            if (two) {
+                pen_sum += pen;
+                col = col || occ;
+            }
         }
         pen_sum = uam_warp_sum(pen_sum);
         len_sum = uam_warp_sum(len_sum);
