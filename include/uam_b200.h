@@ -117,6 +117,13 @@ int uam_map_set_raster(uam_ctx* ctx, const float* h_layers, int L, int H, int W,
 int uam_map_set_raster_device(uam_ctx* ctx, const float* d_layers, int L, int H, int W, double x0,
                               double dx, double y0, double dy, const uint8_t* d_occupancy, void* stream);
 
+/* ---- candidates ---------------------------------------------------------------------------------------
+ * Solver.create_x_init (path_generation/solver.py:103-136) for B displacements at once: d_z (B, 2(N+2)) float64
+ * receives [start, arc through start and goal with sagitta d_b |goal-start|/2 (straight line for d_b = 0), goal].
+ * h_ends = [x_start(2), x_goal(2)]; |d_b| <= 1 is the caller's check (the reference raises ValueError). */
+int uam_make_arc_paths(uam_ctx* ctx, const double* h_ends, int N, const double* d_displacement, int64_t B,
+                       double* d_z, void* stream);
+
 /* ---- path scoring: analytic shapes -------------------------------------------------------------
  * Replaces, batched over B paths:
  *   d_cost[b]    = Problem.get_cost(z_)                      path_generation/problem.py:38-44

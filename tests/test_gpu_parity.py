@@ -503,3 +503,26 @@ def test_edt_mixed_fast_and_slow_rows(uam, torch):
     assert np.array_equal(d2.cpu().numpy().astype(np.int64), ref)
     assert ref.max() > 1100 ** 2
     np.testing.assert_allclose(cl.cpu().numpy(), np.sqrt(ref) * 2.0, rtol=1e-6)
+
+
+@pytest.mark.parametrize('N', [80, 62, 5, 1])
+def test_device_candidate_generator(uam, torch, fixture_spec, golden, N):
+    """Solver.candidates_device == Solver.create_x_init (solver.py:103-136) for a sweep of displacements."""
+    prob = build_product_problem(fixture_spec, N)
+    sol = uam.Solver(prob, {})
+    disp = np.concatenate([golden['arc_disp'], np.linspace(-0.99, 0.99, 37), [0.0, 1.0, -1.0, 1e-9]])
+    Zd = sol.candidates_device(torch.from_numpy(disp).cuda()).cpu().numpy()
+    Zh = sol.candidates(disp)
+    assert Zd.shape == Zh.shape == (len(disp), 2 * (N + 2))
+    scale = np.abs(Zh).max()
+    big = np.abs(disp) > 1e-6                      # tiny |d|: radius ~ 1/d amplifies the last-ulp differences of sin/cos
+    np.testing.assert_allclose(Zd[big], Zh[big], rtol=0, atol=1e-12 * scale)
+    np.testing.assert_allclose(Zd[~big], Zh[~big], rtol=0, atol=1e-6 * scale)
+    assert np.array_equal(Zd[disp == 0], Zh[disp == 0])             # straight line: same bits
+    if N in (80, 62, 5):
+        np.testing.assert_allclose(Zd[:5, 2:-2], golden[f'arc_N{N}_x'], rtol=0, atol=1e-12 * scale)
+    with pytest.raises(ValueError):
+        sol.candidates_device(torch.tensor([0.2, 1.5], dtype=torch.float64).cuda())
+    # generated on the device, scored on the device: same costs as the host-generated candidates
+    c_d = prob.get_cost(sol.candidates_device(torch.from_numpy(disp[big]).cuda())).cpu().numpy()
+    np.testing.assert_allclose(c_d, prob.get_cost(Zh[big]), rtol=1e-9)

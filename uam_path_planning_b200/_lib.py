@@ -43,6 +43,7 @@ SIGNATURES = {
     'uam_map_set_shapes': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i]),
     'uam_map_set_raster': (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _vp]),
     'uam_map_set_raster_device': (_i, [_vp, _vp, _i, _i, _i, _d, _d, _d, _d, _vp, _vp]),
+    'uam_make_arc_paths': (_i, [_vp, _vp, _i, _vp, _i64, _vp, _vp]),
     'uam_score_paths_analytic': (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     'uam_score_paths_analytic_host': (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _vp, _vp, _vp]),
     'uam_analytic_g_len': (_i, [_vp, _i, C.POINTER(_i64)]),

@@ -249,6 +249,19 @@ class Engine:
                                                  int(bool(smooth)), _np_ptr(out)))
         return out
 
+    def make_arc_paths(self, x_start, x_goal, N: int, displacements):
+        """Solver.create_x_init for a CUDA tensor of displacements -> (B, 2(N+2)) float64 paths incl. start and goal."""
+        import torch
+        assert _is_tensor(displacements) and displacements.dtype == torch.float64 and displacements.dim() == 1
+        st = self._tensor_args(displacements)
+        if bool((displacements.abs() > 1).any()):
+            raise ValueError(f'abs(displacement) = {float(displacements.abs().max())} must be smaller than 1')
+        ends = _f64c(np.concatenate([np.ravel(x_start), np.ravel(x_goal)]))
+        Z = torch.empty((displacements.numel(), 2 * (int(N) + 2)), dtype=torch.float64, device=displacements.device)
+        self._check(self._lib.uam_make_arc_paths(self._h, _np_ptr(ends), int(N), C.c_void_p(displacements.data_ptr()),
+                                                 displacements.numel(), C.c_void_p(Z.data_ptr()), st))
+        return Z
+
     def best(self, cost, global_offset: int = 0, key=None):
         """min over b of (float32 bits of cost[b] << 32 | global_offset + b) as a 1-element int64 CUDA tensor
         (costs >= 0, so the key is a non-negative int64 and orders like (cost, index))."""

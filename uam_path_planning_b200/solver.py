@@ -76,6 +76,12 @@ class Solver:
             X = X + rng.normal(0.0, jitter, X.shape)
         return self.full_path(X)
 
+    def candidates_device(self, displacements):
+        """The same arc family generated on the GPU from a CUDA tensor of displacements (8 bytes of input per
+        candidate): (B, 2(N+2)) float64 CUDA tensor, ready for Problem.score / RasterMap.score_paths."""
+        m = self.problem.map
+        return m.engine().make_arc_paths(m.x_start, m.x_goal, self.problem.N, displacements)
+
     def evaluate_candidates(self, Z) -> Dict:
         """Score a batch and pick the best like main.py:162-180: fval = sqrt(cost) (solver.py:48), strict `<`
         so ties keep the earliest candidate; also the shortest by the non-smooth length (solver.py:49)."""
