@@ -526,3 +526,69 @@ def test_device_candidate_generator(uam, torch, fixture_spec, golden, N):
     # generated on the device, scored on the device: same costs as the host-generated candidates
     c_d = prob.get_cost(sol.candidates_device(torch.from_numpy(disp[big]).cuda())).cpu().numpy()
     np.testing.assert_allclose(c_d, prob.get_cost(Zh[big]), rtol=1e-9)
+
+
+@pytest.mark.parametrize('variant', [0, 2])
+def test_degenerate_paths_do_not_disturb_the_batch(uam, torch, variant):
+    """NaN / inf / far-outside waypoints and zero-length segments: the call returns, rows without such values keep
+    exactly the bits they have in a clean batch, far-outside rows clamp to the raster border like the oracle."""
+    rng = np.random.default_rng(9)
+    H, W, geo = 120, 90, (0.0, 0.5, 0.0, 0.5)
+    lay, occ = _random_raster(rng, 3, H, W)
+    rm = uam.RasterMap.from_arrays(lay, geo, occ, options={'integral_variant': variant})
+    Z = _random_paths(rng, 40, 16, geo, H, W)
+    clean_c, clean_k = rm.score_paths(torch.from_numpy(Z).cuda(), [1.0, 2.0, 3.0], 1.0)
+    Zb = Z.copy()
+    Zb[3, 5] = np.nan
+    Zb[7, 0] = np.inf
+    Zb[11, 8:12] = 400.0                                # far outside: hundreds of clamped samples
+    Zb[13, :] = Zb[13, 0]                               # all waypoints coincide (zero-length segments)
+    Zb[17, 2:] = np.tile(Zb[17, :2], 15)                # same with distinct x / y
+    for spc in (0.0, 1.0):
+        c, k = rm.score_paths(torch.from_numpy(Zb).cuda(), [1.0, 2.0, 3.0], spc)
+        c, k = c.cpu().numpy(), k.cpu().numpy()
+        ok = np.ones(40, dtype=bool)
+        ok[[3, 7, 11, 13, 17]] = False
+        if spc == 1.0:
+            assert np.array_equal(c[ok], clean_c.cpu().numpy()[ok]) and np.array_equal(k[ok], clean_k.cpu().numpy()[ok])
+        c_ref, k_ref, _ = orc.score_paths_raster(lay, occ, geo, Zb[[11, 13, 17]], [1.0, 2.0, 3.0], spc, True, None)
+        np.testing.assert_allclose(c[[11, 13, 17]], c_ref, rtol=RTOL_RASTER)
+        assert np.array_equal(k[[11, 13, 17]].astype(bool), k_ref)
+        assert np.isnan(c[3])
+
+
+def test_c_abi_argument_checks(uam):
+    """The C ABI never aborts: bad arguments come back as error codes with a message."""
+    import ctypes as C
+    from uam_path_planning_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.uam_ctx_create(0, C.byref(h)) == 0
+    assert lib.uam_ctx_create(10 ** 6, C.byref(C.c_void_p())) == -2
+    p = (C.c_double * 8)(0, 0, 0, 0, 1, 0.1, 0, 1.0)
+    z = (C.c_double * 24)()
+    out = (C.c_double * 4)()
+    assert lib.uam_score_paths_analytic_host(h, z, 1, 10, p, 8, 0, out, None, None) == -4      # no shapes yet
+    assert b'uam_map_set_shapes' in lib.uam_last_error(h)
+    assert lib.uam_map_set_shapes(h, None, 0, None, None, None, 0, 0) == 0                      # an empty map is legal
+    assert lib.uam_score_paths_analytic_host(h, z, 1, 10, p, 8, 0, out, None, None) == -1      # 1 weight, 0 regions
+    assert lib.uam_score_paths_analytic_host(h, z, 1, 10, p, 7, 0, out, None, None) == 0       # empty map: cost = length term
+    assert lib.uam_score_paths_analytic_host(h, None, 1, 10, p, 7, 0, out, None, None) == -1
+    assert lib.uam_score_paths_analytic_host(h, z, -1, 10, p, 7, 0, out, None, None) == -1
+    assert lib.uam_score_paths_analytic_host(h, z, 1, 0, p, 7, 0, out, None, None) == -1
+    assert lib.uam_score_paths_analytic_host(h, z, 1, 10, p, 3, 0, out, None, None) == -1
+    bad = (C.c_double * 8)(7, 0, 0, 0, 0, 0, 0, 0)
+    off = (C.c_int32 * 2)(0, 1)
+    reg = (C.c_int32 * 1)(-1)
+    cen = (C.c_double * 2)(0, 0)
+    assert lib.uam_map_set_shapes(h, bad, 1, off, reg, cen, 1, 0) == -1                         # unknown inequality kind
+    assert lib.uam_score_paths_raster_host(h, z, 1, 10, p, 8, 0, 1.0, None, None) == -4         # no raster
+    lay = (C.c_float * 16)()
+    assert lib.uam_map_set_raster(h, lay, 1, 1, 16, 0.0, 1.0, 0.0, 1.0, None) == -1             # H < 2
+    assert lib.uam_map_set_raster(h, lay, 1, 4, 4, 0.0, 0.0, 0.0, 1.0, None) == -1              # dx == 0
+    assert lib.uam_map_set_raster(h, lay, 1, 4, 4, 0.0, 1.0, 0.0, 1.0, None) == 0
+    assert lib.uam_score_paths_raster_host(h, z, 1, 10, p, 8, 0, 100.0, None, None) == -1       # samples_per_cell > 64
+    assert lib.uam_score_paths_raster_host(h, z, 1, 10, p, 8, 0, 1.0, None, None) == 0          # outputs are nullable
+    assert lib.uam_ctx_set_option(h, 99, 0) == -1 and lib.uam_ctx_set_option(h, 2, 5) == -1
+    assert lib.uam_edt(h, None, 4, 4, 1.0, None, None, None) == -1
+    assert lib.uam_ctx_destroy(h) == 0 and lib.uam_ctx_destroy(None) == 0
