@@ -107,6 +107,7 @@ extern "C" int uam_ctx_create(int device, uam_ctx** out) {
     // tuning knobs from the environment (bench A/B runs); uam_ctx_set_option overrides
     if (const char* e = getenv("UAM_RASTER_LAYOUT")) ctx->raster_layout = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = std::min(2, std::max(-1, atoi(e)));
+    if (const char* e = getenv("UAM_HOST_CHUNKS")) ctx->host_chunks = std::max(0, atoi(e));
     if (const char* e = getenv("UAM_L2_FETCH_GRANULARITY")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
     *out = ctx;
     return UAM_OK;

@@ -58,6 +58,7 @@ struct uam_ctx {
     uint64_t launches = 0;
     // tuning knobs (uam_ctx_set_option / environment at ctx creation)
     int raster_layout = 1;    // layout used by the next uam_map_set_raster*
+    int host_chunks = 0;      // *_host raster scoring: pipeline chunks per call (0 = default)
     int int_variant = -1;     // integral mode: -1 = auto (2 for large batches, else 0); 0 = warp per path, lane per sample; 1 = lane pair per sample;
                               // 2 = segments binned by raster tile, warp per segment (L2-resident raster)
 

@@ -900,8 +900,8 @@ extern "C" int uam_score_paths_raster_host(uam_ctx* ctx, const double* h_z, int6
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     UAM_CUDA(ctx, cudaDeviceSynchronize());
     const size_t row = (size_t)2 * (N + 2) * sizeof(double);
-    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>((B + 2 * UAM_HOST_PIPE_DEPTH - 1) / (2 * UAM_HOST_PIPE_DEPTH),
-                                                                      (int64_t)((64u << 20) / row)));
+    const int n_chunks = ctx->host_chunks > 0 ? ctx->host_chunks : 2 * UAM_HOST_PIPE_DEPTH;
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>((B + n_chunks - 1) / n_chunks, (int64_t)((64u << 20) / row)));
     int c = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, ++c) {
         const int s = c % UAM_HOST_PIPE_DEPTH;
