@@ -141,6 +141,13 @@ int uam_score_paths_analytic_host(uam_ctx* ctx, const double* h_z, int64_t B, in
                                   int n_p, int flags, double* h_cost, uint8_t* h_collide, double* h_g);
 int uam_analytic_g_len(const uam_ctx* ctx, int N, int64_t* len);
 
+/* Gradient of Problem.get_cost with respect to every waypoint: d_grad (B, 2(N+2)) float64, same layout as d_z
+ * (columns 2 .. 2N+1 are the solver's decision variables z_1..z_N, solver.py:59); d_cost nullable.  The reference gets
+ * this derivative from CasADi's algorithmic differentiation inside OpEn (solver.py:82-101); here it is analytic, fp64.
+ * Needs UAM_PENALTY_SMOOTH.  The length term follows get_cost (last segment absent, problem.py:39,140-145). */
+int uam_grad_paths_analytic(uam_ctx* ctx, const double* d_z, int64_t B, int N, const double* h_p, int n_p, int flags,
+                            double* d_cost, double* d_grad, void* stream);
+
 /* Problem.length_of(x, smooth) (problem.py:130-146) for B rows of M points each (x is (B, 2M) float64):
  * y = [map.x_start; x; map.x_goal], out = sum of nrm(y_{k+1} - y_k) over the FIRST N+1 pairs (N <= M).
  * M = N reproduces Solver.solve's call (solver.py:49), M = N+2 the call inside get_cost (problem.py:39).

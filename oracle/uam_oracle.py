@@ -569,3 +569,64 @@ def grid_search(cost: np.ndarray, start: Tuple[int, int], blocked: np.ndarray = 
                     best, bp = nd, u
         parent[v] = bp
     return dist.reshape(H, W), parent.reshape(H, W)
+
+
+# --------------------------------------------------------------------------- #
+# gradient of get_cost w.r.t. the waypoints (extension: the reference gets it from CasADi's AD inside OpEn,
+# solver.py:82-101; no in-tree counterpart).  Pinned by central finite differences of get_cost above.
+# --------------------------------------------------------------------------- #
+def _grad_h(edge, X):
+    x0, x1 = X[:, 0], X[:, 1]
+    if edge[0] == 'line':
+        _, Ax, Ay, Bx, By, sgn = edge
+        return np.stack([np.full_like(x0, -sgn * (By - Ay)), np.full_like(x0, sgn * (Bx - Ax))], axis=1)
+    if edge[0] == 'ellipse':
+        _, cx, cy, r1, r2 = edge
+        return np.stack([2 * ((x0 - cx) / r1) / r1, 2 * ((x1 - cy) / r2) / r2], axis=1)
+    _, axis, sign, c, r = edge
+    g = np.zeros((X.shape[0], 2))
+    g[:, axis] = 1.0 if sign > 0 else -1.0
+    return g
+
+
+def psi_grad(shape: OShape, X, e: float = 0.0):
+    """(psi, grad psi) at points X for the smooth penalty: grad psi = psi * sum_i 2 grad h_i / m_i where all m_i < 0."""
+    X = np.asarray(X, dtype=F64).reshape(-1, 2)
+    Hm = np.minimum(shape.h(X) - e, 0.0)                       # (n_edges, M)
+    psi = np.prod(Hm ** 2, axis=0) if Hm.shape[0] else np.ones(X.shape[0])
+    inside = np.all(Hm < 0, axis=0)
+    s = np.zeros((X.shape[0], 2))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        for i, edge in enumerate(shape.edges):
+            s += np.where(inside[:, None], 2 * _grad_h(edge, X) / Hm[i][:, None], 0.0)
+    return psi, psi[:, None] * s
+
+
+def get_cost_gradient(m: OMap, z_, N: int, weights: Sequence[float], e: float = 0.0, options: Dict = None) -> np.ndarray:
+    """d get_cost / d z_ (same shape as z_, start and goal columns included), penalty_smooth only."""
+    opts = dict(DEFAULT_OPTIONS)
+    if options:
+        opts.update(options)
+    assert opts['penalty_smooth']
+    z_ = np.asarray(z_, dtype=F64)
+    B = z_.shape[0]
+    P = z_.reshape(B, N + 2, 2)
+    G = np.zeros_like(P)
+    for (name, shapes), w in zip(m.regions, weights):
+        for s in shapes:
+            psi, gp = psi_grad(s, P.reshape(-1, 2), e)
+            pc = s.psi(s.center.reshape(1, 2), True, e)[0] if (s.center is not None and not np.isnan(s.center).any()) else 1.0
+            G += (w * gp / pc).reshape(B, N + 2, 2) / N
+    # length term: pairs (m_s, z_0), (z_0, z_1), ..., (z_{N-1}, z_N)
+    Y = np.concatenate([np.broadcast_to(m.x_start, (B, 1, 2)), P], axis=1)      # Y_0 = m_s, Y_{k+1} = z_k
+    for k in range(N + 1):
+        d = Y[:, k + 1] - Y[:, k]
+        if opts['length_smooth']:
+            gk = 2 * d
+        else:
+            with np.errstate(divide='ignore', invalid='ignore'):
+                gk = d / _norm2(d)[:, None]
+        G[:, k] += (N + 1) * gk                   # d/d z_k   (z_k = Y_{k+1})
+        if k >= 1:
+            G[:, k - 1] -= (N + 1) * gk           # d/d z_{k-1}
+    return G.reshape(B, 2 * (N + 2))

@@ -592,3 +592,32 @@ def test_c_abi_argument_checks(uam):
     assert lib.uam_ctx_set_option(h, 99, 0) == -1 and lib.uam_ctx_set_option(h, 2, 5) == -1
     assert lib.uam_edt(h, None, 4, 4, 1.0, None, None, None) == -1
     assert lib.uam_ctx_destroy(h) == 0 and lib.uam_ctx_destroy(None) == 0
+
+
+def test_cost_gradient(uam, torch, fixture_spec, golden):
+    """Problem.get_cost_gradient: cost equals get_cost (goldens), gradient equals the oracle's analytic gradient
+    (itself pinned by finite differences of the reference-pinned cost, tests/test_oracle_golden.py)."""
+    f = fixture_spec
+    N = 62
+    om = orc.OMap(f)
+    Z = full_paths(f, golden['jit_x'])
+    for opts, e in [({}, 0.0), ({'length_smooth': False}, 0.3), ({}, -0.25)]:
+        prob = build_product_problem(f, N, options=opts, enlargement=e)
+        cost, grad = prob.get_cost_gradient(Z)
+        o = dict(f['options'], **opts)
+        np.testing.assert_allclose(cost, orc.get_cost(om, Z, N, f['weights'], e, o), rtol=RTOL_ANALYTIC)
+        Gref = orc.get_cost_gradient(om, Z, N, f['weights'], e, o)
+        assert grad.shape == Gref.shape == Z.shape
+        np.testing.assert_allclose(grad, Gref, rtol=1e-10, atol=1e-9)
+        assert np.abs(grad[:, -2:]).max() == 0.0 or np.abs(Gref[:, -2:] - grad[:, -2:]).max() < 1e-9   # goal: penalty part only
+    c1, g1 = prob.get_cost_gradient(Z[4])
+    assert isinstance(c1, float) and g1.shape == (2 * (N + 2),) and np.array_equal(g1, grad[4])
+    ct, gt = prob.get_cost_gradient(torch.from_numpy(Z).cuda())
+    assert np.array_equal(gt.cpu().numpy(), grad)
+    # one projected-gradient step on the free waypoints lowers the cost (the use the reference's solver makes of it)
+    step = 1e-6
+    Z2 = Z.copy()
+    Z2[:, 2:-2] -= step * grad[:, 2:-2]
+    assert np.all(prob.get_cost(Z2) < cost)
+    with pytest.raises(uam.UamError):
+        build_product_problem(f, N, options={'penalty_smooth': False}).get_cost_gradient(Z)

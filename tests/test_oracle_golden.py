@@ -172,3 +172,23 @@ def test_raster_reduces_to_analytic(omap, fixture_spec, golden):
     assert np.all(ns2 > ns[:4])
     assert np.max(np.abs(cost2 - ref[:4]) / ref[:4]) < 0.2
     assert np.all(col2 >= col[:4])
+
+
+def test_oracle_gradient_matches_finite_differences(omap, fixture_spec, golden):
+    """The analytic gradient restatement against central differences of the golden-pinned get_cost."""
+    f = fixture_spec
+    N = 62
+    Z = full_paths(f, golden['jit_x'][:3])
+    for opts, e in [(f['options'], 0.0), (dict(f['options'], length_smooth=False), 0.3)]:
+        G = orc.get_cost_gradient(omap, Z, N, f['weights'], e, opts)
+        rng = np.random.default_rng(0)
+        for col in rng.choice(2 * (N + 2), 24, replace=False):
+            if col < 2 and not opts['length_smooth']:
+                continue          # |z_0 - map.x_start| has a kink at 0: the derivative is NaN there (0/0), like AD's
+            h = 1e-6
+            Zp, Zm = Z.copy(), Z.copy()
+            Zp[:, col] += h
+            Zm[:, col] -= h
+            fd = (orc.get_cost(omap, Zp, N, f['weights'], e, opts) - orc.get_cost(omap, Zm, N, f['weights'], e, opts)) / (2 * h)
+            np.testing.assert_allclose(G[:, col], fd, rtol=2e-5, atol=2e-4)
+    assert np.nanmax(np.abs(G)) > 1.0 and np.isnan(G[:, :2]).all() and not np.isnan(G[:, 2:]).any()

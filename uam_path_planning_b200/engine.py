@@ -165,6 +165,23 @@ class Engine:
                                                             _np_ptr(cost), _np_ptr(col), _np_ptr(g)))
         return cost, col, g
 
+    def grad_analytic(self, Z, N: int, p, flags: int):
+        """Z (B, 2(N+2)) float64 -> (cost (B,), grad (B, 2(N+2))) of Problem.get_cost; numpy in -> numpy out, CUDA
+        tensor in -> CUDA tensors out."""
+        import torch
+        p = _f64c(p)
+        N = int(N)
+        host = not _is_tensor(Z)
+        if host:
+            Z = torch.from_numpy(_f64c(Z)).to(f'cuda:{self.device}')
+        assert Z.dtype == torch.float64 and Z.dim() == 2 and Z.shape[1] == 2 * (N + 2)
+        st = self._tensor_args(Z)
+        cost = torch.empty(Z.shape[0], dtype=torch.float64, device=Z.device)
+        grad = torch.empty_like(Z)
+        self._check(self._lib.uam_grad_paths_analytic(self._h, C.c_void_p(Z.data_ptr()), Z.shape[0], N, _np_ptr(p), p.size,
+                                                      flags, C.c_void_p(cost.data_ptr()), C.c_void_p(grad.data_ptr()), st))
+        return (cost.cpu().numpy(), grad.cpu().numpy()) if host else (cost, grad)
+
     def score_raster(self, Z, N: int, p, flags: int, samples_per_cell: float = 0.0, want_nsamples: bool = False,
                      out=None):
         """Z (B, 2(N+2)) float64 -> (cost f32 (B,), collide u8 (B,)[, nsamples i64 (B,)]).

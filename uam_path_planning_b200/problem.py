@@ -92,6 +92,14 @@ class Problem:
         """(N+1) * length_of(z) + sum_j penalty(z_j) / N   (problem.py:38-44)."""
         return self.score(z, want_g=False)[0]
 
+    def get_cost_gradient(self, z):
+        """(cost, d cost / d z_) for one path or a batch; z_ layout as get_cost, the gradient has the same shape (its
+        columns 2..2N+1 are the solver's decision variables, solver.py:59).  Analytic stand-in for the derivative
+        CasADi generates for OpEn (solver.py:82-101)."""
+        Z, single = self._batched(z)
+        cost, grad = self.map.engine().grad_analytic(Z, self.N, self.parameter_vector(), self.flags())
+        return (float(cost[0]), grad[0]) if single else (cost, grad)
+
     def get_nonlincon(self, z):
         """[ratio-hi, ratio-lo, angle] per interior waypoint, then psi_obstacle(z_j) per obstacle and waypoint
         (problem.py:84-114)."""
