@@ -503,7 +503,7 @@ __device__ __forceinline__ int uam_segment_bin(const UamSegRec& r, const UamRast
 
 #define UAM_BIN_CHUNK 8192     // segments per CTA in the histogram / scatter kernels
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 uam_k_bin_hist(const double2* __restrict__ z, unsigned long long n_seg, int Wp, UamRasterParams rp, UamBinGeo bg,
                unsigned short* __restrict__ seg_bin, unsigned* __restrict__ hist) {
     extern __shared__ int s_hist[];
@@ -556,7 +556,7 @@ uam_k_bin_scan(const unsigned* __restrict__ hist, int n, unsigned* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 uam_k_bin_scatter(const double2* __restrict__ z, unsigned long long n_seg, int Wp, UamRasterParams rp, UamBinGeo bg,
                   const unsigned short* __restrict__ seg_bin, unsigned* __restrict__ cursor, UamSegRec* __restrict__ recs) {
     extern __shared__ int s_hist[];
@@ -793,11 +793,11 @@ int uam_raster_launch_binned(uam_ctx* ctx, const double2* z, int64_t B, int Wp, 
         UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
         UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
     }
-    uam_k_bin_hist<<<chunks, 256, hsmem, st>>>(z, n_seg, Wp, rp, bg, seg_bin, hist);
+    uam_k_bin_hist<<<chunks, 1024, hsmem, st>>>(z, n_seg, Wp, rp, bg, seg_bin, hist);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_hist");
     uam_k_bin_scan<<<1, 1024, 0, st>>>(hist, bg.nbins, cursor);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_scan");
-    uam_k_bin_scatter<<<chunks, 256, hsmem, st>>>(z, n_seg, Wp, rp, bg, seg_bin, cursor, recs);
+    uam_k_bin_scatter<<<chunks, 1024, hsmem, st>>>(z, n_seg, Wp, rp, bg, seg_bin, cursor, recs);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_scatter");
     const size_t gsmem = (size_t)UAM_GROUP_SMEM * UAM_WARPS_PER_CTA;
     const unsigned long long n_groups = (n_seg + 31) >> 5;
