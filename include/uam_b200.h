@@ -85,12 +85,17 @@ enum {
     UAM_OPT_RASTER_LAYOUT = 1,        /* texel layout used by the next uam_map_set_raster*: 0 row-major, 1 tiled */
     UAM_OPT_INTEGRAL_VARIANT = 2,     /* integral mode: -1 auto (default: 2 for batches of >= 2^18 segments, else 0),
                                          0 warp per path / lane per sample, 1 lane pair per sample,
-                                         2 segments binned by raster tile, warp per 32 sorted segments */
+                                         2 segments binned by raster tile, warp per 32 sorted segments,
+                                         3 segments cut at 64 x 64-cell tile boundaries, pieces sorted by tile, the
+                                           tile staged in shared memory by one bulk async copy (cp.async.bulk) */
     UAM_OPT_L2_FETCH_GRANULARITY = 3, /* cudaLimitMaxL2FetchGranularity for this device: 32, 64 or 128 bytes */
-    UAM_OPT_TIME_KERNELS = 4          /* 1: bracket the dominant raster-scoring kernel of every device-pointer call with
+    UAM_OPT_TIME_KERNELS = 4,         /* 1: bracket the dominant raster-scoring kernel of every device-pointer call with
                                          CUDA events on the caller's stream (resets the statistics) */
+    UAM_OPT_COMBINE_LAYERS = 5        /* 1 (default): large-batch integral mode on L = 2..3 rasters samples ONE combined
+                                         layer sum_l w_l * layer_l (float2 texels, rebuilt when the weights or the raster
+                                         change) -- the penalty is linear in the layers; 0: always sample every layer */
 };
-/* statistics of UAM_OPT_TIME_KERNELS: mean device time (ms) of the dominant scoring kernel (uam_k_score_groups /
+/* statistics of UAM_OPT_TIME_KERNELS: mean device time (ms) of the dominant scoring kernel (uam_k_score_tiles / uam_k_score_groups /
  * uam_k_score_raster_int / uam_k_score_raster_wp) over the timed calls, and their number */
 enum { UAM_STAT_SCORE_KERNEL_MS_MEAN = 1, UAM_STAT_SCORE_KERNEL_COUNT = 2 };
 int uam_ctx_get_stat(uam_ctx* ctx, int stat, double* value);

@@ -329,7 +329,7 @@ def _random_paths(rng, B, Wp, geo, H, W, spill=0.0):
 
 @pytest.mark.parametrize('L', [1, 2, 3])
 @pytest.mark.parametrize('spc', [0.0, 1.0, 0.37, 2.5])
-@pytest.mark.parametrize('layout,variant', [(1, 1), (0, 0), (1, 0), (0, 1), (1, 2), (0, 2)])
+@pytest.mark.parametrize('layout,variant', [(1, 1), (0, 0), (1, 0), (0, 1), (1, 2), (0, 2), (1, 3), (0, 3)])
 def test_score_paths_raster_vs_oracle(uam, torch, L, spc, layout, variant):
     """Every texel layout (row-major / tiled; H, W not multiples of the tile) and integral-kernel variant (one lane or
     a lane pair per sample) against the oracle."""
@@ -372,8 +372,10 @@ def test_raster_reduces_to_analytic_reference(uam, fixture_spec, golden):
     assert np.mean(col.astype(bool) == golden['jit_collide'].any(axis=1)) > 0.9
 
 
-def test_raster_scorer_full_size_properties(uam, torch):
-    """BASELINE config 2 size (4096^2 raster, 10k paths x 64 waypoints) through size-independent properties."""
+@pytest.mark.parametrize('variant', [-1, 3])
+def test_raster_scorer_full_size_properties(uam, torch, variant):
+    """BASELINE config 2 size (4096^2 raster, 10k paths x 64 waypoints) through size-independent properties
+    (variant -1 = the automatic choice, 3 = the tile-staged pipeline forced)."""
     dev = 'cuda'
     H = W = 4096
     geo = (0.0, 64.0 / W, 0.0, 64.0 / H)
@@ -385,7 +387,7 @@ def test_raster_scorer_full_size_properties(uam, torch):
     e = torch.rand((B, 1, 2), device=dev, generator=g, dtype=torch.float64) * 64
     t = torch.linspace(0, 1, Wp, device=dev, dtype=torch.float64).reshape(1, Wp, 1)
     Z = (s + t * (e - s) + torch.randn((B, Wp, 2), device=dev, generator=g, dtype=torch.float64) * 0.03).reshape(B, 2 * Wp).contiguous()
-    rm = uam.RasterMap.from_arrays(lay, geo, occ)
+    rm = uam.RasterMap.from_arrays(lay, geo, occ, options={'integral_variant': variant})
     for spc in (0.0, 1.0):
         c1, k1, n1 = rm.score_paths(Z, [1.0], spc, want_nsamples=True)
         c3, _ = rm.score_paths(Z, [3.0], spc)
@@ -411,13 +413,55 @@ def test_raster_scorer_full_size_properties(uam, torch):
         torch.testing.assert_close(c0.double(), Lref, rtol=1e-6, atol=0)
         assert (n1 >= Wp).all() and ((n1 == Wp).all() if spc == 0 else (n1 > Wp).any())
     # constant raster: penalty = w * c * (N+2)/N exactly representable checks the sample weights sum to 1 per segment
-    rm2 = uam.RasterMap.from_arrays(torch.full((1, H, W), 0.5, device=dev), geo, torch.ones((H, W), device=dev, dtype=torch.uint8))
+    rm2 = uam.RasterMap.from_arrays(torch.full((1, H, W), 0.5, device=dev), geo, torch.ones((H, W), device=dev, dtype=torch.uint8),
+                                    options={'integral_variant': variant})
     for spc in (0.0, 1.0):
         c, k = rm2.score_paths(Z, [8.0], spc)
         c0, _ = rm2.score_paths(Z, [0.0], spc)
         torch.testing.assert_close((c - c0).double(), torch.full((B,), 8.0 * 0.5 * Wp / (Wp - 2), device=dev, dtype=torch.float64),
                                    rtol=1e-4, atol=8e-3)
         assert bool(k.all())
+
+
+@pytest.mark.parametrize('L', [1, 3])
+def test_tile_staged_hot_tiles_and_variants_agree(uam, torch, L):
+    """Corridor batch (one start / goal, arcs): thousands of pieces land in the start and goal tiles, so the
+    tile-staged pipeline (variant 3) splits those tiles into several work items.  Against the oracle, and against the
+    binned pipeline (same samples, different summation order: float32 rounding only); collision flags and sample
+    counts identical."""
+    rng = np.random.default_rng(77 + L)
+    H, W, geo = 300, 520, (-3.0, 0.125, 11.0, 0.125)
+    lay, occ = _random_raster(rng, L, H, W)
+    w = [200.0, 15000.0, 27000.0][:L]
+    B, Wp = 5000, 12
+    s, g = np.array([2.0, 15.0]), np.array([58.0, 44.0])
+    t = np.linspace(0, 1, Wp).reshape(1, Wp, 1)
+    bow = rng.uniform(-12, 12, (B, 1, 1)) * np.sin(np.pi * t) * np.array([0.45, -0.9])
+    Z = np.ascontiguousarray((s + t * (g - s) + bow + rng.normal(0, 0.05, (B, Wp, 2))).reshape(B, 2 * Wp))
+    Z[:, :2], Z[:, -2:] = s, g
+    c_ref, k_ref, ns_ref = orc.score_paths_raster(lay, occ, geo, Z, w, 1.0, True, None)
+    w_b = [7.0, 3.0, 0.5][:L]                        # a second weight vector: the combined-layer cache must follow it
+    c_ref_b, _, _ = orc.score_paths_raster(lay, occ, geo, Z, w_b, 1.0, True, None)
+    res = {}
+    Zt = torch.from_numpy(Z).cuda()
+    for variant in (2, 3):
+        for combine in (1, 0):
+            rm = uam.RasterMap.from_arrays(lay, geo, occ, options={'integral_variant': variant, 'combine_layers': combine})
+            c, k, ns = rm.score_paths(Zt, w, 1.0, True, None, want_nsamples=True)
+            r = res[variant, combine] = (c.cpu().numpy(), k.cpu().numpy(), ns.cpu().numpy())
+            np.testing.assert_allclose(r[0], c_ref, rtol=RTOL_RASTER)
+            assert np.array_equal(r[1].astype(bool), k_ref) and np.array_equal(r[2], ns_ref)
+            # a path alone == the same path inside the batch, bit for bit
+            c1, k1 = rm.score_paths(torch.from_numpy(Z[17:18].copy()).cuda(), w, 1.0, True, None)
+            assert c1.cpu().numpy()[0] == r[0][17] and k1.cpu().numpy()[0] == r[1][17]
+            # other weights, then the first ones again
+            cb, _ = rm.score_paths(Zt, w_b, 1.0, True, None)
+            np.testing.assert_allclose(cb.cpu().numpy(), c_ref_b, rtol=RTOL_RASTER)
+            ca, _ = rm.score_paths(Zt, w, 1.0, True, None)
+            assert np.array_equal(ca.cpu().numpy(), r[0])
+    for key in res:
+        np.testing.assert_allclose(res[key][0], res[2, 0][0], rtol=2e-6)
+    assert np.array_equal(res[3, 0][0], res[3, 1][0]) == (L == 1)     # L = 1 has nothing to combine
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -528,7 +572,7 @@ def test_device_candidate_generator(uam, torch, fixture_spec, golden, N):
     np.testing.assert_allclose(c_d, prob.get_cost(Zh[big]), rtol=1e-9)
 
 
-@pytest.mark.parametrize('variant', [0, 2])
+@pytest.mark.parametrize('variant', [0, 2, 3])
 def test_degenerate_paths_do_not_disturb_the_batch(uam, torch, variant):
     """NaN / inf / far-outside waypoints and zero-length segments: the call returns, rows without such values keep
     exactly the bits they have in a clean batch, far-outside rows clamp to the raster border like the oracle."""

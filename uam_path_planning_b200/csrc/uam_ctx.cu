@@ -106,7 +106,8 @@ extern "C" int uam_ctx_create(int device, uam_ctx** out) {
     }
     // tuning knobs from the environment (bench A/B runs); uam_ctx_set_option overrides
     if (const char* e = getenv("UAM_RASTER_LAYOUT")) ctx->raster_layout = atoi(e) ? 1 : 0;
-    if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = std::min(2, std::max(-1, atoi(e)));
+    if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = std::min(3, std::max(-1, atoi(e)));
+    if (const char* e = getenv("UAM_COMBINE_LAYERS")) ctx->combine_layers = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_HOST_CHUNKS")) ctx->host_chunks = std::max(0, atoi(e));
     if (const char* e = getenv("UAM_L2_FETCH_GRANULARITY")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
     *out = ctx;
@@ -121,13 +122,17 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             ctx->raster_layout = (int)value;
             return UAM_OK;
         case UAM_OPT_INTEGRAL_VARIANT:
-            if (value < -1 || value > 2) return uam_fail(ctx, UAM_ERR_INVALID, "integral variant must be -1 (auto), 0, 1 or 2");
+            if (value < -1 || value > 3) return uam_fail(ctx, UAM_ERR_INVALID, "integral variant must be -1 (auto), 0, 1, 2 or 3");
             ctx->int_variant = (int)value;
             return UAM_OK;
         case UAM_OPT_L2_FETCH_GRANULARITY:
             if (value != 32 && value != 64 && value != 128) return uam_fail(ctx, UAM_ERR_INVALID, "L2 fetch granularity must be 32, 64 or 128");
             UAM_CUDA(ctx, cudaSetDevice(ctx->device));
             UAM_CUDA(ctx, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+            return UAM_OK;
+        case UAM_OPT_COMBINE_LAYERS:
+            if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "combine_layers must be 0 or 1");
+            ctx->combine_layers = (int)value;
             return UAM_OK;
         case UAM_OPT_TIME_KERNELS:
             UAM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -184,6 +189,9 @@ extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_cull_scratch);
     for (int i = 0; i <= UAM_HOST_PIPE_DEPTH; ++i) cudaFree(ctx->d_bin_scratch[i]);
+    for (int i = 0; i <= UAM_HOST_PIPE_DEPTH; ++i) cudaFree(ctx->d_piece_scratch[i]);
+    cudaFree(ctx->d_tiles);
+    cudaFree(ctx->d_tex_comb);
     for (int i = 0; i < UAM_HOST_PIPE_DEPTH; ++i) {
         cudaFree(ctx->d_stage_in[i]);
         cudaFree(ctx->d_stage_out[i]);
@@ -390,6 +398,9 @@ extern "C" int uam_map_set_raster_device(uam_ctx* ctx, const float* d_layers, in
     ctx->geo.H = H; ctx->geo.W = W; ctx->geo.L = L; ctx->geo.texel_floats = tf;
     ctx->geo.layout = layout; ctx->geo.tiles_x = tiles_x; ctx->geo.tiles_y = tiles_y;
     ctx->has_raster = true;
+    ctx->tiles_valid = false;
+    ctx->comb_valid = false;
+    ctx->raster_gen += 1;
     return UAM_OK;
 }
 

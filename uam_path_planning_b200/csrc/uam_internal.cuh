@@ -59,8 +59,8 @@ struct uam_ctx {
     // tuning knobs (uam_ctx_set_option / environment at ctx creation)
     int raster_layout = 1;    // layout used by the next uam_map_set_raster*
     int host_chunks = 0;      // *_host raster scoring: pipeline chunks per call (0 = default)
-    int int_variant = -1;     // integral mode: -1 = auto (2 for large batches, else 0); 0 = warp per path, lane per sample; 1 = lane pair per sample;
-                              // 2 = segments binned by raster tile, warp per segment (L2-resident raster)
+    int int_variant = -1;     // integral mode: -1 = auto; 0 = warp per path, lane per sample; 1 = lane pair per sample;
+                              // 2 = segments binned by raster tile (L2-resident raster); 3 = pieces sorted by tile, tile staged in smem
 
     // device shape tables
     UamEdge* d_edges = nullptr;
@@ -98,6 +98,20 @@ struct uam_ctx {
     uint64_t time_count = 0;
     void* d_bin_scratch[UAM_HOST_PIPE_DEPTH + 1] = {};   // binned raster scorer: [0] caller stream, [1..] pipeline stages
     size_t bin_scratch_bytes[UAM_HOST_PIPE_DEPTH + 1] = {};
+    // tile-staged raster scorer (variant 3): tile-major copy of the texels (built on first use) + piece scratch
+    void* d_tiles = nullptr;
+    size_t tiles_bytes = 0;
+    bool tiles_valid = false;
+    uint64_t tiles_key = 0;             // which texel array the tile copy was made from
+    // weight-combined single-layer texels (float2) for the large-batch integral pipelines, per (raster, weights)
+    void* d_tex_comb = nullptr;
+    size_t tex_comb_bytes = 0;
+    bool comb_valid = false;
+    float comb_w[3] = {};
+    uint64_t comb_gen = 0, raster_gen = 0;
+    int combine_layers = 1;             // UAM_OPT_COMBINE_LAYERS
+    void* d_piece_scratch[UAM_HOST_PIPE_DEPTH + 1] = {};
+    size_t piece_scratch_bytes[UAM_HOST_PIPE_DEPTH + 1] = {};
 };
 
 int uam_fail(uam_ctx* ctx, int code, const char* fmt, ...);

@@ -36,6 +36,8 @@ struct UamRasterParams {
     float w0, w1, w2;
     int flags;
     int variant;          // integral-mode kernel, decided once per API call from the call's whole batch
+    int combined;         // 1: score on the weight-combined float2 texels (ctx->d_tex_comb, row stride row_stride2)
+    unsigned row_stride2;
 };
 
 template <int TF> struct UamTexel;
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(UAM_CTA_THREADS)
 uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRasterParams rp,
                        const typename UamTexel<TF>::T* __restrict__ tex, float* __restrict__ cost,
                        uint8_t* __restrict__ collide, long long* __restrict__ nsamp) {
-    extern __shared__ __align__(16) unsigned char uam_smem[];
+    extern __shared__ __align__(128) unsigned char uam_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
@@ -587,7 +589,7 @@ template <int TF, int LAYOUT>
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
 uam_k_score_groups(unsigned long long n_seg, UamRasterParams rp, const typename UamTexel<TF>::T* __restrict__ tex,
                    const UamSegRec* __restrict__ recs, float* __restrict__ part_pen, uint8_t* __restrict__ part_col) {
-    extern __shared__ __align__(16) unsigned char uam_smem[];
+    extern __shared__ __align__(128) unsigned char uam_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char* base = uam_smem + (size_t)warp * UAM_GROUP_SMEM;
@@ -737,6 +739,479 @@ uam_k_reduce_paths(const double2* __restrict__ z, long long B, int Wp, UamRaster
     }
 }
 
+// ---- integral mode, tile-staged (variant 3) ----------------------------------------------------------------------
+// The binned pipeline of variant 2 still gathers every texel through L1 (ncu: l1tex 98 % busy, 25 sectors per load
+// request).  Variant 3 removes the gather from the global-memory path altogether: every segment is cut into PIECES
+// at the boundaries of 64 x 64-cell raster tiles (a piece = a run of consecutive samples whose bilinear footprint
+// lies in one tile + its one-cell halo), the pieces are counting-sorted by tile, and a CTA stages the tile it works
+// on -- one contiguous 65 x 65-texel block of the tile-major raster copy -- into shared memory with a single bulk
+// async copy (TMA engine, cp.async.bulk + mbarrier) and then samples it with LDS.128 (4 immediate-offset loads per
+// sample, no tag lookups, no sector misses).
+//   uam_k_piece_count -> uam_k_scan_u32 (paths) + uam_k_tile_scan (tiles, work items) -> [host reads the piece
+//   total and sizes the scratch] -> uam_k_piece_scatter -> uam_k_score_tiles -> uam_k_reduce_slots
+// Sample positions are computed from the parent segment (U + s * SU, fp64, s counted from the segment start), so
+// they are bit-identical to the other variants and to the oracle; the cut points are found with the same
+// expression (estimate by division, then corrected until position(c-1) is inside and position(c) outside), so a
+// sample can never be assigned to a tile that does not hold its footprint.  Each piece writes its partial sum to a
+// slot that depends only on its own path (path-contiguous slot ranges from a prefix sum over per-path piece counts)
+// and the last kernel adds a path's slots in a fixed order: results are independent of the rest of the batch.
+#define UAM_TS 64                         // tile side in cells
+#define UAM_TSH (UAM_TS + 1)              // with the halo row / column
+#define UAM_ITEM_PIECES 2048              // pieces per work item (one tile load per item)
+
+struct __align__(16) UamPieceRec {
+    double U, V, SU, SV;   // parent segment: first sample (pixel coordinates) and per-sample step
+    int s0;                // first sample of the piece (counted from the segment start)
+    int n;                 // samples in the piece
+    float IS;              // 1 / S of the parent segment
+    unsigned slot;         // index of the piece's partial sum (path-contiguous)
+};
+
+struct UamTileGeo {
+    int tiles_x, tiles_y, ntiles;
+    unsigned tile_stride;  // bytes between tiles in the tile-major copy (multiple of 128)
+    unsigned copy_bytes;   // bytes staged per tile (multiple of 16)
+};
+
+__device__ __forceinline__ double uam_pos(double U, double SU, int s) { return __dadd_rn(U, __dmul_rn((double)s, SU)); }
+
+// Smallest s' in (s, S] whose sample leaves tile index t along one axis (n cells on that axis), S if none does.
+// position(s') is monotone in s', cell(s') = clamp(floor(position), 0, n - 2).
+__device__ __forceinline__ int uam_next_cross(double U, double SU, int s, int S, int t, int n) {
+    if (SU > 0.0) {
+        const int b = (t + 1) << 6;
+        if (b > n - 2) return S;                      // the clamp keeps the cell in this tile
+        const double bd = (double)b;
+        const double e = ceil(__ddiv_rn(__dsub_rn(bd, U), SU));
+        int c = s + 1;
+        if (e >= (double)S) c = S; else if (e > (double)c) c = (int)e;
+        while (c > s + 1 && uam_pos(U, SU, c - 1) >= bd) --c;
+        while (c < S && uam_pos(U, SU, c) < bd) ++c;
+        return c;
+    }
+    if (SU < 0.0) {
+        if (t == 0) return S;
+        const double bd = (double)(t << 6);           // outside once position < bd
+        const double e = ceil(__ddiv_rn(__dsub_rn(bd, U), SU));
+        int c = s + 1;
+        if (e >= (double)S) c = S; else if (e > (double)c) c = (int)e;
+        while (c > s + 1 && uam_pos(U, SU, c - 1) < bd) --c;
+        while (c < S && uam_pos(U, SU, c) >= bd) ++c;
+        return c;
+    }
+    return S;                                         // zero or NaN step: the cell never changes
+}
+
+// Calls emit(tile, s0, n, piece_index) for every piece of the segment, in order; returns the number of pieces.
+template <class F>
+__device__ __forceinline__ int uam_walk_pieces(const UamSegRec& r, const UamRasterParams& rp, int tiles_x, F&& emit) {
+    int s = 0, cnt = 0;
+    while (s < r.S) {
+        const double u = uam_pos(r.U, r.SU, s), v = uam_pos(r.V, r.SV, s);
+        const int tj = min(max(__double2int_rd(u), 0), rp.W - 2) >> 6;
+        const int ti = min(max(__double2int_rd(v), 0), rp.H - 2) >> 6;
+        const int nxt = min(uam_next_cross(r.U, r.SU, s, r.S, tj, rp.W), uam_next_cross(r.V, r.SV, s, r.S, ti, rp.H));
+        emit(ti * tiles_x + tj, s, nxt - s, cnt);
+        ++cnt;
+        s = nxt;
+    }
+    return cnt;
+}
+
+// warp per path, lanes stride the path's Wp units (Wp - 1 segments + the goal waypoint)
+__global__ void __launch_bounds__(UAM_CTA_THREADS)
+uam_k_piece_count(const double2* __restrict__ z, long long B, int Wp, UamRasterParams rp, int tiles_x,
+                  unsigned* __restrict__ hist, unsigned short* __restrict__ seg_cnt, unsigned* __restrict__ path_cnt) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * UAM_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * UAM_WARPS_PER_CTA;
+    for (long long path = warp0; path < B; path += nwarps) {
+        unsigned tot = 0;
+        for (int k = lane; k < Wp; k += 32) {
+            const unsigned long long id = (unsigned long long)path * Wp + k;
+            const UamSegRec r = uam_make_segment(z, id, Wp, rp);
+            const int c = uam_walk_pieces(r, rp, tiles_x, [&](int tile, int, int, int) { atomicAdd(&hist[tile], 1u); });
+            seg_cnt[id] = (unsigned short)c;
+            tot += (unsigned)c;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) path_cnt[path] = tot;
+    }
+}
+
+// exclusive prefix of in[0..n) into out[0..n], out[n] = total (mod 2^32); *total64 = exact total (single CTA)
+__global__ void __launch_bounds__(1024)
+uam_k_scan_u32(const unsigned* __restrict__ in, long long n, unsigned* __restrict__ out, unsigned long long* __restrict__ total64) {
+    __shared__ unsigned long long warp_tot[32];
+    const long long per = (n + 1023) / 1024;
+    const long long lo = min((long long)threadIdx.x * per, n), hi = min(lo + per, n);
+    unsigned long long local = 0;
+    for (long long i = lo; i < hi; ++i) local += in[i];
+    unsigned long long incl = local;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = warp_tot[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_tot[lane] = wi - w;
+        if (lane == 31) { *total64 = wi; out[n] = (unsigned)wi; }
+    }
+    __syncthreads();
+    unsigned long long run = warp_tot[warp] + incl - local;
+    for (long long i = lo; i < hi; ++i) {
+        const unsigned h = in[i];
+        out[i] = (unsigned)run;
+        run += h;
+    }
+}
+
+// Tiles: exclusive prefix of the piece histogram -> cursor, and the work-item list: tile t with c pieces becomes
+// ceil(c / UAM_ITEM_PIECES) items (tile, part).  Single CTA; counters[0] = number of items.
+__global__ void __launch_bounds__(1024)
+uam_k_tile_scan(const unsigned* __restrict__ hist, int n, unsigned* __restrict__ cursor, uint2* __restrict__ items,
+                unsigned* __restrict__ counters) {
+    __shared__ unsigned warp_p[32], warp_i[32];
+    const int per = (n + 1023) / 1024;
+    const int lo = min((int)threadIdx.x * per, n), hi = min(lo + per, n);
+    unsigned lp = 0, li = 0;
+    for (int i = lo; i < hi; ++i) {
+        const unsigned h = hist[i];
+        lp += h;
+        li += (h + UAM_ITEM_PIECES - 1) / UAM_ITEM_PIECES;
+    }
+    unsigned ip = lp, ii = li;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned a = __shfl_up_sync(0xffffffffu, ip, o), b = __shfl_up_sync(0xffffffffu, ii, o);
+        if (lane >= o) { ip += a; ii += b; }
+    }
+    if (lane == 31) { warp_p[warp] = ip; warp_i[warp] = ii; }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned a = warp_p[lane], b = warp_i[lane], ai = a, bi = b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned x = __shfl_up_sync(0xffffffffu, ai, o), y = __shfl_up_sync(0xffffffffu, bi, o);
+            if (lane >= o) { ai += x; bi += y; }
+        }
+        warp_p[lane] = ai - a;
+        warp_i[lane] = bi - b;
+        if (lane == 31) counters[0] = bi;
+    }
+    __syncthreads();
+    unsigned rp_ = warp_p[warp] + ip - lp, ri = warp_i[warp] + ii - li;
+    for (int i = lo; i < hi; ++i) {
+        const unsigned h = hist[i];
+        cursor[i] = rp_;
+        rp_ += h;
+        const unsigned ni = (h + UAM_ITEM_PIECES - 1) / UAM_ITEM_PIECES;
+        for (unsigned q = 0; q < ni; ++q) items[ri + q] = make_uint2((unsigned)i, q);
+        ri += ni;
+    }
+}
+
+__global__ void __launch_bounds__(UAM_CTA_THREADS)
+uam_k_piece_scatter(const double2* __restrict__ z, long long B, int Wp, UamRasterParams rp, int tiles_x,
+                    const unsigned short* __restrict__ seg_cnt, const unsigned* __restrict__ path_base,
+                    unsigned* __restrict__ cursor, UamPieceRec* __restrict__ recs) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * UAM_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * UAM_WARPS_PER_CTA;
+    for (long long path = warp0; path < B; path += nwarps) {
+        unsigned carry = path_base[path];
+        for (int k0 = 0; k0 < Wp; k0 += 32) {
+            const int k = k0 + lane;
+            const unsigned long long id = (unsigned long long)path * Wp + k;
+            const unsigned c = k < Wp ? seg_cnt[id] : 0u;
+            unsigned incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const unsigned base = carry + incl - c;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+            if (k < Wp) {
+                const UamSegRec r = uam_make_segment(z, id, Wp, rp);
+                uam_walk_pieces(r, rp, tiles_x, [&](int tile, int s0, int n, int piece) {
+                    const unsigned pos = atomicAdd(&cursor[tile], 1u);
+                    UamPieceRec q;
+                    q.U = r.U; q.V = r.V; q.SU = r.SU; q.SV = r.SV;
+                    q.s0 = s0; q.n = n; q.IS = r.IS; q.slot = base + (unsigned)piece;
+                    recs[pos] = q;
+                });
+            }
+        }
+    }
+}
+
+// ---- bulk async copy (TMA engine, no tensor map: one contiguous block) + mbarrier ------------------------------------
+__device__ __forceinline__ unsigned uam_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void uam_mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(uam_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void uam_bulk_load(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(uam_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(uam_smem_u32(dst)), "l"(src), "r"(bytes), "r"(uam_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void uam_mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "UAM_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra UAM_WAIT_%=;\n\t}"
+        ::"r"(uam_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// A bilinear tap from the staged tile: (i0, j0) are raster cells, (ti0, tj0) the tile's first cell.  The min() is
+// for memory safety only (a correct cut never leaves the tile).
+template <int TF>
+__device__ __forceinline__ void uam_tap_load_tile(const unsigned char* tile, int ti0, int tj0, const UamRasterParams& rp,
+                                                  double u, double v, UamTap<TF>& t) {
+    typedef typename UamTexel<TF>::T T;
+    int i0, j0;
+    uam_cell_frac1(u, rp.W, j0, t.fx);
+    uam_cell_frac1(v, rp.H, i0, t.fy);
+    const unsigned li = min((unsigned)(i0 - ti0), (unsigned)(UAM_TS - 1)), lj = min((unsigned)(j0 - tj0), (unsigned)(UAM_TS - 1));
+    const T* p = reinterpret_cast<const T*>(tile) + (li * UAM_TSH + lj);
+    t.a = p[0];
+    t.b = p[1];
+    t.c = p[UAM_TSH];
+    t.d = p[UAM_TSH + 1];
+}
+
+// shared memory of uam_k_score_tiles: [tile (copy_bytes, 128-aligned)] [mbarrier + control, 128 B] [per-warp areas]
+#define UAM_TILE_CTL_BYTES 128
+
+template <int TF>
+__global__ void __launch_bounds__(UAM_CTA_THREADS, 2)
+uam_k_score_tiles(UamRasterParams rp, UamTileGeo tg, const unsigned char* __restrict__ tiles,
+                  const unsigned* __restrict__ tile_end, const uint2* __restrict__ items, unsigned* __restrict__ counters,
+                  const UamPieceRec* __restrict__ recs, float* __restrict__ part_pen, uint8_t* __restrict__ part_col) {
+    extern __shared__ __align__(128) unsigned char uam_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned char* s_tile = uam_smem;
+    const unsigned tile_area = (tg.copy_bytes + 127u) & ~127u;
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(uam_smem + tile_area);
+    volatile unsigned* s_ctl = reinterpret_cast<volatile unsigned*>(uam_smem + tile_area + 16);   // [0] item, [1] next group
+    unsigned char* base = uam_smem + tile_area + UAM_TILE_CTL_BYTES + (size_t)warp * UAM_GROUP_SMEM;
+    const UamSegTable tb = uam_seg_table(base, 32);
+    int* tQ = reinterpret_cast<int*>(tb.IS);          // P[k] - s0[k]: flat index -> sample number in the parent segment
+    float* part = reinterpret_cast<float*>(base + uam_seg_table_bytes(32));
+    if (threadIdx.x == 0) uam_mbar_init(s_bar, 1);
+    __syncthreads();
+    const unsigned n_items = counters[0];
+    unsigned parity = 0;
+    for (;;) {
+        // all warps are done with the previous tile and with s_ctl
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned it = atomicAdd(&counters[1], 1u);
+            s_ctl[0] = it;
+            if (it < n_items) {
+                const uint2 im = items[it];
+                uam_bulk_load(s_tile, tiles + (size_t)im.x * tg.tile_stride, tg.copy_bytes, s_bar);
+                s_ctl[1] = (im.x ? tile_end[im.x - 1] : 0u) + im.y * UAM_ITEM_PIECES + UAM_WARPS_PER_CTA * 32;
+            }
+        }
+        __syncthreads();
+        const unsigned it = s_ctl[0];
+        if (it >= n_items) break;
+        const uint2 item = items[it];
+        const unsigned t_lo = item.x ? tile_end[item.x - 1] : 0u, t_hi = tile_end[item.x];
+        const unsigned lo = t_lo + item.y * UAM_ITEM_PIECES;
+        const unsigned hi = min(lo + UAM_ITEM_PIECES, t_hi);
+        const int ti0 = (int)(item.x / (unsigned)tg.tiles_x) * UAM_TS, tj0 = (int)(item.x % (unsigned)tg.tiles_x) * UAM_TS;
+        uam_mbar_wait(s_bar, parity);
+        parity ^= 1u;
+        unsigned g = lo + warp * 32;
+        while (g < hi) {
+            const unsigned ridx = g + lane;
+            const bool have = ridx < hi;
+            int S = 0, s0 = 0;
+            unsigned slot = 0;
+            float IS = 0.0f;
+            if (have) {
+                const double2* rp2 = reinterpret_cast<const double2*>(recs + ridx);
+                const double2 a = __ldg(rp2), b = __ldg(rp2 + 1);
+                const int4 c = __ldg(reinterpret_cast<const int4*>(rp2 + 2));
+                tb.U[lane] = a.x; tb.V[lane] = a.y; tb.SU[lane] = b.x; tb.SV[lane] = b.y;
+                s0 = c.x;
+                S = c.y;
+                IS = __int_as_float(c.z);
+                slot = (unsigned)c.w;
+            }
+            int incl = S;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            tb.P[lane] = incl - S;
+            tQ[lane] = incl - S - s0;
+            const int T = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 31) tb.P[32] = T;
+            float4* prow = reinterpret_cast<float4*>(part + lane * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) prow[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            __syncwarp();
+            float acc = 0.0f;
+            unsigned colmask = 0;
+            int k = 0, p1 = tb.P[1];
+            double kU = tb.U[0], kV = tb.V[0], kSU = tb.SU[0], kSV = tb.SV[0];
+            double sd = (double)(lane - tQ[0]);
+            for (int t = lane; t < T; t += 64) {
+                if (t >= p1) {
+                    part[lane * 32 + (k ^ lane)] = acc;
+                    acc = 0.0f;
+                    do { ++k; p1 = tb.P[k + 1]; } while (t >= p1);
+                    sd = (double)(t - tQ[k]);
+                    kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k];
+                }
+                UamTap<TF> ta, tb2;
+                uam_tap_load_tile<TF>(s_tile, ti0, tj0, rp, __dadd_rn(kU, __dmul_rn(sd, kSU)), __dadd_rn(kV, __dmul_rn(sd, kSV)), ta);
+                sd += 32.0;
+                const int k0 = k;
+                const int t2 = t + 32;
+                const bool two = t2 < T;
+                bool moved = false;
+                if (two && t2 >= p1) {
+                    moved = true;
+                    do { ++k; p1 = tb.P[k + 1]; } while (t2 >= p1);
+                    sd = (double)(t2 - tQ[k]);
+                    kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k];
+                }
+                uam_tap_load_tile<TF>(s_tile, ti0, tj0, rp, __dadd_rn(kU, __dmul_rn(sd, kSU)), __dadd_rn(kV, __dmul_rn(sd, kSV)), tb2);
+                if (two) sd += 32.0;
+                float pen;
+                bool occ;
+                uam_tap_eval<TF>(rp, ta, pen, occ);
+                acc += pen;
+                colmask |= (occ ? 1u : 0u) << k0;
+                if (moved) {
+                    part[lane * 32 + (k0 ^ lane)] = acc;
+                    acc = 0.0f;
+                }
+                uam_tap_eval<TF>(rp, tb2, pen, occ);
+                if (two) {
+                    acc += pen;
+                    colmask |= (occ ? 1u : 0u) << k;
+                }
+            }
+            part[lane * 32 + (k ^ lane)] = acc;
+            __syncwarp();
+            float mine = 0.0f;
+#pragma unroll 4
+            for (int s = 0; s < 32; ++s) {
+                // rows rotated by the piece's offset: position `lane` always holds the samples with piece-local index
+                // == lane (mod 32), so the sum does not depend on what else is in the group
+                const int row = (lane + tb.P[s]) & 31;
+                const float v = uam_warp_sum(part[row * 32 + (s ^ row)]);
+                if (lane == s) mine = v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) colmask |= __shfl_xor_sync(0xffffffffu, colmask, o);
+            if (have) {
+                part_pen[slot] = mine * IS;
+                part_col[slot] = (colmask >> lane) & 1u;
+            }
+            __syncwarp();
+            // next group of this item: first come, first served
+            unsigned nx = 0;
+            if (lane == 0) nx = atomicAdd((unsigned*)&s_ctl[1], 32u);
+            g = __shfl_sync(0xffffffffu, nx, 0);
+        }
+    }
+}
+
+// one warp per path: fixed-order sum of the path's piece partials + the length term
+__global__ void __launch_bounds__(UAM_CTA_THREADS)
+uam_k_reduce_slots(const double2* __restrict__ z, long long B, int Wp, UamRasterParams rp,
+                   const unsigned* __restrict__ path_base, const float* __restrict__ part_pen,
+                   const uint8_t* __restrict__ part_col, float* __restrict__ cost, uint8_t* __restrict__ collide,
+                   long long* __restrict__ nsamp) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * UAM_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * UAM_WARPS_PER_CTA;
+    const int N = Wp - 2;
+    for (long long path = warp0; path < B; path += nwarps) {
+        const double2* zp = z + path * Wp;
+        float acc = 0.0f;
+        double len_sum = 0.0;
+        long long ns = 0;
+        bool col = false;
+        const unsigned s_lo = path_base[path], s_hi = path_base[path + 1];
+        for (unsigned s = s_lo + lane; s < s_hi; s += 32) {
+            acc += part_pen[s];
+            col = col || part_col[s];
+        }
+        for (int j = lane; j < Wp; j += 32) {
+            const double2 p = zp[j];
+            len_sum += uam_len_term(zp, j, N, p, rp);
+            if (nsamp) {
+                long long S = 1;
+                if (j < Wp - 1) {
+                    const double2 q = zp[j + 1];
+                    const double dU = __dsub_rn(uam_pix(q.x, rp.x0, rp.dx), uam_pix(p.x, rp.x0, rp.dx));
+                    const double dV = __dsub_rn(uam_pix(q.y, rp.y0, rp.dy), uam_pix(p.y, rp.y0, rp.dy));
+                    S = (long long)uam_seg_samples(dU, dV, rp.spc);
+                }
+                ns += S;
+            }
+        }
+        acc = uam_warp_sum(acc);
+        len_sum = uam_warp_sum(len_sum);
+        col = __any_sync(0xffffffffu, col);
+        if (nsamp) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+        }
+        if (lane == 0) {
+            if (cost) cost[path] = (float)((double)(N + 1) * len_sum + (double)acc / (double)N);
+            if (collide) collide[path] = col ? 1 : 0;
+            if (nsamp) nsamp[path] = ns;
+        }
+    }
+}
+
+// tile-major copy of the texels: tile (ty, tx) = cells [64 ty, 64 ty + 65) x [64 tx, 64 tx + 65), row-major inside
+// the tile, zero outside the raster.  One thread per output texel.
+template <int TF, int LAYOUT>
+__global__ void uam_k_build_tiles(const typename UamTexel<TF>::T* __restrict__ tex, UamRasterParams rp, UamTileGeo tg,
+                                  unsigned char* __restrict__ out) {
+    typedef typename UamTexel<TF>::T T;
+    const unsigned per_tile = UAM_TSH * UAM_TSH;
+    const size_t n = (size_t)tg.ntiles * per_tile;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += stride) {
+        const unsigned tile = (unsigned)(o / per_tile), w = (unsigned)(o - (size_t)tile * per_tile);
+        const unsigned li = w / UAM_TSH, lj = w - li * UAM_TSH;
+        const unsigned i = (tile / (unsigned)tg.tiles_x) * UAM_TS + li, j = (tile % (unsigned)tg.tiles_x) * UAM_TS + lj;
+        T v;
+        if (i < (unsigned)rp.H && j < (unsigned)rp.W) {
+            v = tex[uam_tex_row<TF, LAYOUT>(i, rp.row_stride) + uam_tex_col<TF, LAYOUT>(j)];
+        } else {
+            if constexpr (TF == 2) v = make_float2(0.0f, 0.0f); else v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        reinterpret_cast<T*>(out + (size_t)tile * tg.tile_stride)[w] = v;
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 int uam_raster_prepare(uam_ctx* ctx, int64_t B, int N, const double* h_p, int n_p, int flags, double spc,
                        UamRasterParams* rp) {
@@ -762,12 +1237,14 @@ int uam_raster_prepare(uam_ctx* ctx, int64_t B, int N, const double* h_p, int n_
     // auto (-1): the binned pipeline pays off once the batch has enough segments to fill the raster bins.  Decided
     // from the whole call (not per pipeline chunk), so host-buffer and device-buffer calls run the same kernels.
     rp->variant = ctx->int_variant >= 0 ? ctx->int_variant : ((unsigned long long)B * (N + 2) >= 262144ull ? 2 : 0);
+    rp->combined = 0;
+    rp->row_stride2 = 0;
     return UAM_OK;
 }
 
 template <int TF, int LAYOUT>
-int uam_raster_launch_binned(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const UamRasterParams& rp, float* d_cost,
-                             uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
+int uam_raster_launch_binned(uam_ctx* ctx, const void* texv, const double2* z, int64_t B, int Wp, const UamRasterParams& rp,
+                             float* d_cost, uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
     typedef typename UamTexel<TF>::T T;
     const unsigned long long n_seg = (unsigned long long)B * Wp;
     UamBinGeo bg;
@@ -806,7 +1283,7 @@ int uam_raster_launch_binned(uam_ctx* ctx, const double2* z, int64_t B, int Wp, 
         UAM_TRY(uam_time_collect(ctx));
         UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
     }
-    uam_k_score_groups<TF, LAYOUT><<<(unsigned)sctas, UAM_CTA_THREADS, gsmem, st>>>(n_seg, rp, (const T*)ctx->d_tex, recs, part_pen, part_col);
+    uam_k_score_groups<TF, LAYOUT><<<(unsigned)sctas, UAM_CTA_THREADS, gsmem, st>>>(n_seg, rp, (const T*)texv, recs, part_pen, part_col);
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_groups");
     if (ctx->time_kernels && slot == 0) {
         UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
@@ -818,12 +1295,98 @@ int uam_raster_launch_binned(uam_ctx* ctx, const double2* z, int64_t B, int Wp, 
     return UAM_OK;
 }
 
+// Tile-major copy of the texels for variant 3, built on first use; `key` names the texel array it was made from
+// (raster generation, or generation of the weight-combined texels).
 template <int TF, int LAYOUT>
-int uam_raster_launch_t(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const UamRasterParams& rp, float* d_cost,
-                        uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
+int uam_ensure_tiles(uam_ctx* ctx, const void* texv, uint64_t key, const UamRasterParams& rp, UamTileGeo* tg, cudaStream_t st) {
     typedef typename UamTexel<TF>::T T;
-    const T* tex = (const T*)ctx->d_tex;
-    const bool timed = ctx->time_kernels && slot == 0 && !(rp.spc > 0.0 && rp.variant == 2);
+    tg->tiles_x = (rp.W + UAM_TS - 1) / UAM_TS;
+    tg->tiles_y = (rp.H + UAM_TS - 1) / UAM_TS;
+    tg->ntiles = tg->tiles_x * tg->tiles_y;
+    const unsigned raw = (unsigned)(UAM_TSH * UAM_TSH * sizeof(T));
+    tg->copy_bytes = (raw + 15u) & ~15u;
+    tg->tile_stride = (raw + 127u) & ~127u;
+    if (ctx->tiles_valid && ctx->tiles_key == key) return UAM_OK;
+    UAM_CUDA(ctx, cudaDeviceSynchronize());      // the old copy may still be read by kernels queued on other streams
+    UAM_TRY(uam_reserve(ctx, &ctx->d_tiles, &ctx->tiles_bytes, (size_t)tg->ntiles * tg->tile_stride));
+    uam_k_build_tiles<TF, LAYOUT><<<ctx->sm_count * 8, 256, 0, st>>>((const T*)texv, rp, *tg, (unsigned char*)ctx->d_tiles);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_build_tiles");
+    UAM_CUDA(ctx, cudaStreamSynchronize(st));    // every pipeline stream may use it from now on
+    ctx->tiles_valid = true;
+    ctx->tiles_key = key;
+    return UAM_OK;
+}
+
+template <int TF, int LAYOUT>
+int uam_raster_launch_tiles(uam_ctx* ctx, const void* texv, uint64_t tex_key, const double2* z, int64_t B, int Wp,
+                            const UamRasterParams& rp, float* d_cost, uint8_t* d_collide, long long* d_nsamp, cudaStream_t st,
+                            int slot, bool* fell_back) {
+    *fell_back = false;
+    UamTileGeo tg;
+    UAM_TRY((uam_ensure_tiles<TF, LAYOUT>(ctx, texv, tex_key, rp, &tg, st)));
+    const unsigned long long n_seg = (unsigned long long)B * Wp;
+    // phase 1 scratch: total64 | hist | cursor | counters[4] | path_cnt[B] | path_base[B + 1] | seg_cnt (u16)
+    const size_t nt = (size_t)tg.ntiles;
+    const size_t need1 = 16 + (2 * nt + 4 + (size_t)B + (size_t)B + 1) * 4 + n_seg * 2 + 256;
+    UAM_TRY(uam_reserve(ctx, &ctx->d_bin_scratch[slot], &ctx->bin_scratch_bytes[slot], need1));
+    unsigned long long* total64 = (unsigned long long*)ctx->d_bin_scratch[slot];
+    unsigned* hist = (unsigned*)(total64 + 2);
+    unsigned* cursor = hist + nt;
+    unsigned* counters = cursor + nt;
+    unsigned* path_cnt = counters + 4;
+    unsigned* path_base = path_cnt + B;
+    unsigned short* seg_cnt = (unsigned short*)(path_base + B + 1);
+    UAM_CUDA(ctx, cudaMemsetAsync(total64, 0, 16 + (2 * nt + 4) * 4, st));
+    const long long pctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
+    uam_k_piece_count<<<(unsigned)pctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, tg.tiles_x, hist, seg_cnt, path_cnt);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_piece_count");
+    uam_k_scan_u32<<<1, 1024, 0, st>>>(path_cnt, B, path_base, total64);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_scan_u32");
+    // the scratch for the pieces is sized from their exact number: one 8-byte read-back per call
+    unsigned long long total = 0;
+    UAM_CUDA(ctx, cudaMemcpyAsync(&total, total64, sizeof total, cudaMemcpyDeviceToHost, st));
+    UAM_CUDA(ctx, cudaStreamSynchronize(st));
+    if (total >= 0xffffffffull) {              // slots are 32-bit: leave this batch to the binned pipeline
+        *fell_back = true;
+        return UAM_OK;
+    }
+    const size_t n_items_max = nt + (size_t)(total / UAM_ITEM_PIECES) + 1;
+    const size_t need2 = (size_t)total * (sizeof(UamPieceRec) + 4 + 1) + n_items_max * sizeof(uint2) + 256;
+    UAM_TRY(uam_reserve(ctx, &ctx->d_piece_scratch[slot], &ctx->piece_scratch_bytes[slot], need2));
+    UamPieceRec* recs = (UamPieceRec*)ctx->d_piece_scratch[slot];
+    uint2* items = (uint2*)(recs + total);
+    float* part_pen = (float*)(items + n_items_max);
+    uint8_t* part_col = (uint8_t*)(part_pen + total);
+    uam_k_tile_scan<<<1, 1024, 0, st>>>(hist, tg.ntiles, cursor, items, counters);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_tile_scan");
+    uam_k_piece_scatter<<<(unsigned)pctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, tg.tiles_x, seg_cnt, path_base, cursor, recs);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_piece_scatter");
+    const size_t smem = (size_t)((tg.copy_bytes + 127u) & ~127u) + UAM_TILE_CTL_BYTES + (size_t)UAM_GROUP_SMEM * UAM_WARPS_PER_CTA;
+    UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_score_tiles<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ctx->time_kernels && slot == 0) {
+        UAM_TRY(uam_time_collect(ctx));
+        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
+    }
+    // after the scatter cursor[t] is the END of tile t's pieces
+    uam_k_score_tiles<TF><<<(unsigned)(ctx->sm_count * 2), UAM_CTA_THREADS, smem, st>>>(rp, tg, (const unsigned char*)ctx->d_tiles, cursor, items,
+                                                                                    counters, recs, part_pen, part_col);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_score_tiles");
+    if (ctx->time_kernels && slot == 0) {
+        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
+        ctx->time_pending = true;
+    }
+    const long long rctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
+    uam_k_reduce_slots<<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, path_base, part_pen, part_col, d_cost, d_collide, d_nsamp);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_reduce_slots");
+    return UAM_OK;
+}
+
+template <int TF, int LAYOUT>
+int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const double2* z, int64_t B, int Wp,
+                        const UamRasterParams& rp, float* d_cost, uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
+    typedef typename UamTexel<TF>::T T;
+    const T* tex = (const T*)texv;
+    const bool timed = ctx->time_kernels && slot == 0 && !(rp.spc > 0.0 && rp.variant >= 2);
     if (timed) {
         UAM_TRY(uam_time_collect(ctx));
         UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
@@ -838,8 +1401,14 @@ int uam_raster_launch_t(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const
         }
         return UAM_OK;
     }
-    if (rp.variant == 2 && (unsigned long long)B * Wp < 0xffffffffull)
-        return uam_raster_launch_binned<TF, LAYOUT>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
+    if (rp.variant >= 2 && (unsigned long long)B * Wp < 0xffffffffull) {
+        if (rp.variant == 3 && (rp.W + UAM_TS - 1) / UAM_TS + (rp.H + UAM_TS - 1) / UAM_TS < 65535) {
+            bool fell_back = false;
+            UAM_TRY((uam_raster_launch_tiles<TF, LAYOUT>(ctx, texv, tex_key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot, &fell_back)));
+            if (!fell_back) return UAM_OK;
+        }
+        return uam_raster_launch_binned<TF, LAYOUT>(ctx, texv, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
+    }
     const size_t per_warp = uam_seg_table_bytes(Wp);
     const size_t budget = 200 * 1024;
     if (per_warp > budget) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "N = %d waypoints per path is too many for integral mode", Wp - 2);
@@ -861,16 +1430,86 @@ int uam_raster_launch_t(uam_ctx* ctx, const double2* z, int64_t B, int Wp, const
     return UAM_OK;
 }
 
+// Weight-combined texels.  The penalty is linear in the layers, sum_l w_l * bilerp(layer_l) = bilerp(sum_l w_l * layer_l),
+// so for a given weight vector the L = 2..3 layer raster collapses into ONE layer: float2 texels {sum_l w_l layer_l,
+// occupancy}, half the bytes per bilinear tap (32 instead of 64).  Built per (raster, weights) and kept until either
+// changes; used by the large-batch pipelines (variants 2 and 3), whose gather is bound by the bytes moved through L1 /
+// shared memory.  The combination is fp32 (same rounding class as the per-layer sum it replaces).
+template <int LAYOUT>
+__global__ void uam_k_combine_layers(const float4* __restrict__ tex4, int H, int W, unsigned rs4, unsigned rs2, float w0, float w1,
+                                     float w2, size_t n_out, float2* __restrict__ tex2) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += stride) {
+        // o -> (i, j) of the float2 layout (one thread per output texel, coalesced stores)
+        int i, j;
+        if (LAYOUT == 0) {
+            i = (int)(o / W);
+            j = (int)(o - (size_t)i * W);
+        } else {
+            const size_t tile = o >> 4;
+            const int w = (int)(o & 15), tiles_x = (int)(rs2 >> 4);
+            const int ty = (int)(tile / tiles_x), tx = (int)(tile - (size_t)ty * tiles_x);
+            i = ty * 4 + ((w >> 3) & 1) * 2 + ((w >> 1) & 1);
+            j = tx * 4 + ((w >> 2) & 1) * 2 + (w & 1);
+        }
+        float2 v = make_float2(0.0f, 0.0f);
+        if (i < H && j < W) {
+            const float4 t = tex4[uam_tex_row<4, LAYOUT>(i, rs4) + uam_tex_col<4, LAYOUT>(j)];
+            v = make_float2(w0 * t.x + w1 * t.y + w2 * t.z, t.w);
+        }
+        tex2[o] = v;
+    }
+}
+
+int uam_ensure_combined(uam_ctx* ctx, const UamRasterParams& rp, unsigned* rs2, cudaStream_t st) {
+    const int W = rp.W, H = rp.H, lay = ctx->geo.layout;
+    const int tiles_x = (W + 3) / 4, tiles_y = (H + 3) / 4;
+    *rs2 = lay ? (unsigned)tiles_x * 16u : (unsigned)W;
+    if (ctx->comb_valid && ctx->comb_w[0] == rp.w0 && ctx->comb_w[1] == rp.w1 && ctx->comb_w[2] == rp.w2) return UAM_OK;
+    const size_t n_out = lay ? (size_t)tiles_x * tiles_y * 16 : (size_t)H * W;
+    UAM_CUDA(ctx, cudaDeviceSynchronize());      // kernels on other streams may still read the old combination
+    UAM_TRY(uam_reserve(ctx, &ctx->d_tex_comb, &ctx->tex_comb_bytes, n_out * sizeof(float2)));
+    const int grid = ctx->sm_count * 8;
+    if (lay) uam_k_combine_layers<1><<<grid, 256, 0, st>>>((const float4*)ctx->d_tex, H, W, rp.row_stride, *rs2, rp.w0, rp.w1, rp.w2, n_out, (float2*)ctx->d_tex_comb);
+    else uam_k_combine_layers<0><<<grid, 256, 0, st>>>((const float4*)ctx->d_tex, H, W, rp.row_stride, *rs2, rp.w0, rp.w1, rp.w2, n_out, (float2*)ctx->d_tex_comb);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_combine_layers");
+    UAM_CUDA(ctx, cudaStreamSynchronize(st));    // every pipeline stream may use it from now on
+    ctx->comb_valid = true;
+    ctx->comb_w[0] = rp.w0; ctx->comb_w[1] = rp.w1; ctx->comb_w[2] = rp.w2;
+    ctx->comb_gen += 1;
+    return UAM_OK;
+}
+
 // slot: which scratch buffer of the ctx the binned pipeline may use (0 = caller-stream calls, 1.. = host pipeline stages)
 int uam_raster_launch(uam_ctx* ctx, const double* d_z, int64_t B, int N, const UamRasterParams& rp, float* d_cost,
                       uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
     const int Wp = N + 2;
     const double2* z = reinterpret_cast<const double2*>(d_z);
     const int tf = ctx->geo.texel_floats, lay = ctx->geo.layout;
-    if (tf == 2) return lay ? uam_raster_launch_t<2, 1>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
-                            : uam_raster_launch_t<2, 0>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
-    return lay ? uam_raster_launch_t<4, 1>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
-               : uam_raster_launch_t<4, 0>(ctx, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
+    const uint64_t key = ctx->raster_gen << 1;
+    if (tf == 2) return lay ? uam_raster_launch_t<2, 1>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
+                            : uam_raster_launch_t<2, 0>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
+    if (rp.combined) {
+        // large-batch integral mode on the weight-combined single-layer texels (made by uam_raster_prepare)
+        UamRasterParams rc = rp;
+        rc.w0 = 1.0f; rc.w1 = 0.0f; rc.w2 = 0.0f;
+        rc.row_stride = rp.row_stride2;
+        const uint64_t ckey = (ctx->comb_gen << 1) | 1u;
+        return lay ? uam_raster_launch_t<2, 1>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot)
+                   : uam_raster_launch_t<2, 0>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot);
+    }
+    return lay ? uam_raster_launch_t<4, 1>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
+               : uam_raster_launch_t<4, 0>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
+}
+
+// Once per API call, before any chunk is launched: make the weight-combined texels if this call will use them.
+int uam_raster_precompute(uam_ctx* ctx, UamRasterParams* rp, int64_t B, int N, cudaStream_t st) {
+    if (ctx->geo.texel_floats == 4 && rp->spc > 0.0 && rp->variant >= 2 && ctx->combine_layers &&
+        (unsigned long long)B * (N + 2) < 0xffffffffull) {
+        UAM_TRY(uam_ensure_combined(ctx, *rp, &rp->row_stride2, st));
+        rp->combined = 1;
+    }
+    return UAM_OK;
 }
 
 }  // namespace
@@ -884,6 +1523,7 @@ extern "C" int uam_score_paths_raster(uam_ctx* ctx, const double* d_z, int64_t B
     if (B == 0) return UAM_OK;
     if (!d_z) return uam_fail(ctx, UAM_ERR_INVALID, "paths pointer is NULL");
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UAM_TRY(uam_raster_precompute(ctx, &rp, B, N, uam_pick_stream(ctx, stream)));
     return uam_raster_launch(ctx, d_z, B, N, rp, d_cost, d_collide, (long long*)d_nsamples, uam_pick_stream(ctx, stream), 0);
 }
 
@@ -899,6 +1539,7 @@ extern "C" int uam_score_paths_raster_host(uam_ctx* ctx, const double* h_z, int6
     if (!h_z) return uam_fail(ctx, UAM_ERR_INVALID, "paths pointer is NULL");
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     UAM_CUDA(ctx, cudaDeviceSynchronize());
+    UAM_TRY(uam_raster_precompute(ctx, &rp, B, N, ctx->pipe_stream[0]));
     const size_t row = (size_t)2 * (N + 2) * sizeof(double);
     const int n_chunks = ctx->host_chunks > 0 ? ctx->host_chunks : 2 * UAM_HOST_PIPE_DEPTH;
     const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>((B + n_chunks - 1) / n_chunks, (int64_t)((64u << 20) / row)));

@@ -78,7 +78,8 @@ class Engine:
     def sync(self):
         self._check(self._lib.uam_sync(self._h))
 
-    OPTIONS = {'raster_layout': 1, 'integral_variant': 2, 'l2_fetch_granularity': 3, 'time_kernels': 4}
+    OPTIONS = {'raster_layout': 1, 'integral_variant': 2, 'l2_fetch_granularity': 3, 'time_kernels': 4,
+               'combine_layers': 5}
     STATS = {'score_kernel_ms_mean': 1, 'score_kernel_count': 2}
 
     def get_stat(self, name: str) -> float:
@@ -88,7 +89,7 @@ class Engine:
 
     def set_option(self, name: str, value: int):
         """Tuning knobs of include/uam_b200.h (UAM_OPT_*): raster_layout (0 row-major, 1 tiled; applies to the next
-        set_raster), integral_variant (0 one lane per sample, 1 lane pair), l2_fetch_granularity (32/64/128)."""
+        set_raster), integral_variant (-1 auto, 0 one lane per sample, 1 lane pair, 2 binned, 3 tile-staged), l2_fetch_granularity (32/64/128)."""
         self._check(self._lib.uam_ctx_set_option(self._h, self.OPTIONS[name], int(value)))
 
     def _tensor_args(self, *tensors):
