@@ -27,7 +27,12 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_barrier_per_warp_active.pct',
         'smsp__warp_issue_stalled_not_selected_per_warp_active.pct', 'smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct',
         'smsp__warp_issue_stalled_tex_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct',
-        'smsp__thread_inst_executed_per_inst_executed.ratio']
+        'smsp__thread_inst_executed_per_inst_executed.ratio'] + [
+        f'smsp__average_warps_issue_stalled_{r}_per_issue_active.ratio' for r in (
+            'long_scoreboard', 'short_scoreboard', 'mio_throttle', 'lg_throttle', 'math_pipe_throttle', 'wait', 'not_selected',
+            'barrier', 'branch_resolving', 'dispatch_stall', 'no_instruction', 'tex_throttle', 'sleeping', 'selected')] + [
+        'lts__t_sectors_srcunit_tex_lookup_hit.sum', 'lts__t_sectors_srcunit_tex_lookup_miss.sum',
+        'lts__average_t_sector_hit_rate_srcunit_tex_realtime.pct', 'l1tex__average_t_sector_hit_rate_realtime.pct']
 lines = []
 for r in rows[2:]:
     name = r[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else '?'

@@ -192,6 +192,7 @@ extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
     for (int i = 0; i <= UAM_HOST_PIPE_DEPTH; ++i) cudaFree(ctx->d_piece_scratch[i]);
     cudaFree(ctx->d_tiles);
     cudaFree(ctx->d_tex_comb);
+    cudaFree(ctx->d_occ_bits);
     for (int i = 0; i < UAM_HOST_PIPE_DEPTH; ++i) {
         cudaFree(ctx->d_stage_in[i]);
         cudaFree(ctx->d_stage_out[i]);
@@ -400,6 +401,7 @@ extern "C" int uam_map_set_raster_device(uam_ctx* ctx, const float* d_layers, in
     ctx->has_raster = true;
     ctx->tiles_valid = false;
     ctx->comb_valid = false;
+    ctx->occ_bits_valid = false;
     ctx->raster_gen += 1;
     return UAM_OK;
 }

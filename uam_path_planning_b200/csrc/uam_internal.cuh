@@ -103,10 +103,14 @@ struct uam_ctx {
     size_t tiles_bytes = 0;
     bool tiles_valid = false;
     uint64_t tiles_key = 0;             // which texel array the tile copy was made from
-    // weight-combined single-layer texels (float2) for the large-batch integral pipelines, per (raster, weights)
+    // quad texels (weight-combined layer, 2 x 2 footprint per cell) + occupancy bit-plane for the large-batch
+    // integral pipelines, per (raster, weights)
     void* d_tex_comb = nullptr;
     size_t tex_comb_bytes = 0;
     bool comb_valid = false;
+    void* d_occ_bits = nullptr;
+    size_t occ_bits_bytes = 0;
+    bool occ_bits_valid = false;
     float comb_w[3] = {};
     uint64_t comb_gen = 0, raster_gen = 0;
     int combine_layers = 1;             // UAM_OPT_COMBINE_LAYERS

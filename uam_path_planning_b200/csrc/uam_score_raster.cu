@@ -36,13 +36,16 @@ struct UamRasterParams {
     float w0, w1, w2;
     int flags;
     int variant;          // integral-mode kernel, decided once per API call from the call's whole batch
-    int combined;         // 1: score on the weight-combined float2 texels (ctx->d_tex_comb, row stride row_stride2)
+    int combined;         // 1: score on the weight-combined quad texels (ctx->d_tex_comb, row stride row_stride2)
     unsigned row_stride2;
+    const unsigned* occ_bits;   // quad mode: occupancy bit-plane (uam_occ_word / uam_occ_bit)
+    unsigned occ_blocks_x;      // 32 x 32-cell blocks per block-row of the bit-plane
 };
 
 template <int TF> struct UamTexel;
 template <> struct UamTexel<2> { typedef float2 T; };
 template <> struct UamTexel<4> { typedef float4 T; };
+template <> struct UamTexel<1> { typedef float4 T; };      // quad mode: the 2 x 2 bilinear footprint of a cell in one texel
 
 // Texel address = uam_tex_row(i) + uam_tex_col(j)  (both layouts are separable).
 // LAYOUT 0: row-major (H, W).  LAYOUT 1: tiled so that one 128-byte line is a compact 2-D block and every 32-byte
@@ -78,6 +81,11 @@ __device__ __forceinline__ float uam_lerp2(float t00, float t01, float t10, floa
     return top + fy * (bot - top);
 }
 
+// exact (double)n for any int n without the conversion unit: 2^52 + 2^31 + n assembled as bits, minus the bias
+__device__ __forceinline__ double uam_int2double(int n) {
+    return __dsub_rn(__hiloint2double(0x43300000, n ^ (int)0x80000000), 4503601774854144.0);
+}
+
 // fp64 -> fp32 with clamping to [0, 1] in one conversion
 __device__ __forceinline__ float uam_sat_f32(double x) {
     float r;
@@ -90,14 +98,28 @@ __device__ __forceinline__ float uam_sat_f32(double x) {
 // u > n-1 the cell clamps to n-2 and f saturates to 1.
 __device__ __forceinline__ void uam_cell_frac1(double u, int n, int& j0, float& f) {
     j0 = min(max(__double2int_rd(u), 0), n - 2);
-    f = uam_sat_f32(__dsub_rn(u, (double)j0));
+    f = uam_sat_f32(__dsub_rn(u, uam_int2double(j0)));
 }
+
+// Occupancy bit-plane of the quad mode: one bit per cell, a 32-bit word = 8 x 4 cells, a 128-byte line = 4 x 8 words
+// = a 32 x 32-cell block (8192^2 cells = 8 MiB: L2-resident, mostly L1-resident along a path).
+__host__ __device__ __forceinline__ unsigned uam_occ_word(unsigned i, unsigned j, unsigned blocks_x) {
+    return ((i >> 5) * blocks_x + (j >> 5)) * 32u + ((i >> 2) & 7u) * 4u + ((j >> 3) & 3u);
+}
+__host__ __device__ __forceinline__ unsigned uam_occ_bit(unsigned i, unsigned j) { return (i & 3u) * 8u + (j & 7u); }
 
 // A bilinear tap split into its load half and its arithmetic half, so that a loop can issue the loads of several
 // samples before it consumes the first one.
 template <int TF>
 struct UamTap {
     typename UamTexel<TF>::T a, b, c, d;   // (i0,j0) (i0,j0+1) (i0+1,j0) (i0+1,j0+1)
+    float fx, fy;
+};
+// quad mode: one 16-byte texel holds the four corner values of cell (i0, j0); occupancy of the nearest cell is one bit
+template <>
+struct UamTap<1> {
+    float4 q;              // value at (i0,j0) (i0,j0+1) (i0+1,j0) (i0+1,j0+1)
+    unsigned ow, ob;       // occupancy word and bit index of the nearest cell
     float fx, fy;
 };
 
@@ -107,26 +129,38 @@ __device__ __forceinline__ void uam_tap_load(const typename UamTexel<TF>::T* __r
     int i0, j0;
     uam_cell_frac1(u, rp.W, j0, t.fx);
     uam_cell_frac1(v, rp.H, i0, t.fy);
-    const unsigned r0 = uam_tex_row<TF, LAYOUT>(i0, rp.row_stride), r1 = uam_tex_row<TF, LAYOUT>(i0 + 1, rp.row_stride);
-    const unsigned c0 = uam_tex_col<TF, LAYOUT>(j0), c1 = uam_tex_col<TF, LAYOUT>(j0 + 1);
-    t.a = __ldg(tex + (r0 + c0));
-    t.b = __ldg(tex + (r0 + c1));
-    t.c = __ldg(tex + (r1 + c0));
-    t.d = __ldg(tex + (r1 + c1));
+    if constexpr (TF == 1) {
+        t.q = __ldg(tex + (uam_tex_row<4, LAYOUT>(i0, rp.row_stride) + uam_tex_col<4, LAYOUT>(j0)));
+        const unsigned ni = (unsigned)i0 + (t.fy >= 0.5f ? 1u : 0u), nj = (unsigned)j0 + (t.fx >= 0.5f ? 1u : 0u);
+        t.ow = __ldg(rp.occ_bits + uam_occ_word(ni, nj, rp.occ_blocks_x));
+        t.ob = uam_occ_bit(ni, nj);
+    } else {
+        const unsigned r0 = uam_tex_row<TF, LAYOUT>(i0, rp.row_stride), r1 = uam_tex_row<TF, LAYOUT>(i0 + 1, rp.row_stride);
+        const unsigned c0 = uam_tex_col<TF, LAYOUT>(j0), c1 = uam_tex_col<TF, LAYOUT>(j0 + 1);
+        t.a = __ldg(tex + (r0 + c0));
+        t.b = __ldg(tex + (r0 + c1));
+        t.c = __ldg(tex + (r1 + c0));
+        t.d = __ldg(tex + (r1 + c1));
+    }
 }
 
 template <int TF>
 __device__ __forceinline__ void uam_tap_eval(const UamRasterParams& rp, const UamTap<TF>& t, float& pen, bool& occ) {
-    const bool right = t.fx >= 0.5f, down = t.fy >= 0.5f;
-    if constexpr (TF == 2) {
-        pen = rp.w0 * uam_lerp2(t.a.x, t.b.x, t.c.x, t.d.x, t.fx, t.fy);
-        const float o = down ? (right ? t.d.y : t.c.y) : (right ? t.b.y : t.a.y);
-        occ = o != 0.0f;
+    if constexpr (TF == 1) {
+        pen = rp.w0 * uam_lerp2(t.q.x, t.q.y, t.q.z, t.q.w, t.fx, t.fy);
+        occ = ((t.ow >> t.ob) & 1u) != 0u;
     } else {
-        pen = rp.w0 * uam_lerp2(t.a.x, t.b.x, t.c.x, t.d.x, t.fx, t.fy) + rp.w1 * uam_lerp2(t.a.y, t.b.y, t.c.y, t.d.y, t.fx, t.fy) +
-              rp.w2 * uam_lerp2(t.a.z, t.b.z, t.c.z, t.d.z, t.fx, t.fy);
-        const float o = down ? (right ? t.d.w : t.c.w) : (right ? t.b.w : t.a.w);
-        occ = o != 0.0f;
+        const bool right = t.fx >= 0.5f, down = t.fy >= 0.5f;
+        if constexpr (TF == 2) {
+            pen = rp.w0 * uam_lerp2(t.a.x, t.b.x, t.c.x, t.d.x, t.fx, t.fy);
+            const float o = down ? (right ? t.d.y : t.c.y) : (right ? t.b.y : t.a.y);
+            occ = o != 0.0f;
+        } else {
+            pen = rp.w0 * uam_lerp2(t.a.x, t.b.x, t.c.x, t.d.x, t.fx, t.fy) + rp.w1 * uam_lerp2(t.a.y, t.b.y, t.c.y, t.d.y, t.fx, t.fy) +
+                  rp.w2 * uam_lerp2(t.a.z, t.b.z, t.c.z, t.d.z, t.fx, t.fy);
+            const float o = down ? (right ? t.d.w : t.c.w) : (right ? t.b.w : t.a.w);
+            occ = o != 0.0f;
+        }
     }
 }
 
@@ -580,10 +614,137 @@ uam_k_bin_scatter(const double2* __restrict__ z, unsigned long long n_seg, int W
     }
 }
 
-// One warp per group of 32 consecutive sorted records: flat sample loop over the group, per-segment partial sums
-// in shared memory (row = lane, column swizzled by lane so both the per-lane flush and the per-segment reduction
-// are bank-conflict free), fixed-order reduction per segment.
-#define UAM_GROUP_SMEM (32 * 40 + 4 + 12 + 32 * 32 * 4)    // segment table (32 entries, padded to 16 B) + partials
+#define UAM_TS 64                         // variant 3: tile side in cells
+#define UAM_TSH (UAM_TS + 1)              // with the halo row / column
+
+// A bilinear tap from the staged tile: (i0, j0) are raster cells, (ti0, tj0) the tile's first cell.  The min() is
+// for memory safety only (a correct cut never leaves the tile).
+template <int TF>
+__device__ __forceinline__ void uam_tap_load_tile(const unsigned char* tile, int ti0, int tj0, const UamRasterParams& rp,
+                                                  double u, double v, UamTap<TF>& t) {
+    typedef typename UamTexel<TF>::T T;
+    int i0, j0;
+    uam_cell_frac1(u, rp.W, j0, t.fx);
+    uam_cell_frac1(v, rp.H, i0, t.fy);
+    const unsigned li = min((unsigned)(i0 - ti0), (unsigned)(UAM_TS - 1)), lj = min((unsigned)(j0 - tj0), (unsigned)(UAM_TS - 1));
+    const T* p = reinterpret_cast<const T*>(tile) + (li * UAM_TSH + lj);
+    if constexpr (TF == 1) {
+        t.q = p[0];
+        const unsigned ni = (unsigned)i0 + (t.fy >= 0.5f ? 1u : 0u), nj = (unsigned)j0 + (t.fx >= 0.5f ? 1u : 0u);
+        t.ow = __ldg(rp.occ_bits + uam_occ_word(ni, nj, rp.occ_blocks_x));
+        t.ob = uam_occ_bit(ni, nj);
+    } else {
+        t.a = p[0];
+        t.b = p[1];
+        t.c = p[UAM_TSH];
+        t.d = p[UAM_TSH + 1];
+    }
+}
+
+// One warp per group of 32 consecutive sorted records.  The samples of the 32 records are concatenated (record k owns
+// the flat indices [P_k, P_{k+1})) and lanes stride the flat index, UAM_TAPS windows of 32 samples per trip, so no
+// lane idles on short records.  The record of a flat index is found without branches or dependent shared-memory
+// walks: lane l holds P_l; per window one REDUX.OR builds the bitmap of the record starts that fall inside it and
+// k(lane) = (#records started before the window) + popc(bitmap & lanes <= lane) - 1.  The record's parameters come
+// from a 36-byte-per-record table in shared memory (two LDS.128 + one LDS.32); the loads of all UAM_TAPS taps are
+// issued before the first lerp.  Per-lane accumulators are flushed to a 32 x 32 matrix of partials (row = lane,
+// column swizzled by lane) when the lane moves on to another record; a fixed-order reduction per record follows.
+struct __align__(16) UamGroupRec {
+    double U, SU, V, SV;
+};
+#define UAM_GROUP_SMEM (32 * 32 + 36 * 4 + 32 * 32 * 4)    // records (32 x 32 B) + Q[33] (padded to 16 B) + partials
+
+template <int TF> struct UamTapsPerTrip { static const int N = 2; };
+template <> struct UamTapsPerTrip<1> { static const int N = 4; };
+
+// Scores one group.  In: this lane's record (first sample U/V, step SU/SV, S samples starting at sample number s0 of
+// its parent segment; S = 0 for a lane without a record).  Out: the record's sample sum (not yet divided by the
+// parent's sample count) and its collision bit.  TILE = 0: taps from global memory (tex); TILE = 1: taps from the
+// tile staged in shared memory.
+template <int TF, int LAYOUT, int TILE>
+__device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const typename UamTexel<TF>::T* __restrict__ tex,
+                                                const unsigned char* s_tile, int ti0, int tj0, unsigned char* warp_smem,
+                                                const int lane, const double U, const double V, const double SU,
+                                                const double SV, const int S, const int s0, float& mine, bool& collide) {
+    constexpr int TAPS = UamTapsPerTrip<TF>::N;
+    UamGroupRec* s_rec = reinterpret_cast<UamGroupRec*>(warp_smem);
+    int* s_Q = reinterpret_cast<int*>(warp_smem + 32 * 32);          // Q_k = P_k - s0_k: flat index -> sample number
+    float* part = reinterpret_cast<float*>(warp_smem + 32 * 32 + 36 * 4);
+    int incl = S;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int P = incl - S;
+    const int T = __shfl_sync(0xffffffffu, incl, 31);
+    UamGroupRec mr;
+    mr.U = U; mr.SU = SU; mr.V = V; mr.SV = SV;
+    s_rec[lane] = mr;
+    s_Q[lane] = P - s0;
+    float4* prow = reinterpret_cast<float4*>(part + lane * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) prow[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncwarp();
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
+    // lanes without a record (S == 0, only past the end of the last group) have P == T: they never start inside [0, T)
+    float acc = 0.0f;
+    unsigned colmask = 0;
+    int kcur = 0;          // the record `acc` belongs to
+    int started = 0;       // records whose first flat index lies before the current window (warp-uniform)
+    for (int t0 = 0; t0 < T; t0 += 32 * TAPS) {
+        UamTap<TF> tap[TAPS];
+        int kk[TAPS];
+#pragma unroll
+        for (int j = 0; j < TAPS; ++j) {
+            const int wb = t0 + 32 * j;
+            const unsigned rel = (unsigned)(P - wb);
+            const unsigned starts = __reduce_or_sync(0xffffffffu, (rel < 32u && S > 0) ? (1u << rel) : 0u);
+            const int k = started + __popc(starts & le_mask) - 1;
+            started += __popc(starts);
+            kk[j] = k;
+            const double2 a = *reinterpret_cast<const double2*>(&s_rec[k].U);
+            const double2 b = *reinterpret_cast<const double2*>(&s_rec[k].V);
+            const double sd = uam_int2double(wb + lane - s_Q[k]);
+            const double u = __dadd_rn(a.x, __dmul_rn(sd, a.y)), v = __dadd_rn(b.x, __dmul_rn(sd, b.y));
+            if constexpr (TILE) uam_tap_load_tile<TF>(s_tile, ti0, tj0, rp, u, v, tap[j]);
+            else uam_tap_load<TF, LAYOUT>(tex, rp, u, v, tap[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < TAPS; ++j) {
+            float pen;
+            bool occ;
+            uam_tap_eval<TF>(rp, tap[j], pen, occ);
+            const int k = kk[j];
+            if (k != kcur) {
+                part[lane * 32 + (kcur ^ lane)] = acc;
+                acc = 0.0f;
+                kcur = k;
+            }
+            if (t0 + 32 * j + lane < T) {
+                acc += pen;
+                colmask |= (occ ? 1u : 0u) << k;
+            }
+        }
+    }
+    part[lane * 32 + (kcur ^ lane)] = acc;
+    __syncwarp();
+    // per-record reduction: record s = sum over lanes of part[lane][s]; lane s keeps it
+    mine = 0.0f;
+#pragma unroll 4
+    for (int s = 0; s < 32; ++s) {
+        // rows are rotated by the record's offset so that position `lane` always holds the samples with record-local
+        // index == lane (mod 32): the sum is then independent of what else is in the group / batch
+        const int Ps = __shfl_sync(0xffffffffu, P, s);
+        const int row = (lane + Ps) & 31;
+        const float v = uam_warp_sum(part[row * 32 + (s ^ row)]);
+        if (lane == s) mine = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) colmask |= __shfl_xor_sync(0xffffffffu, colmask, o);
+    collide = ((colmask >> lane) & 1u) != 0u;
+    __syncwarp();
+}
 
 template <int TF, int LAYOUT>
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
@@ -593,15 +754,14 @@ uam_k_score_groups(unsigned long long n_seg, UamRasterParams rp, const typename 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char* base = uam_smem + (size_t)warp * UAM_GROUP_SMEM;
-    const UamSegTable tb = uam_seg_table(base, 32);
-    float* part = reinterpret_cast<float*>(base + uam_seg_table_bytes(32));
     const unsigned long long n_groups = (n_seg + 31) >> 5;
     const unsigned long long warp0 = (unsigned long long)blockIdx.x * UAM_WARPS_PER_CTA + warp;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * UAM_WARPS_PER_CTA;
     for (unsigned long long g = warp0; g < n_groups; g += nwarps) {
         const unsigned long long ridx = (g << 5) + lane;
         const bool have = ridx < n_seg;
-        // load this lane's record (3 x 16 B, coalesced across the warp) and build the group's segment table
+        // this lane's record (3 x 16 B, coalesced across the warp)
+        double U = 0.0, V = 0.0, SU = 0.0, SV = 0.0;
         int S = 0;
         unsigned id = 0;
         float IS = 0.0f;
@@ -609,87 +769,18 @@ uam_k_score_groups(unsigned long long n_seg, UamRasterParams rp, const typename 
             const double2* rp2 = reinterpret_cast<const double2*>(recs + ridx);
             const double2 a = __ldg(rp2), b = __ldg(rp2 + 1);
             const int4 c = __ldg(reinterpret_cast<const int4*>(rp2 + 2));
-            tb.U[lane] = a.x; tb.V[lane] = a.y; tb.SU[lane] = b.x; tb.SV[lane] = b.y;
+            U = a.x; V = a.y; SU = b.x; SV = b.y;
             S = c.x;
             IS = __int_as_float(c.y);
             id = (unsigned)c.z;
         }
-        int incl = S;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        tb.P[lane] = incl - S;
-        const int T = __shfl_sync(0xffffffffu, incl, 31);
-        if (lane == 31) tb.P[32] = T;
-        float4* prow = reinterpret_cast<float4*>(part + lane * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) prow[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        __syncwarp();
-        // flat sample loop; acc belongs to segment k and is flushed when the lane moves on
-        float acc = 0.0f;
-        unsigned colmask = 0;
-        int k = 0, p1 = tb.P[1];
-        double kU = tb.U[0], kV = tb.V[0], kSU = tb.SU[0], kSV = tb.SV[0];
-        double sd = (double)lane;
-        for (int t = lane; t < T; t += 64) {
-            if (t >= p1) {
-                part[lane * 32 + (k ^ lane)] = acc;
-                acc = 0.0f;
-                do { ++k; p1 = tb.P[k + 1]; } while (t >= p1);
-                sd = (double)(t - tb.P[k]);
-                kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k];
-            }
-            UamTap<TF> ta, tb2;
-            uam_tap_load<TF, LAYOUT>(tex, rp, __dadd_rn(kU, __dmul_rn(sd, kSU)), __dadd_rn(kV, __dmul_rn(sd, kSV)), ta);
-            sd += 32.0;
-            const int k0 = k;
-            const int t2 = t + 32;
-            const bool two = t2 < T;
-            bool moved = false;
-            if (two && t2 >= p1) {
-                moved = true;
-                do { ++k; p1 = tb.P[k + 1]; } while (t2 >= p1);
-                sd = (double)(t2 - tb.P[k]);
-                kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k];
-            }
-            uam_tap_load<TF, LAYOUT>(tex, rp, __dadd_rn(kU, __dmul_rn(sd, kSU)), __dadd_rn(kV, __dmul_rn(sd, kSV)), tb2);
-            if (two) sd += 32.0;
-            float pen;
-            bool occ;
-            uam_tap_eval<TF>(rp, ta, pen, occ);
-            acc += pen;
-            colmask |= (occ ? 1u : 0u) << k0;
-            if (moved) {
-                part[lane * 32 + (k0 ^ lane)] = acc;
-                acc = 0.0f;
-            }
-            uam_tap_eval<TF>(rp, tb2, pen, occ);
-            if (two) {
-                acc += pen;
-                colmask |= (occ ? 1u : 0u) << k;
-            }
-        }
-        part[lane * 32 + (k ^ lane)] = acc;
-        __syncwarp();
-        // per-segment reduction: segment s = sum over lanes of part[lane][s]; lane s keeps it
-        float mine = 0.0f;
-#pragma unroll 4
-        for (int s = 0; s < 32; ++s) {
-            // rows are rotated by the segment's offset so that position `lane` always holds the samples with index
-            // == lane (mod 32) of THAT segment: the sum is then independent of what else is in the group / batch
-            const int row = (lane + tb.P[s]) & 31;
-            const float v = uam_warp_sum(part[row * 32 + (s ^ row)]);
-            if (lane == s) mine = v;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) colmask |= __shfl_xor_sync(0xffffffffu, colmask, o);
+        float mine;
+        bool col;
+        uam_group_score<TF, LAYOUT, 0>(rp, tex, nullptr, 0, 0, base, lane, U, V, SU, SV, S, 0, mine, col);
         if (have) {
             part_pen[id] = mine * IS;
-            part_col[id] = (colmask >> lane) & 1u;
+            part_col[id] = col ? 1 : 0;
         }
-        __syncwarp();
     }
 }
 
@@ -755,8 +846,6 @@ uam_k_reduce_paths(const double2* __restrict__ z, long long B, int Wp, UamRaster
 // sample can never be assigned to a tile that does not hold its footprint.  Each piece writes its partial sum to a
 // slot that depends only on its own path (path-contiguous slot ranges from a prefix sum over per-path piece counts)
 // and the last kernel adds a path's slots in a fixed order: results are independent of the rest of the batch.
-#define UAM_TS 64                         // tile side in cells
-#define UAM_TSH (UAM_TS + 1)              // with the halo row / column
 #define UAM_ITEM_PIECES 2048              // pieces per work item (one tile load per item)
 
 struct __align__(16) UamPieceRec {
@@ -977,23 +1066,6 @@ __device__ __forceinline__ void uam_mbar_wait(void* bar, unsigned parity) {
         ::"r"(uam_smem_u32(bar)), "r"(parity) : "memory");
 }
 
-// A bilinear tap from the staged tile: (i0, j0) are raster cells, (ti0, tj0) the tile's first cell.  The min() is
-// for memory safety only (a correct cut never leaves the tile).
-template <int TF>
-__device__ __forceinline__ void uam_tap_load_tile(const unsigned char* tile, int ti0, int tj0, const UamRasterParams& rp,
-                                                  double u, double v, UamTap<TF>& t) {
-    typedef typename UamTexel<TF>::T T;
-    int i0, j0;
-    uam_cell_frac1(u, rp.W, j0, t.fx);
-    uam_cell_frac1(v, rp.H, i0, t.fy);
-    const unsigned li = min((unsigned)(i0 - ti0), (unsigned)(UAM_TS - 1)), lj = min((unsigned)(j0 - tj0), (unsigned)(UAM_TS - 1));
-    const T* p = reinterpret_cast<const T*>(tile) + (li * UAM_TSH + lj);
-    t.a = p[0];
-    t.b = p[1];
-    t.c = p[UAM_TSH];
-    t.d = p[UAM_TSH + 1];
-}
-
 // shared memory of uam_k_score_tiles: [tile (copy_bytes, 128-aligned)] [mbarrier + control, 128 B] [per-warp areas]
 #define UAM_TILE_CTL_BYTES 128
 
@@ -1010,9 +1082,6 @@ uam_k_score_tiles(UamRasterParams rp, UamTileGeo tg, const unsigned char* __rest
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(uam_smem + tile_area);
     volatile unsigned* s_ctl = reinterpret_cast<volatile unsigned*>(uam_smem + tile_area + 16);   // [0] item, [1] next group
     unsigned char* base = uam_smem + tile_area + UAM_TILE_CTL_BYTES + (size_t)warp * UAM_GROUP_SMEM;
-    const UamSegTable tb = uam_seg_table(base, 32);
-    int* tQ = reinterpret_cast<int*>(tb.IS);          // P[k] - s0[k]: flat index -> sample number in the parent segment
-    float* part = reinterpret_cast<float*>(base + uam_seg_table_bytes(32));
     if (threadIdx.x == 0) uam_mbar_init(s_bar, 1);
     __syncthreads();
     const unsigned n_items = counters[0];
@@ -1043,6 +1112,7 @@ uam_k_score_tiles(UamRasterParams rp, UamTileGeo tg, const unsigned char* __rest
         while (g < hi) {
             const unsigned ridx = g + lane;
             const bool have = ridx < hi;
+            double U = 0.0, V = 0.0, SU = 0.0, SV = 0.0;
             int S = 0, s0 = 0;
             unsigned slot = 0;
             float IS = 0.0f;
@@ -1050,87 +1120,19 @@ uam_k_score_tiles(UamRasterParams rp, UamTileGeo tg, const unsigned char* __rest
                 const double2* rp2 = reinterpret_cast<const double2*>(recs + ridx);
                 const double2 a = __ldg(rp2), b = __ldg(rp2 + 1);
                 const int4 c = __ldg(reinterpret_cast<const int4*>(rp2 + 2));
-                tb.U[lane] = a.x; tb.V[lane] = a.y; tb.SU[lane] = b.x; tb.SV[lane] = b.y;
+                U = a.x; V = a.y; SU = b.x; SV = b.y;
                 s0 = c.x;
                 S = c.y;
                 IS = __int_as_float(c.z);
                 slot = (unsigned)c.w;
             }
-            int incl = S;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            tb.P[lane] = incl - S;
-            tQ[lane] = incl - S - s0;
-            const int T = __shfl_sync(0xffffffffu, incl, 31);
-            if (lane == 31) tb.P[32] = T;
-            float4* prow = reinterpret_cast<float4*>(part + lane * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) prow[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            __syncwarp();
-            float acc = 0.0f;
-            unsigned colmask = 0;
-            int k = 0, p1 = tb.P[1];
-            double kU = tb.U[0], kV = tb.V[0], kSU = tb.SU[0], kSV = tb.SV[0];
-            double sd = (double)(lane - tQ[0]);
-            for (int t = lane; t < T; t += 64) {
-                if (t >= p1) {
-                    part[lane * 32 + (k ^ lane)] = acc;
-                    acc = 0.0f;
-                    do { ++k; p1 = tb.P[k + 1]; } while (t >= p1);
-                    sd = (double)(t - tQ[k]);
-                    kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k];
-                }
-                UamTap<TF> ta, tb2;
-                uam_tap_load_tile<TF>(s_tile, ti0, tj0, rp, __dadd_rn(kU, __dmul_rn(sd, kSU)), __dadd_rn(kV, __dmul_rn(sd, kSV)), ta);
-                sd += 32.0;
-                const int k0 = k;
-                const int t2 = t + 32;
-                const bool two = t2 < T;
-                bool moved = false;
-                if (two && t2 >= p1) {
-                    moved = true;
-                    do { ++k; p1 = tb.P[k + 1]; } while (t2 >= p1);
-                    sd = (double)(t2 - tQ[k]);
-                    kU = tb.U[k]; kV = tb.V[k]; kSU = tb.SU[k]; kSV = tb.SV[k];
-                }
-                uam_tap_load_tile<TF>(s_tile, ti0, tj0, rp, __dadd_rn(kU, __dmul_rn(sd, kSU)), __dadd_rn(kV, __dmul_rn(sd, kSV)), tb2);
-                if (two) sd += 32.0;
-                float pen;
-                bool occ;
-                uam_tap_eval<TF>(rp, ta, pen, occ);
-                acc += pen;
-                colmask |= (occ ? 1u : 0u) << k0;
-                if (moved) {
-                    part[lane * 32 + (k0 ^ lane)] = acc;
-                    acc = 0.0f;
-                }
-                uam_tap_eval<TF>(rp, tb2, pen, occ);
-                if (two) {
-                    acc += pen;
-                    colmask |= (occ ? 1u : 0u) << k;
-                }
-            }
-            part[lane * 32 + (k ^ lane)] = acc;
-            __syncwarp();
-            float mine = 0.0f;
-#pragma unroll 4
-            for (int s = 0; s < 32; ++s) {
-                // rows rotated by the piece's offset: position `lane` always holds the samples with piece-local index
-                // == lane (mod 32), so the sum does not depend on what else is in the group
-                const int row = (lane + tb.P[s]) & 31;
-                const float v = uam_warp_sum(part[row * 32 + (s ^ row)]);
-                if (lane == s) mine = v;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) colmask |= __shfl_xor_sync(0xffffffffu, colmask, o);
+            float mine;
+            bool col;
+            uam_group_score<TF, 0, 1>(rp, nullptr, s_tile, ti0, tj0, base, lane, U, V, SU, SV, S, s0, mine, col);
             if (have) {
                 part_pen[slot] = mine * IS;
-                part_col[slot] = (colmask >> lane) & 1u;
+                part_col[slot] = col ? 1 : 0;
             }
-            __syncwarp();
             // next group of this item: first come, first served
             unsigned nx = 0;
             if (lane == 0) nx = atomicAdd((unsigned*)&s_ctl[1], 32u);
@@ -1204,7 +1206,7 @@ __global__ void uam_k_build_tiles(const typename UamTexel<TF>::T* __restrict__ t
         const unsigned i = (tile / (unsigned)tg.tiles_x) * UAM_TS + li, j = (tile % (unsigned)tg.tiles_x) * UAM_TS + lj;
         T v;
         if (i < (unsigned)rp.H && j < (unsigned)rp.W) {
-            v = tex[uam_tex_row<TF, LAYOUT>(i, rp.row_stride) + uam_tex_col<TF, LAYOUT>(j)];
+            v = tex[uam_tex_row<(TF == 1 ? 4 : TF), LAYOUT>(i, rp.row_stride) + uam_tex_col<(TF == 1 ? 4 : TF), LAYOUT>(j)];
         } else {
             if constexpr (TF == 2) v = make_float2(0.0f, 0.0f); else v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
@@ -1391,7 +1393,11 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
         UAM_TRY(uam_time_collect(ctx));
         UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
     }
+    if constexpr (TF == 1) {
+        if (!(rp.spc > 0.0 && rp.variant >= 2)) return uam_fail(ctx, UAM_ERR_STATE, "quad texels are only sampled by the binned pipelines");
+    }
     if (rp.spc == 0.0) {
+      if constexpr (TF != 1) {
         const long long ctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
         uam_k_score_raster_wp<TF, LAYOUT><<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
         UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_wp");
@@ -1399,6 +1405,7 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
             UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
             ctx->time_pending = true;
         }
+      }
         return UAM_OK;
     }
     if (rp.variant >= 2 && (unsigned long long)B * Wp < 0xffffffffull) {
@@ -1409,6 +1416,7 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
         }
         return uam_raster_launch_binned<TF, LAYOUT>(ctx, texv, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
     }
+  if constexpr (TF != 1) {
     const size_t per_warp = uam_seg_table_bytes(Wp);
     const size_t budget = 200 * 1024;
     if (per_warp > budget) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "N = %d waypoints per path is too many for integral mode", Wp - 2);
@@ -1427,56 +1435,106 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
         UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
         ctx->time_pending = true;
     }
+  }
     return UAM_OK;
 }
 
-// Weight-combined texels.  The penalty is linear in the layers, sum_l w_l * bilerp(layer_l) = bilerp(sum_l w_l * layer_l),
-// so for a given weight vector the L = 2..3 layer raster collapses into ONE layer: float2 texels {sum_l w_l layer_l,
-// occupancy}, half the bytes per bilinear tap (32 instead of 64).  Built per (raster, weights) and kept until either
-// changes; used by the large-batch pipelines (variants 2 and 3), whose gather is bound by the bytes moved through L1 /
-// shared memory.  The combination is fp32 (same rounding class as the per-layer sum it replaces).
-template <int LAYOUT>
-__global__ void uam_k_combine_layers(const float4* __restrict__ tex4, int H, int W, unsigned rs4, unsigned rs2, float w0, float w1,
-                                     float w2, size_t n_out, float2* __restrict__ tex2) {
+// Quad texels for the large-batch integral pipelines (variants 2 and 3), whose gather is bound by the number of load
+// requests / bytes moved through L1 or shared memory:
+//  * the penalty is linear in the layers, sum_l w_l * bilerp(layer_l) = bilerp(sum_l w_l * layer_l), so for a given
+//    weight vector an L = 2..3 raster collapses into ONE layer C = sum_l w_l * layer_l (fp32, same rounding class as
+//    the per-layer sum it replaces); an L = 1 raster keeps its raw layer and the weight is applied after the lerp;
+//  * cell (i, j) then stores its whole bilinear footprint {C(i,j), C(i,j+1), C(i+1,j), C(i+1,j+1)} as one float4, and
+//    the occupancy flags move to a bit-plane: a bilinear tap is ONE 16-byte load + one (cache-resident) word load
+//    instead of four 16-byte loads.
+// Built per (raster, weights) and kept until either changes.
+template <int TF, int LAYOUT>
+__global__ void uam_k_build_quads(const typename UamTexel<TF>::T* __restrict__ tex, int H, int W, unsigned rs_src, unsigned rs_q,
+                                  float w0, float w1, float w2, size_t n_out, float4* __restrict__ quad) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    auto value = [&](int i, int j) -> float {
+        if (i >= H || j >= W) return 0.0f;
+        const typename UamTexel<TF>::T t = tex[uam_tex_row<TF, LAYOUT>(i, rs_src) + uam_tex_col<TF, LAYOUT>(j)];
+        if constexpr (TF == 2) return t.x; else return w0 * t.x + w1 * t.y + w2 * t.z;
+    };
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += stride) {
-        // o -> (i, j) of the float2 layout (one thread per output texel, coalesced stores)
-        int i, j;
+        int i, j;                     // o -> cell of the float4 layout (one thread per output texel, coalesced stores)
         if (LAYOUT == 0) {
             i = (int)(o / W);
             j = (int)(o - (size_t)i * W);
         } else {
-            const size_t tile = o >> 4;
-            const int w = (int)(o & 15), tiles_x = (int)(rs2 >> 4);
+            const size_t tile = o >> 3;
+            const int w = (int)(o & 7), tiles_x = (int)(rs_q >> 3);
             const int ty = (int)(tile / tiles_x), tx = (int)(tile - (size_t)ty * tiles_x);
-            i = ty * 4 + ((w >> 3) & 1) * 2 + ((w >> 1) & 1);
+            i = ty * 2 + ((w >> 1) & 1);
             j = tx * 4 + ((w >> 2) & 1) * 2 + (w & 1);
         }
-        float2 v = make_float2(0.0f, 0.0f);
-        if (i < H && j < W) {
-            const float4 t = tex4[uam_tex_row<4, LAYOUT>(i, rs4) + uam_tex_col<4, LAYOUT>(j)];
-            v = make_float2(w0 * t.x + w1 * t.y + w2 * t.z, t.w);
-        }
-        tex2[o] = v;
+        quad[o] = make_float4(value(i, j), value(i, j + 1), value(i + 1, j), value(i + 1, j + 1));
     }
 }
 
-int uam_ensure_combined(uam_ctx* ctx, const UamRasterParams& rp, unsigned* rs2, cudaStream_t st) {
-    const int W = rp.W, H = rp.H, lay = ctx->geo.layout;
-    const int tiles_x = (W + 3) / 4, tiles_y = (H + 3) / 4;
-    *rs2 = lay ? (unsigned)tiles_x * 16u : (unsigned)W;
-    if (ctx->comb_valid && ctx->comb_w[0] == rp.w0 && ctx->comb_w[1] == rp.w1 && ctx->comb_w[2] == rp.w2) return UAM_OK;
-    const size_t n_out = lay ? (size_t)tiles_x * tiles_y * 16 : (size_t)H * W;
-    UAM_CUDA(ctx, cudaDeviceSynchronize());      // kernels on other streams may still read the old combination
-    UAM_TRY(uam_reserve(ctx, &ctx->d_tex_comb, &ctx->tex_comb_bytes, n_out * sizeof(float2)));
-    const int grid = ctx->sm_count * 8;
-    if (lay) uam_k_combine_layers<1><<<grid, 256, 0, st>>>((const float4*)ctx->d_tex, H, W, rp.row_stride, *rs2, rp.w0, rp.w1, rp.w2, n_out, (float2*)ctx->d_tex_comb);
-    else uam_k_combine_layers<0><<<grid, 256, 0, st>>>((const float4*)ctx->d_tex, H, W, rp.row_stride, *rs2, rp.w0, rp.w1, rp.w2, n_out, (float2*)ctx->d_tex_comb);
-    UAM_CHECK_LAUNCH(ctx, "uam_k_combine_layers");
-    UAM_CUDA(ctx, cudaStreamSynchronize(st));    // every pipeline stream may use it from now on
-    ctx->comb_valid = true;
-    ctx->comb_w[0] = rp.w0; ctx->comb_w[1] = rp.w1; ctx->comb_w[2] = rp.w2;
-    ctx->comb_gen += 1;
+// one thread per 32-bit word (8 x 4 cells) of the occupancy bit-plane
+template <int TF, int LAYOUT>
+__global__ void uam_k_build_occ_bits(const typename UamTexel<TF>::T* __restrict__ tex, int H, int W, unsigned rs_src, unsigned blocks_x,
+                                     unsigned n_words, unsigned* __restrict__ bits) {
+    const unsigned o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_words) return;
+    const unsigned blk = o >> 5, wi = (o >> 2) & 7u, wj = o & 3u;
+    const unsigned i0 = (blk / blocks_x) * 32u + wi * 4u, j0 = (blk % blocks_x) * 32u + wj * 8u;
+    unsigned word = 0;
+    for (unsigned b = 0; b < 32; ++b) {
+        const unsigned i = i0 + (b >> 3), j = j0 + (b & 7u);
+        if (i < (unsigned)H && j < (unsigned)W) {
+            const typename UamTexel<TF>::T t = tex[uam_tex_row<TF, LAYOUT>(i, rs_src) + uam_tex_col<TF, LAYOUT>(j)];
+            float occ;
+            if constexpr (TF == 2) occ = t.y; else occ = t.w;
+            if (occ != 0.0f) word |= 1u << b;
+        }
+    }
+    bits[o] = word;
+}
+
+template <int TF, int LAYOUT>
+int uam_build_quads_t(uam_ctx* ctx, const UamRasterParams& rp, unsigned rs_q, size_t n_out, bool bits, unsigned blocks_x,
+                      unsigned n_words, cudaStream_t st) {
+    typedef typename UamTexel<TF>::T T;
+    if (bits) {
+        uam_k_build_occ_bits<TF, LAYOUT><<<(n_words + 255) / 256, 256, 0, st>>>((const T*)ctx->d_tex, rp.H, rp.W, rp.row_stride, blocks_x, n_words,
+                                                                               (unsigned*)ctx->d_occ_bits);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_build_occ_bits");
+    }
+    uam_k_build_quads<TF, LAYOUT><<<ctx->sm_count * 8, 256, 0, st>>>((const T*)ctx->d_tex, rp.H, rp.W, rp.row_stride, rs_q, rp.w0, rp.w1, rp.w2,
+                                                                      n_out, (float4*)ctx->d_tex_comb);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_build_quads");
+    return UAM_OK;
+}
+
+int uam_ensure_quads(uam_ctx* ctx, UamRasterParams* rp, cudaStream_t st) {
+    const int W = rp->W, H = rp->H, lay = ctx->geo.layout, tf = ctx->geo.texel_floats;
+    const int tiles_x = (W + 3) / 4, tiles_y = (H + 1) / 2;
+    const unsigned rs_q = lay ? (unsigned)tiles_x * 8u : (unsigned)W;
+    const unsigned blocks_x = (unsigned)(W + 31) / 32u, blocks_y = (unsigned)(H + 31) / 32u;
+    rp->row_stride2 = rs_q;
+    rp->occ_blocks_x = blocks_x;
+    const bool same_w = tf == 2 || (ctx->comb_w[0] == rp->w0 && ctx->comb_w[1] == rp->w1 && ctx->comb_w[2] == rp->w2);
+    if (!(ctx->comb_valid && same_w && ctx->occ_bits_valid)) {
+        const size_t n_out = lay ? (size_t)tiles_x * tiles_y * 8 : (size_t)H * W;
+        const unsigned n_words = blocks_x * blocks_y * 32u;
+        UAM_CUDA(ctx, cudaDeviceSynchronize());      // kernels on other streams may still read the old quads
+        UAM_TRY(uam_reserve(ctx, &ctx->d_tex_comb, &ctx->tex_comb_bytes, n_out * sizeof(float4)));
+        UAM_TRY(uam_reserve(ctx, &ctx->d_occ_bits, &ctx->occ_bits_bytes, (size_t)n_words * 4));
+        const bool bits = !ctx->occ_bits_valid;
+        if (tf == 2) UAM_TRY(lay ? (uam_build_quads_t<2, 1>(ctx, *rp, rs_q, n_out, bits, blocks_x, n_words, st))
+                                 : (uam_build_quads_t<2, 0>(ctx, *rp, rs_q, n_out, bits, blocks_x, n_words, st)));
+        else UAM_TRY(lay ? (uam_build_quads_t<4, 1>(ctx, *rp, rs_q, n_out, bits, blocks_x, n_words, st))
+                         : (uam_build_quads_t<4, 0>(ctx, *rp, rs_q, n_out, bits, blocks_x, n_words, st)));
+        UAM_CUDA(ctx, cudaStreamSynchronize(st));    // every pipeline stream may use them from now on
+        ctx->comb_valid = true;
+        ctx->occ_bits_valid = true;
+        ctx->comb_w[0] = rp->w0; ctx->comb_w[1] = rp->w1; ctx->comb_w[2] = rp->w2;
+        ctx->comb_gen += 1;
+    }
+    rp->occ_bits = (const unsigned*)ctx->d_occ_bits;
     return UAM_OK;
 }
 
@@ -1487,26 +1545,25 @@ int uam_raster_launch(uam_ctx* ctx, const double* d_z, int64_t B, int N, const U
     const double2* z = reinterpret_cast<const double2*>(d_z);
     const int tf = ctx->geo.texel_floats, lay = ctx->geo.layout;
     const uint64_t key = ctx->raster_gen << 1;
-    if (tf == 2) return lay ? uam_raster_launch_t<2, 1>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
-                            : uam_raster_launch_t<2, 0>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
     if (rp.combined) {
-        // large-batch integral mode on the weight-combined single-layer texels (made by uam_raster_prepare)
+        // large-batch integral mode on the quad texels (made by uam_raster_precompute)
         UamRasterParams rc = rp;
-        rc.w0 = 1.0f; rc.w1 = 0.0f; rc.w2 = 0.0f;
+        if (tf == 4) { rc.w0 = 1.0f; rc.w1 = 0.0f; rc.w2 = 0.0f; }     // the weights are inside the quads
         rc.row_stride = rp.row_stride2;
         const uint64_t ckey = (ctx->comb_gen << 1) | 1u;
-        return lay ? uam_raster_launch_t<2, 1>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot)
-                   : uam_raster_launch_t<2, 0>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot);
+        return lay ? uam_raster_launch_t<1, 1>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot)
+                   : uam_raster_launch_t<1, 0>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot);
     }
+    if (tf == 2) return lay ? uam_raster_launch_t<2, 1>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
+                            : uam_raster_launch_t<2, 0>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
     return lay ? uam_raster_launch_t<4, 1>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
                : uam_raster_launch_t<4, 0>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
 }
 
-// Once per API call, before any chunk is launched: make the weight-combined texels if this call will use them.
+// Once per API call, before any chunk is launched: make the quad texels if this call will use them.
 int uam_raster_precompute(uam_ctx* ctx, UamRasterParams* rp, int64_t B, int N, cudaStream_t st) {
-    if (ctx->geo.texel_floats == 4 && rp->spc > 0.0 && rp->variant >= 2 && ctx->combine_layers &&
-        (unsigned long long)B * (N + 2) < 0xffffffffull) {
-        UAM_TRY(uam_ensure_combined(ctx, *rp, &rp->row_stride2, st));
+    if (rp->spc > 0.0 && rp->variant >= 2 && ctx->combine_layers && (unsigned long long)B * (N + 2) < 0xffffffffull) {
+        UAM_TRY(uam_ensure_quads(ctx, rp, st));
         rp->combined = 1;
     }
     return UAM_OK;
