@@ -92,10 +92,11 @@ enum {
     UAM_OPT_TIME_KERNELS = 4,         /* 1: bracket the dominant raster-scoring kernel of every device-pointer call with
                                          CUDA events on the caller's stream (resets the statistics) */
     UAM_OPT_COMBINE_LAYERS = 5        /* 1 (default): large-batch integral mode samples "quad texels": the layers are folded
-                                         into ONE layer sum_l w_l * layer_l (the penalty is linear in the layers), every
-                                         cell stores its 2 x 2 bilinear footprint as one float4 and occupancy is a
-                                         bit-plane, so a tap is one 16-byte load; rebuilt when the weights or the raster
-                                         change.  0: always sample every layer texel by texel */
+                                         into ONE layer sum_l w_l * layer_l (the penalty is linear in the layers) and every
+                                         cell stores its 2 x 2 bilinear footprint as one float4, so a tap is one 16-byte
+                                         load; occupancy flags ride in the sign bits when all values are >= 0, else in a
+                                         bit-plane.  Rebuilt when the weights or the raster change.  2: as 1 but always the
+                                         bit-plane form.  0: always sample every layer texel by texel */
 };
 /* statistics of UAM_OPT_TIME_KERNELS: mean device time (ms) of the dominant scoring kernel (uam_k_score_tiles / uam_k_score_groups /
  * uam_k_score_raster_int / uam_k_score_raster_wp) over the timed calls, and their number */

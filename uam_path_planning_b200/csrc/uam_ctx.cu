@@ -107,6 +107,7 @@ extern "C" int uam_ctx_create(int device, uam_ctx** out) {
     // tuning knobs from the environment (bench A/B runs); uam_ctx_set_option overrides
     if (const char* e = getenv("UAM_RASTER_LAYOUT")) ctx->raster_layout = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = std::min(3, std::max(-1, atoi(e)));
+    if (const char* e = getenv("UAM_NO_SIGN_PACK")) ctx->no_sign_pack = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_COMBINE_LAYERS")) ctx->combine_layers = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_HOST_CHUNKS")) ctx->host_chunks = std::max(0, atoi(e));
     if (const char* e = getenv("UAM_L2_FETCH_GRANULARITY")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
@@ -131,8 +132,10 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             UAM_CUDA(ctx, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
             return UAM_OK;
         case UAM_OPT_COMBINE_LAYERS:
-            if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "combine_layers must be 0 or 1");
-            ctx->combine_layers = (int)value;
+            if (value < 0 || value > 2) return uam_fail(ctx, UAM_ERR_INVALID, "combine_layers must be 0, 1 or 2");
+            ctx->combine_layers = value != 0;
+            ctx->no_sign_pack = value == 2;
+            ctx->comb_valid = false;
             return UAM_OK;
         case UAM_OPT_TIME_KERNELS:
             UAM_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -111,6 +111,8 @@ struct uam_ctx {
     void* d_occ_bits = nullptr;
     size_t occ_bits_bytes = 0;
     bool occ_bits_valid = false;
+    bool comb_packed = false;           // quads carry the occupancy flags in their sign bits
+    int no_sign_pack = 0;               // UAM_NO_SIGN_PACK=1 forces the bit-plane form (tests)
     float comb_w[3] = {};
     uint64_t comb_gen = 0, raster_gen = 0;
     int combine_layers = 1;             // UAM_OPT_COMBINE_LAYERS

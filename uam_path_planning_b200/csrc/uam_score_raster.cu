@@ -36,7 +36,7 @@ struct UamRasterParams {
     float w0, w1, w2;
     int flags;
     int variant;          // integral-mode kernel, decided once per API call from the call's whole batch
-    int combined;         // 1: score on the weight-combined quad texels (ctx->d_tex_comb, row stride row_stride2)
+    int combined;         // score on the quad texels (ctx->d_tex_comb, row stride row_stride2): 1 = + bit-plane, 2 = sign-packed
     unsigned row_stride2;
     const unsigned* occ_bits;   // quad mode: occupancy bit-plane (uam_occ_word / uam_occ_bit)
     unsigned occ_blocks_x;      // 32 x 32-cell blocks per block-row of the bit-plane
@@ -46,6 +46,8 @@ template <int TF> struct UamTexel;
 template <> struct UamTexel<2> { typedef float2 T; };
 template <> struct UamTexel<4> { typedef float4 T; };
 template <> struct UamTexel<1> { typedef float4 T; };      // quad mode: the 2 x 2 bilinear footprint of a cell in one texel
+template <> struct UamTexel<8> { typedef float4 T; };      // quad mode, occupancy flags in the sign bits (values >= 0)
+template <int TF> struct UamIsQuad { static const bool v = (TF == 1 || TF == 8); };
 
 // Texel address = uam_tex_row(i) + uam_tex_col(j)  (both layouts are separable).
 // LAYOUT 0: row-major (H, W).  LAYOUT 1: tiled so that one 128-byte line is a compact 2-D block and every 32-byte
@@ -123,13 +125,22 @@ struct UamTap<1> {
     float fx, fy;
 };
 
+// sign-packed quads: every corner value is >= 0 and carries its own cell's occupancy flag in the sign bit
+template <>
+struct UamTap<8> {
+    float4 q;
+    float fx, fy;
+};
+
 template <int TF, int LAYOUT>
 __device__ __forceinline__ void uam_tap_load(const typename UamTexel<TF>::T* __restrict__ tex, const UamRasterParams& rp,
                                              double u, double v, UamTap<TF>& t) {
     int i0, j0;
     uam_cell_frac1(u, rp.W, j0, t.fx);
     uam_cell_frac1(v, rp.H, i0, t.fy);
-    if constexpr (TF == 1) {
+    if constexpr (TF == 8) {
+        t.q = __ldg(tex + (uam_tex_row<4, LAYOUT>(i0, rp.row_stride) + uam_tex_col<4, LAYOUT>(j0)));
+    } else if constexpr (TF == 1) {
         t.q = __ldg(tex + (uam_tex_row<4, LAYOUT>(i0, rp.row_stride) + uam_tex_col<4, LAYOUT>(j0)));
         const unsigned ni = (unsigned)i0 + (t.fy >= 0.5f ? 1u : 0u), nj = (unsigned)j0 + (t.fx >= 0.5f ? 1u : 0u);
         t.ow = __ldg(rp.occ_bits + uam_occ_word(ni, nj, rp.occ_blocks_x));
@@ -146,7 +157,12 @@ __device__ __forceinline__ void uam_tap_load(const typename UamTexel<TF>::T* __r
 
 template <int TF>
 __device__ __forceinline__ void uam_tap_eval(const UamRasterParams& rp, const UamTap<TF>& t, float& pen, bool& occ) {
-    if constexpr (TF == 1) {
+    if constexpr (TF == 8) {
+        pen = rp.w0 * uam_lerp2(fabsf(t.q.x), fabsf(t.q.y), fabsf(t.q.z), fabsf(t.q.w), t.fx, t.fy);
+        const bool right = t.fx >= 0.5f, down = t.fy >= 0.5f;
+        const float o = down ? (right ? t.q.w : t.q.z) : (right ? t.q.y : t.q.x);
+        occ = __float_as_int(o) < 0;
+    } else if constexpr (TF == 1) {
         pen = rp.w0 * uam_lerp2(t.q.x, t.q.y, t.q.z, t.q.w, t.fx, t.fy);
         occ = ((t.ow >> t.ob) & 1u) != 0u;
     } else {
@@ -628,7 +644,9 @@ __device__ __forceinline__ void uam_tap_load_tile(const unsigned char* tile, int
     uam_cell_frac1(v, rp.H, i0, t.fy);
     const unsigned li = min((unsigned)(i0 - ti0), (unsigned)(UAM_TS - 1)), lj = min((unsigned)(j0 - tj0), (unsigned)(UAM_TS - 1));
     const T* p = reinterpret_cast<const T*>(tile) + (li * UAM_TSH + lj);
-    if constexpr (TF == 1) {
+    if constexpr (TF == 8) {
+        t.q = p[0];
+    } else if constexpr (TF == 1) {
         t.q = p[0];
         const unsigned ni = (unsigned)i0 + (t.fy >= 0.5f ? 1u : 0u), nj = (unsigned)j0 + (t.fx >= 0.5f ? 1u : 0u);
         t.ow = __ldg(rp.occ_bits + uam_occ_word(ni, nj, rp.occ_blocks_x));
@@ -656,6 +674,7 @@ struct __align__(16) UamGroupRec {
 
 template <int TF> struct UamTapsPerTrip { static const int N = 2; };
 template <> struct UamTapsPerTrip<1> { static const int N = 4; };
+template <> struct UamTapsPerTrip<8> { static const int N = 4; };
 
 // Scores one group.  In: this lane's record (first sample U/V, step SU/SV, S samples starting at sample number s0 of
 // its parent segment; S = 0 for a lane without a record).  Out: the record's sample sum (not yet divided by the
@@ -1206,7 +1225,7 @@ __global__ void uam_k_build_tiles(const typename UamTexel<TF>::T* __restrict__ t
         const unsigned i = (tile / (unsigned)tg.tiles_x) * UAM_TS + li, j = (tile % (unsigned)tg.tiles_x) * UAM_TS + lj;
         T v;
         if (i < (unsigned)rp.H && j < (unsigned)rp.W) {
-            v = tex[uam_tex_row<(TF == 1 ? 4 : TF), LAYOUT>(i, rp.row_stride) + uam_tex_col<(TF == 1 ? 4 : TF), LAYOUT>(j)];
+            v = tex[uam_tex_row<(UamIsQuad<TF>::v ? 4 : TF), LAYOUT>(i, rp.row_stride) + uam_tex_col<(UamIsQuad<TF>::v ? 4 : TF), LAYOUT>(j)];
         } else {
             if constexpr (TF == 2) v = make_float2(0.0f, 0.0f); else v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
@@ -1393,11 +1412,11 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
         UAM_TRY(uam_time_collect(ctx));
         UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
     }
-    if constexpr (TF == 1) {
+    if constexpr (UamIsQuad<TF>::v) {
         if (!(rp.spc > 0.0 && rp.variant >= 2)) return uam_fail(ctx, UAM_ERR_STATE, "quad texels are only sampled by the binned pipelines");
     }
     if (rp.spc == 0.0) {
-      if constexpr (TF != 1) {
+      if constexpr (!UamIsQuad<TF>::v) {
         const long long ctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
         uam_k_score_raster_wp<TF, LAYOUT><<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
         UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_wp");
@@ -1416,7 +1435,7 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
         }
         return uam_raster_launch_binned<TF, LAYOUT>(ctx, texv, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
     }
-  if constexpr (TF != 1) {
+  if constexpr (!UamIsQuad<TF>::v) {
     const size_t per_warp = uam_seg_table_bytes(Wp);
     const size_t budget = 200 * 1024;
     if (per_warp > budget) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "N = %d waypoints per path is too many for integral mode", Wp - 2);
@@ -1445,17 +1464,28 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
 //    weight vector an L = 2..3 raster collapses into ONE layer C = sum_l w_l * layer_l (fp32, same rounding class as
 //    the per-layer sum it replaces); an L = 1 raster keeps its raw layer and the weight is applied after the lerp;
 //  * cell (i, j) then stores its whole bilinear footprint {C(i,j), C(i,j+1), C(i+1,j), C(i+1,j+1)} as one float4, and
-//    the occupancy flags move to a bit-plane: a bilinear tap is ONE 16-byte load + one (cache-resident) word load
-//    instead of four 16-byte loads.
+//    a bilinear tap is ONE 16-byte load instead of four.  The occupancy flags ride in the sign bits of the four
+//    values when every value is >= 0 (checked on the device while building; -0.0 marks an occupied cell of value 0),
+//    otherwise they move to a bit-plane (one extra, cache-resident word load per tap).
 // Built per (raster, weights) and kept until either changes.
-template <int TF, int LAYOUT>
+// PACK = 1: store occupied cells' values negated (sign bit = occupancy flag; needs every value >= 0: a negative or NaN
+// value raises *bad and the caller rebuilds with PACK = 0 + the bit-plane).
+template <int TF, int LAYOUT, int PACK>
 __global__ void uam_k_build_quads(const typename UamTexel<TF>::T* __restrict__ tex, int H, int W, unsigned rs_src, unsigned rs_q,
-                                  float w0, float w1, float w2, size_t n_out, float4* __restrict__ quad) {
+                                  float w0, float w1, float w2, size_t n_out, float4* __restrict__ quad, unsigned* __restrict__ bad) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool neg = false;
     auto value = [&](int i, int j) -> float {
         if (i >= H || j >= W) return 0.0f;
         const typename UamTexel<TF>::T t = tex[uam_tex_row<TF, LAYOUT>(i, rs_src) + uam_tex_col<TF, LAYOUT>(j)];
-        if constexpr (TF == 2) return t.x; else return w0 * t.x + w1 * t.y + w2 * t.z;
+        float c, o;
+        if constexpr (TF == 2) { c = t.x; o = t.y; } else { c = w0 * t.x + w1 * t.y + w2 * t.z; o = t.w; }
+        if constexpr (PACK) {
+            neg = neg || !(c >= 0.0f);
+            c = fabsf(c);                    // -0.0 -> +0.0
+            if (o != 0.0f) c = -c;
+        }
+        return c;
     };
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += stride) {
         int i, j;                     // o -> cell of the float4 layout (one thread per output texel, coalesced stores)
@@ -1471,6 +1501,7 @@ __global__ void uam_k_build_quads(const typename UamTexel<TF>::T* __restrict__ t
         }
         quad[o] = make_float4(value(i, j), value(i, j + 1), value(i + 1, j), value(i + 1, j + 1));
     }
+    if (PACK && neg) atomicOr(bad, 1u);
 }
 
 // one thread per 32-bit word (8 x 4 cells) of the occupancy bit-plane
@@ -1495,16 +1526,29 @@ __global__ void uam_k_build_occ_bits(const typename UamTexel<TF>::T* __restrict_
 }
 
 template <int TF, int LAYOUT>
-int uam_build_quads_t(uam_ctx* ctx, const UamRasterParams& rp, unsigned rs_q, size_t n_out, bool bits, unsigned blocks_x,
-                      unsigned n_words, cudaStream_t st) {
+int uam_build_quads_t(uam_ctx* ctx, const UamRasterParams& rp, unsigned rs_q, size_t n_out, unsigned blocks_x, unsigned n_words,
+                      cudaStream_t st) {
     typedef typename UamTexel<TF>::T T;
-    if (bits) {
+    // first choice: sign-packed quads (no second load per tap); the flag word sits in front of the bit-plane
+    unsigned* bad = (unsigned*)ctx->d_occ_bits;
+    UAM_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, st));
+    uam_k_build_quads<TF, LAYOUT, 1><<<ctx->sm_count * 8, 256, 0, st>>>((const T*)ctx->d_tex, rp.H, rp.W, rp.row_stride, rs_q, rp.w0, rp.w1, rp.w2,
+                                                                         n_out, (float4*)ctx->d_tex_comb, bad);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_build_quads");
+    unsigned h_bad = 0;
+    UAM_CUDA(ctx, cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
+    UAM_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->comb_packed = !h_bad && !ctx->no_sign_pack;
+    if (ctx->comb_packed) return UAM_OK;
+    // negative (or NaN) values somewhere: plain quads + occupancy bit-plane
+    if (!ctx->occ_bits_valid) {
         uam_k_build_occ_bits<TF, LAYOUT><<<(n_words + 255) / 256, 256, 0, st>>>((const T*)ctx->d_tex, rp.H, rp.W, rp.row_stride, blocks_x, n_words,
-                                                                               (unsigned*)ctx->d_occ_bits);
+                                                                               (unsigned*)ctx->d_occ_bits + 4);
         UAM_CHECK_LAUNCH(ctx, "uam_k_build_occ_bits");
+        ctx->occ_bits_valid = true;
     }
-    uam_k_build_quads<TF, LAYOUT><<<ctx->sm_count * 8, 256, 0, st>>>((const T*)ctx->d_tex, rp.H, rp.W, rp.row_stride, rs_q, rp.w0, rp.w1, rp.w2,
-                                                                      n_out, (float4*)ctx->d_tex_comb);
+    uam_k_build_quads<TF, LAYOUT, 0><<<ctx->sm_count * 8, 256, 0, st>>>((const T*)ctx->d_tex, rp.H, rp.W, rp.row_stride, rs_q, rp.w0, rp.w1, rp.w2,
+                                                                         n_out, (float4*)ctx->d_tex_comb, bad);
     UAM_CHECK_LAUNCH(ctx, "uam_k_build_quads");
     return UAM_OK;
 }
@@ -1517,24 +1561,23 @@ int uam_ensure_quads(uam_ctx* ctx, UamRasterParams* rp, cudaStream_t st) {
     rp->row_stride2 = rs_q;
     rp->occ_blocks_x = blocks_x;
     const bool same_w = tf == 2 || (ctx->comb_w[0] == rp->w0 && ctx->comb_w[1] == rp->w1 && ctx->comb_w[2] == rp->w2);
-    if (!(ctx->comb_valid && same_w && ctx->occ_bits_valid)) {
+    if (!(ctx->comb_valid && same_w)) {
         const size_t n_out = lay ? (size_t)tiles_x * tiles_y * 8 : (size_t)H * W;
         const unsigned n_words = blocks_x * blocks_y * 32u;
         UAM_CUDA(ctx, cudaDeviceSynchronize());      // kernels on other streams may still read the old quads
         UAM_TRY(uam_reserve(ctx, &ctx->d_tex_comb, &ctx->tex_comb_bytes, n_out * sizeof(float4)));
-        UAM_TRY(uam_reserve(ctx, &ctx->d_occ_bits, &ctx->occ_bits_bytes, (size_t)n_words * 4));
-        const bool bits = !ctx->occ_bits_valid;
-        if (tf == 2) UAM_TRY(lay ? (uam_build_quads_t<2, 1>(ctx, *rp, rs_q, n_out, bits, blocks_x, n_words, st))
-                                 : (uam_build_quads_t<2, 0>(ctx, *rp, rs_q, n_out, bits, blocks_x, n_words, st)));
-        else UAM_TRY(lay ? (uam_build_quads_t<4, 1>(ctx, *rp, rs_q, n_out, bits, blocks_x, n_words, st))
-                         : (uam_build_quads_t<4, 0>(ctx, *rp, rs_q, n_out, bits, blocks_x, n_words, st)));
+        UAM_TRY(uam_reserve(ctx, &ctx->d_occ_bits, &ctx->occ_bits_bytes, (size_t)(n_words + 4) * 4));
+        if (tf == 2) UAM_TRY(lay ? (uam_build_quads_t<2, 1>(ctx, *rp, rs_q, n_out, blocks_x, n_words, st))
+                                 : (uam_build_quads_t<2, 0>(ctx, *rp, rs_q, n_out, blocks_x, n_words, st)));
+        else UAM_TRY(lay ? (uam_build_quads_t<4, 1>(ctx, *rp, rs_q, n_out, blocks_x, n_words, st))
+                         : (uam_build_quads_t<4, 0>(ctx, *rp, rs_q, n_out, blocks_x, n_words, st)));
         UAM_CUDA(ctx, cudaStreamSynchronize(st));    // every pipeline stream may use them from now on
         ctx->comb_valid = true;
-        ctx->occ_bits_valid = true;
         ctx->comb_w[0] = rp->w0; ctx->comb_w[1] = rp->w1; ctx->comb_w[2] = rp->w2;
         ctx->comb_gen += 1;
     }
-    rp->occ_bits = (const unsigned*)ctx->d_occ_bits;
+    rp->occ_bits = (const unsigned*)ctx->d_occ_bits + 4;
+    rp->combined = ctx->comb_packed ? 2 : 1;
     return UAM_OK;
 }
 
@@ -1551,6 +1594,9 @@ int uam_raster_launch(uam_ctx* ctx, const double* d_z, int64_t B, int N, const U
         if (tf == 4) { rc.w0 = 1.0f; rc.w1 = 0.0f; rc.w2 = 0.0f; }     // the weights are inside the quads
         rc.row_stride = rp.row_stride2;
         const uint64_t ckey = (ctx->comb_gen << 1) | 1u;
+        if (rp.combined == 2)
+            return lay ? uam_raster_launch_t<8, 1>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot)
+                       : uam_raster_launch_t<8, 0>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot);
         return lay ? uam_raster_launch_t<1, 1>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot)
                    : uam_raster_launch_t<1, 0>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot);
     }
@@ -1564,7 +1610,6 @@ int uam_raster_launch(uam_ctx* ctx, const double* d_z, int64_t B, int N, const U
 int uam_raster_precompute(uam_ctx* ctx, UamRasterParams* rp, int64_t B, int N, cudaStream_t st) {
     if (rp->spc > 0.0 && rp->variant >= 2 && ctx->combine_layers && (unsigned long long)B * (N + 2) < 0xffffffffull) {
         UAM_TRY(uam_ensure_quads(ctx, rp, st));
-        rp->combined = 1;
     }
     return UAM_OK;
 }
