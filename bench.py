@@ -282,7 +282,10 @@ def run_ours(args):
     assert int(eng.get_stat('score_kernel_count')) == args.steps
     eng.set_option('time_kernels', 0)
     variant = int(os.environ.get('UAM_INT_VARIANT', '-1'))
-    kname = {0: 'uam_k_score_raster_int<4,L,0>', 1: 'uam_k_score_raster_int<4,L,1>'}.get(variant, 'uam_k_score_groups<4,1>')
+    combine = int(os.environ.get('UAM_COMBINE_LAYERS', '1'))
+    quad = {0: '4', 1: '8', 2: '1'}[combine]         # texel form sampled by the large-batch pipelines (8: sign-packed quads)
+    kname = {0: 'uam_k_score_raster_int<4,L,0>', 1: 'uam_k_score_raster_int<4,L,1>', 3: f'uam_k_score_tiles<{quad}>'}.get(
+        variant, f'uam_k_score_groups<{quad},1>')
 
     # ---- secondary: waypoint mode (the reference's sampling) on the same batch ---------------------------------
     for _ in range(3):
@@ -352,8 +355,10 @@ def run_ours(args):
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'traffic_source': traffic_src, 'kernel': kname, 'kernel_ms': k_ms,
                          'scoring_call_ms': call_ms, 'algorithmic_bytes_per_launch': abytes,
-                         'note': 'achieved = SURVEY 8(d) algorithmic bytes / event-timed kernel duration; the binned kernel '
-                                 'serves most of them from L2 (raster streamed ~once per batch), so achieved may exceed traffic',
+                         'note': 'achieved = SURVEY 8(d) algorithmic bytes (L x 16 + 1 B per sample) / event-timed kernel duration. '
+                                 'The kernel needs fewer physical bytes than that: the L layers are folded into one weighted '
+                                 'layer (linearity), a tap is one 16-B quad texel, and the binned order serves most taps from '
+                                 'L2 (raster streamed ~once per batch) -- so achieved exceeds both traffic and the HBM peak',
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'},
             'e2e': {'value': segs * world / (e2e_ms_max * 1e-3), 'unit': 'segment-evals/s',
                     'h2d_bytes_per_step': B * 2 * WP * 8, 'd2h_bytes_per_step': B * 5, 'ms_per_step': e2e_ms_max,
