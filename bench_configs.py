@@ -33,12 +33,59 @@ def ev_time(torch, fn, reps, warm=2):
     return a.elapsed_time(b) / reps
 
 
+def run_c5(args, torch, uam, dev):
+    eng = uam.Engine()
+    # ---------------- C5 ------------------------------------------------------------------------------------
+    # batched cost-to-go: 4096^2 grid x `bands` altitude bands of uint16 cost, Q queries per launch (a 1024-query job is
+    # 1024/Q launches per GPU x 8 GPUs; queries are independent, so it shards like the paths do)
+    n5 = 4096
+    g = torch.Generator(device=dev).manual_seed(5)
+    for bands, Q in ((1, args.c5_queries), (8, args.c5_queries_bands)):
+        if Q <= 0:
+            continue
+        shape = (n5, n5) if bands == 1 else (bands, n5, n5)
+        cost = torch.randint(1, 1000, shape, device=dev, generator=g, dtype=torch.int32).to(torch.uint16)
+        blk = (torch.rand(shape, device=dev, generator=g) < 0.1).to(torch.uint8)
+        if bands == 1:
+            src = torch.randint(0, n5, (Q, 2), device=dev, generator=g, dtype=torch.int32)
+            blk[src[:, 0].long(), src[:, 1].long()] = 0
+        else:
+            src = torch.cat([torch.randint(0, bands, (Q, 1), device=dev, generator=g, dtype=torch.int32),
+                             torch.randint(0, n5, (Q, 2), device=dev, generator=g, dtype=torch.int32)], dim=1)
+            blk[src[:, 0].long(), src[:, 1].long(), src[:, 2].long()] = 0
+        dt = 1e30
+        for rep in range(3):                                            # first call = warm-up (scratch allocation); best of the rest
+            if rep:
+                del dist, parent
+            l0 = eng.launch_count()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dist, parent = eng.grid_search(cost, src, blk)
+            torch.cuda.synchronize()
+            if rep:
+                dt = min(dt, time.perf_counter() - t0)
+        reach = float((dist < 2 ** 62).float().mean().item())
+        nodes = bands * n5 * n5
+        edges = nodes * (8 + (2 if bands > 1 else 0))
+        print(json.dumps({'config': f'C5: cost-to-go on a {n5}^2 8-connected grid x {bands} altitude band(s), {Q} queries per launch, 1 B200',
+                          'seconds': dt, 'queries_per_s': Q / dt, 'Mnode_per_s': Q * nodes / dt / 1e6,
+                          'min_edge_relaxations_per_s': Q * edges * reach / dt,
+                          'kernel_launches': eng.launch_count() - l0, 'reachable_fraction': reach,
+                          'tile_activations': eng.get_stat('grid_activations'), 'double_sweeps': eng.get_stat('grid_sweeps'),
+                          'rounds': eng.get_stat('grid_rounds'), 'tiles': Q * bands * (n5 // 32) ** 2,
+                          'note': 'exact distances + parents (bit-identical to Dijkstra); warp-per-tile Gauss-Seidel sweeps'}))
+        del dist, parent, cost, blk
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--c4-size', type=int, default=16384)
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--skip-c4', action='store_true')
     ap.add_argument('--c5-queries', type=int, default=16)
+    ap.add_argument('--c5-queries-bands', type=int, default=4)
+    ap.add_argument('--only', default='', help="'c5': run only the grid-search config")
     args = ap.parse_args()
     import torch
     import uam_path_planning_b200 as uam
@@ -49,6 +96,9 @@ def main():
         peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
     except Exception:
         pass
+    if args.only == 'c5':
+        run_c5(args, torch, uam, dev)
+        return
     rng = np.random.default_rng(20260101)
 
     # ---------------- C2 ------------------------------------------------------------------------------------
@@ -102,6 +152,7 @@ def main():
     del rm, Z
 
     if args.skip_c4:
+        run_c5(args, torch, uam, dev)
         return
     # ---------------- C4 ------------------------------------------------------------------------------------
     n = args.c4_size
@@ -150,27 +201,8 @@ def main():
     res['cpu_edt_scipy_Mcell_s'] = crop.size / (time.perf_counter() - t0) / 1e6
     print(json.dumps(res))
     del occ, mm
-
-    # ---------------- C5 ------------------------------------------------------------------------------------
-    # batched cost-to-go: 4096^2 grid, one altitude band's uint16 cost, Q queries per launch (a 1024-query job is
-    # 1024/Q launches per GPU x 8 GPUs; queries are independent, so it shards like the paths do)
-    n5, Q = 4096, args.c5_queries
-    g = torch.Generator(device=dev).manual_seed(5)
-    cost = torch.randint(1, 1000, (n5, n5), device=dev, generator=g, dtype=torch.int32).to(torch.uint16)
-    blk = (torch.rand((n5, n5), device=dev, generator=g) < 0.1).to(torch.uint8)
-    src = torch.randint(0, n5, (Q, 2), device=dev, generator=g, dtype=torch.int32)
-    blk[src[:, 0].long(), src[:, 1].long()] = 0
-    l0 = eng.launch_count()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    dist, parent = eng.grid_search(cost, src, blk)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    reach = float((dist < 2 ** 62).float().mean().item())
-    print(json.dumps({'config': f'C5: cost-to-go on a {n5}^2 8-connected grid, {Q} queries per launch, 1 B200',
-                      'seconds': dt, 'queries_per_s': Q / dt, 'Mcell_per_s': Q * n5 * n5 / dt / 1e6,
-                      'kernel_launches': eng.launch_count() - l0, 'reachable_fraction': reach,
-                      'note': 'exact distances + parents (bit-identical to Dijkstra); tile label-correcting relaxation'}))
+    del eng
+    run_c5(args, torch, uam, dev)
 
 
 if __name__ == '__main__':

@@ -91,6 +91,8 @@ enum {
     UAM_OPT_L2_FETCH_GRANULARITY = 3, /* cudaLimitMaxL2FetchGranularity for this device: 32, 64 or 128 bytes */
     UAM_OPT_TIME_KERNELS = 4,         /* 1: bracket the dominant raster-scoring kernel of every device-pointer call with
                                          CUDA events on the caller's stream (resets the statistics) */
+    UAM_OPT_GRID_DELTA = 6,           /* grid search: width of the distance window relaxed per round (0 = automatic: the cost
+                                         of crossing one 32-cell tile at the mean cell cost); ordering only, same results */
     UAM_OPT_COMBINE_LAYERS = 5        /* 1 (default): large-batch integral mode samples "quad texels": the layers are folded
                                          into ONE layer sum_l w_l * layer_l (the penalty is linear in the layers) and every
                                          cell stores its 2 x 2 bilinear footprint as one float4, so a tap is one 16-byte
@@ -100,7 +102,10 @@ enum {
 };
 /* statistics of UAM_OPT_TIME_KERNELS: mean device time (ms) of the dominant scoring kernel (uam_k_score_tiles / uam_k_score_groups /
  * uam_k_score_raster_int / uam_k_score_raster_wp) over the timed calls, and their number */
-enum { UAM_STAT_SCORE_KERNEL_MS_MEAN = 1, UAM_STAT_SCORE_KERNEL_COUNT = 2 };
+enum { UAM_STAT_SCORE_KERNEL_MS_MEAN = 1, UAM_STAT_SCORE_KERNEL_COUNT = 2,
+       /* counted work of the last uam_grid_search*: tile activations, double sweeps (one = 64 row steps of 32 cells, each
+          relaxing the 8 in-plane edges of its cells), relaxation rounds */
+       UAM_STAT_GRID_ACTIVATIONS = 3, UAM_STAT_GRID_SWEEPS = 4, UAM_STAT_GRID_ROUNDS = 5 };
 int uam_ctx_get_stat(uam_ctx* ctx, int stat, double* value);
 int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value);
 
@@ -225,15 +230,22 @@ int uam_edt(uam_ctx* ctx, const uint8_t* d_occ, int H, int W, double cell, int32
             float* d_clearance, void* stream);
 
 /* ---- grid search / cost-to-go (build-defined extension; the reference has none: SURVEY.md section 0) ----------
- * Q independent single-source cost-to-go sweeps on an 8-connected H x W grid with integer edge costs
- * step(u,v) * (cost[u] + cost[v]), step = 2 (axis) / 3 (diagonal); blocked cells (nullable) are impassable.
- * d_cost (H,W) uint16, d_sources (Q,2) int32 (row, col); outputs d_dist (Q,H,W) int64 (2^62 = unreachable) and
- * d_parent (Q,H,W) int32 (nullable): flat index of the best predecessor, ties to the lowest neighbour slot in the
- * order (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1); parent[source] = source, unreachable = -1.
- * Frontier-parallel tile relaxation; results are bit-identical to Dijkstra.  Synchronises `stream` internally
- * (the number of relaxation rounds is data dependent). */
+ * Q independent single-source cost-to-go sweeps on an 8-connected H x W grid, optionally stacked in `bands` altitude
+ * bands, with integer edge costs: in-plane step(u,v) * (cost[b,u] + cost[b,v]), step = 2 (axis) / 3 (diagonal); band
+ * change at a fixed cell 2 * (cost[b,v] + cost[b+-1,v]); blocked cells (nullable) are impassable.
+ * uam_grid_search:       d_cost (H,W) uint16, d_sources (Q,2) int32 (row, col); d_dist (Q,H,W) int64 (2^62 =
+ *                        unreachable); d_parent (Q,H,W) int32 (nullable): flat index of the best predecessor, ties to
+ *                        the lowest neighbour slot in the order (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1);
+ *                        parent[source] = source, unreachable = -1.
+ * uam_grid_search_bands: d_cost / d_blocked (bands,H,W), d_sources (Q,3) int32 (band, row, col); d_dist / d_parent
+ *                        (Q,bands,H,W); parent = flat index into (bands,H,W); two more predecessor slots after the eight
+ *                        in-plane ones: band below (8), band above (9).
+ * Frontier-parallel tile relaxation (warp per 32 x 32 tile, Gauss-Seidel row sweeps with (min,+) warp scans); results
+ * are bit-identical to Dijkstra.  Synchronises `stream` internally (the number of rounds is data dependent). */
 int uam_grid_search(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int H, int W,
                     const int32_t* d_sources, int Q, int64_t* d_dist, int32_t* d_parent, void* stream);
+int uam_grid_search_bands(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int bands, int H, int W,
+                          const int32_t* d_sources, int Q, int64_t* d_dist, int32_t* d_parent, void* stream);
 
 #ifdef __cplusplus
 }

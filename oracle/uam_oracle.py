@@ -514,61 +514,75 @@ def edt_sq(occ: np.ndarray) -> np.ndarray:
     return np.rint(d * d).astype(np.int64)
 
 
-def grid_search(cost: np.ndarray, start: Tuple[int, int], blocked: np.ndarray = None):
-    """Cost-to-go on an 8-connected grid with integer edge costs (Dijkstra, exact).
+def grid_search(cost: np.ndarray, start, blocked: np.ndarray = None):
+    """Cost-to-go on an 8-connected grid with integer edge costs (Dijkstra, exact), optionally with altitude bands.
 
-    Edge u->v costs step(u,v) * (cost[u] + cost[v]) with step = 2 for axis moves and 3 for diagonal
-    moves (integer 2:3 approximation of 1:sqrt2; all integer so results are order-independent).
-    dist[start] = 0; unreachable / blocked = 2**62.  parent[v] = flat index of the neighbour u that
-    minimises dist[u] + w(u,v), ties -> smallest neighbour slot in the fixed order
-    (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1); parent[start] = start; unreachable = -1.
+    cost (H,W) + start (row, col), or cost (bands,H,W) + start (band, row, col).
+    In-plane edge u->v costs step(u,v) * (cost[b,u] + cost[b,v]) with step = 2 for axis moves and 3 for diagonal
+    moves (integer 2:3 approximation of 1:sqrt2); a band change at a fixed cell costs 2 * (cost[b,v] + cost[b+-1,v]).
+    All integer, so results are order-independent.  dist[start] = 0; unreachable / blocked = 2**62.
+    parent[v] = flat index of the neighbour u that minimises dist[u] + w(u,v), ties -> smallest neighbour slot in the
+    fixed order (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1), band below, band above; parent[start] = start;
+    unreachable = -1.
     """
     import heapq
-    H, W = cost.shape
+    flat2d = cost.ndim == 2
+    if flat2d:
+        cost = cost[None]
+        blocked = None if blocked is None else blocked[None]
+        start = (0,) + tuple(start)
+    Bn, H, W = cost.shape
+    cells = H * W
     INF = 2 ** 62
-    dist = np.full(H * W, INF, dtype=np.int64)
-    c = cost.astype(np.int64).ravel()
-    blk = np.zeros(H * W, dtype=bool) if blocked is None else (blocked.ravel() != 0)
-    s = start[0] * W + start[1]
+    dist = np.full(Bn * cells, INF, dtype=np.int64)
+    c = cost.astype(np.int64).ravel().tolist()
+    blk = (np.zeros(Bn * cells, dtype=bool) if blocked is None else (blocked.ravel() != 0)).tolist()
+    s = start[0] * cells + start[1] * W + start[2]
     nb = [(-1, -1, 3), (-1, 0, 2), (-1, 1, 3), (0, -1, 2), (0, 1, 2), (1, -1, 3), (1, 0, 2), (1, 1, 3)]
+
+    def neighbours(v):
+        vb, vc = divmod(v, cells)
+        vi, vj = divmod(vc, W)
+        for di, dj, st in nb:
+            ui, uj = vi + di, vj + dj
+            if 0 <= ui < H and 0 <= uj < W:
+                yield vb * cells + ui * W + uj, st
+        for db in (-1, 1):
+            if 0 <= vb + db < Bn:
+                yield (vb + db) * cells + vc, 2
+
+    dl = dist.tolist()
     if not blk[s]:
-        dist[s] = 0
+        dl[s] = 0
         pq = [(0, s)]
         while pq:
             d, u = heapq.heappop(pq)
-            if d != dist[u]:
+            if d != dl[u]:
                 continue
-            ui, uj = divmod(u, W)
-            for di, dj, st in nb:
-                vi, vj = ui + di, uj + dj
-                if 0 <= vi < H and 0 <= vj < W:
-                    v = vi * W + vj
-                    if blk[v]:
-                        continue
-                    nd = d + st * (c[u] + c[v])
-                    if nd < dist[v]:
-                        dist[v] = nd
-                        heapq.heappush(pq, (nd, v))
-    parent = np.full(H * W, -1, dtype=np.int64)
-    for v in range(H * W):
-        if dist[v] >= INF:
+            for v, st in neighbours(u):
+                if blk[v]:
+                    continue
+                nd = d + st * (c[u] + c[v])
+                if nd < dl[v]:
+                    dl[v] = nd
+                    heapq.heappush(pq, (nd, v))
+    parent = [-1] * (Bn * cells)
+    for v in range(Bn * cells):
+        if dl[v] >= INF:
             continue
         if v == s:
             parent[v] = s
             continue
-        vi, vj = divmod(v, W)
         best, bp = INF, -1
-        for di, dj, st in nb:
-            ui, uj = vi + di, vj + dj
-            if 0 <= ui < H and 0 <= uj < W:
-                u = ui * W + uj
-                if dist[u] >= INF:
-                    continue
-                nd = dist[u] + st * (c[u] + c[v])
-                if nd < best:
-                    best, bp = nd, u
+        for u, st in neighbours(v):
+            if dl[u] >= INF:
+                continue
+            nd = dl[u] + st * (c[u] + c[v])
+            if nd < best:
+                best, bp = nd, u
         parent[v] = bp
-    return dist.reshape(H, W), parent.reshape(H, W)
+    shape = (H, W) if flat2d else (Bn, H, W)
+    return np.array(dl, dtype=np.int64).reshape(shape), np.array(parent, dtype=np.int64).reshape(shape)
 
 
 # --------------------------------------------------------------------------- #

@@ -500,6 +500,36 @@ def test_grid_search_exact(uam, torch, H, W, wall):
     assert np.array_equal(d2[0].cpu().numpy(), orc.grid_search(cost, tuple(srcs[0]), None)[0])
 
 
+@pytest.mark.parametrize('Bn,H,W', [(3, 40, 50), (8, 33, 65), (2, 5, 3)])
+def test_grid_search_bands_exact(uam, torch, Bn, H, W):
+    """Altitude bands: distances and parent indices over (bands, H, W) bit-identical to the oracle's Dijkstra; a wall
+    that is closed in the start band and open one band up forces paths to climb and come back down."""
+    rng = np.random.default_rng(Bn * 1000 + H)
+    cost = rng.integers(1, 3000, (Bn, H, W)).astype(np.uint16)
+    cost[rng.uniform(size=cost.shape) < 0.03] = 65535
+    blocked = (rng.uniform(size=cost.shape) < 0.12).astype(np.uint8)
+    blocked[0, H // 2, :] = 1                                          # band 0: closed wall
+    blocked[Bn - 1, H // 2, :] = 0                                     # top band: free corridor over it
+    free = np.argwhere(blocked == 0)
+    srcs = [free[rng.integers(len(free))].tolist() for _ in range(3)]
+    srcs[0][0] = 0
+    blocked[tuple(srcs[0])] = 0
+    dist, parent = uam.Engine().grid_search(torch.from_numpy(cost).cuda(), srcs, torch.from_numpy(blocked).cuda())
+    dist, parent = dist.cpu().numpy(), parent.cpu().numpy()
+    assert dist.shape == (3, Bn, H, W)
+    for q, s in enumerate(srcs):
+        d_ref, p_ref = orc.grid_search(cost, tuple(s), blocked)
+        assert np.array_equal(dist[q], d_ref), q
+        assert np.array_equal(parent[q].astype(np.int64), p_ref), q
+    if H > 10:
+        far = dist[0][0, H // 2 + 1:, :]
+        assert (far < 2 ** 62).any()                                   # the far side of the wall is reached (over the top)
+    # one band through the band entry point == the 2-D entry point
+    d1, p1 = uam.Engine().grid_search(torch.from_numpy(cost[:1].copy()).cuda(), [[0] + srcs[0][1:]], torch.from_numpy(blocked[:1].copy()).cuda())
+    d2, p2 = uam.Engine().grid_search(torch.from_numpy(cost[0].copy()).cuda(), [srcs[0][1:]], torch.from_numpy(blocked[0].copy()).cuda())
+    assert torch.equal(d1[0, 0], d2[0]) and torch.equal(p1[0, 0], p2[0])
+
+
 def test_grid_search_large_properties(uam, torch):
     """1024^2 grid, 4 queries: triangle property on every edge (dist is a fixed point of the relaxation) and
     following parents from random cells reaches the source with the recorded distance."""

@@ -61,6 +61,7 @@ SIGNATURES = {
     'uam_rasterize_layers': (_i, [_vp, _i, _i, _d, _d, _d, _d, _d, _vp, _vp]),
     'uam_edt': (_i, [_vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
     'uam_grid_search': (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    'uam_grid_search_bands': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

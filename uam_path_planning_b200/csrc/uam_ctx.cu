@@ -107,6 +107,7 @@ extern "C" int uam_ctx_create(int device, uam_ctx** out) {
     // tuning knobs from the environment (bench A/B runs); uam_ctx_set_option overrides
     if (const char* e = getenv("UAM_RASTER_LAYOUT")) ctx->raster_layout = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = std::min(3, std::max(-1, atoi(e)));
+    if (const char* e = getenv("UAM_GRID_DELTA")) ctx->grid_delta = std::max(0ll, atoll(e));
     if (const char* e = getenv("UAM_NO_SIGN_PACK")) ctx->no_sign_pack = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_COMBINE_LAYERS")) ctx->combine_layers = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_HOST_CHUNKS")) ctx->host_chunks = std::max(0, atoi(e));
@@ -130,6 +131,10 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             if (value != 32 && value != 64 && value != 128) return uam_fail(ctx, UAM_ERR_INVALID, "L2 fetch granularity must be 32, 64 or 128");
             UAM_CUDA(ctx, cudaSetDevice(ctx->device));
             UAM_CUDA(ctx, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+            return UAM_OK;
+        case UAM_OPT_GRID_DELTA:
+            if (value < 0) return uam_fail(ctx, UAM_ERR_INVALID, "grid delta must be >= 0");
+            ctx->grid_delta = (long long)value;
             return UAM_OK;
         case UAM_OPT_COMBINE_LAYERS:
             if (value < 0 || value > 2) return uam_fail(ctx, UAM_ERR_INVALID, "combine_layers must be 0, 1 or 2");
@@ -176,6 +181,9 @@ extern "C" int uam_ctx_get_stat(uam_ctx* ctx, int stat, double* value) {
         case UAM_STAT_SCORE_KERNEL_COUNT:
             *value = (double)ctx->time_count;
             return UAM_OK;
+        case UAM_STAT_GRID_ACTIVATIONS: *value = ctx->grid_activations; return UAM_OK;
+        case UAM_STAT_GRID_SWEEPS: *value = ctx->grid_sweeps; return UAM_OK;
+        case UAM_STAT_GRID_ROUNDS: *value = ctx->grid_rounds; return UAM_OK;
         default:
             return uam_fail(ctx, UAM_ERR_INVALID, "unknown stat %d", stat);
     }

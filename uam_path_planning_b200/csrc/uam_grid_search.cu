@@ -1,15 +1,30 @@
-// Batched cost-to-go sweeps on an 8-connected grid (build-defined extension: the reference has no grid search;
-// BASELINE.json config 5).  Q independent single-source problems share every launch.
+// Batched cost-to-go sweeps on an 8-connected grid with optional altitude bands (build-defined extension: the
+// reference has no grid search; BASELINE.json config 5).  Q independent single-source problems share every launch.
 //
-// Edge u -> v costs step(u,v) * (cost[u] + cost[v]) with step = 2 (axis) / 3 (diagonal): all integer, so shortest
-// distances are unique numbers and a label-correcting relaxation in ANY order converges to the same bits as
-// Dijkstra.  Frontier-parallel relaxation, organised by 32 x 32 tiles:
-//   round:  uam_k_grid_compact  collects the active (query, tile) pairs and clears their flags;
-//           uam_k_grid_relax    one CTA per active pair loads the tile + 1-cell halo of dist/cost into shared memory,
-//                               relaxes it to its local fixed point, writes the interior back and, if any cell of its
-//                               boundary ring dropped, flags the 8 neighbouring tiles for the next round.
+// Graph: node = (band, row, col).  In-plane edge u -> v costs step(u,v) * (cost[b,u] + cost[b,v]) with step = 2
+// (axis) / 3 (diagonal); a band change at a fixed cell costs 2 * (cost[b,v] + cost[b',v]), b' = b +- 1.  All integer,
+// so shortest distances are unique numbers and a label-correcting relaxation in ANY order converges to the same
+// bits as Dijkstra.  Frontier-parallel relaxation, organised by 32 x 32 tiles of one band:
+// Every (query, band, tile) triple has a KEY: the smallest distance that arrived at its border since it was last
+// relaxed (2^62 = nothing pending).  Tiles are relaxed in rough distance order (delta-stepping at tile granularity):
+//   round:  uam_k_grid_minkey   per query, the smallest pending key;
+//           uam_k_grid_select   collects the triples whose key is within `delta` of their query's minimum and
+//                               clears their keys (the others wait: relaxing them now would be redone when the
+//                               shorter fronts arrive -- measured 32 activations per tile without the ordering);
+//           uam_k_grid_relax    one WARP per active triple: loads the tile + 1-cell halo of dist / cost into its slice
+//                               of shared memory, folds in the candidates from the bands above / below (those do
+//                               not change during the activation), then alternates a top-down and a bottom-up
+//                               Gauss-Seidel sweep until nothing moves.  A sweep step handles one row: the three
+//                               neighbours in the previous row, then the exact closure along the row in both
+//                               directions as two (min,+) warp scans -- with S the prefix sum of the horizontal
+//                               edge weights, min_k<=j (d_k + S_j - S_k) = S_j + prefixmin(d - S) and
+//                               min_k>=j (d_k + S_k - S_j) = suffixmin(d + S) - S_j.  Information crosses the
+//                               whole tile in one sweep; no block barriers.  Cells that dropped are written back
+//                               and the smallest dropped value on each side goes into the key of the neighbour
+//                               tile behind that side (atomicMin), the smallest overall into the keys of the same
+//                               tile in the bands above / below.
 //   rounds repeat until no tile is active (the active count is read back every few rounds).
-//   uam_k_grid_parent then picks each cell's predecessor: argmin over the 8 neighbours in a fixed slot order with a
+//   uam_k_grid_parent then picks each cell's predecessor: argmin over the neighbours in a fixed slot order with a
 //   strict '<' -- deterministic, identical to the oracle's post-pass.
 #include <algorithm>
 
@@ -20,144 +35,325 @@ namespace {
 #define GT 32                          // tile side
 #define GH (GT + 2)                    // with halo
 #define UAM_GRID_INF (1ll << 62)
+#define UAM_GRID_WARPS 8
+#define UAM_GRID_WARP_SMEM (GH * GH * 8 + GH * GH * 4)
 
 __device__ __constant__ int c_di[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
 __device__ __constant__ int c_dj[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
 __device__ __constant__ int c_st[8] = {3, 2, 3, 2, 2, 3, 2, 3};
 
+struct UamGridGeo {
+    int H, W, bands, Q;
+    int tiles_x, tiles_y;
+    int src_stride;          // 2: sources are (row, col) in band 0; 3: (band, row, col)
+};
+
 __global__ void __launch_bounds__(256)
-uam_k_grid_init(long long* __restrict__ dist, const uint8_t* __restrict__ blocked, const int* __restrict__ sources, int Q,
-                int H, int W, int tiles_x, int tiles_per_q, uint8_t* __restrict__ flags) {
-    const size_t cells = (size_t)H * W;
-    const size_t total = cells * Q;
+uam_k_grid_init(long long* __restrict__ dist, size_t total) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) dist[t] = UAM_GRID_INF;
-    // all threads of all CTAs must have finished the fill before the sources are written: done by a second launch
+}
+
+__device__ __forceinline__ bool uam_grid_source(const int* __restrict__ sources, const UamGridGeo g, int q, int& b, int& i, int& j) {
+    if (g.src_stride == 3) { b = sources[3 * q]; i = sources[3 * q + 1]; j = sources[3 * q + 2]; }
+    else { b = 0; i = sources[2 * q]; j = sources[2 * q + 1]; }
+    return b >= 0 && b < g.bands && i >= 0 && i < g.H && j >= 0 && j < g.W;
 }
 
 __global__ void uam_k_grid_seed(long long* __restrict__ dist, const uint8_t* __restrict__ blocked,
-                                const int* __restrict__ sources, int Q, int H, int W, int tiles_x, int tiles_per_q,
-                                uint8_t* __restrict__ flags) {
+                                const int* __restrict__ sources, UamGridGeo g, unsigned long long* __restrict__ keys) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
-    const int si = sources[2 * q], sj = sources[2 * q + 1];
-    if (si < 0 || si >= H || sj < 0 || sj >= W) return;
-    const size_t c = (size_t)si * W + sj;
+    if (q >= g.Q) return;
+    int sb, si, sj;
+    if (!uam_grid_source(sources, g, q, sb, si, sj)) return;
+    const size_t cells = (size_t)g.H * g.W;
+    const size_t c = (size_t)sb * cells + (size_t)si * g.W + sj;
     if (blocked && blocked[c]) return;
-    dist[(size_t)q * H * W + c] = 0;
-    flags[(size_t)q * tiles_per_q + (size_t)(si / GT) * tiles_x + sj / GT] = 1;
+    dist[(size_t)q * g.bands * cells + c] = 0;
+    const size_t tiles = (size_t)g.tiles_x * g.tiles_y;
+    keys[((size_t)q * g.bands + sb) * tiles + (size_t)(si / GT) * g.tiles_x + sj / GT] = 0ull;
+}
+
+// per query: smallest pending key (grid = Q x parts CTAs)
+__global__ void __launch_bounds__(256)
+uam_k_grid_minkey(const unsigned long long* __restrict__ keys, size_t per_q, int parts, unsigned long long* __restrict__ minkey) {
+    const int q = blockIdx.x / parts, part = blockIdx.x - q * parts;
+    const unsigned long long* kq = keys + (size_t)q * per_q;
+    unsigned long long m = (unsigned long long)UAM_GRID_INF;
+    for (size_t t = (size_t)part * blockDim.x + threadIdx.x; t < per_q; t += (size_t)parts * blockDim.x) {
+        const unsigned long long k = kq[t];
+        m = k < m ? k : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t < m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m < (unsigned long long)UAM_GRID_INF) atomicMin(&minkey[q], m);
 }
 
 __global__ void __launch_bounds__(256)
-uam_k_grid_compact(uint8_t* __restrict__ flags, size_t n, unsigned* __restrict__ list, unsigned* __restrict__ count) {
+uam_k_grid_select(unsigned long long* __restrict__ keys, size_t n, size_t per_q, const unsigned long long* __restrict__ minkey,
+                  unsigned long long delta, unsigned* __restrict__ list, unsigned* __restrict__ count) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
-        if (flags[t]) {
-            flags[t] = 0;
+        const unsigned long long k = keys[t];
+        if (k < (unsigned long long)UAM_GRID_INF && k <= minkey[t / per_q] + delta) {
+            keys[t] = (unsigned long long)UAM_GRID_INF;
             list[atomicAdd(count, 1u)] = (unsigned)t;
         }
     }
 }
 
-__global__ void __launch_bounds__(256)
-uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ blocked, int H, int W, int tiles_x,
-                 int tiles_y, const unsigned* __restrict__ list, const unsigned* __restrict__ count,
-                 long long* __restrict__ dist, uint8_t* __restrict__ flags_next) {
-    __shared__ long long sd[GH][GH + 1];
-    __shared__ int sc[GH][GH + 1];           // cell cost, -1 = blocked / outside
-    const int tiles_per_q = tiles_x * tiles_y;
+// One sweep step: row li of the tile takes candidates from row ln (li - 1 or li + 1) and closes along the row.
+// Lane l owns column l + 1.  Edge e_l joins columns l and l + 1 (l = 0..32); it is dead when either end is blocked.
+// S_l = real weight of e_0..e_l (32-bit prefix sum, dead edges count 0); a candidate from column k to column j is
+// d_k + |S_j - S_k| and is valid iff no dead edge lies between them -- checked on the ballot of dead edges, so the two
+// 64-bit min-scans (from the left, from the right) need no sentinel weights.  Returns true (per lane) if this
+// lane's cell dropped.
+__device__ __forceinline__ bool uam_grid_row_step(long long* __restrict__ D, const int* __restrict__ C, int li, int ln, int lane) {
+    const int lj = lane + 1;
+    const int cv = C[li * GH + lj];
+    const int cl = C[li * GH + lane];                 // column to the left (lane 0: halo column 0)
+    const long long d0 = D[li * GH + lj];
+    // horizontal edges
+    const bool dead_l = cv < 0 || cl < 0;             // e_lane
+    const unsigned dead = __ballot_sync(0xffffffffu, dead_l);
+    int S = dead_l ? 0 : 2 * (cv + cl);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, S, o);
+        if (lane >= o) S += t;
+    }
+    const int c32 = C[li * GH + GT], c33 = C[li * GH + GT + 1];
+    const bool dead32 = c32 < 0 || c33 < 0;
+    const int S33 = __shfl_sync(0xffffffffu, S, 31) + (dead32 ? 0 : 2 * (c32 + c33));
+    // candidates from the previous row
+    long long d = d0;
+    if (cv >= 0) {
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj) {
+            const int cn = C[ln * GH + lj + dj];
+            if (cn >= 0) {
+                const long long cand = D[ln * GH + lj + dj] + (long long)((dj ? 3 : 2) * (cn + cv));
+                d = cand < d ? cand : d;
+            }
+        }
+    }
+    // closure along the row: m = min over valid k <= j of (d_k - S_k), gm = min over valid k >= j of (d_k + S_k)
+    long long m = d - (long long)S, gm = d + (long long)S;
+    const unsigned below = (2u << lane) - 1u;         // bits 0..lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long tm = __shfl_up_sync(0xffffffffu, m, o);
+        const long long tg = __shfl_down_sync(0xffffffffu, gm, o);
+        // edges between lane - o and lane: e_{lane-o+1}..e_lane; between lane and lane + o: e_{lane+1}..e_{lane+o}
+        const unsigned span_l = below & ~((lane >= o) ? ((2u << (lane - o)) - 1u) : 0u);
+        const unsigned span_r = (lane + o < 32) ? (((2u << (lane + o)) - 1u) & ~below) : 0xffffffffu;
+        if (lane >= o && !(dead & span_l)) m = tm < m ? tm : m;
+        if (lane + o < 32 && !(dead & span_r)) gm = tg < gm ? tg : gm;
+    }
+    // halo columns: column 0 (S = 0) reaches lane j iff e_0..e_j alive; column 33 iff e_{j+1}..e_32 alive
+    if (!(dead & below)) {
+        const long long x0 = D[li * GH];
+        m = x0 < m ? x0 : m;
+    }
+    if (!(dead & ~below) && !dead32) {
+        const long long x33 = D[li * GH + GT + 1] + (long long)S33;
+        gm = x33 < gm ? x33 : gm;
+    }
+    const long long from_left = m + (long long)S, from_right = gm - (long long)S;
+    long long nd = from_left < from_right ? from_left : from_right;
+    nd = d < nd ? d : nd;
+    const bool drop = cv >= 0 && nd < d0;
+    if (drop) D[li * GH + lj] = nd;
+    return drop;
+}
+
+__global__ void __launch_bounds__(UAM_GRID_WARPS * 32)
+uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ blocked, UamGridGeo g,
+                 const unsigned* __restrict__ list, const unsigned* __restrict__ count, long long* __restrict__ dist,
+                 unsigned long long* __restrict__ keys, unsigned long long* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char uam_grid_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long* D = reinterpret_cast<long long*>(uam_grid_smem + (size_t)warp * UAM_GRID_WARP_SMEM);
+    int* C = reinterpret_cast<int*>(D + GH * GH);           // cell cost, -1 = blocked / outside
+    const int H = g.H, W = g.W;
+    const size_t cells = (size_t)H * W;
+    const unsigned tiles = (unsigned)(g.tiles_x * g.tiles_y);
     const unsigned n = *count;
-    for (unsigned w = blockIdx.x; w < n; w += gridDim.x) {
+    for (unsigned w = blockIdx.x * UAM_GRID_WARPS + warp; w < n; w += gridDim.x * UAM_GRID_WARPS) {
         const unsigned ent = list[w];
-        const int q = ent / tiles_per_q;
-        const int tile = ent - q * tiles_per_q;
-        const int ti = tile / tiles_x, tj = tile - ti * tiles_x;
+        const unsigned qb = ent / tiles, tile = ent - qb * tiles;
+        const int q = (int)(qb / (unsigned)g.bands), b = (int)(qb - (unsigned)q * g.bands);
+        const int ti = (int)(tile / (unsigned)g.tiles_x), tj = (int)(tile - (unsigned)ti * g.tiles_x);
         const int i0 = ti * GT - 1, j0 = tj * GT - 1;
-        long long* dq = dist + (size_t)q * H * W;
-        __syncthreads();
-        for (int t = threadIdx.x; t < GH * GH; t += blockDim.x) {
-            const int li = t / GH, lj = t - li * GH;
-            const int i = i0 + li, j = j0 + lj;
-            long long d = UAM_GRID_INF;
-            int c = -1;
-            if (i >= 0 && i < H && j >= 0 && j < W) {
-                const size_t g = (size_t)i * W + j;
-                if (!(blocked && blocked[g])) {
-                    c = cost[g];
-                    d = dq[g];
+        long long* dq = dist + ((size_t)q * g.bands + b) * cells;
+        const uint16_t* cb = cost + (size_t)b * cells;
+        const uint8_t* bb = blocked ? blocked + (size_t)b * cells : nullptr;
+        __syncwarp();
+        // ---- load tile + halo (34 rows x 34 columns: lanes cover columns 0..31, lanes 0..1 also 32..33); the loads of
+        //      several rows are issued together (the activation's latency is what bounds a round) ----------------------
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int lj = lane + 32 * pass;
+            const int j = j0 + lj;
+            const bool col_ok = lj < GH && j >= 0 && j < W;
+            for (int r0 = 0; r0 < GH; r0 += 6) {
+                long long dv[6];
+                int cvv[6];
+                uint8_t bl[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int i = i0 + r0 + k;
+                    const bool ok = col_ok && r0 + k < GH && i >= 0 && i < H;
+                    const size_t gi = ok ? (size_t)i * W + j : 0;
+                    dv[k] = ok ? dq[gi] : UAM_GRID_INF;
+                    cvv[k] = ok ? (int)cb[gi] : -1;
+                    bl[k] = (ok && bb) ? bb[gi] : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    if (lj < GH && r0 + k < GH) {
+                        D[(r0 + k) * GH + lj] = bl[k] ? UAM_GRID_INF : dv[k];
+                        C[(r0 + k) * GH + lj] = bl[k] ? -1 : cvv[k];
+                    }
                 }
             }
-            sd[li][lj] = d;
-            sc[li][lj] = c;
         }
-        __syncthreads();
-        // each thread owns 4 cells of the interior: rows (threadIdx.x >> 5) + 8k, column threadIdx.x & 31
-        const int lj = (threadIdx.x & 31) + 1;
-        const int lr = threadIdx.x >> 5;
-        long long before[4];
+        __syncwarp();
+        // ---- candidates from the bands below / above (fixed during this activation) ----------------------------------
+        for (int db = -1; db <= 1; db += 2) {
+            const int b2 = b + db;
+            if (b2 < 0 || b2 >= g.bands) continue;
+            const long long* d2 = dist + ((size_t)q * g.bands + b2) * cells;
+            const uint16_t* c2 = cost + (size_t)b2 * cells;
+            const uint8_t* bl2 = blocked ? blocked + (size_t)b2 * cells : nullptr;
+            const int j = j0 + lane + 1;
+            for (int r0 = 1; r0 <= GT; r0 += 8) {
+                long long dv[8];
+                int cvv[8];
+                uint8_t bl[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) before[k] = sd[lr + 8 * k + 1][lj];
-        bool any_change = false;
-        int changed;
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + r0 + k;
+                    const bool ok = i < H && j < W;
+                    const size_t gi = ok ? (size_t)i * W + j : 0;
+                    dv[k] = ok ? d2[gi] : UAM_GRID_INF;
+                    cvv[k] = ok ? (int)c2[gi] : 0;
+                    bl[k] = (ok && bl2) ? bl2[gi] : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int li = r0 + k;
+                    const int cv = C[li * GH + lane + 1];
+                    if (cv >= 0 && !bl[k] && dv[k] < UAM_GRID_INF) {
+                        const long long cand = dv[k] + (long long)(2 * (cvv[k] + cv));
+                        if (cand < D[li * GH + lane + 1]) D[li * GH + lane + 1] = cand;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- Gauss-Seidel sweeps to the local fixed point ---------------------------------------------------------------
+        bool changed;
+        unsigned n_sweeps = 0;
         do {
-            changed = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int li = lr + 8 * k + 1;
-                const int cv = sc[li][lj];
-                if (cv < 0) continue;
-                long long best = sd[li][lj];
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const int ni = li + c_di[s], nj = lj + c_dj[s];
-                    const int cn = sc[ni][nj];
-                    if (cn < 0) continue;
-                    const long long cand = sd[ni][nj] + (long long)(c_st[s] * (cn + cv));
-                    best = cand < best ? cand : best;
-                }
-                if (best < sd[li][lj]) {
-                    sd[li][lj] = best;
-                    changed = 1;
-                }
+            bool ch = false;
+            ++n_sweeps;
+            for (int li = 1; li <= GT; ++li) {
+                ch |= uam_grid_row_step(D, C, li, li - 1, lane);
+                __syncwarp();
             }
-            any_change = any_change || changed;
-            changed = __syncthreads_or(changed);
+            for (int li = GT; li >= 1; --li) {
+                ch |= uam_grid_row_step(D, C, li, li + 1, lane);
+                __syncwarp();
+            }
+            changed = __any_sync(0xffffffffu, ch);
         } while (changed);
-        // write back + did the boundary ring change?
-        int ring = 0;
+        // ---- write back the cells that dropped; smallest dropped value per side ------------------------------------------
+        long long m_all = UAM_GRID_INF, m_top = UAM_GRID_INF, m_bot = UAM_GRID_INF, m_side = UAM_GRID_INF;   // m_side: this lane's column
+        long long c_tl = UAM_GRID_INF, c_tr = UAM_GRID_INF, c_bl = UAM_GRID_INF, c_br = UAM_GRID_INF;
+        {
+            const int lj = lane + 1;
+            const int j = j0 + lj;
+            for (int r0 = 1; r0 <= GT; r0 += 8) {
+                long long old[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int li = lr + 8 * k + 1;
-            const long long now = sd[li][lj];
-            if (now < before[k]) {
-                const int i = i0 + li, j = j0 + lj;
-                dq[(size_t)i * W + j] = now;
-                if (li == 1 || li == GT || lj == 1 || lj == GT) ring = 1;
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + r0 + k;
+                    old[k] = (i < H && j < W) ? dq[(size_t)i * W + j] : 0;       // 0: nothing is below it
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int li = r0 + k;
+                    const long long now = D[li * GH + lj];
+                    if (now < old[k]) {
+                        dq[(size_t)(i0 + li) * W + j] = now;
+                        m_all = now < m_all ? now : m_all;
+                        m_side = now < m_side ? now : m_side;
+                        if (li == 1) m_top = now;
+                        if (li == GT) m_bot = now;
+                    }
+                }
             }
         }
-        ring = __syncthreads_or(ring);
-        if (ring && threadIdx.x < 8) {
-            const int ni = ti + c_di[threadIdx.x], nj = tj + c_dj[threadIdx.x];
-            if (ni >= 0 && ni < tiles_y && nj >= 0 && nj < tiles_x)
-                flags_next[(size_t)q * tiles_per_q + (size_t)ni * tiles_x + nj] = 1;
+        // corners (single cells), left / right columns (lanes 0 / 31), top / bottom rows and overall (warp minima)
+        c_tl = __shfl_sync(0xffffffffu, m_top, 0);  c_tr = __shfl_sync(0xffffffffu, m_top, 31);
+        c_bl = __shfl_sync(0xffffffffu, m_bot, 0);  c_br = __shfl_sync(0xffffffffu, m_bot, 31);
+        const long long m_left = __shfl_sync(0xffffffffu, m_side, 0), m_right = __shfl_sync(0xffffffffu, m_side, 31);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            long long t = __shfl_xor_sync(0xffffffffu, m_all, o);
+            m_all = t < m_all ? t : m_all;
+            t = __shfl_xor_sync(0xffffffffu, m_top, o);
+            m_top = t < m_top ? t : m_top;
+            t = __shfl_xor_sync(0xffffffffu, m_bot, o);
+            m_bot = t < m_bot ? t : m_bot;
+        }
+        if (lane == 0) {                      // counted work: tile activations, double sweeps
+            atomicAdd(&stats[0], 1ull);
+            atomicAdd(&stats[1], (unsigned long long)n_sweeps);
+        }
+        if (m_all < UAM_GRID_INF) {
+            unsigned long long* kq = keys + (size_t)q * g.bands * tiles;
+            if (lane < 8) {
+                // slot order of c_di / c_dj: TL, T, TR, L, R, BL, B, BR
+                const long long v = lane == 0 ? c_tl : lane == 1 ? m_top : lane == 2 ? c_tr : lane == 3 ? m_left : lane == 4 ? m_right
+                                  : lane == 5 ? c_bl : lane == 6 ? m_bot : c_br;
+                const int ni = ti + c_di[lane], nj = tj + c_dj[lane];
+                if (v < UAM_GRID_INF && ni >= 0 && ni < g.tiles_y && nj >= 0 && nj < g.tiles_x)
+                    atomicMin(&kq[(size_t)b * tiles + (size_t)ni * g.tiles_x + nj], (unsigned long long)v);
+            } else if (lane == 8 && b > 0) {
+                atomicMin(&kq[(size_t)(b - 1) * tiles + tile], (unsigned long long)m_all);
+            } else if (lane == 9 && b + 1 < g.bands) {
+                atomicMin(&kq[(size_t)(b + 1) * tiles + tile], (unsigned long long)m_all);
+            }
         }
     }
 }
 
+// predecessor slots: 0..7 in-plane (c_di / c_dj), 8 = band below, 9 = band above
 __global__ void __launch_bounds__(256)
-uam_k_grid_parent(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ blocked, int H, int W, int Q,
-                  const long long* __restrict__ dist, const int* __restrict__ sources, int* __restrict__ parent) {
+uam_k_grid_parent(const uint16_t* __restrict__ cost, UamGridGeo g, const long long* __restrict__ dist,
+                  const int* __restrict__ sources, int* __restrict__ parent) {
+    const int H = g.H, W = g.W;
     const size_t cells = (size_t)H * W;
-    const size_t total = cells * Q;
+    const size_t nodes = cells * g.bands;
+    const size_t total = nodes * g.Q;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const int q = (int)(t / cells);
-        const size_t v = t - (size_t)q * cells;
-        const long long* dq = dist + (size_t)q * cells;
+        const int q = (int)(t / nodes);
+        const size_t v = t - (size_t)q * nodes;
+        const long long* dq = dist + (size_t)q * nodes;
         int p = -1;
         if (dq[v] < UAM_GRID_INF) {
-            const int vi = (int)(v / W), vj = (int)(v - (size_t)vi * W);
-            if (vi == sources[2 * q] && vj == sources[2 * q + 1]) {
+            const int vb = (int)(v / cells);
+            const size_t vc = v - (size_t)vb * cells;
+            const int vi = (int)(vc / W), vj = (int)(vc - (size_t)vi * W);
+            int sb, si, sj;
+            uam_grid_source(sources, g, q, sb, si, sj);
+            if (vb == sb && vi == si && vj == sj) {
                 p = (int)v;
             } else {
                 const int cv = cost[v];
@@ -166,10 +362,20 @@ uam_k_grid_parent(const uint16_t* __restrict__ cost, const uint8_t* __restrict__
                 for (int s = 0; s < 8; ++s) {
                     const int ui = vi + c_di[s], uj = vj + c_dj[s];
                     if (ui < 0 || ui >= H || uj < 0 || uj >= W) continue;
-                    const size_t u = (size_t)ui * W + uj;
+                    const size_t u = (size_t)vb * cells + (size_t)ui * W + uj;
                     const long long du = dq[u];
                     if (du >= UAM_GRID_INF) continue;
                     const long long nd = du + (long long)(c_st[s] * ((int)cost[u] + cv));
+                    if (nd < best) { best = nd; p = (int)u; }
+                }
+#pragma unroll
+                for (int db = -1; db <= 1; db += 2) {
+                    const int ub = vb + db;
+                    if (ub < 0 || ub >= g.bands) continue;
+                    const size_t u = (size_t)ub * cells + vc;
+                    const long long du = dq[u];
+                    if (du >= UAM_GRID_INF) continue;
+                    const long long nd = du + (long long)(2 * ((int)cost[u] + cv));
                     if (nd < best) { best = nd; p = (int)u; }
                 }
             }
@@ -178,55 +384,112 @@ uam_k_grid_parent(const uint16_t* __restrict__ cost, const uint8_t* __restrict__
     }
 }
 
-}  // namespace
+__global__ void __launch_bounds__(256)
+uam_k_grid_cost_sum(const uint16_t* __restrict__ cost, size_t n, unsigned long long* __restrict__ sum) {
+    unsigned long long acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) acc += cost[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sum, acc);
+}
 
-extern "C" int uam_grid_search(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int H, int W,
-                               const int32_t* d_sources, int Q, int64_t* d_dist, int32_t* d_parent, void* stream) {
+int uam_grid_mean_cost(uam_ctx* ctx, const uint16_t* d_cost, size_t n, cudaStream_t st, unsigned long long* mean) {
+    unsigned long long* d_sum = (unsigned long long*)ctx->d_scratch;        // scratch: the keys are initialised after this
+    UAM_CUDA(ctx, cudaMemsetAsync(d_sum, 0, 8, st));
+    uam_k_grid_cost_sum<<<ctx->sm_count * 8, 256, 0, st>>>(d_cost, n, d_sum);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_grid_cost_sum");
+    unsigned long long h = 0;
+    UAM_CUDA(ctx, cudaMemcpyAsync(&h, d_sum, 8, cudaMemcpyDeviceToHost, st));
+    UAM_CUDA(ctx, cudaStreamSynchronize(st));
+    *mean = std::max<unsigned long long>(1ull, h / (unsigned long long)n);
+    return UAM_OK;
+}
+
+int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int bands, int H, int W,
+                         const int32_t* d_sources, int src_stride, int Q, int64_t* d_dist, int32_t* d_parent, void* stream) {
     if (!ctx) return UAM_ERR_INVALID;
-    if (H < 1 || W < 1 || Q < 0 || !d_cost || !d_dist || (Q > 0 && !d_sources))
+    if (H < 1 || W < 1 || bands < 1 || Q < 0 || !d_cost || !d_dist || (Q > 0 && !d_sources))
         return uam_fail(ctx, UAM_ERR_INVALID, "bad argument to uam_grid_search");
-    if ((size_t)H * W >= 0x7fffffffull) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "grid has 2^31 or more cells");
+    if ((size_t)H * W * bands >= 0x7fffffffull) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "grid has 2^31 or more nodes");
     if (Q == 0) return UAM_OK;
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = uam_pick_stream(ctx, stream);
-    const int tiles_x = (W + GT - 1) / GT, tiles_y = (H + GT - 1) / GT;
-    const size_t tiles_per_q = (size_t)tiles_x * tiles_y;
-    const size_t n_flags = tiles_per_q * Q;
-    if (n_flags >= 0xffffffffull) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "too many (query, tile) pairs");
-    // scratch: flags A | flags B | list (u32) | count (u32 x 2)
-    const size_t fbytes = (n_flags + 255) & ~(size_t)255;
-    UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, 2 * fbytes + n_flags * 4 + 256));
-    uint8_t* flags_a = (uint8_t*)ctx->d_scratch;
-    uint8_t* flags_b = flags_a + fbytes;
-    unsigned* list = (unsigned*)(flags_b + fbytes);
+    UamGridGeo g;
+    g.H = H; g.W = W; g.bands = bands; g.Q = Q; g.src_stride = src_stride;
+    g.tiles_x = (W + GT - 1) / GT;
+    g.tiles_y = (H + GT - 1) / GT;
+    const size_t tiles = (size_t)g.tiles_x * g.tiles_y;
+    const size_t n_flags = tiles * bands * Q;
+    if (n_flags >= 0xffffffffull) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "too many (query, band, tile) triples");
+    // scratch: keys (u64) | minkey (u64 x Q) | stats (u64 x 2) | list (u32) | count (u32 x 2)
+    UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, n_flags * 12 + (size_t)Q * 8 + 256));
+    unsigned long long* keys = (unsigned long long*)ctx->d_scratch;
+    // delta = cost of crossing about two tiles at the grid's mean cell cost (ordering only: any value gives the same result)
+    unsigned long long delta = ctx->grid_delta > 0 ? (unsigned long long)ctx->grid_delta : 0ull;
+    if (!delta) {
+        UAM_TRY(uam_grid_mean_cost(ctx, d_cost, (size_t)H * W * bands, st, &delta));
+        delta = delta * 8ull * GT;     // measured on C5 (Q = 16): 4x / 8x / 16x -> 640 / 448 / 336 rounds, 1.69 / 1.77 / 2.06 M activations
+    }
+    unsigned long long* minkey = keys + n_flags;
+    unsigned long long* stats = minkey + Q;
+    unsigned* list = (unsigned*)(stats + 2);
     unsigned* count = list + n_flags;
-    UAM_CUDA(ctx, cudaMemsetAsync(flags_a, 0, 2 * fbytes, st));
+    UAM_CUDA(ctx, cudaMemsetAsync(stats, 0, 16, st));
     const int grid_fill = ctx->sm_count * 16;
-    uam_k_grid_init<<<grid_fill, 256, 0, st>>>((long long*)d_dist, d_blocked, d_sources, Q, H, W, tiles_x, (int)tiles_per_q, flags_a);
+    uam_k_grid_init<<<grid_fill, 256, 0, st>>>((long long*)d_dist, (size_t)H * W * bands * Q);
     UAM_CHECK_LAUNCH(ctx, "uam_k_grid_init");
-    uam_k_grid_seed<<<(Q + 127) / 128, 128, 0, st>>>((long long*)d_dist, d_blocked, d_sources, Q, H, W, tiles_x, (int)tiles_per_q, flags_a);
+    uam_k_grid_init<<<grid_fill, 256, 0, st>>>((long long*)keys, n_flags);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_grid_init");
+    uam_k_grid_seed<<<(Q + 127) / 128, 128, 0, st>>>((long long*)d_dist, d_blocked, d_sources, g, keys);
     UAM_CHECK_LAUNCH(ctx, "uam_k_grid_seed");
-    uint8_t* cur = flags_a;
-    uint8_t* nxt = flags_b;
-    const int grid_relax = ctx->sm_count * 8;
-    const long long max_rounds = 64ll * ((long long)tiles_x + tiles_y) * GT + 1024;     // far above any real front count
+    const size_t per_q = tiles * bands;
+    const int parts = (int)std::max<size_t>(1, std::min<size_t>(64, per_q / 2048));
+    const size_t smem = (size_t)UAM_GRID_WARP_SMEM * UAM_GRID_WARPS;
+    UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_grid_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid_relax = ctx->sm_count * 2;
+    const long long max_rounds = 1ll << 40;      // the loop ends when no key is pending
     unsigned h_count = 1;
+    long long rounds_done = 0;
     for (long long round = 0; round < max_rounds && h_count; ++round) {
+        rounds_done = round + 1;
         UAM_CUDA(ctx, cudaMemsetAsync(count, 0, 4, st));
-        uam_k_grid_compact<<<ctx->sm_count * 4, 256, 0, st>>>(cur, n_flags, list, count);
-        UAM_CHECK_LAUNCH(ctx, "uam_k_grid_compact");
-        uam_k_grid_relax<<<grid_relax, 256, 0, st>>>(d_cost, d_blocked, H, W, tiles_x, tiles_y, list, count, (long long*)d_dist, nxt);
+        UAM_CUDA(ctx, cudaMemsetAsync(minkey, 0xff, (size_t)Q * 8, st));
+        uam_k_grid_minkey<<<Q * parts, 256, 0, st>>>(keys, per_q, parts, minkey);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_grid_minkey");
+        uam_k_grid_select<<<ctx->sm_count * 4, 256, 0, st>>>(keys, n_flags, per_q, minkey, delta, list, count);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_grid_select");
+        uam_k_grid_relax<<<grid_relax, UAM_GRID_WARPS * 32, smem, st>>>(d_cost, d_blocked, g, list, count, (long long*)d_dist, keys, stats);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_relax");
-        std::swap(cur, nxt);
         if ((round & 7) == 7) {     // termination check every 8 rounds: rounds with an empty list are no-ops
             UAM_CUDA(ctx, cudaMemcpyAsync(&h_count, count, 4, cudaMemcpyDeviceToHost, st));
             UAM_CUDA(ctx, cudaStreamSynchronize(st));
         }
     }
     if (h_count) return uam_fail(ctx, UAM_ERR_STATE, "grid search did not converge");
+    {
+        unsigned long long h_stats[2] = {0, 0};
+        UAM_CUDA(ctx, cudaMemcpyAsync(h_stats, stats, 16, cudaMemcpyDeviceToHost, st));
+        UAM_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->grid_activations = (double)h_stats[0];
+        ctx->grid_sweeps = (double)h_stats[1];
+        ctx->grid_rounds = (double)rounds_done;
+    }
     if (d_parent) {
-        uam_k_grid_parent<<<grid_fill, 256, 0, st>>>(d_cost, d_blocked, H, W, Q, (const long long*)d_dist, d_sources, d_parent);
+        uam_k_grid_parent<<<grid_fill, 256, 0, st>>>(d_cost, g, (const long long*)d_dist, d_sources, d_parent);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_parent");
     }
     return UAM_OK;
+}
+
+}  // namespace
+
+extern "C" int uam_grid_search(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int H, int W,
+                               const int32_t* d_sources, int Q, int64_t* d_dist, int32_t* d_parent, void* stream) {
+    return uam_grid_search_impl(ctx, d_cost, d_blocked, 1, H, W, d_sources, 2, Q, d_dist, d_parent, stream);
+}
+
+extern "C" int uam_grid_search_bands(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int bands, int H, int W,
+                                     const int32_t* d_sources, int Q, int64_t* d_dist, int32_t* d_parent, void* stream) {
+    return uam_grid_search_impl(ctx, d_cost, d_blocked, bands, H, W, d_sources, 3, Q, d_dist, d_parent, stream);
 }

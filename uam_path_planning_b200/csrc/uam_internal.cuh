@@ -96,6 +96,8 @@ struct uam_ctx {
     cudaEvent_t time_ev[2] = {};
     double time_sum_ms = 0.0;
     uint64_t time_count = 0;
+    long long grid_delta = 0;           // UAM_OPT_GRID_DELTA (0 = automatic)
+    double grid_activations = 0, grid_sweeps = 0, grid_rounds = 0;   // counted work of the last uam_grid_search*
     void* d_bin_scratch[UAM_HOST_PIPE_DEPTH + 1] = {};   // binned raster scorer: [0] caller stream, [1..] pipeline stages
     size_t bin_scratch_bytes[UAM_HOST_PIPE_DEPTH + 1] = {};
     // tile-staged raster scorer (variant 3): tile-major copy of the texels (built on first use) + piece scratch

@@ -79,8 +79,8 @@ class Engine:
         self._check(self._lib.uam_sync(self._h))
 
     OPTIONS = {'raster_layout': 1, 'integral_variant': 2, 'l2_fetch_granularity': 3, 'time_kernels': 4,
-               'combine_layers': 5}
-    STATS = {'score_kernel_ms_mean': 1, 'score_kernel_count': 2}
+               'combine_layers': 5, 'grid_delta': 6}
+    STATS = {'score_kernel_ms_mean': 1, 'score_kernel_count': 2, 'grid_activations': 3, 'grid_sweeps': 4, 'grid_rounds': 5}
 
     def get_stat(self, name: str) -> float:
         v = C.c_double()
@@ -334,20 +334,30 @@ class Engine:
 
     def grid_search(self, cost, sources, blocked=None, want_parent: bool = True):
         """Q cost-to-go sweeps on an 8-connected grid (build-defined extension, include/uam_b200.h).
-        cost (H,W) uint16 CUDA tensor, sources (Q,2) int32 (row, col), blocked (H,W) uint8 or None ->
-        (dist (Q,H,W) int64 with 2**62 = unreachable, parent (Q,H,W) int32 | None)."""
+        2-D: cost (H,W) uint16 CUDA tensor, sources (Q,2) int32 (row, col), blocked (H,W) uint8 or None ->
+        (dist (Q,H,W) int64 with 2**62 = unreachable, parent (Q,H,W) int32 | None).
+        Altitude bands: cost (bands,H,W), sources (Q,3) (band, row, col), blocked (bands,H,W) ->
+        dist / parent (Q,bands,H,W), parent = flat index into (bands,H,W)."""
         import torch
-        assert _is_tensor(cost) and cost.dtype == torch.uint16 and cost.dim() == 2
-        sources = torch.as_tensor(sources, dtype=torch.int32, device=cost.device).reshape(-1, 2).contiguous()
+        assert _is_tensor(cost) and cost.dtype == torch.uint16 and cost.dim() in (2, 3)
+        k = cost.dim()
+        sources = torch.as_tensor(sources, dtype=torch.int32, device=cost.device).reshape(-1, k).contiguous()
+        if blocked is not None:
+            assert blocked.shape == cost.shape and blocked.dtype == torch.uint8
         st = self._tensor_args(cost, sources, blocked)
-        H, W = cost.shape
         Q = sources.shape[0]
-        dist = torch.empty((Q, H, W), dtype=torch.int64, device=cost.device)
-        parent = torch.empty((Q, H, W), dtype=torch.int32, device=cost.device) if want_parent else None
-        self._check(self._lib.uam_grid_search(
-            self._h, C.c_void_p(cost.data_ptr()), C.c_void_p(blocked.data_ptr()) if blocked is not None else None, H, W,
-            C.c_void_p(sources.data_ptr()), Q, C.c_void_p(dist.data_ptr()),
-            C.c_void_p(parent.data_ptr()) if parent is not None else None, st))
+        dist = torch.empty((Q,) + tuple(cost.shape), dtype=torch.int64, device=cost.device)
+        parent = torch.empty((Q,) + tuple(cost.shape), dtype=torch.int32, device=cost.device) if want_parent else None
+        pb = C.c_void_p(blocked.data_ptr()) if blocked is not None else None
+        pp = C.c_void_p(parent.data_ptr()) if parent is not None else None
+        if k == 2:
+            H, W = cost.shape
+            self._check(self._lib.uam_grid_search(self._h, C.c_void_p(cost.data_ptr()), pb, H, W,
+                                                  C.c_void_p(sources.data_ptr()), Q, C.c_void_p(dist.data_ptr()), pp, st))
+        else:
+            Bn, H, W = cost.shape
+            self._check(self._lib.uam_grid_search_bands(self._h, C.c_void_p(cost.data_ptr()), pb, Bn, H, W,
+                                                        C.c_void_p(sources.data_ptr()), Q, C.c_void_p(dist.data_ptr()), pp, st))
         return dist, parent
 
     # ---- single-shape queries (QuadraticObstacle.contains / penalty_function, Function.__call__) -----------------
