@@ -16,8 +16,8 @@ Timing: device-resident inputs, CUDA events on the launching stream, barrier + s
 ranks.  The raster (1 GiB of texels) and the path batch (1 KiB per path) are both larger than L2, so no explicit L2
 flush is needed between steps.  `e2e` times the same step through the host-buffer entry point of the C-ABI
 (uam_score_paths_raster_host: pinned numpy in, numpy out, H2D/D2H inside).  `cpu_baseline` / `--impl reference`
-time the float64 numpy oracle (oracle/uam_oracle.py -- the CPU restatement of the reference's arithmetic; the
-reference itself has no raster path and cannot be installed: it needs casadi/opengen/cargo) on a bounded sample.
+time the oracle (oracle/ -- the CPU restatement of the path; the reference itself has no raster path and cannot be
+installed: it needs casadi/opengen/cargo): its C/OpenMP form on every host core, and its numpy form on one core.
 """
 import argparse
 import json
@@ -139,38 +139,30 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the float64 numpy oracle on a bounded sample
+# CPU arm: the oracle (oracle/ -- CPU restatement of the path; the reference itself is Python + CasADi/OpEn and cannot
+# be installed here) on a bounded sample.  Two forms: the C / OpenMP restatement on every host core (the baseline that
+# is reported) and the float64 numpy restatement on one core (what a direct port of the reference's Python gives).
 # ---------------------------------------------------------------------------------------------------------------
-_CPU = {}
+def cpu_c_rate(layers, occ, geo, Z, threads=0):
+    """segments/s of oracle/uam_oracle_c (C, OpenMP over paths) -> (rate, seconds, threads, (cost, collide, nsamples))."""
+    from oracle import uam_oracle_c as occ_c
+    th = threads or (os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    res = occ_c.score_paths_raster(layers, occ, geo, Z, WEIGHTS, SPC, True, None, threads=th)
+    dt = time.perf_counter() - t0
+    return Z.shape[0] * (WP - 1) / dt, dt, th, res
 
 
-def _cpu_worker(args):
-    lo, hi = args
+def cpu_numpy_rate(layers, occ, geo, Z):
     from oracle import uam_oracle as orc
     t0 = time.perf_counter()
-    orc.score_paths_raster(_CPU['layers'], _CPU['occ'], _CPU['geo'], _CPU['Z'][lo:hi], WEIGHTS, SPC, True, None)
-    return time.perf_counter() - t0
-
-
-def cpu_oracle_rate(layers, occ, geo, Z, procs):
-    """segments/s of the oracle over the paths Z split across `procs` forked workers (wall clock)."""
-    import multiprocessing as mp
-    _CPU.update(layers=layers, occ=occ, geo=geo, Z=Z)
-    B = Z.shape[0]
-    if procs <= 1:
-        dt = _cpu_worker((0, B))
-    else:
-        cuts = np.linspace(0, B, procs + 1).astype(int)
-        ctx = mp.get_context('fork')
-        t0 = time.perf_counter()
-        with ctx.Pool(procs) as pool:
-            pool.map(_cpu_worker, [(int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a])
-        dt = time.perf_counter() - t0
-    return B * (WP - 1) / dt, dt
+    res = orc.score_paths_raster(layers, occ, geo, Z, WEIGHTS, SPC, True, None)
+    dt = time.perf_counter() - t0
+    return Z.shape[0] * (WP - 1) / dt, dt, res
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path on the host cores.  Rank 0 only."""
+    """--impl reference: the CPU implementation of the path on all host cores.  Rank 0 only."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -180,11 +172,11 @@ def run_reference(args):
     torch.manual_seed(0)
     layers, occ, geo = make_raster(torch, 'cpu', n)
     layers, occ = layers.numpy(), occ.numpy()
-    per_step = args.cpu_paths * cores
+    per_step = args.cpu_paths
     Z = make_paths(torch, 'cpu', per_step * (args.steps + args.warmup), 2, n).numpy()
     times = []
     for s in range(args.warmup + args.steps):
-        rate, dt = cpu_oracle_rate(layers, occ, geo, Z[s * per_step:(s + 1) * per_step], cores)
+        rate, dt, th, _ = cpu_c_rate(layers, occ, geo, Z[s * per_step:(s + 1) * per_step], cores)
         if s >= args.warmup:
             times.append(dt)
     T = float(np.sum(times))
@@ -194,8 +186,8 @@ def run_reference(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': workload_config(args, per_step),
             'cpu_baseline': {'value': value, 'unit': 'segment-evals/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'{per_step} paths/step ({args.cpu_paths} per worker x {cores} forked workers), '
-                                       'float64 numpy oracle (oracle/uam_oracle.py), integral mode'},
+                             'sample': f'{per_step} paths/step of the same workload, oracle/uam_oracle_c.c (C restatement of the '
+                                       f'float64 oracle, OpenMP over paths, {cores} threads), integral mode'},
             'e2e': {'value': value, 'unit': 'segment-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -371,18 +363,22 @@ def run_ours(args):
             'best': {'cost': best_cost, 'index': best_idx},
         }
         if world == 1 and not args.no_cpu:
-            cores = 1
-            nb = args.cpu_sample
             Lh, Oh = layers.cpu().numpy(), occ.cpu().numpy()
+            nb = min(B, args.cpu_sample)
             Zs = Z[:nb].cpu().numpy()
-            rate, dt = cpu_oracle_rate(Lh, Oh, geo, Zs, cores)
-            c_ref, col_ref, _ = __import__('oracle.uam_oracle', fromlist=['x']).score_paths_raster(
-                Lh, Oh, geo, Zs[:64], WEIGHTS, SPC, True, None)
-            err = float(np.max(np.abs(cost[:64].cpu().numpy() - c_ref) / np.abs(c_ref)))
-            line['cpu_baseline'] = {'value': rate, 'unit': 'segment-evals/s', 'cores': cores, 'kind': 'port',
-                                    'sample': f'first {nb} paths of the same batch, float64 numpy oracle, integral mode, {dt:.1f} s',
-                                    'max_rel_err_gpu_vs_oracle_64_paths': err,
-                                    'collide_equal': bool(np.array_equal(col[:64].cpu().numpy().astype(bool), col_ref))}
+            rate, dt, th, (c_ref, col_ref, ns_ref) = cpu_c_rate(Lh, Oh, geo, Zs)
+            c_gpu = cost[:nb].cpu().numpy().astype(np.float64)
+            err = float(np.max(np.abs(c_gpu - c_ref) / np.abs(c_ref)))
+            n1 = min(nb, args.numpy_sample)
+            rate1, dt1, (c_np, col_np, _) = cpu_numpy_rate(Lh, Oh, geo, Zs[:n1])
+            line['cpu_baseline'] = {
+                'value': rate, 'unit': 'segment-evals/s', 'cores': th, 'kind': 'port',
+                'sample': f'first {nb} paths of the same batch, oracle/uam_oracle_c.c (C restatement of the float64 oracle, '
+                          f'OpenMP over paths, {th} threads), integral mode, {dt:.1f} s',
+                'max_rel_err_gpu_vs_oracle': err, 'paths_compared': nb,
+                'collide_equal': bool(np.array_equal(col[:nb].cpu().numpy().astype(bool), col_ref)),
+                'numpy_1core': {'value': rate1, 'paths': n1, 'seconds': dt1,
+                                'max_rel_diff_c_vs_numpy': float(np.max(np.abs(c_np - c_ref[:n1]) / np.abs(c_np)))}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -396,8 +392,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--raster', type=int, default=RASTER)
     ap.add_argument('--paths', type=int, default=125000, help='candidate paths per GPU per step (C3: 1M over 8 GPUs)')
-    ap.add_argument('--cpu-paths', type=int, default=384, help='paths per CPU worker per step for --impl reference')
-    ap.add_argument('--cpu-sample', type=int, default=4096, help='paths of the batch the 1-core cpu_baseline leg scores')
+    ap.add_argument('--cpu-paths', type=int, default=31250, help='paths per step for --impl reference (C/OpenMP oracle, all cores)')
+    ap.add_argument('--cpu-sample', type=int, default=125000, help='paths of the batch the cpu_baseline leg scores and compares (C/OpenMP oracle)')
+    ap.add_argument('--numpy-sample', type=int, default=1024, help='paths the 1-core numpy oracle scores')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

@@ -6,6 +6,7 @@ zero pattern of g; analytic costs (fp64 on the device) within 1e-12 relative of 
 (fp32 texel arithmetic and penalty sum) within 1e-5 relative of the float64 oracle.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -470,6 +471,38 @@ def test_tile_staged_hot_tiles_and_variants_agree(uam, torch, L):
     assert np.array_equal(res[3, 2][0], res[3, 1][0]) and np.array_equal(res[2, 2][0], res[2, 1][0])   # both quad forms: same bits
 
 
+@pytest.mark.parametrize('config', ['C2', 'C3'])
+def test_raster_scorer_full_size_vs_c_oracle(uam, torch, config):
+    """BASELINE.json's own sizes, every path compared: C2 = 10k polylines x 64 waypoints on a 4096^2 risk+obstacle
+    raster (L = 1); C3 = a 20 000-path shard on the 8192^2 3-layer raster of bench.py.  The checker is the C / OpenMP
+    form of the oracle (bit-compatible with the numpy oracle, tests/test_oracle_golden.py): costs within 1e-5
+    relative (fp32 accumulation), collision flags and sample counts identical."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from oracle import uam_oracle_c as occ
+    dev = 'cuda'
+    if config == 'C2':
+        n, B, w = 4096, 10000, [5000.0]
+        layers, occu, geo = bench.make_raster(torch, dev, n, seed=20260101)
+        layers, occu = layers[2:3].contiguous(), occu
+    else:
+        n, B, w = 8192, 20000, bench.WEIGHTS
+        layers, occu, geo = bench.make_raster(torch, dev, n)
+    Z = bench.make_paths(torch, dev, B, 7, n)
+    rm = uam.RasterMap.from_arrays(layers, geo, occu)
+    Lh, Oh, Zh = layers.cpu().numpy(), occu.cpu().numpy(), Z.cpu().numpy()
+    for spc in (1.0, 0.0):
+        c, k, ns = rm.score_paths(Z, w, spc, True, None, want_nsamples=True)
+        c_ref, k_ref, ns_ref = occ.score_paths_raster(Lh, Oh, geo, Zh, w, spc, True, None)
+        np.testing.assert_allclose(c.cpu().numpy(), c_ref, rtol=RTOL_RASTER)
+        assert np.array_equal(k.cpu().numpy().astype(bool), k_ref)
+        assert np.array_equal(ns.cpu().numpy(), ns_ref)
+        ch, kh = rm.score_paths(Zh, w, spc, True, None)                      # host-buffer entry point: same bits
+        assert np.array_equal(ch, c.cpu().numpy()) and np.array_equal(kh, k.cpu().numpy())
+    assert k_ref.any() and not k_ref.all()
+
+
 # ------------------------------------------------------------------------------------------------------------
 # grid search / cost-to-go (build-defined extension) vs the oracle's Dijkstra
 # ------------------------------------------------------------------------------------------------------------
@@ -701,3 +734,20 @@ def test_cost_gradient(uam, torch, fixture_spec, golden):
     assert np.all(prob.get_cost(Z2) < cost)
     with pytest.raises(uam.UamError):
         build_product_problem(f, N, options={'penalty_smooth': False}).get_cost_gradient(Z)
+
+
+def test_grid_search_4096_vs_c_oracle(uam, torch):
+    """BASELINE config 5 grid size (4096^2), two queries, against the C oracle's heap Dijkstra: distances and parent
+    indices bit-identical; and a 512^2 x 8-band stack the same way."""
+    from oracle import uam_oracle_c as occ
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(55)
+    for shape, srcs in (((4096, 4096), [[17, 4000], [2048, 2048]]), ((8, 512, 512), [[0, 5, 5], [7, 300, 400]])):
+        cost = torch.randint(1, 1000, shape, device=dev, generator=g, dtype=torch.int32).to(torch.uint16)
+        blk = (torch.rand(shape, device=dev, generator=g) < 0.1).to(torch.uint8)
+        for sv in srcs:
+            blk[tuple(sv)] = 0
+        dist, parent = uam.Engine().grid_search(cost, srcs, blk)
+        d_ref, p_ref = occ.grid_search(cost.cpu().numpy(), srcs, blk.cpu().numpy())
+        assert np.array_equal(dist.cpu().numpy(), d_ref)
+        assert np.array_equal(parent.cpu().numpy(), p_ref)

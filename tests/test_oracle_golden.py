@@ -192,3 +192,56 @@ def test_oracle_gradient_matches_finite_differences(omap, fixture_spec, golden):
             fd = (orc.get_cost(omap, Zp, N, f['weights'], e, opts) - orc.get_cost(omap, Zm, N, f['weights'], e, opts)) / (2 * h)
             np.testing.assert_allclose(G[:, col], fd, rtol=2e-5, atol=2e-4)
     assert np.nanmax(np.abs(G)) > 1.0 and np.isnan(G[:, :2]).all() and not np.isnan(G[:, 2:]).any()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the C / OpenMP form of the oracle (oracle/uam_oracle_c.c) against the numpy oracle it restates
+# ------------------------------------------------------------------------------------------------------------
+def _c_oracle():
+    from oracle import uam_oracle_c as occ
+    occ.build()
+    return occ
+
+
+@pytest.mark.parametrize('L', [1, 3])
+def test_c_oracle_raster_matches_numpy_oracle(L):
+    occ = _c_oracle()
+    rng = np.random.default_rng(40 + L)
+    H, W, geo = 90, 140, (3.0, 0.25, 40.0, -0.2)
+    lay = rng.uniform(0, 2, (L, H, W)).astype(np.float32)
+    oc = (rng.uniform(size=(H, W)) < 0.04).astype(np.uint8)
+    B, Wp = 60, 9
+    org, ext = np.array([3.0, 40.0]), np.array([0.25 * W, -0.2 * H])
+    s = org + rng.uniform(-0.15, 1.15, (B, 1, 2)) * ext          # some paths start / end outside the raster
+    g = org + rng.uniform(-0.15, 1.15, (B, 1, 2)) * ext
+    t = np.linspace(0, 1, Wp).reshape(1, Wp, 1)
+    Z = (s + t * (g - s) + rng.normal(0, 0.4, (B, Wp, 2))).reshape(B, 2 * Wp)
+    Z[5, 4:] = np.tile(Z[5, 2:4], Wp - 2)                        # zero-length segments
+    w = [200.0, 15000.0, 27000.0][:L]
+    for spc in (0.0, 1.0, 0.37, 2.5):
+        for ls in (True, False):
+            for xs in (None, [4.0, 39.0]):
+                a = orc.score_paths_raster(lay, oc, geo, Z, w, spc, ls, xs)
+                for threads in (1, 3):
+                    b = occ.score_paths_raster(lay, oc, geo, Z, w, spc, ls, xs, threads=threads)
+                    np.testing.assert_allclose(b[0], a[0], rtol=1e-13, atol=0)
+                    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_c_oracle_grid_search_matches_numpy_oracle():
+    occ = _c_oracle()
+    rng = np.random.default_rng(8)
+    cost = rng.integers(1, 3000, (3, 17, 23)).astype(np.uint16)
+    cost[rng.uniform(size=cost.shape) < 0.05] = 65535
+    blk = (rng.uniform(size=cost.shape) < 0.15).astype(np.uint8)
+    srcs = [[0, 3, 4], [2, 10, 10], [1, 16, 22], np.argwhere(blk == 1)[0].tolist()]
+    d, p = occ.grid_search(cost, srcs, blk)
+    for q, sv in enumerate(srcs):
+        dr, pr = orc.grid_search(cost, tuple(sv), blk)
+        assert np.array_equal(d[q], dr) and np.array_equal(p[q].astype(np.int64), pr)
+    assert (d[3] == 2 ** 62).all() and (p[3] == -1).all()
+    d2, p2 = occ.grid_search(cost[1], [[5, 6]], blk[1])
+    dr, pr = orc.grid_search(cost[1], (5, 6), blk[1])
+    assert np.array_equal(d2[0], dr) and np.array_equal(p2[0].astype(np.int64), pr)
+    d3, _ = occ.grid_search(cost[1], [[5, 6]], None, want_parent=False)
+    assert np.array_equal(d3[0], orc.grid_search(cost[1], (5, 6), None)[0])
