@@ -67,7 +67,22 @@ def run_c5(args, torch, uam, dev):
         reach = float((dist < 2 ** 62).float().mean().item())
         nodes = bands * n5 * n5
         edges = nodes * (8 + (2 if bands > 1 else 0))
+        nodes = bands * n5 * n5
+        cpu = None
+        if not args.no_cpu:
+            # CPU baseline: heap Dijkstra of oracle/uam_oracle_c.c, one query per thread, and a full-size
+            # parity check of those queries
+            from oracle import uam_oracle_c as occ
+            cores = os.cpu_count() or 1
+            nq = min(Q, cores if bands == 1 else max(1, cores // 8))
+            t0 = time.perf_counter()
+            d_ref, _ = occ.grid_search(cost.cpu().numpy(), src[:nq].cpu().numpy(), blk.cpu().numpy(), want_parent=False, threads=cores)
+            dtc = time.perf_counter() - t0
+            cpu = {'queries': nq, 'threads': min(nq, cores), 'seconds': dtc, 'queries_per_s': nq / dtc,
+                   'Mnode_per_s': nq * nodes / dtc / 1e6, 'dist_equal_gpu': bool(np.array_equal(dist[:nq].cpu().numpy(), d_ref))}
+            del d_ref
         print(json.dumps({'config': f'C5: cost-to-go on a {n5}^2 8-connected grid x {bands} altitude band(s), {Q} queries per launch, 1 B200',
+                          'cpu_baseline': cpu,
                           'seconds': dt, 'queries_per_s': Q / dt, 'Mnode_per_s': Q * nodes / dt / 1e6,
                           'min_edge_relaxations_per_s': Q * edges * reach / dt,
                           'kernel_launches': eng.launch_count() - l0, 'reachable_fraction': reach,
@@ -85,6 +100,7 @@ def main():
     ap.add_argument('--skip-c4', action='store_true')
     ap.add_argument('--c5-queries', type=int, default=16)
     ap.add_argument('--c5-queries-bands', type=int, default=4)
+    ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--only', default='', help="'c5': run only the grid-search config")
     args = ap.parse_args()
     import torch
