@@ -1413,10 +1413,10 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
         UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
     }
     if constexpr (UamIsQuad<TF>::v) {
-        if (!(rp.spc > 0.0 && rp.variant >= 2)) return uam_fail(ctx, UAM_ERR_STATE, "quad texels are only sampled by the binned pipelines");
+        if (rp.spc > 0.0 && rp.variant < 2) return uam_fail(ctx, UAM_ERR_STATE, "quad texels are not sampled by the warp-per-path integral kernels");
     }
     if (rp.spc == 0.0) {
-      if constexpr (!UamIsQuad<TF>::v) {
+      {
         const long long ctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
         uam_k_score_raster_wp<TF, LAYOUT><<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
         UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_wp");
@@ -1608,7 +1608,9 @@ int uam_raster_launch(uam_ctx* ctx, const double* d_z, int64_t B, int N, const U
 
 // Once per API call, before any chunk is launched: make the quad texels if this call will use them.
 int uam_raster_precompute(uam_ctx* ctx, UamRasterParams* rp, int64_t B, int N, cudaStream_t st) {
-    if (rp->spc > 0.0 && rp->variant >= 2 && ctx->combine_layers && (unsigned long long)B * (N + 2) < 0xffffffffull) {
+    // large batches: integral mode through the binned pipelines, waypoint mode when the batch is worth the one-off build
+    const bool big_wp = rp->spc == 0.0 && (unsigned long long)B * (N + 2) >= 262144ull;
+    if (((rp->spc > 0.0 && rp->variant >= 2) || big_wp) && ctx->combine_layers && (unsigned long long)B * (N + 2) < 0xffffffffull) {
         UAM_TRY(uam_ensure_quads(ctx, rp, st));
     }
     return UAM_OK;
