@@ -219,6 +219,7 @@ def run_ours(args):
     dev = f'cuda:{local}'
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # keep NCCL's banner off stdout: stdout is the ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device(dev))
 
     n, B = args.raster, args.paths
