@@ -219,3 +219,32 @@ def test_no_cpu_fallback():
     m = uam.RegionMap()
     with pytest.raises(uam.UamError):
         m.collides([0.0, 0.0])
+
+
+def test_map_file_writer_round_trip_and_reference_file(tmp_path):
+    """save_polygons writes the reference's format (data_manager.py:56-72); the reader takes it back bit for bit.  The
+    text below is the head of the reference's data/processed/populated_area.txt."""
+    ref_head = ('vertices = [polygon([28.836, -32.708], [29.607, -36.124], [32.53, -35.464], [31.759, -32.048]),\n'
+                'polygon([29.185, -27.687], [29.35, -29.043], [32.001, -28.719], [31.835, -27.362])\n]')
+    metres = [[(28836, -32708), (29607, -36124), (32530, -35464), (31759, -32048), (28836, -32708)],
+              [(29185, -27687), (29350, -29043), (32001, -28719), (31835, -27362)]]
+    f = tmp_path / 'populated_area.txt'
+    uam.save_polygons(metres, str(f))
+    assert f.read_text() == ref_head
+    shapes = uam.get_var_from_file(str(f), 'vertices')
+    assert len(shapes) == 2 and all(s.kind == 'polygon' and len(s.inequalities) == 4 for s in shapes)
+    uam.save_polygons([], str(f))
+    assert uam.get_var_from_file(str(f)) == []
+
+
+def test_result_export_conventions():
+    """main.py:103-116: km -> m (x1000), start / goal points prepended / appended, EPSG:2443 axis order."""
+    x = [30.5, -20.25, 28.0, -5.0]
+    pts = uam.result_points(x)
+    assert pts.shape == (4, 2)
+    assert pts[0].tolist() == [35590.685, -27711.422] and pts[-1].tolist() == [26478.673, 9564.082]
+    assert pts[1].tolist() == [30500.0, -20250.0] and pts[2].tolist() == [28000.0, -5000.0]
+    assert uam.result_wkt(x, [1, 2], [3, 4]) == 'LINESTRING (1.0 2.0, 30500.0 -20250.0, 28000.0 -5000.0, 3.0 4.0)'
+    assert uam.result_wkt([], [1, 2], [3, 4], kind='points') == 'MULTIPOINT ((1.0 2.0), (3.0 4.0))'
+    with pytest.raises(ValueError):
+        uam.result_points([1.0, 2.0, 3.0])

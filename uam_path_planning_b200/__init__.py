@@ -9,11 +9,11 @@ from .shapes import QuadraticObstacle, Inequality, polygon, ball, square
 from .region_map import Map, RegionMap
 from .problem import Problem
 from .solver import Solver
-from .mapio import get_var_from_file, parse_shapes
+from .mapio import get_var_from_file, parse_shapes, save_polygons, result_points, result_wkt
 from .engine import Engine, default_engine
 from .raster import RasterMap, load_dem_mask
 from . import distributed
 
 __all__ = ['UamError', 'QuadraticObstacle', 'Inequality', 'polygon', 'ball', 'square', 'Map', 'RegionMap', 'Problem',
-           'Solver', 'get_var_from_file', 'parse_shapes', 'Engine', 'default_engine', 'RasterMap', 'load_dem_mask',
+           'Solver', 'get_var_from_file', 'parse_shapes', 'save_polygons', 'result_points', 'result_wkt', 'Engine', 'default_engine', 'RasterMap', 'load_dem_mask',
            'distributed']

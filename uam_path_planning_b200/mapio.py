@@ -49,3 +49,49 @@ def get_var_from_file(filename: str, varname: str = 'vertices') -> List[Quadrati
     """Same call as path_generation/utils.py:29-35, without exec."""
     with open(filename, 'r') as fh:
         return parse_shapes(fh.read(), varname)
+
+
+def save_polygons(polygons, output_file: str) -> None:
+    """Writer of the same on-disk format (map_generation/data_manager.py:56-72): ``vertices = [polygon([x, y], ...),``
+    one polygon per line, coordinates divided by 1000 (metres -> km) and printed with ``str`` like the reference.
+    `polygons`: sequences of (x, y) vertices in METRES (a closing vertex equal to the first is dropped)."""
+    lines = []
+    for poly in polygons:
+        coords = [tuple(map(float, c)) for c in poly]
+        if len(coords) > 1 and coords[0] == coords[-1]:
+            coords = coords[:-1]
+        lines.append('polygon(' + ', '.join('[' + str(x / 1000) + ', ' + str(y / 1000) + ']' for x, y in coords) + ')')
+    with open(output_file, 'w') as fh:
+        fh.write('vertices = [' + ',\n'.join(lines) + ('\n' if lines else '') + ']')
+
+
+# path_generation/main.py:103-116: start / goal of the shipped scenario in EPSG:2443 metres
+DEFAULT_START_POINT = [35590.685, -27711.422]
+DEFAULT_END_POINT = [26478.673, 9564.082]
+
+
+def result_points(x, start_point=None, end_point=None):
+    """The point list both exporters of the reference build (make_result_line_shp / save_points_to_shp,
+    path_generation/main.py:103-116): [start_point] + [(1000 x_i, 1000 y_i) for the interior waypoints] + [end_point],
+    in EPSG:2443 metres.  `x` is the flat solver vector (2N,) in km.  Returns an (N + 2, 2) float64 array."""
+    import numpy as np
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    if x.size % 2:
+        raise ValueError('x must hold interleaved (x, y) pairs')
+    sp = DEFAULT_START_POINT if start_point is None else start_point
+    ep = DEFAULT_END_POINT if end_point is None else end_point
+    pts = [list(map(float, sp))] + [[1000 * x[i], 1000 * x[i + 1]] for i in range(0, len(x), 2)] + [list(map(float, ep))]
+    return np.asarray(pts, dtype=np.float64)
+
+
+def result_wkt(x, start_point=None, end_point=None, kind: str = 'line') -> str:
+    """WKT of the best path in EPSG:2443 metres: 'line' -> LINESTRING (make_result_line_shp), 'points' -> MULTIPOINT
+    (save_points_to_shp).  The reference then reprojects to EPSG:4612 and writes a shapefile through geopandas /
+    pyproj / fiona, none of which exist here: this is the array / text hand-off to that step."""
+    pts = result_points(x, start_point, end_point)
+    body = ', '.join(f'{p[0]!r} {p[1]!r}' for p in pts.tolist())
+    if kind == 'line':
+        return f'LINESTRING ({body})'
+    if kind == 'points':
+        return 'MULTIPOINT (' + ', '.join(f'({p[0]!r} {p[1]!r})' for p in pts.tolist()) + ')'
+    raise ValueError("kind must be 'line' or 'points'")
