@@ -141,7 +141,7 @@ def main():
     prob.set_weight('Risk', 5000.0)
     sol = uam.Solver(prob, {})
     cell = KM / n
-    Zc = sol.candidates(rng.uniform(-0.9, 0.9, B), jitter=0.25 * cell, rng=rng)                     # corridor
+    Zc = np.ascontiguousarray(sol.candidates(rng.uniform(-0.9, 0.9, B), jitter=0.25 * cell, rng=rng))   # corridor
     s, e = rng.uniform(0, KM, (B, 1, 2)), rng.uniform(0, KM, (B, 1, 2))
     Zs = (s + np.linspace(0, 1, Wp).reshape(1, Wp, 1) * (e - s) + rng.normal(0, 2 * cell, (B, Wp, 2))).reshape(B, 2 * Wp)
     out = {'config': 'C2: 10k polylines x 64 waypoints, 4096^2 risk+obstacle raster (L=1), 1 B200',
