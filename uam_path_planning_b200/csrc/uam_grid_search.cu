@@ -11,7 +11,8 @@
 //           uam_k_grid_select   collects the triples whose key is within `delta` of their query's minimum and
 //                               clears their keys (the others wait: relaxing them now would be redone when the
 //                               shorter fronts arrive -- measured 32 activations per tile without the ordering);
-//           uam_k_grid_relax    one WARP per active triple: loads the tile + 1-cell halo of dist / cost into its slice
+//           uam_k_grid_relax    one WARP per active triple: loads the tile + 1-cell halo of dist (as 32-bit offsets
+//                               from the tile's key; cells below the key are frozen) / cost into its 9 KB slice
 //                               of shared memory, folds in the candidates from the bands above / below (those do
 //                               not change during the activation), then alternates a top-down and a bottom-up
 //                               Gauss-Seidel sweep until nothing moves.  A sweep step handles one row: the three
@@ -36,7 +37,6 @@ namespace {
 #define GH (GT + 2)                    // with halo
 #define UAM_GRID_INF (1ll << 62)
 #define UAM_GRID_WARPS 8
-#define UAM_GRID_WARP_SMEM (GH * GH * 8 + GH * GH * 4)
 
 __device__ __constant__ int c_di[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
 __device__ __constant__ int c_dj[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
@@ -70,8 +70,18 @@ __global__ void uam_k_grid_seed(long long* __restrict__ dist, const uint8_t* __r
     const size_t c = (size_t)sb * cells + (size_t)si * g.W + sj;
     if (blocked && blocked[c]) return;
     dist[(size_t)q * g.bands * cells + c] = 0;
+    // the source is an arrival of value 0 for its own tile AND for every tile whose halo (or band stack) holds it: a tile
+    // relaxed with a larger key would treat the source cell as frozen
     const size_t tiles = (size_t)g.tiles_x * g.tiles_y;
-    keys[((size_t)q * g.bands + sb) * tiles + (size_t)(si / GT) * g.tiles_x + sj / GT] = 0ull;
+    const int ti = si / GT, tj = sj / GT;
+    for (int di = -1; di <= 1; ++di)
+        for (int dj = -1; dj <= 1; ++dj) {
+            const int ni = ti + di, nj = tj + dj;
+            if (ni >= 0 && ni < g.tiles_y && nj >= 0 && nj < g.tiles_x)
+                keys[((size_t)q * g.bands + sb) * tiles + (size_t)ni * g.tiles_x + nj] = 0ull;
+        }
+    if (sb > 0) keys[((size_t)q * g.bands + sb - 1) * tiles + (size_t)ti * g.tiles_x + tj] = 0ull;
+    if (sb + 1 < g.bands) keys[((size_t)q * g.bands + sb + 1) * tiles + (size_t)ti * g.tiles_x + tj] = 0ull;
 }
 
 // per query: smallest pending key (grid = Q x parts CTAs)
@@ -94,29 +104,41 @@ uam_k_grid_minkey(const unsigned long long* __restrict__ keys, size_t per_q, int
 
 __global__ void __launch_bounds__(256)
 uam_k_grid_select(unsigned long long* __restrict__ keys, size_t n, size_t per_q, const unsigned long long* __restrict__ minkey,
-                  unsigned long long delta, unsigned* __restrict__ list, unsigned* __restrict__ count) {
+                  unsigned long long delta, unsigned* __restrict__ list, unsigned long long* __restrict__ list_key,
+                  unsigned* __restrict__ count) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
         const unsigned long long k = keys[t];
         if (k < (unsigned long long)UAM_GRID_INF && k <= minkey[t / per_q] + delta) {
             keys[t] = (unsigned long long)UAM_GRID_INF;
-            list[atomicAdd(count, 1u)] = (unsigned)t;
+            const unsigned pos = atomicAdd(count, 1u);
+            list[pos] = (unsigned)t;
+            list_key[pos] = k;
         }
     }
 }
 
+// Distances inside an activation are 32-bit and RELATIVE TO THE TILE'S KEY.  Everything this activation can produce is
+// >= key (a relaxation chain starts at a border value that arrived since the last relaxation, and the key is their
+// minimum), so a cell whose distance is below the key can neither drop nor pass on anything the tile has not already
+// seen: it is frozen and treated like a blocked cell.  Cells at key + UAM_GRID_LIM or more do not fit: they enter as
+// "unreached"; if one of them is still that far after the sweeps the tile is relaxed again with the smallest such
+// value as its key (a wall inside the tile separating fronts 10^9 apart -- rare).
+#define UAM_GRID_INF32 0x3fffffff
+#define UAM_GRID_LIM 0x38000000          // INF32 - 2^27: room for any in-tile growth (34 cells x 3 x 131070 < 2^24)
+
 // One sweep step: row li of the tile takes candidates from row ln (li - 1 or li + 1) and closes along the row.
 // Lane l owns column l + 1.  Edge e_l joins columns l and l + 1 (l = 0..32); it is dead when either end is blocked.
-// S_l = real weight of e_0..e_l (32-bit prefix sum, dead edges count 0); a candidate from column k to column j is
+// S_l = weight of e_0..e_l (prefix sum, dead edges count 0); a candidate from column k to column j is
 // d_k + |S_j - S_k| and is valid iff no dead edge lies between them -- checked on the ballot of dead edges, so the two
-// 64-bit min-scans (from the left, from the right) need no sentinel weights.  Returns true (per lane) if this
-// lane's cell dropped.
-__device__ __forceinline__ bool uam_grid_row_step(long long* __restrict__ D, const int* __restrict__ C, int li, int ln, int lane) {
+// min-scans (from the left, from the right) need no sentinel weights.  span_l[s] / span_r[s]: the edges between this
+// lane and the lane 2^s to its left / right (all ones when there is no such lane).
+__device__ __forceinline__ bool uam_grid_row_step(int* __restrict__ D, const int* __restrict__ C, int li, int ln, int lane,
+                                                  const unsigned below, const unsigned (&span_l)[5], const unsigned (&span_r)[5]) {
     const int lj = lane + 1;
     const int cv = C[li * GH + lj];
     const int cl = C[li * GH + lane];                 // column to the left (lane 0: halo column 0)
-    const long long d0 = D[li * GH + lj];
-    // horizontal edges
+    const int d0 = D[li * GH + lj];
     const bool dead_l = cv < 0 || cl < 0;             // e_lane
     const unsigned dead = __ballot_sync(0xffffffffu, dead_l);
     int S = dead_l ? 0 : 2 * (cv + cl);
@@ -129,61 +151,60 @@ __device__ __forceinline__ bool uam_grid_row_step(long long* __restrict__ D, con
     const bool dead32 = c32 < 0 || c33 < 0;
     const int S33 = __shfl_sync(0xffffffffu, S, 31) + (dead32 ? 0 : 2 * (c32 + c33));
     // candidates from the previous row
-    long long d = d0;
+    int d = d0;
     if (cv >= 0) {
 #pragma unroll
         for (int dj = -1; dj <= 1; ++dj) {
             const int cn = C[ln * GH + lj + dj];
-            if (cn >= 0) {
-                const long long cand = D[ln * GH + lj + dj] + (long long)((dj ? 3 : 2) * (cn + cv));
-                d = cand < d ? cand : d;
-            }
+            if (cn >= 0) d = min(d, D[ln * GH + lj + dj] + (dj ? 3 : 2) * (cn + cv));
         }
     }
     // closure along the row: m = min over valid k <= j of (d_k - S_k), gm = min over valid k >= j of (d_k + S_k)
-    long long m = d - (long long)S, gm = d + (long long)S;
-    const unsigned below = (2u << lane) - 1u;         // bits 0..lane
+    int m = d - S, gm = d + S;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long tm = __shfl_up_sync(0xffffffffu, m, o);
-        const long long tg = __shfl_down_sync(0xffffffffu, gm, o);
-        // edges between lane - o and lane: e_{lane-o+1}..e_lane; between lane and lane + o: e_{lane+1}..e_{lane+o}
-        const unsigned span_l = below & ~((lane >= o) ? ((2u << (lane - o)) - 1u) : 0u);
-        const unsigned span_r = (lane + o < 32) ? (((2u << (lane + o)) - 1u) & ~below) : 0xffffffffu;
-        if (lane >= o && !(dead & span_l)) m = tm < m ? tm : m;
-        if (lane + o < 32 && !(dead & span_r)) gm = tg < gm ? tg : gm;
+    for (int s = 0; s < 5; ++s) {
+        const int tm = __shfl_up_sync(0xffffffffu, m, 1 << s);
+        const int tg = __shfl_down_sync(0xffffffffu, gm, 1 << s);
+        if (!(dead & span_l[s])) m = min(m, tm);
+        if (!(dead & span_r[s])) gm = min(gm, tg);
     }
     // halo columns: column 0 (S = 0) reaches lane j iff e_0..e_j alive; column 33 iff e_{j+1}..e_32 alive
-    if (!(dead & below)) {
-        const long long x0 = D[li * GH];
-        m = x0 < m ? x0 : m;
-    }
-    if (!(dead & ~below) && !dead32) {
-        const long long x33 = D[li * GH + GT + 1] + (long long)S33;
-        gm = x33 < gm ? x33 : gm;
-    }
-    const long long from_left = m + (long long)S, from_right = gm - (long long)S;
-    long long nd = from_left < from_right ? from_left : from_right;
-    nd = d < nd ? d : nd;
-    const bool drop = cv >= 0 && nd < d0;
+    if (!(dead & below)) m = min(m, D[li * GH]);
+    if (!(dead & ~below) && !dead32) gm = min(gm, D[li * GH + GT + 1] + S33);
+    const int nd = min(d, min(m + S, gm - S));
+    const bool drop = cv >= 0 && nd < d0 && nd < UAM_GRID_INF32;
     if (drop) D[li * GH + lj] = nd;
     return drop;
 }
 
+#define UAM_GRID_WARP_SMEM (GH * GH * 4 + GH * GH * 4)
+
 __global__ void __launch_bounds__(UAM_GRID_WARPS * 32)
 uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ blocked, UamGridGeo g,
-                 const unsigned* __restrict__ list, const unsigned* __restrict__ count, long long* __restrict__ dist,
-                 unsigned long long* __restrict__ keys, unsigned long long* __restrict__ stats) {
+                 const unsigned* __restrict__ list, const unsigned long long* __restrict__ list_key,
+                 const unsigned* __restrict__ count, long long* __restrict__ dist, unsigned long long* __restrict__ keys,
+                 unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char uam_grid_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    long long* D = reinterpret_cast<long long*>(uam_grid_smem + (size_t)warp * UAM_GRID_WARP_SMEM);
-    int* C = reinterpret_cast<int*>(D + GH * GH);           // cell cost, -1 = blocked / outside
+    int* D = reinterpret_cast<int*>(uam_grid_smem + (size_t)warp * UAM_GRID_WARP_SMEM);      // distance - key
+    int* C = D + GH * GH;                                                                      // cell cost, -1 = blocked / outside / frozen
     const int H = g.H, W = g.W;
     const size_t cells = (size_t)H * W;
     const unsigned tiles = (unsigned)(g.tiles_x * g.tiles_y);
     const unsigned n = *count;
+    // lane-constant masks of the scan steps
+    const unsigned below = (2u << lane) - 1u;         // bits 0..lane
+    unsigned span_l[5], span_r[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int o = 1 << s;
+        // edges between lane - o and lane: e_{lane-o+1}..e_lane; between lane and lane + o: e_{lane+1}..e_{lane+o}
+        span_l[s] = lane >= o ? (below & ~((2u << (lane - o)) - 1u)) : 0xffffffffu;
+        span_r[s] = lane + o < 32 ? (((2u << (lane + o)) - 1u) & ~below) : 0xffffffffu;
+    }
     for (unsigned w = blockIdx.x * UAM_GRID_WARPS + warp; w < n; w += gridDim.x * UAM_GRID_WARPS) {
         const unsigned ent = list[w];
+        long long key = (long long)list_key[w];
         const unsigned qb = ent / tiles, tile = ent - qb * tiles;
         const int q = (int)(qb / (unsigned)g.bands), b = (int)(qb - (unsigned)q * g.bands);
         const int ti = (int)(tile / (unsigned)g.tiles_x), tj = (int)(tile - (unsigned)ti * g.tiles_x);
@@ -191,116 +212,134 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
         long long* dq = dist + ((size_t)q * g.bands + b) * cells;
         const uint16_t* cb = cost + (size_t)b * cells;
         const uint8_t* bb = blocked ? blocked + (size_t)b * cells : nullptr;
-        __syncwarp();
-        // ---- load tile + halo (34 rows x 34 columns: lanes cover columns 0..31, lanes 0..1 also 32..33); the loads of
-        //      several rows are issued together (the activation's latency is what bounds a round) ----------------------
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int lj = lane + 32 * pass;
-            const int j = j0 + lj;
-            const bool col_ok = lj < GH && j >= 0 && j < W;
-            for (int r0 = 0; r0 < GH; r0 += 6) {
-                long long dv[6];
-                int cvv[6];
-                uint8_t bl[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int i = i0 + r0 + k;
-                    const bool ok = col_ok && r0 + k < GH && i >= 0 && i < H;
-                    const size_t gi = ok ? (size_t)i * W + j : 0;
-                    dv[k] = ok ? dq[gi] : UAM_GRID_INF;
-                    cvv[k] = ok ? (int)cb[gi] : -1;
-                    bl[k] = (ok && bb) ? bb[gi] : 0;
-                }
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    if (lj < GH && r0 + k < GH) {
-                        D[(r0 + k) * GH + lj] = bl[k] ? UAM_GRID_INF : dv[k];
-                        C[(r0 + k) * GH + lj] = bl[k] ? -1 : cvv[k];
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // ---- candidates from the bands below / above (fixed during this activation) ----------------------------------
-        for (int db = -1; db <= 1; db += 2) {
-            const int b2 = b + db;
-            if (b2 < 0 || b2 >= g.bands) continue;
-            const long long* d2 = dist + ((size_t)q * g.bands + b2) * cells;
-            const uint16_t* c2 = cost + (size_t)b2 * cells;
-            const uint8_t* bl2 = blocked ? blocked + (size_t)b2 * cells : nullptr;
-            const int j = j0 + lane + 1;
-            for (int r0 = 1; r0 <= GT; r0 += 8) {
-                long long dv[8];
-                int cvv[8];
-                uint8_t bl[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i = i0 + r0 + k;
-                    const bool ok = i < H && j < W;
-                    const size_t gi = ok ? (size_t)i * W + j : 0;
-                    dv[k] = ok ? d2[gi] : UAM_GRID_INF;
-                    cvv[k] = ok ? (int)c2[gi] : 0;
-                    bl[k] = (ok && bl2) ? bl2[gi] : 0;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int li = r0 + k;
-                    const int cv = C[li * GH + lane + 1];
-                    if (cv >= 0 && !bl[k] && dv[k] < UAM_GRID_INF) {
-                        const long long cand = dv[k] + (long long)(2 * (cvv[k] + cv));
-                        if (cand < D[li * GH + lane + 1]) D[li * GH + lane + 1] = cand;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // ---- Gauss-Seidel sweeps to the local fixed point ---------------------------------------------------------------
-        bool changed;
-        unsigned n_sweeps = 0;
-        do {
-            bool ch = false;
-            ++n_sweeps;
-            for (int li = 1; li <= GT; ++li) {
-                ch |= uam_grid_row_step(D, C, li, li - 1, lane);
-                __syncwarp();
-            }
-            for (int li = GT; li >= 1; --li) {
-                ch |= uam_grid_row_step(D, C, li, li + 1, lane);
-                __syncwarp();
-            }
-            changed = __any_sync(0xffffffffu, ch);
-        } while (changed);
-        // ---- write back the cells that dropped; smallest dropped value per side ------------------------------------------
         long long m_all = UAM_GRID_INF, m_top = UAM_GRID_INF, m_bot = UAM_GRID_INF, m_side = UAM_GRID_INF;   // m_side: this lane's column
-        long long c_tl = UAM_GRID_INF, c_tr = UAM_GRID_INF, c_bl = UAM_GRID_INF, c_br = UAM_GRID_INF;
-        {
-            const int lj = lane + 1;
-            const int j = j0 + lj;
-            for (int r0 = 1; r0 <= GT; r0 += 8) {
-                long long old[8];
+        unsigned n_sweeps = 0;
+        for (;;) {                               // one trip unless some cell sits 10^9 above the key (see above)
+            long long far_min = UAM_GRID_INF;
+            __syncwarp();
+            // ---- load tile + halo (34 rows x 34 columns: lanes cover columns 0..31, lanes 0..1 also 32..33); the loads of
+            //      several rows are issued together (the activation's latency is what bounds a round) ------------------
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i = i0 + r0 + k;
-                    old[k] = (i < H && j < W) ? dq[(size_t)i * W + j] : 0;       // 0: nothing is below it
-                }
+            for (int pass = 0; pass < 2; ++pass) {
+                const int lj = lane + 32 * pass;
+                const int j = j0 + lj;
+                const bool col_ok = lj < GH && j >= 0 && j < W;
+                for (int r0 = 0; r0 < GH; r0 += 6) {
+                    long long dv[6];
+                    int cvv[6];
+                    uint8_t bl[6];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int li = r0 + k;
-                    const long long now = D[li * GH + lj];
-                    if (now < old[k]) {
-                        dq[(size_t)(i0 + li) * W + j] = now;
-                        m_all = now < m_all ? now : m_all;
-                        m_side = now < m_side ? now : m_side;
-                        if (li == 1) m_top = now;
-                        if (li == GT) m_bot = now;
+                    for (int k = 0; k < 6; ++k) {
+                        const int i = i0 + r0 + k;
+                        const bool ok = col_ok && r0 + k < GH && i >= 0 && i < H;
+                        const size_t gi = ok ? (size_t)i * W + j : 0;
+                        dv[k] = ok ? dq[gi] : UAM_GRID_INF;
+                        cvv[k] = ok ? (int)cb[gi] : -1;
+                        bl[k] = (ok && bb) ? bb[gi] : 0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        if (lj < GH && r0 + k < GH) {
+                            const long long rel = dv[k] - key;
+                            const bool frozen = bl[k] || rel < 0;
+                            const bool far = !frozen && rel >= UAM_GRID_LIM;
+                            if (far && dv[k] < UAM_GRID_INF) far_min = dv[k] < far_min ? dv[k] : far_min;
+                            D[(r0 + k) * GH + lj] = (frozen || far) ? UAM_GRID_INF32 : (int)rel;
+                            C[(r0 + k) * GH + lj] = frozen ? -1 : cvv[k];
+                        }
                     }
                 }
             }
+            __syncwarp();
+            // ---- candidates from the bands below / above (fixed during this activation) ------------------------------
+            for (int db = -1; db <= 1; db += 2) {
+                const int b2 = b + db;
+                if (b2 < 0 || b2 >= g.bands) continue;
+                const long long* d2 = dist + ((size_t)q * g.bands + b2) * cells;
+                const uint16_t* c2 = cost + (size_t)b2 * cells;
+                const uint8_t* bl2 = blocked ? blocked + (size_t)b2 * cells : nullptr;
+                const int j = j0 + lane + 1;
+                for (int r0 = 1; r0 <= GT; r0 += 8) {
+                    long long dv[8];
+                    int cvv[8];
+                    uint8_t bl[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int i = i0 + r0 + k;
+                        const bool ok = i < H && j < W;
+                        const size_t gi = ok ? (size_t)i * W + j : 0;
+                        dv[k] = ok ? d2[gi] : UAM_GRID_INF;
+                        cvv[k] = ok ? (int)c2[gi] : 0;
+                        bl[k] = (ok && bl2) ? bl2[gi] : 0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int li = r0 + k;
+                        const int cv = C[li * GH + lane + 1];
+                        if (cv >= 0 && !bl[k] && dv[k] < UAM_GRID_INF) {
+                            const long long rel = dv[k] + (long long)(2 * (cvv[k] + cv)) - key;
+                            if (rel >= UAM_GRID_LIM) far_min = dv[k] < far_min ? dv[k] : far_min;       // source too far for this key
+                            else if (rel >= 0 && (int)rel < D[li * GH + lane + 1]) D[li * GH + lane + 1] = (int)rel;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- Gauss-Seidel sweeps to the local fixed point -----------------------------------------------------------
+            bool changed;
+            do {
+                bool ch = false;
+                ++n_sweeps;
+                for (int li = 1; li <= GT; ++li) {
+                    ch |= uam_grid_row_step(D, C, li, li - 1, lane, below, span_l, span_r);
+                    __syncwarp();
+                }
+                for (int li = GT; li >= 1; --li) {
+                    ch |= uam_grid_row_step(D, C, li, li + 1, lane, below, span_l, span_r);
+                    __syncwarp();
+                }
+                changed = __any_sync(0xffffffffu, ch);
+            } while (changed);
+            // ---- write back the cells that dropped; smallest dropped value per side ------------------------------------
+            {
+                const int lj = lane + 1;
+                const int j = j0 + lj;
+                for (int r0 = 1; r0 <= GT; r0 += 8) {
+                    long long old[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int i = i0 + r0 + k;
+                        old[k] = (i < H && j < W) ? dq[(size_t)i * W + j] : 0;       // 0: nothing is below it
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int li = r0 + k;
+                        const int rel = D[li * GH + lj];
+                        const long long now = key + (long long)rel;
+                        if (rel < UAM_GRID_INF32 && now < old[k]) {
+                            dq[(size_t)(i0 + li) * W + j] = now;
+                            m_all = now < m_all ? now : m_all;
+                            m_side = now < m_side ? now : m_side;
+                            if (li == 1) m_top = now < m_top ? now : m_top;
+                            if (li == GT) m_bot = now < m_bot ? now : m_bot;
+                        } else if (rel >= UAM_GRID_INF32 && old[k] < UAM_GRID_INF && old[k] - key >= UAM_GRID_LIM) {
+                            // still too far above this key: its own arrivals are handled by the next trip
+                        }
+                    }
+                }
+            }
+            // another trip?  only when something finite did not fit under this key
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const long long t = __shfl_xor_sync(0xffffffffu, far_min, o);
+                far_min = t < far_min ? t : far_min;
+            }
+            if (far_min >= UAM_GRID_INF) break;
+            key = far_min;
         }
         // corners (single cells), left / right columns (lanes 0 / 31), top / bottom rows and overall (warp minima)
-        c_tl = __shfl_sync(0xffffffffu, m_top, 0);  c_tr = __shfl_sync(0xffffffffu, m_top, 31);
-        c_bl = __shfl_sync(0xffffffffu, m_bot, 0);  c_br = __shfl_sync(0xffffffffu, m_bot, 31);
+        const long long c_tl = __shfl_sync(0xffffffffu, m_top, 0), c_tr = __shfl_sync(0xffffffffu, m_top, 31);
+        const long long c_bl = __shfl_sync(0xffffffffu, m_bot, 0), c_br = __shfl_sync(0xffffffffu, m_bot, 31);
         const long long m_left = __shfl_sync(0xffffffffu, m_side, 0), m_right = __shfl_sync(0xffffffffu, m_side, 31);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -422,8 +461,8 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     const size_t tiles = (size_t)g.tiles_x * g.tiles_y;
     const size_t n_flags = tiles * bands * Q;
     if (n_flags >= 0xffffffffull) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "too many (query, band, tile) triples");
-    // scratch: keys (u64) | minkey (u64 x Q) | stats (u64 x 2) | list (u32) | count (u32 x 2)
-    UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, n_flags * 12 + (size_t)Q * 8 + 256));
+    // scratch: keys (u64) | list_key (u64) | minkey (u64 x Q) | stats (u64 x 2) | list (u32) | count (u32 x 2)
+    UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, n_flags * 20 + (size_t)Q * 8 + 256));
     unsigned long long* keys = (unsigned long long*)ctx->d_scratch;
     // delta = cost of crossing about two tiles at the grid's mean cell cost (ordering only: any value gives the same result)
     unsigned long long delta = ctx->grid_delta > 0 ? (unsigned long long)ctx->grid_delta : 0ull;
@@ -431,7 +470,8 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
         UAM_TRY(uam_grid_mean_cost(ctx, d_cost, (size_t)H * W * bands, st, &delta));
         delta = delta * 8ull * GT;     // measured on C5 (Q = 16): 4x / 8x / 16x -> 640 / 448 / 336 rounds, 1.69 / 1.77 / 2.06 M activations
     }
-    unsigned long long* minkey = keys + n_flags;
+    unsigned long long* list_key = keys + n_flags;
+    unsigned long long* minkey = list_key + n_flags;
     unsigned long long* stats = minkey + Q;
     unsigned* list = (unsigned*)(stats + 2);
     unsigned* count = list + n_flags;
@@ -447,7 +487,7 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     const int parts = (int)std::max<size_t>(1, std::min<size_t>(64, per_q / 2048));
     const size_t smem = (size_t)UAM_GRID_WARP_SMEM * UAM_GRID_WARPS;
     UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_grid_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid_relax = ctx->sm_count * 2;
+    const int grid_relax = ctx->sm_count * 3;
     const long long max_rounds = 1ll << 40;      // the loop ends when no key is pending
     unsigned h_count = 1;
     long long rounds_done = 0;
@@ -457,9 +497,9 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
         UAM_CUDA(ctx, cudaMemsetAsync(minkey, 0xff, (size_t)Q * 8, st));
         uam_k_grid_minkey<<<Q * parts, 256, 0, st>>>(keys, per_q, parts, minkey);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_minkey");
-        uam_k_grid_select<<<ctx->sm_count * 4, 256, 0, st>>>(keys, n_flags, per_q, minkey, delta, list, count);
+        uam_k_grid_select<<<ctx->sm_count * 4, 256, 0, st>>>(keys, n_flags, per_q, minkey, delta, list, list_key, count);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_select");
-        uam_k_grid_relax<<<grid_relax, UAM_GRID_WARPS * 32, smem, st>>>(d_cost, d_blocked, g, list, count, (long long*)d_dist, keys, stats);
+        uam_k_grid_relax<<<grid_relax, UAM_GRID_WARPS * 32, smem, st>>>(d_cost, d_blocked, g, list, list_key, count, (long long*)d_dist, keys, stats);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_relax");
         if ((round & 7) == 7) {     // termination check every 8 rounds: rounds with an empty list are no-ops
             UAM_CUDA(ctx, cudaMemcpyAsync(&h_count, count, 4, cudaMemcpyDeviceToHost, st));
