@@ -609,8 +609,8 @@ uam_k_bin_scan(const unsigned* __restrict__ hist, int n, unsigned* __restrict__ 
 }
 
 __global__ void __launch_bounds__(1024)
-uam_k_bin_scatter(const double2* __restrict__ z, unsigned long long n_seg, int Wp, UamRasterParams rp, UamBinGeo bg,
-                  const unsigned short* __restrict__ seg_bin, unsigned* __restrict__ cursor, UamSegRec* __restrict__ recs) {
+uam_k_bin_scatter(unsigned long long n_seg, UamBinGeo bg, const unsigned short* __restrict__ seg_bin,
+                  unsigned* __restrict__ cursor, unsigned* __restrict__ sorted_id) {
     extern __shared__ int s_hist[];
     for (int i = threadIdx.x; i < bg.nbins; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
@@ -624,9 +624,11 @@ uam_k_bin_scatter(const double2* __restrict__ z, unsigned long long n_seg, int W
         if (c) s_hist[i] = (int)atomicAdd(&cursor[i], (unsigned)c);
     }
     __syncthreads();
+    // the sorted order holds 4-byte segment ids only; the scoring kernel rebuilds the segment from its two waypoints
+    // (one lane per record, once per group) -- 48-byte records cost 0.33 ms of scattered writes per C3 shard
     for (unsigned long long id = lo + threadIdx.x; id < hi; id += blockDim.x) {
         const unsigned pos = (unsigned)atomicAdd(&s_hist[seg_bin[id]], 1);
-        recs[pos] = uam_make_segment(z, id, Wp, rp);
+        sorted_id[pos] = (unsigned)id;
     }
 }
 
@@ -767,8 +769,9 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
 
 template <int TF, int LAYOUT>
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
-uam_k_score_groups(unsigned long long n_seg, UamRasterParams rp, const typename UamTexel<TF>::T* __restrict__ tex,
-                   const UamSegRec* __restrict__ recs, float* __restrict__ part_pen, uint8_t* __restrict__ part_col) {
+uam_k_score_groups(unsigned long long n_seg, int Wp, UamRasterParams rp, const typename UamTexel<TF>::T* __restrict__ tex,
+                   const double2* __restrict__ z, const unsigned* __restrict__ sorted_id, float* __restrict__ part_pen,
+                   uint8_t* __restrict__ part_col) {
     extern __shared__ __align__(128) unsigned char uam_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -779,26 +782,16 @@ uam_k_score_groups(unsigned long long n_seg, UamRasterParams rp, const typename 
     for (unsigned long long g = warp0; g < n_groups; g += nwarps) {
         const unsigned long long ridx = (g << 5) + lane;
         const bool have = ridx < n_seg;
-        // this lane's record (3 x 16 B, coalesced across the warp)
-        double U = 0.0, V = 0.0, SU = 0.0, SV = 0.0;
-        int S = 0;
-        unsigned id = 0;
-        float IS = 0.0f;
-        if (have) {
-            const double2* rp2 = reinterpret_cast<const double2*>(recs + ridx);
-            const double2 a = __ldg(rp2), b = __ldg(rp2 + 1);
-            const int4 c = __ldg(reinterpret_cast<const int4*>(rp2 + 2));
-            U = a.x; V = a.y; SU = b.x; SV = b.y;
-            S = c.x;
-            IS = __int_as_float(c.y);
-            id = (unsigned)c.z;
-        }
+        // this lane's segment, rebuilt from its id (same arithmetic as the binning pass)
+        UamSegRec r;
+        r.U = 0.0; r.V = 0.0; r.SU = 0.0; r.SV = 0.0; r.S = 0; r.IS = 0.0f; r.id = 0;
+        if (have) r = uam_make_segment(z, (unsigned long long)__ldg(sorted_id + ridx), Wp, rp);
         float mine;
         bool col;
-        uam_group_score<TF, LAYOUT, 0>(rp, tex, nullptr, 0, 0, base, lane, U, V, SU, SV, S, 0, mine, col);
+        uam_group_score<TF, LAYOUT, 0>(rp, tex, nullptr, 0, 0, base, lane, r.U, r.V, r.SU, r.SV, r.S, 0, mine, col);
         if (have) {
-            part_pen[id] = mine * IS;
-            part_col[id] = col ? 1 : 0;
+            part_pen[r.id] = mine * r.IS;
+            part_col[r.id] = col ? 1 : 0;
         }
     }
 }
@@ -1275,11 +1268,11 @@ int uam_raster_launch_binned(uam_ctx* ctx, const void* texv, const double2* z, i
     int p2 = 1;
     while (p2 < ((side + (1 << bg.shift) - 1) >> bg.shift)) p2 <<= 1;
     bg.nbins = p2 * p2;
-    // scratch: recs (48 B) | part_pen (f32) | hist (u32) | cursor (u32) | seg_bin (u16) | part_col (u8)
-    const size_t need = n_seg * (sizeof(UamSegRec) + 4 + 2 + 1) + (size_t)bg.nbins * 8 + 256;
+    // scratch: sorted ids (u32) | part_pen (f32) | hist (u32) | cursor (u32) | seg_bin (u16) | part_col (u8)
+    const size_t need = n_seg * (4 + 4 + 2 + 1) + (size_t)bg.nbins * 8 + 256;
     UAM_TRY(uam_reserve(ctx, &ctx->d_bin_scratch[slot], &ctx->bin_scratch_bytes[slot], need));
-    UamSegRec* recs = (UamSegRec*)ctx->d_bin_scratch[slot];
-    float* part_pen = (float*)(recs + n_seg);
+    unsigned* sorted_id = (unsigned*)ctx->d_bin_scratch[slot];
+    float* part_pen = (float*)(sorted_id + n_seg);
     unsigned* hist = (unsigned*)(part_pen + n_seg);
     unsigned* cursor = hist + bg.nbins;
     unsigned short* seg_bin = (unsigned short*)(cursor + bg.nbins);
@@ -1295,7 +1288,7 @@ int uam_raster_launch_binned(uam_ctx* ctx, const void* texv, const double2* z, i
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_hist");
     uam_k_bin_scan<<<1, 1024, 0, st>>>(hist, bg.nbins, cursor);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_scan");
-    uam_k_bin_scatter<<<chunks, 1024, hsmem, st>>>(z, n_seg, Wp, rp, bg, seg_bin, cursor, recs);
+    uam_k_bin_scatter<<<chunks, 1024, hsmem, st>>>(n_seg, bg, seg_bin, cursor, sorted_id);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_scatter");
     const size_t gsmem = (size_t)UAM_GROUP_SMEM * UAM_WARPS_PER_CTA;
     const unsigned long long n_groups = (n_seg + 31) >> 5;
@@ -1304,7 +1297,7 @@ int uam_raster_launch_binned(uam_ctx* ctx, const void* texv, const double2* z, i
         UAM_TRY(uam_time_collect(ctx));
         UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
     }
-    uam_k_score_groups<TF, LAYOUT><<<(unsigned)sctas, UAM_CTA_THREADS, gsmem, st>>>(n_seg, rp, (const T*)texv, recs, part_pen, part_col);
+    uam_k_score_groups<TF, LAYOUT><<<(unsigned)sctas, UAM_CTA_THREADS, gsmem, st>>>(n_seg, Wp, rp, (const T*)texv, z, sorted_id, part_pen, part_col);
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_groups");
     if (ctx->time_kernels && slot == 0) {
         UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
