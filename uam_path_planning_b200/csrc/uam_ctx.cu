@@ -75,7 +75,7 @@ int uam_make_params(uam_ctx* ctx, const double* h_p, int n_p, int flags, UamPara
     out->mincos = std::cos(h_p[5]);     // cs.cos(maxalpha), problem.py:98
     out->e = h_p[6];
     for (int r = 0; r < R; ++r) out->w[r] = h_p[7 + r];
-    out->flags = flags;
+    out->flags = flags & 0xffff;          // the upper bits are the library's own (UAM_INTERNAL_*)
     out->n_regions = R;
     return UAM_OK;
 }
@@ -258,6 +258,8 @@ extern "C" int uam_map_set_shapes(uam_ctx* ctx, const double* h_edges, int n_edg
         if (k != UAM_EDGE_LINE && k != UAM_EDGE_ELLIPSE && k != UAM_EDGE_BOX)
             return uam_fail(ctx, UAM_ERR_INVALID, "inequality %d: unknown kind %d", i, k);
     }
+    bool finite = true;
+    for (size_t i = 0; i < 8 * (size_t)n_edges; ++i) finite = finite && std::isfinite(h_edges[i]);
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
 
     // device order: obstacles (insertion order), then regions 0..R-1 (insertion order inside each)
@@ -303,6 +305,7 @@ extern "C" int uam_map_set_shapes(uam_ctx* ctx, const double* h_edges, int n_edg
     ctx->n_regions = n_regions;
     ctx->n_obs = n_obs;
     ctx->has_shapes = true;
+    ctx->edges_finite = finite;
     ctx->psic_valid = false;
     return UAM_OK;
 }

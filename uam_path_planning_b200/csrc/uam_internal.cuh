@@ -14,6 +14,7 @@
 #define UAM_WARPS_PER_CTA 8
 #define UAM_CTA_THREADS (UAM_WARPS_PER_CTA * 32)
 #define UAM_HOST_PIPE_DEPTH 3
+#define UAM_INTERNAL_FINITE_EDGES (1 << 30)   // UamParams.flags, set by the library: psi products may stop at their first zero
 
 // ---- device table records ---------------------------------------------------------------------
 // Inequality record, same 8-double layout as the C-ABI (rec[0] = kind).
@@ -69,6 +70,7 @@ struct uam_ctx {
     int n_shapes = 0, n_edges = 0, n_regions = 0, n_obs = 0;
     int region_begin[UAM_MAX_REGIONS + 1] = {};  // shape index range of each region
     bool has_shapes = false;
+    bool edges_finite = false;          // every inequality record is finite: the psi product may stop at its first zero
     bool psic_valid = false;
     double psic_e = 0.0;
     int psic_flags = -1;
@@ -185,10 +187,15 @@ __device__ __forceinline__ UamEdge uam_load_edge(const UamEdge* __restrict__ p) 
 
 // psi_s(x; e) = prod_i min(h_i - e, 0)^2 (smooth) | prod_i min(e - h_i, 0)   quadratic_obstacle.py:27-39
 // `inside` (nullable) gets all_i h_i <= 1e-14                                  quadratic_obstacle.py:89-94
+// `early_exit`: stop at the first zero of the running product.  Exact: with finite inequality records (checked at
+// upload) and |x|, |y| < 1e100 every later factor is finite, so the reference's full product is the same 0 (a product
+// that overflowed to inf before the zero gives NaN in both); when `inside` is wanted the loop also needs some
+// h_i > 1e-14 before it may stop.
 __device__ __forceinline__ double uam_psi(const UamEdge* __restrict__ edges, int e0, int e1, double x,
-                                          double y, bool smooth, double e, bool* inside) {
+                                          double y, bool smooth, double e, bool* inside, bool early_exit = false) {
     double res = 1.0;
     bool in = true;
+    const bool fast = early_exit && fabs(x) < 1e100 && fabs(y) < 1e100;
     for (int i = e0; i < e1; ++i) {
         const UamEdge r = uam_load_edge(edges + i);
         const double h = uam_h_exact(r, x, y);
@@ -199,6 +206,7 @@ __device__ __forceinline__ double uam_psi(const UamEdge* __restrict__ edges, int
         } else {
             res = __dmul_rn(res, fmin(__dsub_rn(e, h), 0.0));
         }
+        if (fast && res == 0.0 && (!inside || !in)) break;
     }
     if (inside) *inside = in;
     return res;

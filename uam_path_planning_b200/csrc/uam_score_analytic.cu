@@ -19,11 +19,11 @@ __device__ __forceinline__ double uam_norm2(double dx, double dy) {
 // sum over the region's shapes of psi(x)/psi(center)     problem.py:72-80 (without the weight)
 __device__ __forceinline__ double uam_region_total(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes,
                                                    const double* __restrict__ psic, int s0, int s1, double x, double y,
-                                                   bool smooth, double e) {
+                                                   bool smooth, double e, bool early_exit) {
     double total = 0.0;
     for (int s = s0; s < s1; ++s) {
         const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));   // e0, e1, region, has_center
-        const double psi = uam_psi(edges, meta.x, meta.y, x, y, smooth, e, nullptr);
+        const double psi = uam_psi(edges, meta.x, meta.y, x, y, smooth, e, nullptr, early_exit);
         if (meta.w) {
             const double pc = __ldg(psic + s);
             // x + 0/pc == x unless pc == 0 (0/0 = NaN must propagate like the reference)
@@ -51,6 +51,7 @@ uam_k_score_analytic(const double2* __restrict__ z, long long B, int N, UamParam
     const int W = N + 2;
     const bool pen_smooth = (prm.flags & UAM_PENALTY_SMOOTH) != 0;
     const bool obs_smooth = (prm.flags & UAM_OBSTACLE_SMOOTH) != 0;
+    const bool fast = (prm.flags & UAM_INTERNAL_FINITE_EDGES) != 0;
     const bool len_smooth = (prm.flags & UAM_LENGTH_SMOOTH) != 0;
     const bool mr_smooth = (prm.flags & UAM_MAXRATIO_SMOOTH) != 0;
     const double mr = mr_smooth ? __dmul_rn(prm.maxratio, prm.maxratio) : prm.maxratio;   // problem.py:95-96
@@ -68,7 +69,7 @@ uam_k_score_analytic(const double2* __restrict__ z, long long B, int N, UamParam
             double P = 0.0;
             for (int r = 0; r < prm.n_regions; ++r) {
                 const double tot = uam_region_total(edges, shapes, psic, rr.begin[r], rr.begin[r + 1], p.x, p.y,
-                                                    pen_smooth, prm.e);
+                                                    pen_smooth, prm.e, fast);
                 P = __dadd_rn(P, __dmul_rn(prm.w[r], tot));
             }
             pen_sum += __ddiv_rn(P, dN);                                   // problem.py:43
@@ -76,7 +77,7 @@ uam_k_score_analytic(const double2* __restrict__ z, long long B, int N, UamParam
             for (int o = 0; o < n_obs; ++o) {
                 const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[o].e0));
                 bool inside;
-                const double psi = uam_psi(edges, meta.x, meta.y, p.x, p.y, obs_smooth, 0.0, &inside);
+                const double psi = uam_psi(edges, meta.x, meta.y, p.x, p.y, obs_smooth, 0.0, &inside, fast);
                 col = col || inside;
                 if (gp) gp[3 * N + o * W + j] = psi;
             }
@@ -123,23 +124,24 @@ uam_k_eval_points(const double2* __restrict__ x, long long M, UamParams prm, Uam
     const long long stride = (long long)gridDim.x * blockDim.x;
     const bool pen_smooth = (prm.flags & UAM_PENALTY_SMOOTH) != 0;
     const bool obs_smooth = (prm.flags & UAM_OBSTACLE_SMOOTH) != 0;
+    const bool fast = (prm.flags & UAM_INTERNAL_FINITE_EDGES) != 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
         const double2 p = x[i];
         if (region_pen) {
             for (int r = 0; r < prm.n_regions; ++r) {
                 const double tot = uam_region_total(edges, shapes, psic, rr.begin[r], rr.begin[r + 1], p.x, p.y,
-                                                    pen_smooth, prm.e);
+                                                    pen_smooth, prm.e, fast);
                 region_pen[i * prm.n_regions + r] = __dmul_rn(prm.w[r], tot);
             }
         }
         if (obst_pen)   // get_penalty_function(None): w = 1, obstacle_smooth, params['enlargement']
-            obst_pen[i] = uam_region_total(edges, shapes, psic, 0, n_obs, p.x, p.y, obs_smooth, prm.e);
+            obst_pen[i] = uam_region_total(edges, shapes, psic, 0, n_obs, p.x, p.y, obs_smooth, prm.e, fast);
         if (collide) {
             bool col = false;
             for (int o = 0; o < n_obs; ++o) {
                 const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[o].e0));
                 bool inside;
-                uam_psi(edges, meta.x, meta.y, p.x, p.y, true, 0.0, &inside);
+                uam_psi(edges, meta.x, meta.y, p.x, p.y, true, 0.0, &inside, fast);
                 col = col || inside;
             }
             collide[i] = col ? 1 : 0;
@@ -194,6 +196,7 @@ int uam_analytic_prepare(uam_ctx* ctx, const double* h_p, int n_p, int flags, cu
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     UAM_TRY(uam_ensure_shape_norm(ctx, *prm, st));
     for (int r = 0; r <= ctx->n_regions; ++r) rr->begin[r] = ctx->region_begin[r];
+    if (ctx->edges_finite) prm->flags |= UAM_INTERNAL_FINITE_EDGES;
     return UAM_OK;
 }
 
