@@ -471,6 +471,36 @@ def test_tile_staged_hot_tiles_and_variants_agree(uam, torch, L):
     assert np.array_equal(res[3, 2][0], res[3, 1][0]) and np.array_equal(res[2, 2][0], res[2, 1][0])   # both quad forms: same bits
 
 
+@pytest.mark.parametrize('H,W,L', [(2, 2, 2), (2, 3, 1), (65, 129, 2), (33, 64, 3)])
+@pytest.mark.parametrize('variant', [-1, 3])
+def test_large_batch_pipelines_on_small_and_ragged_rasters(uam, torch, H, W, L, variant):
+    """The large-batch pipelines (quad texels, binning, tile staging) on rasters of minimum size (2 x 2), one cell past
+    a tile boundary (65 x 129) and with a negative row step, with most waypoints outside the raster (clamped samples):
+    every path against the C oracle, collision flags and sample counts identical."""
+    from oracle import uam_oracle_c as occ
+    rng = np.random.default_rng(H * 1000 + W + L)
+    lay = rng.uniform(0.0, 3.0, (L, H, W)).astype(np.float32)
+    oc = (rng.uniform(size=(H, W)) < 0.3).astype(np.uint8)
+    geo = (-1.0, 0.5, 7.0, -0.25)
+    B, Wp = 4400, 64                                     # 281 600 segments: above the 2^18 threshold of the pipelines
+    lo = np.array([-1.0 - 0.6 * W * 0.5, 7.0 - 1.6 * H * 0.25])
+    hi = np.array([-1.0 + 1.6 * W * 0.5, 7.0 + 0.6 * H * 0.25])
+    s = lo + rng.uniform(size=(B, 1, 2)) * (hi - lo)
+    g = lo + rng.uniform(size=(B, 1, 2)) * (hi - lo)
+    t = np.linspace(0, 1, Wp).reshape(1, Wp, 1)
+    Z = np.ascontiguousarray((s + t * (g - s) + rng.normal(0, 0.2, (B, Wp, 2))).reshape(B, 2 * Wp))
+    w = [3.0, 0.25, 11.0][:L]
+    rm = uam.RasterMap.from_arrays(lay, geo, oc, options={'integral_variant': variant})
+    for spc in (1.0, 3.0, 0.0):
+        c, k, ns = rm.score_paths(torch.from_numpy(Z).cuda(), w, spc, True, None, want_nsamples=True)
+        c_ref, k_ref, ns_ref = occ.score_paths_raster(lay, oc, geo, Z, w, spc, True, None)
+        np.testing.assert_allclose(c.cpu().numpy(), c_ref, rtol=RTOL_RASTER)
+        assert np.array_equal(k.cpu().numpy().astype(bool), k_ref) and np.array_equal(ns.cpu().numpy(), ns_ref)
+    # empty batch: legal, returns empty outputs
+    c0, k0 = rm.score_paths(torch.empty((0, 2 * Wp), dtype=torch.float64, device='cuda'), w, 1.0, True, None)
+    assert c0.numel() == 0 and k0.numel() == 0
+
+
 @pytest.mark.parametrize('config', ['C2', 'C3'])
 def test_raster_scorer_full_size_vs_c_oracle(uam, torch, config):
     """BASELINE.json's own sizes, every path compared: C2 = 10k polylines x 64 waypoints on a 4096^2 risk+obstacle
