@@ -672,7 +672,7 @@ __device__ __forceinline__ void uam_tap_load_tile(const unsigned char* tile, int
 struct __align__(16) UamGroupRec {
     double U, SU, V, SV;
 };
-#define UAM_GROUP_SMEM (32 * 32 + 36 * 4 + 32 * 32 * 4)    // records (32 x 32 B) + Q[33] (padded to 16 B) + partials
+#define UAM_GROUP_SMEM (32 * 32 + 32 * 8 + 32 * 32 * 4)    // records (32 x 32 B) + {P, Q} (32 x 8 B) + partials
 
 template <int TF> struct UamTapsPerTrip { static const int N = 2; };
 template <> struct UamTapsPerTrip<1> { static const int N = 4; };
@@ -682,6 +682,12 @@ template <> struct UamTapsPerTrip<8> { static const int N = 4; };
 // its parent segment; S = 0 for a lane without a record).  Out: the record's sample sum (not yet divided by the
 // parent's sample count) and its collision bit.  TILE = 0: taps from global memory (tex); TILE = 1: taps from the
 // tile staged in shared memory.
+// Shared-memory traffic is what the LSU data pipe of this kernel is busiest with (ncu: 256 M shared wavefronts against
+// 111 M global ones per C3 launch before the three measures below): (1) the partials are zeroed with conflict-free
+// stores (each lane clearing its own row put all 32 lanes on the same 4 banks); (2) a lane re-reads the record
+// parameters only when its record changes; (3) a lane's partial for record k goes to the row of its record-local
+// residue class (lane - P_k) mod 32, so the final per-record sums are one 32 x 32 transpose-reduce (31 shuffles)
+// instead of 32 warp sums (160 shuffles) -- same pairing tree, same bits.
 template <int TF, int LAYOUT, int TILE>
 __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const typename UamTexel<TF>::T* __restrict__ tex,
                                                 const unsigned char* s_tile, int ti0, int tj0, unsigned char* warp_smem,
@@ -689,8 +695,8 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
                                                 const double SV, const int S, const int s0, float& mine, bool& collide) {
     constexpr int TAPS = UamTapsPerTrip<TF>::N;
     UamGroupRec* s_rec = reinterpret_cast<UamGroupRec*>(warp_smem);
-    int* s_Q = reinterpret_cast<int*>(warp_smem + 32 * 32);          // Q_k = P_k - s0_k: flat index -> sample number
-    float* part = reinterpret_cast<float*>(warp_smem + 32 * 32 + 36 * 4);
+    int2* s_PQ = reinterpret_cast<int2*>(warp_smem + 32 * 32);       // {P_k, Q_k = P_k - s0_k}: flat index -> sample number
+    float* part = reinterpret_cast<float*>(warp_smem + 32 * 32 + 32 * 8);
     int incl = S;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -702,20 +708,27 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
     UamGroupRec mr;
     mr.U = U; mr.SU = SU; mr.V = V; mr.SV = SV;
     s_rec[lane] = mr;
-    s_Q[lane] = P - s0;
-    float4* prow = reinterpret_cast<float4*>(part + lane * 32);
+    s_PQ[lane] = make_int2(P, P - s0);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) prow[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(part)[q * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __syncwarp();
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
     // lanes without a record (S == 0, only past the end of the last group) have P == T: they never start inside [0, T)
     float acc = 0.0f;
     unsigned colmask = 0;
-    int kcur = 0;          // the record `acc` belongs to
-    int started = 0;       // records whose first flat index lies before the current window (warp-uniform)
+    int kcur = 0, pcur = 0;     // the record `acc` belongs to and its first flat index
+    int started = 0;            // records whose first flat index lies before the current window (warp-uniform)
+    // record parameters of this lane's current record (re-read only when the record changes)
+    int kc = 0, pc = 0, qc = -s0;
+    double2 ca = make_double2(U, SU), cb = make_double2(V, SV);
+    {
+        const UamGroupRec r0 = s_rec[0];
+        const int2 pq0 = s_PQ[0];
+        ca = make_double2(r0.U, r0.SU); cb = make_double2(r0.V, r0.SV); pc = pq0.x; qc = pq0.y;
+    }
     for (int t0 = 0; t0 < T; t0 += 32 * TAPS) {
         UamTap<TF> tap[TAPS];
-        int kk[TAPS];
+        int kk[TAPS], pp[TAPS];
 #pragma unroll
         for (int j = 0; j < TAPS; ++j) {
             const int wb = t0 + 32 * j;
@@ -723,11 +736,17 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
             const unsigned starts = __reduce_or_sync(0xffffffffu, (rel < 32u && S > 0) ? (1u << rel) : 0u);
             const int k = started + __popc(starts & le_mask) - 1;
             started += __popc(starts);
+            if (k != kc) {
+                ca = *reinterpret_cast<const double2*>(&s_rec[k].U);
+                cb = *reinterpret_cast<const double2*>(&s_rec[k].V);
+                const int2 pq = s_PQ[k];
+                pc = pq.x; qc = pq.y;
+                kc = k;
+            }
             kk[j] = k;
-            const double2 a = *reinterpret_cast<const double2*>(&s_rec[k].U);
-            const double2 b = *reinterpret_cast<const double2*>(&s_rec[k].V);
-            const double sd = uam_int2double(wb + lane - s_Q[k]);
-            const double u = __dadd_rn(a.x, __dmul_rn(sd, a.y)), v = __dadd_rn(b.x, __dmul_rn(sd, b.y));
+            pp[j] = pc;
+            const double sd = uam_int2double(wb + lane - qc);
+            const double u = __dadd_rn(ca.x, __dmul_rn(sd, ca.y)), v = __dadd_rn(cb.x, __dmul_rn(sd, cb.y));
             if constexpr (TILE) uam_tap_load_tile<TF>(s_tile, ti0, tj0, rp, u, v, tap[j]);
             else uam_tap_load<TF, LAYOUT>(tex, rp, u, v, tap[j]);
         }
@@ -738,9 +757,11 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
             uam_tap_eval<TF>(rp, tap[j], pen, occ);
             const int k = kk[j];
             if (k != kcur) {
-                part[lane * 32 + (kcur ^ lane)] = acc;
+                const int row = (lane - pcur) & 31;          // record-local residue class of this lane's samples
+                part[row * 32 + (kcur ^ row)] = acc;
                 acc = 0.0f;
                 kcur = k;
+                pcur = pp[j];
             }
             if (t0 + 32 * j + lane < T) {
                 acc += pen;
@@ -748,19 +769,27 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
             }
         }
     }
-    part[lane * 32 + (kcur ^ lane)] = acc;
-    __syncwarp();
-    // per-record reduction: record s = sum over lanes of part[lane][s]; lane s keeps it
-    mine = 0.0f;
-#pragma unroll 4
-    for (int s = 0; s < 32; ++s) {
-        // rows are rotated by the record's offset so that position `lane` always holds the samples with record-local
-        // index == lane (mod 32): the sum is then independent of what else is in the group / batch
-        const int Ps = __shfl_sync(0xffffffffu, P, s);
-        const int row = (lane + Ps) & 31;
-        const float v = uam_warp_sum(part[row * 32 + (s ^ row)]);
-        if (lane == s) mine = v;
+    {
+        const int row = (lane - pcur) & 31;
+        part[row * 32 + (kcur ^ row)] = acc;
     }
+    __syncwarp();
+    // per-record sums: v[s] = this lane's residue class of record s; 32 x 32 transpose-reduce, pairing tree
+    // (l, l^16), (.., ^8), (.., ^4), (.., ^2), (.., ^1) like uam_warp_sum; lane s ends with the sum of record s
+    float v[32];
+#pragma unroll
+    for (int s = 0; s < 32; ++s) v[s] = part[lane * 32 + (s ^ lane)];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool hi = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = hi ? v[i] : v[i + o];
+            const float keep = hi ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    mine = v[0];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) colmask |= __shfl_xor_sync(0xffffffffu, colmask, o);
     collide = ((colmask >> lane) & 1u) != 0u;
@@ -768,7 +797,7 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
 }
 
 template <int TF, int LAYOUT>
-__global__ void __launch_bounds__(UAM_CTA_THREADS)
+__global__ void __launch_bounds__(UAM_CTA_THREADS, 4)
 uam_k_score_groups(unsigned long long n_seg, int Wp, UamRasterParams rp, const typename UamTexel<TF>::T* __restrict__ tex,
                    const double2* __restrict__ z, const unsigned* __restrict__ sorted_id, float* __restrict__ part_pen,
                    uint8_t* __restrict__ part_col) {
