@@ -102,6 +102,11 @@ __device__ __forceinline__ void uam_cell_frac1(double u, int n, int& j0, float& 
     j0 = min(max(__double2int_rd(u), 0), n - 2);
     f = uam_sat_f32(__dsub_rn(u, uam_int2double(j0)));
 }
+// the same for 0 <= u < n - 1 (caller's promise): neither clamp nor saturation can act, same bits
+__device__ __forceinline__ void uam_cell_frac1_inside(double u, int& j0, float& f) {
+    j0 = __double2int_rd(u);
+    f = (float)__dsub_rn(u, uam_int2double(j0));
+}
 
 // Occupancy bit-plane of the quad mode: one bit per cell, a 32-bit word = 8 x 4 cells, a 128-byte line = 4 x 8 words
 // = a 32 x 32-cell block (8192^2 cells = 8 MiB: L2-resident, mostly L1-resident along a path).
@@ -132,12 +137,17 @@ struct UamTap<8> {
     float fx, fy;
 };
 
-template <int TF, int LAYOUT>
+template <int TF, int LAYOUT, bool CLAMP = true>
 __device__ __forceinline__ void uam_tap_load(const typename UamTexel<TF>::T* __restrict__ tex, const UamRasterParams& rp,
                                              double u, double v, UamTap<TF>& t) {
     int i0, j0;
-    uam_cell_frac1(u, rp.W, j0, t.fx);
-    uam_cell_frac1(v, rp.H, i0, t.fy);
+    if constexpr (CLAMP) {
+        uam_cell_frac1(u, rp.W, j0, t.fx);
+        uam_cell_frac1(v, rp.H, i0, t.fy);
+    } else {
+        uam_cell_frac1_inside(u, j0, t.fx);
+        uam_cell_frac1_inside(v, i0, t.fy);
+    }
     if constexpr (TF == 8) {
         t.q = __ldg(tex + (uam_tex_row<4, LAYOUT>(i0, rp.row_stride) + uam_tex_col<4, LAYOUT>(j0)));
     } else if constexpr (TF == 1) {
@@ -678,49 +688,20 @@ template <int TF> struct UamTapsPerTrip { static const int N = 2; };
 template <> struct UamTapsPerTrip<1> { static const int N = 4; };
 template <> struct UamTapsPerTrip<8> { static const int N = 4; };
 
-// Scores one group.  In: this lane's record (first sample U/V, step SU/SV, S samples starting at sample number s0 of
-// its parent segment; S = 0 for a lane without a record).  Out: the record's sample sum (not yet divided by the
-// parent's sample count) and its collision bit.  TILE = 0: taps from global memory (tex); TILE = 1: taps from the
-// tile staged in shared memory.
-// Shared-memory traffic is what the LSU data pipe of this kernel is busiest with (ncu: 256 M shared wavefronts against
-// 111 M global ones per C3 launch before the three measures below): (1) the partials are zeroed with conflict-free
-// stores (each lane clearing its own row put all 32 lanes on the same 4 banks); (2) a lane re-reads the record
-// parameters only when its record changes; (3) a lane's partial for record k goes to the row of its record-local
-// residue class (lane - P_k) mod 32, so the final per-record sums are one 32 x 32 transpose-reduce (31 shuffles)
-// instead of 32 warp sums (160 shuffles) -- same pairing tree, same bits.
-template <int TF, int LAYOUT, int TILE>
-__device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const typename UamTexel<TF>::T* __restrict__ tex,
-                                                const unsigned char* s_tile, int ti0, int tj0, unsigned char* warp_smem,
-                                                const int lane, const double U, const double V, const double SU,
-                                                const double SV, const int S, const int s0, float& mine, bool& collide) {
+// The sample loop of uam_group_score.  CLAMP = false: the caller guarantees that every sample of the group lies
+// strictly inside the raster.
+template <int TF, int LAYOUT, int TILE, bool CLAMP>
+__device__ __forceinline__ void uam_group_samples(const UamRasterParams& rp, const typename UamTexel<TF>::T* __restrict__ tex,
+                                                  const unsigned char* s_tile, int ti0, int tj0, const UamGroupRec* s_rec,
+                                                  const int2* s_PQ, float* part, const int lane, const int P, const int S,
+                                                  const int T, float& acc, unsigned& colmask, int& kcur, int& pcur) {
     constexpr int TAPS = UamTapsPerTrip<TF>::N;
-    UamGroupRec* s_rec = reinterpret_cast<UamGroupRec*>(warp_smem);
-    int2* s_PQ = reinterpret_cast<int2*>(warp_smem + 32 * 32);       // {P_k, Q_k = P_k - s0_k}: flat index -> sample number
-    float* part = reinterpret_cast<float*>(warp_smem + 32 * 32 + 32 * 8);
-    int incl = S;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const int P = incl - S;
-    const int T = __shfl_sync(0xffffffffu, incl, 31);
-    UamGroupRec mr;
-    mr.U = U; mr.SU = SU; mr.V = V; mr.SV = SV;
-    s_rec[lane] = mr;
-    s_PQ[lane] = make_int2(P, P - s0);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(part)[q * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    __syncwarp();
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
     // lanes without a record (S == 0, only past the end of the last group) have P == T: they never start inside [0, T)
-    float acc = 0.0f;
-    unsigned colmask = 0;
-    int kcur = 0, pcur = 0;     // the record `acc` belongs to and its first flat index
     int started = 0;            // records whose first flat index lies before the current window (warp-uniform)
     // record parameters of this lane's current record (re-read only when the record changes)
-    int kc = 0, pc = 0, qc = -s0;
-    double2 ca = make_double2(U, SU), cb = make_double2(V, SV);
+    int kc = 0, pc = 0, qc = 0;
+    double2 ca, cb;
     {
         const UamGroupRec r0 = s_rec[0];
         const int2 pq0 = s_PQ[0];
@@ -745,10 +726,12 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
             }
             kk[j] = k;
             pp[j] = pc;
-            const double sd = uam_int2double(wb + lane - qc);
+            int si = wb + lane - qc;
+            if (!CLAMP && wb + lane >= T) si = 0;      // lanes past the end must stay inside the raster: any own sample
+            const double sd = uam_int2double(si);
             const double u = __dadd_rn(ca.x, __dmul_rn(sd, ca.y)), v = __dadd_rn(cb.x, __dmul_rn(sd, cb.y));
             if constexpr (TILE) uam_tap_load_tile<TF>(s_tile, ti0, tj0, rp, u, v, tap[j]);
-            else uam_tap_load<TF, LAYOUT>(tex, rp, u, v, tap[j]);
+            else uam_tap_load<TF, LAYOUT, CLAMP>(tex, rp, u, v, tap[j]);
         }
 #pragma unroll
         for (int j = 0; j < TAPS; ++j) {
@@ -769,6 +752,56 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
             }
         }
     }
+}
+
+// Scores one group.  In: this lane's record (first sample U/V, step SU/SV, S samples starting at sample number s0 of
+// its parent segment; S = 0 for a lane without a record).  Out: the record's sample sum (not yet divided by the
+// parent's sample count) and its collision bit.  TILE = 0: taps from global memory (tex); TILE = 1: taps from the
+// tile staged in shared memory.
+// Shared-memory traffic is what the LSU data pipe of this kernel is busiest with (ncu: 256 M shared wavefronts against
+// 111 M global ones per C3 launch before the three measures below): (1) the partials are zeroed with conflict-free
+// stores (each lane clearing its own row put all 32 lanes on the same 4 banks); (2) a lane re-reads the record
+// parameters only when its record changes; (3) a lane's partial for record k goes to the row of its record-local
+// residue class (lane - P_k) mod 32, so the final per-record sums are one 32 x 32 transpose-reduce (31 shuffles)
+// instead of 32 warp sums (160 shuffles) -- same pairing tree, same bits.
+template <int TF, int LAYOUT, int TILE>
+__device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const typename UamTexel<TF>::T* __restrict__ tex,
+                                                const unsigned char* s_tile, int ti0, int tj0, unsigned char* warp_smem,
+                                                const int lane, const double U, const double V, const double SU,
+                                                const double SV, const int S, const int s0, float& mine, bool& collide) {
+    UamGroupRec* s_rec = reinterpret_cast<UamGroupRec*>(warp_smem);
+    int2* s_PQ = reinterpret_cast<int2*>(warp_smem + 32 * 32);       // {P_k, Q_k = P_k - s0_k}: flat index -> sample number
+    float* part = reinterpret_cast<float*>(warp_smem + 32 * 32 + 32 * 8);
+    int incl = S;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int P = incl - S;
+    const int T = __shfl_sync(0xffffffffu, incl, 31);
+    UamGroupRec mr;
+    mr.U = U; mr.SU = SU; mr.V = V; mr.SV = SV;
+    s_rec[lane] = mr;
+    s_PQ[lane] = make_int2(P, P - s0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(part)[q * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncwarp();
+    // Fast path: when every record of the group lies strictly inside the raster (first and last sample in
+    // [0, W-1) x [0, H-1); the samples in between are monotone), the clamps and the saturation of the cell / fraction
+    // step cannot act and are left out (same bits).
+    bool rec_inside = true;
+    if (S > 0 && !TILE) {
+        const double ue = __dadd_rn(U, __dmul_rn(uam_int2double(S - 1), SU)), ve = __dadd_rn(V, __dmul_rn(uam_int2double(S - 1), SV));
+        const double wl = (double)(rp.W - 1), hl = (double)(rp.H - 1);
+        rec_inside = U >= 0.0 && U < wl && ue >= 0.0 && ue < wl && V >= 0.0 && V < hl && ve >= 0.0 && ve < hl;
+    }
+    const bool all_inside = !TILE && __all_sync(0xffffffffu, rec_inside);
+    float acc = 0.0f;
+    unsigned colmask = 0;
+    int kcur = 0, pcur = 0;     // the record `acc` belongs to and its first flat index
+    if (all_inside) uam_group_samples<TF, LAYOUT, TILE, false>(rp, tex, s_tile, ti0, tj0, s_rec, s_PQ, part, lane, P, S, T, acc, colmask, kcur, pcur);
+    else uam_group_samples<TF, LAYOUT, TILE, true>(rp, tex, s_tile, ti0, tj0, s_rec, s_PQ, part, lane, P, S, T, acc, colmask, kcur, pcur);
     {
         const int row = (lane - pcur) & 31;
         part[row * 32 + (kcur ^ row)] = acc;
