@@ -145,11 +145,10 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
         case UAM_OPT_TIME_KERNELS:
             UAM_CUDA(ctx, cudaSetDevice(ctx->device));
             if (value && !ctx->time_ev[0]) {
-                UAM_CUDA(ctx, cudaEventCreate(&ctx->time_ev[0]));
-                UAM_CUDA(ctx, cudaEventCreate(&ctx->time_ev[1]));
+                for (int i = 0; i < 2 * uam_ctx::kTimeRing; ++i) UAM_CUDA(ctx, cudaEventCreate(&ctx->time_ev[i]));
             }
             ctx->time_kernels = value ? 1 : 0;
-            ctx->time_pending = false;
+            ctx->time_pending = 0;
             ctx->time_sum_ms = 0.0;
             ctx->time_count = 0;
             return UAM_OK;
@@ -158,15 +157,29 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
     }
 }
 
-// Folds the pending event pair into the running sum (waits for the kernel).  Called before the events are re-recorded.
+// Folds the pending event pairs into the running sum (waits for the last timed kernel).  Called when the ring is full
+// and before a statistic is read -- never between two launches of a timed loop shorter than the ring.
 int uam_time_collect(uam_ctx* ctx) {
-    if (!ctx->time_pending) return UAM_OK;
-    float ms = 0.0f;
-    UAM_CUDA(ctx, cudaEventSynchronize(ctx->time_ev[1]));
-    UAM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->time_ev[0], ctx->time_ev[1]));
-    ctx->time_sum_ms += ms;
-    ctx->time_count += 1;
-    ctx->time_pending = false;
+    for (int i = 0; i < ctx->time_pending; ++i) {
+        float ms = 0.0f;
+        UAM_CUDA(ctx, cudaEventSynchronize(ctx->time_ev[2 * i + 1]));
+        UAM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->time_ev[2 * i], ctx->time_ev[2 * i + 1]));
+        ctx->time_sum_ms += ms;
+        ctx->time_count += 1;
+    }
+    ctx->time_pending = 0;
+    return UAM_OK;
+}
+
+int uam_time_begin(uam_ctx* ctx, cudaStream_t st) {
+    if (ctx->time_pending == uam_ctx::kTimeRing) UAM_TRY(uam_time_collect(ctx));
+    UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[2 * ctx->time_pending], st));
+    return UAM_OK;
+}
+
+int uam_time_end(uam_ctx* ctx, cudaStream_t st) {
+    UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[2 * ctx->time_pending + 1], st));
+    ctx->time_pending += 1;
     return UAM_OK;
 }
 
@@ -211,8 +224,8 @@ extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
         if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
         if (ctx->pipe_event[i]) cudaEventDestroy(ctx->pipe_event[i]);
     }
-    if (ctx->time_ev[0]) cudaEventDestroy(ctx->time_ev[0]);
-    if (ctx->time_ev[1]) cudaEventDestroy(ctx->time_ev[1]);
+    for (int i = 0; i < 2 * uam_ctx::kTimeRing; ++i)
+        if (ctx->time_ev[i]) cudaEventDestroy(ctx->time_ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return UAM_OK;

@@ -94,8 +94,11 @@ struct uam_ctx {
     size_t scratch_bytes = 0;
     // optional CUDA-event timing of the dominant scoring kernel (UAM_OPT_TIME_KERNELS), read by uam_ctx_get_stat
     int time_kernels = 0;
-    bool time_pending = false;
-    cudaEvent_t time_ev[2] = {};
+    // ring of event pairs: the timed kernel's begin / end are recorded on the launching stream and read back only when
+    // the ring is full or a statistic is asked for, so a timed loop never makes the host wait for the device
+    static constexpr int kTimeRing = 128;
+    cudaEvent_t time_ev[2 * kTimeRing] = {};
+    int time_pending = 0;
     double time_sum_ms = 0.0;
     uint64_t time_count = 0;
     long long grid_delta = 0;           // UAM_OPT_GRID_DELTA (0 = automatic)
@@ -132,6 +135,8 @@ int uam_make_params(uam_ctx* ctx, const double* h_p, int n_p, int flags, UamPara
 int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st);
 cudaStream_t uam_pick_stream(uam_ctx* ctx, void* stream);
 int uam_time_collect(uam_ctx* ctx);
+int uam_time_begin(uam_ctx* ctx, cudaStream_t st);
+int uam_time_end(uam_ctx* ctx, cudaStream_t st);
 
 #define UAM_CUDA(ctx, call)                                             \
     do {                                                                \

@@ -1356,14 +1356,12 @@ int uam_raster_launch_binned(uam_ctx* ctx, const void* texv, const double2* z, i
     const unsigned long long n_groups = (n_seg + 31) >> 5;
     const long long sctas = std::min<long long>((long long)((n_groups + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA), (long long)ctx->sm_count * 16);
     if (ctx->time_kernels && slot == 0) {
-        UAM_TRY(uam_time_collect(ctx));
-        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
+        UAM_TRY(uam_time_begin(ctx, st));
     }
     uam_k_score_groups<TF, LAYOUT><<<(unsigned)sctas, UAM_CTA_THREADS, gsmem, st>>>(n_seg, Wp, rp, (const T*)texv, z, sorted_id, part_pen, part_col);
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_groups");
     if (ctx->time_kernels && slot == 0) {
-        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
-        ctx->time_pending = true;
+        UAM_TRY(uam_time_end(ctx, st));
     }
     const long long rctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
     uam_k_reduce_paths<<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, d_cost, d_collide, d_nsamp);
@@ -1440,16 +1438,14 @@ int uam_raster_launch_tiles(uam_ctx* ctx, const void* texv, uint64_t tex_key, co
     const size_t smem = (size_t)((tg.copy_bytes + 127u) & ~127u) + UAM_TILE_CTL_BYTES + (size_t)UAM_GROUP_SMEM * UAM_WARPS_PER_CTA;
     UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_score_tiles<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ctx->time_kernels && slot == 0) {
-        UAM_TRY(uam_time_collect(ctx));
-        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
+        UAM_TRY(uam_time_begin(ctx, st));
     }
     // after the scatter cursor[t] is the END of tile t's pieces
     uam_k_score_tiles<TF><<<(unsigned)(ctx->sm_count * 2), UAM_CTA_THREADS, smem, st>>>(rp, tg, (const unsigned char*)ctx->d_tiles, cursor, items,
                                                                                     counters, recs, part_pen, part_col);
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_tiles");
     if (ctx->time_kernels && slot == 0) {
-        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
-        ctx->time_pending = true;
+        UAM_TRY(uam_time_end(ctx, st));
     }
     const long long rctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
     uam_k_reduce_slots<<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, path_base, part_pen, part_col, d_cost, d_collide, d_nsamp);
@@ -1464,8 +1460,7 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
     const T* tex = (const T*)texv;
     const bool timed = ctx->time_kernels && slot == 0 && !(rp.spc > 0.0 && rp.variant >= 2);
     if (timed) {
-        UAM_TRY(uam_time_collect(ctx));
-        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[0], st));
+        UAM_TRY(uam_time_begin(ctx, st));
     }
     if constexpr (UamIsQuad<TF>::v) {
         if (rp.spc > 0.0 && rp.variant < 2) return uam_fail(ctx, UAM_ERR_STATE, "quad texels are not sampled by the warp-per-path integral kernels");
@@ -1476,8 +1471,7 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
         uam_k_score_raster_wp<TF, LAYOUT><<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, tex, d_cost, d_collide, d_nsamp);
         UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_wp");
         if (timed) {
-            UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
-            ctx->time_pending = true;
+            UAM_TRY(uam_time_end(ctx, st));
         }
       }
         return UAM_OK;
@@ -1506,8 +1500,7 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
     }
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_raster_int");
     if (timed) {
-        UAM_CUDA(ctx, cudaEventRecord(ctx->time_ev[1], st));
-        ctx->time_pending = true;
+        UAM_TRY(uam_time_end(ctx, st));
     }
   }
     return UAM_OK;
