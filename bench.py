@@ -119,7 +119,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append([c.strip() for c in line.split(',')] + [time.time()])
+
+    def window(self, t0, t1):
+        """keep the samples taken inside [t0, t1] (the timed region); all of them if none fell inside"""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
@@ -130,6 +134,10 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        t0, t1 = getattr(self, 't0', None), getattr(self, 't1', None)
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 <= r[-1] <= t1 + 0.06]
+            self.rows = inside or self.rows
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -242,19 +250,20 @@ def run_ours(args):
     _, _, ns = rm.score_paths(Z, WEIGHTS, SPC, True, None, want_nsamples=True)
     total_samples = int(ns.sum().item())
     del ns
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()              # polling already while the warm-up runs; only the samples of the timed region are kept
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = eng.launch_count()
     eng.set_option('time_kernels', 1)      # CUDA events around the dominant scoring kernel, on the launching stream
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    wall0 = time.time()
     t_start.record()
     for s in range(args.steps):
         k_ev[s][0].record()
@@ -265,6 +274,7 @@ def run_ours(args):
             dist.all_reduce(key, op=dist.ReduceOp.MIN)
     t_end.record()
     torch.cuda.synchronize()
+    clocks.window(wall0, time.time())
     if world > 1:
         dist.barrier()
     launches = eng.launch_count() - launches0
@@ -388,7 +398,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--raster', type=int, default=RASTER)

@@ -93,12 +93,17 @@ enum {
                                          CUDA events on the caller's stream (resets the statistics) */
     UAM_OPT_GRID_DELTA = 6,           /* grid search: width of the distance window relaxed per round (0 = automatic: the cost
                                          of crossing one 32-cell tile at the mean cell cost); ordering only, same results */
-    UAM_OPT_COMBINE_LAYERS = 5        /* 1 (default): large-batch integral mode samples "quad texels": the layers are folded
+    UAM_OPT_COMBINE_LAYERS = 5,       /* 1 (default): large-batch integral mode samples "quad texels": the layers are folded
                                          into ONE layer sum_l w_l * layer_l (the penalty is linear in the layers) and every
                                          cell stores its 2 x 2 bilinear footprint as one float4, so a tap is one 16-byte
                                          load; occupancy flags ride in the sign bits when all values are >= 0, else in a
                                          bit-plane.  Rebuilt when the weights or the raster change.  2: as 1 but always the
                                          bit-plane form.  0: always sample every layer texel by texel */
+    UAM_OPT_HOST_CHUNKS = 7,          /* uam_score_paths_raster_host: chunks per call flowing through the copy / score
+                                         pipeline (0 = default 4) */
+    UAM_OPT_HOST_TAPER = 8            /* ... chunk sizes change linearly from the first to the last chunk: t > 0 the last chunk
+                                         is t percent smaller than the first, t < 0 the first is |t| percent smaller than the
+                                         last, 0 (default) equal chunks; -95 .. 95 */
 };
 /* statistics of UAM_OPT_TIME_KERNELS: mean device time (ms) of the dominant scoring kernel (uam_k_score_tiles / uam_k_score_groups /
  * uam_k_score_raster_int / uam_k_score_raster_wp) over the timed calls, and their number */

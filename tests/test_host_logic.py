@@ -155,6 +155,15 @@ def test_shard_range_and_keys():
     assert udist.encode_key(2.5, 101) == k and 0 <= k < 2 ** 63
     assert udist.host_best_key(np.zeros(0)) == udist.KEY_EMPTY
     assert udist.global_best(k) == (2.5, 101)          # no process group: identity
+    # the argmin shortcut and the bit-pattern keys agree, also with zeros / NaN / inf in the vector (key order:
+    # 0 < positive < inf < NaN, ties to the smaller index)
+    rng = np.random.default_rng(3)
+    for special in ([], [0.0], [np.nan], [np.inf, np.nan], [0.0, 0.0, np.nan]):
+        c = rng.random(257).astype(np.float32) + np.float32(0.25)
+        c[rng.choice(257, len(special), replace=False)] = special
+        keys = (c.view(np.uint32).astype(np.uint64) << np.uint64(32)) | (np.arange(257, dtype=np.uint64) + np.uint64(7))
+        assert udist.host_best_key(c, 7) == int(keys.min())
+    assert udist.decode_key(udist.host_best_key(np.array([np.nan, 3.0, 1.0], dtype=np.float32)))[1] == 2
 
 
 _GLOO_WORKER = r'''

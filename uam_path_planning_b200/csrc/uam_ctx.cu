@@ -111,6 +111,7 @@ extern "C" int uam_ctx_create(int device, uam_ctx** out) {
     if (const char* e = getenv("UAM_NO_SIGN_PACK")) ctx->no_sign_pack = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_COMBINE_LAYERS")) ctx->combine_layers = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_HOST_CHUNKS")) ctx->host_chunks = std::max(0, atoi(e));
+    if (const char* e = getenv("UAM_HOST_TAPER")) ctx->host_taper = std::min(95, std::max(-95, atoi(e)));
     if (const char* e = getenv("UAM_L2_FETCH_GRANULARITY")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
     *out = ctx;
     return UAM_OK;
@@ -141,6 +142,14 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             ctx->combine_layers = value != 0;
             ctx->no_sign_pack = value == 2;
             ctx->comb_valid = false;
+            return UAM_OK;
+        case UAM_OPT_HOST_CHUNKS:
+            if (value < 0 || value > 64) return uam_fail(ctx, UAM_ERR_INVALID, "host chunks must be 0 (default) .. 64");
+            ctx->host_chunks = (int)value;
+            return UAM_OK;
+        case UAM_OPT_HOST_TAPER:
+            if (value < -95 || value > 95) return uam_fail(ctx, UAM_ERR_INVALID, "host taper must be -95 .. 95 percent");
+            ctx->host_taper = (int)value;
             return UAM_OK;
         case UAM_OPT_TIME_KERNELS:
             UAM_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -1693,12 +1693,32 @@ extern "C" int uam_score_paths_raster_host(uam_ctx* ctx, const double* h_z, int6
     UAM_CUDA(ctx, cudaDeviceSynchronize());
     UAM_TRY(uam_raster_precompute(ctx, &rp, B, N, ctx->pipe_stream[0]));
     const size_t row = (size_t)2 * (N + 2) * sizeof(double);
-    const int n_chunks = ctx->host_chunks > 0 ? ctx->host_chunks : 4;      // measured on C3: 3 / 4 / 6 / 8 / 12 chunks -> 4.70 / 4.42 / 4.68 / 4.92 / 5.29 ms
-    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>((B + n_chunks - 1) / n_chunks, (int64_t)((64u << 20) / row)));
-    int c = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++c) {
-        const int s = c % UAM_HOST_PIPE_DEPTH;
-        const int64_t nb = std::min(chunk, B - b0);
+    // The pipeline is bound by the kernels (a chunk scores a little slower than it uploads: binning a quarter of the batch
+    // streams the raster through L2 once more), so a call lasts about upload(first chunk) + sum of the kernel times.
+    // Chunk sizes may change linearly from the first to the last chunk (taper > 0: shrinking, < 0: growing).
+    const int n_chunks = (int)std::min<int64_t>(ctx->host_chunks > 0 ? ctx->host_chunks : 4, std::max<int64_t>(1, B / 1024));
+    const double taper = ctx->host_taper / 100.0;
+    auto weight = [&](int c) {
+        const double x = n_chunks > 1 ? (double)c / (n_chunks - 1) : 0.0;
+        return taper >= 0.0 ? 1.0 - taper * x : 1.0 + taper * (1.0 - x);
+    };
+    const int64_t max_rows = std::max<int64_t>(1024, (int64_t)((96u << 20) / row));
+    std::vector<int64_t> bounds(1, 0);
+    {
+        double wsum = 0.0, acc = 0.0;
+        for (int c = 0; c < n_chunks; ++c) wsum += weight(c);
+        for (int c = 0; c < n_chunks; ++c) {
+            acc += weight(c) / wsum;
+            int64_t e = c + 1 == n_chunks ? B : std::min<int64_t>(B, (int64_t)(acc * (double)B));
+            while (e - bounds.back() > max_rows) bounds.push_back(bounds.back() + max_rows);   // staging stays bounded
+            if (e > bounds.back()) bounds.push_back(e);
+        }
+    }
+    int64_t chunk = 0;
+    for (size_t c = 0; c + 1 < bounds.size(); ++c) chunk = std::max(chunk, bounds[c + 1] - bounds[c]);
+    for (size_t c = 0; c + 1 < bounds.size(); ++c) {
+        const int s = (int)(c % UAM_HOST_PIPE_DEPTH);
+        const int64_t b0 = bounds[c], nb = bounds[c + 1] - bounds[c];
         cudaStream_t st = ctx->pipe_stream[s];
         UAM_TRY(uam_reserve(ctx, &ctx->d_stage_in[s], &ctx->stage_in_bytes[s], (size_t)chunk * row));
         UAM_TRY(uam_reserve(ctx, &ctx->d_stage_out[s], &ctx->stage_out_bytes[s], (size_t)chunk * 8));

@@ -40,6 +40,9 @@ def host_best_key(cost: np.ndarray, global_offset: int = 0) -> int:
     cost = np.asarray(cost, dtype=np.float32)
     if cost.size == 0:
         return KEY_EMPTY
+    i = int(np.argmin(cost))            # first minimum = smallest index on ties, like the key order
+    if cost[i] > 0.0:                   # strictly positive and not NaN: the float order is the bit-pattern order
+        return encode_key(cost[i], i + int(global_offset))
     keys = (cost.view(np.uint32).astype(np.uint64) << np.uint64(32)) | (
         (np.arange(cost.size, dtype=np.uint64) + np.uint64(global_offset)) & np.uint64(0xFFFFFFFF))
     return int(keys.min())
