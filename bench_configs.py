@@ -101,7 +101,7 @@ def main():
     ap.add_argument('--c5-queries', type=int, default=16)
     ap.add_argument('--c5-queries-bands', type=int, default=4)
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--only', default='', help="'c5': run only the grid-search config")
+    ap.add_argument('--only', default='', help="'c2' / 'c5': run only that config")
     args = ap.parse_args()
     import torch
     import uam_path_planning_b200 as uam
@@ -162,10 +162,23 @@ def main():
         out[f'{name}_integral_e2e_ms'] = (time.perf_counter() - t0) * 100
     Z = torch.from_numpy(Zc).to(dev)
     ms = ev_time(torch, lambda: prob.score(Z), 10, 2)
+    eng_a = prob.map.engine()
+    eng_a.set_option('shape_grid', 0)
+    ms_all = ev_time(torch, lambda: prob.score(Z), 10, 2)
+    eng_a.set_option('shape_grid', 1)
+    ms = ev_time(torch, lambda: prob.score(Z), 10, 2)
+    ms_g = ev_time(torch, lambda: prob.score(Z, want_g=True), 10, 2)
+    ms_grad = ev_time(torch, lambda: prob.get_cost_gradient(Z), 10, 2)
     out['analytic_corridor'] = {'ms': ms, 'value': B * (Wp - 1) / (ms * 1e-3), 'shapes': 256 + 32,
-                                'note': 'fp64 analytic scorer (Problem.get_cost + collides), compute-bound'}
+                                'ms_every_shape_at_every_point': ms_all, 'ms_with_constraint_vector': ms_g,
+                                'ms_cost_and_gradient': ms_grad,
+                                'shape_grid_cells': eng_a.get_stat('shape_grid_cells'),
+                                'shape_grid_items': eng_a.get_stat('shape_grid_items'),
+                                'note': 'fp64 analytic scorer (Problem.get_cost + collides) with per-cell candidate lists over the shapes'}
     print(json.dumps(out))
     del rm, Z
+    if args.only == 'c2':
+        return
 
     if args.skip_c4:
         run_c5(args, torch, uam, dev)

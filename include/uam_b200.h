@@ -101,16 +101,21 @@ enum {
                                          bit-plane form.  0: always sample every layer texel by texel */
     UAM_OPT_HOST_CHUNKS = 7,          /* uam_score_paths_raster_host: chunks per call flowing through the copy / score
                                          pipeline (0 = default 4) */
-    UAM_OPT_HOST_TAPER = 8            /* ... chunk sizes change linearly from the first to the last chunk: t > 0 the last chunk
+    UAM_OPT_HOST_TAPER = 8,           /* ... chunk sizes change linearly from the first to the last chunk: t > 0 the last chunk
                                          is t percent smaller than the first, t < 0 the first is |t| percent smaller than the
                                          last, 0 (default) equal chunks; -95 .. 95 */
+    UAM_OPT_SHAPE_GRID = 9            /* 1 (default): the analytic scorer / point queries look up per-cell candidate lists over
+                                         the shapes (a shape with one inequality > max(e, 1e-14) on a whole cell contributes
+                                         exact zeros there and is left out; same bits).  0: every shape at every point */
 };
 /* statistics of UAM_OPT_TIME_KERNELS: mean device time (ms) of the dominant scoring kernel (uam_k_score_tiles / uam_k_score_groups /
  * uam_k_score_raster_int / uam_k_score_raster_wp) over the timed calls, and their number */
 enum { UAM_STAT_SCORE_KERNEL_MS_MEAN = 1, UAM_STAT_SCORE_KERNEL_COUNT = 2,
        /* counted work of the last uam_grid_search*: tile activations, double sweeps (one = 64 row steps of 32 cells, each
           relaxing the 8 in-plane edges of its cells), relaxation rounds */
-       UAM_STAT_GRID_ACTIVATIONS = 3, UAM_STAT_GRID_SWEEPS = 4, UAM_STAT_GRID_ROUNDS = 5 };
+       UAM_STAT_GRID_ACTIVATIONS = 3, UAM_STAT_GRID_SWEEPS = 4, UAM_STAT_GRID_ROUNDS = 5,
+       /* shape grid of the analytic scorer (UAM_OPT_SHAPE_GRID) as last built: cells (0 = none) and list entries in all */
+       UAM_STAT_SHAPE_GRID_CELLS = 6, UAM_STAT_SHAPE_GRID_ITEMS = 7 };
 int uam_ctx_get_stat(uam_ctx* ctx, int stat, double* value);
 int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value);
 

@@ -781,3 +781,89 @@ def test_grid_search_4096_vs_c_oracle(uam, torch):
         d_ref, p_ref = occ.grid_search(cost.cpu().numpy(), srcs, blk.cpu().numpy())
         assert np.array_equal(dist.cpu().numpy(), d_ref)
         assert np.array_equal(parent.cpu().numpy(), p_ref)
+
+
+@pytest.mark.gpu
+def test_shape_grid_changes_no_bit(uam, torch):
+    """The analytic scorer's per-cell candidate lists (UAM_OPT_SHAPE_GRID) leave out only shapes that contribute exact
+    zeros: cost, collision flags, the whole constraint vector, the point queries and the gradient are bit-identical
+    with the grid on and off -- for points inside / outside the grid, non-finite points, zero / negative weights,
+    positive / negative enlargement and a shape whose centre normaliser is 0 (the reference's 0/0 = NaN everywhere)."""
+    rng = np.random.default_rng(23)
+
+    def rand_shape(span):
+        k = rng.integers(3)
+        c = rng.uniform(-span, span, 2)
+        if k == 0:
+            ang = np.sort(rng.uniform(0, 2 * np.pi, rng.integers(3, 8)))
+            r = rng.uniform(0.5, 4)
+            V = np.stack([c[0] + r * np.cos(ang), c[1] + 0.7 * r * np.sin(ang)], 1)
+            return {'kind': 'polygon', 'verts': V.tolist()}
+        if k == 1:
+            return {'kind': 'ball', 'center': c.tolist(), 'r1': float(rng.uniform(0.5, 3)), 'r2': float(rng.uniform(0.5, 3))}
+        return {'kind': 'square', 'center': c.tolist(), 'r1': float(rng.uniform(0.5, 3)), 'r2': float(rng.uniform(0.5, 3))}
+
+    regions = [('A', []), ('B', []), ('C', [])]
+    for _ in range(300):
+        regions[rng.integers(3)][1].append(rand_shape(32))
+    spec = {'obstacles': [rand_shape(32) for _ in range(40)], 'regions': regions, 'x_start': [-30.0, -29.0],
+            'x_goal': [31.0, 28.0], 'options': {}, 'maxratio': 1.3, 'maxalpha': 0.3, 'enlargement': 0.0,
+            'weights': [3.0, 70.0, 1.0]}
+    N = 62
+    Z = np.stack([full_paths(spec, orc.create_x_init(spec['x_start'], spec['x_goal'], N, d))[0]
+                  for d in rng.uniform(-0.9, 0.9, 256)])
+    Z[:, 2:-2] += rng.normal(0, 0.8, (256, 2 * N))
+    Z[3, 10:14] = [1e3, -1e3, 5e8, 0.0]            # far outside the grid
+    Z[5, 20] = np.nan
+    Z[6, 31] = np.inf
+    Z[7, 40:42] = [1e200, -1e200]
+    X = np.concatenate([rng.uniform(-40, 40, (4000, 2)), [[np.nan, 0.0], [0.0, np.inf], [1e150, 1e150], [-36.0, 36.0]]])
+    om = orc.OMap(spec)
+    # reference defaults (obstacle_smooth off: the lists serve the obstacles' `contains` only) and main.py's options
+    for e, weights, opts in [(0.0, [3.0, 70.0, 1.0], {}), (0.0, [3.0, 70.0, 1.0], {'obstacle_smooth': True, 'length_smooth': True}),
+                             (0.4, [3.0, 0.0, -2.0], {'obstacle_smooth': True}), (-1e-4, [1.0, 1.0, 1.0], {}),
+                             (-0.3, [1.0, 1.0, 1.0], {})]:      # -0.3: small shapes shrink to nothing, psi(centre) = 0, NaN everywhere
+        prob = build_product_problem(spec, N, options=opts, weights=weights, enlargement=e)
+        eng = prob.map.engine()
+        res = {}
+        for grid in (1, 0):
+            eng.set_option('shape_grid', grid)
+            inside = prob.map.collides(X)         # before the first scoring call: no grid yet; later: whatever grid there is
+            cost, col, g = prob.score(Z, want_g=True)
+            assert np.array_equal(inside, prob.map.collides(X))
+            cost2, col2, _ = prob.score(Z)          # without the constraint vector: the obstacle loop walks the list only
+            assert np.array_equal(cost, cost2, equal_nan=True) and np.array_equal(col, col2)
+            pts = eng.eval_points(X, prob.parameter_vector(), prob.flags())
+            c3, grad = prob.get_cost_gradient(Z)
+            res[grid] = (cost, col, g, pts['region'], pts['obstacle'], pts['collide'], c3, grad)
+            cells, items = eng.get_stat('shape_grid_cells'), eng.get_stat('shape_grid_items')
+            assert (cells > 0) == bool(grid)
+            if grid and abs(e) < 1e-3:  # (e > 0 moves an un-normalised polygon edge out by e / |edge|: long lists, legitimately)
+                assert items / cells < 12, 'candidate lists are short'       # 340 shapes in all
+        for a, b in zip(res[1], res[0]):
+            assert np.array_equal(a, b, equal_nan=True)
+        ok = np.isfinite(Z).all(axis=1)
+        np.testing.assert_allclose(res[1][0][ok], orc.get_cost(om, Z[ok], N, weights, e, opts), rtol=RTOL_ANALYTIC)
+        assert np.array_equal(res[1][1][ok].astype(bool), orc.path_collides(om, Z[ok], N))
+        assert np.array_equal(res[1][5].astype(bool), inside)
+    # a region shape with psi(centre) = 0 (centre on its own boundary after shrinking): NaN for every point, grid or not
+    spec2 = dict(spec, regions=[('A', regions[0][1][:20] + [{'kind': 'ball', 'center': [0.0, 0.0], 'r1': 1.0, 'r2': 1.0}]),
+                                ('B', regions[1][1][:20])], weights=[2.0, 5.0])
+    prob = build_product_problem(spec2, N, enlargement=-1.0)       # (0 - 1) - (-1) = 0 at the ball's centre
+    eng = prob.map.engine()
+    out = {}
+    for grid in (1, 0):
+        eng.set_option('shape_grid', grid)
+        out[grid] = (prob.get_cost(Z), eng.eval_points(X, prob.parameter_vector(), prob.flags())['region'])
+    assert np.isnan(out[0][0]).all() and np.isnan(out[0][1][:, 0]).all()
+    for a, b in zip(out[1], out[0]):
+        assert np.array_equal(a, b, equal_nan=True)
+    # non-smooth penalties / infinite weights: the grid is not consulted (same results as with the option off)
+    prob = build_product_problem(spec, N, options={'obstacle_smooth': False})
+    eng = prob.map.engine()
+    eng.set_option('shape_grid', 1)
+    g1 = prob.score(Z[:32], want_g=True)
+    eng.set_option('shape_grid', 0)
+    g0 = prob.score(Z[:32], want_g=True)
+    for a, b in zip(g1, g0):
+        assert np.array_equal(a, b, equal_nan=True)

@@ -151,6 +151,12 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             if (value < -95 || value > 95) return uam_fail(ctx, UAM_ERR_INVALID, "host taper must be -95 .. 95 percent");
             ctx->host_taper = (int)value;
             return UAM_OK;
+        case UAM_OPT_SHAPE_GRID:
+            if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "shape grid must be 0 or 1");
+            ctx->shape_grid_opt = (int)value;
+            ctx->psic_valid = false;        // rebuilt (or dropped) with the next analytic call
+            ctx->shape_grid = UamShapeGrid{};
+            return UAM_OK;
         case UAM_OPT_TIME_KERNELS:
             UAM_CUDA(ctx, cudaSetDevice(ctx->device));
             if (value && !ctx->time_ev[0]) {
@@ -206,6 +212,8 @@ extern "C" int uam_ctx_get_stat(uam_ctx* ctx, int stat, double* value) {
         case UAM_STAT_GRID_ACTIVATIONS: *value = ctx->grid_activations; return UAM_OK;
         case UAM_STAT_GRID_SWEEPS: *value = ctx->grid_sweeps; return UAM_OK;
         case UAM_STAT_GRID_ROUNDS: *value = ctx->grid_rounds; return UAM_OK;
+        case UAM_STAT_SHAPE_GRID_CELLS: *value = (double)ctx->shape_grid.G * ctx->shape_grid.G; return UAM_OK;
+        case UAM_STAT_SHAPE_GRID_ITEMS: *value = ctx->shape_grid.G ? (double)ctx->grid_items_total : 0.0; return UAM_OK;
         default:
             return uam_fail(ctx, UAM_ERR_INVALID, "unknown stat %d", stat);
     }
@@ -218,6 +226,8 @@ extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
     cudaFree(ctx->d_edges);
     cudaFree(ctx->d_shapes);
     cudaFree(ctx->d_psic);
+    cudaFree(ctx->d_grid_start);
+    cudaFree(ctx->d_grid_items);
     cudaFree(ctx->d_tex);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_cull_scratch);
@@ -282,6 +292,26 @@ extern "C" int uam_map_set_shapes(uam_ctx* ctx, const double* h_edges, int n_edg
     }
     bool finite = true;
     for (size_t i = 0; i < 8 * (size_t)n_edges; ++i) finite = finite && std::isfinite(h_edges[i]);
+    // bounding box of the shapes as far as the records tell (polygon vertices, ellipse / box extents): the extent of
+    // the analytic scorer's shape grid.  Points outside it are scored with the full loops, so it only has to be sensible.
+    double bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
+    for (int i = 0; i < n_edges && finite; ++i) {
+        const double* r = h_edges + 8 * (size_t)i;
+        const int k = (int)r[0];
+        if (k == UAM_EDGE_LINE) {
+            bx0 = std::min(bx0, std::min(r[1], r[1] + r[3])); bx1 = std::max(bx1, std::max(r[1], r[1] + r[3]));
+            by0 = std::min(by0, std::min(r[2], r[2] + r[4])); by1 = std::max(by1, std::max(r[2], r[2] + r[4]));
+        } else if (k == UAM_EDGE_ELLIPSE) {
+            bx0 = std::min(bx0, r[1] - std::fabs(r[3])); bx1 = std::max(bx1, r[1] + std::fabs(r[3]));
+            by0 = std::min(by0, r[2] - std::fabs(r[4])); by1 = std::max(by1, r[2] + std::fabs(r[4]));
+        } else if ((int)r[1] == 0) {
+            bx0 = std::min(bx0, r[3] - std::fabs(r[4])); bx1 = std::max(bx1, r[3] + std::fabs(r[4]));
+        } else {
+            by0 = std::min(by0, r[3] - std::fabs(r[4])); by1 = std::max(by1, r[3] + std::fabs(r[4]));
+        }
+    }
+    ctx->shape_bbox[0] = bx0; ctx->shape_bbox[1] = bx1; ctx->shape_bbox[2] = by0; ctx->shape_bbox[3] = by1;
+    ctx->shape_grid = UamShapeGrid{};
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
 
     // device order: obstacles (insertion order), then regions 0..R-1 (insertion order inside each)
@@ -354,6 +384,7 @@ int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st) {
                                                                        prm.flags, prm.e, ctx->d_psic);
         UAM_CHECK_LAUNCH(ctx, "uam_k_shape_norm");
         UAM_CUDA(ctx, cudaStreamSynchronize(st));
+        UAM_TRY(uam_build_shape_grid(ctx, prm.e, prm.flags, st));
     }
     ctx->psic_valid = true;
     ctx->psic_e = prm.e;

@@ -52,7 +52,7 @@ __device__ __forceinline__ double uam_psi_grad(const UamEdge* __restrict__ edges
 }
 
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
-uam_k_grad_analytic(const double2* __restrict__ z, long long B, int N, UamParams prm, UamRegionRanges3 rr,
+uam_k_grad_analytic(const double2* __restrict__ z, long long B, int N, UamParams prm, UamRegionRanges3 rr, UamShapeGrid sg,
                     const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes,
                     const double* __restrict__ psic, double* __restrict__ cost, double2* __restrict__ grad) {
     const int lane = threadIdx.x & 31;
@@ -69,22 +69,39 @@ uam_k_grad_analytic(const double2* __restrict__ z, long long B, int N, UamParams
             const double2 p = zp[j];
             // ---- penalty term and its gradient at z_j ----
             double P = 0.0, Gx = 0.0, Gy = 0.0;
-            for (int r = 0; r < prm.n_regions; ++r) {
-                double tot = 0.0, tx = 0.0, ty = 0.0;
-                for (int s = rr.begin[r]; s < rr.begin[r + 1]; ++s) {
-                    const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
-                    double gx, gy;
-                    const double psi = uam_psi_grad(edges, meta.x, meta.y, p.x, p.y, prm.e, gx, gy);
-                    const double pc = meta.w ? __ldg(psic + s) : 1.0;
-                    if (psi != 0.0 || pc == 0.0 || pc != pc) {
-                        tot += psi / pc;
-                        tx += gx / pc;
-                        ty += gy / pc;
-                    }
+            auto add_shape = [&](int s, double& tot, double& tx, double& ty) {
+                const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
+                double gx, gy;
+                const double psi = uam_psi_grad(edges, meta.x, meta.y, p.x, p.y, prm.e, gx, gy);
+                const double pc = meta.w ? __ldg(psic + s) : 1.0;
+                if (psi != 0.0 || pc == 0.0 || pc != pc) {
+                    tot += psi / pc;
+                    tx += gx / pc;
+                    ty += gy / pc;
                 }
-                P += prm.w[r] * tot;
-                Gx += prm.w[r] * tx;
-                Gy += prm.w[r] * ty;
+            };
+            const int cell = uam_shape_grid_cell(sg, p.x, p.y);
+            if (cell < 0) {
+                for (int r = 0; r < prm.n_regions; ++r) {
+                    double tot = 0.0, tx = 0.0, ty = 0.0;
+                    for (int s = rr.begin[r]; s < rr.begin[r + 1]; ++s) add_shape(s, tot, tx, ty);
+                    P += prm.w[r] * tot;
+                    Gx += prm.w[r] * tx;
+                    Gy += prm.w[r] * ty;
+                }
+            } else {
+                // shape grid: only the cell's candidates, region by region (the shapes left out have psi = 0 and grad = 0)
+                int li = __ldg(sg.start + cell);
+                const int l1 = __ldg(sg.start + cell + 1);
+                while (li < l1 && __ldg(sg.items + li) < rr.begin[0]) ++li;          // hard obstacles are not in the cost
+                while (li < l1) {
+                    const int r = __ldg(&shapes[__ldg(sg.items + li)].region);
+                    double tot = 0.0, tx = 0.0, ty = 0.0;
+                    for (; li < l1 && __ldg(sg.items + li) < rr.begin[r + 1]; ++li) add_shape(__ldg(sg.items + li), tot, tx, ty);
+                    P += prm.w[r] * tot;
+                    Gx += prm.w[r] * tx;
+                    Gy += prm.w[r] * ty;
+                }
             }
             pen_sum += P / dN;
             Gx /= dN;
@@ -141,7 +158,7 @@ extern "C" int uam_grad_paths_analytic(uam_ctx* ctx, const double* d_z, int64_t 
     UamRegionRanges3 rr;
     for (int r = 0; r <= ctx->n_regions; ++r) rr.begin[r] = ctx->region_begin[r];
     const long long ctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 8);
-    uam_k_grad_analytic<<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(reinterpret_cast<const double2*>(d_z), B, N, prm, rr, ctx->d_edges,
+    uam_k_grad_analytic<<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(reinterpret_cast<const double2*>(d_z), B, N, prm, rr, uam_pick_shape_grid(ctx, prm), ctx->d_edges,
                                                                     ctx->d_shapes, ctx->d_psic, d_cost, reinterpret_cast<double2*>(d_grad));
     UAM_CHECK_LAUNCH(ctx, "uam_k_grad_analytic");
     return UAM_OK;

@@ -39,6 +39,17 @@ struct UamParams {
     int n_regions;
 };
 
+// Cell lists over the shapes for the analytic scorer (uam_shape_grid.cu): cell (cy, cx) of a G x G grid over the shapes'
+// bounding box holds, in ascending device order, every shape that can contribute a non-zero penalty / constraint term or
+// contain a point anywhere in the cell; all other shapes contribute exact zeros there.  G == 0: no grid (evaluate all).
+struct UamShapeGrid {
+    double gx0, gy0, inv_cw, inv_ch;
+    int G;
+    int obs_values;       // 1: the obstacles' psi values may come from the lists too (obstacle_smooth); 0: only `contains`
+    const int* start;     // G * G + 1 offsets into items
+    const int* items;
+};
+
 struct UamRasterGeo {
     double x0, dx, y0, dy;
     int H, W, L;
@@ -75,6 +86,14 @@ struct uam_ctx {
     bool psic_valid = false;
     double psic_e = 0.0;
     int psic_flags = -1;
+    // shape grid of the analytic scorer (rebuilt with psic: it depends on the enlargement)
+    int shape_grid_opt = 1;             // UAM_OPT_SHAPE_GRID
+    double shape_bbox[4] = {};          // x0, x1, y0, y1 of all shapes (host, from the records); x0 > x1: none
+    int* d_grid_start = nullptr;
+    int* d_grid_items = nullptr;
+    size_t grid_start_bytes = 0, grid_items_bytes = 0;
+    UamShapeGrid shape_grid = {};       // G == 0 until built / when disabled
+    int grid_items_total = 0;
 
     // raster
     void* d_tex = nullptr;              // float2 / float4 texels, row-major (H, W)
@@ -134,6 +153,9 @@ int uam_reserve(uam_ctx* ctx, void** ptr, size_t* cur, size_t need);
 int uam_reserve_pinned(uam_ctx* ctx, void** ptr, size_t* cur, size_t need);
 int uam_make_params(uam_ctx* ctx, const double* h_p, int n_p, int flags, UamParams* out);
 int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st);
+int uam_build_shape_grid(uam_ctx* ctx, double e, int flags, cudaStream_t st);
+// the grid to use for a call with these parameters (G == 0 when culling would not be exact for them)
+UamShapeGrid uam_pick_shape_grid(const uam_ctx* ctx, const UamParams& prm);
 cudaStream_t uam_pick_stream(uam_ctx* ctx, void* stream);
 int uam_time_collect(uam_ctx* ctx);
 int uam_time_begin(uam_ctx* ctx, cudaStream_t st);
@@ -182,6 +204,30 @@ __device__ __forceinline__ double uam_h_exact(const UamEdge& r, double x, double
     }
 }
 
+// true if inequality r is > thr everywhere on the box [xa,xb] x [ya,yb] (with a rounding margin): used to cull shapes
+// per raster tile (uam_map_rebuild.cu) and per cell of the shape grid (uam_shape_grid.cu)
+__device__ __forceinline__ bool uam_edge_excludes_tile(const UamEdge& r, double xa, double xb, double ya, double yb,
+                                                       double thr) {
+    const int kind = (int)r.kind;
+    double hmin, scale;
+    if (kind == UAM_EDGE_ELLIPSE) {
+        const double px = fmin(fmax(r.p0, xa), xb), py = fmin(fmax(r.p1, ya), yb);
+        hmin = uam_h_exact(r, px, py);
+        scale = fabs(hmin) + 2.0;
+    } else {
+        const double h0 = uam_h_exact(r, xa, ya), h1 = uam_h_exact(r, xb, ya);
+        const double h2 = uam_h_exact(r, xa, yb), h3 = uam_h_exact(r, xb, yb);
+        hmin = fmin(fmin(h0, h1), fmin(h2, h3));
+        if (kind == UAM_EDGE_LINE) {
+            const double mx = fmax(fabs(xa - r.p0), fabs(xb - r.p0)), my = fmax(fabs(ya - r.p1), fabs(yb - r.p1));
+            scale = fabs(r.p3) * mx + fabs(r.p2) * my;
+        } else {
+            scale = fmax(fabs(xa), fabs(xb)) + fmax(fabs(ya), fabs(yb)) + fabs(r.p2) + fabs(r.p3);
+        }
+    }
+    return hmin > thr + 1e-9 * scale + 1e-300;
+}
+
 __device__ __forceinline__ UamEdge uam_load_edge(const UamEdge* __restrict__ p) {
     // 4 x 16-byte read-only loads; every lane reads the same record (broadcast, L1-resident)
     const double2* q = reinterpret_cast<const double2*>(p);
@@ -216,6 +262,15 @@ __device__ __forceinline__ double uam_psi(const UamEdge* __restrict__ edges, int
     }
     if (inside) *inside = in;
     return res;
+}
+
+// cell of (x, y) in the shape grid, -1 when there is no grid or the point is outside it (or not finite)
+__device__ __forceinline__ int uam_shape_grid_cell(const UamShapeGrid& sg, double x, double y) {
+    if (sg.G == 0) return -1;
+    const double fx = __dmul_rn(__dsub_rn(x, sg.gx0), sg.inv_cw), fy = __dmul_rn(__dsub_rn(y, sg.gy0), sg.inv_ch);
+    const double g = (double)sg.G;
+    if (!(fx >= 0.0 && fx < g && fy >= 0.0 && fy < g)) return -1;
+    return (int)fy * sg.G + (int)fx;
 }
 
 __device__ __forceinline__ float uam_warp_sum(float v) {

@@ -49,29 +49,6 @@ uam_k_dem_mask(const float* __restrict__ img, long long n, float thr, int eq_mod
 // -------------------------------------------------------------------------------------------------------
 // tile culling
 // -------------------------------------------------------------------------------------------------------
-// true if inequality r is > thr everywhere on the tile [xa,xb] x [ya,yb] (with a rounding margin)
-__device__ __forceinline__ bool uam_edge_excludes_tile(const UamEdge& r, double xa, double xb, double ya, double yb,
-                                                       double thr) {
-    const int kind = (int)r.kind;
-    double hmin, scale;
-    if (kind == UAM_EDGE_ELLIPSE) {
-        const double px = fmin(fmax(r.p0, xa), xb), py = fmin(fmax(r.p1, ya), yb);
-        hmin = uam_h_exact(r, px, py);
-        scale = fabs(hmin) + 2.0;
-    } else {
-        const double h0 = uam_h_exact(r, xa, ya), h1 = uam_h_exact(r, xb, ya);
-        const double h2 = uam_h_exact(r, xa, yb), h3 = uam_h_exact(r, xb, yb);
-        hmin = fmin(fmin(h0, h1), fmin(h2, h3));
-        if (kind == UAM_EDGE_LINE) {
-            const double mx = fmax(fabs(xa - r.p0), fabs(xb - r.p0)), my = fmax(fabs(ya - r.p1), fabs(yb - r.p1));
-            scale = fabs(r.p3) * mx + fabs(r.p2) * my;
-        } else {
-            scale = fmax(fabs(xa), fabs(xb)) + fmax(fabs(ya), fabs(yb)) + fabs(r.p2) + fabs(r.p3);
-        }
-    }
-    return hmin > thr + 1e-9 * scale + 1e-300;
-}
-
 // Ordered compaction of the candidates at positions [s_begin, s_end) that survive the tile test into list[0..n)
 // (n <= CAP).  A candidate is shape cand[p] (or shape p itself when cand is NULL).  Returns the next position to
 // continue from.  Must be called by all threads of a 256-thread CTA.

@@ -16,6 +16,20 @@ __device__ __forceinline__ double uam_norm2(double dx, double dy) {
     return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
+// one term of a region sum: total += psi_s(x)/psi_s(center_s)     problem.py:76-80 (without the weight)
+__device__ __forceinline__ void uam_add_shape_term(const UamEdge* __restrict__ edges, const double* __restrict__ psic,
+                                                   int s, const int4 meta, double x, double y, bool smooth, double e,
+                                                   bool early_exit, double& total) {
+    const double psi = uam_psi(edges, meta.x, meta.y, x, y, smooth, e, nullptr, early_exit);
+    if (meta.w) {
+        const double pc = __ldg(psic + s);
+        // x + 0/pc == x unless pc == 0 (0/0 = NaN must propagate like the reference)
+        if (psi != 0.0 || pc == 0.0 || pc != pc) total = __dadd_rn(total, __ddiv_rn(psi, pc));
+    } else {
+        total = __dadd_rn(total, psi);
+    }
+}
+
 // sum over the region's shapes of psi(x)/psi(center)     problem.py:72-80 (without the weight)
 __device__ __forceinline__ double uam_region_total(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes,
                                                    const double* __restrict__ psic, int s0, int s1, double x, double y,
@@ -23,14 +37,22 @@ __device__ __forceinline__ double uam_region_total(const UamEdge* __restrict__ e
     double total = 0.0;
     for (int s = s0; s < s1; ++s) {
         const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));   // e0, e1, region, has_center
-        const double psi = uam_psi(edges, meta.x, meta.y, x, y, smooth, e, nullptr, early_exit);
-        if (meta.w) {
-            const double pc = __ldg(psic + s);
-            // x + 0/pc == x unless pc == 0 (0/0 = NaN must propagate like the reference)
-            if (psi != 0.0 || pc == 0.0 || pc != pc) total = __dadd_rn(total, __ddiv_rn(psi, pc));
-        } else {
-            total = __dadd_rn(total, psi);
-        }
+        uam_add_shape_term(edges, psic, s, meta, x, y, smooth, e, early_exit, total);
+    }
+    return total;
+}
+
+// The same sum over the candidates items[i..i1) that belong to shapes [s0, s1) (ascending ids; the shape grid's cell
+// list): the shapes left out contribute exact zeros.  Advances i past the range.
+__device__ __forceinline__ double uam_region_total_listed(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes,
+                                                          const double* __restrict__ psic, const int* __restrict__ items,
+                                                          int& i, int i1, int s1, double x, double y, bool smooth, double e) {
+    double total = 0.0;
+    for (; i < i1; ++i) {
+        const int s = __ldg(items + i);
+        if (s >= s1) break;
+        const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
+        uam_add_shape_term(edges, psic, s, meta, x, y, smooth, e, true, total);
     }
     return total;
 }
@@ -41,7 +63,7 @@ struct UamRegionRanges {
 
 // One warp per path; lanes stride the N+2 waypoints.
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
-uam_k_score_analytic(const double2* __restrict__ z, long long B, int N, UamParams prm, UamRegionRanges rr,
+uam_k_score_analytic(const double2* __restrict__ z, long long B, int N, UamParams prm, UamRegionRanges rr, UamShapeGrid sg,
                      const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes,
                      const double* __restrict__ psic, int n_obs, double* __restrict__ cost,
                      uint8_t* __restrict__ collide, double* __restrict__ g) {
@@ -65,22 +87,60 @@ uam_k_score_analytic(const double2* __restrict__ z, long long B, int N, UamParam
         bool col = false;
         for (int j = lane; j < W; j += 32) {
             const double2 p = zp[j];
+            // cell of the shape grid (-1: no grid, or the point is outside it / not finite -> every shape is evaluated)
+            const int cell = uam_shape_grid_cell(sg, p.x, p.y);
+            int li = 0, l1 = 0;
+            if (cell >= 0) { li = __ldg(sg.start + cell); l1 = __ldg(sg.start + cell + 1); }
+            // ---- hard obstacles: collision (map.py:41-43) and g's obstacle block (problem.py:109-112) ----
+            if (cell < 0 || (gp && !sg.obs_values)) {
+                for (int o = 0; o < n_obs; ++o) {
+                    const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[o].e0));
+                    bool inside;
+                    const double psi = uam_psi(edges, meta.x, meta.y, p.x, p.y, obs_smooth, 0.0, &inside, fast);
+                    col = col || inside;
+                    if (gp) gp[3 * N + o * W + j] = psi;
+                }
+            } else if (gp) {
+                for (int o = 0; o < n_obs; ++o) {
+                    double psi = 0.0;          // an obstacle that is not in the cell's list: psi = 0, not inside
+                    if (li < l1 && __ldg(sg.items + li) == o) {
+                        const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[o].e0));
+                        bool inside;
+                        psi = uam_psi(edges, meta.x, meta.y, p.x, p.y, true, 0.0, &inside, true);
+                        col = col || inside;
+                        ++li;
+                    }
+                    gp[3 * N + o * W + j] = psi;
+                }
+            } else {
+                for (; li < l1; ++li) {
+                    const int o = __ldg(sg.items + li);
+                    if (o >= n_obs) break;
+                    const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[o].e0));
+                    bool inside;
+                    uam_psi(edges, meta.x, meta.y, p.x, p.y, true, 0.0, &inside, true);     // `contains` only
+                    col = col || inside;
+                }
+            }
             // ---- weighted region penalties at z_j, regions in insertion order (problem.py:49-56) ----
             double P = 0.0;
-            for (int r = 0; r < prm.n_regions; ++r) {
-                const double tot = uam_region_total(edges, shapes, psic, rr.begin[r], rr.begin[r + 1], p.x, p.y,
-                                                    pen_smooth, prm.e, fast);
-                P = __dadd_rn(P, __dmul_rn(prm.w[r], tot));
+            if (cell < 0) {
+                for (int r = 0; r < prm.n_regions; ++r) {
+                    const double tot = uam_region_total(edges, shapes, psic, rr.begin[r], rr.begin[r + 1], p.x, p.y,
+                                                        pen_smooth, prm.e, fast);
+                    P = __dadd_rn(P, __dmul_rn(prm.w[r], tot));
+                }
+            } else {
+                // only the regions with a listed shape: w_r * 0 = +-0 leaves P unchanged (finite weights: uam_pick_shape_grid)
+                while (li < l1 && __ldg(sg.items + li) < n_obs) ++li;
+                while (li < l1) {
+                    const int r = __ldg(&shapes[__ldg(sg.items + li)].region);
+                    const double tot = uam_region_total_listed(edges, shapes, psic, sg.items, li, l1, rr.begin[r + 1], p.x, p.y,
+                                                               pen_smooth, prm.e);
+                    P = __dadd_rn(P, __dmul_rn(prm.w[r], tot));
+                }
             }
             pen_sum += __ddiv_rn(P, dN);                                   // problem.py:43
-            // ---- hard obstacles: collision (map.py:41-43) and g's obstacle block (problem.py:109-112) ----
-            for (int o = 0; o < n_obs; ++o) {
-                const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[o].e0));
-                bool inside;
-                const double psi = uam_psi(edges, meta.x, meta.y, p.x, p.y, obs_smooth, 0.0, &inside, fast);
-                col = col || inside;
-                if (gp) gp[3 * N + o * W + j] = psi;
-            }
             // ---- segment pair k = j: length term (problem.py:130-146) and ratio/angle block (:100-107) ----
             if (j < N) {
                 const double2 q = zp[j + 1], r2 = zp[j + 2];
@@ -117,7 +177,7 @@ uam_k_score_analytic(const double2* __restrict__ z, long long B, int N, UamParam
 
 // One thread per query point.
 __global__ void __launch_bounds__(256)
-uam_k_eval_points(const double2* __restrict__ x, long long M, UamParams prm, UamRegionRanges rr,
+uam_k_eval_points(const double2* __restrict__ x, long long M, UamParams prm, UamRegionRanges rr, UamShapeGrid sg,
                   const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes,
                   const double* __restrict__ psic, int n_obs, double* __restrict__ region_pen,
                   double* __restrict__ obst_pen, uint8_t* __restrict__ collide) {
@@ -127,6 +187,37 @@ uam_k_eval_points(const double2* __restrict__ x, long long M, UamParams prm, Uam
     const bool fast = (prm.flags & UAM_INTERNAL_FINITE_EDGES) != 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
         const double2 p = x[i];
+        const int cell = uam_shape_grid_cell(sg, p.x, p.y);
+        if (cell >= 0) {
+            // candidates of the cell only (ascending: obstacles, then region by region); the rest are exact zeros
+            const int l0 = __ldg(sg.start + cell), l1 = __ldg(sg.start + cell + 1);
+            int li = l0;
+            if (obst_pen)
+                obst_pen[i] = sg.obs_values ? uam_region_total_listed(edges, shapes, psic, sg.items, li, l1, n_obs, p.x, p.y, true, prm.e)
+                                            : uam_region_total(edges, shapes, psic, 0, n_obs, p.x, p.y, obs_smooth, prm.e, fast);
+            if (collide) {
+                bool col = false;
+                for (li = l0; li < l1; ++li) {
+                    const int o = __ldg(sg.items + li);
+                    if (o >= n_obs) break;
+                    const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[o].e0));
+                    bool inside;
+                    uam_psi(edges, meta.x, meta.y, p.x, p.y, true, 0.0, &inside, true);
+                    col = col || inside;
+                }
+                collide[i] = col ? 1 : 0;
+            }
+            if (region_pen) {
+                li = l0;
+                while (li < l1 && __ldg(sg.items + li) < n_obs) ++li;
+                for (int r = 0; r < prm.n_regions; ++r) {
+                    const double tot = uam_region_total_listed(edges, shapes, psic, sg.items, li, l1, rr.begin[r + 1], p.x, p.y,
+                                                               pen_smooth, prm.e);
+                    region_pen[i * prm.n_regions + r] = __dmul_rn(prm.w[r], tot);
+                }
+            }
+            continue;
+        }
         if (region_pen) {
             for (int r = 0; r < prm.n_regions; ++r) {
                 const double tot = uam_region_total(edges, shapes, psic, rr.begin[r], rr.begin[r + 1], p.x, p.y,
@@ -186,15 +277,17 @@ uam_k_eval_inequalities(const UamEdge* __restrict__ recs, int n_rec, const doubl
     }
 }
 
+// need_norm = false: the call only asks for `contains` (no psi value is divided by psi(centre)), so the psi(centre)
+// table and the shape grid are left as they are (a grid built for any enlargement / flags culls `contains` correctly)
 int uam_analytic_prepare(uam_ctx* ctx, const double* h_p, int n_p, int flags, cudaStream_t st, UamParams* prm,
-                         UamRegionRanges* rr) {
+                         UamRegionRanges* rr, bool need_norm = true) {
     if (!ctx->has_shapes) return uam_fail(ctx, UAM_ERR_STATE, "no shape table: call uam_map_set_shapes first");
     UAM_TRY(uam_make_params(ctx, h_p, n_p, flags, prm));
     if (prm->n_regions != ctx->n_regions)
         return uam_fail(ctx, UAM_ERR_INVALID, "p carries %d region weights, the map has %d regions", prm->n_regions,
                         ctx->n_regions);
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
-    UAM_TRY(uam_ensure_shape_norm(ctx, *prm, st));
+    if (need_norm) UAM_TRY(uam_ensure_shape_norm(ctx, *prm, st));
     for (int r = 0; r <= ctx->n_regions; ++r) rr->begin[r] = ctx->region_begin[r];
     if (ctx->edges_finite) prm->flags |= UAM_INTERNAL_FINITE_EDGES;
     return UAM_OK;
@@ -214,8 +307,8 @@ extern "C" int uam_score_paths_analytic(uam_ctx* ctx, const double* d_z, int64_t
     if (B == 0) return UAM_OK;
     const long long ctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 8);
     uam_k_score_analytic<<<(unsigned)ctas, UAM_CTA_THREADS, 0, st>>>(
-        reinterpret_cast<const double2*>(d_z), B, N, prm, rr, ctx->d_edges, ctx->d_shapes, ctx->d_psic, ctx->n_obs, d_cost,
-        d_collide, d_g);
+        reinterpret_cast<const double2*>(d_z), B, N, prm, rr, uam_pick_shape_grid(ctx, prm), ctx->d_edges, ctx->d_shapes, ctx->d_psic,
+        ctx->n_obs, d_cost, d_collide, d_g);
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_analytic");
     return UAM_OK;
 }
@@ -266,10 +359,12 @@ extern "C" int uam_eval_points(uam_ctx* ctx, const double* d_x, int64_t M, const
     cudaStream_t st = uam_pick_stream(ctx, stream);
     UamParams prm;
     UamRegionRanges rr;
-    UAM_TRY(uam_analytic_prepare(ctx, h_p, n_p, flags, st, &prm, &rr));
+    const bool only_contains = !d_region_pen && !d_obst_pen;
+    UAM_TRY(uam_analytic_prepare(ctx, h_p, n_p, flags, st, &prm, &rr, !only_contains));
     if (M == 0) return UAM_OK;
+    const UamShapeGrid sg = only_contains ? (ctx->shape_grid_opt ? ctx->shape_grid : UamShapeGrid{}) : uam_pick_shape_grid(ctx, prm);
     const long long ctas = std::min<long long>((M + 255) / 256, (long long)ctx->sm_count * 8);
-    uam_k_eval_points<<<(unsigned)ctas, 256, 0, st>>>(reinterpret_cast<const double2*>(d_x), M, prm, rr, ctx->d_edges,
+    uam_k_eval_points<<<(unsigned)ctas, 256, 0, st>>>(reinterpret_cast<const double2*>(d_x), M, prm, rr, sg, ctx->d_edges,
                                                        ctx->d_shapes, ctx->d_psic, ctx->n_obs, d_region_pen, d_obst_pen,
                                                        d_collide);
     UAM_CHECK_LAUNCH(ctx, "uam_k_eval_points");
