@@ -239,6 +239,30 @@ int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, double dx, doubl
 int uam_edt(uam_ctx* ctx, const uint8_t* d_occ, int H, int W, double cell, int32_t* d_dist2,
             float* d_clearance, void* stream);
 
+/* ---- polygon front-end of map_generation ------------------------------------------------
+ * The data-parallel core of DataManager.load_dem_polygons_from_geotiff (map_generation/data_manager.py:11-19: one polygon
+ * per connected region of the mask, as rasterio.features.shapes yields them with its default 4-connectivity) and of
+ * DataProcessor.process_polygons (map_generation/data_processor.py:16-34,67-71: area filter + cv2.minAreaRect of each
+ * polygon's exterior ring).
+ * uam_label_components: d_mask (H,W) uint8 -> d_labels (H,W) int32: 0 = background, components numbered 1..n in raster-scan
+ *                       order of their first cell (scipy.ndimage.label's numbering); connectivity 4 or 8; *h_n_components
+ *                       (host) receives n.  Synchronises `stream`.
+ * uam_component_stats:  d_area (n) int64 = cells per component (polygon.area / cell area); d_bbox (n,4) int32 =
+ *                       {row min, row max, col min, col max}.  Synchronises `stream`.
+ * uam_component_rects:  minimum-area enclosing rectangle of the cell corners of each listed component (d_ids: K distinct
+ *                       labels) = of the polygon's exterior ring; d_rect (K,4,2) float64 world coordinates of the corners
+ *                       (x0 + col*dx, y0 + row*dy at cell corners), consecutive around the rectangle, the first two on the
+ *                       line of the chosen hull edge; d_info (K,2) int32 (nullable) = {hull vertices, chosen edge}.  Exact:
+ *                       every hull edge is tried with integer extents and a 128-bit area comparison, ties to the first
+ *                       edge.  Needs square cells and H, W <= 32766.  Synchronises `stream`. */
+int uam_label_components(uam_ctx* ctx, const uint8_t* d_mask, int H, int W, int connectivity, int32_t* d_labels,
+                         int32_t* h_n_components, void* stream);
+int uam_component_stats(uam_ctx* ctx, const int32_t* d_labels, int H, int W, int n_components, int64_t* d_area,
+                        int32_t* d_bbox, void* stream);
+int uam_component_rects(uam_ctx* ctx, const int32_t* d_labels, int H, int W, int n_components, const int32_t* d_bbox,
+                        const int32_t* d_ids, int K, double x0, double dx, double y0, double dy, double* d_rect,
+                        int32_t* d_info, void* stream);
+
 /* ---- grid search / cost-to-go (build-defined extension; the reference has none: SURVEY.md section 0) ----------
  * Q independent single-source cost-to-go sweeps on an 8-connected H x W grid, optionally stacked in `bands` altitude
  * bands, with integer edge costs: in-plane step(u,v) * (cost[b,u] + cost[b,v]), step = 2 (axis) / 3 (diagonal); band

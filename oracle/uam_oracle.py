@@ -644,3 +644,97 @@ def get_cost_gradient(m: OMap, z_, N: int, weights: Sequence[float], e: float = 
         if k >= 1:
             G[:, k - 1] -= (N + 1) * gk           # d/d z_{k-1}
     return G.reshape(B, 2 * (N + 2))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# polygon front-end of map_generation: mask -> connected regions -> minimum-area rectangles
+# ---------------------------------------------------------------------------------------------------------------
+def label_components(mask, connectivity: int = 4):
+    """One label per connected region of the mask, numbered in raster-scan order of the region's first cell
+    (scipy.ndimage.label).  The reference gets the same regions as polygons from rasterio.features.shapes
+    (map_generation/data_manager.py:18-19; 4-connectivity is rasterio's default)."""
+    from scipy import ndimage
+    st = ndimage.generate_binary_structure(2, 1 if connectivity == 4 else 2)
+    lab, n = ndimage.label(np.asarray(mask) != 0, structure=st)
+    return lab.astype(np.int32), int(n)
+
+
+def component_stats(labels, n: int):
+    """cells per component (= polygon.area / cell area, map_generation/data_processor.py:19) and bounding boxes
+    {row min, row max, col min, col max}."""
+    area = np.bincount(labels.ravel(), minlength=n + 1)[1:].astype(np.int64)
+    bbox = np.zeros((n, 4), dtype=np.int32)
+    ii, jj = np.nonzero(labels)
+    lab = labels[ii, jj] - 1
+    for k, (arr, fn) in enumerate([(ii, np.minimum), (ii, np.maximum), (jj, np.minimum), (jj, np.maximum)]):
+        v = np.full(n, np.iinfo(np.int32).max if fn is np.minimum else -1, dtype=np.int64)
+        fn.at(v, lab, arr)
+        bbox[:, k] = v
+    return area, bbox
+
+
+def _hull_int(points):
+    """Strictly convex hull of integer points (Andrew's monotone chain, exact), as a list of (x, y) tuples."""
+    pts = sorted(set((int(x), int(y)) for x, y in points))
+    if len(pts) <= 2:
+        return pts
+
+    def half(seq):
+        h = []
+        for p in seq:
+            while len(h) >= 2 and (h[-1][0] - h[-2][0]) * (p[1] - h[-2][1]) - (h[-1][1] - h[-2][1]) * (p[0] - h[-2][0]) <= 0:
+                h.pop()
+            h.append(p)
+        return h
+    lo, up = half(pts), half(pts[::-1])
+    return lo[:-1] + up[:-1]
+
+
+def min_area_rect_exact(points):
+    """Minimum-area enclosing rectangle of integer points: a side of it lies on a hull edge, so every hull edge is
+    tried; extents are exact integers, areas are compared as exact fractions, ties go to the first edge of the hull
+    listed from its top-most (then left-most) vertex down the left side (y grows downwards, raster rows).
+    -> (corners (4,2) float64, area as a Fraction, number of hull vertices, index of the chosen edge).
+    This is what cv2.minAreaRect approximates in float32 (map_generation/data_processor.py:67-71)."""
+    from fractions import Fraction
+    h = _hull_int(points)
+    n = len(h)
+    assert n >= 3
+    # orientation: cross(b - a, c - a) < 0 for consecutive vertices (down the left side first when y grows downwards)
+    a, b, c = h[0], h[1], h[2]
+    if (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0]) > 0:
+        h = h[::-1]
+    s = min(range(n), key=lambda i: (h[i][1], h[i][0]))
+    h = h[s:] + h[:s]
+    best = None
+    for e in range(n):
+        ax, ay = h[e]
+        bx, by = h[(e + 1) % n]
+        ex, ey = bx - ax, by - ay
+        us = [(px - ax) * ex + (py - ay) * ey for px, py in h]
+        vs = [abs((px - ax) * ey - (py - ay) * ex) for px, py in h]
+        den = ex * ex + ey * ey
+        area = Fraction((max(us) - min(us)) * max(vs), den)
+        if best is None or area < best[0]:
+            best = (area, e, min(us), max(us), max(vs), den, (ax, ay, ex, ey))
+    area, e, u0, u1, vv, den, (ax, ay, ex, ey) = best
+    nx, ny = ey, -ex
+    u0, u1, vv = u0 / den, u1 / den, vv / den
+    corners = np.array([[ax + u0 * ex, ay + u0 * ey], [ax + u1 * ex, ay + u1 * ey],
+                        [ax + u1 * ex + vv * nx, ay + u1 * ey + vv * ny], [ax + u0 * ex + vv * nx, ay + u0 * ey + vv * ny]], dtype=F64)
+    return corners, area, n, e
+
+
+def component_rects(labels, ids, geo):
+    """Minimum-area rectangle of the cell corners of each listed component, world coordinates (x0 + col dx, y0 + row dy)."""
+    x0, dx, y0, dy = geo
+    out = np.zeros((len(ids), 4, 2), dtype=F64)
+    info = np.zeros((len(ids), 2), dtype=np.int32)
+    for k, lab in enumerate(ids):
+        ii, jj = np.nonzero(labels == lab)
+        pts = np.concatenate([np.stack([jj + a, ii + b], 1) for a in (0, 1) for b in (0, 1)])
+        c, _, nh, e = min_area_rect_exact(pts)
+        out[k, :, 0] = x0 + c[:, 0] * dx
+        out[k, :, 1] = y0 + c[:, 1] * dy
+        info[k] = (nh, e)
+    return out, info

@@ -867,3 +867,107 @@ def test_shape_grid_changes_no_bit(uam, torch):
     g0 = prob.score(Z[:32], want_g=True)
     for a, b in zip(g1, g0):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+def _blob_mask(rng, H, W, density, smooth=2):
+    """Random mask with blob-like regions (box-filtered noise thresholded at the requested density)."""
+    f = rng.random((H, W))
+    for _ in range(smooth):
+        f = (f + np.roll(f, 1, 0) + np.roll(f, -1, 0) + np.roll(f, 1, 1) + np.roll(f, -1, 1)) / 5.0
+    return (f > np.quantile(f, 1.0 - density)).astype(np.uint8) if 0.0 < density < 1.0 else np.full((H, W), int(density >= 1.0), np.uint8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('H,W,density,smooth', [(40, 50, 0.45, 0), (64, 64, 0.6, 1), (33, 257, 0.5, 2), (200, 31, 0.55, 0), (1, 1, 1.0, 0),
+                                                (1, 70, 0.5, 0), (70, 1, 0.5, 0), (50, 64, 0.0, 0), (37, 96, 1.0, 0), (300, 333, 0.35, 3)])
+@pytest.mark.parametrize('conn', [4, 8])
+def test_label_components_and_stats(uam, torch, H, W, density, smooth, conn):
+    """Connected regions of a mask (the polygons of rasterio.features.shapes, data_manager.py:18-19): same labels, in
+    the same numbering, as scipy.ndimage.label; cell counts and bounding boxes exact."""
+    rng = np.random.default_rng(H * 1000 + W + conn)
+    mask = _blob_mask(rng, H, W, density, smooth)
+    eng = uam.Engine()
+    labels, n = eng.label_components(torch.from_numpy(mask).cuda(), conn)
+    lab_ref, n_ref = orc.label_components(mask, conn)
+    assert n == n_ref
+    assert np.array_equal(labels.cpu().numpy(), lab_ref)
+    if n:
+        area, bbox = eng.component_stats(labels, n)
+        a_ref, b_ref = orc.component_stats(lab_ref, n)
+        assert np.array_equal(area.cpu().numpy(), a_ref) and np.array_equal(bbox.cpu().numpy(), b_ref)
+
+
+@pytest.mark.gpu
+def test_component_rectangles_exact(uam, torch):
+    """Minimum-area rectangle of every component's cell corners: the same hull size, the same chosen edge and the same
+    corners as the exact-arithmetic oracle; the area agrees with cv2.minAreaRect (what the reference calls,
+    data_processor.py:67-71) to float32 accuracy; the rectangle contains every cell of its component."""
+    rng = np.random.default_rng(77)
+    geo = (1000.0, 10.0, 5000.0, -10.0)             # rasterio-like: y decreases with the row
+    eng = uam.Engine()
+    for H, W, density, smooth in [(60, 80, 0.4, 1), (128, 96, 0.5, 2), (16, 200, 0.55, 0), (90, 90, 0.25, 3)]:
+        mask = _blob_mask(rng, H, W, density, smooth)
+        labels, n = eng.label_components(torch.from_numpy(mask).cuda(), 4)
+        lab_h = labels.cpu().numpy()
+        area, bbox = eng.component_stats(labels, n)
+        ids = rng.permutation(n)[:min(n, 60)].astype(np.int32) + 1          # any order, any subset
+        rect, info = eng.component_rects(labels, n, bbox, ids, geo, want_info=True)
+        r_ref, i_ref = orc.component_rects(lab_h, ids, geo)
+        assert np.array_equal(info.cpu().numpy(), i_ref)
+        np.testing.assert_allclose(rect.cpu().numpy(), r_ref, rtol=1e-13, atol=1e-9)
+        R = rect.cpu().numpy()
+        try:
+            import cv2
+        except ImportError:
+            cv2 = None
+        for k, lab in enumerate(ids):
+            ii, jj = np.nonzero(lab_h == lab)
+            pts = np.concatenate([np.stack([geo[0] + (jj + a) * geo[1], geo[2] + (ii + b) * geo[3]], 1) for a in (0, 1) for b in (0, 1)])
+            # containment: every corner on the inner side of the 4 edges (up to rounding)
+            c = R[k]
+            d0, d1 = c[1] - c[0], c[2] - c[1]
+            sgn = np.sign(d0[0] * d1[1] - d0[1] * d1[0])
+            for e in range(4):
+                d = c[(e + 1) % 4] - c[e]
+                assert np.all(sgn * (d[0] * (pts[:, 1] - c[e, 1]) - d[1] * (pts[:, 0] - c[e, 0])) >= -1e-6 * (1 + np.abs(d).max()))
+            if cv2 is not None:
+                (_, (w, h), _) = cv2.minAreaRect((pts - [geo[0], geo[2]]).astype(np.float32))
+                assert abs(uam.mapgen.rect_area(c[None])[0] - w * h) <= 2e-5 * w * h + 1e-3
+    with pytest.raises(uam.UamError):
+        eng.component_rects(labels, n, bbox, [1, 1], geo)               # listed twice
+    with pytest.raises(uam.UamError):
+        eng.component_rects(labels, n, bbox, [n + 1], geo)
+    with pytest.raises(uam.UamError):
+        eng.component_rects(labels, n, bbox, [1], (0.0, 10.0, 0.0, -5.0))    # cells not square
+
+
+@pytest.mark.gpu
+def test_dem_rectangles_pipeline(uam, torch, tmp_path):
+    """DEM band -> mask -> regions -> rectangles -> map file, against the same steps done with scipy + the exact
+    rectangle oracle on the host (load_dem_polygons_from_geotiff + process_polygons without the large-polygon split)."""
+    rng = np.random.default_rng(5)
+    H, W = 700, 900
+    f = rng.random((H, W))
+    for _ in range(25):
+        f = (f + np.roll(f, 1, 0) + np.roll(f, -1, 0) + np.roll(f, 1, 1) + np.roll(f, -1, 1)) / 5.0
+    dem = ((f - np.quantile(f, 0.55)) * 4e4).astype(np.float32)
+    dem[dem <= 0] = -9999.0
+    geo = (20000.0, 50.0, 15000.0, -50.0)           # 50 m cells, EPSG:2443-like metres
+    for thr, min_area in [(0.0, 750000.0), (-9999, 2.0e6), (30.0, 1.0e5)]:
+        got = uam.mapgen.dem_rectangles(dem, geo, thr, min_area=min_area, min_approx_polygon_area=min_area * 1.04)
+        mask = (dem == -9999) if thr == -9999 else (dem > thr)
+        lab, n = orc.label_components(mask, 4)
+        area, _ = orc.component_stats(lab, n)
+        ids = np.nonzero(area * 2500.0 > min_area)[0].astype(np.int32) + 1
+        assert got['n_components'] == n and got['n_polygons_over_min_area'] == len(ids) and len(ids) > 0
+        r_ref, _ = orc.component_rects(lab, ids, geo)
+        r_int = np.trunc(r_ref).astype(np.int64)
+        keep = uam.mapgen.rect_area(r_int.astype(np.float64)) > min_area * 1.04
+        assert np.array_equal(got['labels'], ids[keep])
+        assert np.abs(got['rects'] - r_int[keep]).max() <= 1          # truncation of a corner that sits on an integer
+        assert np.array_equal(got['area'], area[ids[keep] - 1] * 2500.0)
+    # the rectangles go out in the reference's map-file format and come back as polygons (km)
+    path = tmp_path / 'rects.txt'
+    uam.save_polygons([r.tolist() for r in got['rects']], str(path))
+    shapes = uam.get_var_from_file(str(path))
+    assert len(shapes) == len(got['rects'])

@@ -245,3 +245,39 @@ def test_c_oracle_grid_search_matches_numpy_oracle():
     assert np.array_equal(d2[0], dr) and np.array_equal(p2[0].astype(np.int64), pr)
     d3, _ = occ.grid_search(cost[1], [[5, 6]], None, want_parent=False)
     assert np.array_equal(d3[0], orc.grid_search(cost[1], (5, 6), None)[0])
+
+
+def test_oracle_components_and_min_area_rect():
+    """Oracle of the polygon front-end: labels number the regions in raster-scan order; the exact minimum-area rectangle
+    has the area cv2.minAreaRect finds (the reference's call, map_generation/data_processor.py:67-71) and is never larger
+    than any rectangle aligned with another direction."""
+    mask = np.array([[1, 1, 0, 0, 1],
+                     [0, 1, 0, 1, 1],
+                     [0, 0, 1, 0, 0],
+                     [1, 0, 1, 1, 0]], dtype=np.uint8)
+    lab4, n4 = orc.label_components(mask, 4)
+    assert n4 == 4 and lab4[0, 0] == 1 and lab4[0, 4] == 2 and lab4[2, 2] == 3 and lab4[3, 0] == 4 and lab4[1, 3] == 2
+    lab8, n8 = orc.label_components(mask, 8)
+    assert n8 == 2 and lab8[2, 2] == 1 and lab8[1, 3] == 1 and lab8[3, 0] == 2
+    area, bbox = orc.component_stats(lab4, n4)
+    assert area.tolist() == [3, 3, 3, 1] and bbox[1].tolist() == [0, 1, 3, 4]
+    # unit cell, axis-aligned box, a tilted lattice parallelogram
+    c, a, nh, e = orc.min_area_rect_exact([(0, 0), (1, 0), (0, 1), (1, 1)])
+    assert a == 1 and nh == 4
+    c, a, nh, e = orc.min_area_rect_exact([(x, y) for x in range(5) for y in range(3)])
+    assert a == 8
+    c, a, nh, e = orc.min_area_rect_exact([(0, 0), (3, 1), (4, 4), (1, 3)])
+    assert float(a) < 16 and nh == 4
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(1)
+    for _ in range(40):
+        pts = rng.integers(0, 60, (rng.integers(3, 40), 2))
+        if len(orc._hull_int(pts)) < 3:
+            continue
+        c, a, nh, e = orc.min_area_rect_exact(pts)
+        (_, (w, h), _) = cv2.minAreaRect(pts.astype(np.float32))
+        assert abs(float(a) - w * h) <= 2e-5 * w * h + 1e-3
+        # corners form a rectangle of that area
+        d1, d2 = c[1] - c[0], c[3] - c[0]
+        assert abs(d1 @ d2) < 1e-9 * (1 + abs(d1).max() * abs(d2).max())
+        assert abs(np.linalg.norm(d1) * np.linalg.norm(d2) - float(a)) < 1e-9 * (1 + float(a))

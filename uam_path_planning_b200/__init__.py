@@ -13,7 +13,8 @@ from .mapio import get_var_from_file, parse_shapes, save_polygons, result_points
 from .engine import Engine, default_engine
 from .raster import RasterMap, load_dem_mask
 from . import distributed
+from . import mapgen
 
 __all__ = ['UamError', 'QuadraticObstacle', 'Inequality', 'polygon', 'ball', 'square', 'Map', 'RegionMap', 'Problem',
            'Solver', 'get_var_from_file', 'parse_shapes', 'save_polygons', 'result_points', 'result_wkt', 'Engine', 'default_engine', 'RasterMap', 'load_dem_mask',
-           'distributed']
+           'distributed', 'mapgen']

@@ -60,6 +60,9 @@ SIGNATURES = {
     'uam_rasterize_occupancy': (_i, [_vp, _i, _i, _d, _d, _d, _d, _vp, _vp]),
     'uam_rasterize_layers': (_i, [_vp, _i, _i, _d, _d, _d, _d, _d, _vp, _vp]),
     'uam_edt': (_i, [_vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
+    'uam_label_components': (_i, [_vp, _vp, _i, _i, _i, _vp, C.POINTER(C.c_int32), _vp]),
+    'uam_component_stats': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    'uam_component_rects': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _d, _d, _d, _d, _vp, _vp, _vp]),
     'uam_grid_search': (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     'uam_grid_search_bands': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
 }

@@ -1,0 +1,544 @@
+// Polygon front-end of map_generation on the GPU: the data-parallel core of
+//   DataManager.load_dem_polygons_from_geotiff  (data_manager.py:11-19: mask -> rasterio.features.shapes -> one polygon
+//                                                per connected region of the mask, 4-connectivity)
+//   DataProcessor.process_polygons              (data_processor.py:16-34,67-71: area filter, cv2.minAreaRect of each
+//                                                polygon's exterior ring)
+// as three steps on device arrays:
+//   uam_label_components   connected-component labelling, labels 1..n in raster-scan order of each component's first cell
+//                          (= scipy.ndimage.label's numbering); union-find with atomicMin on flat indices, so a component's
+//                          root is its smallest flat index and the result does not depend on the schedule
+//   uam_component_stats    cells per component (polygon.area / cell area: holes are not counted, like the polygon's
+//                          interior rings) and bounding box, warp-aggregated atomics
+//   uam_component_rects    minimum-area enclosing rectangle of each chosen component's cell corners = of the exterior ring
+//                          cv2.minAreaRect gets.  Per component: column extremes per grid line (atomics from run ends
+//                          only), convex hull by two monotone stacks, then every hull edge is tried as the rectangle's
+//                          direction (a minimum-area rectangle has a side on a hull edge) with exact integer extents and a
+//                          128-bit cross-multiplied area comparison, ties to the first edge: deterministic, no float
+//                          comparisons decide which rectangle wins.
+#include <algorithm>
+#include <climits>
+
+#include "uam_internal.cuh"
+
+namespace {
+
+// ---- union-find on flat indices -------------------------------------------------------------------------------------
+__device__ __forceinline__ int uam_uf_find(const int* __restrict__ L, int i) {
+    int p = L[i];
+    while (p != i) {
+        i = p;
+        p = L[i];
+    }
+    return i;
+}
+
+__device__ __forceinline__ void uam_uf_union(int* L, int a, int b) {
+    bool done = false;
+    while (!done) {
+        a = uam_uf_find(L, a);
+        b = uam_uf_find(L, b);
+        if (a < b) {
+            const int old = atomicMin(&L[b], a);
+            done = old == b;
+            b = old;
+        } else if (b < a) {
+            const int old = atomicMin(&L[a], b);
+            done = old == a;
+            a = old;
+        } else {
+            done = true;
+        }
+    }
+}
+
+// Row pass: every foreground cell starts as the first cell of its horizontal run (a run = consecutive foreground cells of
+// one row), found with a ballot per 32 cells + the carry across 32-cell words done by a union in the merge pass.
+__global__ void __launch_bounds__(256)
+uam_k_ccl_init(const uint8_t* __restrict__ mask, int H, int W, int* __restrict__ L) {
+    const long long n = (long long)H * W;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in = i < n;
+    const bool fg = in && mask[i] != 0;
+    const int col = in ? (int)(i % W) : 0;
+    // cells of this warp that continue a run inside the warp: foreground, not at column 0, left neighbour (lane - 1) foreground
+    const unsigned fgm = __ballot_sync(0xffffffffu, fg);
+    if (!in) return;
+    if (!fg) { L[i] = -1; return; }
+    // start of the run inside this warp's 32 cells: walk left over set bits while the row does not wrap
+    int back = 0;
+    if (lane > 0) {
+        const unsigned below = fgm << (32 - lane);        // bit 31 = lane - 1, bit 30 = lane - 2, ...
+        back = min(__clz(~below), min(lane, col));        // consecutive foreground lanes to the left, inside the row
+    }
+    L[i] = (int)(i - back);
+}
+
+// Merge pass: unite a cell with its upper neighbour(s), and a run that starts at a warp boundary with the cell to its left.
+__global__ void __launch_bounds__(256)
+uam_k_ccl_merge(const uint8_t* __restrict__ mask, int H, int W, int conn8, int* __restrict__ L) {
+    const long long n = (long long)H * W;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || mask[i] == 0) return;
+    const int row = (int)(i / W), col = (int)(i - (long long)row * W);
+    // a run that continues across a 32-cell word boundary: the init pass linked cells inside a word only
+    if (col > 0 && (i & 31) == 0 && mask[i - 1] != 0) uam_uf_union(L, (int)i, (int)(i - 1));
+    if (row > 0) {
+        const uint8_t up = mask[i - W];
+        // one union per run of the upper row that touches this cell: skip when the left cell is foreground and shares `up`
+        if (up != 0 && !(col > 0 && mask[i - 1] != 0 && mask[i - W - 1] != 0)) uam_uf_union(L, (int)i, (int)(i - W));
+        if (conn8) {
+            if (col > 0 && mask[i - W - 1] != 0 && up == 0 && !(mask[i - 1] != 0)) uam_uf_union(L, (int)i, (int)(i - W - 1));
+            if (col + 1 < W && mask[i - W + 1] != 0 && up == 0) uam_uf_union(L, (int)i, (int)(i - W + 1));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+uam_k_ccl_flatten(long long n, int* __restrict__ L) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int v = L[i];
+    if (v >= 0) L[i] = uam_uf_find(L, (int)i);
+}
+
+// ---- exclusive scan of a per-element count (three passes; element order = index order) ------------------------------
+#define UAM_SCAN_PER_THREAD 16
+#define UAM_SCAN_CHUNK (256 * UAM_SCAN_PER_THREAD)
+
+struct UamIsRoot {
+    const int* L;
+    __device__ int operator()(long long i) const { return L[i] == (int)i ? 1 : 0; }
+};
+struct UamIntArray {
+    const int* v;
+    __device__ int operator()(long long i) const { return v[i]; }
+};
+
+template <class F>
+__global__ void __launch_bounds__(256)
+uam_k_scan_counts(F f, long long n, unsigned long long* __restrict__ block_sum) {
+    __shared__ unsigned long long warp_sum[8];
+    const long long base = (long long)blockIdx.x * UAM_SCAN_CHUNK + (long long)threadIdx.x * UAM_SCAN_PER_THREAD;
+    unsigned long long c = 0;
+    for (int k = 0; k < UAM_SCAN_PER_THREAD; ++k)
+        if (base + k < n) c += (unsigned long long)f(base + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += warp_sum[w];
+        block_sum[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of block_sum[0..nb) in place, total to block_sum[nb] (single CTA)
+__global__ void __launch_bounds__(1024)
+uam_k_scan_blocks(unsigned long long* __restrict__ block_sum, int nb) {
+    __shared__ unsigned long long warp_tot[32];
+    const int per = (nb + 1023) / 1024;
+    const int lo = min((int)threadIdx.x * per, nb), hi = min(lo + per, nb);
+    unsigned long long local = 0;
+    for (int i = lo; i < hi; ++i) local += block_sum[i];
+    unsigned long long incl = local;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long w = warp_tot[lane];
+        unsigned long long wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned long long run = warp_tot[warp] + incl - local;
+    for (int i = lo; i < hi; ++i) {
+        const unsigned long long c = block_sum[i];
+        block_sum[i] = run;
+        run += c;
+    }
+    if (threadIdx.x == 1023) block_sum[nb] = run;
+}
+
+// third pass: out(i, exclusive prefix) for every element with a non-zero count
+template <class F, class OUT>
+__global__ void __launch_bounds__(256)
+uam_k_scan_apply(F f, long long n, const unsigned long long* __restrict__ block_sum, OUT out) {
+    __shared__ unsigned long long warp_sum[8];
+    const long long base = (long long)blockIdx.x * UAM_SCAN_CHUNK + (long long)threadIdx.x * UAM_SCAN_PER_THREAD;
+    int cnt[UAM_SCAN_PER_THREAD];
+    unsigned long long c = 0;
+    for (int k = 0; k < UAM_SCAN_PER_THREAD; ++k) {
+        cnt[k] = base + k < n ? f(base + k) : 0;
+        c += (unsigned long long)cnt[k];
+    }
+    unsigned long long incl = c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    unsigned long long run = block_sum[blockIdx.x] + incl - c;
+    for (int w = 0; w < warp; ++w) run += warp_sum[w];
+    for (int k = 0; k < UAM_SCAN_PER_THREAD; ++k) {
+        if (base + k < n) out(base + k, run, cnt[k]);
+        run += (unsigned long long)cnt[k];
+    }
+}
+
+struct UamRootCode {       // a root gets the code -2 - rank (rank = number of roots before it in raster-scan order)
+    int* L;
+    __device__ void operator()(long long i, unsigned long long prefix, int cnt) const {
+        if (cnt) L[i] = -2 - (int)prefix;
+    }
+};
+struct UamOffsets {
+    long long* off;
+    __device__ void operator()(long long i, unsigned long long prefix, int) const { off[i] = (long long)prefix; }
+};
+
+// labels: 0 = background, 1 + rank of the component's root
+__global__ void __launch_bounds__(256)
+uam_k_ccl_relabel(long long n, const int* __restrict__ L, int32_t* __restrict__ labels) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int v = L[i];
+    int lab = 0;
+    if (v < -1) lab = -1 - v;                 // a root: code -2 - rank -> 1 + rank
+    else if (v >= 0) lab = -1 - L[v];         // v is a root index (flattened); its entry holds the code
+    labels[i] = lab;
+}
+
+// ---- per-component statistics ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+uam_k_comp_init(int n_comp, unsigned long long* __restrict__ area, int* __restrict__ bbox) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_comp) return;
+    area[c] = 0ull;
+    bbox[4 * c + 0] = INT_MAX; bbox[4 * c + 1] = -1; bbox[4 * c + 2] = INT_MAX; bbox[4 * c + 3] = -1;   // rmin rmax cmin cmax
+}
+
+// one thread per cell; the lanes of a warp that hold the same label combine (match_any) and their leader does the atomics
+__global__ void __launch_bounds__(256)
+uam_k_comp_stats(const int32_t* __restrict__ labels, int H, int W, int n_comp, unsigned long long* __restrict__ area,
+                 int* __restrict__ bbox, unsigned* __restrict__ bad) {
+    const long long n = (long long)H * W;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int lab = i < n ? labels[i] : 0;
+    if (lab < 0 || lab > n_comp) { atomicOr(bad, 1u); lab = 0; }
+    const int row = i < n ? (int)(i / W) : 0, col = i < n ? (int)(i - (long long)row * W) : 0;
+    const unsigned peers = __match_any_sync(0xffffffffu, lab);
+    if (lab == 0) return;
+    int rmin = row, rmax = row, cmin = col, cmax = col;
+    // reduce over the peer group (all lanes of the group execute the same shuffles: iterate over the mask's set bits)
+    const int leader = __ffs(peers) - 1;
+    for (unsigned m = peers & ~(1u << leader); m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const int r = __shfl_sync(peers, row, src), c = __shfl_sync(peers, col, src);
+        rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+    }
+    if (lane == leader) {
+        const int c = lab - 1;
+        atomicAdd(&area[c], (unsigned long long)__popc(peers));
+        atomicMin(&bbox[4 * c + 0], rmin); atomicMax(&bbox[4 * c + 1], rmax);
+        atomicMin(&bbox[4 * c + 2], cmin); atomicMax(&bbox[4 * c + 3], cmax);
+    }
+}
+
+// ---- minimum-area rectangles -------------------------------------------------------------------------------------
+// slot[label] = position of the component in the caller's list (-1 = not asked for); heights = grid lines it spans
+__global__ void uam_k_rect_slots(const int32_t* __restrict__ ids, int K, int n_comp, const int* __restrict__ bbox,
+                                 int* __restrict__ slot, int* __restrict__ lines, unsigned* __restrict__ bad) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int id = ids[k];
+    if (id < 1 || id > n_comp || bbox[4 * (id - 1) + 1] < 0) { atomicOr(bad, 2u); lines[k] = 0; return; }
+    if (atomicExch(&slot[id], k) != -1) atomicOr(bad, 4u);       // listed twice
+    lines[k] = bbox[4 * (id - 1) + 1] - bbox[4 * (id - 1) + 0] + 2;      // grid lines rmin .. rmax + 1
+}
+
+__global__ void __launch_bounds__(256)
+uam_k_fill_i32(int* __restrict__ p, long long n, int v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// Column extremes per grid line: a cell (row, col) of component c touches the grid lines y = row and y = row + 1 with corner
+// x from col to col + 1.  Only run ends write (the left end gives the minimum, the right end the maximum).
+__global__ void __launch_bounds__(256)
+uam_k_rect_extremes(const int32_t* __restrict__ labels, int H, int W, const int* __restrict__ slot,
+                    const int32_t* __restrict__ ids, const int* __restrict__ bbox, const long long* __restrict__ off,
+                    int* __restrict__ xl, int* __restrict__ xr) {
+    const long long n = (long long)H * W;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int lab = labels[i];
+    if (lab == 0) return;
+    const int k = slot[lab];
+    if (k < 0) return;
+    const int row = (int)(i / W), col = (int)(i - (long long)row * W);
+    const bool left_end = col == 0 || labels[i - 1] != lab;
+    const bool right_end = col + 1 == W || labels[i + 1] != lab;
+    if (!left_end && !right_end) return;
+    const long long o = off[k] + (row - bbox[4 * (lab - 1)]);
+    if (left_end) { atomicMin(&xl[o], col); atomicMin(&xl[o + 1], col); }
+    if (right_end) { atomicMax(&xr[o], col + 1); atomicMax(&xr[o + 1], col + 1); }
+}
+
+__device__ __forceinline__ long long uam_cross(long long ax, long long ay, long long bx, long long by) { return ax * by - ay * bx; }
+
+// One CTA per listed component.  hull: scratch for 2 * lines + 2 vertices (int2) at hull_off = 2 * off[k] + 2 * k.
+// rect out: 4 corners (x, y) in world coordinates, counter-clockwise in pixel space starting at the corner that lies on the
+// chosen hull edge's line at the smallest projection; info out: hull vertices, chosen edge.
+__global__ void __launch_bounds__(128)
+uam_k_rect_hull(const int32_t* __restrict__ ids, int K, const int* __restrict__ bbox, const long long* __restrict__ off,
+                const int* __restrict__ xl, const int* __restrict__ xr, int2* __restrict__ hull_all, double x0, double dx,
+                double y0, double dy, double* __restrict__ rect, int* __restrict__ info) {
+    const int k = blockIdx.x;
+    if (k >= K) return;
+    const int id = ids[k];
+    const int rmin = bbox[4 * (id - 1)], lines = bbox[4 * (id - 1) + 1] - rmin + 2;
+    const long long o = off[k];
+    int2* hull = hull_all + 2 * o + 2 * k;
+    __shared__ int s_nh;
+    if (threadIdx.x == 0) {
+        // left chain, top to bottom: x as a function of y must be convex (hull's left side); right chain likewise concave.
+        // Counter-clockwise order in (x right, y down) screen coordinates = left chain downwards, then right chain upwards.
+        int nl = 0;
+        for (int t = 0; t < lines; ++t) {
+            const int2 p = make_int2(xl[o + t], rmin + t);
+            while (nl >= 2 && uam_cross(hull[nl - 1].x - hull[nl - 2].x, hull[nl - 1].y - hull[nl - 2].y, p.x - hull[nl - 2].x,
+                                        p.y - hull[nl - 2].y) >= 0) --nl;      // keep strictly convex turns only
+            hull[nl++] = p;
+        }
+        int nr0 = nl, nh = nl;
+        for (int t = lines - 1; t >= 0; --t) {
+            const int2 p = make_int2(xr[o + t], rmin + t);
+            while (nh - nr0 >= 2 && uam_cross(hull[nh - 1].x - hull[nh - 2].x, hull[nh - 1].y - hull[nh - 2].y, p.x - hull[nh - 2].x,
+                                              p.y - hull[nh - 2].y) >= 0) --nh;
+            hull[nh++] = p;
+        }
+        // the corners where the chains meet: bottom-left -> bottom-right and top-right -> top-left are hull edges when the
+        // x differ; the chains never share a vertex because xr > xl on every line
+        s_nh = nh;
+    }
+    __syncthreads();
+    const int nh = s_nh;
+    // the joined polygon (left chain down, right chain up) can have a reflex turn only at the 4 chain ends; remove those
+    // by one more monotone pass done by thread 0 (cheap: at most a few pops)
+    __shared__ int s_nh2;
+    if (threadIdx.x == 0) {
+        // generic cyclic clean-up: repeat until no vertex is popped
+        int n = nh;
+        bool changed = true;
+        while (changed && n > 3) {
+            changed = false;
+            for (int v = 0; v < n && n > 3; ++v) {
+                const int2 a = hull[(v + n - 1) % n], b = hull[v], c = hull[(v + 1) % n];
+                if (uam_cross(b.x - a.x, b.y - a.y, c.x - a.x, c.y - a.y) >= 0) {        // not a strict turn of the chains' sense
+                    for (int w = v; w + 1 < n; ++w) hull[w] = hull[w + 1];
+                    --n; --v;
+                    changed = true;
+                }
+            }
+        }
+        s_nh2 = n;
+    }
+    __syncthreads();
+    const int n = s_nh2;
+    // every hull edge as the rectangle's direction: exact integer extents, area = (du * dv) / |e|^2
+    unsigned long long best_num = 0, best_den = 0;
+    int best_edge = -1;
+    long long b_umin = 0, b_umax = 0, b_v = 0;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int2 a = hull[e], b = hull[(e + 1) % n];
+        const long long ex = b.x - a.x, ey = b.y - a.y;
+        long long umin = 0, umax = 0, vext = 0;          // projections of (p - a) on e and on the inward normal
+        for (int q = 0; q < n; ++q) {
+            const long long px = hull[q].x - a.x, py = hull[q].y - a.y;
+            const long long u = px * ex + py * ey, v = uam_cross(px, py, ex, ey);      // v >= 0 for this orientation
+            umin = min(umin, u); umax = max(umax, u);
+            vext = max(vext, v < 0 ? -v : v);
+        }
+        const unsigned long long num = (unsigned long long)(umax - umin) * (unsigned long long)vext;
+        const unsigned long long den = (unsigned long long)(ex * ex + ey * ey);
+        // num / den < best_num / best_den  <=>  num * best_den < best_num * den   (128-bit products)
+        bool better = best_edge < 0;
+        if (!better) {
+            const unsigned __int128 l = (unsigned __int128)num * best_den, r = (unsigned __int128)best_num * den;
+            better = l < r;
+        }
+        if (better) { best_num = num; best_den = den; best_edge = e; b_umin = umin; b_umax = umax; b_v = vext; }
+    }
+    // block argmin, ties to the lowest edge index
+    __shared__ unsigned long long s_num[128], s_den[128];
+    __shared__ int s_edge[128];
+    __shared__ long long s_u0[128], s_u1[128], s_v[128];
+    s_num[threadIdx.x] = best_num; s_den[threadIdx.x] = best_den; s_edge[threadIdx.x] = best_edge;
+    s_u0[threadIdx.x] = b_umin; s_u1[threadIdx.x] = b_umax; s_v[threadIdx.x] = b_v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int w = -1;
+        for (int t = 0; t < (int)blockDim.x; ++t) {
+            if (s_edge[t] < 0) continue;
+            bool better = w < 0;
+            if (!better) {
+                const unsigned __int128 l = (unsigned __int128)s_num[t] * s_den[w], r = (unsigned __int128)s_num[w] * s_den[t];
+                better = l < r || (l == r && s_edge[t] < s_edge[w]);
+            }
+            if (better) w = t;
+        }
+        const int e = s_edge[w];
+        const int2 a = hull[e], b = hull[(e + 1) % n];
+        const double ex = (double)(b.x - a.x), ey = (double)(b.y - a.y), den = (double)s_den[w];
+        // inward normal of a hull edge in this orientation: v = cross(p - a, e) >= 0  ->  n = (ey, -ex)
+        const double nx = ey, ny = -ex;
+        const double u0 = (double)s_u0[w] / den, u1 = (double)s_u1[w] / den, vv = (double)s_v[w] / den;
+        const double cx[4] = {a.x + u0 * ex, a.x + u1 * ex, a.x + u1 * ex + vv * nx, a.x + u0 * ex + vv * nx};
+        const double cy[4] = {a.y + u0 * ey, a.y + u1 * ey, a.y + u1 * ey + vv * ny, a.y + u0 * ey + vv * ny};
+        for (int c = 0; c < 4; ++c) {
+            rect[8 * (size_t)k + 2 * c + 0] = x0 + cx[c] * dx;
+            rect[8 * (size_t)k + 2 * c + 1] = y0 + cy[c] * dy;
+        }
+        if (info) { info[2 * k] = n; info[2 * k + 1] = e; }
+    }
+}
+
+template <class F, class OUT>
+int uam_scan(uam_ctx* ctx, F f, long long n, OUT out, unsigned long long* block_sum, unsigned long long* h_total, cudaStream_t st) {
+    const int nb = (int)((n + UAM_SCAN_CHUNK - 1) / UAM_SCAN_CHUNK);
+    uam_k_scan_counts<<<nb, 256, 0, st>>>(f, n, block_sum);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_scan_counts");
+    uam_k_scan_blocks<<<1, 1024, 0, st>>>(block_sum, nb);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_scan_blocks");
+    uam_k_scan_apply<<<nb, 256, 0, st>>>(f, n, block_sum, out);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_scan_apply");
+    if (h_total) {
+        UAM_CUDA(ctx, cudaMemcpyAsync(h_total, block_sum + nb, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        UAM_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return UAM_OK;
+}
+
+}  // namespace
+
+extern "C" int uam_label_components(uam_ctx* ctx, const uint8_t* d_mask, int H, int W, int connectivity, int32_t* d_labels,
+                                    int32_t* h_n_components, void* stream) {
+    if (!ctx) return UAM_ERR_INVALID;
+    if (H < 0 || W < 0) return uam_fail(ctx, UAM_ERR_INVALID, "negative raster size");
+    if (connectivity != 4 && connectivity != 8) return uam_fail(ctx, UAM_ERR_INVALID, "connectivity must be 4 or 8");
+    const long long n = (long long)H * W;
+    if (n >= (1ll << 31) - 2) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "rasters of 2^31 cells or more are not supported");
+    if (h_n_components) *h_n_components = 0;
+    if (n == 0) return UAM_OK;
+    if (!d_mask || !d_labels) return uam_fail(ctx, UAM_ERR_INVALID, "NULL pointer");
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = uam_pick_stream(ctx, stream);
+    const int nb = (int)((n + UAM_SCAN_CHUNK - 1) / UAM_SCAN_CHUNK);
+    UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, (size_t)n * 4 + (size_t)(nb + 2) * 8 + 256));
+    unsigned long long* block_sum = (unsigned long long*)ctx->d_scratch;
+    int* L = (int*)(block_sum + nb + 2);
+    const unsigned ctas = (unsigned)((n + 255) / 256);
+    uam_k_ccl_init<<<ctas, 256, 0, st>>>(d_mask, H, W, L);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_init");
+    uam_k_ccl_merge<<<ctas, 256, 0, st>>>(d_mask, H, W, connectivity == 8 ? 1 : 0, L);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_merge");
+    uam_k_ccl_flatten<<<ctas, 256, 0, st>>>(n, L);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_flatten");
+    unsigned long long total = 0;
+    UAM_TRY(uam_scan(ctx, UamIsRoot{L}, n, UamRootCode{L}, block_sum, &total, st));
+    uam_k_ccl_relabel<<<ctas, 256, 0, st>>>(n, L, d_labels);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_relabel");
+    if (h_n_components) *h_n_components = (int32_t)total;
+    return UAM_OK;
+}
+
+extern "C" int uam_component_stats(uam_ctx* ctx, const int32_t* d_labels, int H, int W, int n_components, int64_t* d_area,
+                                   int32_t* d_bbox, void* stream) {
+    if (!ctx) return UAM_ERR_INVALID;
+    if (H < 0 || W < 0 || n_components < 0) return uam_fail(ctx, UAM_ERR_INVALID, "negative size");
+    if (n_components == 0) return UAM_OK;
+    if (!d_labels || !d_area || !d_bbox) return uam_fail(ctx, UAM_ERR_INVALID, "NULL pointer");
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = uam_pick_stream(ctx, stream);
+    const long long n = (long long)H * W;
+    UAM_TRY(uam_reserve(ctx, &ctx->d_cull_scratch, &ctx->cull_scratch_bytes, 256));
+    unsigned* bad = (unsigned*)ctx->d_cull_scratch;
+    UAM_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, st));
+    uam_k_comp_init<<<(n_components + 255) / 256, 256, 0, st>>>(n_components, (unsigned long long*)d_area, d_bbox);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_comp_init");
+    if (n > 0) {
+        uam_k_comp_stats<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_labels, H, W, n_components, (unsigned long long*)d_area, d_bbox, bad);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_comp_stats");
+    }
+    unsigned h_bad = 0;
+    UAM_CUDA(ctx, cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
+    UAM_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_bad) return uam_fail(ctx, UAM_ERR_INVALID, "labels outside 0 .. n_components");
+    return UAM_OK;
+}
+
+extern "C" int uam_component_rects(uam_ctx* ctx, const int32_t* d_labels, int H, int W, int n_components, const int32_t* d_bbox,
+                                   const int32_t* d_ids, int K, double x0, double dx, double y0, double dy, double* d_rect,
+                                   int32_t* d_info, void* stream) {
+    if (!ctx) return UAM_ERR_INVALID;
+    if (H < 0 || W < 0 || n_components < 0 || K < 0) return uam_fail(ctx, UAM_ERR_INVALID, "negative size");
+    if (K == 0) return UAM_OK;
+    if (!d_labels || !d_bbox || !d_ids || !d_rect) return uam_fail(ctx, UAM_ERR_INVALID, "NULL pointer");
+    if (!(fabs(fabs(dx) - fabs(dy)) <= 1e-12 * fabs(dx)) || dx == 0.0)
+        return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "minimum-area rectangles need square cells (|dx| == |dy|)");
+    if (H > 32766 || W > 32766) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "rasters beyond 32766 cells per side: the exact area comparison is sized for 2^15");
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = uam_pick_stream(ctx, stream);
+    const long long n = (long long)H * W;
+    const int nb = (K + UAM_SCAN_CHUNK - 1) / UAM_SCAN_CHUNK;
+    // fixed part of the scratch: flags | block sums | slot[n_components + 1] | lines[K] | off[K + 1]
+    const size_t fixed = 256 + (size_t)(nb + 2) * 8 + (size_t)(n_components + 1) * 4 + (size_t)K * 4 + 16 + (size_t)(K + 1) * 8;
+    UAM_TRY(uam_reserve(ctx, &ctx->d_cull_scratch, &ctx->cull_scratch_bytes, fixed));
+    unsigned* bad = (unsigned*)ctx->d_cull_scratch;
+    unsigned long long* block_sum = (unsigned long long*)((char*)ctx->d_cull_scratch + 256);
+    long long* off = (long long*)(block_sum + nb + 2);
+    int* slot = (int*)(off + K + 1);
+    int* lines = slot + n_components + 1;
+    UAM_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, st));
+    uam_k_fill_i32<<<(n_components + 1 + 255) / 256, 256, 0, st>>>(slot, n_components + 1, -1);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_fill_i32");
+    uam_k_rect_slots<<<(K + 255) / 256, 256, 0, st>>>(d_ids, K, n_components, d_bbox, slot, lines, bad);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_rect_slots");
+    unsigned long long total = 0;
+    UAM_TRY(uam_scan(ctx, UamIntArray{lines}, (long long)K, UamOffsets{off}, block_sum, &total, st));
+    unsigned h_bad = 0;
+    UAM_CUDA(ctx, cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
+    UAM_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_bad) return uam_fail(ctx, UAM_ERR_INVALID, "component ids must be distinct labels in 1 .. n_components of non-empty components");
+    // per-line extremes (2 x total ints) + hull vertices (2 * total + 2 * K int2)
+    const size_t need = (size_t)total * 8 + ((size_t)total * 2 + (size_t)K * 2) * 8 + 256;
+    UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, need));
+    int* xl = (int*)ctx->d_scratch;
+    int* xr = xl + total;
+    int2* hull = (int2*)(xr + total);           // 8 * total bytes in: still 8-byte aligned
+    uam_k_fill_i32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xl, (long long)total, INT_MAX);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_fill_i32");
+    uam_k_fill_i32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xr, (long long)total, -1);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_fill_i32");
+    uam_k_rect_extremes<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_labels, H, W, slot, d_ids, d_bbox, off, xl, xr);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_rect_extremes");
+    uam_k_rect_hull<<<K, 128, 0, st>>>(d_ids, K, d_bbox, off, xl, xr, hull, x0, dx, y0, dy, d_rect, d_info);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_rect_hull");
+    return UAM_OK;
+}

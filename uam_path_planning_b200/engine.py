@@ -333,6 +333,49 @@ class Engine:
                                       C.c_void_p(cl.data_ptr()) if cl is not None else None, st))
         return d2, cl
 
+    # ---- polygon front-end (map_generation: mask -> connected regions -> minimum-area rectangles) -------------
+    def label_components(self, mask, connectivity: int = 4):
+        """mask (H,W) uint8 CUDA tensor -> (labels (H,W) int32, n): 0 = background, components 1..n in raster-scan order
+        of their first cell (scipy.ndimage.label's numbering)."""
+        import torch
+        assert _is_tensor(mask) and mask.dtype == torch.uint8 and mask.dim() == 2
+        st = self._tensor_args(mask)
+        H, W = mask.shape
+        labels = torch.empty((H, W), dtype=torch.int32, device=mask.device)
+        n = C.c_int32(0)
+        self._check(self._lib.uam_label_components(self._h, C.c_void_p(mask.data_ptr()), H, W, int(connectivity),
+                                                   C.c_void_p(labels.data_ptr()), C.byref(n), st))
+        return labels, int(n.value)
+
+    def component_stats(self, labels, n: int):
+        """labels (H,W) int32 -> (area (n,) int64 cells per component, bbox (n,4) int32 {row min, row max, col min, col max})."""
+        import torch
+        assert _is_tensor(labels) and labels.dtype == torch.int32 and labels.dim() == 2
+        st = self._tensor_args(labels)
+        H, W = labels.shape
+        area = torch.empty(n, dtype=torch.int64, device=labels.device)
+        bbox = torch.empty((n, 4), dtype=torch.int32, device=labels.device)
+        self._check(self._lib.uam_component_stats(self._h, C.c_void_p(labels.data_ptr()), H, W, int(n),
+                                                  C.c_void_p(area.data_ptr()), C.c_void_p(bbox.data_ptr()), st))
+        return area, bbox
+
+    def component_rects(self, labels, n: int, bbox, ids, geo, want_info: bool = False):
+        """Minimum-area enclosing rectangle of the cell corners of the components `ids` (K distinct labels) -> (K,4,2)
+        float64 world coordinates, corners consecutive around the rectangle."""
+        import torch
+        assert _is_tensor(labels) and labels.dtype == torch.int32 and labels.dim() == 2
+        ids = torch.as_tensor(ids, dtype=torch.int32, device=labels.device).reshape(-1).contiguous()
+        st = self._tensor_args(labels, bbox, ids)
+        H, W = labels.shape
+        K = ids.numel()
+        x0, dx, y0, dy = [float(v) for v in geo]
+        rect = torch.empty((K, 4, 2), dtype=torch.float64, device=labels.device)
+        info = torch.empty((K, 2), dtype=torch.int32, device=labels.device) if want_info else None
+        self._check(self._lib.uam_component_rects(self._h, C.c_void_p(labels.data_ptr()), H, W, int(n), C.c_void_p(bbox.data_ptr()),
+                                                  C.c_void_p(ids.data_ptr()), K, x0, dx, y0, dy, C.c_void_p(rect.data_ptr()),
+                                                  C.c_void_p(info.data_ptr()) if info is not None else None, st))
+        return (rect, info) if want_info else rect
+
     def grid_search(self, cost, sources, blocked=None, want_parent: bool = True):
         """Q cost-to-go sweeps on an 8-connected grid (build-defined extension, include/uam_b200.h).
         2-D: cost (H,W) uint16 CUDA tensor, sources (Q,2) int32 (row, col), blocked (H,W) uint8 or None ->
