@@ -98,6 +98,7 @@ def main():
     ap.add_argument('--c4-size', type=int, default=16384)
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--skip-c4', action='store_true')
+    ap.add_argument('--skip-c5', action='store_true')
     ap.add_argument('--c5-queries', type=int, default=16)
     ap.add_argument('--c5-queries-bands', type=int, default=4)
     ap.add_argument('--no-cpu', action='store_true')
@@ -197,7 +198,37 @@ def main():
            'hbm_peak_GBps': peak}
     ms = ev_time(torch, lambda: eng.dem_mask(dem, 0.0), args.reps)
     res['dem_mask'] = {'ms': ms, 'Mcell_s': cells / ms / 1e3, 'frac': cells * 5 / (ms * 1e-3) / 1e9 / peak}
-    del dem
+    # polygon front-end: land mask -> 4-connected regions -> cell counts -> minimum-area rectangles of the
+    # regions over min_area.  Wall-clock per call (each step reads a count back); algorithmic bytes of the labelling =
+    # 1 B mask in + 4 B label out per cell
+    mask = eng.dem_mask(dem, 0.0)
+    cellm = 64000.0 * (n / 8192) / n                     # metres per cell (a 64 km map at 8192^2)
+    geo_m = (0.0, cellm, 0.0, -cellm)
+
+    def wall(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3 / reps, out
+    ms_l, (labels, ncomp) = wall(lambda: eng.label_components(mask, 4))
+    ms_s, (area, bbox) = wall(lambda: eng.component_stats(labels, ncomp))
+    ids = (torch.nonzero(area.double() * cellm * cellm > 750000.0).reshape(-1) + 1).to(torch.int32)
+    ms_r, rect = wall(lambda: eng.component_rects(labels, ncomp, bbox, ids, geo_m))
+    res['polygon_front_end'] = {'components': ncomp, 'over_min_area': int(ids.numel()), 'label_ms': ms_l, 'stats_ms': ms_s,
+                                'rects_ms': ms_r, 'label_Mcell_s': cells / ms_l / 1e3,
+                                'label_frac_of_hbm_peak': cells * 5 / (ms_l * 1e-3) / 1e9 / peak}
+    if not args.no_cpu:
+        from oracle import uam_oracle as orc
+        crop = mask[:4096, :4096].cpu().numpy()
+        t0 = time.perf_counter()
+        lab_c, n_c = orc.label_components(crop, 4)
+        res['polygon_front_end']['cpu_scipy_label_Mcell_s'] = crop.size / (time.perf_counter() - t0) / 1e6
+        lab_g, n_g = eng.label_components(mask[:4096, :4096].contiguous(), 4)
+        res['polygon_front_end']['crop_labels_equal_scipy'] = bool(n_g == n_c and np.array_equal(lab_g.cpu().numpy(), lab_c))
+    del dem, mask, labels, area, bbox, rect
     KMn = 64.0 * n / 8192
     mm = uam.RegionMap()
     for r in ('Land', 'Population', 'Hist'):
@@ -231,6 +262,8 @@ def main():
     print(json.dumps(res))
     del occ, mm
     del eng
+    if args.skip_c5:
+        return
     run_c5(args, torch, uam, dev)
 
 

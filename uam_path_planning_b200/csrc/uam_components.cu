@@ -232,31 +232,94 @@ uam_k_comp_init(int n_comp, unsigned long long* __restrict__ area, int* __restri
     bbox[4 * c + 0] = INT_MAX; bbox[4 * c + 1] = -1; bbox[4 * c + 2] = INT_MAX; bbox[4 * c + 3] = -1;   // rmin rmax cmin cmax
 }
 
-// one thread per cell; the lanes of a warp that hold the same label combine (match_any) and their leader does the atomics
+// A CTA owns 4096 consecutive cells, a thread 16 consecutive ones.  A thread keeps one open entry {label, cells, bbox}
+// while it walks its cells (a row run keeps its label), entries closed early go straight to the global atomics (region
+// borders only); the entries still open at the end are combined per warp (match_any) and then per CTA (a short list in
+// shared memory), so a region that covers whole CTAs costs 5 atomics per 4096 cells instead of 5 per warp.
+#define UAM_STATS_PER_THREAD 16
+struct UamCompEntry {
+    int lab, rmin, rmax, cmin, cmax;
+    unsigned cnt;
+};
+
+__device__ __forceinline__ void uam_comp_flush(const UamCompEntry& e, unsigned long long* __restrict__ area, int* __restrict__ bbox) {
+    const int c = e.lab - 1;
+    atomicAdd(&area[c], (unsigned long long)e.cnt);
+    atomicMin(&bbox[4 * c + 0], e.rmin); atomicMax(&bbox[4 * c + 1], e.rmax);
+    atomicMin(&bbox[4 * c + 2], e.cmin); atomicMax(&bbox[4 * c + 3], e.cmax);
+}
+
 __global__ void __launch_bounds__(256)
 uam_k_comp_stats(const int32_t* __restrict__ labels, int H, int W, int n_comp, unsigned long long* __restrict__ area,
                  int* __restrict__ bbox, unsigned* __restrict__ bad) {
+    __shared__ UamCompEntry s_ent[8];
     const long long n = (long long)H * W;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    int lab = i < n ? labels[i] : 0;
-    if (lab < 0 || lab > n_comp) { atomicOr(bad, 1u); lab = 0; }
-    const int row = i < n ? (int)(i / W) : 0, col = i < n ? (int)(i - (long long)row * W) : 0;
-    const unsigned peers = __match_any_sync(0xffffffffu, lab);
-    if (lab == 0) return;
-    int rmin = row, rmax = row, cmin = col, cmax = col;
-    // reduce over the peer group (all lanes of the group execute the same shuffles: iterate over the mask's set bits)
-    const int leader = __ffs(peers) - 1;
-    for (unsigned m = peers & ~(1u << leader); m; m &= m - 1) {
-        const int src = __ffs(m) - 1;
-        const int r = __shfl_sync(peers, row, src), c = __shfl_sync(peers, col, src);
-        rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+    const long long base = ((long long)blockIdx.x * 256 + threadIdx.x) * UAM_STATS_PER_THREAD;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    UamCompEntry cur;
+    cur.lab = 0; cur.cnt = 0; cur.rmin = cur.rmax = cur.cmin = cur.cmax = 0;
+    if (base < n) {
+        int row = (int)(base / W), col = (int)(base - (long long)row * W);
+        for (int k = 0; k < UAM_STATS_PER_THREAD && base + k < n; ++k) {
+            int lab = labels[base + k];
+            if (lab < 0 || lab > n_comp) { atomicOr(bad, 1u); lab = 0; }
+            if (lab != cur.lab) {
+                if (cur.lab) uam_comp_flush(cur, area, bbox);
+                cur.lab = lab; cur.cnt = 0; cur.rmin = cur.rmax = row; cur.cmin = cur.cmax = col;
+            }
+            if (lab) {
+                cur.cnt += 1;
+                cur.rmax = row;                       // rows only grow along the walk
+                cur.cmin = min(cur.cmin, col); cur.cmax = max(cur.cmax, col);
+            }
+            if (++col == W) { col = 0; ++row; }
+        }
     }
-    if (lane == leader) {
-        const int c = lab - 1;
-        atomicAdd(&area[c], (unsigned long long)__popc(peers));
-        atomicMin(&bbox[4 * c + 0], rmin); atomicMax(&bbox[4 * c + 1], rmax);
-        atomicMin(&bbox[4 * c + 2], cmin); atomicMax(&bbox[4 * c + 3], cmax);
+    // per warp: lanes whose open entries carry the same label combine
+    const unsigned peers = __match_any_sync(0xffffffffu, cur.lab);
+    const int leader = __ffs(peers) - 1;
+    // every lane publishes its entry in turn, the leader of a group folds its peers
+    UamCompEntry tot = cur;
+    for (int src = 0; src < 32; ++src) {
+        const int l = __shfl_sync(0xffffffffu, cur.lab, src);
+        const unsigned c = __shfl_sync(0xffffffffu, cur.cnt, src);
+        const int r0 = __shfl_sync(0xffffffffu, cur.rmin, src), r1 = __shfl_sync(0xffffffffu, cur.rmax, src);
+        const int c0 = __shfl_sync(0xffffffffu, cur.cmin, src), c1 = __shfl_sync(0xffffffffu, cur.cmax, src);
+        if (lane == leader && src != lane && l == cur.lab && cur.lab) {
+            tot.cnt += c;
+            tot.rmin = min(tot.rmin, r0); tot.rmax = max(tot.rmax, r1);
+            tot.cmin = min(tot.cmin, c0); tot.cmax = max(tot.cmax, c1);
+        }
+    }
+    // per CTA: the first leader of each warp whose label equals the warp-0 entry's label joins it, the others go to global
+    const bool is_leader = cur.lab != 0 && lane == leader;
+    // the lowest-lane leader of the warp represents it in shared memory
+    const unsigned leaders = __ballot_sync(0xffffffffu, is_leader);
+    const bool rep = is_leader && lane == __ffs(leaders) - 1;
+    if (lane == 0) s_ent[warp].lab = 0;
+    __syncwarp();
+    if (rep) s_ent[warp] = tot;
+    else if (is_leader) uam_comp_flush(tot, area, bbox);
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        // entry w is folded into the first earlier entry with the same label; the first of each label flushes the sum
+        const UamCompEntry mine = s_ent[threadIdx.x];
+        if (mine.lab) {
+            bool first = true;
+            for (int w = 0; w < (int)threadIdx.x; ++w) first = first && s_ent[w].lab != mine.lab;
+            if (first) {
+                UamCompEntry sum = mine;
+                for (int w = threadIdx.x + 1; w < 8; ++w) {
+                    const UamCompEntry o = s_ent[w];
+                    if (o.lab == mine.lab) {
+                        sum.cnt += o.cnt;
+                        sum.rmin = min(sum.rmin, o.rmin); sum.rmax = max(sum.rmax, o.rmax);
+                        sum.cmin = min(sum.cmin, o.cmin); sum.cmax = max(sum.cmax, o.cmax);
+                    }
+                }
+                uam_comp_flush(sum, area, bbox);
+            }
+        }
     }
 }
 
@@ -483,7 +546,8 @@ extern "C" int uam_component_stats(uam_ctx* ctx, const int32_t* d_labels, int H,
     uam_k_comp_init<<<(n_components + 255) / 256, 256, 0, st>>>(n_components, (unsigned long long*)d_area, d_bbox);
     UAM_CHECK_LAUNCH(ctx, "uam_k_comp_init");
     if (n > 0) {
-        uam_k_comp_stats<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_labels, H, W, n_components, (unsigned long long*)d_area, d_bbox, bad);
+        const long long per_cta = 256ll * UAM_STATS_PER_THREAD;
+        uam_k_comp_stats<<<(unsigned)((n + per_cta - 1) / per_cta), 256, 0, st>>>(d_labels, H, W, n_components, (unsigned long long*)d_area, d_bbox, bad);
         UAM_CHECK_LAUNCH(ctx, "uam_k_comp_stats");
     }
     unsigned h_bad = 0;
