@@ -201,6 +201,45 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def analytic_c1(torch, dev, args, B=100000, n_cpu=2000):
+    import uam_path_planning_b200 as uam
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from conftest import build_product_problem
+    spec = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'fixture_main_map.json')))
+    N = 80
+    prob = build_product_problem(spec, N)
+    sol = uam.Solver(prob, {})
+    g = torch.Generator(device=dev).manual_seed(7)
+    d = torch.rand(B, device=dev, generator=g, dtype=torch.float64) * 1.8 - 0.9
+    Z = sol.candidates_device(d)
+    Z[:, 2:-2] += torch.randn((B, 2 * N), device=dev, generator=g, dtype=torch.float64) * 0.05
+    for _ in range(3):
+        cost, col, _ = prob.score(Z)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        cost, col, _ = prob.score(Z)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    out = {'workload': f'C1: Problem.get_cost + collides on the main.py map ({len(prob.map.obstacles)} obstacles, '
+                       f'{sum(len(r) for r in prob.map._region_lists())} region shapes), N = {N}, {B} arc candidates + jitter',
+           'ms_per_batch': ms, 'paths_per_s': B / (ms * 1e-3), 'value': B * (N + 1) / (ms * 1e-3), 'unit': 'segment-evals/s',
+           'dtype': 'f64', 'collisions': int(col.sum().item())}
+    if not args.no_cpu:
+        from oracle import uam_oracle as orc
+        om = orc.OMap(spec)
+        Zh = Z[:n_cpu].cpu().numpy()
+        t0 = time.perf_counter()
+        c_ref = orc.get_cost(om, Zh, N, spec['weights'], spec['enlargement'], spec['options'])
+        k_ref = orc.path_collides(om, Zh, N)
+        dt = time.perf_counter() - t0
+        out['cpu_numpy_1core'] = {'paths': n_cpu, 'seconds': dt, 'paths_per_s': n_cpu / dt,
+                                  'max_rel_err_gpu_vs_oracle': float(np.max(np.abs(cost[:n_cpu].cpu().numpy() - c_ref) / np.abs(c_ref))),
+                                  'collide_equal': bool(np.array_equal(col[:n_cpu].cpu().numpy().astype(bool), k_ref))}
+    return out
+
+
 def workload_config(args, paths_per_step):
     return {'workload': f'C3: {args.raster}^2 raster, L=3 float32 layers + uint8 occupancy, scatter paths x {WP} waypoints, '
                         f'integral mode samples_per_cell={SPC}',
@@ -225,9 +264,13 @@ def run_ours(args):
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
     torch.cuda.set_device(local)
     dev = f'cuda:{local}'
+    # stdout carries the ONE JSON line and nothing else: NCCL prints its version banner on file descriptor 1 from C, so
+    # fd 1 is pointed at stderr for the whole run and the line is written to a saved copy of the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # keep NCCL's banner off stdout: stdout is the ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device(dev))
 
     n, B = args.raster, args.paths
@@ -303,6 +346,16 @@ def run_ours(args):
     rm.score_paths(Z, WEIGHTS, SPC, True, None, out=(cost, col))        # restore the integral-mode costs
     best_cost, best_idx = udist.decode_key(int(key.item()))
 
+    # ---- secondary: the reference's own function on the reference's own map (C1) ----------------------------------
+    # Problem.get_cost + Map.collides (path_generation/problem.py:38-44, map.py:41-43) on the main.py scenario (34 region
+    # shapes + 5 obstacle discs, N = 80), arcs of Solver.create_x_init + jitter; CPU: the float64 numpy oracle, one core
+    analytic = None
+    if rank == 0:
+        try:
+            analytic = analytic_c1(torch, dev, args)
+        except Exception as exc:              # a secondary figure must not take the headline down
+            analytic = {'error': repr(exc)}
+
     # ---- e2e: host buffers through the C-ABI host entry point ------------------------------------------------
     Zh = torch.empty((B, 2 * WP), dtype=torch.float64).pin_memory()
     Zh.copy_(Z)
@@ -372,6 +425,7 @@ def run_ours(args):
                                       'a DRAM-latency-bound gather, reported, not the roofline claim'},
             'gpu_launches': launches, 'clocks': clk,
             'best': {'cost': best_cost, 'index': best_idx},
+            'analytic_mode': analytic,
         }
         if world == 1 and not args.no_cpu:
             Lh, Oh = layers.cpu().numpy(), occ.cpu().numpy()
@@ -390,7 +444,8 @@ def run_ours(args):
                 'collide_equal': bool(np.array_equal(col[:nb].cpu().numpy().astype(bool), col_ref)),
                 'numpy_1core': {'value': rate1, 'paths': n1, 'seconds': dt1,
                                 'max_rel_diff_c_vs_numpy': float(np.max(np.abs(c_np - c_ref[:n1]) / np.abs(c_np)))}}
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + '\n')
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
