@@ -276,6 +276,20 @@ int uam_component_rects(uam_ctx* ctx, const int32_t* d_labels, int H, int W, int
  *                        in-plane ones: band below (8), band above (9).
  * Frontier-parallel tile relaxation (warp per 32 x 32 tile, Gauss-Seidel row sweeps with (min,+) warp scans); results
  * are bit-identical to Dijkstra.  Synchronises `stream` internally (the number of rounds is data dependent). */
+/* uam_grid_search_goals: start/goal queries.  As uam_grid_search_bands (bands >= 1; d_sources and d_goals are (Q,3) int32
+ *                        {band, row, col}), but a query stops as soon as nothing pending can lower its goal's distance:
+ *                        dist is exact for the goal and for every node closer to the source than the goal (nodes farther
+ *                        away hold upper bounds or 2^62), and the predecessors of those nodes are the ones of the full
+ *                        search (edge weights are positive for cost >= 1), so the extracted path is the same.  A goal
+ *                        outside the grid leaves the query unbounded.
+ * uam_grid_extract_paths: one path per query from d_parent (Q,bands,H,W): d_path (Q,max_len) int32 flat node ids from the
+ *                        source to the goal, d_len (Q) = nodes on the path, 0 = goal not reached, -k = the path has
+ *                        k > max_len nodes (nothing written). */
+int uam_grid_search_goals(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int bands, int H, int W,
+                          const int32_t* d_sources, const int32_t* d_goals, int Q, int64_t* d_dist, int32_t* d_parent,
+                          void* stream);
+int uam_grid_extract_paths(uam_ctx* ctx, const int32_t* d_parent, int bands, int H, int W, const int32_t* d_sources,
+                           const int32_t* d_goals, int Q, int max_len, int32_t* d_path, int32_t* d_len, void* stream);
 int uam_grid_search(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int H, int W,
                     const int32_t* d_sources, int Q, int64_t* d_dist, int32_t* d_parent, void* stream);
 int uam_grid_search_bands(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int bands, int H, int W,

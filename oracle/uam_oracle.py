@@ -738,3 +738,23 @@ def component_rects(labels, ids, geo):
         out[k, :, 1] = y0 + c[:, 1] * dy
         info[k] = (nh, e)
     return out, info
+
+
+def grid_path(parent: np.ndarray, start, goal):
+    """Node list (flat indices into the grid) from start to goal along the predecessors of ``grid_search``; empty when the
+    goal was not reached.  start / goal: (row, col) or (band, row, col)."""
+    shape = parent.shape
+    if len(shape) == 2:
+        start, goal = (0,) + tuple(start), (0,) + tuple(goal)
+        shape = (1,) + shape
+    p = parent.reshape(-1)
+    cells = shape[1] * shape[2]
+    s = start[0] * cells + start[1] * shape[2] + start[2]
+    v = goal[0] * cells + goal[1] * shape[2] + goal[2]
+    out = [v]
+    while v != s:
+        v = int(p[v])
+        if v < 0:
+            return []
+        out.append(v)
+    return out[::-1]

@@ -971,3 +971,79 @@ def test_dem_rectangles_pipeline(uam, torch, tmp_path):
     uam.save_polygons([r.tolist() for r in got['rects']], str(path))
     shapes = uam.get_var_from_file(str(path))
     assert len(shapes) == len(got['rects'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('Bn,H,W', [(1, 70, 90), (3, 64, 65), (1, 33, 200)])
+def test_grid_search_goal_bounded_and_paths(uam, torch, Bn, H, W):
+    """Start/goal queries: the goal-bounded search stops early but returns the goal's exact distance, exact distances and
+    the full search's predecessors for every node closer than the goal, hence the same path; paths come back as node
+    lists and resample into a solver seed."""
+    rng = np.random.default_rng(Bn * 100 + H)
+    cost = rng.integers(1, 400, (Bn, H, W)).astype(np.uint16)
+    blocked = (rng.random((Bn, H, W)) < 0.12).astype(np.uint8)
+    blocked[:, H // 2, 3:W - 9] = 1                      # a wall with a gap at both ends
+    Q = 12
+    src = np.stack([rng.integers(0, Bn, Q), rng.integers(0, H, Q), rng.integers(0, W, Q)], 1).astype(np.int32)
+    goal = np.stack([rng.integers(0, Bn, Q), rng.integers(0, H, Q), rng.integers(0, W, Q)], 1).astype(np.int32)
+    goal[0] = src[0]                                     # goal == source
+    goal[1] = np.clip(src[1] + [0, 2, 3], 0, [Bn - 1, H - 1, W - 1])        # a near goal
+    for q in range(Q):
+        blocked[tuple(src[q])] = 0
+    while any((goal[2] == src[q]).all() for q in range(Q)) or (goal[2] == goal[1]).all():
+        goal[2] = [rng.integers(0, Bn), rng.integers(0, H), rng.integers(0, W)]
+    blocked[tuple(goal[2])] = 1                          # a goal that cannot be reached
+    blocked[tuple(goal[1])] = 0
+    eng = uam.Engine()
+    ct, bt = torch.from_numpy(cost).cuda(), torch.from_numpy(blocked).cuda()
+    if Bn == 1:                                          # the 2-D calling form
+        dist, parent = eng.grid_search(ct[0], src[:, 1:], bt[0], goals=goal[:, 1:])
+        path, length = eng.grid_paths(parent, src[:, 1:], goal[:, 1:])
+        dist, parent = dist[:, None], parent[:, None]
+    else:
+        dist, parent = eng.grid_search(ct, src, bt, goals=goal)
+        path, length = eng.grid_paths(parent, src, goal)
+    work_bounded = eng.get_stat('grid_activations')
+    eng.grid_search(ct, src, bt)
+    assert work_bounded < eng.get_stat('grid_activations')
+    dist, parent, path, length = dist.cpu().numpy(), parent.cpu().numpy(), path.cpu().numpy(), length.cpu().numpy()
+    INF = 2 ** 62
+    for q in range(Q):
+        d_ref, p_ref = orc.grid_search(cost, tuple(src[q]), blocked)
+        dg = d_ref[tuple(goal[q])]
+        assert dist[q][tuple(goal[q])] == dg
+        near = d_ref < dg if dg < INF else np.ones_like(d_ref, dtype=bool)
+        assert np.array_equal(dist[q][near], d_ref[near]) and np.array_equal(parent[q][near], p_ref[near])
+        assert np.all(dist[q] >= d_ref)                  # everything else is an upper bound
+        ref_path = orc.grid_path(p_ref, tuple(src[q]), tuple(goal[q]))
+        assert length[q] == len(ref_path) and path[q, :length[q]].tolist() == ref_path
+    assert length[0] == 1 and length[2] == 0 and length[1] >= 2
+    # a buffer that is too short reports the length it needs
+    big = int(length.max())
+    if Bn == 1:
+        _, l2 = eng.grid_paths(torch.from_numpy(parent[:, 0]).cuda(), src[:, 1:], goal[:, 1:], max_len=big - 1)
+    else:
+        _, l2 = eng.grid_paths(torch.from_numpy(parent).cuda(), src, goal, max_len=big - 1)
+    l2 = l2.cpu().numpy()
+    assert (l2 == np.where(length == big, -big, length)).all()
+    # a path becomes a seed for the scorer: N points equally spaced along it, between map.x_start and map.x_goal
+    q = int(np.argmax(length))
+    geo = (0.0, 0.5, 10.0, 0.5)
+    m = uam.RegionMap()
+    m.x_start = [geo[0] + (src[q, 2] + 0.5) * geo[1], geo[2] + (src[q, 1] + 0.5) * geo[3]]
+    m.x_goal = [geo[0] + (goal[q, 2] + 0.5) * geo[1], geo[2] + (goal[q, 1] + 0.5) * geo[3]]
+    sol = uam.Solver(uam.Problem(m, 20, {}), {})
+    x = sol.seed_from_grid_path(path[q, :length[q]], (Bn, H, W), geo).reshape(-1, 2)
+    assert x.shape == (20, 2)
+    full = np.concatenate([[m.x_start], x, [m.x_goal]])
+    steps = np.sqrt(((full[1:] - full[:-1]) ** 2).sum(1))
+    v = path[q, :length[q]].astype(np.int64) % (H * W)
+    poly = np.stack([geo[0] + (v % W + 0.5) * geo[1], geo[2] + (v // W + 0.5) * geo[3]], 1)
+    route = np.sqrt(((poly[1:] - poly[:-1]) ** 2).sum(1)).sum()
+    assert steps.max() <= route / 21 + 1e-9 and steps.sum() >= 0.8 * route          # equal arc spacing; chords cut the zig-zags only
+    for pt in x:                                         # every seed point lies on the route
+        a, b = poly[:-1], poly[1:]
+        ab = b - a
+        den = np.maximum((ab * ab).sum(1), 1e-300)
+        t = np.clip(((pt - a) * ab).sum(1) / den, 0, 1)
+        assert np.sqrt((((a + t[:, None] * ab) - pt) ** 2).sum(1)).min() < 1e-9

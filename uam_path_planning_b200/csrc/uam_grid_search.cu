@@ -105,10 +105,16 @@ uam_k_grid_minkey(const unsigned long long* __restrict__ keys, size_t per_q, int
 __global__ void __launch_bounds__(256)
 uam_k_grid_select(unsigned long long* __restrict__ keys, size_t n, size_t per_q, const unsigned long long* __restrict__ minkey,
                   unsigned long long delta, unsigned* __restrict__ list, unsigned long long* __restrict__ list_key,
-                  unsigned* __restrict__ count) {
+                  unsigned* __restrict__ count, const long long* __restrict__ dist, const long long* __restrict__ goal_at) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
         const unsigned long long k = keys[t];
+        // goal-bounded query: an arrival that is not below the goal's current distance cannot lower it (edge weights are
+        // >= 0) -- the tile stays pending but is never relaxed; the query is finished when nothing below the bound is left
+        if (goal_at) {
+            const long long ga = goal_at[t / per_q];
+            if (ga >= 0 && k >= (unsigned long long)dist[ga]) continue;
+        }
         if (k < (unsigned long long)UAM_GRID_INF && k <= minkey[t / per_q] + delta) {
             keys[t] = (unsigned long long)UAM_GRID_INF;
             const unsigned pos = atomicAdd(count, 1u);
@@ -423,6 +429,43 @@ uam_k_grid_parent(const uint16_t* __restrict__ cost, UamGridGeo g, const long lo
     }
 }
 
+// flat index of each query's goal inside dist (q * nodes + node), -1 = no bound for this query (goal outside the grid)
+__global__ void uam_k_grid_goal_index(const int* __restrict__ goals, UamGridGeo g, long long* __restrict__ goal_at) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= g.Q) return;
+    int b, i, j;
+    const size_t cells = (size_t)g.H * g.W;
+    goal_at[q] = uam_grid_source(goals, g, q, b, i, j) ? (long long)((size_t)q * g.bands * cells + (size_t)b * cells + (size_t)i * g.W + j) : -1ll;
+}
+
+// One thread per query: follow the predecessors from the goal back to the source, then write the nodes source -> goal.
+// len[q] = nodes on the path; 0 = goal not reached (or source / goal outside the grid); -k = the path has k > max_len nodes.
+__global__ void uam_k_grid_extract(const int* __restrict__ parent, UamGridGeo g, const int* __restrict__ sources,
+                                   const int* __restrict__ goals, int max_len, int* __restrict__ path, int* __restrict__ len) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= g.Q) return;
+    const size_t cells = (size_t)g.H * g.W, nodes = cells * g.bands;
+    int sb, si, sj, gb, gi, gj;
+    if (!uam_grid_source(sources, g, q, sb, si, sj) || !uam_grid_source(goals, g, q, gb, gi, gj)) { len[q] = 0; return; }
+    const int s = (int)((size_t)sb * cells + (size_t)si * g.W + sj), t = (int)((size_t)gb * cells + (size_t)gi * g.W + gj);
+    const int* pq = parent + (size_t)q * nodes;
+    long long n = 1;
+    int v = t;
+    while (v != s) {
+        v = pq[v];
+        if (v < 0 || n > (long long)nodes) { len[q] = 0; return; }        // unreachable (or not a tree: cannot happen)
+        ++n;
+    }
+    if (n > max_len) { len[q] = (int)-n; return; }
+    len[q] = (int)n;
+    int* out = path + (size_t)q * max_len;
+    v = t;
+    for (long long k = n - 1; k >= 0; --k) {
+        out[k] = v;
+        if (k) v = pq[v];
+    }
+}
+
 __global__ void __launch_bounds__(256)
 uam_k_grid_cost_sum(const uint16_t* __restrict__ cost, size_t n, unsigned long long* __restrict__ sum) {
     unsigned long long acc = 0;
@@ -446,7 +489,8 @@ int uam_grid_mean_cost(uam_ctx* ctx, const uint16_t* d_cost, size_t n, cudaStrea
 }
 
 int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int bands, int H, int W,
-                         const int32_t* d_sources, int src_stride, int Q, int64_t* d_dist, int32_t* d_parent, void* stream) {
+                         const int32_t* d_sources, int src_stride, int Q, int64_t* d_dist, int32_t* d_parent, void* stream,
+                         const int32_t* d_goals = nullptr) {
     if (!ctx) return UAM_ERR_INVALID;
     if (H < 1 || W < 1 || bands < 1 || Q < 0 || !d_cost || !d_dist || (Q > 0 && !d_sources))
         return uam_fail(ctx, UAM_ERR_INVALID, "bad argument to uam_grid_search");
@@ -461,8 +505,8 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     const size_t tiles = (size_t)g.tiles_x * g.tiles_y;
     const size_t n_flags = tiles * bands * Q;
     if (n_flags >= 0xffffffffull) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "too many (query, band, tile) triples");
-    // scratch: keys (u64) | list_key (u64) | minkey (u64 x Q) | stats (u64 x 2) | list (u32) | count (u32 x 2)
-    UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, n_flags * 20 + (size_t)Q * 8 + 256));
+    // scratch: keys (u64) | list_key (u64) | minkey (u64 x Q) | stats (u64 x 2) | goal_at (i64 x Q) | list (u32) | count (u32 x 2)
+    UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, n_flags * 20 + (size_t)Q * 16 + 256));
     unsigned long long* keys = (unsigned long long*)ctx->d_scratch;
     // delta = cost of crossing about two tiles at the grid's mean cell cost (ordering only: any value gives the same result)
     unsigned long long delta = ctx->grid_delta > 0 ? (unsigned long long)ctx->grid_delta : 0ull;
@@ -473,7 +517,8 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     unsigned long long* list_key = keys + n_flags;
     unsigned long long* minkey = list_key + n_flags;
     unsigned long long* stats = minkey + Q;
-    unsigned* list = (unsigned*)(stats + 2);
+    long long* goal_at = (long long*)(stats + 2);
+    unsigned* list = (unsigned*)(goal_at + Q);
     unsigned* count = list + n_flags;
     UAM_CUDA(ctx, cudaMemsetAsync(stats, 0, 16, st));
     const int grid_fill = ctx->sm_count * 16;
@@ -483,6 +528,10 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     UAM_CHECK_LAUNCH(ctx, "uam_k_grid_init");
     uam_k_grid_seed<<<(Q + 127) / 128, 128, 0, st>>>((long long*)d_dist, d_blocked, d_sources, g, keys);
     UAM_CHECK_LAUNCH(ctx, "uam_k_grid_seed");
+    if (d_goals) {
+        uam_k_grid_goal_index<<<(Q + 127) / 128, 128, 0, st>>>(d_goals, g, goal_at);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_grid_goal_index");
+    }
     const size_t per_q = tiles * bands;
     const int parts = (int)std::max<size_t>(1, std::min<size_t>(64, per_q / 2048));
     const size_t smem = (size_t)UAM_GRID_WARP_SMEM * UAM_GRID_WARPS;
@@ -497,7 +546,8 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
         UAM_CUDA(ctx, cudaMemsetAsync(minkey, 0xff, (size_t)Q * 8, st));
         uam_k_grid_minkey<<<Q * parts, 256, 0, st>>>(keys, per_q, parts, minkey);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_minkey");
-        uam_k_grid_select<<<ctx->sm_count * 4, 256, 0, st>>>(keys, n_flags, per_q, minkey, delta, list, list_key, count);
+        uam_k_grid_select<<<ctx->sm_count * 4, 256, 0, st>>>(keys, n_flags, per_q, minkey, delta, list, list_key, count,
+                                                             (const long long*)d_dist, d_goals ? goal_at : nullptr);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_select");
         uam_k_grid_relax<<<grid_relax, UAM_GRID_WARPS * 32, smem, st>>>(d_cost, d_blocked, g, list, list_key, count, (long long*)d_dist, keys, stats);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_relax");
@@ -527,6 +577,29 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
 extern "C" int uam_grid_search(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int H, int W,
                                const int32_t* d_sources, int Q, int64_t* d_dist, int32_t* d_parent, void* stream) {
     return uam_grid_search_impl(ctx, d_cost, d_blocked, 1, H, W, d_sources, 2, Q, d_dist, d_parent, stream);
+}
+
+extern "C" int uam_grid_search_goals(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int bands, int H, int W,
+                                     const int32_t* d_sources, const int32_t* d_goals, int Q, int64_t* d_dist, int32_t* d_parent,
+                                     void* stream) {
+    if (ctx && !d_goals && Q > 0) return uam_fail(ctx, UAM_ERR_INVALID, "goals pointer is NULL");
+    return uam_grid_search_impl(ctx, d_cost, d_blocked, bands, H, W, d_sources, 3, Q, d_dist, d_parent, stream, d_goals);
+}
+
+extern "C" int uam_grid_extract_paths(uam_ctx* ctx, const int32_t* d_parent, int bands, int H, int W, const int32_t* d_sources,
+                                      const int32_t* d_goals, int Q, int max_len, int32_t* d_path, int32_t* d_len, void* stream) {
+    if (!ctx) return UAM_ERR_INVALID;
+    if (H < 1 || W < 1 || bands < 1 || Q < 0 || max_len < 0) return uam_fail(ctx, UAM_ERR_INVALID, "bad argument to uam_grid_extract_paths");
+    if (Q == 0) return UAM_OK;
+    if (!d_parent || !d_sources || !d_goals || !d_len || (max_len > 0 && !d_path)) return uam_fail(ctx, UAM_ERR_INVALID, "NULL pointer");
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UamGridGeo g;
+    g.H = H; g.W = W; g.bands = bands; g.Q = Q; g.src_stride = 3;
+    g.tiles_x = (W + GT - 1) / GT;
+    g.tiles_y = (H + GT - 1) / GT;
+    uam_k_grid_extract<<<(Q + 63) / 64, 64, 0, uam_pick_stream(ctx, stream)>>>(d_parent, g, d_sources, d_goals, max_len, d_path, d_len);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_grid_extract");
+    return UAM_OK;
 }
 
 extern "C" int uam_grid_search_bands(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int bands, int H, int W,

@@ -376,12 +376,14 @@ class Engine:
                                                   C.c_void_p(info.data_ptr()) if info is not None else None, st))
         return (rect, info) if want_info else rect
 
-    def grid_search(self, cost, sources, blocked=None, want_parent: bool = True):
+    def grid_search(self, cost, sources, blocked=None, want_parent: bool = True, goals=None):
         """Q cost-to-go sweeps on an 8-connected grid (build-defined extension, include/uam_b200.h).
         2-D: cost (H,W) uint16 CUDA tensor, sources (Q,2) int32 (row, col), blocked (H,W) uint8 or None ->
         (dist (Q,H,W) int64 with 2**62 = unreachable, parent (Q,H,W) int32 | None).
         Altitude bands: cost (bands,H,W), sources (Q,3) (band, row, col), blocked (bands,H,W) ->
-        dist / parent (Q,bands,H,W), parent = flat index into (bands,H,W)."""
+        dist / parent (Q,bands,H,W), parent = flat index into (bands,H,W).
+        goals (same layout as sources): start/goal queries -- each query stops once its goal's distance is final; dist /
+        parent are then exact for the goal and every node closer to the source than the goal."""
         import torch
         assert _is_tensor(cost) and cost.dtype == torch.uint16 and cost.dim() in (2, 3)
         k = cost.dim()
@@ -394,7 +396,14 @@ class Engine:
         parent = torch.empty((Q,) + tuple(cost.shape), dtype=torch.int32, device=cost.device) if want_parent else None
         pb = C.c_void_p(blocked.data_ptr()) if blocked is not None else None
         pp = C.c_void_p(parent.data_ptr()) if parent is not None else None
-        if k == 2:
+        if goals is not None:
+            goals = torch.as_tensor(goals, dtype=torch.int32, device=cost.device).reshape(-1, k).contiguous()
+            assert goals.shape == sources.shape
+            Bn, (H, W) = (1 if k == 2 else cost.shape[0]), cost.shape[-2:]
+            s3, g3 = self._with_band(sources), self._with_band(goals)
+            self._check(self._lib.uam_grid_search_goals(self._h, C.c_void_p(cost.data_ptr()), pb, Bn, H, W, C.c_void_p(s3.data_ptr()),
+                                                        C.c_void_p(g3.data_ptr()), Q, C.c_void_p(dist.data_ptr()), pp, st))
+        elif k == 2:
             H, W = cost.shape
             self._check(self._lib.uam_grid_search(self._h, C.c_void_p(cost.data_ptr()), pb, H, W,
                                                   C.c_void_p(sources.data_ptr()), Q, C.c_void_p(dist.data_ptr()), pp, st))
@@ -403,6 +412,34 @@ class Engine:
             self._check(self._lib.uam_grid_search_bands(self._h, C.c_void_p(cost.data_ptr()), pb, Bn, H, W,
                                                         C.c_void_p(sources.data_ptr()), Q, C.c_void_p(dist.data_ptr()), pp, st))
         return dist, parent
+
+    @staticmethod
+    def _with_band(rc):
+        """(Q,2) (row, col) -> (Q,3) (0, row, col); (Q,3) unchanged."""
+        import torch
+        if rc.shape[1] == 3:
+            return rc
+        return torch.cat([torch.zeros((rc.shape[0], 1), dtype=torch.int32, device=rc.device), rc], dim=1).contiguous()
+
+    def grid_paths(self, parent, sources, goals, max_len: Optional[int] = None):
+        """Paths of start/goal queries from the predecessor field of grid_search: (path (Q,max_len) int32 flat node ids
+        from the source to the goal, length (Q,) int32: nodes on the path, 0 = goal not reached, -k = needs k > max_len)."""
+        import torch
+        assert _is_tensor(parent) and parent.dtype == torch.int32 and parent.dim() in (3, 4)
+        k = parent.dim() - 1
+        Q = parent.shape[0]
+        Bn, (H, W) = (1 if k == 2 else parent.shape[1]), parent.shape[-2:]
+        s3 = self._with_band(torch.as_tensor(sources, dtype=torch.int32, device=parent.device).reshape(-1, k).contiguous())
+        g3 = self._with_band(torch.as_tensor(goals, dtype=torch.int32, device=parent.device).reshape(-1, k).contiguous())
+        assert s3.shape[0] == Q and g3.shape[0] == Q
+        max_len = int(max_len) if max_len is not None else 4 * (H + W) + 2 * Bn
+        st = self._tensor_args(parent, s3, g3)
+        path = torch.full((Q, max_len), -1, dtype=torch.int32, device=parent.device)
+        length = torch.empty(Q, dtype=torch.int32, device=parent.device)
+        self._check(self._lib.uam_grid_extract_paths(self._h, C.c_void_p(parent.data_ptr()), Bn, H, W, C.c_void_p(s3.data_ptr()),
+                                                     C.c_void_p(g3.data_ptr()), Q, max_len, C.c_void_p(path.data_ptr()),
+                                                     C.c_void_p(length.data_ptr()), st))
+        return path, length
 
     # ---- single-shape queries (QuadraticObstacle.contains / penalty_function, Function.__call__) -----------------
     def _scratch(self) -> 'Engine':

@@ -82,6 +82,26 @@ class Solver:
         m = self.problem.map
         return m.engine().make_arc_paths(m.x_start, m.x_goal, self.problem.N, displacements)
 
+    def seed_from_grid_path(self, nodes, raster_shape, geo) -> np.ndarray:
+        """A grid-search path (flat node ids of Engine.grid_paths, source -> goal, on an (H,W) or (bands,H,W) grid whose
+        cell centres are (x0 + (j + 1/2) dx, y0 + (i + 1/2) dy)) resampled at N points equally spaced in arc length:
+        the flat (2N,) vector Solver.create_x_init returns (solver.py:103-136), i.e. a seed for the scorer / optimiser
+        that follows the cheapest grid route instead of a circular arc.  The path's ends are replaced by map.x_start /
+        map.x_goal (they lie within a cell of them when the query was made from those points)."""
+        H, W = raster_shape[-2:]
+        x0, dx, y0, dy = [float(v) for v in geo]
+        v = np.asarray(nodes, dtype=np.int64).reshape(-1) % (H * W)
+        pts = np.stack([x0 + (v % W + 0.5) * dx, y0 + (v // W + 0.5) * dy], axis=1)
+        m = self.problem.map
+        pts = np.concatenate([[np.asarray(m.x_start, dtype=np.float64)], pts[1:-1], [np.asarray(m.x_goal, dtype=np.float64)]])
+        seg = np.sqrt(((pts[1:] - pts[:-1]) ** 2).sum(axis=1))
+        keep = np.concatenate([[True], seg > 0])             # a band change repeats a cell
+        pts, seg = pts[keep], seg[seg > 0]
+        s = np.concatenate([[0.0], np.cumsum(seg)])
+        N = self.problem.N
+        t = np.linspace(0.0, s[-1], N + 2)[1:-1]
+        return np.stack([np.interp(t, s, pts[:, 0]), np.interp(t, s, pts[:, 1])], axis=1).reshape(-1)
+
     def evaluate_candidates(self, Z) -> Dict:
         """Score a batch and pick the best like main.py:162-180: fval = sqrt(cost) (solver.py:48), strict `<`
         so ties keep the earliest candidate; also the shortest by the non-smooth length (solver.py:49)."""
