@@ -1047,3 +1047,97 @@ def test_grid_search_goal_bounded_and_paths(uam, torch, Bn, H, W):
         den = np.maximum((ab * ab).sum(1), 1e-300)
         t = np.clip(((pt - a) * ab).sum(1) / den, 0, 1)
         assert np.sqrt((((a + t[:, None] * ab) - pt) ** 2).sum(1)).min() < 1e-9
+
+
+@pytest.mark.gpu
+def test_map_rebuild_full_size_properties(uam, torch):
+    """BASELINE config 4 at its own size (16384^2 DEM + rectangular footprints): every stage of the rebuild checked on
+    the full raster through properties the oracle can afford -- the mask against the definition, occupancy and the risk
+    layers on 30 000 sampled cells against the exact oracle, the clearance transform by an exhaustive search of the disc
+    the reported distance defines, the regions of the land mask against scipy on the whole raster."""
+    import bench
+    n = 16384
+    rng = np.random.default_rng(4)
+    layers, _, _ = bench.make_raster(torch, 'cuda:0', n)
+    dem = (layers[0] * 557.5).contiguous()
+    del layers
+    dem[dem <= 0] = -9999.0
+    eng = uam.Engine()
+    for thr in (0.0, -9999, 120.5):
+        mask = eng.dem_mask(dem, thr)
+        ref = (dem == -9999) if thr == -9999 else (dem > thr)
+        assert torch.equal(mask.bool(), ref)
+    # ---- regions of the land mask: the whole raster against scipy ----------------------------------------------------
+    mask = eng.dem_mask(dem, 0.0)
+    del dem, ref
+    labels, ncomp = eng.label_components(mask, 4)
+    lab_ref, n_ref = orc.label_components(mask.cpu().numpy(), 4)
+    assert ncomp == n_ref
+    assert torch.equal(labels.cpu(), torch.from_numpy(lab_ref))
+    area, bbox = eng.component_stats(labels, ncomp)
+    assert np.array_equal(area.cpu().numpy(), np.bincount(lab_ref.ravel(), minlength=ncomp + 1)[1:])
+    assert int(area.sum().item()) == int(mask.sum().item())
+    del labels, lab_ref, mask
+    # ---- occupancy / risk layers / clearance from 1200 rectangular footprints ----------------------------------------------
+    KM = 128.0
+    spec = {'obstacles': [], 'regions': [('Land', []), ('Population', []), ('Hist', [])]}
+    for k in range(1200):
+        c, a = rng.uniform(1, KM - 1, 2), rng.uniform(0, np.pi)
+        hw, hh = rng.uniform(0.45, 0.9, 2)
+        R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        V = (np.trunc((c + np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]]) @ R.T) * 1000) / 1000).tolist()
+        sh = {'kind': 'polygon', 'verts': V}
+        spec['obstacles'].append(sh)
+        spec['regions'][k % 3][1].append(sh)
+    m = build_product_map(dict(spec, x_start=[0, 0], x_goal=[1, 1]))
+    geo = (0.0, KM / n, 0.0, KM / n)
+    rm = uam.RasterMap.from_map(m, n, n, geo, clearance=True)
+    om = orc.OMap(spec)
+    occ = rm.occupancy.cpu().numpy()
+    assert 0.05 < occ.mean() < 0.5
+    # sampled cells: uniform + cells next to an occupancy change (where a wrong inequality would show)
+    ii, jj = rng.integers(0, n, 20000), rng.integers(0, n, 20000)
+    edge = np.argwhere(occ[:, 1:] != occ[:, :-1])
+    pick = edge[rng.integers(0, len(edge), 10000)]
+    ii, jj = np.concatenate([ii, pick[:, 0]]), np.concatenate([jj, pick[:, 1] + rng.integers(0, 2, 10000)])
+    X = np.stack([orc.cell_centres(n, geo[0], geo[1])[jj], orc.cell_centres(n, geo[2], geo[3])[ii]], axis=1)
+    assert np.array_equal(occ[ii, jj].astype(bool), om.collides(X))
+    lay = rm.layers[:, torch.from_numpy(ii).cuda(), torch.from_numpy(jj).cuda()].cpu().numpy()
+    for l, (name, shapes) in enumerate(om.regions):
+        ref = orc.region_penalty(shapes, X, 1.0, True, 0.0).astype(np.float32)
+        assert np.array_equal(lay[l] == 0, ref == 0)
+        np.testing.assert_allclose(lay[l], ref, rtol=2e-7, atol=0)
+    # clearance: d2 = 0 exactly on the occupied cells; elsewhere no occupied cell lies strictly inside the disc of radius
+    # sqrt(d2) and at least one lies on its rim (exhaustive search of the disc's bounding window)
+    d2 = rm.dist2.cpu().numpy()
+    assert np.array_equal(d2 == 0, occ != 0)
+    free = np.argwhere(occ == 0)
+    for i, j in free[rng.integers(0, len(free), 1500)]:
+        r = int(np.ceil(np.sqrt(d2[i, j])))
+        i0, i1, j0, j1 = max(0, i - r), min(n, i + r + 1), max(0, j - r), min(n, j + r + 1)
+        win = occ[i0:i1, j0:j1]
+        di, dj = np.arange(i0, i1)[:, None] - i, np.arange(j0, j1)[None, :] - j
+        dd = (di * di + dj * dj)[win != 0]
+        assert dd.size and dd.min() == d2[i, j]
+    np.testing.assert_allclose(rm.clearance[:64].cpu().numpy(), np.sqrt(d2[:64].astype(np.float64)) * geo[1], rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_label_components_long_chains(uam, torch):
+    """One region that snakes through the whole raster (the union-find's worst case: every merge lengthens one chain),
+    nested rings (regions inside the holes of other regions) and a checkerboard (as many regions as cells / 2)."""
+    eng = uam.Engine()
+    H, W = 257, 1000
+    snake = np.zeros((H, W), np.uint8)
+    snake[0::2] = 1
+    snake[1::4, W - 1] = 1
+    snake[3::4, 0] = 1
+    rings = np.zeros((200, 200), np.uint8)
+    for k in range(0, 100, 2):
+        rings[k:200 - k, k:200 - k] = (k // 2) % 2 == 0
+    board = (np.indices((64, 96)).sum(0) % 2).astype(np.uint8)
+    for mask, conn, n_expect in [(snake, 4, 1), (snake, 8, 1), (rings, 4, None), (board, 4, 64 * 96 // 2), (board, 8, 1)]:
+        labels, n = eng.label_components(torch.from_numpy(mask).cuda(), conn)
+        lab_ref, n_ref = orc.label_components(mask, conn)
+        assert n == n_ref and (n_expect is None or n == n_expect)
+        assert np.array_equal(labels.cpu().numpy(), lab_ref)
