@@ -180,7 +180,9 @@ def run_reference(args):
     torch.manual_seed(0)
     layers, occ, geo = make_raster(torch, 'cpu', n)
     layers, occ = layers.numpy(), occ.numpy()
-    per_step = args.cpu_paths
+    # a step = a bounded sample of the workload: --cpu-paths paths, fewer when many steps are asked for, so that the whole
+    # run stays at about half a minute of CPU work (the rate does not depend on the sample size)
+    per_step = args.cpu_paths if args.steps <= 50 else max(2000, args.cpu_paths * 50 // args.steps)
     Z = make_paths(torch, 'cpu', per_step * (args.steps + args.warmup), 2, n).numpy()
     times = []
     for s in range(args.warmup + args.steps):
