@@ -1696,7 +1696,10 @@ extern "C" int uam_score_paths_raster_host(uam_ctx* ctx, const double* h_z, int6
     // The pipeline is bound by the kernels (a chunk scores a little slower than it uploads: binning a quarter of the batch
     // streams the raster through L2 once more), so a call lasts about upload(first chunk) + sum of the kernel times.
     // Chunk sizes may change linearly from the first to the last chunk (taper > 0: shrinking, < 0: growing).
-    const int n_chunks = (int)std::min<int64_t>(ctx->host_chunks > 0 ? ctx->host_chunks : 4, std::max<int64_t>(1, B / 1024));
+    // default: 4 chunks, fewer for small batches (a chunk under ~16 MB of waypoints costs more in launches than its upload hides)
+    const int64_t by_bytes = std::max<int64_t>(1, (int64_t)((size_t)B * row / (16u << 20)));
+    const int n_chunks = (int)std::min<int64_t>(ctx->host_chunks > 0 ? ctx->host_chunks : std::min<int64_t>(4, by_bytes),
+                                                std::max<int64_t>(1, B / 1024));
     const double taper = ctx->host_taper / 100.0;
     auto weight = [&](int c) {
         const double x = n_chunks > 1 ? (double)c / (n_chunks - 1) : 0.0;
