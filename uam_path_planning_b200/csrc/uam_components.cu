@@ -365,7 +365,7 @@ uam_k_rect_extremes(const int32_t* __restrict__ labels, int H, int W, const int*
 
 __device__ __forceinline__ long long uam_cross(long long ax, long long ay, long long bx, long long by) { return ax * by - ay * bx; }
 
-// One CTA per listed component.  hull: scratch for 2 * lines + 2 vertices (int2) at hull_off = 2 * off[k] + 2 * k.
+// One CTA per listed component.  hull_all: scratch for 4 * lines + 2 vertices (int2) per component at 4 * off[k] + 2 * k.
 // rect out: 4 corners (x, y) in world coordinates, counter-clockwise in pixel space starting at the corner that lies on the
 // chosen hull edge's line at the smallest projection; info out: hull vertices, chosen edge.
 __global__ void __launch_bounds__(128)
@@ -377,50 +377,62 @@ uam_k_rect_hull(const int32_t* __restrict__ ids, int K, const int* __restrict__ 
     const int id = ids[k];
     const int rmin = bbox[4 * (id - 1)], lines = bbox[4 * (id - 1) + 1] - rmin + 2;
     const long long o = off[k];
-    int2* hull = hull_all + 2 * o + 2 * k;
-    __shared__ int s_nh;
-    if (threadIdx.x == 0) {
-        // left chain, top to bottom: x as a function of y must be convex (hull's left side); right chain likewise concave.
-        // Counter-clockwise order in (x right, y down) screen coordinates = left chain downwards, then right chain upwards.
-        int nl = 0;
-        for (int t = 0; t < lines; ++t) {
+    // scratch of this component: [0, 2 lines) the threads' local chains (left chains in [0, lines), right chains in
+    // [lines, 2 lines), each thread inside the slice of its own grid lines), then the final hull (at most 2 lines vertices)
+    int2* loc = hull_all + 4 * o + 2 * k;
+    int2* hull = loc + 2 * lines;
+    // Phase A, parallel: thread t reduces the grid lines [t c, (t + 1) c) to their local chains.  The hull of the union is
+    // the hull of the local hulls, so phase B only sees the few points that survive locally.
+    // Left chain, top to bottom: x as a function of y must be convex (the hull's left side) -- pop while the turn
+    // a -> b -> p is not strictly convex, cross(b - a, p - a) >= 0; the right chain is the mirror image (<= 0).
+    const int c = (lines + (int)blockDim.x - 1) / (int)blockDim.x;
+    __shared__ int s_nl[128], s_nr[128];
+    {
+        const int t0 = min((int)threadIdx.x * c, lines), t1 = min(t0 + c, lines);
+        int2* L = loc + t0;
+        int2* R = loc + lines + t0;
+        int nl = 0, nr = 0;
+        for (int t = t0; t < t1; ++t) {
             const int2 p = make_int2(xl[o + t], rmin + t);
-            while (nl >= 2 && uam_cross(hull[nl - 1].x - hull[nl - 2].x, hull[nl - 1].y - hull[nl - 2].y, p.x - hull[nl - 2].x,
-                                        p.y - hull[nl - 2].y) >= 0) --nl;      // keep strictly convex turns only
-            hull[nl++] = p;
+            while (nl >= 2 && uam_cross(L[nl - 1].x - L[nl - 2].x, L[nl - 1].y - L[nl - 2].y, p.x - L[nl - 2].x, p.y - L[nl - 2].y) >= 0) --nl;
+            L[nl++] = p;
+            const int2 q = make_int2(xr[o + t], rmin + t);
+            while (nr >= 2 && uam_cross(R[nr - 1].x - R[nr - 2].x, R[nr - 1].y - R[nr - 2].y, q.x - R[nr - 2].x, q.y - R[nr - 2].y) <= 0) --nr;
+            R[nr++] = q;
         }
-        int nr0 = nl, nh = nl;
-        for (int t = lines - 1; t >= 0; --t) {
-            const int2 p = make_int2(xr[o + t], rmin + t);
-            while (nh - nr0 >= 2 && uam_cross(hull[nh - 1].x - hull[nh - 2].x, hull[nh - 1].y - hull[nh - 2].y, p.x - hull[nh - 2].x,
-                                              p.y - hull[nh - 2].y) >= 0) --nh;
-            hull[nh++] = p;
-        }
-        // the corners where the chains meet: bottom-left -> bottom-right and top-right -> top-left are hull edges when the
-        // x differ; the chains never share a vertex because xr > xl on every line
-        s_nh = nh;
+        s_nl[threadIdx.x] = nl;
+        s_nr[threadIdx.x] = nr;
     }
     __syncthreads();
-    const int nh = s_nh;
-    // the joined polygon (left chain down, right chain up) can have a reflex turn only at the 4 chain ends; remove those
-    // by one more monotone pass done by thread 0 (cheap: at most a few pops)
+    // Phase B, thread 0: the local chains in order through the same monotone stacks; the polygon is the left chain
+    // downwards followed by the right chain upwards (counter-clockwise on the screen: x right, y down).
     __shared__ int s_nh2;
     if (threadIdx.x == 0) {
-        // generic cyclic clean-up: repeat until no vertex is popped
-        int n = nh;
-        bool changed = true;
-        while (changed && n > 3) {
-            changed = false;
-            for (int v = 0; v < n && n > 3; ++v) {
-                const int2 a = hull[(v + n - 1) % n], b = hull[v], c = hull[(v + 1) % n];
-                if (uam_cross(b.x - a.x, b.y - a.y, c.x - a.x, c.y - a.y) >= 0) {        // not a strict turn of the chains' sense
-                    for (int w = v; w + 1 < n; ++w) hull[w] = hull[w + 1];
-                    --n; --v;
-                    changed = true;
-                }
+        int nl = 0;
+        for (int t = 0; t < (int)blockDim.x; ++t) {
+            const int2* L = loc + min(t * c, lines);
+            for (int i = 0; i < s_nl[t]; ++i) {
+                const int2 p = L[i];
+                while (nl >= 2 && uam_cross(hull[nl - 1].x - hull[nl - 2].x, hull[nl - 1].y - hull[nl - 2].y, p.x - hull[nl - 2].x,
+                                            p.y - hull[nl - 2].y) >= 0) --nl;
+                hull[nl++] = p;
             }
         }
-        s_nh2 = n;
+        // right chain: built top to bottom behind the left chain, then reversed in place
+        int2* rc = hull + nl;
+        int nr = 0;
+        for (int t = 0; t < (int)blockDim.x; ++t) {
+            const int2* R = loc + lines + min(t * c, lines);
+            for (int i = 0; i < s_nr[t]; ++i) {
+                const int2 q = R[i];
+                while (nr >= 2 && uam_cross(rc[nr - 1].x - rc[nr - 2].x, rc[nr - 1].y - rc[nr - 2].y, q.x - rc[nr - 2].x, q.y - rc[nr - 2].y) <= 0) --nr;
+                rc[nr++] = q;
+            }
+        }
+        for (int i = 0, j = nr - 1; i < j; ++i, --j) { const int2 tmp = rc[i]; rc[i] = rc[j]; rc[j] = tmp; }
+        // The chains never share a vertex (xr > xl on every grid line) and the turns at the four chain ends are strict
+        // (the end points are the extreme points of the top / bottom grid line), so hull[0 .. nl + nr) is the hull.
+        s_nh2 = nl + nr;
     }
     __syncthreads();
     const int n = s_nh2;
@@ -590,8 +602,8 @@ extern "C" int uam_component_rects(uam_ctx* ctx, const int32_t* d_labels, int H,
     UAM_CUDA(ctx, cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
     UAM_CUDA(ctx, cudaStreamSynchronize(st));
     if (h_bad) return uam_fail(ctx, UAM_ERR_INVALID, "component ids must be distinct labels in 1 .. n_components of non-empty components");
-    // per-line extremes (2 x total ints) + hull vertices (2 * total + 2 * K int2)
-    const size_t need = (size_t)total * 8 + ((size_t)total * 2 + (size_t)K * 2) * 8 + 256;
+    // per-line extremes (2 x total ints) + chain / hull scratch (4 * total + 2 * K int2)
+    const size_t need = (size_t)total * 8 + ((size_t)total * 4 + (size_t)K * 2) * 8 + 256;
     UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, need));
     int* xl = (int*)ctx->d_scratch;
     int* xr = xl + total;
