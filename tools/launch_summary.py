@@ -19,13 +19,13 @@ for r in rows:
 print(f'# {path}: per-launch device time (us; under ncu: cold-cache, serialised)')
 STEP = ['uam_k_bin_hist', 'uam_k_bin_scan', 'uam_k_bin_scatter', 'uam_k_score_groups', 'uam_k_reduce_paths', 'uam_k_best']
 # a step kernel is launched on the whole batch (the timed step) and on the chunks of the host pipeline (e2e leg, a
-# quarter of the batch each): the whole-batch launches are the ones within 40 % of that kernel's longest launch
+# quarter of the batch each): the whole-batch launches are the ones above 45 % of that kernel's longest launch
 whole, chunk, other = {}, {}, {}
 for name, v in byname.items():
     if any(name.startswith(k) for k in STEP):
         m = max(v)
-        whole[name] = [x for x in v if x > 0.6 * m]
-        rest = [x for x in v if x <= 0.6 * m]
+        whole[name] = [x for x in v if x > 0.45 * m]
+        rest = [x for x in v if x <= 0.45 * m]
         if rest:
             chunk[name] = rest
     else:
