@@ -682,7 +682,8 @@ __device__ __forceinline__ void uam_tap_load_tile(const unsigned char* tile, int
 struct __align__(16) UamGroupRec {
     double U, SU, V, SV;
 };
-#define UAM_GROUP_SMEM (32 * 32 + 32 * 8 + 32 * 32 * 4)    // records (32 x 32 B) + {P, Q} (32 x 8 B) + partials
+#define UAM_GROUP_SMEM (32 * 32 + 32 * 8 + 32 * 32 * 4 + 32 * 8 + 32 * 4)    // records (32 x 32 B) + {P, Q} (32 x 8 B) + partials + window table + its bit words
+#define UAM_GROUP_SEG 1024          // flat samples covered by one fill of the window table (32 windows of 32)
 
 template <int TF> struct UamTapsPerTrip { static const int N = 2; };
 template <> struct UamTapsPerTrip<1> { static const int N = 4; };
@@ -693,12 +694,11 @@ template <> struct UamTapsPerTrip<8> { static const int N = 4; };
 template <int TF, int LAYOUT, int TILE, bool CLAMP>
 __device__ __forceinline__ void uam_group_samples(const UamRasterParams& rp, const typename UamTexel<TF>::T* __restrict__ tex,
                                                   const unsigned char* s_tile, int ti0, int tj0, const UamGroupRec* s_rec,
-                                                  const int2* s_PQ, float* part, const int lane, const int P, const int S,
-                                                  const int T, float& acc, unsigned& colmask, int& kcur, int& pcur) {
+                                                  const int2* s_PQ, float* part, uint2* s_tab, unsigned* s_bits, const int lane,
+                                                  const int P, const int S, const int T, float& acc, unsigned& colmask, int& kcur,
+                                                  int& pcur) {
     constexpr int TAPS = UamTapsPerTrip<TF>::N;
     const unsigned le_mask = 0xffffffffu >> (31 - lane);
-    // lanes without a record (S == 0, only past the end of the last group) have P == T: they never start inside [0, T)
-    int started = 0;            // records whose first flat index lies before the current window (warp-uniform)
     // record parameters of this lane's current record (re-read only when the record changes)
     int kc = 0, pc = 0, qc = 0;
     double2 ca, cb;
@@ -707,48 +707,74 @@ __device__ __forceinline__ void uam_group_samples(const UamRasterParams& rp, con
         const int2 pq0 = s_PQ[0];
         ca = make_double2(r0.U, r0.SU); cb = make_double2(r0.V, r0.SV); pc = pq0.x; qc = pq0.y;
     }
-    for (int t0 = 0; t0 < T; t0 += 32 * TAPS) {
-        UamTap<TF> tap[TAPS];
-        int kk[TAPS], pp[TAPS];
+    // The record of a flat index comes from a WINDOW TABLE, filled once per UAM_GROUP_SEG flat samples: entry w =
+    // {bitmap of the record starts inside window w, number of records that start before it}; then
+    // k(lane) = count + popc(bitmap & lanes <= lane) - 1 -- one LDS.64, a LOP3, a POPC and an add per tap, where a
+    // per-window REDUX.OR over freshly built one-hot words cost about ten instructions more.
+    // Lanes without a record (S == 0, only past the end of the last group) have P == T and set no bit.
+    for (int f0 = 0; f0 < T; f0 += UAM_GROUP_SEG) {
+        __syncwarp();
+        s_bits[lane] = 0u;
+        __syncwarp();
+        const unsigned rel0 = (unsigned)(P - f0);
+        if (S > 0 && rel0 < (unsigned)UAM_GROUP_SEG) atomicOr(&s_bits[rel0 >> 5], 1u << (rel0 & 31u));
+        __syncwarp();
+        {
+            const unsigned bits = s_bits[lane];
+            const int c = __popc(bits);
+            int incl = c;
 #pragma unroll
-        for (int j = 0; j < TAPS; ++j) {
-            const int wb = t0 + 32 * j;
-            const unsigned rel = (unsigned)(P - wb);
-            const unsigned starts = __reduce_or_sync(0xffffffffu, (rel < 32u && S > 0) ? (1u << rel) : 0u);
-            const int k = started + __popc(starts & le_mask) - 1;
-            started += __popc(starts);
-            if (k != kc) {
-                ca = *reinterpret_cast<const double2*>(&s_rec[k].U);
-                cb = *reinterpret_cast<const double2*>(&s_rec[k].V);
-                const int2 pq = s_PQ[k];
-                pc = pq.x; qc = pq.y;
-                kc = k;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
-            kk[j] = k;
-            pp[j] = pc;
-            int si = wb + lane - qc;
-            if (!CLAMP && wb + lane >= T) si = 0;      // lanes past the end must stay inside the raster: any own sample
-            const double sd = uam_int2double(si);
-            const double u = __dadd_rn(ca.x, __dmul_rn(sd, ca.y)), v = __dadd_rn(cb.x, __dmul_rn(sd, cb.y));
-            if constexpr (TILE) uam_tap_load_tile<TF>(s_tile, ti0, tj0, rp, u, v, tap[j]);
-            else uam_tap_load<TF, LAYOUT, CLAMP>(tex, rp, u, v, tap[j]);
+            const int before = __popc(__ballot_sync(0xffffffffu, S > 0 && P < f0));
+            s_tab[lane] = make_uint2(bits, (unsigned)(before + incl - c));
         }
+        __syncwarp();
+        const int t_end = min(T, f0 + UAM_GROUP_SEG);
+        for (int t0 = f0; t0 < t_end; t0 += 32 * TAPS) {
+            UamTap<TF> tap[TAPS];
+            int kk[TAPS], pp[TAPS];
+            const uint2* tab = s_tab + ((t0 - f0) >> 5);
 #pragma unroll
-        for (int j = 0; j < TAPS; ++j) {
-            float pen;
-            bool occ;
-            uam_tap_eval<TF>(rp, tap[j], pen, occ);
-            const int k = kk[j];
-            if (k != kcur) {
-                const int row = (lane - pcur) & 31;          // record-local residue class of this lane's samples
-                part[row * 32 + (kcur ^ row)] = acc;
-                acc = 0.0f;
-                kcur = k;
-                pcur = pp[j];
+            for (int j = 0; j < TAPS; ++j) {
+                const int wb = t0 + 32 * j;
+                const uint2 e = tab[j];                 // (a window past the segment's table can only be past T: masked below)
+                const int k = (int)e.y + __popc(e.x & le_mask) - 1;
+                if (k != kc) {
+                    ca = *reinterpret_cast<const double2*>(&s_rec[k].U);
+                    cb = *reinterpret_cast<const double2*>(&s_rec[k].V);
+                    const int2 pq = s_PQ[k];
+                    pc = pq.x; qc = pq.y;
+                    kc = k;
+                }
+                kk[j] = k;
+                pp[j] = pc;
+                int si = wb + lane - qc;
+                if (!CLAMP && wb + lane >= T) si = 0;      // lanes past the end must stay inside the raster: any own sample
+                const double sd = uam_int2double(si);
+                const double u = __dadd_rn(ca.x, __dmul_rn(sd, ca.y)), v = __dadd_rn(cb.x, __dmul_rn(sd, cb.y));
+                if constexpr (TILE) uam_tap_load_tile<TF>(s_tile, ti0, tj0, rp, u, v, tap[j]);
+                else uam_tap_load<TF, LAYOUT, CLAMP>(tex, rp, u, v, tap[j]);
             }
-            if (t0 + 32 * j + lane < T) {
-                acc += pen;
-                colmask |= (occ ? 1u : 0u) << k;
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) {
+                float pen;
+                bool occ;
+                uam_tap_eval<TF>(rp, tap[j], pen, occ);
+                const int k = kk[j];
+                if (k != kcur) {
+                    const int row = (lane - pcur) & 31;          // record-local residue class of this lane's samples
+                    part[row * 32 + (kcur ^ row)] = acc;
+                    acc = 0.0f;
+                    kcur = k;
+                    pcur = pp[j];
+                }
+                if (t0 + 32 * j + lane < T) {
+                    acc += pen;
+                    colmask |= (occ ? 1u : 0u) << k;
+                }
             }
         }
     }
@@ -772,6 +798,8 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
     UamGroupRec* s_rec = reinterpret_cast<UamGroupRec*>(warp_smem);
     int2* s_PQ = reinterpret_cast<int2*>(warp_smem + 32 * 32);       // {P_k, Q_k = P_k - s0_k}: flat index -> sample number
     float* part = reinterpret_cast<float*>(warp_smem + 32 * 32 + 32 * 8);
+    uint2* s_tab = reinterpret_cast<uint2*>(warp_smem + 32 * 32 + 32 * 8 + 32 * 32 * 4);
+    unsigned* s_bits = reinterpret_cast<unsigned*>(warp_smem + 32 * 32 + 32 * 8 + 32 * 32 * 4 + 32 * 8);
     int incl = S;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -800,8 +828,8 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
     float acc = 0.0f;
     unsigned colmask = 0;
     int kcur = 0, pcur = 0;     // the record `acc` belongs to and its first flat index
-    if (all_inside) uam_group_samples<TF, LAYOUT, TILE, false>(rp, tex, s_tile, ti0, tj0, s_rec, s_PQ, part, lane, P, S, T, acc, colmask, kcur, pcur);
-    else uam_group_samples<TF, LAYOUT, TILE, true>(rp, tex, s_tile, ti0, tj0, s_rec, s_PQ, part, lane, P, S, T, acc, colmask, kcur, pcur);
+    if (all_inside) uam_group_samples<TF, LAYOUT, TILE, false>(rp, tex, s_tile, ti0, tj0, s_rec, s_PQ, part, s_tab, s_bits, lane, P, S, T, acc, colmask, kcur, pcur);
+    else uam_group_samples<TF, LAYOUT, TILE, true>(rp, tex, s_tile, ti0, tj0, s_rec, s_PQ, part, s_tab, s_bits, lane, P, S, T, acc, colmask, kcur, pcur);
     {
         const int row = (lane - pcur) & 31;
         part[row * 32 + (kcur ^ row)] = acc;
