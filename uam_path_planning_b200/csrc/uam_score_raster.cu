@@ -102,10 +102,13 @@ __device__ __forceinline__ void uam_cell_frac1(double u, int n, int& j0, float& 
     j0 = min(max(__double2int_rd(u), 0), n - 2);
     f = uam_sat_f32(__dsub_rn(u, uam_int2double(j0)));
 }
-// the same for 0 <= u < n - 1 (caller's promise): neither clamp nor saturation can act, same bits
+// the same for 0 <= u < n - 1 (caller's promise): neither clamp nor saturation can act, same bits.  floor(u) comes from
+// one round-down add: u + 2^52 rounded towards -inf is 2^52 + floor(u) (the spacing of doubles in [2^52, 2^53) is 1), whose
+// low word IS the integer -- no conversion instruction, no bit assembly of (double)j0.
 __device__ __forceinline__ void uam_cell_frac1_inside(double u, int& j0, float& f) {
-    j0 = __double2int_rd(u);
-    f = (float)__dsub_rn(u, uam_int2double(j0));
+    const double fu = __dadd_rd(u, 4503599627370496.0);
+    j0 = __double2loint(fu);
+    f = (float)__dsub_rn(u, __dsub_rn(fu, 4503599627370496.0));
 }
 
 // Occupancy bit-plane of the quad mode: one bit per cell, a 32-bit word = 8 x 4 cells, a 128-byte line = 4 x 8 words
@@ -671,6 +674,13 @@ __device__ __forceinline__ void uam_tap_load_tile(const unsigned char* tile, int
     }
 }
 
+// x << n with PTX semantics (a shift by 32 or more gives 0; in C++ it would be undefined)
+__device__ __forceinline__ unsigned uam_shl_clamp(unsigned x, unsigned n) {
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
+
 // One warp per group of 32 consecutive sorted records.  The samples of the 32 records are concatenated (record k owns
 // the flat indices [P_k, P_{k+1})) and lanes stride the flat index, UAM_TAPS windows of 32 samples per trip, so no
 // lane idles on short records.  The record of a flat index is found without branches or dependent shared-memory
@@ -682,7 +692,14 @@ __device__ __forceinline__ void uam_tap_load_tile(const unsigned char* tile, int
 struct __align__(16) UamGroupRec {
     double U, SU, V, SV;
 };
-#define UAM_GROUP_SMEM (32 * 32 + 32 * 8 + 32 * 32 * 4 + 32 * 8 + 32 * 4)    // records (32 x 32 B) + {P, Q} (32 x 8 B) + partials + window table + its bit words
+// per-warp shared memory of a group: 33 records (32 + the dummy that owns the flat indices past the end) of 32 B, their
+// {P, Q} (8 B), the 32 x 33 partials (row stride 33: conflict-free both ways), the window table and its bit words
+#define UAM_GROUP_REC_OFF 0
+#define UAM_GROUP_PQ_OFF (33 * 32)
+#define UAM_GROUP_PART_OFF (33 * 32 + 33 * 8 + 8)             // 1328: 16-byte aligned
+#define UAM_GROUP_TAB_OFF (UAM_GROUP_PART_OFF + 32 * 33 * 4)
+#define UAM_GROUP_BITS_OFF (UAM_GROUP_TAB_OFF + 32 * 8)
+#define UAM_GROUP_SMEM (UAM_GROUP_BITS_OFF + 32 * 4)          // 5936
 #define UAM_GROUP_SEG 1024          // flat samples covered by one fill of the window table (32 windows of 32)
 
 template <int TF> struct UamTapsPerTrip { static const int N = 2; };
@@ -711,13 +728,18 @@ __device__ __forceinline__ void uam_group_samples(const UamRasterParams& rp, con
     // {bitmap of the record starts inside window w, number of records that start before it}; then
     // k(lane) = count + popc(bitmap & lanes <= lane) - 1 -- one LDS.64, a LOP3, a POPC and an add per tap, where a
     // per-window REDUX.OR over freshly built one-hot words cost about ten instructions more.
-    // Lanes without a record (S == 0, only past the end of the last group) have P == T and set no bit.
+    // Lanes without a record (S == 0, only past the end of the last group) have P == T and set no bit.  The flat indices
+    // past T (the tail of the last trip) belong to a DUMMY record that starts at T (slot = number of records, all-zero
+    // parameters: it samples pixel (0, 0)), so the loop needs no "past the end" test anywhere: the dummy's sum and
+    // collision bit land in a slot nobody reads (column 32 of the partials / a shift by 32, or the slot of a lane
+    // that has no record).
     for (int f0 = 0; f0 < T; f0 += UAM_GROUP_SEG) {
         __syncwarp();
         s_bits[lane] = 0u;
         __syncwarp();
         const unsigned rel0 = (unsigned)(P - f0);
         if (S > 0 && rel0 < (unsigned)UAM_GROUP_SEG) atomicOr(&s_bits[rel0 >> 5], 1u << (rel0 & 31u));
+        if (lane == 0 && (unsigned)(T - f0) < (unsigned)UAM_GROUP_SEG) atomicOr(&s_bits[(unsigned)(T - f0) >> 5], 1u << ((unsigned)(T - f0) & 31u));
         __syncwarp();
         {
             const unsigned bits = s_bits[lane];
@@ -751,9 +773,7 @@ __device__ __forceinline__ void uam_group_samples(const UamRasterParams& rp, con
                 }
                 kk[j] = k;
                 pp[j] = pc;
-                int si = wb + lane - qc;
-                if (!CLAMP && wb + lane >= T) si = 0;      // lanes past the end must stay inside the raster: any own sample
-                const double sd = uam_int2double(si);
+                const double sd = uam_int2double(wb + lane - qc);
                 const double u = __dadd_rn(ca.x, __dmul_rn(sd, ca.y)), v = __dadd_rn(cb.x, __dmul_rn(sd, cb.y));
                 if constexpr (TILE) uam_tap_load_tile<TF>(s_tile, ti0, tj0, rp, u, v, tap[j]);
                 else uam_tap_load<TF, LAYOUT, CLAMP>(tex, rp, u, v, tap[j]);
@@ -766,15 +786,13 @@ __device__ __forceinline__ void uam_group_samples(const UamRasterParams& rp, con
                 const int k = kk[j];
                 if (k != kcur) {
                     const int row = (lane - pcur) & 31;          // record-local residue class of this lane's samples
-                    part[row * 32 + (kcur ^ row)] = acc;
+                    part[row * 33 + kcur] = acc;
                     acc = 0.0f;
                     kcur = k;
                     pcur = pp[j];
                 }
-                if (t0 + 32 * j + lane < T) {
-                    acc += pen;
-                    colmask |= (occ ? 1u : 0u) << k;
-                }
+                acc += pen;
+                colmask |= uam_shl_clamp(occ ? 1u : 0u, (unsigned)k);    // (k = 32, the dummy of a full group: shifted out)
             }
         }
     }
@@ -795,11 +813,11 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
                                                 const unsigned char* s_tile, int ti0, int tj0, unsigned char* warp_smem,
                                                 const int lane, const double U, const double V, const double SU,
                                                 const double SV, const int S, const int s0, float& mine, bool& collide) {
-    UamGroupRec* s_rec = reinterpret_cast<UamGroupRec*>(warp_smem);
-    int2* s_PQ = reinterpret_cast<int2*>(warp_smem + 32 * 32);       // {P_k, Q_k = P_k - s0_k}: flat index -> sample number
-    float* part = reinterpret_cast<float*>(warp_smem + 32 * 32 + 32 * 8);
-    uint2* s_tab = reinterpret_cast<uint2*>(warp_smem + 32 * 32 + 32 * 8 + 32 * 32 * 4);
-    unsigned* s_bits = reinterpret_cast<unsigned*>(warp_smem + 32 * 32 + 32 * 8 + 32 * 32 * 4 + 32 * 8);
+    UamGroupRec* s_rec = reinterpret_cast<UamGroupRec*>(warp_smem + UAM_GROUP_REC_OFF);
+    int2* s_PQ = reinterpret_cast<int2*>(warp_smem + UAM_GROUP_PQ_OFF);       // {P_k, Q_k = P_k - s0_k}: flat index -> sample number
+    float* part = reinterpret_cast<float*>(warp_smem + UAM_GROUP_PART_OFF);
+    uint2* s_tab = reinterpret_cast<uint2*>(warp_smem + UAM_GROUP_TAB_OFF);
+    unsigned* s_bits = reinterpret_cast<unsigned*>(warp_smem + UAM_GROUP_BITS_OFF);
     int incl = S;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -812,8 +830,19 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
     mr.U = U; mr.SU = SU; mr.V = V; mr.SV = SV;
     s_rec[lane] = mr;
     s_PQ[lane] = make_int2(P, P - s0);
+    {
+        // the dummy record behind the last real one (the real records are the lanes 0 .. n_rec - 1)
+        const int n_rec = __popc(__ballot_sync(0xffffffffu, S > 0));
+        if (lane == 0) {
+            UamGroupRec z0;
+            z0.U = 0.0; z0.SU = 0.0; z0.V = 0.0; z0.SV = 0.0;
+            s_rec[n_rec] = z0;
+            s_PQ[n_rec] = make_int2(T, T);
+        }
+    }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(part)[q * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int q = 0; q < 9; ++q)
+        if (q * 32 + lane < 32 * 33 / 4) reinterpret_cast<float4*>(part)[q * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __syncwarp();
     // Fast path: when every record of the group lies strictly inside the raster (first and last sample in
     // [0, W-1) x [0, H-1); the samples in between are monotone), the clamps and the saturation of the cell / fraction
@@ -832,14 +861,14 @@ __device__ __forceinline__ void uam_group_score(const UamRasterParams& rp, const
     else uam_group_samples<TF, LAYOUT, TILE, true>(rp, tex, s_tile, ti0, tj0, s_rec, s_PQ, part, s_tab, s_bits, lane, P, S, T, acc, colmask, kcur, pcur);
     {
         const int row = (lane - pcur) & 31;
-        part[row * 32 + (kcur ^ row)] = acc;
+        part[row * 33 + kcur] = acc;             // (kcur = 32, the dummy of a full group, is the padding column)
     }
     __syncwarp();
     // per-record sums: v[s] = this lane's residue class of record s; 32 x 32 transpose-reduce, pairing tree
     // (l, l^16), (.., ^8), (.., ^4), (.., ^2), (.., ^1) like uam_warp_sum; lane s ends with the sum of record s
     float v[32];
 #pragma unroll
-    for (int s = 0; s < 32; ++s) v[s] = part[lane * 32 + (s ^ lane)];
+    for (int s = 0; s < 32; ++s) v[s] = part[lane * 33 + s];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const bool hi = (lane & o) != 0;
