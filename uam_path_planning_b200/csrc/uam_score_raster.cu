@@ -558,9 +558,16 @@ __device__ __forceinline__ UamSegRec uam_make_segment(const double2* __restrict_
     return r;
 }
 
-__device__ __forceinline__ int uam_segment_bin(const UamSegRec& r, const UamRasterParams& rp, const UamBinGeo bg) {
-    // bin of the segment midpoint, clamped into the raster (NaN -> 0)
-    double u = r.U + 0.5 * (double)r.S * r.SU, v = r.V + 0.5 * (double)r.S * r.SV;
+// Raster bin of a segment's midpoint (of the goal waypoint for the pseudo-segment k = Wp - 1), clamped into the raster
+// (NaN -> 0).  The bin only decides the ORDER the segments are scored in (locality), never a result, so it is computed
+// with two multiplications per coordinate -- no sample count, no divisions.
+__device__ __forceinline__ int uam_segment_bin(const double2* __restrict__ z, unsigned long long id, int Wp,
+                                               const UamRasterParams& rp, const UamBinGeo bg, double inv_dx, double inv_dy) {
+    const unsigned long long b = id / (unsigned)Wp;
+    const int k = (int)(id - b * (unsigned)Wp);
+    const double2 p = z[id];
+    const double2 q = k < Wp - 1 ? z[id + 1] : p;
+    double u = (0.5 * (p.x + q.x) - rp.x0) * inv_dx - 0.5, v = (0.5 * (p.y + q.y) - rp.y0) * inv_dy - 0.5;
     u = fmin(fmax(u, 0.0), (double)(rp.W - 1));
     v = fmin(fmax(v, 0.0), (double)(rp.H - 1));
     return (int)(uam_part1by1((unsigned)((int)u >> bg.shift)) | (uam_part1by1((unsigned)((int)v >> bg.shift)) << 1));
@@ -576,8 +583,9 @@ uam_k_bin_hist(const double2* __restrict__ z, unsigned long long n_seg, int Wp, 
     __syncthreads();
     const unsigned long long lo = (unsigned long long)blockIdx.x * UAM_BIN_CHUNK;
     const unsigned long long hi = lo + UAM_BIN_CHUNK < n_seg ? lo + UAM_BIN_CHUNK : n_seg;
+    const double inv_dx = 1.0 / rp.dx, inv_dy = 1.0 / rp.dy;
     for (unsigned long long id = lo + threadIdx.x; id < hi; id += blockDim.x) {
-        const int bin = uam_segment_bin(uam_make_segment(z, id, Wp, rp), rp, bg);
+        const int bin = uam_segment_bin(z, id, Wp, rp, bg, inv_dx, inv_dy);
         seg_bin[id] = (unsigned short)bin;
         atomicAdd(&s_hist[bin], 1);
     }
