@@ -51,6 +51,26 @@ def main():
             ref = cost_h.copy()
         assert np.array_equal(ref, cost_h), 'chunking changed the costs'
         print(f'chunks {ch} taper {tp:3d} %: median {np.median(ts):.3f} ms  min {np.min(ts):.3f} ms', flush=True)
+    # the same call with an ordinary (pageable) numpy array, as a numpy user would make it
+    rm.engine.set_option('host_chunks', 0)
+    rm.engine.set_option('host_taper', 0)
+    Zp = np.array(Zh, copy=True)
+    cp, kp = np.empty(B, np.float32), np.empty(B, np.uint8)
+    for _ in range(3):
+        rm.score_paths(Zp, bench.WEIGHTS, bench.SPC, True, None, out=(cp, kp))
+    ts = []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        rm.score_paths(Zp, bench.WEIGHTS, bench.SPC, True, None, out=(cp, kp))
+        ts.append((time.perf_counter() - t0) * 1e3)
+    assert ref is None or np.array_equal(ref, cp)
+    print(f'pageable numpy input, default chunks: median {np.median(ts):.3f} ms  min {np.min(ts):.3f} ms', flush=True)
+    Zd2 = torch.empty_like(Z)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        Zd2.copy_(torch.from_numpy(Zp))
+    torch.cuda.synchronize()
+    print(f'(torch copy of the same pageable array to the device: {(time.perf_counter() - t0) * 200:.3f} ms)', flush=True)
 
 
 if __name__ == '__main__':
