@@ -257,3 +257,33 @@ def test_result_export_conventions():
     assert uam.result_wkt([], [1, 2], [3, 4], kind='points') == 'MULTIPOINT ((1.0 2.0), (3.0 4.0))'
     with pytest.raises(ValueError):
         uam.result_points([1.0, 2.0, 3.0])
+
+
+def test_seed_from_grid_path_and_rect_area():
+    """Host-side helpers around the grid search and the polygon front-end (no GPU involved): a grid route resampled into
+    the flat (2N,) vector Solver.create_x_init returns (solver.py:103-136), the shoelace area used for the
+    `p.area > min_approx_polygon_area` filter (map_generation/data_processor.py:34)."""
+    m = uam.RegionMap()
+    geo = (100.0, 2.0, -50.0, 2.0)                  # cell centres at x0 + (j + 1/2) dx, y0 + (i + 1/2) dy
+    H, W = 40, 60
+    # an L-shaped route on a 2-band grid: along row 5 from column 3 to 30, a band change, then down column 30 to row 25
+    nodes = [5 * W + j for j in range(3, 31)] + [H * W + 5 * W + 30] + [H * W + i * W + 30 for i in range(6, 26)]
+    m.x_start = [geo[0] + 3.5 * geo[1], geo[2] + 5.5 * geo[3]]
+    m.x_goal = [geo[0] + 30.5 * geo[1], geo[2] + 25.5 * geo[3]]
+    N = 46
+    sol = uam.Solver(uam.Problem(m, N, {}), {})
+    x = sol.seed_from_grid_path(nodes, (2, H, W), geo).reshape(N, 2)
+    full = np.concatenate([[m.x_start], x, [m.x_goal]])
+    steps = np.sqrt(((full[1:] - full[:-1]) ** 2).sum(1))
+    route = 27 * 2.0 + 20 * 2.0                     # 27 cells east, 20 cells south
+    assert np.all(steps <= route / (N + 1) + 1e-9)
+    on_first_leg = np.isclose(x[:, 1], m.x_start[1])
+    on_second_leg = np.isclose(x[:, 0], m.x_goal[0])
+    assert np.all(on_first_leg | on_second_leg) and on_first_leg.sum() >= 20 and on_second_leg.sum() >= 15
+    assert np.all(np.diff(x[on_first_leg, 0]) > 0) and np.all(np.diff(x[on_second_leg & ~on_first_leg, 1]) > 0)
+    assert sol.seed_from_grid_path(nodes, (2, H, W), geo).shape == sol.create_x_init(0.0).shape
+    # source == goal: every point is the start
+    m.x_goal = m.x_start
+    assert np.allclose(sol.seed_from_grid_path([5 * W + 3], (H, W), geo).reshape(N, 2), m.x_start)
+    r = np.array([[[0, 0], [4, 0], [4, 3], [0, 3]], [[0, 0], [2, 2], [0, 4], [-2, 2]]], dtype=np.float64)
+    assert np.allclose(uam.mapgen.rect_area(r), [12.0, 8.0])
