@@ -775,8 +775,12 @@ __device__ __forceinline__ void uam_group_samples(const UamRasterParams& rp, con
                 if (k != kc) {
                     ca = *reinterpret_cast<const double2*>(&s_rec[k].U);
                     cb = *reinterpret_cast<const double2*>(&s_rec[k].V);
-                    const int2 pq = s_PQ[k];
-                    pc = pq.x; qc = pq.y;
+                    if constexpr (TILE) {
+                        const int2 pq = s_PQ[k];
+                        pc = pq.x; qc = pq.y;
+                    } else {
+                        pc = qc = reinterpret_cast<const int*>(s_PQ)[2 * k];    // whole segments: Q == P (one 4-byte load)
+                    }
                     kc = k;
                 }
                 kk[j] = k;
