@@ -72,7 +72,7 @@ def test_constructor_errors(golden_meta):
     with pytest.raises(Exception):              # integer first vertex + float vertices: numpy casting error (Q6)
         uam.polygon([0, 0], [1.5, 0.], [1., 1.])
     sq = uam.square([1, 1], 0.5)
-    assert sq.area == 1.0 and len(sq.inequalities) == 4
+    assert sq.area == 1.0 and len(sq.inequalities) == 4 and len(sq) == 4 and len(uam.ball(1.0)) == 1
     bl = uam.ball([1, 1], 2, 1)
     assert bl.area == pytest.approx(golden_meta['constructors']['ball_area'])
     assert uam.ball(3.0).records()[0].tolist() == [1, 0, 0, 3, 3, 0, 0, 0]
@@ -93,6 +93,8 @@ def test_create_x_init(fixture_spec, golden, golden_meta, N):
     np.testing.assert_array_equal(Z[:, -2:], np.tile(fixture_spec['x_goal'], (3, 1)))
     with pytest.raises(NotImplementedError):
         sol.solve(None, None)
+    assert sol.get_error_code_explanation(3003) == 'Vector `parameter` has wrong length'
+    assert sol.get_error_code_explanation(7) == 'Error code not found'
 
 
 def test_region_map_container():

@@ -54,6 +54,10 @@ class QuadraticObstacle:
             assert ineq.n == 2, f'Function must be 2-dimensional, got {ineq.n}-dimensional'
             self.inequalities.append(ineq)
 
+    def __len__(self):
+        """Number of inequalities (quadratic_obstacle.py:211-213)."""
+        return len(self.inequalities)
+
     # ---- table form -------------------------------------------------------------------------------
     def records(self) -> np.ndarray:
         if not self.inequalities:

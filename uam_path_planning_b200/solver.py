@@ -31,6 +31,12 @@ class Solver:
 
     build_solver = solve
 
+    def get_error_code_explanation(self, error_code):
+        """Texts of the OpEn TCP server's error codes (solver.py:169-177), kept for callers that report them."""
+        return {1000: 'Invalid request: Malformed or invalid JSON', 1600: 'Initial guess has incompatible dimensions',
+                1700: 'Wrong dimension of Langrange multipliers', 2000: 'Problem solution failed (solver error)',
+                3003: 'Vector `parameter` has wrong length'}.get(error_code, 'Error code not found')
+
     def create_x_init(self, displacement=0):
         """Straight line (displacement 0) or the circular arc through start and goal whose sagitta is
         displacement * |goal - start| / 2; N interior points equally spaced in angle (solver.py:103-136)."""
