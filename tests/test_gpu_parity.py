@@ -1141,3 +1141,46 @@ def test_label_components_long_chains(uam, torch):
         lab_ref, n_ref = orc.label_components(mask, conn)
         assert n == n_ref and (n_expect is None or n == n_expect)
         assert np.array_equal(labels.cpu().numpy(), lab_ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('variant', [-1, 3])
+def test_raster_scorer_long_and_exact_length_segments(uam, torch, variant):
+    """The grouped sample loop on records that are far longer than its 1024-sample window table and on groups whose
+    sample total is an exact multiple of the trip (128) and of the table segment (1024): 3-waypoint paths across a 2048^2
+    raster (about 1400 samples per segment) mixed with axis-aligned paths of exactly 32 / 128 / 512 cells per segment and
+    with zero-length segments -- every path against the C oracle."""
+    import bench
+    from oracle import uam_oracle_c as occ
+    n = 2048
+    layers, occu, geo = bench.make_raster(torch, 'cuda', n, seed=99)
+    cell = geo[1]
+    rng = np.random.default_rng(8)
+    B = 90000                                          # x 3 waypoints >= 2^18 segments: the large-batch pipelines
+    Z = np.empty((B, 3, 2))
+    Z[:, 0] = rng.uniform(0, n * cell, (B, 2))
+    Z[:, 2] = rng.uniform(0, n * cell, (B, 2))
+    Z[:, 1] = 0.5 * (Z[:, 0] + Z[:, 2]) + rng.normal(0, 3 * cell, (B, 2))
+    # exact lengths along a row: 32, 128 and 512 cells per segment, starting at a cell centre (32 records of 32 samples
+    # fill one 1024-sample table segment exactly)
+    for k, cells in enumerate((32, 128, 512)):
+        sel = slice(1000 * k, 1000 * (k + 1))
+        i0 = rng.integers(10, n - 10, 1000)
+        j0 = rng.integers(1, n - 2 * cells - 2, 1000)
+        for w in range(3):
+            Z[sel, w, 0] = (j0 + w * cells + 0.5) * cell
+            Z[sel, w, 1] = (i0 + 0.5) * cell
+    Z[3000:3500, 1] = Z[3000:3500, 0]                  # zero-length first segment
+    Z[3500:4000, 2] = Z[3500:4000, 1] = Z[3500:4000, 0]    # a path that is one point
+    Zh = np.ascontiguousarray(Z.reshape(B, 6))
+    rm = uam.RasterMap.from_arrays(layers, geo, occu, options={'integral_variant': variant})
+    Zd = torch.from_numpy(Zh).cuda()
+    Lh, Oh = layers.cpu().numpy(), occu.cpu().numpy()
+    for spc in (1.0, 0.73):
+        c, k, ns = rm.score_paths(Zd, bench.WEIGHTS, spc, True, None, want_nsamples=True)
+        c_ref, k_ref, ns_ref = occ.score_paths_raster(Lh, Oh, geo, Zh, bench.WEIGHTS, spc, True, None)
+        assert np.array_equal(ns.cpu().numpy(), ns_ref)
+        np.testing.assert_allclose(c.cpu().numpy(), c_ref, rtol=RTOL_RASTER)
+        assert np.array_equal(k.cpu().numpy().astype(bool), k_ref)
+        if spc == 1.0:
+            assert ns_ref.max() > 2000 and (ns_ref[:1000] == 65).all()      # 2 x 32 samples + the goal
