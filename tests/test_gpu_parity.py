@@ -1184,3 +1184,37 @@ def test_raster_scorer_long_and_exact_length_segments(uam, torch, variant):
         assert np.array_equal(k.cpu().numpy().astype(bool), k_ref)
         if spc == 1.0:
             assert ns_ref.max() > 2000 and (ns_ref[:1000] == 65).all()      # 2 x 32 samples + the goal
+
+
+@pytest.mark.gpu
+def test_pipeline_map_to_seeded_candidates(uam, torch, fixture_spec, tmp_path):
+    """The steps of INTEGRATION.md 3b chained on the main.py scenario: rasterise the map, run a start/goal grid search on
+    the quantised risk raster, turn the route into a create_x_init-shaped seed, score it next to the reference's five
+    arcs with the analytic scorer (checked against the oracle), export the winner."""
+    f = fixture_spec
+    N = 62
+    prob = build_product_problem(f, N)
+    sol = uam.Solver(prob, {})
+    H = W = 512
+    geo = (8.0, 64.0 / W, -42.0, 64.0 / H)
+    rm = uam.RasterMap.from_map(prob.map, H, W, geo)
+    risk = (rm.layers * torch.tensor(f['weights'], device='cuda', dtype=torch.float32)[:, None, None]).sum(0)
+    cost_u16 = (1 + torch.clamp(risk / risk.max() * 2000.0, 0, 2000)).to(torch.uint16)
+    cell = lambda p: [int((p[1] - geo[2]) / geo[3]), int((p[0] - geo[0]) / geo[1])]         # (row, col)
+    src, goal = cell(f['x_start']), cell(f['x_goal'])
+    eng = rm.engine
+    dist_, parent = eng.grid_search(cost_u16, [src], rm.occupancy, goals=[goal])
+    nodes, length = eng.grid_paths(parent, [src], [goal])
+    assert int(length[0]) > 50 and int(dist_[0, goal[0], goal[1]]) < 2 ** 62
+    x_seed = sol.seed_from_grid_path(nodes[0, :int(length[0])].cpu().numpy(), cost_u16.shape, geo)
+    X = np.stack([x_seed] + [sol.create_x_init(d) for d in (-0.5, -0.25, 0.0, 0.25, 0.5)])
+    Z = sol.full_path(X)
+    cost, collide, _ = prob.score(Z)
+    om = orc.OMap(f)
+    np.testing.assert_allclose(cost, orc.get_cost(om, Z, N, f['weights'], f['enlargement'], f['options']), rtol=RTOL_ANALYTIC)
+    assert np.array_equal(collide.astype(bool), orc.path_collides(om, Z, N))
+    assert not collide[0]                     # the grid route avoids the occupied cells, its resampling stays clear here
+    res = sol.evaluate_candidates(Z)
+    best = res['min_fval_index']
+    wkt = uam.result_wkt(X[best])
+    assert wkt.startswith('LINESTRING (') and wkt.count(',') == N + 1
