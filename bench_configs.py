@@ -262,6 +262,7 @@ def main():
     mm = uam.RegionMap()
     for r in ('Land', 'Population', 'Hist'):
         mm.new_region(r, 'r')
+    spec4 = {'obstacles': [], 'regions': [('Land', []), ('Population', []), ('Hist', [])]}
     for k in range(4096):
         c, a = rng.uniform(1, KMn - 1, 2), rng.uniform(0, np.pi)
         hw, hh = rng.uniform(0.45, 0.9, 2)                 # area > 0.78 km^2 like data_processor.py:9,32
@@ -270,6 +271,8 @@ def main():
         sh = uam.polygon(*V.tolist())
         mm.add_obstacle(sh)
         mm.add_shape_to_region(('Land', 'Population', 'Hist')[k % 3], sh)
+        spec4['obstacles'].append({'kind': 'polygon', 'verts': V.tolist()})
+        spec4['regions'][k % 3][1].append({'kind': 'polygon', 'verts': V.tolist()})
     eng.set_shapes(mm.obstacles, mm._region_lists())
     geo = (0.0, KMn / n, 0.0, KMn / n)
     occ = eng.rasterize_occupancy(n, n, geo)
@@ -288,6 +291,19 @@ def main():
     t0 = time.perf_counter()
     ndimage.distance_transform_edt(crop == 0)
     res['cpu_edt_scipy_Mcell_s'] = crop.size / (time.perf_counter() - t0) / 1e6
+    if not args.no_cpu:
+        # CPU baseline of the rasterisation: the numpy oracle (vectorised half-plane tests over all shapes, one core) on a
+        # 96 x 96-cell crop, which also checks the GPU cells of that crop
+        from oracle import uam_oracle as orc
+        om4 = orc.OMap(spec4)
+        cr = 96
+        t0 = time.perf_counter()
+        occ_ref = orc.rasterize_occupancy(om4, cr, cr, *geo)
+        res['cpu_occupancy_numpy_Mcell_s'] = cr * cr / (time.perf_counter() - t0) / 1e6
+        res['crop_occupancy_equal_oracle'] = bool(np.array_equal(occ[:cr, :cr].cpu().numpy(), occ_ref))
+        t0 = time.perf_counter()
+        orc.rasterize_layers(om4, cr, cr, *geo, 0.0)
+        res['cpu_layers_numpy_Mcell_s'] = cr * cr / (time.perf_counter() - t0) / 1e6
     print(json.dumps(res))
     del occ, mm
     del eng
