@@ -394,12 +394,12 @@ def run_ours(args):
         peak = float(peaks.get('hbm_gbs', 6650.0))
         abytes = algorithmic_bytes(total_samples, B)
         achieved = abytes / (k_ms * 1e-3) / 1e9
-        traffic, traffic_src = None, None
+        traffic, traffic_src, limiter = None, None, None
         try:
             tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
             for ent in tj['entries']:
                 if ent['kernel'] == kname and ent['paths'] == B and ent['raster'] == n:
-                    traffic, traffic_src = ent['dram_bytes_per_launch'], ent['source']
+                    traffic, traffic_src, limiter = ent['dram_bytes_per_launch'], ent['source'], ent.get('limiter')
         except Exception:
             pass
         wp_bytes = (WP - 1) * B * 16 + B * WP * 49 + B * 21
@@ -411,7 +411,9 @@ def run_ours(args):
             'samples_per_step_per_gpu': total_samples,
             'samples_per_s': total_samples * world * args.steps / (ms_total * 1e-3),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'traffic_source': traffic_src, 'kernel': kname, 'kernel_ms': k_ms,
+                         'traffic': traffic, 'traffic_source': traffic_src,
+                         'traffic_frac': (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,     # physical DRAM bytes / time / peak
+                         'limiter': limiter, 'kernel': kname, 'kernel_ms': k_ms,
                          'scoring_call_ms': call_ms, 'algorithmic_bytes_per_launch': abytes,
                          'note': 'achieved = SURVEY 8(d) algorithmic bytes (L x 16 + 1 B per sample) / event-timed kernel duration. '
                                  'The kernel needs fewer physical bytes than that: the L layers are folded into one weighted '
