@@ -214,11 +214,14 @@ int uam_eval_inequalities_host(uam_ctx* ctx, const double* h_records, int n_rec,
 
 /* ---- best candidate --------------------------------------------------------------------------------
  * Replaces the running min of path_generation/main.py:162-180.  *d_key = min over b of
- * (float32 bits of cost[b] << 32) | (global_offset + b); costs are >= 0 so the bit pattern orders
- * like the value, ties resolve to the smaller index (the `<` of main.py:175).  The caller min-reduces
- * the 8-byte key across ranks (NCCL).  d_key must be pre-set (e.g. to UINT64_MAX) by the caller or
- * by passing reset != 0.  d_cost is float32 (raster scorer) or float64 (analytic scorer, rounded to
- * float32 for the key) according to cost_is_f64. */
+ *     key(cost[b], global_offset + b) = (img(float32 cost) << 31) | index        (63 bits, index < 2^31)
+ * img = order-preserving image of the float32 bit pattern (all bits flipped for a negative value, top bit set otherwise;
+ * NaN -> 0xffffffff), so the unsigned order of the keys is the float order of the costs for EVERY value (negative costs
+ * are reachable through negative layer weights), a NaN never wins, ties resolve to the smaller index (the strict `<` of
+ * main.py:175) and the key is a non-negative int64: the caller min-reduces it across ranks with a signed or unsigned min
+ * alike (NCCL).  An empty batch leaves 2^63 - 1.  d_key must be pre-set (to 2^63 - 1) by the caller or by passing
+ * reset != 0.  d_cost is float32 (raster scorer) or float64 (analytic scorer, rounded to float32 for the key) according
+ * to cost_is_f64. */
 int uam_best(uam_ctx* ctx, const void* d_cost, int cost_is_f64, int64_t B, int64_t global_offset,
              uint64_t* d_key, int reset, void* stream);
 
@@ -275,7 +278,10 @@ int uam_component_rects(uam_ctx* ctx, const int32_t* d_labels, int H, int W, int
  *                        (Q,bands,H,W); parent = flat index into (bands,H,W); two more predecessor slots after the eight
  *                        in-plane ones: band below (8), band above (9).
  * Frontier-parallel tile relaxation (warp per 32 x 32 tile, Gauss-Seidel row sweeps with (min,+) warp scans); results
- * are bit-identical to Dijkstra.  Synchronises `stream` internally (the number of rounds is data dependent). */
+ * are bit-identical to Dijkstra.  Synchronises `stream` internally (the number of rounds is data dependent).
+ * Precondition for predecessors: every passable cell has cost >= 1 (a weight-0 edge between two cost-0 cells would let
+ * them choose each other); with d_parent != NULL a grid with passable cost-0 cells is refused (UAM_ERR_UNSUPPORTED),
+ * with d_parent == NULL distances are computed as usual (they stay exact for weights >= 0). */
 /* uam_grid_search_goals: start/goal queries.  As uam_grid_search_bands (bands >= 1; d_sources and d_goals are (Q,3) int32
  *                        {band, row, col}), but a query stops as soon as nothing pending can lower its goal's distance:
  *                        dist is exact for the goal and for every node closer to the source than the goal (nodes farther

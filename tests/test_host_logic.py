@@ -157,15 +157,32 @@ def test_shard_range_and_keys():
     assert udist.encode_key(2.5, 101) == k and 0 <= k < 2 ** 63
     assert udist.host_best_key(np.zeros(0)) == udist.KEY_EMPTY
     assert udist.global_best(k) == (2.5, 101)          # no process group: identity
-    # the argmin shortcut and the bit-pattern keys agree, also with zeros / NaN / inf in the vector (key order:
-    # 0 < positive < inf < NaN, ties to the smaller index)
+    # the argmin shortcut and the image keys agree, also with zeros / negatives / NaN / inf in the vector (key order =
+    # float order, -inf < negative < -0 < +0 < positive < inf < NaN, ties to the smaller index)
     rng = np.random.default_rng(3)
-    for special in ([], [0.0], [np.nan], [np.inf, np.nan], [0.0, 0.0, np.nan]):
+
+    def ref_key(c, off):
+        order = sorted(range(c.size), key=lambda i: (np.isnan(c[i]), 0.0 if np.isnan(c[i]) else float(c[i]),
+                                                     0 if np.isnan(c[i]) else (not np.signbit(c[i])), i))
+        return order[0] + off
+    for special in ([], [0.0], [np.nan], [np.inf, np.nan], [0.0, 0.0, np.nan], [-1.5, -1.5, 0.0], [-np.inf, -3.0],
+                    [-0.0, 0.0], [-2.0, np.nan, -2.5]):
         c = rng.random(257).astype(np.float32) + np.float32(0.25)
         c[rng.choice(257, len(special), replace=False)] = special
-        keys = (c.view(np.uint32).astype(np.uint64) << np.uint64(32)) | (np.arange(257, dtype=np.uint64) + np.uint64(7))
-        assert udist.host_best_key(c, 7) == int(keys.min())
+        k = udist.host_best_key(c, 7)
+        assert 0 <= k < udist.KEY_EMPTY
+        cost_k, idx_k = udist.decode_key(k)
+        assert idx_k == ref_key(c, 7), special
+        assert cost_k == c[idx_k - 7] and np.signbit(cost_k) == np.signbit(c[idx_k - 7])
     assert udist.decode_key(udist.host_best_key(np.array([np.nan, 3.0, 1.0], dtype=np.float32)))[1] == 2
+    # every key is a non-negative int64 below KEY_EMPTY, so an empty shard can never win a signed MIN reduction, and a
+    # negative cost beats a positive one (the old bit-pattern key ranked negatives last and an empty shard first)
+    assert udist.host_best_key(np.array([-1.0, 2.0], dtype=np.float32)) < udist.host_best_key(np.array([2.0], dtype=np.float32))
+    assert udist.host_best_key(np.array([np.nan], dtype=np.float32)) < udist.KEY_EMPTY
+    assert min(udist.KEY_EMPTY, udist.host_best_key(np.array([7.0], dtype=np.float32), 3)) != udist.KEY_EMPTY
+    assert np.isnan(udist.decode_key(udist.KEY_EMPTY)[0])
+    with pytest.raises(ValueError):
+        udist.host_best_key(np.zeros(4, dtype=np.float32), 2 ** 31 - 2)
 
 
 _GLOO_WORKER = r'''
@@ -184,6 +201,11 @@ c, i = ud.global_best(key)
 full = ud.gather_costs(torch.from_numpy(np.pad(cost[b:e], (0, 501 - (e - b)))))
 assert (c, i) == (0.5, 17), (c, i)
 assert full.numel() == 1002
+# one rank with an empty shard (fewer units than ranks) and a negative cost on the other: the empty key must lose
+one = np.array([-3.25], dtype=np.float32)
+b, e = ud.shard_range(1, rank, 2)
+key = torch.tensor([ud.host_best_key(one[b:e], b)], dtype=torch.int64)
+assert ud.global_best(key) == (-3.25, 0)
 print('ok', rank)
 '''
 
@@ -289,3 +311,20 @@ def test_seed_from_grid_path_and_rect_area():
     assert np.allclose(sol.seed_from_grid_path([5 * W + 3], (H, W), geo).reshape(N, 2), m.x_start)
     r = np.array([[[0, 0], [4, 0], [4, 3], [0, 3]], [[0, 0], [2, 2], [0, 4], [-2, 2]]], dtype=np.float64)
     assert np.allclose(uam.mapgen.rect_area(r), [12.0, 8.0])
+
+
+def test_map_signature_follows_content(fixture_spec):
+    """the cached device shape table must be re-uploaded after in-place edits (centre, inequality record) and
+    must not be confused by rebuilt lists -- the signature is a hash of the uploaded content, not of object ids."""
+    from conftest import build_product_map
+    m = build_product_map(fixture_spec)
+    s0 = m._signature()
+    assert s0 == build_product_map(fixture_spec)._signature()          # same content, other objects
+    m.obstacles[0].center = np.array([1.0, 2.0])
+    s1 = m._signature()
+    assert s1 != s0
+    m.obstacles[1].inequalities[0].record[3] += 0.5
+    s2 = m._signature()
+    assert s2 not in (s0, s1)
+    m.regions['Land']['shapes'].pop()
+    assert m._signature() not in (s0, s1, s2)

@@ -174,6 +174,55 @@ def test_raster_reduces_to_analytic(omap, fixture_spec, golden):
     assert np.all(col2 >= col[:4])
 
 
+def _rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - b) / np.abs(b)))
+
+
+def test_raster_converges_to_reference_waypoint_mode(omap, fixture_spec, golden):
+    """Raster waypoint mode against the REFERENCE'S analytic get_cost (golden jit_cost, problem.py:38-44) at 2048^2,
+    4096^2 and 8192^2 over the 64 km window: the error is the bilinear discretisation of the rasterised penalty field and
+    nothing else -- second order in the cell size (x ~3.4-4 per doubling: 1.7e-4, 5.1e-5, 1.5e-5; 3.6e-6 at 16384^2,
+    asserted on the GPU where the full rasterisation is cheap).  float32 vs float64 texels make no difference at this
+    level (checked when the rate was measured).  Only the texels the paths touch are rasterised here."""
+    f = fixture_spec
+    Z = full_paths(f, golden['jit_x'])
+    ref = golden['jit_cost']
+    err = {}
+    for R in (2048, 4096, 8192):
+        geo = (8.0, 64.0 / R, -42.0, 64.0 / R)
+        layers, occ = orc.rasterize_along_paths(omap, Z, R, R, *geo, 0.0)
+        cost, col, ns = orc.score_paths_raster(layers, occ, geo, Z, f['weights'], 0.0, True, f['x_start'])
+        err[R] = _rel(cost, ref)
+        del layers, occ
+    assert err[2048] < 2.5e-4 and err[4096] < 7e-5 and err[8192] < 2e-5, err
+    assert err[2048] / err[4096] > 2.8 and err[4096] / err[8192] > 2.8, err
+
+
+def test_raster_integral_mode_pinned_to_reference(omap, fixture_spec):
+    """Integral mode against golden_integral.npz = the reference's own get_total_penalty_function (problem.py:49-82) at
+    every sample position of the line integral + the reference's length_of (tests/golden/make_golden_integral.py).  Same
+    sample counts; cost error = bilinear discretisation, x 4 per doubling: 3.9e-5 at 4096^2, 9.7e-6 at 8192^2 (7.8 m
+    cells -- the cell size of the benchmarked configuration), i.e. within north_star's 1e-5 at the benchmarked size."""
+    import os
+    gi = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'golden_integral.npz'))
+    f = fixture_spec
+    x0, y0, side = gi['window']
+    err = {}
+    for R in (4096, 8192):
+        geo = (x0, side / R, y0, side / R)
+        e = 0.0
+        for name, key in (('N5', 'arc_N5'), ('N62', 'jit_N62')):
+            Z = gi['paths_' + name]
+            layers, occ = orc.rasterize_along_paths(omap, Z, R, R, *geo, float(gi['spc']))
+            cost, col, ns = orc.score_paths_raster(layers, occ, geo, Z, f['weights'], float(gi['spc']), True, f['x_start'])
+            assert np.array_equal(ns, gi[f'nsamples_{key}_R{R}'])
+            e = max(e, _rel(cost, gi[f'cost_{key}_R{R}']))
+            del layers, occ
+        err[R] = e
+    assert err[4096] < 5e-5 and err[8192] <= 1e-5, err
+    assert err[4096] / err[8192] > 3.0, err
+
+
 def test_oracle_gradient_matches_finite_differences(omap, fixture_spec, golden):
     """The analytic gradient restatement against central differences of the golden-pinned get_cost."""
     f = fixture_spec

@@ -1,4 +1,4 @@
-// Best candidate of a batch: min over b of (float32 bits of cost[b] << 32 | global index) -- the device half of the
+// Best candidate of a batch: min over b of uam_best_key(cost[b], global index) (uam_internal.cuh) -- the device half of the
 // running min of path_generation/main.py:162-180; the 8-byte key is min-reduced across ranks by the caller (NCCL).
 #include <algorithm>
 
@@ -9,11 +9,10 @@ namespace {
 template <typename CT>
 __global__ void __launch_bounds__(256)
 uam_k_best(const CT* __restrict__ cost, long long B, unsigned long long offset, unsigned long long* __restrict__ key) {
-    unsigned long long best = ~0ull;
+    unsigned long long best = UAM_KEY_EMPTY;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
-        const float c = (float)cost[b];
-        const unsigned long long k = ((unsigned long long)__float_as_uint(c) << 32) | ((offset + (unsigned long long)b) & 0xffffffffull);
+        const unsigned long long k = uam_best_key((float)cost[b], offset + (unsigned long long)b);
         best = k < best ? k : best;
     }
 #pragma unroll
@@ -26,7 +25,7 @@ uam_k_best(const CT* __restrict__ cost, long long B, unsigned long long offset, 
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < (int)(blockDim.x >> 5); ++i) best = s[i] < best ? s[i] : best;
-        if (best != ~0ull) atomicMin(key, best);
+        if (best != UAM_KEY_EMPTY) atomicMin(key, best);
     }
 }
 
@@ -38,12 +37,12 @@ extern "C" int uam_best(uam_ctx* ctx, const void* d_cost, int cost_is_f64, int64
                         uint64_t* d_key, int reset, void* stream) {
     if (!ctx) return UAM_ERR_INVALID;
     if (!d_key || B < 0 || (B > 0 && !d_cost)) return uam_fail(ctx, UAM_ERR_INVALID, "bad argument to uam_best");
-    if (global_offset < 0 || global_offset + B > 0xffffffffll)
-        return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "global path index must fit 32 bits");
+    if (global_offset < 0 || global_offset + B > 0x7fffffffll)
+        return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "global path index must fit 31 bits");
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = uam_pick_stream(ctx, stream);
     if (reset) {
-        uam_k_set_u64<<<1, 1, 0, st>>>((unsigned long long*)d_key, ~0ull);
+        uam_k_set_u64<<<1, 1, 0, st>>>((unsigned long long*)d_key, UAM_KEY_EMPTY);
         UAM_CHECK_LAUNCH(ctx, "uam_k_set_u64");
     }
     if (B == 0) return UAM_OK;

@@ -114,7 +114,7 @@ uam_k_grad_analytic(const double2* __restrict__ z, long long B, int N, UamParams
                     const double2 a = j >= 1 ? zp[j - 1] : make_double2(prm.ms_x, prm.ms_y);
                     const double dx = p.x - a.x, dy = p.y - a.y;
                     if (len_smooth) { Lx += 2.0 * dx; Ly += 2.0 * dy; }
-                    else { const double n = sqrt(dx * dx + dy * dy); Lx += dx / n; Ly += dy / n; }
+                    else { const double n = sqrt(dx * dx + dy * dy); if (n > 0.0) { Lx += dx / n; Ly += dy / n; } }   // |d| = 0: zero subgradient
                 }
                 // pair starting at z_j: (z_j, z_{j+1}) for j <= N-1
                 if (j <= N - 1) {
@@ -122,7 +122,7 @@ uam_k_grad_analytic(const double2* __restrict__ z, long long B, int N, UamParams
                     const double dx = q.x - p.x, dy = q.y - p.y;
                     const double n = sqrt(dx * dx + dy * dy);
                     if (len_smooth) { Lx -= 2.0 * dx; Ly -= 2.0 * dy; len_sum += n * n; }
-                    else { Lx -= dx / n; Ly -= dy / n; len_sum += n; }
+                    else { if (n > 0.0) { Lx -= dx / n; Ly -= dy / n; } len_sum += n; }
                 }
                 if (j == 0 && !own_start) {
                     const double dx = p.x - prm.ms_x, dy = p.y - prm.ms_y;

@@ -466,25 +466,39 @@ __global__ void uam_k_grid_extract(const int* __restrict__ parent, UamGridGeo g,
     }
 }
 
+// sum of the cell costs (-> mean, for the automatic delta) and number of passable cells of cost 0
 __global__ void __launch_bounds__(256)
-uam_k_grid_cost_sum(const uint16_t* __restrict__ cost, size_t n, unsigned long long* __restrict__ sum) {
-    unsigned long long acc = 0;
+uam_k_grid_cost_sum(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ blocked, size_t n,
+                    unsigned long long* __restrict__ sum) {
+    unsigned long long acc = 0, zeros = 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) acc += cost[t];
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        const unsigned c = cost[t];
+        acc += c;
+        zeros += (c == 0 && !(blocked && blocked[t])) ? 1u : 0u;
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(sum, acc);
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sum, acc);
+        if (zeros) atomicAdd(sum + 1, zeros);
+    }
 }
 
-int uam_grid_mean_cost(uam_ctx* ctx, const uint16_t* d_cost, size_t n, cudaStream_t st, unsigned long long* mean) {
+int uam_grid_mean_cost(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, size_t n, cudaStream_t st,
+                       unsigned long long* mean, unsigned long long* zero_cells) {
     unsigned long long* d_sum = (unsigned long long*)ctx->d_scratch;        // scratch: the keys are initialised after this
-    UAM_CUDA(ctx, cudaMemsetAsync(d_sum, 0, 8, st));
-    uam_k_grid_cost_sum<<<ctx->sm_count * 8, 256, 0, st>>>(d_cost, n, d_sum);
+    UAM_CUDA(ctx, cudaMemsetAsync(d_sum, 0, 16, st));
+    uam_k_grid_cost_sum<<<ctx->sm_count * 8, 256, 0, st>>>(d_cost, d_blocked, n, d_sum);
     UAM_CHECK_LAUNCH(ctx, "uam_k_grid_cost_sum");
-    unsigned long long h = 0;
-    UAM_CUDA(ctx, cudaMemcpyAsync(&h, d_sum, 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long h[2] = {0, 0};
+    UAM_CUDA(ctx, cudaMemcpyAsync(h, d_sum, 16, cudaMemcpyDeviceToHost, st));
     UAM_CUDA(ctx, cudaStreamSynchronize(st));
-    *mean = std::max<unsigned long long>(1ull, h / (unsigned long long)n);
+    *mean = std::max<unsigned long long>(1ull, h[0] / (unsigned long long)n);
+    *zero_cells = h[1];
     return UAM_OK;
 }
 
@@ -510,9 +524,16 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     unsigned long long* keys = (unsigned long long*)ctx->d_scratch;
     // delta = cost of crossing about two tiles at the grid's mean cell cost (ordering only: any value gives the same result)
     unsigned long long delta = ctx->grid_delta > 0 ? (unsigned long long)ctx->grid_delta : 0ull;
-    if (!delta) {
-        UAM_TRY(uam_grid_mean_cost(ctx, d_cost, (size_t)H * W * bands, st, &delta));
-        delta = delta * 8ull * GT;     // measured on C5 (Q = 16): 4x / 8x / 16x -> 640 / 448 / 336 rounds, 1.69 / 1.77 / 2.06 M activations
+    {
+        unsigned long long mean = 1, zero_cells = 0;
+        UAM_TRY(uam_grid_mean_cost(ctx, d_cost, d_blocked, (size_t)H * W * bands, st, &mean, &zero_cells));
+        // Edge weights are positive only for cost >= 1.  Two adjacent passable cells of cost 0 are joined by a weight-0 edge:
+        // the distances stay exact, but the predecessor rule (argmin of du + w, strict '<' in slot order) could make the
+        // two cells each other's parent.  Predecessors are therefore refused on such grids (block the cells or use cost 1).
+        if (zero_cells && d_parent)
+            return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "%llu passable cells have cost 0: predecessors need cost >= 1 on every passable cell "
+                                                      "(pass d_parent = NULL for distances only)", zero_cells);
+        if (!delta) delta = mean * 8ull * GT;     // measured on C5 (Q = 16): 4x / 8x / 16x -> 640 / 448 / 336 rounds, 1.69 / 1.77 / 2.06 M activations
     }
     unsigned long long* list_key = keys + n_flags;
     unsigned long long* minkey = list_key + n_flags;

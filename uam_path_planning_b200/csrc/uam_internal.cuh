@@ -273,6 +273,18 @@ __device__ __forceinline__ int uam_shape_grid_cell(const UamShapeGrid& sg, doubl
     return (int)fy * sg.G + (int)fx;
 }
 
+// Best-candidate key (uam_best, the fused tail of the raster scorer): 63 bits, (order-preserving image of the float32 cost)
+// << 31 | global index (31 bits).  The image flips all bits of a negative cost and sets the top bit of a non-negative one,
+// so unsigned order = float order for EVERY value (negative costs are reachable through negative layer weights), NaN maps
+// to the largest image (a NaN never wins), and the key is a non-negative int64: the unsigned device min and the signed
+// min of the cross-rank all-reduce agree.  Empty batch = 2^63 - 1 = distributed.KEY_EMPTY.
+#define UAM_KEY_EMPTY 0x7fffffffffffffffull
+__device__ __forceinline__ unsigned long long uam_best_key(float c, unsigned long long index) {
+    unsigned bits = __float_as_uint(c);
+    bits = (c != c) ? 0xffffffffu : ((bits & 0x80000000u) ? ~bits : (bits | 0x80000000u));
+    return ((unsigned long long)bits << 31) | (index & 0x7fffffffull);
+}
+
 __device__ __forceinline__ float uam_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

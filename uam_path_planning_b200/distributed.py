@@ -2,9 +2,11 @@
 ranges over the ranks with the map replicated per GPU; the only exchange is the final argmin of the best path
 (path_generation/main.py:162-180) -- one 8-byte min-all-reduce over NCCL (gloo on CPU in the tests).
 
-Key = (float32 bit pattern of the cost << 32) | global path index.  Costs are >= 0, so the bit pattern orders
-like the value, the key is a non-negative int64, and ties resolve to the smaller index (the strict `<` of
-main.py:175).
+Key = (img(float32 cost) << 31) | global path index (31 bits), img = order-preserving image of the float32 bit
+pattern: all bits flipped for a negative value, top bit set otherwise, NaN -> 0xFFFFFFFF.  The integer order of the
+keys is the float order of the costs for every value (negative costs are reachable through negative layer weights),
+a NaN never wins, ties resolve to the smaller index (the strict `<` of main.py:175), and every key is a non-negative
+int64 <= KEY_EMPTY, so the device's unsigned atomicMin and the signed MIN of the all-reduce agree.
 """
 from __future__ import annotations
 
@@ -24,27 +26,41 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def _image(cost) -> np.ndarray:
+    """order-preserving uint32 image of float32 values (uam_best_key in csrc/uam_internal.cuh)"""
+    c = np.atleast_1d(np.asarray(cost, dtype=np.float32))
+    bits = c.view(np.uint32)
+    img = np.where(bits & np.uint32(0x80000000), ~bits, bits | np.uint32(0x80000000))
+    return np.where(np.isnan(c), np.uint32(0xFFFFFFFF), img).astype(np.uint32)
+
+
 def encode_key(cost: float, index: int) -> int:
-    bits = int(np.float32(cost).view(np.uint32))
-    return (bits << 32) | (int(index) & 0xFFFFFFFF)
+    if not 0 <= int(index) < 2 ** 31:
+        raise ValueError('global path index must fit 31 bits')
+    return (int(_image(cost)[0]) << 31) | int(index)
 
 
 def decode_key(key: int) -> Tuple[float, int]:
+    """(cost, global index); KEY_EMPTY (no candidate) decodes to (nan, 2^31 - 1)"""
     key = int(key)
-    return float(np.uint32((key >> 32) & 0xFFFFFFFF).view(np.float32)), key & 0xFFFFFFFF
+    img = (key >> 31) & 0xFFFFFFFF
+    bits = (img ^ 0x80000000) if img & 0x80000000 else (~img & 0xFFFFFFFF)
+    return float(np.uint32(bits).view(np.float32)), key & 0x7FFFFFFF
 
 
 def host_best_key(cost: np.ndarray, global_offset: int = 0) -> int:
-    """Host-side packing of an already computed cost vector into the key (used for tiny batches and tests;
-    the device path is Engine.best)."""
-    cost = np.asarray(cost, dtype=np.float32)
+    """Host-side packing of an already computed cost vector into the key (used for tiny batches, the host-buffer
+    entry points and tests; the device path is Engine.best)."""
+    cost = np.asarray(cost, dtype=np.float32).ravel()
     if cost.size == 0:
         return KEY_EMPTY
-    i = int(np.argmin(cost))            # first minimum = smallest index on ties, like the key order
-    if cost[i] > 0.0:                   # strictly positive and not NaN: the float order is the bit-pattern order
-        return encode_key(cost[i], i + int(global_offset))
-    keys = (cost.view(np.uint32).astype(np.uint64) << np.uint64(32)) | (
-        (np.arange(cost.size, dtype=np.uint64) + np.uint64(global_offset)) & np.uint64(0xFFFFFFFF))
+    if int(global_offset) < 0 or int(global_offset) + cost.size > 2 ** 31 - 1:
+        raise ValueError('global path index must fit 31 bits')
+    if not np.isnan(cost).any():
+        i = int(np.argmin(cost))        # first minimum = smallest index on ties, like the key order (-0.0 < +0.0 aside)
+        if cost[i] != 0.0:
+            return encode_key(cost[i], i + int(global_offset))
+    keys = (_image(cost).astype(np.uint64) << np.uint64(31)) | (np.arange(cost.size, dtype=np.uint64) + np.uint64(global_offset))
     return int(keys.min())
 
 

@@ -282,8 +282,8 @@ class Engine:
         return Z
 
     def best(self, cost, global_offset: int = 0, key=None):
-        """min over b of (float32 bits of cost[b] << 32 | global_offset + b) as a 1-element int64 CUDA tensor
-        (costs >= 0, so the key is a non-negative int64 and orders like (cost, index))."""
+        """min over b of key(cost[b], global_offset + b) as a 1-element int64 CUDA tensor; the key (distributed.py) orders
+        like (cost, index) for every float value and is a non-negative int64; an empty batch gives KEY_EMPTY."""
         import torch
         assert _is_tensor(cost) and cost.dtype in (torch.float32, torch.float64)
         reset = key is None

@@ -95,7 +95,8 @@ class Problem:
     def get_cost_gradient(self, z):
         """(cost, d cost / d z_) for one path or a batch; z_ layout as get_cost, the gradient has the same shape (its
         columns 2..2N+1 are the solver's decision variables, solver.py:59).  Analytic stand-in for the derivative
-        CasADi generates for OpEn (solver.py:82-101)."""
+        CasADi generates for OpEn (solver.py:82-101).  With length_smooth = False a pair of coincident consecutive points
+        (always the case for (map.x_start, z_0) in the reference's layout) contributes the zero subgradient, never NaN."""
         Z, single = self._batched(z)
         cost, grad = self.map.engine().grad_analytic(Z, self.N, self.parameter_vector(), self.flags())
         return (float(cost[0]), grad[0]) if single else (cost, grad)

@@ -47,7 +47,15 @@ class Map:
         return []
 
     def _signature(self):
-        return (tuple(id(o) for o in self.obstacles), tuple(len(o.inequalities) for o in self.obstacles))
+        """Content of the device shape table (records + centres, tens of KB): in-place edits of a shape's centre or of an
+        inequality record, and rebuilt shape lists whose objects happen to reuse ids, all change it."""
+        import hashlib
+        from .shapes import flatten_shapes
+        edges, off, reg, cen = flatten_shapes(self.obstacles, self._region_lists())
+        h = hashlib.blake2b(digest_size=16)
+        for a in (edges, off, reg, cen):
+            h.update(a.tobytes())
+        return h.digest()
 
     def engine(self, device: Optional[int] = None):
         """The map's Engine with the current shape table uploaded (rebuilt when the shape lists changed)."""
@@ -124,8 +132,3 @@ class RegionMap(Map):
 
     def _region_lists(self):
         return [r['shapes'] for r in self.regions.values()]
-
-    def _signature(self):
-        return (super()._signature(),
-                tuple((name, tuple(id(s) for s in r['shapes']), tuple(len(s.inequalities) for s in r['shapes']))
-                      for name, r in self.regions.items()))
