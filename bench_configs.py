@@ -33,30 +33,38 @@ def ev_time(torch, fn, reps, warm=2):
     return a.elapsed_time(b) / reps
 
 
-def run_c5(args, torch, uam, dev):
-    eng = uam.Engine()
-    # ---------------- C5 ------------------------------------------------------------------------------------
-    # batched cost-to-go: 4096^2 grid x `bands` altitude bands of uint16 cost, Q queries per launch (a 1024-query job is
-    # 1024/Q launches per GPU x 8 GPUs; queries are independent, so it shards like the paths do)
-    n5 = 4096
-    g = torch.Generator(device=dev).manual_seed(5)
+def run_c5(args, torch, uam, dev, rank=0, world=1, reduce_max=None):
+    """C5: batched cost-to-go / start-goal queries on a 4096^2 grid x `bands` altitude bands of uint16 cost.  Queries are
+    independent: with `world` ranks the job's Q * world queries shard contiguously over the ranks (distributed.shard_range),
+    the grid is replicated, there is no exchange at all; times are the max over ranks (`reduce_max`)."""
+    from uam_path_planning_b200 import distributed as udist
+    eng = uam.Engine(torch.cuda.current_device())
+    reduce_max = reduce_max or (lambda x: x)
+    n5 = args.c5_size
+    out = []
     for bands, Q in ((1, args.c5_queries), (8, args.c5_queries_bands)):
         if Q <= 0:
             continue
+        g = torch.Generator(device=dev).manual_seed(5 + bands)          # same grid and query list on every rank
         shape = (n5, n5) if bands == 1 else (bands, n5, n5)
         cost = torch.randint(1, 1000, shape, device=dev, generator=g, dtype=torch.int32).to(torch.uint16)
         blk = (torch.rand(shape, device=dev, generator=g) < 0.1).to(torch.uint8)
-        if bands == 1:
-            src = torch.randint(0, n5, (Q, 2), device=dev, generator=g, dtype=torch.int32)
-            blk[src[:, 0].long(), src[:, 1].long()] = 0
-        else:
-            src = torch.cat([torch.randint(0, bands, (Q, 1), device=dev, generator=g, dtype=torch.int32),
-                             torch.randint(0, n5, (Q, 2), device=dev, generator=g, dtype=torch.int32)], dim=1)
-            blk[src[:, 0].long(), src[:, 1].long(), src[:, 2].long()] = 0
+        Qall = Q * world
+        src = torch.randint(0, n5, (Qall, 2), device=dev, generator=g, dtype=torch.int32)
+        goal = torch.randint(0, n5, (Qall, 2), device=dev, generator=g, dtype=torch.int32)
+        if bands > 1:
+            sb = torch.randint(0, bands, (Qall, 1), device=dev, generator=g, dtype=torch.int32)
+            src, goal = torch.cat([sb, src], dim=1), torch.cat([sb, goal], dim=1)
+        idx = lambda t: tuple(t[:, k].long() for k in range(t.shape[1]))
+        blk[idx(src)] = 0
+        b0, b1 = udist.shard_range(Qall, rank, world)
+        src, goal = src[b0:b1].contiguous(), goal[b0:b1].contiguous()
+        Ql = b1 - b0
+        # ---- full cost-to-go sweeps (distance + parent fields) -------------------------------------------------
         dt = 1e30
-        for rep in range(3):                                            # first call = warm-up (scratch allocation); best of the rest
-            if rep:
-                del dist, parent
+        dist = parent = None
+        for rep in range(1 + args.c5_reps):                             # first call = warm-up (scratch allocation)
+            del dist, parent
             l0 = eng.launch_count()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -64,84 +72,67 @@ def run_c5(args, torch, uam, dev):
             torch.cuda.synchronize()
             if rep:
                 dt = min(dt, time.perf_counter() - t0)
+        launches = eng.launch_count() - l0
+        full_stats = {k: eng.get_stat('grid_' + k) for k in ('activations', 'sweeps', 'rounds')}
         reach = float((dist < 2 ** 62).float().mean().item())
-        # start/goal form of the same queries: goals uniform in the grid, every query stops when its goal is final; the
-        # goal distances must equal the full sweep's
-        goal = src.clone()
-        goal[:, -2:] = torch.randint(0, n5, (Q, 2), device=dev, generator=g, dtype=torch.int32)
-        gidx = tuple(goal[:, k].long() for k in range(goal.shape[1]))
-        d_goal_full = dist[(torch.arange(Q, device=dev),) + gidx].clone()
+        d_goal_full = dist[(torch.arange(Ql, device=dev),) + idx(goal)].clone()
+        cpu = None
+        if not args.no_cpu and rank == 0:
+            # CPU baseline: heap Dijkstra of oracle/uam_oracle_c.c, one query per thread (SURVEY 8d item 4), and a full-size
+            # parity check of those queries
+            from oracle import uam_oracle_c as occ
+            cores = os.cpu_count() or 1
+            nq = min(Ql, cores if bands == 1 else max(1, cores // 8))
+            t0 = time.perf_counter()
+            d_ref, _ = occ.grid_search(cost.cpu().numpy(), src[:nq].cpu().numpy(), blk.cpu().numpy(), want_parent=False, threads=cores)
+            dtc = time.perf_counter() - t0
+            cpu = {'queries': nq, 'threads': min(nq, cores), 'seconds': dtc, 'queries_per_s': nq / dtc,
+                   'dist_equal_gpu': bool(np.array_equal(dist[:nq].cpu().numpy(), d_ref))}
+            del d_ref
         del dist, parent
+        # ---- start/goal form of the same queries: every query stops when its goal is final ---------------------
         dtg = 1e30
-        for rep in range(2):
+        for rep in range(1 + args.c5_reps):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             dist, parent = eng.grid_search(cost, src, blk, goals=goal)
             path, plen = eng.grid_paths(parent, src, goal, max_len=8 * n5)
             torch.cuda.synchronize()
-            dtg = min(dtg, time.perf_counter() - t0)
-            if rep == 0:
-                del dist, parent
-        goals_ok = bool(torch.equal(dist[(torch.arange(Q, device=dev),) + gidx], d_goal_full))
-        goal_stats = {'seconds': dtg, 'queries_per_s': Q / dtg, 'goal_distances_equal_full_sweep': goals_ok,
-                      'tile_activations': eng.get_stat('grid_activations'), 'rounds': eng.get_stat('grid_rounds'),
-                      'mean_path_nodes': float(plen.float().mean().item()), 'paths_found': int((plen > 0).sum().item())}
-        del path, plen
-        del dist, parent
-        dist, parent = eng.grid_search(cost, src, blk)          # the full sweep again: its counters and fields are reported below
+            if rep:
+                dtg = min(dtg, time.perf_counter() - t0)
+            if rep < args.c5_reps:
+                del dist, parent, path, plen
+        goals_ok = bool(torch.equal(dist[(torch.arange(Ql, device=dev),) + idx(goal)], d_goal_full))
+        goal_stats = {k: eng.get_stat('grid_' + k) for k in ('activations', 'rounds')}
+        mean_nodes, found = float(plen.float().mean().item()), int((plen > 0).sum().item())
+        del dist, parent, path, plen, cost, blk
+        dt, dtg = reduce_max(dt), reduce_max(dtg)
         nodes = bands * n5 * n5
         edges = nodes * (8 + (2 if bands > 1 else 0))
-        nodes = bands * n5 * n5
-        cpu = None
-        if not args.no_cpu:
-            # CPU baseline: heap Dijkstra of oracle/uam_oracle_c.c, one query per thread (SURVEY 8d item 4), and a full-size
-            # parity check of those queries
-            from oracle import uam_oracle_c as occ
-            cores = os.cpu_count() or 1
-            nq = min(Q, cores if bands == 1 else max(1, cores // 8))
-            t0 = time.perf_counter()
-            d_ref, _ = occ.grid_search(cost.cpu().numpy(), src[:nq].cpu().numpy(), blk.cpu().numpy(), want_parent=False, threads=cores)
-            dtc = time.perf_counter() - t0
-            cpu = {'queries': nq, 'threads': min(nq, cores), 'seconds': dtc, 'queries_per_s': nq / dtc,
-                   'Mnode_per_s': nq * nodes / dtc / 1e6, 'dist_equal_gpu': bool(np.array_equal(dist[:nq].cpu().numpy(), d_ref))}
-            del d_ref
-        print(json.dumps({'config': f'C5: cost-to-go on a {n5}^2 8-connected grid x {bands} altitude band(s), {Q} queries per launch, 1 B200',
-                          'cpu_baseline': cpu, 'start_goal_queries': goal_stats,
-                          'seconds': dt, 'queries_per_s': Q / dt, 'Mnode_per_s': Q * nodes / dt / 1e6,
-                          'min_edge_relaxations_per_s': Q * edges * reach / dt,
-                          'kernel_launches': eng.launch_count() - l0, 'reachable_fraction': reach,
-                          'tile_activations': eng.get_stat('grid_activations'), 'double_sweeps': eng.get_stat('grid_sweeps'),
-                          'rounds': eng.get_stat('grid_rounds'), 'tiles': Q * bands * (n5 // 32) ** 2,
-                          'note': 'exact distances + parents (bit-identical to Dijkstra); warp-per-tile Gauss-Seidel sweeps'}))
-        del dist, parent, cost, blk
+        out.append({'config': f'C5: cost-to-go on a {n5}^2 8-connected grid x {bands} altitude band(s), {Q} queries per GPU per launch, '
+                              f'{world} B200 ({Qall} queries)', 'bands': bands, 'queries': Qall, 'n_gpus': world,
+                    'full_sweeps': {'seconds': dt, 'queries_per_s': Qall / dt, 'Mnode_per_s': Qall * nodes / dt / 1e6,
+                                    'min_edge_relaxations_per_s': Qall * edges * reach / dt, 'kernel_launches_per_call': launches,
+                                    'reachable_fraction': reach, **{k + '_rank0': v for k, v in full_stats.items()}},
+                    'start_goal_queries': {'seconds': dtg, 'queries_per_s': Qall / dtg, 'goal_distances_equal_full_sweep': goals_ok,
+                                           'mean_path_nodes': mean_nodes, 'paths_found_rank0': found,
+                                           **{k + '_rank0': v for k, v in goal_stats.items()}},
+                    'cpu_baseline': cpu,
+                    'note': 'exact distances + parents (bit-identical to Dijkstra); warp-per-tile Gauss-Seidel sweeps; queries '
+                            'sharded over the ranks, grid replicated, no collective'})
+    return out
 
 
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--c4-size', type=int, default=16384)
-    ap.add_argument('--reps', type=int, default=5)
-    ap.add_argument('--skip-c4', action='store_true')
-    ap.add_argument('--skip-c5', action='store_true')
-    ap.add_argument('--c5-queries', type=int, default=16)
-    ap.add_argument('--c5-queries-bands', type=int, default=4)
-    ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--only', default='', help="'c2' / 'c5': run only that config")
-    args = ap.parse_args()
-    import torch
-    import uam_path_planning_b200 as uam
-    assert torch.cuda.is_available()
-    dev = 'cuda'
-    peak = 6650.0
+def hbm_peak():
     try:
-        peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+        return float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
     except Exception:
-        pass
-    if args.only == 'c5':
-        run_c5(args, torch, uam, dev)
-        return
-    rng = np.random.default_rng(20260101)
+        return 6650.0
 
+
+def run_c2(args, torch, uam, dev):
+    peak = hbm_peak()
+    rng = np.random.default_rng(20260101)
     # ---------------- C2 ------------------------------------------------------------------------------------
     n, KM, Wp, B = 4096, 64.0, 64, 10000
     m = uam.RegionMap()
@@ -205,14 +196,13 @@ def main():
                                 'shape_grid_cells': eng_a.get_stat('shape_grid_cells'),
                                 'shape_grid_items': eng_a.get_stat('shape_grid_items'),
                                 'note': 'fp64 analytic scorer (Problem.get_cost + collides) with per-cell candidate lists over the shapes'}
-    print(json.dumps(out))
     del rm, Z
-    if args.only == 'c2':
-        return
+    return out
 
-    if args.skip_c4:
-        run_c5(args, torch, uam, dev)
-        return
+
+def run_c4(args, torch, uam, dev):
+    peak = hbm_peak()
+    rng = np.random.default_rng(20260104)
     # ---------------- C4 ------------------------------------------------------------------------------------
     n = args.c4_size
     sys.path.insert(0, ROOT)
@@ -304,12 +294,34 @@ def main():
         t0 = time.perf_counter()
         orc.rasterize_layers(om4, cr, cr, *geo, 0.0)
         res['cpu_layers_numpy_Mcell_s'] = cr * cr / (time.perf_counter() - t0) / 1e6
-    print(json.dumps(res))
-    del occ, mm
-    del eng
-    if args.skip_c5:
-        return
-    run_c5(args, torch, uam, dev)
+    del occ, mm, eng
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--c4-size', type=int, default=16384)
+    ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--skip-c4', action='store_true')
+    ap.add_argument('--skip-c5', action='store_true')
+    ap.add_argument('--c5-size', type=int, default=4096)
+    ap.add_argument('--c5-queries', type=int, default=16)
+    ap.add_argument('--c5-queries-bands', type=int, default=4)
+    ap.add_argument('--c5-reps', type=int, default=2)
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--only', default='', help="'c2' / 'c4' / 'c5': run only that config")
+    args = ap.parse_args()
+    import torch
+    import uam_path_planning_b200 as uam
+    assert torch.cuda.is_available()
+    dev = 'cuda'
+    if args.only in ('', 'c2'):
+        print(json.dumps(run_c2(args, torch, uam, dev)))
+    if args.only in ('', 'c4') and not args.skip_c4:
+        print(json.dumps(run_c4(args, torch, uam, dev)))
+    if args.only in ('', 'c5') and not args.skip_c5:
+        for line in run_c5(args, torch, uam, dev):
+            print(json.dumps(line))
 
 
 if __name__ == '__main__':

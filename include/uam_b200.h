@@ -147,6 +147,14 @@ int uam_map_set_raster_device(uam_ctx* ctx, const float* d_layers, int L, int H,
 int uam_make_arc_paths(uam_ctx* ctx, const double* h_ends, int N, const double* d_displacement, int64_t B,
                        double* d_z, void* stream);
 
+/* The general form: row b of d_cand = {xs, ys, xg, yg, displacement} -- every candidate its own start / goal (a batch of
+ * independent start/goal queries, 40 bytes each) -- and, for jitter_sigma > 0, N(0, sigma^2) added to both coordinates of
+ * the N interior waypoints (start and goal stay fixed, as in the reference's flow create_x_init -> solve, main.py:160-171).
+ * The normals come from a counter-based generator keyed by (seed, index0 + b, waypoint): a candidate depends on its global
+ * index only, not on the batch split or the number of GPUs. */
+int uam_make_candidates(uam_ctx* ctx, const double* d_cand, int64_t B, int N, double jitter_sigma, uint64_t seed,
+                        uint64_t index0, double* d_z, void* stream);
+
 /* ---- path scoring: analytic shapes -------------------------------------------------------------
  * Replaces, batched over B paths:
  *   d_cost[b]    = Problem.get_cost(z_)                      path_generation/problem.py:38-44
@@ -196,6 +204,32 @@ int uam_score_paths_raster_host(uam_ctx* ctx, const double* h_z, int64_t B, int 
                                 int n_p, int flags, double samples_per_cell, float* h_cost,
                                 uint8_t* h_collide);
 
+/* Scoring + best candidate in one call: as uam_score_paths_raster, and *d_key receives the best key (see uam_best) of the
+ * batch -- of ALL ranks' batches when a peer group is attached (uam_peer_attach): the last kernel of the step finds the
+ * local min, pushes it into every peer's symmetric block over NVLink and waits for theirs (no separate collective).
+ * Every rank of the group must make the same sequence of *_best / uam_best_allreduce calls (B == 0 is allowed). */
+int uam_score_paths_raster_best(uam_ctx* ctx, const double* d_z, int64_t B, int N, const double* h_p, int n_p,
+                                int flags, double samples_per_cell, float* d_cost, uint8_t* d_collide,
+                                int64_t global_offset, uint64_t* d_key, void* stream);
+
+/* Asynchronous host-buffer scoring: a ring of 3 slots (stream + staging each).  submit queues upload -> (candidate
+ * generation ->) whole-batch scoring -> download on the slot's stream and returns a ticket at once; uam_raster_wait(ticket)
+ * returns when the results are in h_cost / h_collide / *h_key (nullable; *h_key = this rank's best key with
+ * global_offset + b as index).  With two tickets in flight the upload of batch s+1 overlaps the kernels of batch s.  The
+ * host buffers must stay valid (and should be pinned) until the wait; a 4th submission first waits for the oldest ticket.
+ *   uam_raster_submit_paths_host       h_z (B, 2(N+2)) float64: the caller's waypoints (1 KiB per path at N = 62)
+ *   uam_raster_submit_candidates_host  h_cand (B, 5) float64 {xs, ys, xg, yg, displacement}: the candidates are generated on
+ *                                      the device (uam_make_candidates with index0 = global_offset), 40 bytes per path --
+ *                                      the reference's own flow (displacement -> create_x_init -> score, main.py:160-171) */
+int uam_raster_submit_paths_host(uam_ctx* ctx, const double* h_z, int64_t B, int N, const double* h_p, int n_p,
+                                 int flags, double samples_per_cell, float* h_cost, uint8_t* h_collide,
+                                 uint64_t* h_key, int64_t global_offset, int* ticket);
+int uam_raster_submit_candidates_host(uam_ctx* ctx, const double* h_cand, int64_t B, int N, double jitter_sigma,
+                                      uint64_t seed, const double* h_p, int n_p, int flags, double samples_per_cell,
+                                      float* h_cost, uint8_t* h_collide, uint64_t* h_key, int64_t global_offset,
+                                      int* ticket);
+int uam_raster_wait(uam_ctx* ctx, int ticket);
+
 /* ---- point queries --------------------------------------------------------------------------------
  * Replaces Problem.get_penalty_function(region)(x) (problem.py:59-82), get_total_penalty_function
  * (:49-56) and Map.collides(x) (map.py:41-43) for M points x (M,2) float64.  Outputs nullable:
@@ -224,6 +258,19 @@ int uam_eval_inequalities_host(uam_ctx* ctx, const double* h_records, int n_rec,
  * to cost_is_f64. */
 int uam_best(uam_ctx* ctx, const void* d_cost, int cost_is_f64, int64_t B, int64_t global_offset,
              uint64_t* d_key, int reset, void* stream);
+
+/* The same with the cross-rank exchange built in: *d_key = min over the attached peer group (or this rank alone when no
+ * group is attached) of the batch keys; B == 0 takes part with "no candidate".  One kernel: local min + push / wait over
+ * NVLink peer memory in its last CTA. */
+int uam_best_allreduce(uam_ctx* ctx, const void* d_cost, int cost_is_f64, int64_t B, int64_t global_offset,
+                       uint64_t* d_key, void* stream);
+/* Peer group of the ranks of one box (one process per GPU).  uam_peer_export writes the 64-byte CUDA IPC handle of this
+ * ctx's symmetric block; the caller all-gathers the handles (torch.distributed, any backend) and passes all `world` of them
+ * (rank order, 64 bytes each) to uam_peer_attach, which maps the peers' blocks.  uam_peer_status: *timed_out != 0 if a
+ * wait for the peers ever gave up (2 s; the key of that step is then a partial min). */
+int uam_peer_export(uam_ctx* ctx, void* h_handle64);
+int uam_peer_attach(uam_ctx* ctx, int rank, int world, const void* h_handles);
+int uam_peer_status(uam_ctx* ctx, int* timed_out);
 
 /* ---- map rebuild (map_generation) --------------------------------------------------------------------
  * uam_dem_mask: mask = image > threshold, or image == -9999 when threshold == -9999

@@ -342,6 +342,47 @@ def create_x_init(x_start, x_goal, N: int, displacement: float = 0.0) -> np.ndar
 # --------------------------------------------------------------------------- #
 # config 1: tests/test_path_generation.py inline problem (:28-66)
 # --------------------------------------------------------------------------- #
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over='ignore'):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def candidate_normals(seed: int, index: np.ndarray, Wp: int) -> np.ndarray:
+    """(len(index), Wp, 2) standard normals of the device candidate generator (csrc/uam_candidates.cu: splitmix64 of
+    (seed, path index, waypoint) -> two uniforms -> Box-Muller).  Build-defined (the reference jitters nothing)."""
+    ctr = (np.asarray(index, dtype=np.uint64)[:, None] * np.uint64(Wp) + np.arange(Wp, dtype=np.uint64)[None, :])
+    with np.errstate(over='ignore'):
+        h1 = _splitmix64(np.uint64(seed) ^ _splitmix64(np.uint64(2) * ctr))
+        h2 = _splitmix64(np.uint64(seed) ^ _splitmix64(np.uint64(2) * ctr + np.uint64(1)))
+    u1 = ((h1 >> np.uint64(11)) + np.uint64(1)).astype(F64) * 2.0 ** -53
+    u2 = (h2 >> np.uint64(11)).astype(F64) * 2.0 ** -53
+    r = np.sqrt(-2.0 * np.log(u1))
+    a = 6.283185307179586 * u2
+    return np.stack([r * np.cos(a), r * np.sin(a)], axis=-1)
+
+
+def make_candidates(cand: np.ndarray, N: int, jitter_sigma: float = 0.0, seed: int = 0, index0: int = 0) -> np.ndarray:
+    """rows {xs, ys, xg, yg, displacement} -> (B, 2(N+2)) paths [start, create_x_init(displacement), goal]
+    (solver.py:103-136 per candidate) + N(0, sigma^2) jitter on the N interior waypoints."""
+    cand = np.asarray(cand, dtype=F64).reshape(-1, 5)
+    B = cand.shape[0]
+    Z = np.empty((B, N + 2, 2), dtype=F64)
+    Z[:, 0], Z[:, -1] = cand[:, 0:2], cand[:, 2:4]
+    straight = cand[:, 4] == 0.0
+    if straight.any():                 # np.linspace on arrays performs the same operations as on scalars (create_x_init, d = 0)
+        Z[straight, 1:-1, 0] = np.linspace(cand[straight, 0], cand[straight, 2], N + 2, axis=1)[:, 1:-1]
+        Z[straight, 1:-1, 1] = np.linspace(cand[straight, 1], cand[straight, 3], N + 2, axis=1)[:, 1:-1]
+    for b in np.nonzero(~straight)[0]:
+        Z[b, 1:-1] = create_x_init(cand[b, 0:2], cand[b, 2:4], N, float(cand[b, 4])).reshape(N, 2)
+    if jitter_sigma:
+        n = candidate_normals(seed, index0 + np.arange(B), N + 2)
+        Z[:, 1:-1] += jitter_sigma * n[:, 1:-1]
+    return Z.reshape(B, 2 * (N + 2))
+
+
 def testscript_cost(z, z_start, z_goal, center, R: float = 2.0, w_dist: float = 1.0,
                     w_obs: float = 500.0) -> Tuple[float, float, float]:
     """dist = sum |dz|^2 over N+1 segments; penalty = sum_i max(0, R - |z_i-c|^2)^2 over the N free

@@ -755,6 +755,139 @@ def test_device_candidate_generator(uam, torch, fixture_spec, golden, N):
     np.testing.assert_allclose(c_d, prob.get_cost(Zh[big]), rtol=1e-9)
 
 
+def test_make_candidates_per_candidate_ends_and_jitter(uam, torch):
+    """uam_make_candidates: every candidate its own start / goal / displacement (Solver.create_x_init per row,
+    solver.py:103-136) + counter-based Gaussian jitter on the interior waypoints, against the oracle's restatement; a
+    candidate depends on its global index only (index0 + b), not on how the batch is split."""
+    rng = np.random.default_rng(5)
+    B, N = 300, 62
+    cand = np.concatenate([rng.uniform(0, 64, (B, 4)), rng.uniform(-0.9, 0.9, (B, 1))], axis=1)
+    cand[:40, 4] = 0.0                                                  # straight lines
+    eng = uam.Engine()
+    ct = torch.from_numpy(cand).cuda()
+    Z0 = eng.make_candidates(ct, N).cpu().numpy()
+    R0 = orc.make_candidates(cand, N)
+    np.testing.assert_allclose(Z0, R0, rtol=0, atol=1e-11 * 64)
+    assert np.array_equal(Z0[:40], R0[:40])                             # straight lines without jitter: same bits
+    assert np.array_equal(Z0[:, :2], cand[:, :2]) and np.array_equal(Z0[:, -2:], cand[:, 2:4])
+    Zj = eng.make_candidates(ct, N, 0.25, seed=99, index0=1000).cpu().numpy()
+    Rj = orc.make_candidates(cand, N, 0.25, 99, 1000)
+    np.testing.assert_allclose(Zj, Rj, rtol=0, atol=1e-11 * 64)
+    assert np.array_equal(Zj[:, :2], cand[:, :2]) and np.array_equal(Zj[:, -2:], cand[:, 2:4])      # ends stay fixed
+    jit = (Zj - Z0)[:, 2:-2] / 0.25
+    assert abs(jit.mean()) < 0.02 and abs(jit.std() - 1.0) < 0.02
+    # split invariance: the second half generated alone with its global index base
+    Zh = eng.make_candidates(ct[150:].contiguous(), N, 0.25, seed=99, index0=1150).cpu().numpy()
+    assert np.array_equal(Zh, Zj[150:])
+    assert not np.array_equal(eng.make_candidates(ct, N, 0.25, seed=100, index0=1000).cpu().numpy(), Zj)
+    with pytest.raises(ValueError):
+        eng.make_candidates(torch.tensor([[0, 0, 1, 1, 1.5]], dtype=torch.float64).cuda(), N)
+
+
+@pytest.mark.parametrize('spc,variant', [(1.0, 2), (1.0, 0), (0.0, -1)])
+def test_fused_best_and_async_ring(uam, torch, spc, variant):
+    """uam_score_paths_raster_best (best key from the tail of the step's last kernel), uam_raster_submit_paths_host /
+    uam_raster_submit_candidates_host / uam_raster_wait (ring of 3 in-flight host-buffer batches): same bits as the plain
+    device-pointer call, key == the host's packing of the costs, candidates generated on the device == scoring the
+    generator's own output, oracle parity on those paths."""
+    from uam_path_planning_b200 import distributed as ud
+    rng = np.random.default_rng(21)
+    H, W, geo = 300, 400, (3.0, 0.25, 40.0, -0.2)
+    lay, occ = _random_raster(rng, 3, H, W)
+    rm = uam.RasterMap.from_arrays(lay, geo, occ, options={'integral_variant': variant})
+    w = [200.0, 15000.0, 27000.0]
+    N, B = 30, 5000
+    Z = _random_paths(rng, B, N + 2, geo, H, W, 0.02)
+    Zt = torch.from_numpy(Z).cuda()
+    c0, k0 = rm.score_paths(Zt, w, spc, True, None)
+    c1, k1, key = rm.score_paths_best(Zt, w, spc, True, None, global_offset=777)
+    assert torch.equal(c0, c1) and torch.equal(k0, k1)
+    assert int(key.item()) == ud.host_best_key(c0.cpu().numpy(), 777)
+    e0, _, ekey = rm.score_paths_best(Zt[:0], w, spc, True, None, global_offset=5)
+    assert e0.numel() == 0 and int(ekey.item()) == ud.KEY_EMPTY
+    # ring: 5 submissions (two more than slots) of different batches, waited for out of order
+    pin = lambda *sh, dt: torch.empty(sh, dtype=dt).pin_memory().numpy()
+    outs, tickets = [], []
+    for i in range(5):
+        Zi = pin(B - 100 * i, 2 * (N + 2), dt=torch.float64)
+        Zi[:] = Z[100 * i:]
+        co, kl, ky = pin(len(Zi), dt=torch.float32), pin(len(Zi), dt=torch.uint8), pin(1, dt=torch.int64).view(np.uint64)
+        tickets.append(rm.submit(w, spc, co, kl, Z=Zi, key=ky, global_offset=10 * i))
+        outs.append((Zi, co, kl, ky))
+    for i in (4, 0, 3, 1, 2):
+        rm.wait(tickets[i])
+        Zi, co, kl, ky = outs[i]
+        assert np.array_equal(co, c0.cpu().numpy()[100 * i:]) and np.array_equal(kl, k0.cpu().numpy()[100 * i:])
+        assert int(ky[0]) == ud.host_best_key(co, 10 * i)
+    # candidates generated on the device (40 bytes per path)
+    cand = np.concatenate([rng.uniform(5, 95, (B, 2)) , rng.uniform(5, 95, (B, 2)), rng.uniform(-0.5, 0.5, (B, 1))], axis=1)
+    cand[:, [0, 2]] = geo[0] + cand[:, [0, 2]] / 100 * W * geo[1]
+    cand[:, [1, 3]] = geo[2] + cand[:, [1, 3]] / 100 * H * geo[3]
+    cc, kc, keyc = rm.score_candidates(cand, N, w, spc, jitter_sigma=0.3, seed=4, global_offset=2000)
+    Zg = rm.engine.make_candidates(torch.from_numpy(cand).cuda(), N, 0.3, 4, 2000)
+    cg, kg = rm.score_paths(Zg, w, spc, True, None)
+    assert np.array_equal(cc, cg.cpu().numpy()) and np.array_equal(kc, kg.cpu().numpy())
+    assert keyc == ud.host_best_key(cc, 2000)
+    c_ref, k_ref, _ = orc.score_paths_raster(lay, occ, geo, Zg.cpu().numpy()[:400], w, spc, True, None)
+    np.testing.assert_allclose(cc[:400], c_ref, rtol=RTOL_RASTER)
+    assert np.array_equal(kc[:400].astype(bool), k_ref)
+    empty_c, empty_k, empty_key = rm.score_candidates(np.zeros((0, 5)), N, w, spc)
+    assert empty_c.size == 0 and empty_key == ud.KEY_EMPTY
+
+
+_PEER_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+rank, world = int(sys.argv[3]), int(sys.argv[4])
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:' + sys.argv[2], rank=rank, world_size=world)
+import uam_path_planning_b200 as uam
+from uam_path_planning_b200 import distributed as ud
+dev = rank % torch.cuda.device_count()
+torch.cuda.set_device(dev)
+eng = uam.Engine(dev)
+assert ud.attach_peer_group(eng) == world
+rng = np.random.default_rng(3)
+cost = rng.uniform(1, 100, 40001).astype(np.float32)         # the same global vector on every rank
+cost[[17, 30000]] = 0.5                                       # a tie across shards -> the smaller index
+for step in range(12):
+    c = cost.copy()
+    c[(step * 3331) % c.size] = 0.25 - 0.01 * step            # a new winner every step
+    if step == 7:
+        c[5] = -3.0                                           # a negative cost wins over everything
+    b, e = ud.shard_range(c.size, rank, world) if step != 9 else ((0, c.size) if rank == 0 else (c.size, c.size))   # step 9: empty shards
+    key = eng.best_allreduce(torch.from_numpy(c[b:e]).cuda(), b)
+    got = ud.decode_key(int(key.item()))
+    want = (float(c.min()), int(np.argmin(c)))
+    assert got == want, (step, rank, got, want)
+assert not eng.peer_timed_out()
+dist.barrier()
+print('ok', rank)
+'''
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_best_allreduce_over_peer_memory(torch, tmp_path, world):
+    """The cross-rank argmin without NCCL: `world` processes (one per GPU when the box has that many, else sharing cuda:0)
+    exchange CUDA IPC handles over gloo, then every step's key is min-reduced by stores into the peers' symmetric blocks
+    from the tail of uam_k_best -- ties, a negative cost, empty shards, 12 epochs through the 4-slot ring."""
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = str(s.getsockname()[1])
+    s.close()
+    script = tmp_path / 'w.py'
+    script.write_text(_PEER_WORKER)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = [subprocess.Popen([sys.executable, str(script), root, port, str(r), str(world)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f'ok {r}' in o, o[-3000:]
+
+
 @pytest.mark.parametrize('variant', [0, 2, 3])
 def test_degenerate_paths_do_not_disturb_the_batch(uam, torch, variant):
     """NaN / inf / far-outside waypoints and zero-length segments: the call returns, rows without such values keep

@@ -206,6 +206,13 @@ one = np.array([-3.25], dtype=np.float32)
 b, e = ud.shard_range(1, rank, 2)
 key = torch.tensor([ud.host_best_key(one[b:e], b)], dtype=torch.int64)
 assert ud.global_best(key) == (-3.25, 0)
+# peer-group plumbing (the CUDA IPC handles are plain bytes): every rank ends up with all handles in rank order
+class FakeEngine:
+    def peer_handle(self): return bytes([rank]) * 64
+    def attach_peers(self, r, handles): self.got = (r, list(handles))
+fe = FakeEngine()
+assert ud.attach_peer_group(fe) == 2
+assert fe.got == (rank, [bytes([0]) * 64, bytes([1]) * 64])
 print('ok', rank)
 '''
 

@@ -56,6 +56,16 @@ SIGNATURES = {
     'uam_length_of': (_i, [_vp, _vp, _i64, _i, _i, _vp, _i, _vp, _vp]),
     'uam_length_of_host': (_i, [_vp, _vp, _i64, _i, _i, _vp, _i, _vp]),
     'uam_best': (_i, [_vp, _vp, _i, _i64, _i64, _vp, _i, _vp]),
+    'uam_best_allreduce': (_i, [_vp, _vp, _i, _i64, _i64, _vp, _vp]),
+    'uam_peer_export': (_i, [_vp, _vp]),
+    'uam_peer_attach': (_i, [_vp, _i, _i, _vp]),
+    'uam_peer_status': (_i, [_vp, C.POINTER(_i)]),
+    'uam_make_candidates': (_i, [_vp, _vp, _i64, _i, _d, C.c_uint64, C.c_uint64, _vp, _vp]),
+    'uam_score_paths_raster_best': (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _d, _vp, _vp, _i64, _vp, _vp]),
+    'uam_raster_submit_paths_host': (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _i64, C.POINTER(_i)]),
+    'uam_raster_submit_candidates_host': (_i, [_vp, _vp, _i64, _i, _d, C.c_uint64, _vp, _i, _i, _d, _vp, _vp, _vp, _i64,
+                                               C.POINTER(_i)]),
+    'uam_raster_wait': (_i, [_vp, _i]),
     'uam_dem_mask': (_i, [_vp, _vp, _i64, C.c_float, _vp, _vp]),
     'uam_rasterize_occupancy': (_i, [_vp, _i, _i, _d, _d, _d, _d, _vp, _vp]),
     'uam_rasterize_layers': (_i, [_vp, _i, _i, _d, _d, _d, _d, _d, _vp, _vp]),

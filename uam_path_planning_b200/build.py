@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libuam_b200.so')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC,-ffp-contract=off', '-shared', '-cudart', 'static']
+              '-Xcompiler', '-fPIC,-ffp-contract=off', '-shared', '-cudart', 'static', '-ldl']
 
 
 def sources():

@@ -515,6 +515,7 @@ int uam_scan(uam_ctx* ctx, F f, long long n, OUT out, unsigned long long* block_
 extern "C" int uam_label_components(uam_ctx* ctx, const uint8_t* d_mask, int H, int W, int connectivity, int32_t* d_labels,
                                     int32_t* h_n_components, void* stream) {
     if (!ctx) return UAM_ERR_INVALID;
+    UAM_NVTX("uam.map.label_components");
     if (H < 0 || W < 0) return uam_fail(ctx, UAM_ERR_INVALID, "negative raster size");
     if (connectivity != 4 && connectivity != 8) return uam_fail(ctx, UAM_ERR_INVALID, "connectivity must be 4 or 8");
     const long long n = (long long)H * W;
@@ -546,6 +547,7 @@ extern "C" int uam_label_components(uam_ctx* ctx, const uint8_t* d_mask, int H, 
 extern "C" int uam_component_stats(uam_ctx* ctx, const int32_t* d_labels, int H, int W, int n_components, int64_t* d_area,
                                    int32_t* d_bbox, void* stream) {
     if (!ctx) return UAM_ERR_INVALID;
+    UAM_NVTX("uam.map.component_stats");
     if (H < 0 || W < 0 || n_components < 0) return uam_fail(ctx, UAM_ERR_INVALID, "negative size");
     if (n_components == 0) return UAM_OK;
     if (!d_labels || !d_area || !d_bbox) return uam_fail(ctx, UAM_ERR_INVALID, "NULL pointer");
@@ -573,6 +575,7 @@ extern "C" int uam_component_rects(uam_ctx* ctx, const int32_t* d_labels, int H,
                                    const int32_t* d_ids, int K, double x0, double dx, double y0, double dy, double* d_rect,
                                    int32_t* d_info, void* stream) {
     if (!ctx) return UAM_ERR_INVALID;
+    UAM_NVTX("uam.map.component_rects");
     if (H < 0 || W < 0 || n_components < 0 || K < 0) return uam_fail(ctx, UAM_ERR_INVALID, "negative size");
     if (K == 0) return UAM_OK;
     if (!d_labels || !d_bbox || !d_ids || !d_rect) return uam_fail(ctx, UAM_ERR_INVALID, "NULL pointer");

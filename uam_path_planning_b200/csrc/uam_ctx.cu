@@ -243,6 +243,14 @@ extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
         if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
         if (ctx->pipe_event[i]) cudaEventDestroy(ctx->pipe_event[i]);
     }
+    for (int i = 0; i < UAM_HOST_PIPE_DEPTH; ++i) {
+        cudaFree(ctx->d_ring_cand[i]);
+        cudaFree(ctx->d_ring_key[i]);
+    }
+    cudaFree(ctx->d_best_local);
+    for (int r = 0; r < ctx->peer_world; ++r)
+        if (r != ctx->peer_rank && ctx->peer_ptr[r]) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
+    cudaFree(ctx->d_peer_own);
     for (int i = 0; i < 2 * uam_ctx::kTimeRing; ++i)
         if (ctx->time_ev[i]) cudaEventDestroy(ctx->time_ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -273,6 +281,7 @@ extern "C" int uam_map_set_shapes(uam_ctx* ctx, const double* h_edges, int n_edg
                                   const int32_t* h_shape_region, const double* h_shape_center, int n_shapes,
                                   int n_regions) {
     if (!ctx) return UAM_ERR_INVALID;
+    UAM_NVTX("uam.map.set_shapes");
     if (n_shapes < 0 || n_edges < 0 || n_regions < 0) return uam_fail(ctx, UAM_ERR_INVALID, "negative table size");
     if (n_regions > UAM_MAX_REGIONS)
         return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "%d regions, at most %d supported", n_regions, UAM_MAX_REGIONS);
@@ -444,6 +453,7 @@ static int uam_check_raster_args(uam_ctx* ctx, const void* layers, int L, int H,
 extern "C" int uam_map_set_raster_device(uam_ctx* ctx, const float* d_layers, int L, int H, int W, double x0, double dx,
                                          double y0, double dy, const uint8_t* d_occupancy, void* stream) {
     UAM_TRY(uam_check_raster_args(ctx, d_layers, L, H, W, dx, dy));
+    UAM_NVTX("uam.map.set_raster (pack texels)");
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = uam_pick_stream(ctx, stream);
     const int tf = (L == 1) ? 2 : 4;

@@ -511,6 +511,7 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     if ((size_t)H * W * bands >= 0x7fffffffull) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "grid has 2^31 or more nodes");
     if (Q == 0) return UAM_OK;
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UAM_NVTX("uam.grid_search");
     cudaStream_t st = uam_pick_stream(ctx, stream);
     UamGridGeo g;
     g.H = H; g.W = W; g.bands = bands; g.Q = Q; g.src_stride = src_stride;

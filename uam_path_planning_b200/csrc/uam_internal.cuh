@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <string>
@@ -57,6 +58,28 @@ struct UamRasterGeo {
     int layout;               // 0 = row-major texels, 1 = tiled (see uam_tex_index)
     int tiles_x;              // tiled: tiles per tile-row (tile = 4 x 2 texels for float4, 4 x 4 for float2)
     int tiles_y;
+};
+
+// ---- best-candidate exchange between the ranks of one box (uam_best.cu) -------------------------------------------
+// One-sided min-reduce of the 8-byte best key over NVLink peer memory: every rank owns a small "symmetric block"
+// (cudaMalloc + CUDA IPC, mapped into every peer process); the tail of the scoring step stores this rank's key into its
+// own column of every peer's block, raises an epoch-tagged flag behind a system-scope fence, then waits until the flags
+// of all ranks carry the epoch and takes the min -- the all-reduce is part of the step's last kernel, no NCCL launch.
+#define UAM_MAX_PEERS 16
+#define UAM_PEER_RING 4        // epochs in flight: a rank cannot be more than one epoch ahead of a peer (it waits for all)
+struct UamPeerBlock {
+    unsigned long long keys[UAM_PEER_RING][UAM_MAX_PEERS];
+    unsigned flags[UAM_PEER_RING][UAM_MAX_PEERS];      // = epoch of the key in the same cell (monotone, never reset)
+};
+struct UamBestTail {
+    unsigned long long* local;     // [0] running min of this launch, [1] CTAs done (both restored by the last CTA)
+    unsigned long long* out;       // where the (global) best key goes (device, nullable)
+    unsigned* status;              // != 0: the wait for the peers timed out
+    UamPeerBlock* peer[UAM_MAX_PEERS];
+    unsigned long long offset;     // global index of this launch's first path
+    int world, rank;               // world <= 1: no exchange
+    unsigned epoch;
+    int combine;                   // 1: *out = min(*out, key) (uam_best's accumulate form), 0: *out = key
 };
 
 // ---- context --------------------------------------------------------------------------------------
@@ -145,6 +168,18 @@ struct uam_ctx {
     int combine_layers = 1;             // UAM_OPT_COMBINE_LAYERS
     void* d_piece_scratch[UAM_HOST_PIPE_DEPTH + 1] = {};
     size_t piece_scratch_bytes[UAM_HOST_PIPE_DEPTH + 1] = {};
+    // best-candidate tail / peer exchange (uam_best.cu)
+    unsigned long long* d_best_local = nullptr;      // {running min, CTAs done, status} x (1 + UAM_HOST_PIPE_DEPTH) slots
+    UamPeerBlock* d_peer_own = nullptr;              // this rank's symmetric block
+    UamPeerBlock* peer_ptr[UAM_MAX_PEERS] = {};      // every rank's block as mapped here ([rank] = d_peer_own)
+    int peer_world = 0, peer_rank = 0;
+    unsigned peer_epoch = 0;
+    // asynchronous host-buffer scoring (uam_raster_submit_* / uam_raster_wait): one ticket per pipeline slot
+    int ring_next = 0;
+    bool ring_busy[UAM_HOST_PIPE_DEPTH] = {};
+    void* d_ring_cand[UAM_HOST_PIPE_DEPTH] = {};
+    size_t ring_cand_bytes[UAM_HOST_PIPE_DEPTH] = {};
+    unsigned long long* d_ring_key[UAM_HOST_PIPE_DEPTH] = {};
 };
 
 int uam_fail(uam_ctx* ctx, int code, const char* fmt, ...);
@@ -160,6 +195,24 @@ cudaStream_t uam_pick_stream(uam_ctx* ctx, void* stream);
 int uam_time_collect(uam_ctx* ctx);
 int uam_time_begin(uam_ctx* ctx, cudaStream_t st);
 int uam_time_end(uam_ctx* ctx, cudaStream_t st);
+// best-candidate tail (uam_best.cu): the tail descriptor for a launch that starts at global index `offset` (slot = which
+// {running min, counter} pair of the ctx: 0 for caller-stream calls, 1.. for the host pipeline slots); with_peers: exchange
+// with the attached ranks (advances the epoch); and the stand-alone kernel for scorers without a fused tail
+int uam_best_tail(uam_ctx* ctx, int slot, unsigned long long offset, unsigned long long* d_out, bool with_peers, bool combine,
+                  UamBestTail* tail);
+int uam_best_launch(uam_ctx* ctx, const void* d_cost, int cost_is_f64, int64_t B, const UamBestTail& tail, cudaStream_t st);
+int uam_make_candidates_launch(uam_ctx* ctx, const double* d_cand, const double* h_ends, const double* d_disp, int N, int64_t B,
+                               double jitter_sigma, uint64_t seed, uint64_t index0, double* d_z, cudaStream_t st);
+
+// NVTX range over the rest of the enclosing scope (host side; a no-op costing a few ns when no profiler is attached):
+// upload / bin / score / reduce / exchange phases show up by name on an Nsight Systems timeline
+struct UamNvtxRange {
+    explicit UamNvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~UamNvtxRange() { nvtxRangePop(); }
+};
+#define UAM_NVTX_CAT2(a, b) a##b
+#define UAM_NVTX_CAT(a, b) UAM_NVTX_CAT2(a, b)
+#define UAM_NVTX(name) UamNvtxRange UAM_NVTX_CAT(uam_nvtx_, __LINE__)(name)
 
 #define UAM_CUDA(ctx, call)                                             \
     do {                                                                \
@@ -283,6 +336,81 @@ __device__ __forceinline__ unsigned long long uam_best_key(float c, unsigned lon
     unsigned bits = __float_as_uint(c);
     bits = (c != c) ? 0xffffffffu : ((bits & 0x80000000u) ? ~bits : (bits | 0x80000000u));
     return ((unsigned long long)bits << 31) | (index & 0x7fffffffull);
+}
+
+// ---- tail of a best-candidate launch -----------------------------------------------------------------------------------
+// Every CTA calls it once with its own min key (thread 0's value counts); the last CTA to arrive owns the launch's min, and
+// its first warp exchanges it with the peers: lane r stores the key into column `rank` of rank r's block, fences, raises
+// the flag, then waits (bounded: ~2 s) for column r of its own block and the warp takes the min.  Must be reached by all
+// threads of the CTA (it synchronises).
+__device__ __forceinline__ unsigned long long uam_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void uam_best_tail_cta(const UamBestTail& tl, unsigned long long cta_key) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        if (cta_key != UAM_KEY_EMPTY) atomicMin(tl.local, cta_key);
+        __threadfence();
+        const unsigned long long t = atomicAdd(tl.local + 1, 1ull);
+        s_last = (t == (unsigned long long)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    __threadfence();
+    unsigned long long key = *((volatile unsigned long long*)tl.local);
+    if (lane == 0) {                       // ready for the next launch on this slot
+        tl.local[0] = UAM_KEY_EMPTY;
+        tl.local[1] = 0ull;
+    }
+    if (tl.world > 1) {
+        const int ring = (int)(tl.epoch % UAM_PEER_RING);
+        if (lane < tl.world) {
+            UamPeerBlock* pb = tl.peer[lane];
+            *((volatile unsigned long long*)&pb->keys[ring][tl.rank]) = key;
+            __threadfence_system();
+            *((volatile unsigned*)&pb->flags[ring][tl.rank]) = tl.epoch;
+        }
+        unsigned long long got = UAM_KEY_EMPTY;
+        bool late = false;
+        if (lane < tl.world) {
+            UamPeerBlock* own = tl.peer[tl.rank];
+            const unsigned long long t0 = uam_globaltimer();
+            while (*((volatile unsigned*)&own->flags[ring][lane]) != tl.epoch) {
+                if (uam_globaltimer() - t0 > 2000000000ull) { late = true; break; }
+                __nanosleep(64);
+            }
+            __threadfence_system();
+            if (!late) got = *((volatile unsigned long long*)&own->keys[ring][lane]);
+        }
+        if (__any_sync(0xffffffffu, late) && lane == 0 && tl.status) atomicExch(tl.status, 1u);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, got, o);
+            got = t < got ? t : got;
+        }
+        key = got;
+    }
+    if (lane == 0 && tl.out) {
+        if (tl.combine) atomicMin(tl.out, key);
+        else *tl.out = key;
+    }
+}
+// min over the CTA of per-thread keys (all threads call; thread 0 returns the CTA's min)
+__device__ __forceinline__ unsigned long long uam_cta_min_key(unsigned long long k) {
+    __shared__ unsigned long long s_k[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o);
+        k = t < k ? t : k;
+    }
+    if ((threadIdx.x & 31) == 0) s_k[threadIdx.x >> 5] = k;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int i = 1; i < (int)((blockDim.x + 31) >> 5); ++i) k = s_k[i] < k ? s_k[i] : k;
+    return k;
 }
 
 __device__ __forceinline__ float uam_warp_sum(float v) {

@@ -465,6 +465,7 @@ uam_k_edt_clearance(const int* __restrict__ d2, long long n, double cell, float*
 extern "C" int uam_dem_mask(uam_ctx* ctx, const float* d_image, int64_t n, float threshold, uint8_t* d_mask,
                             void* stream) {
     if (!ctx) return UAM_ERR_INVALID;
+    UAM_NVTX("uam.map.dem_mask");
     if (n < 0 || (n > 0 && (!d_image || !d_mask))) return uam_fail(ctx, UAM_ERR_INVALID, "bad argument to uam_dem_mask");
     if (n == 0) return UAM_OK;
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -537,6 +538,9 @@ extern "C" int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, doubl
 extern "C" int uam_edt(uam_ctx* ctx, const uint8_t* d_occ, int H, int W, double cell, int32_t* d_dist2,
                        float* d_clearance, void* stream) {
     if (!ctx) return UAM_ERR_INVALID;
+    UAM_NVTX("uam.map.edt");
+    UAM_NVTX("uam.map.rasterize_layers");
+    UAM_NVTX("uam.map.rasterize_occupancy");
     if (H < 1 || W < 1 || !d_occ || (!d_dist2 && !d_clearance)) return uam_fail(ctx, UAM_ERR_INVALID, "bad argument to uam_edt");
     if (H > 23170 || W > 23170) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "raster larger than 23170 per side (d^2 must stay below 2^30)");
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -298,6 +298,7 @@ int uam_analytic_prepare(uam_ctx* ctx, const double* h_p, int n_p, int flags, cu
 extern "C" int uam_score_paths_analytic(uam_ctx* ctx, const double* d_z, int64_t B, int N, const double* h_p, int n_p,
                                         int flags, double* d_cost, uint8_t* d_collide, double* d_g, void* stream) {
     if (!ctx) return UAM_ERR_INVALID;
+    UAM_NVTX("uam.analytic.score");
     if (B < 0 || N < 1) return uam_fail(ctx, UAM_ERR_INVALID, "need B >= 0 and N >= 1 (got B=%lld N=%d)", (long long)B, N);
     if (B > 0 && !d_z) return uam_fail(ctx, UAM_ERR_INVALID, "paths pointer is NULL");
     cudaStream_t st = uam_pick_stream(ctx, stream);

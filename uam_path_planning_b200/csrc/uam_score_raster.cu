@@ -928,14 +928,17 @@ uam_k_score_groups(unsigned long long n_seg, int Wp, UamRasterParams rp, const t
 }
 
 // one warp per path: fixed-order sum of the per-segment partials + the length term
+// BEST: the launch also finds the best candidate (and exchanges it with the peer ranks): uam_best_tail_cta
+template <int BEST>
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
 uam_k_reduce_paths(const double2* __restrict__ z, long long B, int Wp, UamRasterParams rp,
                    const float* __restrict__ part_pen, const uint8_t* __restrict__ part_col, float* __restrict__ cost,
-                   uint8_t* __restrict__ collide, long long* __restrict__ nsamp) {
+                   uint8_t* __restrict__ collide, long long* __restrict__ nsamp, UamBestTail tl) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * UAM_WARPS_PER_CTA + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * UAM_WARPS_PER_CTA;
     const int N = Wp - 2;
+    unsigned long long kbest = UAM_KEY_EMPTY;
     for (long long path = warp0; path < B; path += nwarps) {
         const double2* zp = z + path * Wp;
         float acc = 0.0f;
@@ -966,11 +969,17 @@ uam_k_reduce_paths(const double2* __restrict__ z, long long B, int Wp, UamRaster
             for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
         }
         if (lane == 0) {
-            if (cost) cost[path] = (float)((double)(N + 1) * len_sum + (double)acc / (double)N);
+            const float c = (float)((double)(N + 1) * len_sum + (double)acc / (double)N);
+            if (cost) cost[path] = c;
             if (collide) collide[path] = col ? 1 : 0;
             if (nsamp) nsamp[path] = ns;
+            if (BEST) {
+                const unsigned long long k = uam_best_key(c, tl.offset + (unsigned long long)path);
+                kbest = k < kbest ? k : kbest;
+            }
         }
     }
+    if (BEST) uam_best_tail_cta(tl, uam_cta_min_key(kbest));
 }
 
 // ---- integral mode, tile-staged (variant 3) ----------------------------------------------------------------------
@@ -1389,7 +1398,8 @@ int uam_raster_prepare(uam_ctx* ctx, int64_t B, int N, const double* h_p, int n_
 
 template <int TF, int LAYOUT>
 int uam_raster_launch_binned(uam_ctx* ctx, const void* texv, const double2* z, int64_t B, int Wp, const UamRasterParams& rp,
-                             float* d_cost, uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
+                             float* d_cost, uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot,
+                             const UamBestTail* best, bool* best_done) {
     typedef typename UamTexel<TF>::T T;
     const unsigned long long n_seg = (unsigned long long)B * Wp;
     UamBinGeo bg;
@@ -1408,6 +1418,7 @@ int uam_raster_launch_binned(uam_ctx* ctx, const void* texv, const double2* z, i
     unsigned* cursor = hist + bg.nbins;
     unsigned short* seg_bin = (unsigned short*)(cursor + bg.nbins);
     uint8_t* part_col = (uint8_t*)(seg_bin + n_seg);
+    UAM_NVTX("uam.raster.binned");
     UAM_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)bg.nbins * 4, st));
     const unsigned chunks = (unsigned)((n_seg + UAM_BIN_CHUNK - 1) / UAM_BIN_CHUNK);
     const size_t hsmem = (size_t)bg.nbins * 4;
@@ -1415,25 +1426,35 @@ int uam_raster_launch_binned(uam_ctx* ctx, const void* texv, const double2* z, i
         UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
         UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
     }
+    nvtxRangePushA("uam.raster.bin");
     uam_k_bin_hist<<<chunks, 1024, hsmem, st>>>(z, n_seg, Wp, rp, bg, seg_bin, hist);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_hist");
     uam_k_bin_scan<<<1, 1024, 0, st>>>(hist, bg.nbins, cursor);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_scan");
     uam_k_bin_scatter<<<chunks, 1024, hsmem, st>>>(n_seg, bg, seg_bin, cursor, sorted_id);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_scatter");
+    nvtxRangePop();
     const size_t gsmem = (size_t)UAM_GROUP_SMEM * UAM_WARPS_PER_CTA;
     const unsigned long long n_groups = (n_seg + 31) >> 5;
     const long long sctas = std::min<long long>((long long)((n_groups + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA), (long long)ctx->sm_count * 16);
     if (ctx->time_kernels && slot == 0) {
         UAM_TRY(uam_time_begin(ctx, st));
     }
+    nvtxRangePushA("uam.raster.score");
     uam_k_score_groups<TF, LAYOUT><<<(unsigned)sctas, UAM_CTA_THREADS, gsmem, st>>>(n_seg, Wp, rp, (const T*)texv, z, sorted_id, part_pen, part_col);
+    nvtxRangePop();
     UAM_CHECK_LAUNCH(ctx, "uam_k_score_groups");
     if (ctx->time_kernels && slot == 0) {
         UAM_TRY(uam_time_end(ctx, st));
     }
     const long long rctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
-    uam_k_reduce_paths<<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, d_cost, d_collide, d_nsamp);
+    UAM_NVTX("uam.raster.reduce+best");
+    if (best) {
+        uam_k_reduce_paths<1><<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, d_cost, d_collide, d_nsamp, *best);
+        *best_done = true;
+    } else {
+        uam_k_reduce_paths<0><<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, d_cost, d_collide, d_nsamp, UamBestTail{});
+    }
     UAM_CHECK_LAUNCH(ctx, "uam_k_reduce_paths");
     return UAM_OK;
 }
@@ -1524,7 +1545,8 @@ int uam_raster_launch_tiles(uam_ctx* ctx, const void* texv, uint64_t tex_key, co
 
 template <int TF, int LAYOUT>
 int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const double2* z, int64_t B, int Wp,
-                        const UamRasterParams& rp, float* d_cost, uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
+                        const UamRasterParams& rp, float* d_cost, uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot,
+                        const UamBestTail* best, bool* best_done) {
     typedef typename UamTexel<TF>::T T;
     const T* tex = (const T*)texv;
     const bool timed = ctx->time_kernels && slot == 0 && !(rp.spc > 0.0 && rp.variant >= 2);
@@ -1551,7 +1573,7 @@ int uam_raster_launch_t(uam_ctx* ctx, const void* texv, uint64_t tex_key, const 
             UAM_TRY((uam_raster_launch_tiles<TF, LAYOUT>(ctx, texv, tex_key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot, &fell_back)));
             if (!fell_back) return UAM_OK;
         }
-        return uam_raster_launch_binned<TF, LAYOUT>(ctx, texv, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
+        return uam_raster_launch_binned<TF, LAYOUT>(ctx, texv, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot, best, best_done);
     }
   if constexpr (!UamIsQuad<TF>::v) {
     const size_t per_warp = uam_seg_table_bytes(Wp);
@@ -1679,6 +1701,7 @@ int uam_ensure_quads(uam_ctx* ctx, UamRasterParams* rp, cudaStream_t st) {
     rp->occ_blocks_x = blocks_x;
     const bool same_w = tf == 2 || (ctx->comb_w[0] == rp->w0 && ctx->comb_w[1] == rp->w1 && ctx->comb_w[2] == rp->w2);
     if (!(ctx->comb_valid && same_w)) {
+        UAM_NVTX("uam.raster.build_quads");
         const size_t n_out = lay ? (size_t)tiles_x * tiles_y * 8 : (size_t)H * W;
         const unsigned n_words = blocks_x * blocks_y * 32u;
         UAM_CUDA(ctx, cudaDeviceSynchronize());      // kernels on other streams may still read the old quads
@@ -1698,29 +1721,40 @@ int uam_ensure_quads(uam_ctx* ctx, UamRasterParams* rp, cudaStream_t st) {
     return UAM_OK;
 }
 
-// slot: which scratch buffer of the ctx the binned pipeline may use (0 = caller-stream calls, 1.. = host pipeline stages)
+// slot: which scratch buffer of the ctx the binned pipeline may use (0 = caller-stream calls, 1.. = host pipeline stages).
+// best (nullable): also find the best candidate of the launch (fused into the last kernel of the binned pipeline; one more
+// small kernel behind the other scorers).
 int uam_raster_launch(uam_ctx* ctx, const double* d_z, int64_t B, int N, const UamRasterParams& rp, float* d_cost,
-                      uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot) {
+                      uint8_t* d_collide, long long* d_nsamp, cudaStream_t st, int slot, const UamBestTail* best = nullptr) {
     const int Wp = N + 2;
     const double2* z = reinterpret_cast<const double2*>(d_z);
     const int tf = ctx->geo.texel_floats, lay = ctx->geo.layout;
     const uint64_t key = ctx->raster_gen << 1;
+    bool best_done = false;
+    int rc;
+    if (best && !d_cost) return uam_fail(ctx, UAM_ERR_INVALID, "the best-candidate key needs the cost output");
     if (rp.combined) {
         // large-batch integral mode on the quad texels (made by uam_raster_precompute)
-        UamRasterParams rc = rp;
-        if (tf == 4) { rc.w0 = 1.0f; rc.w1 = 0.0f; rc.w2 = 0.0f; }     // the weights are inside the quads
-        rc.row_stride = rp.row_stride2;
+        UamRasterParams rc2 = rp;
+        if (tf == 4) { rc2.w0 = 1.0f; rc2.w1 = 0.0f; rc2.w2 = 0.0f; }     // the weights are inside the quads
+        rc2.row_stride = rp.row_stride2;
         const uint64_t ckey = (ctx->comb_gen << 1) | 1u;
         if (rp.combined == 2)
-            return lay ? uam_raster_launch_t<8, 1>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot)
-                       : uam_raster_launch_t<8, 0>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot);
-        return lay ? uam_raster_launch_t<1, 1>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot)
-                   : uam_raster_launch_t<1, 0>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc, d_cost, d_collide, d_nsamp, st, slot);
+            rc = lay ? uam_raster_launch_t<8, 1>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc2, d_cost, d_collide, d_nsamp, st, slot, best, &best_done)
+                     : uam_raster_launch_t<8, 0>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc2, d_cost, d_collide, d_nsamp, st, slot, best, &best_done);
+        else
+            rc = lay ? uam_raster_launch_t<1, 1>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc2, d_cost, d_collide, d_nsamp, st, slot, best, &best_done)
+                     : uam_raster_launch_t<1, 0>(ctx, ctx->d_tex_comb, ckey, z, B, Wp, rc2, d_cost, d_collide, d_nsamp, st, slot, best, &best_done);
+    } else if (tf == 2) {
+        rc = lay ? uam_raster_launch_t<2, 1>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot, best, &best_done)
+                 : uam_raster_launch_t<2, 0>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot, best, &best_done);
+    } else {
+        rc = lay ? uam_raster_launch_t<4, 1>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot, best, &best_done)
+                 : uam_raster_launch_t<4, 0>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot, best, &best_done);
     }
-    if (tf == 2) return lay ? uam_raster_launch_t<2, 1>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
-                            : uam_raster_launch_t<2, 0>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
-    return lay ? uam_raster_launch_t<4, 1>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot)
-               : uam_raster_launch_t<4, 0>(ctx, ctx->d_tex, key, z, B, Wp, rp, d_cost, d_collide, d_nsamp, st, slot);
+    UAM_TRY(rc);
+    if (best && !best_done) UAM_TRY(uam_best_launch(ctx, d_cost, 0, B, *best, st));
+    return UAM_OK;
 }
 
 // Once per API call, before any chunk is launched: make the quad texels if this call will use them.
@@ -1735,17 +1769,136 @@ int uam_raster_precompute(uam_ctx* ctx, UamRasterParams* rp, int64_t B, int N, c
 
 }  // namespace
 
-extern "C" int uam_score_paths_raster(uam_ctx* ctx, const double* d_z, int64_t B, int N, const double* h_p, int n_p,
-                                      int flags, double samples_per_cell, float* d_cost, uint8_t* d_collide,
-                                      int64_t* d_nsamples, void* stream) {
+static int uam_score_paths_raster_impl(uam_ctx* ctx, const double* d_z, int64_t B, int N, const double* h_p, int n_p, int flags,
+                                       double samples_per_cell, float* d_cost, uint8_t* d_collide, int64_t* d_nsamples,
+                                       bool want_best, int64_t global_offset, uint64_t* d_key, void* stream) {
     if (!ctx) return UAM_ERR_INVALID;
     UamRasterParams rp;
     UAM_TRY(uam_raster_prepare(ctx, B, N, h_p, n_p, flags, samples_per_cell, &rp));
-    if (B == 0) return UAM_OK;
-    if (!d_z) return uam_fail(ctx, UAM_ERR_INVALID, "paths pointer is NULL");
+    if (want_best && (!d_key || global_offset < 0 || global_offset + B > 0x7fffffffll))
+        return uam_fail(ctx, UAM_ERR_INVALID, "best key: NULL pointer or global path index beyond 31 bits");
+    if (B > 0 && !d_z) return uam_fail(ctx, UAM_ERR_INVALID, "paths pointer is NULL");
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
-    UAM_TRY(uam_raster_precompute(ctx, &rp, B, N, uam_pick_stream(ctx, stream)));
-    return uam_raster_launch(ctx, d_z, B, N, rp, d_cost, d_collide, (long long*)d_nsamples, uam_pick_stream(ctx, stream), 0);
+    cudaStream_t st = uam_pick_stream(ctx, stream);
+    UamBestTail tl;
+    if (want_best) UAM_TRY(uam_best_tail(ctx, 0, (unsigned long long)global_offset, (unsigned long long*)d_key, true, false, &tl));
+    if (B == 0) {
+        // an empty shard still takes part in the exchange (its key is "no candidate")
+        if (want_best) UAM_TRY(uam_best_launch(ctx, nullptr, 0, 0, tl, st));
+        return UAM_OK;
+    }
+    UAM_TRY(uam_raster_precompute(ctx, &rp, B, N, st));
+    return uam_raster_launch(ctx, d_z, B, N, rp, d_cost, d_collide, (long long*)d_nsamples, st, 0, want_best ? &tl : nullptr);
+}
+
+extern "C" int uam_score_paths_raster(uam_ctx* ctx, const double* d_z, int64_t B, int N, const double* h_p, int n_p,
+                                      int flags, double samples_per_cell, float* d_cost, uint8_t* d_collide,
+                                      int64_t* d_nsamples, void* stream) {
+    return uam_score_paths_raster_impl(ctx, d_z, B, N, h_p, n_p, flags, samples_per_cell, d_cost, d_collide, d_nsamples, false, 0,
+                                       nullptr, stream);
+}
+
+extern "C" int uam_score_paths_raster_best(uam_ctx* ctx, const double* d_z, int64_t B, int N, const double* h_p, int n_p,
+                                           int flags, double samples_per_cell, float* d_cost, uint8_t* d_collide,
+                                           int64_t global_offset, uint64_t* d_key, void* stream) {
+    return uam_score_paths_raster_impl(ctx, d_z, B, N, h_p, n_p, flags, samples_per_cell, d_cost, d_collide, nullptr, true,
+                                       global_offset, d_key, stream);
+}
+
+// ---- asynchronous host-buffer scoring -------------------------------------------------------------------------------
+// A ring of UAM_HOST_PIPE_DEPTH slots, each with its own stream, staging and scratch: submit() queues the upload of the
+// caller's (pinned) buffers, the whole-batch scoring pipeline and the download of the results on the slot's stream and
+// returns a ticket; wait() blocks until that slot is done.  With two submissions in flight the upload of step s+1 overlaps
+// the kernels of step s, so a stream of host-buffer batches runs at max(PCIe time, kernel time) per batch, and every batch
+// is binned whole (the chunked synchronous call re-streams the raster through L2 once per chunk).
+static int uam_ring_acquire(uam_ctx* ctx, int* slot) {
+    const int s = ctx->ring_next;
+    if (ctx->ring_busy[s]) {
+        UAM_CUDA(ctx, cudaStreamSynchronize(ctx->pipe_stream[s]));      // the oldest ticket: its results are complete now
+        ctx->ring_busy[s] = false;
+    }
+    ctx->ring_next = (s + 1) % UAM_HOST_PIPE_DEPTH;
+    if (!ctx->d_ring_key[s]) UAM_CUDA(ctx, cudaMalloc(&ctx->d_ring_key[s], 8));
+    *slot = s;
+    return UAM_OK;
+}
+
+static int uam_raster_submit_impl(uam_ctx* ctx, const double* h_z, const double* h_cand, double jitter_sigma, uint64_t seed,
+                                  int64_t B, int N, const double* h_p, int n_p, int flags, double spc, float* h_cost,
+                                  uint8_t* h_collide, uint64_t* h_key, int64_t global_offset, int* ticket) {
+    if (!ctx) return UAM_ERR_INVALID;
+    if (!ticket) return uam_fail(ctx, UAM_ERR_INVALID, "ticket pointer is NULL");
+    *ticket = -1;
+    UamRasterParams rp;
+    UAM_TRY(uam_raster_prepare(ctx, B, N, h_p, n_p, flags, spc, &rp));
+    if (B > 0 && !h_z && !h_cand) return uam_fail(ctx, UAM_ERR_INVALID, "paths / candidates pointer is NULL");
+    if (h_cand && !(jitter_sigma >= 0.0)) return uam_fail(ctx, UAM_ERR_INVALID, "jitter sigma must be >= 0");
+    if (global_offset < 0 || global_offset + B > 0x7fffffffll)
+        return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "global path index must fit 31 bits");
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UAM_NVTX("uam.raster.submit (upload -> score -> download)");
+    int s;
+    UAM_TRY(uam_ring_acquire(ctx, &s));
+    cudaStream_t st = ctx->pipe_stream[s];
+    *ticket = s;
+    ctx->ring_busy[s] = true;
+    UamBestTail tl;
+    // the exchange with the peer ranks is for caller-stream calls (uam_score_paths_raster_best): here the key is this rank's
+    if (h_key) UAM_TRY(uam_best_tail(ctx, 1 + s, (unsigned long long)global_offset, ctx->d_ring_key[s], false, false, &tl));
+    if (B == 0) {
+        if (h_key) *h_key = UAM_KEY_EMPTY;
+        return UAM_OK;
+    }
+    const size_t row = (size_t)2 * (N + 2) * sizeof(double);
+    UAM_TRY(uam_reserve(ctx, &ctx->d_stage_in[s], &ctx->stage_in_bytes[s], (size_t)B * row));
+    UAM_TRY(uam_reserve(ctx, &ctx->d_stage_out[s], &ctx->stage_out_bytes[s], (size_t)B * 8));
+    float* d_cost = (float*)ctx->d_stage_out[s];
+    uint8_t* d_col = (uint8_t*)(d_cost + B);
+    // the quad texels are shared by all slots: (re)built here, before anything of this submission is queued
+    {
+        const uint64_t gen0 = ctx->comb_gen;
+        UAM_TRY(uam_raster_precompute(ctx, &rp, B, N, st));
+        (void)gen0;
+    }
+    if (h_cand) {
+        UAM_TRY(uam_reserve(ctx, &ctx->d_ring_cand[s], &ctx->ring_cand_bytes[s], (size_t)B * 5 * sizeof(double)));
+        UAM_CUDA(ctx, cudaMemcpyAsync(ctx->d_ring_cand[s], h_cand, (size_t)B * 5 * sizeof(double), cudaMemcpyHostToDevice, st));
+        UAM_TRY(uam_make_candidates_launch(ctx, (const double*)ctx->d_ring_cand[s], nullptr, nullptr, N, B, jitter_sigma, seed,
+                                           (uint64_t)global_offset, (double*)ctx->d_stage_in[s], st));
+    } else {
+        UAM_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in[s], h_z, (size_t)B * row, cudaMemcpyHostToDevice, st));
+    }
+    UAM_TRY(uam_raster_launch(ctx, (const double*)ctx->d_stage_in[s], B, N, rp, d_cost, d_col, nullptr, st, 1 + s, h_key ? &tl : nullptr));
+    if (h_cost) UAM_CUDA(ctx, cudaMemcpyAsync(h_cost, d_cost, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (h_collide) UAM_CUDA(ctx, cudaMemcpyAsync(h_collide, d_col, (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (h_key) UAM_CUDA(ctx, cudaMemcpyAsync(h_key, ctx->d_ring_key[s], 8, cudaMemcpyDeviceToHost, st));
+    return UAM_OK;
+}
+
+extern "C" int uam_raster_submit_paths_host(uam_ctx* ctx, const double* h_z, int64_t B, int N, const double* h_p, int n_p,
+                                            int flags, double samples_per_cell, float* h_cost, uint8_t* h_collide,
+                                            uint64_t* h_key, int64_t global_offset, int* ticket) {
+    return uam_raster_submit_impl(ctx, h_z, nullptr, 0.0, 0, B, N, h_p, n_p, flags, samples_per_cell, h_cost, h_collide, h_key,
+                                  global_offset, ticket);
+}
+
+extern "C" int uam_raster_submit_candidates_host(uam_ctx* ctx, const double* h_cand, int64_t B, int N, double jitter_sigma,
+                                                 uint64_t seed, const double* h_p, int n_p, int flags, double samples_per_cell,
+                                                 float* h_cost, uint8_t* h_collide, uint64_t* h_key, int64_t global_offset,
+                                                 int* ticket) {
+    return uam_raster_submit_impl(ctx, nullptr, h_cand, jitter_sigma, seed, B, N, h_p, n_p, flags, samples_per_cell, h_cost,
+                                  h_collide, h_key, global_offset, ticket);
+}
+
+extern "C" int uam_raster_wait(uam_ctx* ctx, int ticket) {
+    if (!ctx) return UAM_ERR_INVALID;
+    if (ticket < 0 || ticket >= UAM_HOST_PIPE_DEPTH) return uam_fail(ctx, UAM_ERR_INVALID, "bad ticket %d", ticket);
+    if (!ctx->ring_busy[ticket]) return UAM_OK;             // already waited for (or reclaimed by a later submission)
+    UAM_NVTX("uam.raster.wait");
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UAM_CUDA(ctx, cudaStreamSynchronize(ctx->pipe_stream[ticket]));
+    ctx->ring_busy[ticket] = false;
+    return UAM_OK;
 }
 
 // Host buffers in, host buffers out: the batch is cut into chunks that flow through UAM_HOST_PIPE_DEPTH

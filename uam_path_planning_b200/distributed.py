@@ -84,3 +84,19 @@ def gather_costs(local_cost, group=None):
     parts = [torch.empty_like(local_cost) for _ in range(dist.get_world_size(group))]
     dist.all_gather(parts, local_cost, group=group)
     return torch.cat(parts)
+
+
+def attach_peer_group(engine, group=None) -> int:
+    """Give `engine` the symmetric blocks of every rank of the box: all-gather the 64-byte CUDA IPC handles
+    (Engine.peer_handle) over torch.distributed (any backend; the handles are plain bytes) and map them
+    (Engine.attach_peers).  After this, RasterMap.score_paths_best / Engine.best_allreduce return the min over all ranks
+    without any NCCL call on the data path.  Returns the world size (1 = nothing to attach)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 1
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    handles = [None] * world
+    dist.all_gather_object(handles, engine.peer_handle(), group=group)
+    engine.attach_peers(rank, handles)
+    dist.barrier(group=group)           # every rank has mapped every block before the first exchange
+    return world

@@ -215,6 +215,60 @@ class Engine:
                                                           float(samples_per_cell), _np_ptr(cost), _np_ptr(col)))
         return cost, col
 
+    def score_raster_best(self, Z, N: int, p, flags: int, samples_per_cell: float, global_offset: int = 0, out=None, key=None):
+        """score_raster on a CUDA tensor + the best key of the batch -- of every rank's batch when a peer group is attached
+        (attach_peers): the exchange over NVLink peer memory rides in the last kernel of the step.
+        -> (cost, collide, key (1,) int64 CUDA tensor)."""
+        import torch
+        p = _f64c(p)
+        N = int(N)
+        assert _is_tensor(Z) and Z.dtype == torch.float64 and Z.dim() == 2 and Z.shape[1] == 2 * (N + 2)
+        B = Z.shape[0]
+        cost, col = out if out is not None else (torch.empty(B, dtype=torch.float32, device=Z.device),
+                                                 torch.empty(B, dtype=torch.uint8, device=Z.device))
+        if key is None:
+            key = torch.empty(1, dtype=torch.int64, device=Z.device)
+        st = self._tensor_args(Z, cost, col, key)
+        self._check(self._lib.uam_score_paths_raster_best(
+            self._h, C.c_void_p(Z.data_ptr()), B, N, _np_ptr(p), p.size, flags, float(samples_per_cell),
+            C.c_void_p(cost.data_ptr()), C.c_void_p(col.data_ptr()), int(global_offset), C.c_void_p(key.data_ptr()), st))
+        return cost, col, key
+
+    def submit_raster(self, N: int, p, flags: int, samples_per_cell: float, cost, collide, Z=None, candidates=None,
+                      jitter_sigma: float = 0.0, seed: int = 0, key=None, global_offset: int = 0) -> int:
+        """Asynchronous host-buffer scoring (uam_raster_submit_*): queue one batch and return a ticket for wait_raster.
+        Z (B, 2(N+2)) float64 numpy = the caller's waypoints, or candidates (B, 5) float64 numpy {xs, ys, xg, yg,
+        displacement} generated on the device.  cost (B,) float32 / collide (B,) uint8 / key (1,) uint64 are numpy arrays
+        filled by the time wait_raster(ticket) returns; every buffer must stay alive until then (pin them:
+        torch.empty(...).pin_memory().numpy())."""
+        p = _f64c(p)
+        t = C.c_int(-1)
+        for a, dt in ((cost, np.float32), (collide, np.uint8)):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous):
+                raise ValueError('output buffers must be contiguous numpy arrays of float32 / uint8')
+        if key is not None and not (isinstance(key, np.ndarray) and key.dtype == np.uint64 and key.size >= 1):
+            raise ValueError('key must be a numpy uint64 array')
+        if (Z is None) == (candidates is None):
+            raise ValueError('give either Z or candidates')
+        if Z is not None:
+            if not (isinstance(Z, np.ndarray) and Z.dtype == np.float64 and Z.flags.c_contiguous and Z.ndim == 2 and
+                    Z.shape[1] == 2 * (int(N) + 2)):
+                raise ValueError(f'paths must be a C-contiguous float64 array (B, {2 * (int(N) + 2)})')
+            self._check(self._lib.uam_raster_submit_paths_host(
+                self._h, _np_ptr(Z), Z.shape[0], int(N), _np_ptr(p), p.size, flags, float(samples_per_cell), _np_ptr(cost),
+                _np_ptr(collide), _np_ptr(key), int(global_offset), C.byref(t)))
+        else:
+            cd = candidates
+            if not (isinstance(cd, np.ndarray) and cd.dtype == np.float64 and cd.flags.c_contiguous and cd.ndim == 2 and cd.shape[1] == 5):
+                raise ValueError('candidates must be a C-contiguous float64 array (B, 5): xs, ys, xg, yg, displacement')
+            self._check(self._lib.uam_raster_submit_candidates_host(
+                self._h, _np_ptr(cd), cd.shape[0], int(N), float(jitter_sigma), int(seed), _np_ptr(p), p.size, flags,
+                float(samples_per_cell), _np_ptr(cost), _np_ptr(collide), _np_ptr(key), int(global_offset), C.byref(t)))
+        return int(t.value)
+
+    def wait_raster(self, ticket: int):
+        self._check(self._lib.uam_raster_wait(self._h, int(ticket)))
+
     def eval_points(self, X, p, flags: int, want=('region', 'obstacle', 'collide')):
         """X (M,2) float64 -> dict(region=(M,R) weighted penalties, obstacle=(M,), collide=(M,) u8)."""
         p = _f64c(p)
@@ -280,6 +334,49 @@ class Engine:
         self._check(self._lib.uam_make_arc_paths(self._h, _np_ptr(ends), int(N), C.c_void_p(displacements.data_ptr()),
                                                  displacements.numel(), C.c_void_p(Z.data_ptr()), st))
         return Z
+
+    def make_candidates(self, candidates, N: int, jitter_sigma: float = 0.0, seed: int = 0, index0: int = 0):
+        """candidates (B, 5) float64 CUDA tensor {xs, ys, xg, yg, displacement} -> (B, 2(N+2)) paths: per-candidate start /
+        goal, arc of Solver.create_x_init, N(0, sigma^2) jitter on the interior waypoints from the counter-based generator
+        keyed by (seed, index0 + b, waypoint)."""
+        import torch
+        assert _is_tensor(candidates) and candidates.dtype == torch.float64 and candidates.dim() == 2 and candidates.shape[1] == 5
+        st = self._tensor_args(candidates)
+        if bool((candidates[:, 4].abs() > 1).any()):
+            raise ValueError(f'abs(displacement) = {float(candidates[:, 4].abs().max())} must be smaller than 1')
+        Z = torch.empty((candidates.shape[0], 2 * (int(N) + 2)), dtype=torch.float64, device=candidates.device)
+        self._check(self._lib.uam_make_candidates(self._h, C.c_void_p(candidates.data_ptr()), candidates.shape[0], int(N),
+                                                  float(jitter_sigma), int(seed), int(index0), C.c_void_p(Z.data_ptr()), st))
+        return Z
+
+    def best_allreduce(self, cost, global_offset: int = 0, key=None):
+        """Engine.best with the cross-rank min built in (uam_best_allreduce): one kernel, exchange over NVLink peer memory
+        when a peer group is attached, this rank's key otherwise."""
+        import torch
+        assert _is_tensor(cost) and cost.dtype in (torch.float32, torch.float64)
+        if key is None:
+            key = torch.empty(1, dtype=torch.int64, device=cost.device)
+        st = self._tensor_args(cost, key)
+        self._check(self._lib.uam_best_allreduce(self._h, C.c_void_p(cost.data_ptr()), int(cost.dtype == torch.float64),
+                                                 cost.numel(), int(global_offset), C.c_void_p(key.data_ptr()), st))
+        return key
+
+    def peer_handle(self) -> bytes:
+        """64-byte CUDA IPC handle of this engine's symmetric block (to be all-gathered over the ranks)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.uam_peer_export(self._h, buf))
+        return buf.raw
+
+    def attach_peers(self, rank: int, handles: Sequence[bytes]):
+        """Map the symmetric blocks of all ranks (handles in rank order, this rank's own included)."""
+        blob = b''.join(handles)
+        assert len(blob) == 64 * len(handles)
+        self._check(self._lib.uam_peer_attach(self._h, int(rank), len(handles), C.c_char_p(blob)))
+
+    def peer_timed_out(self) -> bool:
+        v = C.c_int(0)
+        self._check(self._lib.uam_peer_status(self._h, C.byref(v)))
+        return bool(v.value)
 
     def best(self, cost, global_offset: int = 0, key=None):
         """min over b of key(cost[b], global_offset + b) as a 1-element int64 CUDA tensor; the key (distributed.py) orders

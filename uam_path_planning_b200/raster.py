@@ -87,3 +87,40 @@ class RasterMap:
         flags = (_lib.UAM_LENGTH_SMOOTH if length_smooth else 0) | (_lib.UAM_OWN_START if x_start is None else 0)
         p = self.parameter_vector(weights, x_start)
         return self.engine.score_raster(Z, N, p, flags, samples_per_cell, want_nsamples, out)
+
+    def score_paths_best(self, Z, weights: Sequence[float], samples_per_cell: float = 0.0, length_smooth: bool = True,
+                         x_start=None, global_offset: int = 0, out=None, key=None):
+        """score_paths on a CUDA tensor + the best candidate's key (distributed.decode_key) in the same call; with a peer
+        group attached (distributed.attach_peer_group) the key is the min over every rank's batch -- the only cross-rank
+        step of the path, fused into the step's last kernel."""
+        N = Z.shape[1] // 2 - 2
+        flags = (_lib.UAM_LENGTH_SMOOTH if length_smooth else 0) | (_lib.UAM_OWN_START if x_start is None else 0)
+        return self.engine.score_raster_best(Z, N, self.parameter_vector(weights, x_start), flags, samples_per_cell,
+                                             global_offset, out, key)
+
+    def submit(self, weights: Sequence[float], samples_per_cell: float, cost, collide, Z=None, candidates=None, N: int = None,
+               jitter_sigma: float = 0.0, seed: int = 0, key=None, global_offset: int = 0, length_smooth: bool = True,
+               x_start=None) -> int:
+        """Queue one host-buffer batch (numpy waypoints Z, or (B, 5) candidates {xs, ys, xg, yg, displacement} that the
+        device turns into paths of N interior waypoints) and return a ticket; `wait(ticket)` returns when cost / collide /
+        key are filled.  Up to three batches in flight: uploads overlap the kernels of the batch before."""
+        if Z is not None:
+            N = Z.shape[1] // 2 - 2
+        flags = (_lib.UAM_LENGTH_SMOOTH if length_smooth else 0) | (_lib.UAM_OWN_START if x_start is None else 0)
+        return self.engine.submit_raster(N, self.parameter_vector(weights, x_start), flags, samples_per_cell, cost, collide,
+                                         Z, candidates, jitter_sigma, seed, key, global_offset)
+
+    def wait(self, ticket: int):
+        self.engine.wait_raster(ticket)
+
+    def score_candidates(self, candidates, N: int, weights: Sequence[float], samples_per_cell: float = 0.0,
+                         jitter_sigma: float = 0.0, seed: int = 0, global_offset: int = 0, length_smooth: bool = True,
+                         x_start=None):
+        """The reference's flow for a whole batch (displacement -> Solver.create_x_init -> score, main.py:160-171) with 40
+        bytes of input per candidate: candidates (B, 5) numpy {xs, ys, xg, yg, displacement} -> (cost, collide, key)."""
+        cd = np.ascontiguousarray(candidates, dtype=np.float64)
+        B = cd.shape[0]
+        cost, col, key = np.empty(B, dtype=np.float32), np.empty(B, dtype=np.uint8), np.empty(1, dtype=np.uint64)
+        self.wait(self.submit(weights, samples_per_cell, cost, col, candidates=cd, N=N, jitter_sigma=jitter_sigma, seed=seed,
+                              key=key, global_offset=global_offset, length_smooth=length_smooth, x_start=x_start))
+        return cost, col, int(key[0])
