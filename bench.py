@@ -605,7 +605,8 @@ def other_configs(args, torch, uam, dev, rank, world, reduce_max, free):
     import types
     import bench_configs as bc
     a = types.SimpleNamespace(c4_size=args.c4_size, reps=3, no_cpu=args.no_cpu, c5_size=4096, c5_queries=args.c5_queries,
-                              c5_queries_bands=args.c5_queries_bands, c5_reps=1)
+                              c5_queries_bands=args.c5_queries_bands, c5_reps=1,
+                              c5_cpu_bands=False)      # one 8-band CPU Dijkstra takes 18 s: bench_configs.py times it
     out = {}
     torch.cuda.empty_cache()
     if world == 1:

@@ -77,7 +77,7 @@ def run_c5(args, torch, uam, dev, rank=0, world=1, reduce_max=None):
         reach = float((dist < 2 ** 62).float().mean().item())
         d_goal_full = dist[(torch.arange(Ql, device=dev),) + idx(goal)].clone()
         cpu = None
-        if not args.no_cpu and rank == 0:
+        if not args.no_cpu and rank == 0 and (bands == 1 or getattr(args, 'c5_cpu_bands', True)):
             # CPU baseline: heap Dijkstra of oracle/uam_oracle_c.c, one query per thread, and a full-size
             # parity check of those queries
             from oracle import uam_oracle_c as occ

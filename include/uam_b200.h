@@ -104,6 +104,10 @@ enum {
     UAM_OPT_HOST_TAPER = 8,           /* ... chunk sizes change linearly from the first to the last chunk: t > 0 the last chunk
                                          is t percent smaller than the first, t < 0 the first is |t| percent smaller than the
                                          last, 0 (default) equal chunks; -95 .. 95 */
+    UAM_OPT_RASTERIZER = 10,          /* 1 (default): uam_rasterize_occupancy / uam_rasterize_layers find, per raster row and shape, the
+                                         interval of cells inside the shape by bisection with the exact fp64 predicate (the value of
+                                         an inequality along a row is monotone in the column) and only touch those cells; 0: every
+                                         cell of every surviving tile is evaluated (round-1 kernels).  Same bits either way */
     UAM_OPT_SHAPE_GRID = 9            /* 1 (default): the analytic scorer / point queries look up per-cell candidate lists over
                                          the shapes (a shape with one inequality > max(e, 1e-14) on a whole cell contributes
                                          exact zeros there and is left out; same bits).  0: every shape at every point */

@@ -287,6 +287,53 @@ def test_rasterize_layers_enlargement_and_many_shapes(uam, torch):
         np.testing.assert_allclose(lay, ref, rtol=2e-7)
 
 
+@pytest.mark.parametrize('H,W,geo', [(4099, 4113, (0.0, 32.0 / 4113, 0.0, 32.0 / 4099)), (1500, 777, (32.0, -32.0 / 777, 32.0, -32.0 / 1500)),
+                                     (300, 5000, (-3.0, 0.0077, 40.0, -0.11))])
+def test_scanline_rasterisers_equal_per_cell_evaluation(uam, torch, H, W, geo):
+    """The scanline rasterisers (row intervals by bisection with the exact predicate; UAM_OPT_RASTERIZER = 1, default)
+    against the per-cell kernels (= 0) on rotated rectangles, triangles, ellipses (incl. very flat ones), boxes, shapes
+    far larger than a supertile, slivers thinner than a cell and shapes overlapping each other: identical bytes for the
+    occupancy grid, identical bits for the layers -- odd raster sizes, negative cell sizes, map partly outside the raster."""
+    rng = np.random.default_rng(H + W)
+    m = uam.RegionMap()
+    for r in ('A', 'B', 'C'):
+        m.new_region(r, 'r')
+    def rect(c, hw, hh, a):
+        R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        return uam.polygon(*(c + np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]]) @ R.T).tolist())
+    shapes = []
+    for k in range(260):
+        c = rng.uniform(-2, 34, 2)
+        t = k % 6
+        if t == 0:
+            sh = rect(c, *rng.uniform(0.05, 2.5, 2), rng.uniform(0, np.pi))
+        elif t == 1:
+            sh = uam.ball(c.tolist(), float(rng.uniform(0.05, 3.0)), float(rng.uniform(0.02, 3.0)))
+        elif t == 2:
+            sh = uam.square(c.tolist(), float(rng.uniform(0.05, 2.0)), float(rng.uniform(0.05, 2.0)))
+        elif t == 3:
+            sh = uam.polygon(*(c + rng.uniform(-1.5, 1.5, (3, 2))).tolist())
+        elif t == 4:
+            sh = rect(c, rng.uniform(2.0, 9.0), rng.uniform(0.001, 0.01), rng.uniform(0, np.pi))        # sliver
+        else:
+            sh = rect(c, *rng.uniform(4.0, 12.0, 2), rng.uniform(0, np.pi))                               # larger than a supertile
+        shapes.append(sh)
+        m.add_obstacle(sh)
+        m.add_shape_to_region('ABC'[k % 3], sh)
+    m.add_obstacle(rect(np.array([16.0, 16.0]), 8.0, 8.0, 0.0))          # axis-aligned edges (constant along a row / a column)
+    eng = m.engine()
+    res = {}
+    for mode in (0, 1):
+        eng.set_option('rasterizer', mode)
+        res[mode] = (eng.rasterize_occupancy(H, W, geo), eng.rasterize_layers(H, W, geo, 0.0), eng.rasterize_layers(H, W, geo, 0.04),
+                     eng.rasterize_layers(H, W, geo, -0.03))
+    assert 0.2 < float(res[0][0].float().mean()) < 0.95
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    assert float((res[0][1] != 0).float().mean()) > 0.05
+
+
 def test_dem_mask(uam, torch):
     rng = np.random.default_rng(3)
     eng = uam.Engine()

@@ -321,17 +321,27 @@ def test_seed_from_grid_path_and_rect_area():
 
 
 def test_map_signature_follows_content(fixture_spec):
-    """the cached device shape table must be re-uploaded after in-place edits (centre, inequality record) and
-    must not be confused by rebuilt lists -- the signature is a hash of the uploaded content, not of object ids."""
+    """the cached device shape table must be re-uploaded after a shape changes and must not be confused by rebuilt
+    lists whose objects reuse ids.  Centres and inequality records are stored read-only (an in-place edit raises), so every
+    change is an assignment, and every assignment takes a fresh serial number that the signature carries."""
     from conftest import build_product_map
     m = build_product_map(fixture_spec)
     s0 = m._signature()
-    assert s0 == build_product_map(fixture_spec)._signature()          # same content, other objects
+    assert s0 == m._signature()
+    assert s0 != build_product_map(fixture_spec)._signature()          # other objects: re-upload (cheap, and always safe)
+    with pytest.raises(ValueError):
+        m.obstacles[0].center[0] = 1.0                                  # read-only
+    with pytest.raises(ValueError):
+        m.obstacles[1].inequalities[0].record[3] += 0.5                 # read-only
     m.obstacles[0].center = np.array([1.0, 2.0])
     s1 = m._signature()
     assert s1 != s0
-    m.obstacles[1].inequalities[0].record[3] += 0.5
+    rec = m.obstacles[1].inequalities[0].record.copy()
+    rec[3] += 0.5
+    m.obstacles[1].inequalities[0].record = rec
     s2 = m._signature()
     assert s2 not in (s0, s1)
     m.regions['Land']['shapes'].pop()
     assert m._signature() not in (s0, s1, s2)
+    import timeit
+    assert timeit.timeit(m._signature, number=200) / 200 < 2e-3        # cheap enough to check on every call

@@ -157,6 +157,10 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             ctx->psic_valid = false;        // rebuilt (or dropped) with the next analytic call
             ctx->shape_grid = UamShapeGrid{};
             return UAM_OK;
+        case UAM_OPT_RASTERIZER:
+            if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "rasterizer must be 0 (per cell) or 1 (scanline)");
+            ctx->rasterizer_scan = (int)value;
+            return UAM_OK;
         case UAM_OPT_TIME_KERNELS:
             UAM_CUDA(ctx, cudaSetDevice(ctx->device));
             if (value && !ctx->time_ev[0]) {
@@ -300,7 +304,15 @@ extern "C" int uam_map_set_shapes(uam_ctx* ctx, const double* h_edges, int n_edg
             return uam_fail(ctx, UAM_ERR_INVALID, "inequality %d: unknown kind %d", i, k);
     }
     bool finite = true;
-    for (size_t i = 0; i < 8 * (size_t)n_edges; ++i) finite = finite && std::isfinite(h_edges[i]);
+    double max_abs = 0.0;
+    for (size_t i = 0; i < 8 * (size_t)n_edges; ++i) {
+        finite = finite && std::isfinite(h_edges[i]);
+        if (std::isfinite(h_edges[i])) max_abs = std::max(max_abs, std::fabs(h_edges[i]));
+    }
+    int max_per_shape = 0;
+    for (int s = 0; s < n_shapes; ++s) max_per_shape = std::max(max_per_shape, h_shape_off[s + 1] - h_shape_off[s]);
+    ctx->edges_max_abs = max_abs;
+    ctx->max_edges_per_shape = max_per_shape;
     // bounding box of the shapes as far as the records tell (polygon vertices, ellipse / box extents): the extent of
     // the analytic scorer's shape grid.  Points outside it are scored with the full loops, so it only has to be sensible.
     double bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;

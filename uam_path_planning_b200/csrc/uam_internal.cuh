@@ -95,6 +95,7 @@ struct uam_ctx {
     int raster_layout = 1;    // layout used by the next uam_map_set_raster*
     int host_chunks = 0;      // *_host raster scoring: pipeline chunks per call (0 = default)
     int host_taper = 0;       // ... and by how many percent the last chunk is smaller (> 0) / the first chunk is smaller (< 0)
+    int rasterizer_scan = 1;  // UAM_OPT_RASTERIZER: 1 = scanline rasterisers (row intervals), 0 = per-cell evaluation
     int int_variant = -1;     // integral mode: -1 = auto; 0 = warp per path, lane per sample; 1 = lane pair per sample;
                               // 2 = segments binned by raster tile (L2-resident raster); 3 = pieces sorted by tile, tile staged in smem
 
@@ -106,6 +107,8 @@ struct uam_ctx {
     int region_begin[UAM_MAX_REGIONS + 1] = {};  // shape index range of each region
     bool has_shapes = false;
     bool edges_finite = false;          // every inequality record is finite: the psi product may stop at its first zero
+    double edges_max_abs = 0.0;         // largest magnitude in the records (finite ones)
+    int max_edges_per_shape = 0;
     bool psic_valid = false;
     double psic_e = 0.0;
     int psic_flags = -1;
@@ -176,6 +179,7 @@ struct uam_ctx {
     unsigned peer_epoch = 0;
     // asynchronous host-buffer scoring (uam_raster_submit_* / uam_raster_wait): one ticket per pipeline slot
     int ring_next = 0;
+    int ring_last = -1;                                  // slot of the latest submission (its pipe_event marks its kernels' end)
     bool ring_busy[UAM_HOST_PIPE_DEPTH] = {};
     void* d_ring_cand[UAM_HOST_PIPE_DEPTH] = {};
     size_t ring_cand_bytes[UAM_HOST_PIPE_DEPTH] = {};

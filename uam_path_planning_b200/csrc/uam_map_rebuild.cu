@@ -182,6 +182,136 @@ uam_k_rasterize_occupancy(const UamEdge* __restrict__ edges, const UamShape* __r
 }
 
 // -------------------------------------------------------------------------------------------------------
+// row intervals of a convex shape (scanline form of the two rasterisers)
+// -------------------------------------------------------------------------------------------------------
+// Along one raster row the fp64 value of an inequality at the cell centres, evaluated by uam_h_exact in the reference's
+// operation order, is a MONOTONE function of the column (every rounding step is monotone: x_j = x0 + (j + 1/2) dx,
+// x_j - Ax, the product with a constant, the difference with a constant), and for an ellipse it is monotone on either side
+// of the centre column ((x_j - cx) / r1 is monotone and its square is monotone in its magnitude).  So the set of cells of
+// the row where the predicate "h <= thr" (contains, quadratic_obstacle.py:89-94) or "h - e < 0" (psi != 0,
+// quadratic_obstacle.py:33-35) holds is a prefix, a suffix or -- for the ellipse -- the union of a suffix and a prefix
+// around the centre: one interval per inequality, found by bisection WITH THE EXACT PREDICATE.  The cells of a convex
+// shape on a row are the intersection of its inequalities' intervals.  No approximate geometry decides a cell, so the
+// result has the bits of the per-cell evaluation; the gain is ~8 predicate evaluations per (row, inequality) instead of
+// one per cell.  Needs finite records (uam_map_set_shapes checks) -- NaN breaks monotonicity; callers fall back to the
+// per-cell kernels otherwise.
+template <int KIND>      // 0: h <= t (contains)   1: h - t < 0 (psi != 0 for enlargement t)
+__device__ __forceinline__ bool uam_row_pred(const UamEdge& r, double x, double y, double t) {
+    const double h = uam_h_exact(r, x, y);
+    return KIND == 0 ? (h <= t) : (__dsub_rn(h, t) < 0.0);
+}
+// cells of [a, b) (columns relative to jbase) where the predicate holds, the predicate being monotone on [a, b)
+template <int KIND>
+__device__ __forceinline__ void uam_monotone_cells(const UamEdge& r, double y, double x0, double dx, int jbase, int a, int b,
+                                                   double t, int& lo, int& hi) {
+    lo = hi = a;
+    if (a >= b) return;
+    const bool pa = uam_row_pred<KIND>(r, uam_cell_centre(jbase + a, x0, dx), y, t);
+    const bool pb = (b - 1 == a) ? pa : uam_row_pred<KIND>(r, uam_cell_centre(jbase + b - 1, x0, dx), y, t);
+    if (pa && pb) { hi = b; return; }
+    if (!pa && !pb) return;
+    int l = a, h = b - 1;                               // pred(l) == pa, pred(h) == pb, pa != pb
+    while (h - l > 1) {
+        const int m = (l + h) >> 1;
+        if (uam_row_pred<KIND>(r, uam_cell_centre(jbase + m, x0, dx), y, t) == pa) l = m; else h = m;
+    }
+    if (pa) { lo = a; hi = l + 1; } else { lo = h; hi = b; }
+}
+// [lo, hi) := [lo, hi) intersected with the cells of [0, n) where inequality r holds
+template <int KIND>
+__device__ __forceinline__ void uam_row_interval_edge(const UamEdge& r, double y, double x0, double dx, int jbase, int n, double t,
+                                                      int& lo, int& hi) {
+    int l, h;
+    if ((int)r.kind == UAM_EDGE_ELLIPSE) {
+        // split where x_j - cx changes sign (monotone in j)
+        int a = 0, b = n;
+        const bool s0 = uam_cell_centre(jbase, x0, dx) >= r.p0;
+        const bool s1 = uam_cell_centre(jbase + n - 1, x0, dx) >= r.p0;
+        int split = n;                                  // first column on the other side of the centre than column 0
+        if (s0 != s1) {
+            int ll = 0, hh = n - 1;
+            while (hh - ll > 1) {
+                const int m = (ll + hh) >> 1;
+                if ((uam_cell_centre(jbase + m, x0, dx) >= r.p0) == s0) ll = m; else hh = m;
+            }
+            split = hh;
+        }
+        int l1, h1, l2, h2;
+        uam_monotone_cells<KIND>(r, y, x0, dx, jbase, a, split, t, l1, h1);
+        uam_monotone_cells<KIND>(r, y, x0, dx, jbase, split, b, t, l2, h2);
+        if (h1 > l1 && h2 > l2) { l = l1; h = h2; }      // a suffix of [0, split) and a prefix of [split, n): contiguous
+        else if (h1 > l1) { l = l1; h = h1; }
+        else { l = l2; h = h2; }
+    } else {
+        uam_monotone_cells<KIND>(r, y, x0, dx, jbase, 0, n, t, l, h);
+    }
+    lo = max(lo, l);
+    hi = min(hi, h);
+}
+
+// One CTA per 256 x 256-cell supertile, thread r = row r of the supertile.  For every candidate obstacle of the supertile
+// (coarse list) the thread finds the row's cell interval and sets the bits in its row of a shared-memory bitmap (32 bytes
+// per row: no atomics, the row is the thread's own); the bitmap is then expanded to bytes with 16-byte stores.  Every cell of
+// the raster is written exactly once.
+__global__ void __launch_bounds__(256)
+uam_k_occupancy_scan(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, int n_obs, int H, int W,
+                     double x0, double dx, double y0, double dy, const int* __restrict__ coarse_list,
+                     const int* __restrict__ coarse_count, uint8_t* __restrict__ occ) {
+    __shared__ unsigned bits[UAM_SUPER][UAM_SUPER / 32 + 1];        // + 1: rows start in different banks
+    const int sup = blockIdx.y * gridDim.x + blockIdx.x;
+    const int j0 = blockIdx.x * UAM_SUPER, i0 = blockIdx.y * UAM_SUPER;
+    const int ncols = min(UAM_SUPER, W - j0);
+    const int row = threadIdx.x;
+    const int i = i0 + row;
+    unsigned w[UAM_SUPER / 32];
+#pragma unroll
+    for (int k = 0; k < UAM_SUPER / 32; ++k) w[k] = 0u;
+    if (i < H) {
+        const double y = uam_cell_centre(i, y0, dy);
+        const int* cand = coarse_list + (size_t)sup * n_obs;
+        const int n_cand = coarse_count[sup];
+        for (int c = 0; c < n_cand; ++c) {
+            const int s = __ldg(cand + c);
+            const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
+            int lo = 0, hi = ncols;
+            for (int e = meta.x; e < meta.y && lo < hi; ++e) {
+                const UamEdge r = uam_load_edge(edges + e);
+                uam_row_interval_edge<0>(r, y, x0, dx, j0, ncols, 1e-14, lo, hi);
+            }
+            if (lo < hi) {
+#pragma unroll
+                for (int k = 0; k < UAM_SUPER / 32; ++k) {
+                    const int a = max(lo - 32 * k, 0), b = min(hi - 32 * k, 32);
+                    if (a < b) w[k] |= (b - a == 32) ? 0xffffffffu : (((1u << (b - a)) - 1u) << a);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < UAM_SUPER / 32; ++k) bits[row][k] = w[k];
+    __syncthreads();
+    // expand: 16 cells (one 16-byte store) per thread per trip; a warp covers two rows of the supertile per trip
+    const bool vec = (W & 15) == 0 && ((((uintptr_t)occ) & 15) == 0);
+    for (int t = threadIdx.x; t < UAM_SUPER * (UAM_SUPER / 16); t += blockDim.x) {
+        const int r = t >> 4, q = t & 15;               // row, 16-cell group
+        const int ii = i0 + r, jj = j0 + q * 16;
+        if (ii >= H || jj >= W) continue;
+        const unsigned m = (bits[r][q >> 1] >> ((q & 1) * 16)) & 0xffffu;
+        uint8_t* dst = occ + (size_t)ii * W + jj;
+        if (vec && jj + 16 <= W) {
+            uint4 v;
+            v.x = ((m >> 0) & 1u) | (((m >> 1) & 1u) << 8) | (((m >> 2) & 1u) << 16) | (((m >> 3) & 1u) << 24);
+            v.y = ((m >> 4) & 1u) | (((m >> 5) & 1u) << 8) | (((m >> 6) & 1u) << 16) | (((m >> 7) & 1u) << 24);
+            v.z = ((m >> 8) & 1u) | (((m >> 9) & 1u) << 8) | (((m >> 10) & 1u) << 16) | (((m >> 11) & 1u) << 24);
+            v.w = ((m >> 12) & 1u) | (((m >> 13) & 1u) << 8) | (((m >> 14) & 1u) << 16) | (((m >> 15) & 1u) << 24);
+            __stcs(reinterpret_cast<uint4*>(dst), v);
+        } else {
+            for (int c = 0; c < 16 && jj + c < W; ++c) dst[c] = (m >> c) & 1u;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
 // penalty layers (smooth psi only)
 // -------------------------------------------------------------------------------------------------------
 struct UamRegionRanges2 {
@@ -238,6 +368,107 @@ uam_k_rasterize_layers(const UamEdge* __restrict__ edges, const UamShape* __rest
                         tot[c] = __dadd_rn(tot[c], psi[c]);
                     }
                 }
+            }
+            __syncthreads();
+        }
+        if (i < H) {
+            float* row = layers + (size_t)r * plane + (size_t)i * W;
+            if (j + 3 < W && (W & 3) == 0 && ((((uintptr_t)layers) & 15) == 0)) {
+                __stcs(reinterpret_cast<float4*>(row + j), make_float4((float)tot[0], (float)tot[1], (float)tot[2], (float)tot[3]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (j + c < W) row[j + c] = (float)tot[c];
+            }
+        }
+    }
+}
+
+// Scanline form of uam_k_rasterize_layers: same tiles, same ordered shape lists, same per-cell arithmetic -- but before a
+// chunk of 16 listed shapes is evaluated, the CTA finds for each (shape, tile row) the interval of cells where psi can be
+// non-zero (all h_i - e < 0: uam_row_interval_edge<1>, exact predicate), and a thread evaluates a shape only if its four
+// cells touch the row's interval.  A skipped cell has a zero factor in psi, i.e. contributes the exact +0 the per-cell
+// kernel adds (the host checks that no product can overflow first), so the bits do not change.  Shapes whose psi(centre)
+// is 0 or NaN (0/0 reaches every cell in the reference) are never skipped.
+__global__ void __launch_bounds__(256)
+uam_k_layers_scan(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, const double* __restrict__ psic,
+                  UamRegionRanges2 rr, int n_regions, int H, int W, double x0, double dx, double y0, double dy, double e,
+                  const int* __restrict__ coarse_list, const int* __restrict__ coarse_count, int n_super,
+                  float* __restrict__ layers) {
+    __shared__ int list[UAM_LIST_CAP];
+    __shared__ int warp_cnt[8];
+    __shared__ unsigned short iv[16][16];               // [shape of the chunk][tile row] = lo | hi << 8 (tile columns)
+    const int tj0 = blockIdx.x * UAM_TILE_W, ti0 = blockIdx.y * UAM_TILE_H;
+    const int tj1 = min(tj0 + UAM_TILE_W, W), ti1 = min(ti0 + UAM_TILE_H, H);
+    const int ncols = tj1 - tj0;
+    const double xe0 = x0 + tj0 * dx, xe1 = x0 + tj1 * dx, ye0 = y0 + ti0 * dy, ye1 = y0 + ti1 * dy;
+    const double xa = fmin(xe0, xe1), xb = fmax(xe0, xe1), ya = fmin(ye0, ye1), yb = fmax(ye0, ye1);
+    const int trow = threadIdx.x >> 4, tq = threadIdx.x & 15;
+    const int i = ti0 + trow;
+    const int c0 = tq << 2;
+    const int j = tj0 + c0;
+    const double y = uam_cell_centre(i, y0, dy);
+    double x[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] = uam_cell_centre(j + c, x0, dx);
+    const size_t plane = (size_t)H * W;
+    const int sup = uam_supertile_of_block();
+    for (int r = 0; r < n_regions; ++r) {
+        double tot[4] = {0.0, 0.0, 0.0, 0.0};
+        const int* cand = coarse_list + (size_t)n_super * (rr.begin[r] - rr.begin[0]) + (size_t)sup * (rr.begin[r + 1] - rr.begin[r]);
+        const int s_end = coarse_count[r * n_super + sup];
+        int s_next = 0;
+        while (s_next < s_end) {
+            int n;
+            s_next = uam_cull_shapes(edges, shapes, cand, s_next, s_end, xa, xb, ya, yb, e, list, &n, warp_cnt);
+            for (int t0 = 0; t0 < n; t0 += 16) {
+                {   // interval of (shape t0 + tq, tile row trow)
+                    const int t = t0 + tq;
+                    int lo = 0, hi = 0;
+                    if (t < n && i < H) {
+                        const int s = list[t];
+                        const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
+                        hi = ncols;
+                        for (int ed = meta.x; ed < meta.y && lo < hi; ++ed) {
+                            const UamEdge rcd = uam_load_edge(edges + ed);
+                            uam_row_interval_edge<1>(rcd, y, x0, dx, tj0, ncols, e, lo, hi);
+                        }
+                        if (meta.w) {
+                            const double pc = __ldg(psic + s);
+                            if (pc == 0.0 || pc != pc) { lo = 0; hi = ncols; }
+                        }
+                        if (lo >= hi) lo = hi = 0;
+                    }
+                    iv[tq][trow] = (unsigned short)(lo | (hi << 8));
+                }
+                __syncthreads();
+                const int nt = min(16, n - t0);
+                for (int k = 0; k < nt; ++k) {
+                    const unsigned v = iv[k][trow];
+                    const int lo = (int)(v & 255u), hi = (int)(v >> 8);
+                    if (!(c0 < hi && c0 + 4 > lo)) continue;
+                    const int s = list[t0 + k];
+                    const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
+                    double psi[4] = {1.0, 1.0, 1.0, 1.0};
+                    for (int ed = meta.x; ed < meta.y; ++ed) {
+                        const UamEdge rcd = uam_load_edge(edges + ed);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const double m = fmin(__dsub_rn(uam_h_exact(rcd, x[c], y), e), 0.0);
+                            psi[c] = __dmul_rn(psi[c], __dmul_rn(m, m));
+                        }
+                    }
+                    const double pc = meta.w ? __ldg(psic + s) : 1.0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (meta.w) {
+                            if (psi[c] != 0.0 || pc == 0.0 || pc != pc) tot[c] = __dadd_rn(tot[c], __ddiv_rn(psi[c], pc));
+                        } else {
+                            tot[c] = __dadd_rn(tot[c], psi[c]);
+                        }
+                    }
+                }
+                __syncthreads();
             }
             __syncthreads();
         }
@@ -487,6 +718,7 @@ static int uam_check_grid(uam_ctx* ctx, int H, int W, double dx, double dy, cons
 extern "C" int uam_rasterize_occupancy(uam_ctx* ctx, int H, int W, double x0, double dx, double y0, double dy,
                                        uint8_t* d_occ, void* stream) {
     UAM_TRY(uam_check_grid(ctx, H, W, dx, dy, d_occ));
+    UAM_NVTX("uam.map.rasterize_occupancy");
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     dim3 grid((W + UAM_TILE_W - 1) / UAM_TILE_W, (H + UAM_TILE_H - 1) / UAM_TILE_H);
     if (grid.y > 65535) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "H too large");
@@ -498,6 +730,13 @@ extern "C" int uam_rasterize_occupancy(uam_ctx* ctx, int H, int W, double x0, do
     int* ccount = clist + n_super * (size_t)std::max(ctx->n_obs, 1);
     uam_k_cull_coarse<<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, 0, ctx->n_obs, 1e-14, H, W, x0, dx, y0, dy, clist, ccount);
     UAM_CHECK_LAUNCH(ctx, "uam_k_cull_coarse");
+    // scanline form (row intervals by bisection with the exact predicate) unless the records hold non-finite numbers or the
+    // per-cell form is asked for (UAM_OPT_RASTERIZER = 0: the round-1 kernel, kept as the cross-check of the tests)
+    if (ctx->edges_finite && ctx->rasterizer_scan && std::isfinite(x0) && std::isfinite(dx) && std::isfinite(y0) && std::isfinite(dy)) {
+        uam_k_occupancy_scan<<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->n_obs, H, W, x0, dx, y0, dy, clist, ccount, d_occ);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_occupancy_scan");
+        return UAM_OK;
+    }
     uam_k_rasterize_occupancy<<<grid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->n_obs, H, W, x0, dx, y0, dy, clist, ccount, d_occ);
     UAM_CHECK_LAUNCH(ctx, "uam_k_rasterize_occupancy");
     return UAM_OK;
@@ -506,6 +745,7 @@ extern "C" int uam_rasterize_occupancy(uam_ctx* ctx, int H, int W, double x0, do
 extern "C" int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, double dx, double y0, double dy,
                                     double enlargement, float* d_layers, void* stream) {
     UAM_TRY(uam_check_grid(ctx, H, W, dx, dy, d_layers));
+    UAM_NVTX("uam.map.rasterize_layers");
     if (ctx->n_regions < 1) return uam_fail(ctx, UAM_ERR_STATE, "the map has no regions");
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = uam_pick_stream(ctx, stream);
@@ -529,6 +769,22 @@ extern "C" int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, doubl
                                                   y0, dy, clist + n_super * (size_t)(rr.begin[r] - rr.begin[0]), ccount + (size_t)r * n_super);
         UAM_CHECK_LAUNCH(ctx, "uam_k_cull_coarse");
     }
+    // scanline form unless it could change a bit: non-finite numbers, or magnitudes for which a product of squared factors
+    // could overflow before its zero factor (inf * 0 = NaN in the reference; a skipped cell would give 0)
+    bool scan = ctx->edges_finite && ctx->rasterizer_scan && std::isfinite(x0) && std::isfinite(dx) && std::isfinite(y0) &&
+                std::isfinite(dy) && std::isfinite(enlargement);
+    if (scan) {
+        const double ext = std::max(std::max(std::fabs(x0), std::fabs(x0 + dx * W)), std::max(std::fabs(y0), std::fabs(y0 + dy * H)));
+        // |h| <= 4 (M + ext)^3 for every record kind with all numbers below M; a shape has at most max_edges factors m^2
+        const double hb = 4.0 * std::pow(ctx->edges_max_abs + ext + std::fabs(enlargement) + 1.0, 3.0);
+        scan = 2.0 * ctx->max_edges_per_shape * std::log10(hb) < 300.0;
+    }
+    if (scan) {
+        uam_k_layers_scan<<<grid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
+                                                y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_layers_scan");
+        return UAM_OK;
+    }
     uam_k_rasterize_layers<<<grid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
                                                  y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
     UAM_CHECK_LAUNCH(ctx, "uam_k_rasterize_layers");
@@ -539,8 +795,6 @@ extern "C" int uam_edt(uam_ctx* ctx, const uint8_t* d_occ, int H, int W, double 
                        float* d_clearance, void* stream) {
     if (!ctx) return UAM_ERR_INVALID;
     UAM_NVTX("uam.map.edt");
-    UAM_NVTX("uam.map.rasterize_layers");
-    UAM_NVTX("uam.map.rasterize_occupancy");
     if (H < 1 || W < 1 || !d_occ || (!d_dist2 && !d_clearance)) return uam_fail(ctx, UAM_ERR_INVALID, "bad argument to uam_edt");
     if (H > 23170 || W > 23170) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "raster larger than 23170 per side (d^2 must stay below 2^30)");
     UAM_CUDA(ctx, cudaSetDevice(ctx->device));

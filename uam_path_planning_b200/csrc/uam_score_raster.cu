@@ -1868,7 +1868,13 @@ static int uam_raster_submit_impl(uam_ctx* ctx, const double* h_z, const double*
     } else {
         UAM_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in[s], h_z, (size_t)B * row, cudaMemcpyHostToDevice, st));
     }
+    // kernels of consecutive submissions run one after the other (two binned pipelines side by side would halve each
+    // other's L2): this slot's kernels wait for the previous submission's, while its upload above and the previous
+    // submission's download below overlap them on the copy engines
+    if (ctx->ring_last >= 0 && ctx->ring_last != s) UAM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_event[ctx->ring_last], 0));
     UAM_TRY(uam_raster_launch(ctx, (const double*)ctx->d_stage_in[s], B, N, rp, d_cost, d_col, nullptr, st, 1 + s, h_key ? &tl : nullptr));
+    UAM_CUDA(ctx, cudaEventRecord(ctx->pipe_event[s], st));
+    ctx->ring_last = s;
     if (h_cost) UAM_CUDA(ctx, cudaMemcpyAsync(h_cost, d_cost, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     if (h_collide) UAM_CUDA(ctx, cudaMemcpyAsync(h_collide, d_col, (size_t)B, cudaMemcpyDeviceToHost, st));
     if (h_key) UAM_CUDA(ctx, cudaMemcpyAsync(h_key, ctx->d_ring_key[s], 8, cudaMemcpyDeviceToHost, st));

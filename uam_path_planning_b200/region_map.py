@@ -47,15 +47,11 @@ class Map:
         return []
 
     def _signature(self):
-        """Content of the device shape table (records + centres, tens of KB): in-place edits of a shape's centre or of an
-        inequality record, and rebuilt shape lists whose objects happen to reuse ids, all change it."""
-        import hashlib
-        from .shapes import flatten_shapes
-        edges, off, reg, cen = flatten_shapes(self.obstacles, self._region_lists())
-        h = hashlib.blake2b(digest_size=16)
-        for a in (edges, off, reg, cen):
-            h.update(a.tobytes())
-        return h.digest()
+        """State of everything the device shape table is made from: per shape a serial number that changes with every
+        assignment of its centre or of one of its inequality records (both are stored read-only, so in-place edits are
+        impossible), plus the composition of the lists.  Serial numbers are never reused (unlike id())."""
+        return (tuple(o.state_key() for o in self.obstacles),
+                tuple(tuple(s.state_key() for s in shapes) for shapes in self._region_lists()))
 
     def engine(self, device: Optional[int] = None):
         """The map's Engine with the current shape table uploaded (rebuilt when the shape lists changed)."""

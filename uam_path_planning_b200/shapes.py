@@ -13,6 +13,7 @@ Only the table is built on the host; every evaluation (``contains``, ``penalty_f
 """
 from __future__ import annotations
 
+import itertools
 import math
 from typing import List, Optional, Sequence
 
@@ -21,14 +22,29 @@ import numpy as np
 from ._lib import UAM_EDGE_BOX, UAM_EDGE_ELLIPSE, UAM_EDGE_LINE
 
 
+_SERIAL = itertools.count(1)      # every Inequality / shape state gets a fresh number: cheap, collision-free change detection
+
+
 class Inequality:
-    """One record h(x) <= 0 of a shape (stands in for the reference's ``Function``, function.py:4-120)."""
-    __slots__ = ('record', 'is_quadratic', 'n')
+    """One record h(x) <= 0 of a shape (stands in for the reference's ``Function``, function.py:4-120).  The record array
+    is read-only: an edit means assigning a new record (``ineq.record = ...``), which the maps' device tables notice."""
+    __slots__ = ('_record', '_serial', 'is_quadratic', 'n')
 
     def __init__(self, record):
-        self.record = np.asarray(record, dtype=np.float64).reshape(8)
+        self.record = record
         self.is_quadratic = True
         self.n = 2
+
+    @property
+    def record(self) -> np.ndarray:
+        return self._record
+
+    @record.setter
+    def record(self, value):
+        r = np.array(value, dtype=np.float64).reshape(8)
+        r.flags.writeable = False
+        self._record = r
+        self._serial = next(_SERIAL)
 
     def __call__(self, x):
         from .engine import default_engine
@@ -42,7 +58,8 @@ class QuadraticObstacle:
     def __init__(self, *inequalities: Inequality):
         self.inequalities: List[Inequality] = []
         self.area = float('nan')
-        self.center = float('nan')
+        self._center = float('nan')
+        self._serial = next(_SERIAL)
         self.xlim: Optional[List[float]] = None
         self.ylim: Optional[List[float]] = None
         self.kind = 'generic'
@@ -53,6 +70,24 @@ class QuadraticObstacle:
             assert isinstance(ineq, Inequality), f'Expected Inequality, got {type(ineq)}'
             assert ineq.n == 2, f'Function must be 2-dimensional, got {ineq.n}-dimensional'
             self.inequalities.append(ineq)
+
+    @property
+    def center(self):
+        """``QuadraticObstacle.center`` (assignable like the reference's attribute; array values are stored read-only, so
+        a change is always an assignment and bumps the shape's state number)."""
+        return self._center
+
+    @center.setter
+    def center(self, value):
+        if isinstance(value, np.ndarray):
+            value = value.copy()
+            value.flags.writeable = False
+        self._center = value
+        self._serial = next(_SERIAL)
+
+    def state_key(self):
+        """Changes whenever something the device table depends on changes (centre, inequality list, any record)."""
+        return (self._serial, tuple(h._serial for h in self.inequalities))
 
     def __len__(self):
         """Number of inequalities (quadratic_obstacle.py:211-213)."""
