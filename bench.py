@@ -605,7 +605,7 @@ def other_configs(args, torch, uam, dev, rank, world, reduce_max, free):
     import types
     import bench_configs as bc
     a = types.SimpleNamespace(c4_size=args.c4_size, reps=3, no_cpu=args.no_cpu, c5_size=4096, c5_queries=args.c5_queries,
-                              c5_queries_bands=args.c5_queries_bands, c5_reps=1,
+                              c5_queries_bands=args.c5_queries_bands, c5_reps=1, c5_routes=args.c5_routes,
                               c5_cpu_bands=False)      # one 8-band CPU Dijkstra takes 18 s: bench_configs.py times it
     out = {}
     torch.cuda.empty_cache()
@@ -641,7 +641,8 @@ def main():
     ap.add_argument('--no-configs', action='store_true', help='skip the short C2 / C4 / C5 runs')
     ap.add_argument('--c4-size', type=int, default=16384)
     ap.add_argument('--c5-queries', type=int, default=16, help='C5: queries per GPU, 1 altitude band')
-    ap.add_argument('--c5-queries-bands', type=int, default=4, help='C5: queries per GPU, 8 altitude bands')
+    ap.add_argument('--c5-queries-bands', type=int, default=4, help='C5: full sweeps per GPU, 8 altitude bands')
+    ap.add_argument('--c5-routes', type=int, default=128, help='C5: start/goal queries per GPU (128 x 8 GPUs = the 1024 of BASELINE config 5)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

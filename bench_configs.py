@@ -34,22 +34,26 @@ def ev_time(torch, fn, reps, warm=2):
 
 
 def run_c5(args, torch, uam, dev, rank=0, world=1, reduce_max=None):
-    """C5: batched cost-to-go / start-goal queries on a 4096^2 grid x `bands` altitude bands of uint16 cost.  Queries are
-    independent: with `world` ranks the job's Q * world queries shard contiguously over the ranks (distributed.shard_range),
-    the grid is replicated, there is no exchange at all; times are the max over ranks (`reduce_max`)."""
+    """C5 (BASELINE.json configs[4]): batched grid search on a 4096^2 grid x `bands` altitude bands of uint16 cost.
+    Queries are independent: with `world` ranks the job's queries shard contiguously over the ranks
+    (distributed.shard_range), the grid is replicated, there is no exchange at all; times are the max over ranks.
+      full sweeps        c5_queries (1 band) / c5_queries_bands (8 bands) per GPU: whole distance + predecessor fields
+      start/goal routes  c5_routes per GPU (128 x 8 GPUs = BASELINE's 1024 queries), in chunks of 16 through
+                         Engine.grid_routes (bounded memory); the first chunk's goal distances must equal the full sweep's"""
     from uam_path_planning_b200 import distributed as udist
     eng = uam.Engine(torch.cuda.current_device())
     reduce_max = reduce_max or (lambda x: x)
     n5 = args.c5_size
     out = []
-    for bands, Q in ((1, args.c5_queries), (8, args.c5_queries_bands)):
-        if Q <= 0:
+    for bands, Qf in ((1, args.c5_queries), (8, args.c5_queries_bands)):
+        if Qf <= 0:
             continue
+        Qr = max(Qf, getattr(args, 'c5_routes', Qf))
         g = torch.Generator(device=dev).manual_seed(5 + bands)          # same grid and query list on every rank
         shape = (n5, n5) if bands == 1 else (bands, n5, n5)
         cost = torch.randint(1, 1000, shape, device=dev, generator=g, dtype=torch.int32).to(torch.uint16)
         blk = (torch.rand(shape, device=dev, generator=g) < 0.1).to(torch.uint8)
-        Qall = Q * world
+        Qall = Qr * world
         src = torch.randint(0, n5, (Qall, 2), device=dev, generator=g, dtype=torch.int32)
         goal = torch.randint(0, n5, (Qall, 2), device=dev, generator=g, dtype=torch.int32)
         if bands > 1:
@@ -60,7 +64,7 @@ def run_c5(args, torch, uam, dev, rank=0, world=1, reduce_max=None):
         b0, b1 = udist.shard_range(Qall, rank, world)
         src, goal = src[b0:b1].contiguous(), goal[b0:b1].contiguous()
         Ql = b1 - b0
-        # ---- full cost-to-go sweeps (distance + parent fields) -------------------------------------------------
+        # ---- full cost-to-go sweeps (distance + parent fields) of this rank's first Qf queries ---------------------
         dt = 1e30
         dist = parent = None
         for rep in range(1 + args.c5_reps):                             # first call = warm-up (scratch allocation)
@@ -68,21 +72,21 @@ def run_c5(args, torch, uam, dev, rank=0, world=1, reduce_max=None):
             l0 = eng.launch_count()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            dist, parent = eng.grid_search(cost, src, blk)
+            dist, parent = eng.grid_search(cost, src[:Qf], blk)
             torch.cuda.synchronize()
             if rep:
                 dt = min(dt, time.perf_counter() - t0)
         launches = eng.launch_count() - l0
         full_stats = {k: eng.get_stat('grid_' + k) for k in ('activations', 'sweeps', 'rounds')}
         reach = float((dist < 2 ** 62).float().mean().item())
-        d_goal_full = dist[(torch.arange(Ql, device=dev),) + idx(goal)].clone()
+        d_goal_full = dist[(torch.arange(Qf, device=dev),) + idx(goal[:Qf])].clone()
         cpu = None
         if not args.no_cpu and rank == 0 and (bands == 1 or getattr(args, 'c5_cpu_bands', True)):
             # CPU baseline: heap Dijkstra of oracle/uam_oracle_c.c, one query per thread, and a full-size
             # parity check of those queries
             from oracle import uam_oracle_c as occ
             cores = os.cpu_count() or 1
-            nq = min(Ql, cores if bands == 1 else max(1, cores // 8))
+            nq = min(Qf, cores if bands == 1 else max(1, cores // 8))
             t0 = time.perf_counter()
             d_ref, _ = occ.grid_search(cost.cpu().numpy(), src[:nq].cpu().numpy(), blk.cpu().numpy(), want_parent=False, threads=cores)
             dtc = time.perf_counter() - t0
@@ -90,33 +94,30 @@ def run_c5(args, torch, uam, dev, rank=0, world=1, reduce_max=None):
                    'dist_equal_gpu': bool(np.array_equal(dist[:nq].cpu().numpy(), d_ref))}
             del d_ref
         del dist, parent
-        # ---- start/goal form of the same queries: every query stops when its goal is final ---------------------
+        # ---- start/goal routes of all of this rank's queries, 16 at a time ------------------------------------------
         dtg = 1e30
-        for rep in range(1 + args.c5_reps):
+        for rep in range(1 + (args.c5_reps if bands == 1 else 0) + (1 if Qr <= 16 else 0)):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            dist, parent = eng.grid_search(cost, src, blk, goals=goal)
-            path, plen = eng.grid_paths(parent, src, goal, max_len=8 * n5)
+            gd, path, plen = eng.grid_routes(cost, src, goal, blk, chunk=16, max_len=8 * n5)
             torch.cuda.synchronize()
-            if rep:
+            if rep or bands > 1 and Qr > 16:
                 dtg = min(dtg, time.perf_counter() - t0)
-            if rep < args.c5_reps:
-                del dist, parent, path, plen
-        goals_ok = bool(torch.equal(dist[(torch.arange(Ql, device=dev),) + idx(goal)], d_goal_full))
-        goal_stats = {k: eng.get_stat('grid_' + k) for k in ('activations', 'rounds')}
+        goals_ok = bool(torch.equal(gd[:Qf], d_goal_full))
         mean_nodes, found = float(plen.float().mean().item()), int((plen > 0).sum().item())
-        del dist, parent, path, plen, cost, blk
+        del gd, path, plen, cost, blk
         dt, dtg = reduce_max(dt), reduce_max(dtg)
         nodes = bands * n5 * n5
         edges = nodes * (8 + (2 if bands > 1 else 0))
-        out.append({'config': f'C5: cost-to-go on a {n5}^2 8-connected grid x {bands} altitude band(s), {Q} queries per GPU per launch, '
-                              f'{world} B200 ({Qall} queries)', 'bands': bands, 'queries': Qall, 'n_gpus': world,
-                    'full_sweeps': {'seconds': dt, 'queries_per_s': Qall / dt, 'Mnode_per_s': Qall * nodes / dt / 1e6,
-                                    'min_edge_relaxations_per_s': Qall * edges * reach / dt, 'kernel_launches_per_call': launches,
+        out.append({'config': f'C5: grid search on a {n5}^2 8-connected grid x {bands} altitude band(s), {world} B200: {Qall} start/goal '
+                              f'queries ({Qr} per GPU), {Qf * world} full cost-to-go sweeps ({Qf} per GPU)', 'bands': bands, 'n_gpus': world,
+                    'start_goal_queries': {'queries': Qall, 'seconds': dtg, 'queries_per_s': Qall / dtg,
+                                           'goal_distances_equal_full_sweep': goals_ok, 'mean_path_nodes': mean_nodes,
+                                           'paths_found_rank0': found, 'queries_per_launch': 16},
+                    'full_sweeps': {'queries': Qf * world, 'seconds': dt, 'queries_per_s': Qf * world / dt,
+                                    'Mnode_per_s': Qf * world * nodes / dt / 1e6,
+                                    'min_edge_relaxations_per_s': Qf * world * edges * reach / dt, 'kernel_launches_per_call': launches,
                                     'reachable_fraction': reach, **{k + '_rank0': v for k, v in full_stats.items()}},
-                    'start_goal_queries': {'seconds': dtg, 'queries_per_s': Qall / dtg, 'goal_distances_equal_full_sweep': goals_ok,
-                                           'mean_path_nodes': mean_nodes, 'paths_found_rank0': found,
-                                           **{k + '_rank0': v for k, v in goal_stats.items()}},
                     'cpu_baseline': cpu,
                     'note': 'exact distances + parents (bit-identical to Dijkstra); warp-per-tile Gauss-Seidel sweeps; queries '
                             'sharded over the ranks, grid replicated, no collective'})
@@ -308,6 +309,7 @@ def main():
     ap.add_argument('--c5-queries', type=int, default=16)
     ap.add_argument('--c5-queries-bands', type=int, default=4)
     ap.add_argument('--c5-reps', type=int, default=2)
+    ap.add_argument('--c5-routes', type=int, default=128, help='start/goal queries per GPU (128 x 8 GPUs = BASELINE config 5)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--only', default='', help="'c2' / 'c4' / 'c5': run only that config")
     args = ap.parse_args()

@@ -317,6 +317,16 @@ int uam_component_rects(uam_ctx* ctx, const int32_t* d_labels, int H, int W, int
                         const int32_t* d_ids, int K, double x0, double dx, double y0, double dy, double* d_rect,
                         int32_t* d_info, void* stream);
 
+/* Large-polygon split of DataProcessor._divide_and_approximate_polygon (map_generation/data_processor.py:34-53): mask of
+ * box (box_row, box_col) of the divisions x divisions box grid over component `label`'s bounding box h_bbox = {row min, row
+ * max, col min, col max} (host), on the grid refined `divisions` times: d_mask (nr, nc) uint8 with nr, nc = the bounding
+ * box's extents in cells.  Sub-cell (r, c) has the corners (col min + (box_col nc + c) / divisions, row min + (box_row nr +
+ * r) / divisions) .. + 1 / divisions in cell units.  The box edges are sub-cell boundaries, so the 4-connected regions of the
+ * mask (uam_label_components) are the pieces of polygon.intersection(box) and uam_component_rects on them, with the affine of
+ * the refined grid, gives each piece's minimum-area rectangle. */
+int uam_component_submask(uam_ctx* ctx, const int32_t* d_labels, int H, int W, int label, const int32_t* h_bbox,
+                          int divisions, int box_row, int box_col, uint8_t* d_mask, void* stream);
+
 /* ---- grid search / cost-to-go (build-defined extension; the reference has none: SURVEY.md section 0) ----------
  * Q independent single-source cost-to-go sweeps on an 8-connected H x W grid, optionally stacked in `bands` altitude
  * bands, with integer edge costs: in-plane step(u,v) * (cost[b,u] + cost[b,v]), step = 2 (axis) / 3 (diagonal); band

@@ -812,6 +812,33 @@ def component_rects(labels, ids, geo):
     return out, info
 
 
+def split_component_rects(labels, label: int, bbox, geo, divisions: int = 5):
+    """DataProcessor._divide_and_approximate_polygon (map_generation/data_processor.py:34-53) restated on the raster: the
+    component's bounding box is cut into divisions x divisions boxes; on the grid refined `divisions` times a box is a block
+    of sub-cells, its 4-connected regions are the pieces of polygon.intersection(box), and each piece gets the exact
+    minimum-area rectangle of its sub-cell corners.  Box order as in the reference (x index outer, y index inner, counted
+    from minx / miny).  -> (rects (P,4,2) float64 world coordinates, box index j * divisions + k per piece)."""
+    x0, dx, y0, dy = [float(v) for v in geo]
+    r0, r1, c0, c1 = [int(v) for v in bbox]
+    nr, nc = r1 - r0 + 1, c1 - c0 + 1
+    fine = np.kron((labels[r0:r1 + 1, c0:c1 + 1] == label).astype(np.uint8), np.ones((divisions, divisions), dtype=np.uint8))
+    rows = list(range(divisions)) if dy > 0 else list(range(divisions - 1, -1, -1))
+    cols = list(range(divisions)) if dx > 0 else list(range(divisions - 1, -1, -1))
+    rects, boxes = [], []
+    for j, bc in enumerate(cols):
+        for k, br in enumerate(rows):
+            sub = fine[br * nr:(br + 1) * nr, bc * nc:(bc + 1) * nc]
+            lab, n = label_components(sub, 4)
+            gx0, gy0 = x0 + (c0 + bc * nc / divisions) * dx, y0 + (r0 + br * nr / divisions) * dy
+            for p in range(1, n + 1):
+                ii, jj = np.nonzero(lab == p)
+                pts = np.concatenate([np.stack([jj + a, ii + b], axis=1) for a in (0, 1) for b in (0, 1)])
+                corners, _, _, _ = min_area_rect_exact(pts)
+                rects.append(np.stack([gx0 + corners[:, 0] * (dx / divisions), gy0 + corners[:, 1] * (dy / divisions)], axis=1))
+                boxes.append(j * divisions + k)
+    return (np.stack(rects) if rects else np.zeros((0, 4, 2))), np.asarray(boxes, dtype=np.int32)
+
+
 def grid_path(parent: np.ndarray, start, goal):
     """Node list (flat indices into the grid) from start to goal along the predecessors of ``grid_search``; empty when the
     goal was not reached.  start / goal: (row, col) or (band, row, col)."""

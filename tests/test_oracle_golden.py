@@ -330,3 +330,58 @@ def test_oracle_components_and_min_area_rect():
         d1, d2 = c[1] - c[0], c[3] - c[0]
         assert abs(d1 @ d2) < 1e-9 * (1 + abs(d1).max() * abs(d2).max())
         assert abs(np.linalg.norm(d1) * np.linalg.norm(d2) - float(a)) < 1e-9 * (1 + float(a))
+
+
+def test_oracle_large_polygon_split():
+    """DataProcessor._divide_and_approximate_polygon (map_generation/data_processor.py:34-53) on the raster: a solid
+    rectangle splits into divisions^2 equal boxes (the box edges fall inside cells: 7 x 11 cells / 5); a ring's hole cuts
+    boxes into several pieces; every piece's rectangle has the area cv2.minAreaRect gives for the clipped cells' corners
+    and the pieces' areas add up to at least the component's."""
+    geo = (100.0, 2.0, 50.0, -2.0)
+    lab = np.zeros((20, 30), dtype=np.int32)
+    lab[3:10, 4:15] = 7                                   # 7 rows x 11 columns
+    r, b = orc.split_component_rects(lab, 7, (3, 9, 4, 14), geo, 5)
+    assert len(r) == 25 and sorted(b.tolist()) == list(range(25))
+    bw, bh = 11 * 2.0 / 5, 7 * 2.0 / 5
+    for rect, box in zip(r, b):
+        j, k = divmod(int(box), 5)                        # x index outer; k counts from miny: y decreases with the row here
+        xs, ys = rect[:, 0], rect[:, 1]
+        assert abs(xs.min() - (100.0 + 4 * 2.0 + j * bw)) < 1e-9 and abs(xs.max() - xs.min() - bw) < 1e-9
+        assert abs(ys.min() - (50.0 - 10 * 2.0 + k * bh)) < 1e-9 and abs(ys.max() - ys.min() - bh) < 1e-9
+    # a comb: a bar with teeth two cells wide every three cells -- every box below the bar holds two separate pieces
+    comb = np.zeros((40, 40), dtype=np.int32)
+    comb[5:9, 5:35] = 1
+    for c in range(5, 35, 3):
+        comb[9:35, c:c + 2] = 1
+    r, b = orc.split_component_rects(comb, 1, (5, 34, 5, 34), (0.0, 1.0, 0.0, 1.0), 5)
+    counts = np.bincount(b, minlength=25).reshape(5, 5)          # [x box][y box]
+    assert (counts[:, 0] == 1).all() and (counts[:, 1:] == 2).all() and len(r) == 45
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(9)
+    f = rng.random((60, 70))
+    for _ in range(6):
+        f = (f + np.roll(f, 1, 0) + np.roll(f, -1, 0) + np.roll(f, 1, 1) + np.roll(f, -1, 1)) / 5.0
+    labels, n = orc.label_components(f > np.quantile(f, 0.45), 4)
+    area, bbox = orc.component_stats(labels, n)
+    cid = int(np.argmax(area)) + 1
+    r, b = orc.split_component_rects(labels, cid, bbox[cid - 1], (0.0, 1.0, 0.0, 1.0), 5)
+    assert uam_rect_area(r).sum() >= area[cid - 1] - 1e-9
+    r0, r1, c0, c1 = bbox[cid - 1]
+    nr, nc = r1 - r0 + 1, c1 - c0 + 1
+    fine = np.kron((labels[r0:r1 + 1, c0:c1 + 1] == cid).astype(np.uint8), np.ones((5, 5), dtype=np.uint8))
+    k = 0
+    for j in range(5):
+        for kk in range(5):
+            sub, ns = orc.label_components(fine[kk * nr:(kk + 1) * nr, j * nc:(j + 1) * nc], 4)
+            for p in range(1, ns + 1):
+                ii, jj = np.nonzero(sub == p)
+                pts = np.concatenate([np.stack([jj + a, ii + c], 1) for a in (0, 1) for c in (0, 1)]).astype(np.float32)
+                (_, (w, h), _) = cv2.minAreaRect(pts)
+                assert abs(uam_rect_area(r[k:k + 1])[0] * 25 - w * h) <= 2e-5 * w * h + 1e-3
+                k += 1
+    assert k == len(r)
+
+
+def uam_rect_area(rect):
+    x, y = rect[..., 0], rect[..., 1]
+    return 0.5 * np.abs(np.sum(x * np.roll(y, -1, axis=-1) - np.roll(x, -1, axis=-1) * y, axis=-1))

@@ -73,6 +73,7 @@ SIGNATURES = {
     'uam_label_components': (_i, [_vp, _vp, _i, _i, _i, _vp, C.POINTER(C.c_int32), _vp]),
     'uam_component_stats': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     'uam_component_rects': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _d, _d, _d, _d, _vp, _vp, _vp]),
+    'uam_component_submask': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     'uam_grid_search': (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     'uam_grid_search_goals': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     'uam_grid_extract_paths': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),

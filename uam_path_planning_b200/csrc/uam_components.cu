@@ -621,3 +621,40 @@ extern "C" int uam_component_rects(uam_ctx* ctx, const int32_t* d_labels, int H,
     UAM_CHECK_LAUNCH(ctx, "uam_k_rect_hull");
     return UAM_OK;
 }
+
+// ---- large-polygon split (map_generation/data_processor.py:34-53) -----------------------------------------------------
+// The reference cuts a polygon larger than `large_area` with a divisions x divisions grid of boxes over its bounding box
+// and approximates every piece of polygon.intersection(box) by its own rectangle.  The box edges fall inside cells; on a
+// grid refined `div` times they fall on (sub-)cell boundaries, so box (bj, bk) of a component whose bounding box is nr x nc
+// cells is exactly the nr x nc block of sub-cells starting at sub-row bk * nr, sub-column bj * nc, and sub-cell (r, c) of
+// the block lies in cell (row0 + (bk * nr + r) / div, col0 + (bj * nc + c) / div).  This kernel writes that block's mask;
+// its 4-connected regions are the pieces (two clipped cells are connected iff they share an edge of positive length inside
+// the box), and the hull of a piece's sub-cell corners is the hull of the clipped polygon's exterior ring.
+__global__ void __launch_bounds__(256)
+uam_k_component_submask(const int32_t* __restrict__ labels, int W, int label, int row0, int col0, int sub_row0, int sub_col0,
+                        int nr, int nc, int div, uint8_t* __restrict__ mask) {
+    const long long n = (long long)nr * nc;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        const int r = (int)(t / nc), c = (int)(t - (long long)r * nc);
+        const int i = row0 + (sub_row0 + r) / div, j = col0 + (sub_col0 + c) / div;
+        mask[t] = labels[(size_t)i * W + j] == label ? 1 : 0;
+    }
+}
+
+extern "C" int uam_component_submask(uam_ctx* ctx, const int32_t* d_labels, int H, int W, int label, const int32_t* h_bbox,
+                                     int divisions, int box_row, int box_col, uint8_t* d_mask, void* stream) {
+    if (!ctx) return UAM_ERR_INVALID;
+    if (!d_labels || !h_bbox || !d_mask || divisions < 1 || box_row < 0 || box_row >= divisions || box_col < 0 || box_col >= divisions)
+        return uam_fail(ctx, UAM_ERR_INVALID, "bad argument to uam_component_submask");
+    const int r0 = h_bbox[0], r1 = h_bbox[1], c0 = h_bbox[2], c1 = h_bbox[3];
+    if (r0 < 0 || r1 >= H || c0 < 0 || c1 >= W || r1 < r0 || c1 < c0) return uam_fail(ctx, UAM_ERR_INVALID, "bounding box outside the raster");
+    const int nr = r1 - r0 + 1, nc = c1 - c0 + 1;
+    UAM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const long long n = (long long)nr * nc;
+    const long long ctas = std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    uam_k_component_submask<<<(unsigned)ctas, 256, 0, uam_pick_stream(ctx, stream)>>>(d_labels, W, label, r0, c0, box_row * nr, box_col * nc,
+                                                                                      nr, nc, divisions, d_mask);
+    UAM_CHECK_LAUNCH(ctx, "uam_k_component_submask");
+    return UAM_OK;
+}

@@ -235,6 +235,7 @@ extern "C" int uam_ctx_destroy(uam_ctx* ctx) {
     cudaFree(ctx->d_tex);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_cull_scratch);
+    cudaFree(ctx->d_cull0_scratch);
     for (int i = 0; i <= UAM_HOST_PIPE_DEPTH; ++i) cudaFree(ctx->d_bin_scratch[i]);
     for (int i = 0; i <= UAM_HOST_PIPE_DEPTH; ++i) cudaFree(ctx->d_piece_scratch[i]);
     cudaFree(ctx->d_tiles);

@@ -136,6 +136,8 @@ struct uam_ctx {
     size_t h_stage_out_bytes[UAM_HOST_PIPE_DEPTH] = {};
     void* d_cull_scratch = nullptr;     // rasteriser: coarse (supertile) shape lists
     size_t cull_scratch_bytes = 0;
+    void* d_cull0_scratch = nullptr;    // ... and the lists of the 2048-cell blocks above them
+    size_t cull0_scratch_bytes = 0;
     void* d_scratch = nullptr;          // EDT, grid search
     size_t scratch_bytes = 0;
     // optional CUDA-event timing of the dominant scoring kernel (UAM_OPT_TIME_KERNELS), read by uam_ctx_get_stat

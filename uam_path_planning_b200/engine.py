@@ -473,6 +473,19 @@ class Engine:
                                                   C.c_void_p(info.data_ptr()) if info is not None else None, st))
         return (rect, info) if want_info else rect
 
+    def component_submask(self, labels, label: int, bbox, divisions: int, box_row: int, box_col: int):
+        """Mask of one box of the large-polygon split (data_processor.py:34-53) on the grid refined `divisions` times:
+        (nr, nc) uint8 CUDA tensor, nr / nc = extents of bbox = (row min, row max, col min, col max) in cells."""
+        import torch
+        assert _is_tensor(labels) and labels.dtype == torch.int32 and labels.dim() == 2
+        st = self._tensor_args(labels)
+        bb = np.ascontiguousarray(bbox, dtype=np.int32).reshape(4)
+        nr, nc = int(bb[1] - bb[0] + 1), int(bb[3] - bb[2] + 1)
+        mask = torch.empty((nr, nc), dtype=torch.uint8, device=labels.device)
+        self._check(self._lib.uam_component_submask(self._h, C.c_void_p(labels.data_ptr()), labels.shape[0], labels.shape[1], int(label),
+                                                    _np_ptr(bb), int(divisions), int(box_row), int(box_col), C.c_void_p(mask.data_ptr()), st))
+        return mask
+
     def grid_search(self, cost, sources, blocked=None, want_parent: bool = True, goals=None):
         """Q cost-to-go sweeps on an 8-connected grid (build-defined extension, include/uam_b200.h).
         2-D: cost (H,W) uint16 CUDA tensor, sources (Q,2) int32 (row, col), blocked (H,W) uint8 or None ->
@@ -537,6 +550,34 @@ class Engine:
                                                      C.c_void_p(g3.data_ptr()), Q, max_len, C.c_void_p(path.data_ptr()),
                                                      C.c_void_p(length.data_ptr()), st))
         return path, length
+
+    def grid_routes(self, cost, sources, goals, blocked=None, chunk: int = 16, max_len: Optional[int] = None):
+        """Start/goal queries with bounded memory: the queries run `chunk` at a time through grid_search(goals=...) +
+        grid_paths, the (chunk, bands, H, W) distance / predecessor fields are reused from chunk to chunk, and only what a
+        planner keeps comes back: (goal_dist (Q,) int64 with 2**62 = unreachable, path (Q, max_len) int32 flat node ids
+        source -> goal, length (Q,) int32).  1024 queries on 4096^2 x 8 bands need 26 GB this way instead of 1.6 TB."""
+        import torch
+        k = cost.dim()
+        sources = torch.as_tensor(sources, dtype=torch.int32, device=cost.device).reshape(-1, k).contiguous()
+        goals = torch.as_tensor(goals, dtype=torch.int32, device=cost.device).reshape(-1, k).contiguous()
+        Q = sources.shape[0]
+        Bn, (H, W) = (1 if k == 2 else cost.shape[0]), cost.shape[-2:]
+        max_len = int(max_len) if max_len is not None else 4 * (H + W) + 2 * Bn
+        gd = torch.empty(Q, dtype=torch.int64, device=cost.device)
+        path = torch.empty((Q, max_len), dtype=torch.int32, device=cost.device)
+        length = torch.empty(Q, dtype=torch.int32, device=cost.device)
+        for q0 in range(0, Q, int(chunk)):
+            q1 = min(Q, q0 + int(chunk))
+            dist, parent = self.grid_search(cost, sources[q0:q1], blocked, True, goals[q0:q1])
+            g = goals[q0:q1].long()
+            inside = ((g >= 0) & (g < torch.tensor(cost.shape, device=cost.device))).all(dim=1)
+            gc = g.clamp(min=0)
+            gc = torch.minimum(gc, torch.tensor(cost.shape, device=cost.device) - 1)
+            d = dist[(torch.arange(q1 - q0, device=cost.device),) + tuple(gc[:, c] for c in range(k))]
+            gd[q0:q1] = torch.where(inside, d, torch.full_like(d, 2 ** 62))
+            path[q0:q1], length[q0:q1] = self.grid_paths(parent, sources[q0:q1], goals[q0:q1], max_len)
+            del dist, parent
+        return gd, path, length
 
     # ---- single-shape queries (QuadraticObstacle.contains / penalty_function, Function.__call__) -----------------
     def _scratch(self) -> 'Engine':
