@@ -107,7 +107,8 @@ enum {
     UAM_OPT_RASTERIZER = 10,          /* 1 (default): uam_rasterize_occupancy / uam_rasterize_layers find, per raster row and shape, the
                                          interval of cells inside the shape by bisection with the exact fp64 predicate (the value of
                                          an inequality along a row is monotone in the column) and only touch those cells; 0: every
-                                         cell of every surviving tile is evaluated (round-1 kernels).  Same bits either way */
+                                         cell of every surviving tile is evaluated (round-1 kernels); 2: as 1 with the tile form of the
+                                         layer kernel (row intervals by bisection inside 16 x 64 tiles).  Same bits in every mode */
     UAM_OPT_SHAPE_GRID = 9            /* 1 (default): the analytic scorer / point queries look up per-cell candidate lists over
                                          the shapes (a shape with one inequality > max(e, 1e-14) on a whole cell contributes
                                          exact zeros there and is left out; same bits).  0: every shape at every point */

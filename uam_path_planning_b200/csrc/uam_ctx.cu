@@ -158,7 +158,7 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             ctx->shape_grid = UamShapeGrid{};
             return UAM_OK;
         case UAM_OPT_RASTERIZER:
-            if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "rasterizer must be 0 (per cell) or 1 (scanline)");
+            if (value < 0 || value > 2) return uam_fail(ctx, UAM_ERR_INVALID, "rasterizer must be 0 (per cell), 1 (scanline) or 2 (scanline, tile form of the layers)");
             ctx->rasterizer_scan = (int)value;
             return UAM_OK;
         case UAM_OPT_TIME_KERNELS:
@@ -396,21 +396,32 @@ __global__ void uam_k_shape_norm(const UamEdge* __restrict__ edges, const UamSha
     psic[s] = uam_psi(edges, sh.e0, sh.e1, sh.cx, sh.cy, smooth, e, nullptr);
 }
 
-int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st) {
+int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st, bool want_grid) {
     const int key = prm.flags & (UAM_PENALTY_SMOOTH | UAM_OBSTACLE_SMOOTH);
-    if (ctx->psic_valid && ctx->psic_e == prm.e && ctx->psic_flags == key) return UAM_OK;
-    if (ctx->n_shapes > 0) {
-        // all streams that may still read the old table must be done before it is overwritten
-        UAM_CUDA(ctx, cudaDeviceSynchronize());
-        uam_k_shape_norm<<<(ctx->n_shapes + 127) / 128, 128, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->n_shapes,
-                                                                       prm.flags, prm.e, ctx->d_psic);
-        UAM_CHECK_LAUNCH(ctx, "uam_k_shape_norm");
-        UAM_CUDA(ctx, cudaStreamSynchronize(st));
-        UAM_TRY(uam_build_shape_grid(ctx, prm.e, prm.flags, st));
+    if (!(ctx->psic_valid && ctx->psic_e == prm.e && ctx->psic_flags == key)) {
+        if (ctx->n_shapes > 0) {
+            // all streams that may still read the old table must be done before it is overwritten
+            UAM_CUDA(ctx, cudaDeviceSynchronize());
+            uam_k_shape_norm<<<(ctx->n_shapes + 127) / 128, 128, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->n_shapes,
+                                                                           prm.flags, prm.e, ctx->d_psic);
+            UAM_CHECK_LAUNCH(ctx, "uam_k_shape_norm");
+            UAM_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+        ctx->shape_grid = UamShapeGrid{};
+        ctx->shape_grid_built = false;
+        ctx->psic_valid = true;
+        ctx->psic_e = prm.e;
+        ctx->psic_flags = key;
     }
-    ctx->psic_valid = true;
-    ctx->psic_e = prm.e;
-    ctx->psic_flags = key;
+    // the analytic scorer's cell lists are built on its first call for these parameters, not for the rasterisers (which
+    // cull per raster tile): 8 ms per build on config C4's 4096 shapes
+    if (want_grid && !ctx->shape_grid_built) {
+        if (ctx->n_shapes > 0) {
+            UAM_CUDA(ctx, cudaDeviceSynchronize());
+            UAM_TRY(uam_build_shape_grid(ctx, prm.e, prm.flags, st));
+        }
+        ctx->shape_grid_built = true;
+    }
     return UAM_OK;
 }
 

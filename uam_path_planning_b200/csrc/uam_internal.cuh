@@ -110,6 +110,7 @@ struct uam_ctx {
     double edges_max_abs = 0.0;         // largest magnitude in the records (finite ones)
     int max_edges_per_shape = 0;
     bool psic_valid = false;
+    bool shape_grid_built = false;      // the analytic scorer's cell lists exist for the current (e, flags)
     double psic_e = 0.0;
     int psic_flags = -1;
     // shape grid of the analytic scorer (rebuilt with psic: it depends on the enlargement)
@@ -193,7 +194,7 @@ int uam_cuda_fail(uam_ctx* ctx, cudaError_t e, const char* what);
 int uam_reserve(uam_ctx* ctx, void** ptr, size_t* cur, size_t need);
 int uam_reserve_pinned(uam_ctx* ctx, void** ptr, size_t* cur, size_t need);
 int uam_make_params(uam_ctx* ctx, const double* h_p, int n_p, int flags, UamParams* out);
-int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st);
+int uam_ensure_shape_norm(uam_ctx* ctx, const UamParams& prm, cudaStream_t st, bool want_grid = true);
 int uam_build_shape_grid(uam_ctx* ctx, double e, int flags, cudaStream_t st);
 // the grid to use for a call with these parameters (G == 0 when culling would not be exact for them)
 UamShapeGrid uam_pick_shape_grid(const uam_ctx* ctx, const UamParams& prm);

@@ -497,6 +497,98 @@ uam_k_layers_scan(const UamEdge* __restrict__ edges, const UamShape* __restrict_
     }
 }
 
+// Row form of the layer rasteriser (the default): one CTA per 256 x 256-cell supertile, one warp per raster row of it at a
+// time.  For every candidate shape of the supertile (coarse list, shape order) the warp samples the row at 32 columns
+// (first and last included, spacing <= 9): the value of an inequality is monotone along the row (see above), so the cells
+// where psi can be non-zero lie strictly between the samples next to the first / last sample that satisfies "h - e < 0" --
+// a coarse span per inequality from ONE predicate evaluation per lane, intersected over the shape's inequalities (an ellipse,
+// monotone on either side of its centre, also gets the three columns next to its centre checked).  Only the cells of the
+// span are evaluated, 32 at a time (lane = column mod 32), with the per-cell arithmetic of uam_k_rasterize_layers, and
+// accumulated in shape order in a shared-memory row of doubles; the row is stored once, coalesced.  A cell outside the span
+// has a zero factor in psi: the exact +0 the per-cell kernel adds (host-side overflow guard as for the other scan forms).
+__global__ void __launch_bounds__(256)
+uam_k_layers_rows(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, const double* __restrict__ psic,
+                  UamRegionRanges2 rr, int n_regions, int H, int W, double x0, double dx, double y0, double dy, double e,
+                  const int* __restrict__ coarse_list, const int* __restrict__ coarse_count, int n_super,
+                  float* __restrict__ layers) {
+    __shared__ double acc_all[8][UAM_SUPER];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* acc = acc_all[warp];
+    const int sup = blockIdx.y * gridDim.x + blockIdx.x;
+    const int j0 = blockIdx.x * UAM_SUPER, i0 = blockIdx.y * UAM_SUPER;
+    const int ncols = min(UAM_SUPER, W - j0);
+    const size_t plane = (size_t)H * W;
+    // sample columns: 0 .. ncols - 1 inclusive
+    const int sj = (lane * (ncols - 1)) / 31;
+    const int sj_prev = lane > 0 ? ((lane - 1) * (ncols - 1)) / 31 : -1;
+    const int sj_next = lane < 31 ? ((lane + 1) * (ncols - 1)) / 31 : ncols;
+    const double xs = uam_cell_centre(j0 + sj, x0, dx);
+    for (int row = warp; row < UAM_SUPER; row += 8) {
+        const int i = i0 + row;
+        if (i >= H) break;
+        const double y = uam_cell_centre(i, y0, dy);
+        for (int r = 0; r < n_regions; ++r) {
+            const int* cand = coarse_list + (size_t)n_super * (rr.begin[r] - rr.begin[0]) + (size_t)sup * (rr.begin[r + 1] - rr.begin[r]);
+            const int n_cand = coarse_count[r * n_super + sup];
+            bool dirty = false;
+            for (int c = 0; c < n_cand; ++c) {
+                const int s = __ldg(cand + c);
+                const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
+                const double pc = meta.w ? __ldg(psic + s) : 1.0;
+                int lo = 0, hi = ncols;
+                if (!(meta.w && (pc == 0.0 || pc != pc))) {           // (psi(centre) = 0 / NaN reaches every cell: never skipped)
+                    for (int ed = meta.x; ed < meta.y && lo < hi; ++ed) {
+                        const UamEdge rcd = uam_load_edge(edges + ed);
+                        const unsigned t = __ballot_sync(0xffffffffu, uam_row_pred<1>(rcd, xs, y, e));
+                        if (t) {
+                            const int f = __ffs(t) - 1, g = 31 - __clz(t);
+                            lo = max(lo, __shfl_sync(0xffffffffu, sj_prev, f) + 1);
+                            hi = min(hi, __shfl_sync(0xffffffffu, sj_next, g));
+                        } else if ((int)rcd.kind == UAM_EDGE_ELLIPSE) {
+                            // no sample inside: the ellipse's cells on this row, if any, include the column nearest its centre
+                            const double uc = (rcd.p0 - x0) / dx - 0.5 - (double)j0;
+                            int jc = (uc >= 0.0 && uc < (double)ncols) ? (int)uc : (uc < 0.0 ? 0 : ncols - 1);
+                            const int jt = min(max(jc - 1 + min(lane, 3), 0), ncols - 1);     // lanes 0..3: jc - 1 .. jc + 2
+                            const bool in = uam_row_pred<1>(rcd, uam_cell_centre(j0 + jt, x0, dx), y, e);
+                            if (__ballot_sync(0xffffffffu, in)) { lo = max(lo, jc - 10); hi = min(hi, jc + 12); }
+                            else hi = lo;
+                        } else {
+                            hi = lo;
+                        }
+                    }
+                }
+                if (lo >= hi) continue;
+                if (!dirty) {
+#pragma unroll
+                    for (int k = 0; k < UAM_SUPER / 32; ++k) acc[lane + 32 * k] = 0.0;
+                    dirty = true;
+                }
+                for (int j = (lo & ~31) + lane; j < hi; j += 32) {
+                    if (j < lo) continue;
+                    const double x = uam_cell_centre(j0 + j, x0, dx);
+                    double psi = 1.0;
+                    for (int ed = meta.x; ed < meta.y; ++ed) {
+                        const UamEdge rcd = uam_load_edge(edges + ed);
+                        const double m = fmin(__dsub_rn(uam_h_exact(rcd, x, y), e), 0.0);
+                        psi = __dmul_rn(psi, __dmul_rn(m, m));
+                    }
+                    if (meta.w) {
+                        if (psi != 0.0 || pc == 0.0 || pc != pc) acc[j] = __dadd_rn(acc[j], __ddiv_rn(psi, pc));
+                    } else {
+                        acc[j] = __dadd_rn(acc[j], psi);
+                    }
+                }
+            }
+            float* out = layers + (size_t)r * plane + (size_t)i * W + j0;
+#pragma unroll
+            for (int k = 0; k < UAM_SUPER / 32; ++k) {
+                const int j = lane + 32 * k;
+                if (j < ncols) __stcs(out + j, dirty ? (float)acc[j] : 0.0f);
+            }
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------------------
 // exact EDT (squared Euclidean distance to the nearest occupied cell), two separable phases:
 //   phase 1  g(i,j) = distance along column j to the nearest occupied cell.  Banded: per (256-row band, column) find
@@ -584,15 +676,48 @@ __device__ __forceinline__ float uam_clearance_of(int d2, float cellf) { return 
 // phase 2 fast path: block = UAM_EDT_SPAN consecutive cells of one row (4 per thread); the row segment and UAM_EDT_R
 // columns on either side are staged in shared memory together with the minimum of g over every aligned group of 8 columns.
 // A cell scans its own group, then walks outwards group by group: a group at column distance D whose minimum is m cannot
-// hold a better column when D^2 + m^2 >= best, and no farther group can when D^2 >= best -- the exact minimum at about an
-// eighth of the loads of the column-by-column search (ncu r02: that search was issue-bound, 4.5 ms at 16384^2).
+// hold a better column when D^2 + m^2 >= best, and no farther group can when D^2 >= best.  What makes the skipping bite is
+// a tight `best` from the start: the block first solves one ANCHOR cell per group exactly (1/8 of the cells, starting from
+// the loose bound g(c)^2), then every other cell starts from its group's anchor through the Lipschitz bound
+// d(u) <= d(anchor) + |u - anchor| -- so almost every group on its way is dismissed by one comparison and only the groups
+// around the true nearest column are scanned.  Exact (a bound only prunes columns that cannot win).  ncu r02: the
+// column-by-column search was issue-bound, 4.5 ms at 16384^2.
 #define UAM_EDT_SPAN 1024
 #define UAM_EDT_WIN (UAM_EDT_SPAN + 2 * UAM_EDT_R)
+__device__ __forceinline__ void uam_edt_scan_group(const unsigned short* sg, int q, int c, int& best) {
+    const uint4 v = *reinterpret_cast<const uint4*>(&sg[q * 8]);
+    const int b = q * 8 - c;                       // column offset of the group's first cell
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int g0 = (int)(w[k] & 0xffffu), g1 = (int)(w[k] >> 16);
+        const int d0 = b + 2 * k, d1 = b + 2 * k + 1;
+        best = min(best, d0 * d0 + g0 * g0);
+        best = min(best, d1 * d1 + g1 * g1);
+    }
+}
+// exact min over the window's columns of (c - v)^2 + g(v)^2, given best > that minimum on entry; false if the window's edge
+// was reached before the search could stop
+__device__ __forceinline__ bool uam_edt_search(const unsigned short* sg, const unsigned short* sm, int c, int& best) {
+    const int q0 = c >> 3;
+    uam_edt_scan_group(sg, q0, c, best);
+    int d = 1;
+    for (; d <= UAM_EDT_R / 8; ++d) {
+        const int Dl = c - ((q0 - d) * 8 + 7), Dr = (q0 + d) * 8 - c;       // both >= 1
+        const int Dm = min(Dl, Dr);
+        if (Dm * Dm >= best) break;
+        const int ml = sm[q0 - d], mr = sm[q0 + d];
+        if (Dl * Dl + ml * ml < best) uam_edt_scan_group(sg, q0 - d, c, best);
+        if (Dr * Dr + mr * mr < best) uam_edt_scan_group(sg, q0 + d, c, best);
+    }
+    return d <= UAM_EDT_R / 8;
+}
 __global__ void __launch_bounds__(256)
 uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __restrict__ d2, float* __restrict__ clearance,
                     float cellf, uint8_t* __restrict__ row_flag, int* __restrict__ any_flag) {
     __shared__ __align__(16) unsigned short sg[UAM_EDT_WIN];
     __shared__ unsigned short sm[UAM_EDT_WIN / 8];
+    __shared__ int anchor[UAM_EDT_SPAN / 8];
     const int i = blockIdx.y;
     const int u0 = blockIdx.x * UAM_EDT_SPAN;
     const unsigned short* grow = g + (size_t)i * W;
@@ -609,37 +734,32 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
     }
     __syncthreads();
     bool unresolved = false;
-    auto scan_group = [&](int q, int c, int& best) {
-        const uint4 v = *reinterpret_cast<const uint4*>(&sg[q * 8]);
-        const int b = q * 8 - c;                       // column offset of the group's first cell
-        const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int g0 = (int)(w[k] & 0xffffu), g1 = (int)(w[k] >> 16);
-            const int d0 = b + 2 * k, d1 = b + 2 * k + 1;
-            best = min(best, d0 * d0 + g0 * g0);
-            best = min(best, d1 * d1 + g1 * g1);
-        }
-    };
+    // anchors: column 4 of every group of the span
+    if (threadIdx.x < UAM_EDT_SPAN / 8) {
+        const int c = UAM_EDT_R + threadIdx.x * 8 + 4;
+        int best = (int)sg[c] * (int)sg[c] + 1;
+        unresolved = !uam_edt_search(sg, sm, c, best);
+        anchor[threadIdx.x] = best;
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int k = 0; k < UAM_EDT_SPAN / 256; ++k) {
         const int off = k * 256 + threadIdx.x;
         const int u = u0 + off;
         if (u < W) {
             const int c = UAM_EDT_R + off;
-            const int q0 = c >> 3;
-            int best = (int)sg[c] * (int)sg[c];
-            scan_group(q0, c, best);
-            int d = 1;
-            for (; d <= UAM_EDT_R / 8; ++d) {
-                const int Dl = c - ((q0 - d) * 8 + 7), Dr = (q0 + d) * 8 - c;       // both >= 1
-                const int Dm = min(Dl, Dr);
-                if (Dm * Dm >= best) break;
-                const int ml = sm[q0 - d], mr = sm[q0 + d];
-                if (Dl * Dl + ml * ml < best) scan_group(q0 - d, c, best);
-                if (Dr * Dr + mr * mr < best) scan_group(q0 + d, c, best);
+            int best;
+            if ((off & 7) == 4) {
+                best = anchor[off >> 3];
+            } else {
+                // d(u) <= d(anchor) + |u - anchor|: a bound strictly above d2(u) (s over-estimates sqrt(d2(anchor)))
+                const int a = anchor[off >> 3], dl = abs((off & 7) - 4);
+                const int sq = (int)__fsqrt_ru((float)a) + 1;
+                const long long bnd = (long long)a + 2ll * dl * sq + dl * dl + 1;
+                const int own = (int)sg[c] * (int)sg[c] + 1;
+                best = (int)min((long long)own, bnd);
+                if (!uam_edt_search(sg, sm, c, best)) unresolved = true;
             }
-            unresolved = unresolved || (d > UAM_EDT_R / 8);
             const size_t o = (size_t)i * W + u;
             d2[o] = best;
             if (clearance) clearance[o] = uam_clearance_of(best, cellf);
@@ -835,7 +955,7 @@ extern "C" int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, doubl
     UamParams prm = {};
     prm.e = enlargement;
     prm.flags = UAM_PENALTY_SMOOTH | UAM_OBSTACLE_SMOOTH;
-    UAM_TRY(uam_ensure_shape_norm(ctx, prm, st));
+    UAM_TRY(uam_ensure_shape_norm(ctx, prm, st, false));
     UamRegionRanges2 rr;
     for (int r = 0; r <= ctx->n_regions; ++r) rr.begin[r] = ctx->region_begin[r];
     dim3 grid((W + UAM_TILE_W - 1) / UAM_TILE_W, (H + UAM_TILE_H - 1) / UAM_TILE_H);
@@ -861,10 +981,16 @@ extern "C" int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, doubl
         const double hb = 4.0 * std::pow(ctx->edges_max_abs + ext + std::fabs(enlargement) + 1.0, 3.0);
         scan = 2.0 * ctx->max_edges_per_shape * std::log10(hb) < 300.0;
     }
-    if (scan) {
+    if (scan && ctx->rasterizer_scan == 2) {         // the tile form with row intervals by bisection (slower: kept for comparison)
         uam_k_layers_scan<<<grid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
                                                 y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
         UAM_CHECK_LAUNCH(ctx, "uam_k_layers_scan");
+        return UAM_OK;
+    }
+    if (scan) {
+        uam_k_layers_rows<<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
+                                                 y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_layers_rows");
         return UAM_OK;
     }
     uam_k_rasterize_layers<<<grid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
