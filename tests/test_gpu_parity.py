@@ -280,11 +280,13 @@ def test_rasterize_layers_enlargement_and_many_shapes(uam, torch):
     eng = m.engine()
     occ = eng.rasterize_occupancy(H, W, geo).cpu().numpy()
     assert np.array_equal(occ, orc.rasterize_occupancy(om, H, W, *geo))
-    for e in (0.0, 0.05):
+    for e in (0.0, 0.05, -0.02, -0.3):       # -0.3: psi(centre) = 0 for the narrow shapes -> 0/0 = NaN over the whole layer, like the oracle
         lay = eng.rasterize_layers(H, W, geo, e).cpu().numpy()
-        ref = orc.rasterize_layers(om, H, W, *geo, e)
-        assert np.array_equal(lay == 0, ref == 0)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            ref = orc.rasterize_layers(om, H, W, *geo, e)
+        assert np.array_equal(lay == 0, ref == 0) and np.array_equal(np.isnan(lay), np.isnan(ref))
         np.testing.assert_allclose(lay, ref, rtol=2e-7)
+    assert np.isnan(lay).all()
 
 
 @pytest.mark.parametrize('H,W,geo', [(4099, 4113, (0.0, 32.0 / 4113, 0.0, 32.0 / 4099)), (1500, 777, (32.0, -32.0 / 777, 32.0, -32.0 / 1500)),
@@ -323,15 +325,19 @@ def test_scanline_rasterisers_equal_per_cell_evaluation(uam, torch, H, W, geo):
     m.add_obstacle(rect(np.array([16.0, 16.0]), 4.0, 4.0, 0.0))          # axis-aligned edges (constant along a row / a column)
     eng = m.engine()
     res = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         eng.set_option('rasterizer', mode)
+        # (e = -0.03 is more than the slivers' half width: their psi(centre) is 0, the reference's 0/0 = NaN reaches every cell of
+        #  their layer -- such shapes are never culled, by any of the kernels)
         res[mode] = (eng.rasterize_occupancy(H, W, geo), eng.rasterize_layers(H, W, geo, 0.0), eng.rasterize_layers(H, W, geo, 0.04),
-                     eng.rasterize_layers(H, W, geo, -0.03))
+                     eng.rasterize_layers(H, W, geo, -0.0005), eng.rasterize_layers(H, W, geo, -0.03))
     assert 0.2 < float(res[0][0].float().mean()) < 0.995
-    assert torch.equal(res[0][0], res[1][0])
-    for a, b in zip(res[0][1:], res[1][1:]):
-        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    for mode in (1, 2):
+        assert torch.equal(res[0][0], res[mode][0])
+        for a, b in zip(res[0][1:], res[mode][1:]):
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32))
     assert float((res[0][1] != 0).float().mean()) > 0.05
+    assert not bool(torch.isnan(res[1][3]).any()) and bool(torch.isnan(res[1][4]).all())
 
 
 def test_dem_mask(uam, torch):

@@ -52,9 +52,11 @@ uam_k_dem_mask(const float* __restrict__ img, long long n, float thr, int eq_mod
 // Ordered compaction of the candidates at positions [s_begin, s_end) that survive the tile test into list[0..n)
 // (n <= CAP).  A candidate is shape cand[p] (or shape p itself when cand is NULL).  Returns the next position to
 // continue from.  Must be called by all threads of a 256-thread CTA.
+// psic (nullable: the occupancy pass has no use for it): a shape whose psi(centre) is 0 or NaN is never culled -- the
+// reference's psi(x) / psi(centre) is 0/0 = NaN at EVERY point for it (problem.py:79), not only near the shape.
 __device__ int uam_cull_shapes(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes,
                                const int* __restrict__ cand, int s_begin, int s_end, double xa, double xb, double ya,
-                               double yb, double thr, int* list, int* n_out, int* warp_cnt) {
+                               double yb, double thr, int* list, int* n_out, int* warp_cnt, const double* __restrict__ psic = nullptr) {
     int n = 0;
     int s0 = s_begin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -66,7 +68,12 @@ __device__ int uam_cull_shapes(const UamEdge* __restrict__ edges, const UamShape
             s = cand ? __ldg(cand + pos) : pos;
             const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
             keep = true;
-            for (int i = meta.x; i < meta.y && keep; ++i) {
+            bool never = false;
+            if (psic && meta.w) {
+                const double pc = __ldg(psic + s);
+                never = pc == 0.0 || pc != pc;
+            }
+            for (int i = meta.x; i < meta.y && keep && !never; ++i) {
                 const UamEdge r = uam_load_edge(edges + i);
                 if (uam_edge_excludes_tile(r, xa, xb, ya, yb, thr)) keep = false;
             }
@@ -99,7 +106,7 @@ __global__ void __launch_bounds__(256)
 uam_k_cull_coarse(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, int s_begin, int s_end,
                   double thr, int H, int W, double x0, double dx, double y0, double dy, int size,
                   const int* __restrict__ parent_list, const int* __restrict__ parent_count, int parent_size, int parent_gx,
-                  int* __restrict__ out_list, int* __restrict__ out_count) {
+                  int* __restrict__ out_list, int* __restrict__ out_count, const double* __restrict__ psic) {
     __shared__ int list[UAM_LIST_CAP];
     __shared__ int warp_cnt[8];
     const int sup = blockIdx.y * gridDim.x + blockIdx.x;
@@ -120,7 +127,7 @@ uam_k_cull_coarse(const UamEdge* __restrict__ edges, const UamShape* __restrict_
     int s_next = lo;
     while (s_next < hi) {
         int n;
-        s_next = uam_cull_shapes(edges, shapes, cand, s_next, hi, xa, xb, ya, yb, thr, list, &n, warp_cnt);
+        s_next = uam_cull_shapes(edges, shapes, cand, s_next, hi, xa, xb, ya, yb, thr, list, &n, warp_cnt, psic);
         for (int t = threadIdx.x; t < n; t += blockDim.x) dst[total + t] = list[t];
         total += n;
         __syncthreads();
@@ -358,7 +365,7 @@ uam_k_rasterize_layers(const UamEdge* __restrict__ edges, const UamShape* __rest
         while (s_next < s_end) {
             int n;
             // psi != 0 needs h_i - e < 0 for every i: cull when some h_i > e on the whole tile
-            s_next = uam_cull_shapes(edges, shapes, cand, s_next, s_end, xa, xb, ya, yb, e, list, &n, warp_cnt);
+            s_next = uam_cull_shapes(edges, shapes, cand, s_next, s_end, xa, xb, ya, yb, e, list, &n, warp_cnt, psic);
             for (int t = 0; t < n; ++t) {
                 const int s = list[t];
                 const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
@@ -432,7 +439,7 @@ uam_k_layers_scan(const UamEdge* __restrict__ edges, const UamShape* __restrict_
         int s_next = 0;
         while (s_next < s_end) {
             int n;
-            s_next = uam_cull_shapes(edges, shapes, cand, s_next, s_end, xa, xb, ya, yb, e, list, &n, warp_cnt);
+            s_next = uam_cull_shapes(edges, shapes, cand, s_next, s_end, xa, xb, ya, yb, e, list, &n, warp_cnt, psic);
             for (int t0 = 0; t0 < n; t0 += 16) {
                 {   // interval of (shape t0 + tq, tile row trow)
                     const int t = t0 + tq;
@@ -647,27 +654,56 @@ uam_k_edt_band_carry(int n_bands, int W, const int* __restrict__ band_first, con
 }
 
 // g is stored as uint16, clipped at UAM_EDT_CLIP = 2^15 ("no occupied cell in this column": a real distance is below
-// 23170, the largest raster side): half the bytes of phase 1's output and of phase 2's input
+// 23170, the largest raster side): half the bytes of phase 1's output and of phase 2's input.  COLS = 4: a thread sweeps four
+// adjacent columns (4-byte loads of the occupancy, 8-byte stores of g; needs W % 4 == 0), COLS = 1 otherwise.
+template <int COLS>
 __global__ void __launch_bounds__(128)
 uam_k_edt_band_sweep(const uint8_t* __restrict__ occ, int H, int W, const int* __restrict__ above,
                      const int* __restrict__ below, unsigned short* __restrict__ g) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) * COLS;
     const int band = blockIdx.y;
     if (j >= W) return;
     const int i0 = band * UAM_EDT_BAND, i1 = min(i0 + UAM_EDT_BAND, H);
-    int last = above[(size_t)band * W + j];
-#pragma unroll 8
+    int last[COLS], next[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) last[c] = above[(size_t)band * W + j + c];
+#pragma unroll 4
     for (int i = i0; i < i1; ++i) {
-        if (occ[(size_t)i * W + j]) last = i;
-        g[(size_t)i * W + j] = (unsigned short)(last >= 0 ? min(i - last, UAM_EDT_CLIP) : UAM_EDT_CLIP);
+        unsigned o4;
+        if (COLS == 4) o4 = *reinterpret_cast<const unsigned*>(occ + (size_t)i * W + j);
+        else o4 = occ[(size_t)i * W + j];
+        unsigned short out[COLS];
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+            if ((o4 >> (8 * c)) & 0xffu) last[c] = i;
+            out[c] = (unsigned short)(last[c] >= 0 ? min(i - last[c], UAM_EDT_CLIP) : UAM_EDT_CLIP);
+        }
+        if (COLS == 4) *reinterpret_cast<uint2*>(g + (size_t)i * W + j) = make_uint2(out[0] | ((unsigned)out[1] << 16), out[2] | ((unsigned)out[3 % COLS] << 16));
+        else g[(size_t)i * W + j] = out[0];
     }
-    int next = below[(size_t)band * W + j];
-#pragma unroll 8
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) next[c] = below[(size_t)band * W + j + c];
+#pragma unroll 4
     for (int i = i1 - 1; i >= i0; --i) {
-        const int cur = g[(size_t)i * W + j];
-        if (cur == 0) next = i;
-        const int d = next >= 0 ? min(next - i, UAM_EDT_CLIP) : UAM_EDT_CLIP;
-        if (d < cur) g[(size_t)i * W + j] = (unsigned short)d;
+        unsigned short cur[COLS];
+        if (COLS == 4) {
+            const uint2 v = *reinterpret_cast<const uint2*>(g + (size_t)i * W + j);
+            cur[0] = (unsigned short)(v.x & 0xffffu); cur[1 % COLS] = (unsigned short)(v.x >> 16);
+            cur[2 % COLS] = (unsigned short)(v.y & 0xffffu); cur[3 % COLS] = (unsigned short)(v.y >> 16);
+        } else {
+            cur[0] = g[(size_t)i * W + j];
+        }
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+            if (cur[c] == 0) next[c] = i;
+            const int d = next[c] >= 0 ? min(next[c] - i, UAM_EDT_CLIP) : UAM_EDT_CLIP;
+            if (d < (int)cur[c]) { cur[c] = (unsigned short)d; any = true; }
+        }
+        if (any) {
+            if (COLS == 4) *reinterpret_cast<uint2*>(g + (size_t)i * W + j) = make_uint2(cur[0] | ((unsigned)cur[1 % COLS] << 16), cur[2 % COLS] | ((unsigned)cur[3 % COLS] << 16));
+            else g[(size_t)i * W + j] = cur[0];
+        }
     }
 }
 
@@ -682,7 +718,7 @@ __device__ __forceinline__ float uam_clearance_of(int d2, float cellf) { return 
 // d(u) <= d(anchor) + |u - anchor| -- so almost every group on its way is dismissed by one comparison and only the groups
 // around the true nearest column are scanned.  Exact (a bound only prunes columns that cannot win).  ncu r02: the
 // column-by-column search was issue-bound, 4.5 ms at 16384^2.
-#define UAM_EDT_SPAN 1024
+#define UAM_EDT_SPAN 4096
 #define UAM_EDT_WIN (UAM_EDT_SPAN + 2 * UAM_EDT_R)
 __device__ __forceinline__ void uam_edt_scan_group(const unsigned short* sg, int q, int c, int& best) {
     const uint4 v = *reinterpret_cast<const uint4*>(&sg[q * 8]);
@@ -696,70 +732,121 @@ __device__ __forceinline__ void uam_edt_scan_group(const unsigned short* sg, int
         best = min(best, d1 * d1 + g1 * g1);
     }
 }
-// exact min over the window's columns of (c - v)^2 + g(v)^2, given best > that minimum on entry; false if the window's edge
-// was reached before the search could stop
-__device__ __forceinline__ bool uam_edt_search(const unsigned short* sg, const unsigned short* sm, int c, int& best) {
-    const int q0 = c >> 3;
-    uam_edt_scan_group(sg, q0, c, best);
-    int d = 1;
-    for (; d <= UAM_EDT_R / 8; ++d) {
-        const int Dl = c - ((q0 - d) * 8 + 7), Dr = (q0 + d) * 8 - c;       // both >= 1
-        const int Dm = min(Dl, Dr);
-        if (Dm * Dm >= best) break;
-        const int ml = sm[q0 - d], mr = sm[q0 + d];
-        if (Dl * Dl + ml * ml < best) uam_edt_scan_group(sg, q0 - d, c, best);
-        if (Dr * Dr + mr * mr < best) uam_edt_scan_group(sg, q0 + d, c, best);
-    }
-    return d <= UAM_EDT_R / 8;
+// Lipschitz bound: d(u) <= d(u') + |u - u'|, as a squared distance strictly above d2(u) (sq over-estimates sqrt(b))
+__device__ __forceinline__ int uam_edt_bound(int b, int dl) {
+    const int sq = (int)__fsqrt_ru((float)b) + 1;
+    const long long v = (long long)b + 2ll * dl * sq + dl * dl + 1;
+    return v > 0x7fffffffll ? 0x7fffffff : (int)v;
 }
+
+// Staging the window and the divergence of per-lane searches are what the earlier versions of this kernel spent their time
+// on (ncu r02: 4.7 G warp instructions at 16384^2, issue-bound).  Now: the span is 4096 cells (halo overhead 1.5 x instead
+// of 3 x) and a thread stages whole groups of 8 columns with one 16-byte load, taking the group minimum (and the minimum of
+// every 64 columns) on the way; and the SEARCH IS WARP-UNIFORM: the 32 consecutive cells of a warp walk outwards over the
+// same groups at the same time -- first 64-column blocks (skipped as a whole when no lane can gain from them), inside a
+// block the 8-column groups, a group being scanned by every lane (one broadcast 16-byte load) as soon as one lane can gain.
+// Before that each lane scans its own group and the lanes exchange Lipschitz bounds, so one lane that already sees a near
+// obstacle tightens all 32.  Exact: a bound only prunes columns that cannot win.
+#define UAM_EDT_BLK 64
 __global__ void __launch_bounds__(256)
 uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __restrict__ d2, float* __restrict__ clearance,
                     float cellf, uint8_t* __restrict__ row_flag, int* __restrict__ any_flag) {
     __shared__ __align__(16) unsigned short sg[UAM_EDT_WIN];
     __shared__ unsigned short sm[UAM_EDT_WIN / 8];
-    __shared__ int anchor[UAM_EDT_SPAN / 8];
+    __shared__ unsigned short sm64[UAM_EDT_WIN / UAM_EDT_BLK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.y;
     const int u0 = blockIdx.x * UAM_EDT_SPAN;
     const unsigned short* grow = g + (size_t)i * W;
-    for (int t = threadIdx.x; t < UAM_EDT_WIN; t += 256) {
-        const int col = u0 - UAM_EDT_R + t;
-        sg[t] = (col >= 0 && col < W) ? grow[col] : (unsigned short)UAM_EDT_CLIP;
-    }
-    __syncthreads();
+    const bool vec = (W & 7) == 0 && ((((uintptr_t)g) & 15) == 0);
     for (int q = threadIdx.x; q < UAM_EDT_WIN / 8; q += 256) {
-        const uint4 v = *reinterpret_cast<const uint4*>(&sg[q * 8]);
+        const int col = u0 - UAM_EDT_R + q * 8;
+        uint4 v;
+        if (vec && col >= 0 && col + 8 <= W) {
+            v = __ldg(reinterpret_cast<const uint4*>(grow + col));
+        } else {
+            unsigned w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c0 = col + 2 * k, c1 = c0 + 1;
+                const unsigned a0 = (c0 >= 0 && c0 < W) ? grow[c0] : (unsigned)UAM_EDT_CLIP;
+                const unsigned a1 = (c1 >= 0 && c1 < W) ? grow[c1] : (unsigned)UAM_EDT_CLIP;
+                w[k] = a0 | (a1 << 16);
+            }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        *reinterpret_cast<uint4*>(&sg[q * 8]) = v;
         unsigned m = min(min(v.x & 0xffffu, v.x >> 16), min(v.y & 0xffffu, v.y >> 16));
         m = min(m, min(min(v.z & 0xffffu, v.z >> 16), min(v.w & 0xffffu, v.w >> 16)));
         sm[q] = (unsigned short)m;
+        // 8 consecutive groups = one 64-column block: consecutive lanes hold them (q = threadIdx.x + 256 k, 8 | 256)
+        unsigned m8 = m;
+        m8 = min(m8, __shfl_xor_sync(0xffffffffu, m8, 1));
+        m8 = min(m8, __shfl_xor_sync(0xffffffffu, m8, 2));
+        m8 = min(m8, __shfl_xor_sync(0xffffffffu, m8, 4));
+        if ((lane & 7) == 0) sm64[q >> 3] = (unsigned short)m8;
     }
     __syncthreads();
     bool unresolved = false;
-    // anchors: column 4 of every group of the span
-    if (threadIdx.x < UAM_EDT_SPAN / 8) {
-        const int c = UAM_EDT_R + threadIdx.x * 8 + 4;
-        int best = (int)sg[c] * (int)sg[c] + 1;
-        unresolved = !uam_edt_search(sg, sm, c, best);
-        anchor[threadIdx.x] = best;
-    }
-    __syncthreads();
 #pragma unroll 1
     for (int k = 0; k < UAM_EDT_SPAN / 256; ++k) {
-        const int off = k * 256 + threadIdx.x;
-        const int u = u0 + off;
-        if (u < W) {
-            const int c = UAM_EDT_R + off;
-            int best;
-            if ((off & 7) == 4) {
-                best = anchor[off >> 3];
-            } else {
-                // d(u) <= d(anchor) + |u - anchor|: a bound strictly above d2(u) (s over-estimates sqrt(d2(anchor)))
-                const int a = anchor[off >> 3], dl = abs((off & 7) - 4);
-                const int sq = (int)__fsqrt_ru((float)a) + 1;
-                const long long bnd = (long long)a + 2ll * dl * sq + dl * dl + 1;
-                const int own = (int)sg[c] * (int)sg[c] + 1;
-                best = (int)min((long long)own, bnd);
-                if (!uam_edt_search(sg, sm, c, best)) unresolved = true;
+        const int off0 = k * 256 + warp * 32;                 // the warp's first cell (a multiple of 32)
+        if (u0 + off0 >= W) break;                            // (warp-uniform)
+        const int c = UAM_EDT_R + off0 + lane;
+        const int qa = (UAM_EDT_R + off0) >> 3;               // the warp's four own groups: qa .. qa + 3
+        int best = (int)sg[c] * (int)sg[c] + 1;
+        uam_edt_scan_group(sg, c >> 3, c, best);
+        // the warp's other three groups, then Lipschitz bounds across the lanes
+#pragma unroll
+        for (int t = 1; t < 4; ++t) uam_edt_scan_group(sg, qa + (((c >> 3) - qa + t) & 3), c, best);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) best = min(best, uam_edt_bound(__shfl_xor_sync(0xffffffffu, best, o), o));
+        if (u0 + off0 + lane >= W) best = 0;                  // a lane past the end of the row wants nothing (after the exchange)
+        // outwards: left groups qa - 1, qa - 2, ...; right groups qa + 4, qa + 5, ...
+        int ql = qa - 1, qr = qa + 4;
+        bool open_l = true, open_r = true, hit_edge = false;
+        while (open_l || open_r) {
+            if (open_l) {
+                const int D = c - (ql * 8 + 7);                                     // >= 1
+                if (__all_sync(0xffffffffu, D * D >= best)) open_l = false;          // no farther group on this side can win
+                else if (ql < 0) { open_l = false; hit_edge = hit_edge || u0 - UAM_EDT_R > 0; }        // (more raster beyond the window?)
+                else if ((ql & 7) == 7 && ql >= 7) {
+                    // entering a 64-column block from its right end: skip it whole if no lane can gain
+                    const int m64 = sm64[ql >> 3];
+                    if (__all_sync(0xffffffffu, D * D + m64 * m64 >= best)) ql -= 8;
+                    else {
+                        const int m = sm[ql];
+                        if (__any_sync(0xffffffffu, D * D + m * m < best)) uam_edt_scan_group(sg, ql, c, best);
+                        --ql;
+                    }
+                } else {
+                    const int m = sm[ql];
+                    if (__any_sync(0xffffffffu, D * D + m * m < best)) uam_edt_scan_group(sg, ql, c, best);
+                    --ql;
+                }
             }
+            if (open_r) {
+                const int D = qr * 8 - c;                                           // >= 1
+                if (__all_sync(0xffffffffu, D * D >= best)) open_r = false;
+                else if (qr >= UAM_EDT_WIN / 8) { open_r = false; hit_edge = hit_edge || u0 + UAM_EDT_SPAN + UAM_EDT_R < W; }
+                else if ((qr & 7) == 0 && qr + 8 <= UAM_EDT_WIN / 8) {
+                    const int m64 = sm64[qr >> 3];
+                    if (__all_sync(0xffffffffu, D * D + m64 * m64 >= best)) qr += 8;
+                    else {
+                        const int m = sm[qr];
+                        if (__any_sync(0xffffffffu, D * D + m * m < best)) uam_edt_scan_group(sg, qr, c, best);
+                        ++qr;
+                    }
+                } else {
+                    const int m = sm[qr];
+                    if (__any_sync(0xffffffffu, D * D + m * m < best)) uam_edt_scan_group(sg, qr, c, best);
+                    ++qr;
+                }
+            }
+        }
+        unresolved = unresolved || hit_edge;
+        const int u = u0 + off0 + lane;
+        if (u < W) {
             const size_t o = (size_t)i * W + u;
             d2[o] = best;
             if (clearance) clearance[o] = uam_clearance_of(best, cellf);
@@ -888,13 +975,13 @@ extern "C" int uam_dem_mask(uam_ctx* ctx, const float* d_image, int64_t n, float
 
 // supertile lists of the shapes [s_begin, s_end) into out_list / out_count; through 2048-cell blocks first on large rasters
 static int uam_cull_two_level(uam_ctx* ctx, int s_begin, int s_end, double thr, int H, int W, double x0, double dx, double y0,
-                              double dy, int* out_list, int* out_count, cudaStream_t st) {
+                              double dy, int* out_list, int* out_count, cudaStream_t st, const double* psic = nullptr) {
     dim3 sgrid((W + UAM_SUPER - 1) / UAM_SUPER, (H + UAM_SUPER - 1) / UAM_SUPER);
     dim3 g0((W + UAM_SUPER0 - 1) / UAM_SUPER0, (H + UAM_SUPER0 - 1) / UAM_SUPER0);
     const int ns = s_end - s_begin;
     if (ns <= 0 || (size_t)g0.x * g0.y < 4) {
         uam_k_cull_coarse<<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, s_begin, s_end, thr, H, W, x0, dx, y0, dy, UAM_SUPER, nullptr,
-                                                  nullptr, 1, 1, out_list, out_count);
+                                                  nullptr, 1, 1, out_list, out_count, psic);
         UAM_CHECK_LAUNCH(ctx, "uam_k_cull_coarse");
         return UAM_OK;
     }
@@ -903,10 +990,10 @@ static int uam_cull_two_level(uam_ctx* ctx, int s_begin, int s_end, double thr, 
     int* list0 = (int*)ctx->d_cull0_scratch;
     int* count0 = list0 + n0 * (size_t)ns;
     uam_k_cull_coarse<<<g0, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, s_begin, s_end, thr, H, W, x0, dx, y0, dy, UAM_SUPER0, nullptr, nullptr, 1,
-                                          1, list0, count0);
+                                          1, list0, count0, psic);
     UAM_CHECK_LAUNCH(ctx, "uam_k_cull_coarse");
     uam_k_cull_coarse<<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, s_begin, s_end, thr, H, W, x0, dx, y0, dy, UAM_SUPER, list0, count0,
-                                              UAM_SUPER0, (int)g0.x, out_list, out_count);
+                                              UAM_SUPER0, (int)g0.x, out_list, out_count, psic);
     UAM_CHECK_LAUNCH(ctx, "uam_k_cull_coarse");
     return UAM_OK;
 }
@@ -969,7 +1056,7 @@ extern "C" int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, doubl
     int* ccount = clist + n_super * (size_t)std::max(n_reg_shapes, 1);
     for (int r = 0; r < ctx->n_regions; ++r) {
         UAM_TRY(uam_cull_two_level(ctx, rr.begin[r], rr.begin[r + 1], enlargement, H, W, x0, dx, y0, dy,
-                                   clist + n_super * (size_t)(rr.begin[r] - rr.begin[0]), ccount + (size_t)r * n_super, st));
+                                   clist + n_super * (size_t)(rr.begin[r] - rr.begin[0]), ccount + (size_t)r * n_super, st, ctx->d_psic));
     }
     // scanline form unless it could change a bit: non-finite numbers, or magnitudes for which a product of squared factors
     // could overflow before its zero factor (inf * 0 = NaN in the reference; a skipped cell would give 0)
@@ -1032,7 +1119,12 @@ extern "C" int uam_edt(uam_ctx* ctx, const uint8_t* d_occ, int H, int W, double 
     UAM_CHECK_LAUNCH(ctx, "uam_k_edt_band_summary");
     uam_k_edt_band_carry<<<(W + 127) / 128, 128, 0, st>>>(n_bands, W, band_first, band_last, above, below);
     UAM_CHECK_LAUNCH(ctx, "uam_k_edt_band_carry");
-    uam_k_edt_band_sweep<<<bgrid, 128, 0, st>>>(d_occ, H, W, above, below, g);
+    if ((W & 3) == 0 && ((((uintptr_t)d_occ) & 3) == 0)) {
+        dim3 bgrid4((W / 4 + 127) / 128, n_bands);
+        uam_k_edt_band_sweep<4><<<bgrid4, 128, 0, st>>>(d_occ, H, W, above, below, g);
+    } else {
+        uam_k_edt_band_sweep<1><<<bgrid, 128, 0, st>>>(d_occ, H, W, above, below, g);
+    }
     UAM_CHECK_LAUNCH(ctx, "uam_k_edt_band_sweep");
     // phase 2, fast path (writes d2 and, when asked for, the clearance)
     const float cellf = (float)cell;
