@@ -720,40 +720,39 @@ __device__ __forceinline__ float uam_clearance_of(int d2, float cellf) { return 
 // column-by-column search was issue-bound, 4.5 ms at 16384^2.
 #define UAM_EDT_SPAN 4096
 #define UAM_EDT_WIN (UAM_EDT_SPAN + 2 * UAM_EDT_R)
-__device__ __forceinline__ void uam_edt_scan_group(const unsigned short* sg, int q, int c, int& best) {
-    const uint4 v = *reinterpret_cast<const uint4*>(&sg[q * 8]);
+// one group of 8 columns against cell c: sq holds g^2 (2^30 = "no occupied cell in this column")
+__device__ __forceinline__ void uam_edt_scan_group(const int* sq, int q, int c, int& best) {
+    const int4 a = *reinterpret_cast<const int4*>(&sq[q * 8]);
+    const int4 b4 = *reinterpret_cast<const int4*>(&sq[q * 8 + 4]);
     const int b = q * 8 - c;                       // column offset of the group's first cell
-    const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int g0 = (int)(w[k] & 0xffffu), g1 = (int)(w[k] >> 16);
-        const int d0 = b + 2 * k, d1 = b + 2 * k + 1;
-        best = min(best, d0 * d0 + g0 * g0);
-        best = min(best, d1 * d1 + g1 * g1);
-    }
-}
-// Lipschitz bound: d(u) <= d(u') + |u - u'|, as a squared distance strictly above d2(u) (sq over-estimates sqrt(b))
-__device__ __forceinline__ int uam_edt_bound(int b, int dl) {
-    const int sq = (int)__fsqrt_ru((float)b) + 1;
-    const long long v = (long long)b + 2ll * dl * sq + dl * dl + 1;
-    return v > 0x7fffffffll ? 0x7fffffff : (int)v;
+    best = min(best, b * b + a.x);
+    best = min(best, (b + 1) * (b + 1) + a.y);
+    best = min(best, (b + 2) * (b + 2) + a.z);
+    best = min(best, (b + 3) * (b + 3) + a.w);
+    best = min(best, (b + 4) * (b + 4) + b4.x);
+    best = min(best, (b + 5) * (b + 5) + b4.y);
+    best = min(best, (b + 6) * (b + 6) + b4.z);
+    best = min(best, (b + 7) * (b + 7) + b4.w);
 }
 
 // Staging the window and the divergence of per-lane searches are what the earlier versions of this kernel spent their time
-// on (ncu r02: 4.7 G warp instructions at 16384^2, issue-bound).  Now: the span is 4096 cells (halo overhead 1.5 x instead
-// of 3 x) and a thread stages whole groups of 8 columns with one 16-byte load, taking the group minimum (and the minimum of
-// every 64 columns) on the way; and the SEARCH IS WARP-UNIFORM: the 32 consecutive cells of a warp walk outwards over the
-// same groups at the same time -- first 64-column blocks (skipped as a whole when no lane can gain from them), inside a
-// block the 8-column groups, a group being scanned by every lane (one broadcast 16-byte load) as soon as one lane can gain.
-// Before that each lane scans its own group and the lanes exchange Lipschitz bounds, so one lane that already sees a near
-// obstacle tightens all 32.  Exact: a bound only prunes columns that cannot win.
+// on (ncu r02: 4.7 G warp instructions at 16384^2, issue-bound; counted on config C4: the mean distance is 42 cells, yet a
+// warp needs only ~6 group steps and ~3 scans once the search is organised as below -- what is left is fixed cost per warp).
+// The span is 4096 cells (halo overhead 1.5 x instead of 3 x); a thread stages whole groups of 8 columns with one 16-byte
+// load, writes their squares, the group minimum and the minimum of every 64 columns.  The SEARCH IS WARP-UNIFORM: the 32
+// consecutive cells of a warp look at the same group at the same time; a group is scanned by every lane (two broadcast
+// 16-byte loads) as soon as one lane can gain from it, skipped with one vote otherwise, and a whole 64-column block is
+// skipped when no lane can gain from its minimum.  Each lane starts from its own column, the lanes then exchange their
+// radii (r_l = min(r_l, r_k + |l - k|): the Lipschitz bound d(u) <= d(u') + |u - u'|), so one lane that sees a near obstacle
+// tightens all 32.  Exact: a bound only prunes columns that cannot win.
 #define UAM_EDT_BLK 64
+#define UAM_EDT_NONE (1 << 30)
 __global__ void __launch_bounds__(256)
 uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __restrict__ d2, float* __restrict__ clearance,
                     float cellf, uint8_t* __restrict__ row_flag, int* __restrict__ any_flag) {
-    __shared__ __align__(16) unsigned short sg[UAM_EDT_WIN];
-    __shared__ unsigned short sm[UAM_EDT_WIN / 8];
-    __shared__ unsigned short sm64[UAM_EDT_WIN / UAM_EDT_BLK];
+    __shared__ __align__(16) int sq[UAM_EDT_WIN];                      // g^2
+    __shared__ int sm[UAM_EDT_WIN / 8];                                // min of g^2 per group of 8 columns
+    __shared__ int sm64[UAM_EDT_WIN / UAM_EDT_BLK];                    // ... per block of 64
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.y;
     const int u0 = blockIdx.x * UAM_EDT_SPAN;
@@ -775,16 +774,23 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
             }
             v = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4*>(&sg[q * 8]) = v;
-        unsigned m = min(min(v.x & 0xffffu, v.x >> 16), min(v.y & 0xffffu, v.y >> 16));
-        m = min(m, min(min(v.z & 0xffffu, v.z >> 16), min(v.w & 0xffffu, v.w >> 16)));
-        sm[q] = (unsigned short)m;
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        int s8[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int g0 = (int)(w[k] & 0xffffu), g1 = (int)(w[k] >> 16);
+            s8[2 * k] = g0 * g0;
+            s8[2 * k + 1] = g1 * g1;
+        }
+        *reinterpret_cast<int4*>(&sq[q * 8]) = make_int4(s8[0], s8[1], s8[2], s8[3]);
+        *reinterpret_cast<int4*>(&sq[q * 8 + 4]) = make_int4(s8[4], s8[5], s8[6], s8[7]);
+        int m = min(min(min(s8[0], s8[1]), min(s8[2], s8[3])), min(min(s8[4], s8[5]), min(s8[6], s8[7])));
+        sm[q] = m;
         // 8 consecutive groups = one 64-column block: consecutive lanes hold them (q = threadIdx.x + 256 k, 8 | 256)
-        unsigned m8 = m;
-        m8 = min(m8, __shfl_xor_sync(0xffffffffu, m8, 1));
-        m8 = min(m8, __shfl_xor_sync(0xffffffffu, m8, 2));
-        m8 = min(m8, __shfl_xor_sync(0xffffffffu, m8, 4));
-        if ((lane & 7) == 0) sm64[q >> 3] = (unsigned short)m8;
+        m = min(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = min(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        m = min(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        if ((lane & 7) == 0) sm64[q >> 3] = m;
     }
     __syncthreads();
     bool unresolved = false;
@@ -794,15 +800,20 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
         if (u0 + off0 >= W) break;                            // (warp-uniform)
         const int c = UAM_EDT_R + off0 + lane;
         const int qa = (UAM_EDT_R + off0) >> 3;               // the warp's four own groups: qa .. qa + 3
-        int best = (int)sg[c] * (int)sg[c] + 1;
-        uam_edt_scan_group(sg, c >> 3, c, best);
-        // the warp's other three groups, then Lipschitz bounds across the lanes
+        const bool live = u0 + off0 + lane < W;
+        // start: the own column; radii exchanged between the lanes (r >= the true distance, r + |l - k| bounds the neighbour's)
+        int best = sq[c];
+        int r = (int)__fsqrt_ru((float)best) + 1;
 #pragma unroll
-        for (int t = 1; t < 4; ++t) uam_edt_scan_group(sg, qa + (((c >> 3) - qa + t) & 3), c, best);
+        for (int o = 1; o < 32; o <<= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, o) + o);
+        best = live ? min(best, r * r) + 1 : 0;               // strictly above the minimum; a lane past the row's end wants nothing
+        // the warp's own groups, then outwards: left groups qa - 1, qa - 2, ...; right groups qa + 4, qa + 5, ...
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) best = min(best, uam_edt_bound(__shfl_xor_sync(0xffffffffu, best, o), o));
-        if (u0 + off0 + lane >= W) best = 0;                  // a lane past the end of the row wants nothing (after the exchange)
-        // outwards: left groups qa - 1, qa - 2, ...; right groups qa + 4, qa + 5, ...
+        for (int t = 0; t < 4; ++t) {
+            const int q = qa + t;
+            const int D = max(max(q * 8 - c, c - (q * 8 + 7)), 0);
+            if (__any_sync(0xffffffffu, D * D + sm[q] < best)) uam_edt_scan_group(sq, q, c, best);
+        }
         int ql = qa - 1, qr = qa + 4;
         bool open_l = true, open_r = true, hit_edge = false;
         while (open_l || open_r) {
@@ -810,18 +821,9 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
                 const int D = c - (ql * 8 + 7);                                     // >= 1
                 if (__all_sync(0xffffffffu, D * D >= best)) open_l = false;          // no farther group on this side can win
                 else if (ql < 0) { open_l = false; hit_edge = hit_edge || u0 - UAM_EDT_R > 0; }        // (more raster beyond the window?)
-                else if ((ql & 7) == 7 && ql >= 7) {
-                    // entering a 64-column block from its right end: skip it whole if no lane can gain
-                    const int m64 = sm64[ql >> 3];
-                    if (__all_sync(0xffffffffu, D * D + m64 * m64 >= best)) ql -= 8;
-                    else {
-                        const int m = sm[ql];
-                        if (__any_sync(0xffffffffu, D * D + m * m < best)) uam_edt_scan_group(sg, ql, c, best);
-                        --ql;
-                    }
-                } else {
-                    const int m = sm[ql];
-                    if (__any_sync(0xffffffffu, D * D + m * m < best)) uam_edt_scan_group(sg, ql, c, best);
+                else if ((ql & 7) == 7 && __all_sync(0xffffffffu, D * D + sm64[ql >> 3] >= best)) ql -= 8;    // a whole block of 64
+                else {
+                    if (__any_sync(0xffffffffu, D * D + sm[ql] < best)) uam_edt_scan_group(sq, ql, c, best);
                     --ql;
                 }
             }
@@ -829,25 +831,16 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
                 const int D = qr * 8 - c;                                           // >= 1
                 if (__all_sync(0xffffffffu, D * D >= best)) open_r = false;
                 else if (qr >= UAM_EDT_WIN / 8) { open_r = false; hit_edge = hit_edge || u0 + UAM_EDT_SPAN + UAM_EDT_R < W; }
-                else if ((qr & 7) == 0 && qr + 8 <= UAM_EDT_WIN / 8) {
-                    const int m64 = sm64[qr >> 3];
-                    if (__all_sync(0xffffffffu, D * D + m64 * m64 >= best)) qr += 8;
-                    else {
-                        const int m = sm[qr];
-                        if (__any_sync(0xffffffffu, D * D + m * m < best)) uam_edt_scan_group(sg, qr, c, best);
-                        ++qr;
-                    }
-                } else {
-                    const int m = sm[qr];
-                    if (__any_sync(0xffffffffu, D * D + m * m < best)) uam_edt_scan_group(sg, qr, c, best);
+                else if ((qr & 7) == 0 && __all_sync(0xffffffffu, D * D + sm64[qr >> 3] >= best)) qr += 8;
+                else {
+                    if (__any_sync(0xffffffffu, D * D + sm[qr] < best)) uam_edt_scan_group(sq, qr, c, best);
                     ++qr;
                 }
             }
         }
         unresolved = unresolved || hit_edge;
-        const int u = u0 + off0 + lane;
-        if (u < W) {
-            const size_t o = (size_t)i * W + u;
+        if (live) {
+            const size_t o = (size_t)i * W + u0 + off0 + lane;
             d2[o] = best;
             if (clearance) clearance[o] = uam_clearance_of(best, cellf);
         }
