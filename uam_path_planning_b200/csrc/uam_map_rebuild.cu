@@ -807,36 +807,31 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, o) + o);
         best = live ? min(best, r * r) + 1 : 0;               // strictly above the minimum; a lane past the row's end wants nothing
-        // the warp's own groups, then outwards: left groups qa - 1, qa - 2, ...; right groups qa + 4, qa + 5, ...
+        // the warp's own groups, then outwards, one group on either side per step: left qa - d, right qa + 3 + d
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int q = qa + t;
             const int D = max(max(q * 8 - c, c - (q * 8 + 7)), 0);
             if (__any_sync(0xffffffffu, D * D + sm[q] < best)) uam_edt_scan_group(sq, q, c, best);
         }
-        int ql = qa - 1, qr = qa + 4;
-        bool open_l = true, open_r = true, hit_edge = false;
-        while (open_l || open_r) {
-            if (open_l) {
-                const int D = c - (ql * 8 + 7);                                     // >= 1
-                if (__all_sync(0xffffffffu, D * D >= best)) open_l = false;          // no farther group on this side can win
-                else if (ql < 0) { open_l = false; hit_edge = hit_edge || u0 - UAM_EDT_R > 0; }        // (more raster beyond the window?)
-                else if ((ql & 7) == 7 && __all_sync(0xffffffffu, D * D + sm64[ql >> 3] >= best)) ql -= 8;    // a whole block of 64
-                else {
-                    if (__any_sync(0xffffffffu, D * D + sm[ql] < best)) uam_edt_scan_group(sq, ql, c, best);
-                    --ql;
-                }
+        bool hit_edge = false;
+        constexpr int NQ = UAM_EDT_WIN / 8;
+#pragma unroll 1
+        for (int d = 1;; ++d) {
+            const int ql = qa - d, qr = qa + 3 + d;
+            const int Dl = c - (ql * 8 + 7), Dr = qr * 8 - c;                       // both >= 1
+            const int Dm = min(Dl, Dr);
+            if (__all_sync(0xffffffffu, Dm * Dm >= best)) break;                     // no farther group can win
+            if (ql < 0 || qr >= NQ) {
+                // one side of the window is used up (the other is searched on with the clamped index: rescanning the last
+                // group is harmless); unresolved if some lane could still gain beyond it and the raster goes on there
+                if (ql < 0 && qr >= NQ) { hit_edge = true; break; }
+                if (ql < 0 && u0 - UAM_EDT_R > 0 && __any_sync(0xffffffffu, Dl * Dl < best)) hit_edge = true;
+                if (qr >= NQ && u0 + UAM_EDT_SPAN + UAM_EDT_R < W && __any_sync(0xffffffffu, Dr * Dr < best)) hit_edge = true;
             }
-            if (open_r) {
-                const int D = qr * 8 - c;                                           // >= 1
-                if (__all_sync(0xffffffffu, D * D >= best)) open_r = false;
-                else if (qr >= UAM_EDT_WIN / 8) { open_r = false; hit_edge = hit_edge || u0 + UAM_EDT_SPAN + UAM_EDT_R < W; }
-                else if ((qr & 7) == 0 && __all_sync(0xffffffffu, D * D + sm64[qr >> 3] >= best)) qr += 8;
-                else {
-                    if (__any_sync(0xffffffffu, D * D + sm[qr] < best)) uam_edt_scan_group(sq, qr, c, best);
-                    ++qr;
-                }
-            }
+            const int qlc = max(ql, 0), qrc = min(qr, NQ - 1);
+            if (__any_sync(0xffffffffu, Dl * Dl + sm[qlc] < best)) uam_edt_scan_group(sq, qlc, c, best);
+            if (__any_sync(0xffffffffu, Dr * Dr + sm[qrc] < best)) uam_edt_scan_group(sq, qrc, c, best);
         }
         unresolved = unresolved || hit_edge;
         if (live) {
