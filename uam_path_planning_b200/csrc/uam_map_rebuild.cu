@@ -803,6 +803,14 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
         const bool live = u0 + off0 + lane < W;
         // start: the own column; radii exchanged between the lanes (r >= the true distance, r + |l - k| bounds the neighbour's)
         int best = sq[c];
+        if (__all_sync(0xffffffffu, !live || best == 0)) {    // a warp inside an obstacle: nothing to search
+            if (live) {
+                const size_t o = (size_t)i * W + u0 + off0 + lane;
+                d2[o] = 0;
+                if (clearance) clearance[o] = 0.0f;
+            }
+            continue;
+        }
         int r = (int)__fsqrt_ru((float)best) + 1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, o) + o);
