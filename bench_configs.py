@@ -38,7 +38,7 @@ def run_c5(args, torch, uam, dev, rank=0, world=1, reduce_max=None):
     Queries are independent: with `world` ranks the job's queries shard contiguously over the ranks
     (distributed.shard_range), the grid is replicated, there is no exchange at all; times are the max over ranks.
       full sweeps        c5_queries (1 band) / c5_queries_bands (8 bands) per GPU: whole distance + predecessor fields
-      start/goal routes  c5_routes per GPU (128 x 8 GPUs = BASELINE's 1024 queries), in chunks of 16 through
+      start/goal routes  c5_routes per GPU (128 x 8 GPUs = BASELINE's 1024 queries), in chunks of 64 / 16 through
                          Engine.grid_routes (bounded memory); the first chunk's goal distances must equal the full sweep's"""
     from uam_path_planning_b200 import distributed as udist
     eng = uam.Engine(torch.cuda.current_device())
@@ -96,10 +96,11 @@ def run_c5(args, torch, uam, dev, rank=0, world=1, reduce_max=None):
         del dist, parent
         # ---- start/goal routes of all of this rank's queries, 16 at a time ------------------------------------------
         dtg = 1e30
+        chunk = 64 if bands == 1 else 16            # (chunk, bands, 4096, 4096) int64 + int32 fields: 12.9 GB / 25.8 GB
         for rep in range(1 + (args.c5_reps if bands == 1 else 0) + (1 if Qr <= 16 else 0)):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            gd, path, plen = eng.grid_routes(cost, src, goal, blk, chunk=16, max_len=8 * n5)
+            gd, path, plen = eng.grid_routes(cost, src, goal, blk, chunk=chunk, max_len=8 * n5)
             torch.cuda.synchronize()
             if rep or bands > 1 and Qr > 16:
                 dtg = min(dtg, time.perf_counter() - t0)
@@ -113,7 +114,7 @@ def run_c5(args, torch, uam, dev, rank=0, world=1, reduce_max=None):
                               f'queries ({Qr} per GPU), {Qf * world} full cost-to-go sweeps ({Qf} per GPU)', 'bands': bands, 'n_gpus': world,
                     'start_goal_queries': {'queries': Qall, 'seconds': dtg, 'queries_per_s': Qall / dtg,
                                            'goal_distances_equal_full_sweep': goals_ok, 'mean_path_nodes': mean_nodes,
-                                           'paths_found_rank0': found, 'queries_per_launch': 16},
+                                           'paths_found_rank0': found, 'queries_per_launch': chunk},
                     'full_sweeps': {'queries': Qf * world, 'seconds': dt, 'queries_per_s': Qf * world / dt,
                                     'Mnode_per_s': Qf * world * nodes / dt / 1e6,
                                     'min_edge_relaxations_per_s': Qf * world * edges * reach / dt, 'kernel_launches_per_call': launches,

@@ -23,6 +23,7 @@ from ._lib import UAM_EDGE_BOX, UAM_EDGE_ELLIPSE, UAM_EDGE_LINE
 
 
 _SERIAL = itertools.count(1)      # every Inequality / shape state gets a fresh number: cheap, collision-free change detection
+EPOCH = [0]                       # bumped by every such change anywhere: "nothing changed since" is one integer compare
 
 
 class Inequality:
@@ -45,6 +46,7 @@ class Inequality:
         r.flags.writeable = False
         self._record = r
         self._serial = next(_SERIAL)
+        EPOCH[0] += 1
 
     def __call__(self, x):
         from .engine import default_engine
@@ -70,6 +72,7 @@ class QuadraticObstacle:
             assert isinstance(ineq, Inequality), f'Expected Inequality, got {type(ineq)}'
             assert ineq.n == 2, f'Function must be 2-dimensional, got {ineq.n}-dimensional'
             self.inequalities.append(ineq)
+            EPOCH[0] += 1
 
     @property
     def center(self):
@@ -84,6 +87,7 @@ class QuadraticObstacle:
             value.flags.writeable = False
         self._center = value
         self._serial = next(_SERIAL)
+        EPOCH[0] += 1
 
     def state_key(self):
         """Changes whenever something the device table depends on changes (centre, inequality list, any record)."""
