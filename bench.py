@@ -261,7 +261,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def analytic_c1(torch, dev, args, B=100000, n_cpu=2000):
+def analytic_c1(torch, dev, args, B=100000, n_cpu=2000, with_cpu=True):
     import uam_path_planning_b200 as uam
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from conftest import build_product_problem
@@ -286,7 +286,7 @@ def analytic_c1(torch, dev, args, B=100000, n_cpu=2000):
                        f'{sum(len(r) for r in prob.map._region_lists())} region shapes), N = {N}, {B} arc candidates + jitter',
            'ms_per_batch': ms, 'paths_per_s': B / (ms * 1e-3), 'value': B * (N + 1) / (ms * 1e-3), 'unit': 'segment-evals/s',
            'dtype': 'f64', 'collisions': int(col.sum().item())}
-    if not args.no_cpu:
+    if not args.no_cpu and with_cpu:
         from oracle import uam_oracle as orc
         om = orc.OMap(spec)
         Zh = Z[:n_cpu].cpu().numpy()
@@ -450,7 +450,7 @@ def run_ours(args):
     analytic = None
     if rank == 0:
         try:
-            analytic = analytic_c1(torch, dev, args)
+            analytic = analytic_c1(torch, dev, args, with_cpu=world == 1)      # CPU legs run at N = 1 only
         except Exception as exc:              # a secondary figure must not take the headline down
             analytic = {'error': repr(exc)}
 
@@ -502,6 +502,12 @@ def run_ours(args):
     peer_late = eng.peer_timed_out() if world > 1 and not use_nccl else False
 
     # ---- max over ranks -----------------------------------------------------------------------------------------
+    per_rank = torch.tensor([ms_total / args.steps, e2e_c_ms, e2e_z_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        parts = [torch.empty_like(per_rank) for _ in range(world)]
+        dist.all_gather(parts, per_rank)
+        per_rank = torch.stack(parts)
+    per_rank = per_rank.reshape(-1, 3).cpu().numpy()
     ms_total, k_ms, e2e_c_ms, e2e_z_ms, e2e_sync_ms, wp_ms, wchg_ms, late = allmax(
         [ms_total, k_ms, e2e_c_ms, e2e_z_ms, e2e_sync_ms, wp_ms, wchg_ms, float(peer_late)])
 
@@ -534,6 +540,9 @@ def run_ours(args):
             'samples_per_step_per_gpu': total_samples,
             'samples_per_s': total_samples * world * args.steps / (ms_total * 1e-3),
             'best_reduction': reduce_mode, 'peer_wait_timed_out': bool(late),
+            'ms_per_step_per_rank': {'device_resident': [round(float(v), 4) for v in per_rank[:, 0]],
+                                     'e2e': [round(float(v), 4) for v in per_rank[:, 1]],
+                                     'e2e_host_waypoints': [round(float(v), 4) for v in per_rank[:, 2]]},
             'roofline': {
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'traffic_source': prof.get('source'),
