@@ -824,19 +824,30 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
         }
         bool hit_edge = false;
         constexpr int NQ = UAM_EDT_WIN / 8;
+        // hot loop: while both sides are inside the window there is nothing to check but the two votes per side
+        const int d_in = min(qa, NQ - 4 - qa);                // steps d = 1 .. d_in keep qa - d >= 0 and qa + 3 + d < NQ
+        int d = 1;
+        bool done = false;
 #pragma unroll 1
-        for (int d = 1;; ++d) {
+        for (; d <= d_in; ++d) {
             const int ql = qa - d, qr = qa + 3 + d;
             const int Dl = c - (ql * 8 + 7), Dr = qr * 8 - c;                       // both >= 1
             const int Dm = min(Dl, Dr);
-            if (__all_sync(0xffffffffu, Dm * Dm >= best)) break;                     // no farther group can win
-            if (ql < 0 || qr >= NQ) {
-                // one side of the window is used up (the other is searched on with the clamped index: rescanning the last
-                // group is harmless); unresolved if some lane could still gain beyond it and the raster goes on there
-                if (ql < 0 && qr >= NQ) { hit_edge = true; break; }
-                if (ql < 0 && u0 - UAM_EDT_R > 0 && __any_sync(0xffffffffu, Dl * Dl < best)) hit_edge = true;
-                if (qr >= NQ && u0 + UAM_EDT_SPAN + UAM_EDT_R < W && __any_sync(0xffffffffu, Dr * Dr < best)) hit_edge = true;
-            }
+            if (__all_sync(0xffffffffu, Dm * Dm >= best)) { done = true; break; }    // no farther group can win
+            if (__any_sync(0xffffffffu, Dl * Dl + sm[ql] < best)) uam_edt_scan_group(sq, ql, c, best);
+            if (__any_sync(0xffffffffu, Dr * Dr + sm[qr] < best)) uam_edt_scan_group(sq, qr, c, best);
+        }
+        // rare: one side of the window is used up.  The other side is searched on (the clamped index rescans the last group,
+        // which is harmless); unresolved if some lane could still gain beyond the window and the raster goes on there
+#pragma unroll 1
+        for (; !done; ++d) {
+            const int ql = qa - d, qr = qa + 3 + d;
+            const int Dl = c - (ql * 8 + 7), Dr = qr * 8 - c;
+            const int Dm = min(Dl, Dr);
+            if (__all_sync(0xffffffffu, Dm * Dm >= best)) break;
+            if (ql < 0 && qr >= NQ) { hit_edge = true; break; }
+            if (ql < 0 && u0 - UAM_EDT_R > 0 && __any_sync(0xffffffffu, Dl * Dl < best)) hit_edge = true;
+            if (qr >= NQ && u0 + UAM_EDT_SPAN + UAM_EDT_R < W && __any_sync(0xffffffffu, Dr * Dr < best)) hit_edge = true;
             const int qlc = max(ql, 0), qrc = min(qr, NQ - 1);
             if (__any_sync(0xffffffffu, Dl * Dl + sm[qlc] < best)) uam_edt_scan_group(sq, qlc, c, best);
             if (__any_sync(0xffffffffu, Dr * Dr + sm[qrc] < best)) uam_edt_scan_group(sq, qrc, c, best);
