@@ -534,7 +534,10 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
         if (zero_cells && d_parent)
             return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "%llu passable cells have cost 0: predecessors need cost >= 1 on every passable cell "
                                                       "(pass d_parent = NULL for distances only)", zero_cells);
-        if (!delta) delta = mean * 8ull * GT;     // measured on C5 (Q = 16): 4x / 8x / 16x -> 640 / 448 / 336 rounds, 1.69 / 1.77 / 2.06 M activations
+        // measured on C5 (profiles/r02_sweep_grid_delta.json): one band, 64 queries: 4x / 8x / 16x mean x GT -> 183 / 193 / 180
+        // queries/s; eight bands (the fronts also climb between bands: a narrower window re-relaxes fewer tiles), 16 queries:
+        // 1x / 2x / 4x / 8x -> 13.8 / 14.3 / 13.6 / 11.3 queries/s
+        if (!delta) delta = mean * (bands > 1 ? 2ull : 8ull) * GT;
     }
     unsigned long long* list_key = keys + n_flags;
     unsigned long long* minkey = list_key + n_flags;
