@@ -1158,10 +1158,12 @@ def test_label_components_and_stats(uam, torch, H, W, density, smooth, conn):
     rng = np.random.default_rng(H * 1000 + W + conn)
     mask = _blob_mask(rng, H, W, density, smooth)
     eng = uam.Engine()
-    labels, n = eng.label_components(torch.from_numpy(mask).cuda(), conn)
     lab_ref, n_ref = orc.label_components(mask, conn)
-    assert n == n_ref
-    assert np.array_equal(labels.cpu().numpy(), lab_ref)
+    for tiles in (0, 1):          # round 1's global union-find / tile-local labelling in shared memory + border unions
+        eng.set_option('ccl_tiles', tiles)
+        labels, n = eng.label_components(torch.from_numpy(mask).cuda(), conn)
+        assert n == n_ref
+        assert np.array_equal(labels.cpu().numpy(), lab_ref)
     if n:
         area, bbox = eng.component_stats(labels, n)
         a_ref, b_ref = orc.component_stats(lab_ref, n)

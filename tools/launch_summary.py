@@ -25,6 +25,9 @@ for name, v in byname.items():
     if any(name.startswith(k) for k in STEP):
         m = max(v)
         whole[name] = [x for x in v if x > 0.45 * m]
+        if len(whole[name]) == 1 and len(v) > 1 or len(v) == 1:      # a one-off launch (set-up call), not a step kernel
+            other[name] = whole.pop(name)
+            continue
         rest = [x for x in v if x <= 0.45 * m]
         if rest:
             chunk[name] = rest

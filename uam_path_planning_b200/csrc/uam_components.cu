@@ -94,6 +94,117 @@ uam_k_ccl_merge(const uint8_t* __restrict__ mask, int H, int W, int conn8, int* 
     }
 }
 
+// ---- block-local labelling (round 2) --------------------------------------------------------------------------------
+// The two kernels above chase pointers through HBM for every cell (ncu r01: long-scoreboard stalls of 28-31 per issue).
+// Here a CTA first labels a 32 x 32-cell tile entirely in shared memory -- runs per tile row by ballot, unions with the
+// row above by shared-memory atomicMin, local flatten -- and writes for every cell the GLOBAL index of its tile-local
+// root (the smallest index of its local component, hence <= the cell's own index: the union-find invariant holds).
+// Only the pairs that cross a tile border are then united in HBM (1/16 of the cells), and the global flatten finds a
+// root in one or two hops.  The pairing rules are the ones of uam_k_ccl_merge (a union is idempotent, so a rule applied by
+// both kernels costs nothing but time); the result is the same partition, hence the same roots and the same labels.
+#define UAM_CCL_T 32
+__device__ __forceinline__ int uam_sm_find(const int* lab, int i) {
+    int p = lab[i];
+    while (p != i) { i = p; p = lab[i]; }
+    return i;
+}
+__device__ __forceinline__ void uam_sm_union(int* lab, int a, int b) {
+    bool done = false;
+    while (!done) {
+        a = uam_sm_find(lab, a);
+        b = uam_sm_find(lab, b);
+        if (a < b) { const int old = atomicMin(&lab[b], a); done = old == b; b = old; }
+        else if (b < a) { const int old = atomicMin(&lab[a], b); done = old == a; a = old; }
+        else done = true;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+uam_k_ccl_tile(const uint8_t* __restrict__ mask, int H, int W, int conn8, int* __restrict__ L) {
+    __shared__ int lab[UAM_CCL_T * UAM_CCL_T];
+    __shared__ unsigned rowbits[UAM_CCL_T];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = blockIdx.y * UAM_CCL_T, j0 = blockIdx.x * UAM_CCL_T;
+    const int j = j0 + lane;
+    // rows of the tile: warp w owns rows w, w + 8, w + 16, w + 24
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = warp + 8 * k, i = i0 + r;
+        const bool fg = i < H && j < W && mask[(size_t)i * W + j] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, fg);
+        if (lane == 0) rowbits[r] = m;
+        int v = -1;
+        if (fg) {
+            const unsigned below = lane ? (m << (32 - lane)) : 0u;      // bit 31 = lane - 1, ...
+            v = r * UAM_CCL_T + lane - (lane ? min(__clz(~below), lane) : 0);
+        }
+        lab[r * UAM_CCL_T + lane] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = warp + 8 * k;
+        if (r == 0) continue;
+        const unsigned cur = rowbits[r], up = rowbits[r - 1];
+        const unsigned me = 1u << lane;
+        if (!(cur & me)) continue;
+        const bool left = lane > 0 && (cur & (me >> 1)), upleft = lane > 0 && (up & (me >> 1));
+        const int idx = r * UAM_CCL_T + lane;
+        if ((up & me) && !(left && upleft)) uam_sm_union(lab, idx, idx - UAM_CCL_T);
+        if (conn8 && !(up & me)) {
+            if (upleft && !left) uam_sm_union(lab, idx, idx - UAM_CCL_T - 1);
+            if (lane < 31 && (up & (me << 1))) uam_sm_union(lab, idx, idx - UAM_CCL_T + 1);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = warp + 8 * k, i = i0 + r;
+        if (i >= H || j >= W) continue;
+        const int v = lab[r * UAM_CCL_T + lane];
+        int out = -1;
+        if (v >= 0) {
+            const int root = uam_sm_find(lab, r * UAM_CCL_T + lane);
+            out = (i0 + (root >> 5)) * W + j0 + (root & 31);
+        }
+        L[(size_t)i * W + j] = out;
+    }
+}
+
+// the pairs of uam_k_ccl_merge's rules that cross a tile border: border rows (row % 32 == 0) and border columns
+__global__ void __launch_bounds__(256)
+uam_k_ccl_borders(const uint8_t* __restrict__ mask, int H, int W, int conn8, int* __restrict__ L) {
+    const long long n_rows = (long long)((H - 1) / UAM_CCL_T) * W;             // cells of the rows 32, 64, ...
+    const long long n_cols = (long long)((W - 1) / UAM_CCL_T) * H;             // cells of the columns 32, 64, ...
+    const long long total = n_rows + n_cols * (conn8 ? 2 : 1);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        int row, col, part;
+        if (t < n_rows) { part = 0; row = (int)(t / W + 1) * UAM_CCL_T; col = (int)(t % W); }
+        else if (t < n_rows + n_cols) { part = 1; const long long u = t - n_rows; col = (int)(u / H + 1) * UAM_CCL_T; row = (int)(u % H); }
+        else { part = 2; const long long u = t - n_rows - n_cols; col = (int)(u / H + 1) * UAM_CCL_T - 1; row = (int)(u % H); }
+        const long long i = (long long)row * W + col;
+        if (mask[i] == 0) continue;
+        const bool left = col > 0 && mask[i - 1] != 0;
+        if (part == 0) {
+            const bool up = mask[i - W] != 0;
+            const bool upleft = col > 0 && mask[i - W - 1] != 0;
+            if (up && !(left && upleft)) uam_uf_union(L, (int)i, (int)(i - W));
+            if (conn8 && !up) {
+                if (upleft && !left) uam_uf_union(L, (int)i, (int)(i - W - 1));
+                if (col + 1 < W && mask[i - W + 1] != 0) uam_uf_union(L, (int)i, (int)(i - W + 1));
+            }
+        } else if (part == 1) {
+            if (left) uam_uf_union(L, (int)i, (int)(i - 1));
+            // the up-left diagonal across the vertical border (rows on a horizontal border were handled by part 0)
+            if (conn8 && row % UAM_CCL_T != 0 && !left && mask[i - W] == 0 && mask[i - W - 1] != 0) uam_uf_union(L, (int)i, (int)(i - W - 1));
+        } else {
+            // column 32 k - 1: the up-right diagonal across the vertical border
+            if (row % UAM_CCL_T != 0 && col + 1 < W && mask[i - W] == 0 && mask[i - W + 1] != 0) uam_uf_union(L, (int)i, (int)(i - W + 1));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 uam_k_ccl_flatten(long long n, int* __restrict__ L) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -530,10 +641,19 @@ extern "C" int uam_label_components(uam_ctx* ctx, const uint8_t* d_mask, int H, 
     unsigned long long* block_sum = (unsigned long long*)ctx->d_scratch;
     int* L = (int*)(block_sum + nb + 2);
     const unsigned ctas = (unsigned)((n + 255) / 256);
-    uam_k_ccl_init<<<ctas, 256, 0, st>>>(d_mask, H, W, L);
-    UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_init");
-    uam_k_ccl_merge<<<ctas, 256, 0, st>>>(d_mask, H, W, connectivity == 8 ? 1 : 0, L);
-    UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_merge");
+    if (ctx->ccl_tiles && (H + UAM_CCL_T - 1) / UAM_CCL_T <= 65535) {
+        // tile-local labelling in shared memory, then only the pairs across tile borders are united in HBM
+        dim3 tgrid((W + UAM_CCL_T - 1) / UAM_CCL_T, (H + UAM_CCL_T - 1) / UAM_CCL_T);
+        uam_k_ccl_tile<<<tgrid, 256, 0, st>>>(d_mask, H, W, connectivity == 8 ? 1 : 0, L);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_tile");
+        uam_k_ccl_borders<<<ctx->sm_count * 16, 256, 0, st>>>(d_mask, H, W, connectivity == 8 ? 1 : 0, L);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_borders");
+    } else {
+        uam_k_ccl_init<<<ctas, 256, 0, st>>>(d_mask, H, W, L);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_init");
+        uam_k_ccl_merge<<<ctas, 256, 0, st>>>(d_mask, H, W, connectivity == 8 ? 1 : 0, L);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_merge");
+    }
     uam_k_ccl_flatten<<<ctas, 256, 0, st>>>(n, L);
     UAM_CHECK_LAUNCH(ctx, "uam_k_ccl_flatten");
     unsigned long long total = 0;

@@ -157,6 +157,10 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             ctx->psic_valid = false;        // rebuilt (or dropped) with the next analytic call
             ctx->shape_grid = UamShapeGrid{};
             return UAM_OK;
+        case UAM_OPT_CCL_TILES:
+            if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "ccl_tiles must be 0 or 1");
+            ctx->ccl_tiles = (int)value;
+            return UAM_OK;
         case UAM_OPT_RASTERIZER:
             if (value < 0 || value > 2) return uam_fail(ctx, UAM_ERR_INVALID, "rasterizer must be 0 (per cell), 1 (scanline) or 2 (scanline, tile form of the layers)");
             ctx->rasterizer_scan = (int)value;

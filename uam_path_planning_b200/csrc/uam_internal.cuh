@@ -95,6 +95,7 @@ struct uam_ctx {
     int raster_layout = 1;    // layout used by the next uam_map_set_raster*
     int host_chunks = 0;      // *_host raster scoring: pipeline chunks per call (0 = default)
     int host_taper = 0;       // ... and by how many percent the last chunk is smaller (> 0) / the first chunk is smaller (< 0)
+    int ccl_tiles = 1;        // UAM_OPT_CCL_TILES: 1 = tile-local labelling in shared memory first, 0 = global union-find only
     int rasterizer_scan = 1;  // UAM_OPT_RASTERIZER: 1 = scanline rasterisers (row intervals), 0 = per-cell evaluation
     int int_variant = -1;     // integral mode: -1 = auto; 0 = warp per path, lane per sample; 1 = lane pair per sample;
                               // 2 = segments binned by raster tile (L2-resident raster); 3 = pieces sorted by tile, tile staged in smem

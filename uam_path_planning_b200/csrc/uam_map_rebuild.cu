@@ -543,58 +543,24 @@ uam_k_layers_rows(const UamEdge* __restrict__ edges, const UamShape* __restrict_
                 const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
                 const double pc = meta.w ? __ldg(psic + s) : 1.0;
                 int lo = 0, hi = ncols;
-                const bool never = meta.w && (pc == 0.0 || pc != pc);         // psi(centre) = 0 / NaN reaches every cell: never skipped
-                // Shapes of up to four straight edges (every rectangle and triangle of a footprint map): the records stay in
-                // registers for the row, with the row-constant half of h = -sgn (p3 (x - Ax) - p2 (y - Ay)) taken out -- the same
-                // operations in the same order as uam_h_exact, so the same bits, without reloading 64-byte records per 32 cells
-                const int ne = meta.y - meta.x;
-                bool fast = ne <= 4;
-                double ep0[4], ep3[4], et2[4], ens[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    ep0[k] = 0.0; ep3[k] = 0.0; et2[k] = 0.0; ens[k] = 0.0;
-                    if (fast && k < ne) {
-                        const UamEdge rcd = uam_load_edge(edges + meta.x + k);
-                        if ((int)rcd.kind != UAM_EDGE_LINE) fast = false;
-                        ep0[k] = rcd.p0; ep3[k] = rcd.p3; ens[k] = -rcd.p4;
-                        et2[k] = __dmul_rn(rcd.p2, __dsub_rn(y, rcd.p1));
-                    }
-                }
-                if (!never) {
-                    if (fast) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (k < ne && lo < hi) {
-                                const double h = __dmul_rn(ens[k], __dsub_rn(__dmul_rn(ep3[k], __dsub_rn(xs, ep0[k])), et2[k]));
-                                const unsigned t = __ballot_sync(0xffffffffu, __dsub_rn(h, e) < 0.0);
-                                if (t) {
-                                    const int f = __ffs(t) - 1, g = 31 - __clz(t);
-                                    lo = max(lo, __shfl_sync(0xffffffffu, sj_prev, f) + 1);
-                                    hi = min(hi, __shfl_sync(0xffffffffu, sj_next, g));
-                                } else {
-                                    hi = lo;
-                                }
-                            }
-                        }
-                    } else {
-                        for (int ed = meta.x; ed < meta.y && lo < hi; ++ed) {
-                            const UamEdge rcd = uam_load_edge(edges + ed);
-                            const unsigned t = __ballot_sync(0xffffffffu, uam_row_pred<1>(rcd, xs, y, e));
-                            if (t) {
-                                const int f = __ffs(t) - 1, g = 31 - __clz(t);
-                                lo = max(lo, __shfl_sync(0xffffffffu, sj_prev, f) + 1);
-                                hi = min(hi, __shfl_sync(0xffffffffu, sj_next, g));
-                            } else if ((int)rcd.kind == UAM_EDGE_ELLIPSE) {
-                                // no sample inside: the ellipse's cells on this row, if any, include the column nearest its centre
-                                const double uc = (rcd.p0 - x0) / dx - 0.5 - (double)j0;
-                                int jc = (uc >= 0.0 && uc < (double)ncols) ? (int)uc : (uc < 0.0 ? 0 : ncols - 1);
-                                const int jt = min(max(jc - 1 + min(lane, 3), 0), ncols - 1);     // lanes 0..3: jc - 1 .. jc + 2
-                                const bool in = uam_row_pred<1>(rcd, uam_cell_centre(j0 + jt, x0, dx), y, e);
-                                if (__ballot_sync(0xffffffffu, in)) { lo = max(lo, jc - 10); hi = min(hi, jc + 12); }
-                                else hi = lo;
-                            } else {
-                                hi = lo;
-                            }
+                if (!(meta.w && (pc == 0.0 || pc != pc))) {           // (psi(centre) = 0 / NaN reaches every cell: never skipped)
+                    for (int ed = meta.x; ed < meta.y && lo < hi; ++ed) {
+                        const UamEdge rcd = uam_load_edge(edges + ed);
+                        const unsigned t = __ballot_sync(0xffffffffu, uam_row_pred<1>(rcd, xs, y, e));
+                        if (t) {
+                            const int f = __ffs(t) - 1, g = 31 - __clz(t);
+                            lo = max(lo, __shfl_sync(0xffffffffu, sj_prev, f) + 1);
+                            hi = min(hi, __shfl_sync(0xffffffffu, sj_next, g));
+                        } else if ((int)rcd.kind == UAM_EDGE_ELLIPSE) {
+                            // no sample inside: the ellipse's cells on this row, if any, include the column nearest its centre
+                            const double uc = (rcd.p0 - x0) / dx - 0.5 - (double)j0;
+                            int jc = (uc >= 0.0 && uc < (double)ncols) ? (int)uc : (uc < 0.0 ? 0 : ncols - 1);
+                            const int jt = min(max(jc - 1 + min(lane, 3), 0), ncols - 1);     // lanes 0..3: jc - 1 .. jc + 2
+                            const bool in = uam_row_pred<1>(rcd, uam_cell_centre(j0 + jt, x0, dx), y, e);
+                            if (__ballot_sync(0xffffffffu, in)) { lo = max(lo, jc - 10); hi = min(hi, jc + 12); }
+                            else hi = lo;
+                        } else {
+                            hi = lo;
                         }
                     }
                 }
@@ -608,21 +574,10 @@ uam_k_layers_rows(const UamEdge* __restrict__ edges, const UamShape* __restrict_
                     if (j < lo) continue;
                     const double x = uam_cell_centre(j0 + j, x0, dx);
                     double psi = 1.0;
-                    if (fast) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (k < ne) {
-                                const double h = __dmul_rn(ens[k], __dsub_rn(__dmul_rn(ep3[k], __dsub_rn(x, ep0[k])), et2[k]));
-                                const double m = fmin(__dsub_rn(h, e), 0.0);
-                                psi = __dmul_rn(psi, __dmul_rn(m, m));
-                            }
-                        }
-                    } else {
-                        for (int ed = meta.x; ed < meta.y; ++ed) {
-                            const UamEdge rcd = uam_load_edge(edges + ed);
-                            const double m = fmin(__dsub_rn(uam_h_exact(rcd, x, y), e), 0.0);
-                            psi = __dmul_rn(psi, __dmul_rn(m, m));
-                        }
+                    for (int ed = meta.x; ed < meta.y; ++ed) {
+                        const UamEdge rcd = uam_load_edge(edges + ed);
+                        const double m = fmin(__dsub_rn(uam_h_exact(rcd, x, y), e), 0.0);
+                        psi = __dmul_rn(psi, __dmul_rn(m, m));
                     }
                     if (meta.w) {
                         if (psi != 0.0 || pc == 0.0 || pc != pc) acc[j] = __dadd_rn(acc[j], __ddiv_rn(psi, pc));
