@@ -560,8 +560,10 @@ def test_tile_staged_hot_tiles_and_variants_agree(uam, torch, L):
     c_ref, k_ref, ns_ref = orc.score_paths_raster(lay, occ, geo, Z, w, 1.0, True, None)
     w_b = [7.0, 3.0, 0.5][:L]                        # a second weight vector: the combined-layer cache must follow it
     c_ref_b, _, _ = orc.score_paths_raster(lay, occ, geo, Z, w_b, 1.0, True, None)
-    w_n = [5.0, -40.0, 1.0]
-    c_ref_n = orc.score_paths_raster(lay, occ, geo, Z, w_n, 1.0, True, None)[0] if L == 3 else None
+    # L = 3: the folded layer goes negative (bit-plane quads); L = 1: sign-packed quads of the raw layer times a negative
+    # weight (the partial sums are negative: their sign bits cannot carry the collision flags)
+    w_n = [5.0, -40.0, 1.0] if L == 3 else [-40.0]
+    c_ref_n = orc.score_paths_raster(lay, occ, geo, Z, w_n, 1.0, True, None)[0]
     res = {}
     Zt = torch.from_numpy(Z).cuda()
     for variant in (2, 3):
@@ -579,10 +581,9 @@ def test_tile_staged_hot_tiles_and_variants_agree(uam, torch, L):
             np.testing.assert_allclose(cb.cpu().numpy(), c_ref_b, rtol=RTOL_RASTER)
             ca, _ = rm.score_paths(Zt, w, 1.0, True, None)
             assert np.array_equal(ca.cpu().numpy(), r[0])
-            if L == 3:                                # a negative weight: values < 0 cannot carry flags in their sign bits
-                cn, kn = rm.score_paths(Zt, w_n, 1.0, True, None)
-                np.testing.assert_allclose(cn.cpu().numpy(), c_ref_n, rtol=RTOL_RASTER, atol=1e-4)
-                assert np.array_equal(kn.cpu().numpy().astype(bool), k_ref)
+            cn, kn = rm.score_paths(Zt, w_n, 1.0, True, None)  # a negative weight: values < 0 cannot carry flags in their sign bits
+            np.testing.assert_allclose(cn.cpu().numpy(), c_ref_n, rtol=RTOL_RASTER, atol=1e-4)
+            assert np.array_equal(kn.cpu().numpy().astype(bool), k_ref)
     for key in res:
         np.testing.assert_allclose(res[key][0], res[2, 0][0], rtol=2e-6)
     assert np.array_equal(res[3, 2][0], res[3, 1][0]) and np.array_equal(res[2, 2][0], res[2, 1][0])   # both quad forms: same bits

@@ -108,6 +108,9 @@ extern "C" int uam_ctx_create(int device, uam_ctx** out) {
     if (const char* e = getenv("UAM_RASTER_LAYOUT")) ctx->raster_layout = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = std::min(3, std::max(-1, atoi(e)));
     if (const char* e = getenv("UAM_GRID_DELTA")) ctx->grid_delta = std::max(0ll, atoll(e));
+    if (const char* e = getenv("UAM_BIN_CHUNK")) ctx->bin_chunk = std::min(1 << 20, std::max(1024, atoi(e)));
+    if (const char* e = getenv("UAM_BIN_PT")) ctx->bin_pt = atoi(e);
+    if (const char* e = getenv("UAM_BIN_SHIFT")) ctx->bin_shift = std::min(10, std::max(4, atoi(e)));
     if (const char* e = getenv("UAM_NO_SIGN_PACK")) ctx->no_sign_pack = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_COMBINE_LAYERS")) ctx->combine_layers = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_HOST_CHUNKS")) ctx->host_chunks = std::max(0, atoi(e));

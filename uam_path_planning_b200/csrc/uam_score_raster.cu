@@ -515,6 +515,7 @@ uam_k_score_raster_int(const double2* __restrict__ z, long long B, int Wp, UamRa
 struct UamBinGeo {
     int shift;        // bin side = 1 << shift cells
     int nbins;        // Morton id space (power of 4)
+    float hx, ox, hy, oy;   // float32 pixel coordinate of a segment's midpoint: u = (p.x + q.x) * hx + ox (ordering only)
 };
 
 struct __align__(16) UamSegRec {
@@ -558,36 +559,88 @@ __device__ __forceinline__ UamSegRec uam_make_segment(const double2* __restrict_
     return r;
 }
 
-// Raster bin of a segment's midpoint (of the goal waypoint for the pseudo-segment k = Wp - 1), clamped into the raster
-// (NaN -> 0).  The bin only decides the ORDER the segments are scored in (locality), never a result, so it is computed
-// with two multiplications per coordinate -- no sample count, no divisions.
-__device__ __forceinline__ int uam_segment_bin(const double2* __restrict__ z, unsigned long long id, int Wp,
-                                               const UamRasterParams& rp, const UamBinGeo bg, double inv_dx, double inv_dy) {
-    const unsigned long long b = id / (unsigned)Wp;
-    const int k = (int)(id - b * (unsigned)Wp);
-    const double2 p = z[id];
-    const double2 q = k < Wp - 1 ? z[id + 1] : p;
-    double u = (0.5 * (p.x + q.x) - rp.x0) * inv_dx - 0.5, v = (0.5 * (p.y + q.y) - rp.y0) * inv_dy - 0.5;
-    u = fmin(fmax(u, 0.0), (double)(rp.W - 1));
-    v = fmin(fmax(v, 0.0), (double)(rp.H - 1));
-    return (int)(uam_part1by1((unsigned)((int)u >> bg.shift)) | (uam_part1by1((unsigned)((int)v >> bg.shift)) << 1));
-}
+// The raster bin of a segment (uam_k_bin_hist) is the Morton id of the bin that holds its midpoint (the goal waypoint for the
+// pseudo-segment k = Wp - 1), clamped into the raster (NaN -> 0).  The bin only decides the ORDER the segments are scored in
+// (locality), never a result, so it is computed with two multiplications per coordinate -- no sample count, no divisions.
+#define UAM_BIN_CHUNK 8192     // segments per CTA in the histogram / scatter kernels (rounded down to whole paths)
 
-#define UAM_BIN_CHUNK 8192     // segments per CTA in the histogram / scatter kernels
-
+// One pass over the waypoints: bin id of every segment + per-CTA histogram, and -- the waypoints being in registers anyway --
+// the path's length term (same lane assignment and shuffle tree as uam_k_reduce_paths used to run, same bits), so the last
+// kernel of the step no longer re-reads the 1 KiB of waypoints per path.  A CTA owns `ppc` consecutive paths, a warp one path
+// at a time, lanes stride its waypoints: path and waypoint index are loop counters (the id -> (path, k) form of this kernel
+// spent its time in a 64-bit division per segment: ncu r02, issue-bound at 78 %).
+template <int PT>
 __global__ void __launch_bounds__(1024)
-uam_k_bin_hist(const double2* __restrict__ z, unsigned long long n_seg, int Wp, UamRasterParams rp, UamBinGeo bg,
-               unsigned short* __restrict__ seg_bin, unsigned* __restrict__ hist) {
+uam_k_bin_hist(const double2* __restrict__ z, long long B, int Wp, int ppc, UamRasterParams rp, UamBinGeo bg,
+               unsigned short* __restrict__ seg_bin, unsigned* __restrict__ hist, double* __restrict__ len_path) {
     extern __shared__ int s_hist[];
     for (int i = threadIdx.x; i < bg.nbins; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    const unsigned long long lo = (unsigned long long)blockIdx.x * UAM_BIN_CHUNK;
-    const unsigned long long hi = lo + UAM_BIN_CHUNK < n_seg ? lo + UAM_BIN_CHUNK : n_seg;
-    const double inv_dx = 1.0 / rp.dx, inv_dy = 1.0 / rp.dy;
-    for (unsigned long long id = lo + threadIdx.x; id < hi; id += blockDim.x) {
-        const int bin = uam_segment_bin(z, id, Wp, rp, bg, inv_dx, inv_dy);
-        seg_bin[id] = (unsigned short)bin;
-        atomicAdd(&s_hist[bin], 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long p0 = (long long)blockIdx.x * ppc;
+    const long long p1 = p0 + ppc < B ? p0 + ppc : B;
+    // bin coordinate in float32 (ordering only): u = (mid_x - x0) / dx - 0.5 with mid_x = (p.x + q.x) / 2
+    const float hx = bg.hx, hy = bg.hy, ox = bg.ox, oy = bg.oy;
+    const float wl = (float)(rp.W - 1), hl = (float)(rp.H - 1);
+    const int N = Wp - 2;
+    const bool len_smooth = (rp.flags & UAM_LENGTH_SMOOTH) != 0;
+    const bool map_start = !(rp.flags & UAM_OWN_START);
+    // a warp works on PT paths at a time: 2 x PT 16-byte loads in flight per lane, PT interleaved shuffle trees
+    for (long long pb = p0 + (long long)warp * PT; pb < p1; pb += 32 * PT) {
+        const double2* zb = z + pb * Wp;
+        const int np = (int)(p1 - pb < PT ? p1 - pb : PT);
+        // the term |z_0 - map start| of uam_len_term (added to waypoint 0's own term): lane t computes path t's
+        double d_start = 0.0;
+        if (map_start && lane < np) {
+            const double2 p = zb[(size_t)lane * Wp];
+            const double d = uam_norm2r(__dsub_rn(p.x, rp.ms_x), __dsub_rn(p.y, rp.ms_y));
+            d_start = len_smooth ? __dmul_rn(d, d) : d;
+        }
+        double len_sum[PT], ds[PT];
+#pragma unroll
+        for (int t = 0; t < PT; ++t) {
+            len_sum[t] = 0.0;
+            ds[t] = __shfl_sync(0xffffffffu, d_start, t);
+        }
+        for (int j0 = 0; j0 < Wp; j0 += 32) {
+            const int j = j0 + lane;
+            double2 p[PT], q[PT];
+            bool ok[PT];
+#pragma unroll
+            for (int t = 0; t < PT; ++t) {
+                ok[t] = j < Wp && t < np;
+                const double2* zp = zb + (size_t)t * Wp;
+                p[t] = ok[t] ? zp[j] : make_double2(0.0, 0.0);
+                q[t] = (ok[t] && j < Wp - 1) ? zp[j + 1] : p[t];
+            }
+#pragma unroll
+            for (int t = 0; t < PT; ++t) {
+                if (ok[t]) {
+                    const float u = fminf(fmaxf(fmaf((float)(p[t].x + q[t].x), hx, ox), 0.0f), wl);
+                    const float v = fminf(fmaxf(fmaf((float)(p[t].y + q[t].y), hy, oy), 0.0f), hl);
+                    const int bin = (int)(uam_part1by1((unsigned)((int)u >> bg.shift)) | (uam_part1by1((unsigned)((int)v >> bg.shift)) << 1));
+                    seg_bin[(size_t)(pb + t) * Wp + j] = (unsigned short)bin;
+                    atomicAdd(&s_hist[bin], 1);
+                    // uam_len_term: acc = 0; j < N: acc += d(z_j, z_j+1); j == 0: acc += d(z_0, map start); len_sum += acc
+                    double acc = 0.0;
+                    if (j < N) {
+                        const double d = uam_norm2r(__dsub_rn(q[t].x, p[t].x), __dsub_rn(q[t].y, p[t].y));
+                        acc += len_smooth ? __dmul_rn(d, d) : d;
+                    }
+                    if (j == 0 && map_start) acc += ds[t];
+                    len_sum[t] += acc;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int t = 0; t < PT; ++t) len_sum[t] += __shfl_xor_sync(0xffffffffu, len_sum[t], o);      // (the tree of uam_warp_sum)
+        }
+        double mine = len_sum[0];
+#pragma unroll
+        for (int t = 1; t < PT; ++t) mine = lane == t ? len_sum[t] : mine;
+        if (lane < np) len_path[pb + lane] = mine;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < bg.nbins; i += blockDim.x)
@@ -630,26 +683,56 @@ uam_k_bin_scan(const unsigned* __restrict__ hist, int n, unsigned* __restrict__ 
 }
 
 __global__ void __launch_bounds__(1024)
-uam_k_bin_scatter(unsigned long long n_seg, UamBinGeo bg, const unsigned short* __restrict__ seg_bin,
+uam_k_bin_scatter(unsigned long long n_seg, unsigned long long chunk, UamBinGeo bg, const unsigned short* __restrict__ seg_bin,
                   unsigned* __restrict__ cursor, unsigned* __restrict__ sorted_id) {
     extern __shared__ int s_hist[];
     for (int i = threadIdx.x; i < bg.nbins; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    const unsigned long long lo = (unsigned long long)blockIdx.x * UAM_BIN_CHUNK;
-    const unsigned long long hi = lo + UAM_BIN_CHUNK < n_seg ? lo + UAM_BIN_CHUNK : n_seg;
-    for (unsigned long long id = lo + threadIdx.x; id < hi; id += blockDim.x) atomicAdd(&s_hist[seg_bin[id]], 1);
+    const unsigned long long lo = (unsigned long long)blockIdx.x * chunk;
+    const unsigned long long hi = lo + chunk < n_seg ? lo + chunk : n_seg;
+    // up to KEEP ids per thread stay in registers between the counting and the writing pass (one load of the bin ids)
+    constexpr int KEEP = 8;
+    const bool keep = chunk <= 1024ull * KEEP;
+    unsigned short b[KEEP];
+    if (keep) {
+#pragma unroll
+        for (int t = 0; t < KEEP; ++t) {
+            const unsigned long long id = lo + threadIdx.x + 1024u * t;
+            b[t] = id < hi ? seg_bin[id] : (unsigned short)0;
+        }
+#pragma unroll
+        for (int t = 0; t < KEEP; ++t)
+            if (lo + threadIdx.x + 1024u * t < hi) atomicAdd(&s_hist[b[t]], 1);
+    } else {
+        for (unsigned long long id = lo + threadIdx.x; id < hi; id += blockDim.x) atomicAdd(&s_hist[seg_bin[id]], 1);
+    }
     __syncthreads();
-    // reserve this CTA's range in every bin it touches; s_hist becomes the CTA's write cursor
-    for (int i = threadIdx.x; i < bg.nbins; i += blockDim.x) {
-        const int c = s_hist[i];
-        if (c) s_hist[i] = (int)atomicAdd(&cursor[i], (unsigned)c);
+    // reserve this CTA's range in every bin it touches; s_hist becomes the CTA's write cursor (4 independent atomics in flight)
+    for (int i0 = threadIdx.x; i0 < bg.nbins; i0 += 4 * 1024) {
+        int c[4];
+        unsigned r[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) c[t] = i0 + 1024 * t < bg.nbins ? s_hist[i0 + 1024 * t] : 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) r[t] = c[t] ? atomicAdd(&cursor[i0 + 1024 * t], (unsigned)c[t]) : 0u;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (c[t]) s_hist[i0 + 1024 * t] = (int)r[t];
     }
     __syncthreads();
     // the sorted order holds 4-byte segment ids only; the scoring kernel rebuilds the segment from its two waypoints
     // (one lane per record, once per group) -- 48-byte records cost 0.33 ms of scattered writes per C3 shard
-    for (unsigned long long id = lo + threadIdx.x; id < hi; id += blockDim.x) {
-        const unsigned pos = (unsigned)atomicAdd(&s_hist[seg_bin[id]], 1);
-        sorted_id[pos] = (unsigned)id;
+    if (keep) {
+#pragma unroll
+        for (int t = 0; t < KEEP; ++t) {
+            const unsigned long long id = lo + threadIdx.x + 1024u * t;
+            if (id < hi) sorted_id[(unsigned)atomicAdd(&s_hist[b[t]], 1)] = (unsigned)id;
+        }
+    } else {
+        for (unsigned long long id = lo + threadIdx.x; id < hi; id += blockDim.x) {
+            const unsigned pos = (unsigned)atomicAdd(&s_hist[seg_bin[id]], 1);
+            sorted_id[pos] = (unsigned)id;
+        }
     }
 }
 
@@ -921,58 +1004,103 @@ uam_k_score_groups(unsigned long long n_seg, int Wp, UamRasterParams rp, const t
         bool col;
         uam_group_score<TF, LAYOUT, 0>(rp, tex, nullptr, 0, 0, base, lane, r.U, r.V, r.SU, r.SV, r.S, 0, mine, col);
         if (have) {
-            part_pen[r.id] = mine * r.IS;
-            part_col[r.id] = col ? 1 : 0;
+            if (TF == 8 && rp.w0 >= 0.0f) {
+                // sign-packed quads with a weight >= 0: every tap is >= 0, so the partial is >= 0 (or NaN) and its sign bit is
+                // free to carry the collision flag (-0.0f = "0, occupied"): one scattered 4-byte store per segment instead of
+                // 4 + 1 bytes (uam_k_reduce_paths<., 1> reads it back)
+                part_pen[r.id] = __uint_as_float((__float_as_uint(mine * r.IS) & 0x7fffffffu) | (col ? 0x80000000u : 0u));
+            } else {
+                part_pen[r.id] = mine * r.IS;
+                part_col[r.id] = col ? 1 : 0;
+            }
         }
     }
 }
 
 // one warp per path: fixed-order sum of the per-segment partials + the length term
 // BEST: the launch also finds the best candidate (and exchanges it with the peer ranks): uam_best_tail_cta
-template <int BEST>
+// PACKED: the collision flag is the sign bit of the partial (uam_k_score_groups<8>), part_col is not read.
+// len_path: the paths' length terms from uam_k_bin_hist (the waypoints are then read only when nsamp is asked for).
+template <int BEST, int PACKED>
 __global__ void __launch_bounds__(UAM_CTA_THREADS)
 uam_k_reduce_paths(const double2* __restrict__ z, long long B, int Wp, UamRasterParams rp,
-                   const float* __restrict__ part_pen, const uint8_t* __restrict__ part_col, float* __restrict__ cost,
+                   const float* __restrict__ part_pen, const uint8_t* __restrict__ part_col,
+                   const double* __restrict__ len_path, float* __restrict__ cost,
                    uint8_t* __restrict__ collide, long long* __restrict__ nsamp, UamBestTail tl) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * UAM_WARPS_PER_CTA + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * UAM_WARPS_PER_CTA;
     const int N = Wp - 2;
     unsigned long long kbest = UAM_KEY_EMPTY;
-    for (long long path = warp0; path < B; path += nwarps) {
-        const double2* zp = z + path * Wp;
-        float acc = 0.0f;
-        double len_sum = 0.0;
-        long long ns = 0;
-        bool col = false;
+    // a warp works on PT consecutive paths at a time (PT independent load streams, interleaved shuffle trees)
+    constexpr int PT = 4;
+    for (long long pb = warp0 * PT; pb < B; pb += nwarps * PT) {
+        float acc[PT];
+        long long ns[PT];
+        bool col[PT];
+#pragma unroll
+        for (int t = 0; t < PT; ++t) { acc[t] = 0.0f; ns[t] = 0; col[t] = false; }
         for (int j = lane; j < Wp; j += 32) {
-            const double2 p = zp[j];
-            acc += part_pen[path * Wp + j];
-            col = col || part_col[path * Wp + j];
-            len_sum += uam_len_term(zp, j, N, p, rp);
-            if (nsamp) {
-                long long S = 1;
-                if (j < Wp - 1) {
-                    const double2 q = zp[j + 1];
-                    const double dU = __dsub_rn(uam_pix(q.x, rp.x0, rp.dx), uam_pix(p.x, rp.x0, rp.dx));
-                    const double dV = __dsub_rn(uam_pix(q.y, rp.y0, rp.dy), uam_pix(p.y, rp.y0, rp.dy));
-                    S = (long long)uam_seg_samples(dU, dV, rp.spc);
+            float pv[PT];
+            uint8_t cv[PT];
+#pragma unroll
+            for (int t = 0; t < PT; ++t) {
+                const bool ok = pb + t < B;
+                pv[t] = ok ? part_pen[(pb + t) * Wp + j] : 0.0f;
+                cv[t] = (!PACKED && ok) ? part_col[(pb + t) * Wp + j] : (uint8_t)0;
+            }
+#pragma unroll
+            for (int t = 0; t < PT; ++t) {
+                if (PACKED) {
+                    acc[t] += fabsf(pv[t]);
+                    col[t] = col[t] || (__float_as_uint(pv[t]) >> 31);
+                } else {
+                    acc[t] += pv[t];
+                    col[t] = col[t] || cv[t];
                 }
-                ns += S;
+                if (nsamp && pb + t < B) {
+                    long long S = 1;
+                    if (j < Wp - 1) {
+                        const double2* zp = z + (pb + t) * Wp;
+                        const double2 p = zp[j];
+                        const double2 q = zp[j + 1];
+                        const double dU = __dsub_rn(uam_pix(q.x, rp.x0, rp.dx), uam_pix(p.x, rp.x0, rp.dx));
+                        const double dV = __dsub_rn(uam_pix(q.y, rp.y0, rp.dy), uam_pix(p.y, rp.y0, rp.dy));
+                        S = (long long)uam_seg_samples(dU, dV, rp.spc);
+                    }
+                    ns[t] += S;
+                }
             }
         }
-        acc = uam_warp_sum(acc);
-        len_sum = uam_warp_sum(len_sum);
-        col = __any_sync(0xffffffffu, col);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int t = 0; t < PT; ++t) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);              // (the tree of uam_warp_sum)
+        }
+        float a_mine = acc[0];
+        bool c_mine = __any_sync(0xffffffffu, col[0]);
+        long long n_mine = 0;
+#pragma unroll
+        for (int t = 1; t < PT; ++t) {
+            const bool ct = __any_sync(0xffffffffu, col[t]);
+            a_mine = lane == t ? acc[t] : a_mine;
+            c_mine = lane == t ? ct : c_mine;
+        }
         if (nsamp) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+            for (int t = 0; t < PT; ++t) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ns[t] += __shfl_xor_sync(0xffffffffu, ns[t], o);
+                n_mine = lane == t ? ns[t] : n_mine;
+            }
         }
-        if (lane == 0) {
-            const float c = (float)((double)(N + 1) * len_sum + (double)acc / (double)N);
+        const long long path = pb + lane;
+        if (lane < PT && path < B) {
+            const double len_sum = len_path[path];
+            const float c = (float)((double)(N + 1) * len_sum + (double)a_mine / (double)N);
             if (cost) cost[path] = c;
-            if (collide) collide[path] = col ? 1 : 0;
-            if (nsamp) nsamp[path] = ns;
+            if (collide) collide[path] = c_mine ? 1 : 0;
+            if (nsamp) nsamp[path] = n_mine;
             if (BEST) {
                 const unsigned long long k = uam_best_key(c, tl.offset + (unsigned long long)path);
                 kbest = k < kbest ? k : kbest;
@@ -1403,35 +1531,45 @@ int uam_raster_launch_binned(uam_ctx* ctx, const void* texv, const double2* z, i
     typedef typename UamTexel<TF>::T T;
     const unsigned long long n_seg = (unsigned long long)B * Wp;
     UamBinGeo bg;
-    bg.shift = 6;
+    bg.shift = ctx->bin_shift;
     const int side = std::max(rp.W, rp.H);
     while (((side + (1 << bg.shift) - 1) >> bg.shift) > 128) ++bg.shift;       // at most 128 x 128 bins (64 KiB of smem)
     int p2 = 1;
     while (p2 < ((side + (1 << bg.shift) - 1) >> bg.shift)) p2 <<= 1;
     bg.nbins = p2 * p2;
-    // scratch: sorted ids (u32) | part_pen (f32) | hist (u32) | cursor (u32) | seg_bin (u16) | part_col (u8)
-    const size_t need = n_seg * (4 + 4 + 2 + 1) + (size_t)bg.nbins * 8 + 256;
+    bg.hx = (float)(0.5 / rp.dx); bg.hy = (float)(0.5 / rp.dy);
+    bg.ox = (float)(-rp.x0 / rp.dx - 0.5); bg.oy = (float)(-rp.y0 / rp.dy - 0.5);
+    // scratch: sorted ids (u32) | part_pen (f32) | hist (u32) | cursor (u32) | len_path (f64) | seg_bin (u16) | part_col (u8)
+    const size_t need = n_seg * (4 + 4 + 2 + 1) + (size_t)bg.nbins * 8 + (size_t)B * 8 + 256;
     UAM_TRY(uam_reserve(ctx, &ctx->d_bin_scratch[slot], &ctx->bin_scratch_bytes[slot], need));
     unsigned* sorted_id = (unsigned*)ctx->d_bin_scratch[slot];
     float* part_pen = (float*)(sorted_id + n_seg);
     unsigned* hist = (unsigned*)(part_pen + n_seg);
     unsigned* cursor = hist + bg.nbins;
-    unsigned short* seg_bin = (unsigned short*)(cursor + bg.nbins);
+    double* len_path = (double*)(cursor + bg.nbins);          // (8-byte aligned: n_seg * 8 + nbins * 8 bytes in)
+    unsigned short* seg_bin = (unsigned short*)(len_path + B);
     uint8_t* part_col = (uint8_t*)(seg_bin + n_seg);
     UAM_NVTX("uam.raster.binned");
     UAM_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)bg.nbins * 4, st));
-    const unsigned chunks = (unsigned)((n_seg + UAM_BIN_CHUNK - 1) / UAM_BIN_CHUNK);
+    // a CTA of the histogram / scatter kernels owns whole paths: ppc paths = about UAM_BIN_CHUNK segments
+    const int ppc = std::max(1, ctx->bin_chunk / Wp);
+    const unsigned long long chunk = (unsigned long long)ppc * Wp;
+    const unsigned chunks = (unsigned)((B + ppc - 1) / ppc);
     const size_t hsmem = (size_t)bg.nbins * 4;
     if (hsmem > 48 * 1024) {
-        UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+        UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_hist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+        UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_hist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+        UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_hist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
         UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
     }
     nvtxRangePushA("uam.raster.bin");
-    uam_k_bin_hist<<<chunks, 1024, hsmem, st>>>(z, n_seg, Wp, rp, bg, seg_bin, hist);
+    if (ctx->bin_pt == 1) uam_k_bin_hist<1><<<chunks, 1024, hsmem, st>>>(z, (long long)B, Wp, ppc, rp, bg, seg_bin, hist, len_path);
+    else if (ctx->bin_pt == 2) uam_k_bin_hist<2><<<chunks, 1024, hsmem, st>>>(z, (long long)B, Wp, ppc, rp, bg, seg_bin, hist, len_path);
+    else uam_k_bin_hist<4><<<chunks, 1024, hsmem, st>>>(z, (long long)B, Wp, ppc, rp, bg, seg_bin, hist, len_path);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_hist");
     uam_k_bin_scan<<<1, 1024, 0, st>>>(hist, bg.nbins, cursor);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_scan");
-    uam_k_bin_scatter<<<chunks, 1024, hsmem, st>>>(n_seg, bg, seg_bin, cursor, sorted_id);
+    uam_k_bin_scatter<<<chunks, 1024, hsmem, st>>>(n_seg, chunk, bg, seg_bin, cursor, sorted_id);
     UAM_CHECK_LAUNCH(ctx, "uam_k_bin_scatter");
     nvtxRangePop();
     const size_t gsmem = (size_t)UAM_GROUP_SMEM * UAM_WARPS_PER_CTA;
@@ -1447,14 +1585,15 @@ int uam_raster_launch_binned(uam_ctx* ctx, const void* texv, const double2* z, i
     if (ctx->time_kernels && slot == 0) {
         UAM_TRY(uam_time_end(ctx, st));
     }
-    const long long rctas = std::min<long long>((B + UAM_WARPS_PER_CTA - 1) / UAM_WARPS_PER_CTA, (long long)ctx->sm_count * 16);
+    const long long rctas = std::min<long long>((B + 4 * UAM_WARPS_PER_CTA - 1) / (4 * UAM_WARPS_PER_CTA), (long long)ctx->sm_count * 16);   // 4 paths per warp and trip
     UAM_NVTX("uam.raster.reduce+best");
-    if (best) {
-        uam_k_reduce_paths<1><<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, d_cost, d_collide, d_nsamp, *best);
-        *best_done = true;
-    } else {
-        uam_k_reduce_paths<0><<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, d_cost, d_collide, d_nsamp, UamBestTail{});
-    }
+    const bool packed = TF == 8 && rp.w0 >= 0.0f;       // the condition uam_k_score_groups tests
+    const UamBestTail tl = best ? *best : UamBestTail{};
+    if (best && packed) uam_k_reduce_paths<1, 1><<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, len_path, d_cost, d_collide, d_nsamp, tl);
+    else if (best) uam_k_reduce_paths<1, 0><<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, len_path, d_cost, d_collide, d_nsamp, tl);
+    else if (packed) uam_k_reduce_paths<0, 1><<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, len_path, d_cost, d_collide, d_nsamp, tl);
+    else uam_k_reduce_paths<0, 0><<<(unsigned)rctas, UAM_CTA_THREADS, 0, st>>>(z, B, Wp, rp, part_pen, part_col, len_path, d_cost, d_collide, d_nsamp, tl);
+    if (best) *best_done = true;
     UAM_CHECK_LAUNCH(ctx, "uam_k_reduce_paths");
     return UAM_OK;
 }
