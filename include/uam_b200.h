@@ -108,7 +108,8 @@ enum {
                                          interval of cells inside the shape by bisection with the exact fp64 predicate (the value of
                                          an inequality along a row is monotone in the column) and only touch those cells; 0: every
                                          cell of every surviving tile is evaluated (round-1 kernels); 2: as 1 with the tile form of the
-                                         layer kernel (row intervals by bisection inside 16 x 64 tiles).  Same bits in every mode */
+                                         layer kernel (row intervals by bisection inside 16 x 64 tiles); 3: as 1 with the sampled row
+                                         form of the layer kernel (coarse spans from 32 sample columns per row).  Same bits in every mode */
     UAM_OPT_CCL_TILES = 11,           /* 1 (default): uam_label_components labels 32 x 32-cell tiles in shared memory first and unites only
                                          the pairs across tile borders in HBM; 0: global union-find over all cells (round 1).  Same labels */
     UAM_OPT_SHAPE_GRID = 9            /* 1 (default): the analytic scorer / point queries look up per-cell candidate lists over

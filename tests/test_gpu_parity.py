@@ -325,14 +325,14 @@ def test_scanline_rasterisers_equal_per_cell_evaluation(uam, torch, H, W, geo):
     m.add_obstacle(rect(np.array([16.0, 16.0]), 4.0, 4.0, 0.0))          # axis-aligned edges (constant along a row / a column)
     eng = m.engine()
     res = {}
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         eng.set_option('rasterizer', mode)
         # (e = -0.03 is more than the slivers' half width: their psi(centre) is 0, the reference's 0/0 = NaN reaches every cell of
         #  their layer -- such shapes are never culled, by any of the kernels)
         res[mode] = (eng.rasterize_occupancy(H, W, geo), eng.rasterize_layers(H, W, geo, 0.0), eng.rasterize_layers(H, W, geo, 0.04),
                      eng.rasterize_layers(H, W, geo, -0.0005), eng.rasterize_layers(H, W, geo, -0.03))
     assert 0.2 < float(res[0][0].float().mean()) < 0.995
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         assert torch.equal(res[0][0], res[mode][0])
         for a, b in zip(res[0][1:], res[mode][1:]):
             assert torch.equal(a.view(torch.int32), b.view(torch.int32))

@@ -165,7 +165,7 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             ctx->ccl_tiles = (int)value;
             return UAM_OK;
         case UAM_OPT_RASTERIZER:
-            if (value < 0 || value > 2) return uam_fail(ctx, UAM_ERR_INVALID, "rasterizer must be 0 (per cell), 1 (scanline) or 2 (scanline, tile form of the layers)");
+            if (value < 0 || value > 3) return uam_fail(ctx, UAM_ERR_INVALID, "rasterizer must be 0 (per cell), 1 (scanline), 2 (scanline, tile form of the layers) or 3 (scanline, sampled row form of the layers)");
             ctx->rasterizer_scan = (int)value;
             return UAM_OK;
         case UAM_OPT_TIME_KERNELS:

@@ -513,12 +513,12 @@ uam_k_layers_scan(const UamEdge* __restrict__ edges, const UamShape* __restrict_
 // span are evaluated, 32 at a time (lane = column mod 32), with the per-cell arithmetic of uam_k_rasterize_layers, and
 // accumulated in shape order in a shared-memory row of doubles; the row is stored once, coalesced.  A cell outside the span
 // has a zero factor in psi: the exact +0 the per-cell kernel adds (host-side overflow guard as for the other scan forms).
-__global__ void __launch_bounds__(256)
-uam_k_layers_rows(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, const double* __restrict__ psic,
-                  UamRegionRanges2 rr, int n_regions, int H, int W, double x0, double dx, double y0, double dy, double e,
-                  const int* __restrict__ coarse_list, const int* __restrict__ coarse_count, int n_super,
-                  float* __restrict__ layers) {
-    __shared__ double acc_all[8][UAM_SUPER];
+__device__ __noinline__ void uam_layers_rows_sampled(double (*acc_all)[UAM_SUPER], const UamEdge* __restrict__ edges,
+                                                        const UamShape* __restrict__ shapes, const double* __restrict__ psic,
+                                                        const UamRegionRanges2& rr, int n_regions, int H, int W, double x0,
+                                                        double dx, double y0, double dy, double e,
+                                                        const int* __restrict__ coarse_list, const int* __restrict__ coarse_count,
+                                                        int n_super, float* __restrict__ layers) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* acc = acc_all[warp];
     const int sup = blockIdx.y * gridDim.x + blockIdx.x;
@@ -592,6 +592,224 @@ uam_k_layers_rows(const UamEdge* __restrict__ edges, const UamShape* __restrict_
                 const int j = lane + 32 * k;
                 if (j < ncols) __stcs(out + j, dirty ? (float)acc[j] : 0.0f);
             }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+uam_k_layers_rows(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, const double* __restrict__ psic,
+                  UamRegionRanges2 rr, int n_regions, int H, int W, double x0, double dx, double y0, double dy, double e,
+                  const int* __restrict__ coarse_list, const int* __restrict__ coarse_count, int n_super,
+                  float* __restrict__ layers) {
+    __shared__ double acc_all[8][UAM_SUPER];
+    uam_layers_rows_sampled(acc_all, edges, shapes, psic, rr, n_regions, H, W, x0, dx, y0, dy, e, coarse_list, coarse_count, n_super, layers);
+}
+
+// Cells [lo, hi) of one raster row against a shape of NE straight edges (records at ed[0 .. NE)): the row constants of every
+// edge stay in registers, no record loads and no dispatch on the record kind per cell.  Same operations in the same order as
+// uam_h_exact + the psi product of the generic loop (the minimum min(v, 0) is taken as v < 0 ? v : 0, which differs from
+// fmin only in the sign of a zero that is squared next).  Returns false -- nothing done -- if an edge is not a straight line.
+template <int NE>
+__device__ __forceinline__ bool uam_layers_cells_lines(const UamEdge* __restrict__ ed, double* __restrict__ acc, int lane, int lo,
+                                                       int hi, int j0, double x0, double dx, double y, double e, bool normalised,
+                                                       double pc, bool always) {
+    double A0[NE], A3[NE], T2[NE], NP4[NE];
+    bool lines = true;
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const UamEdge rcd = uam_load_edge(ed + k);
+        lines = lines && (int)rcd.kind == UAM_EDGE_LINE;
+        A0[k] = rcd.p0; A3[k] = rcd.p3; T2[k] = __dmul_rn(rcd.p2, __dsub_rn(y, rcd.p1)); NP4[k] = -rcd.p4;
+    }
+    if (!lines) return false;
+    // whole double trips first (two cells per lane, j and j + 32: two independent dependency chains through the fp64 pipe), then
+    // the remaining < 64 cells one per lane and trip
+    int j = lo + lane;
+    for (const int hi2 = lo + ((hi - lo) & ~63); j < hi2; j += 64) {
+        const double xa = uam_cell_centre(j0 + j, x0, dx), xb = uam_cell_centre(j0 + j + 32, x0, dx);
+        double psa = 1.0, psb = 1.0;
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            // uam_h_exact, line: -sgn * ((By-Ay)*(x-Ax) - (Bx-Ax)*(y-Ay)), the second product hoisted out of the row
+            const double va = __dsub_rn(__dmul_rn(NP4[k], __dsub_rn(__dmul_rn(A3[k], __dsub_rn(xa, A0[k])), T2[k])), e);
+            const double vb = __dsub_rn(__dmul_rn(NP4[k], __dsub_rn(__dmul_rn(A3[k], __dsub_rn(xb, A0[k])), T2[k])), e);
+            const double ma = va < 0.0 ? va : 0.0, mb = vb < 0.0 ? vb : 0.0;
+            psa = __dmul_rn(psa, __dmul_rn(ma, ma));
+            psb = __dmul_rn(psb, __dmul_rn(mb, mb));
+        }
+        if (normalised) {
+            if (psa != 0.0 || always) acc[j] = __dadd_rn(acc[j], __ddiv_rn(psa, pc));
+            if (psb != 0.0 || always) acc[j + 32] = __dadd_rn(acc[j + 32], __ddiv_rn(psb, pc));
+        } else {
+            acc[j] = __dadd_rn(acc[j], psa);
+            acc[j + 32] = __dadd_rn(acc[j + 32], psb);
+        }
+    }
+    for (; j < hi; j += 32) {
+        const double x = uam_cell_centre(j0 + j, x0, dx);
+        double psi = 1.0;
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const double v = __dsub_rn(__dmul_rn(NP4[k], __dsub_rn(__dmul_rn(A3[k], __dsub_rn(x, A0[k])), T2[k])), e);
+            const double m = v < 0.0 ? v : 0.0;
+            psi = __dmul_rn(psi, __dmul_rn(m, m));
+        }
+        if (normalised) {
+            if (psi != 0.0 || always) acc[j] = __dadd_rn(acc[j], __ddiv_rn(psi, pc));
+        } else {
+            acc[j] = __dadd_rn(acc[j], psi);
+        }
+    }
+    return true;
+}
+
+// Interval form of the layer rasteriser (the default).  What the sampled row form above still pays per (row, candidate
+// shape) -- one predicate evaluation per lane and inequality, a vote and two shuffles, whether the shape touches the row
+// or not (ncu r02: 2.8 ms at 16384^2, issue-bound, the fp64 pipe a quarter busy) -- is done here the way the occupancy
+// kernel does it: phase A, THREAD per row of the supertile: for every candidate shape of every region the thread finds the
+// row's exact interval of cells with all h_i - e < 0 by bisection with the exact predicate (uam_row_interval_edge<1>, ~9
+// evaluations per inequality, 32 rows per warp instruction) and leaves it in shared memory (2 bytes per (row, candidate));
+// phase B, WARP per row: only the cells of the interval are evaluated (they are exactly the cells where psi != 0), lanes =
+// columns, same per-cell arithmetic and shape order as every other form, so the same bits.  Shapes of up to 4 straight edges
+// (rectangular footprints, triangles) keep their row constants {Ax, By - Ay, (Bx - Ax)(y - Ay), -sgn} in registers: no
+// record loads and no dispatch on the record kind per cell.  A supertile with more than UAM_IV_CAP candidates over all
+// regions (their intervals would not fit) runs the sampled form.
+#define UAM_IV_CAP 60
+#define UAM_IV_EMPTY 1u          // lo | (hi - 1) << 8 with hi - 1 < lo
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+uam_k_layers_iv(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, const double* __restrict__ psic,
+                const __grid_constant__ UamRegionRanges2 rr, int n_regions, int H, int W, double x0, double dx, double y0, double dy, double e,
+                const int* __restrict__ coarse_list, const int* __restrict__ coarse_count, int n_super,
+                float* __restrict__ layers) {
+    __shared__ double acc_all[8][UAM_SUPER];
+    __shared__ unsigned short iv[UAM_IV_CAP][UAM_SUPER];
+    __shared__ int s_ncand[UAM_MAX_REGIONS];
+    __shared__ const int* s_cand[UAM_MAX_REGIONS];
+    const int sup = blockIdx.y * gridDim.x + blockIdx.x;
+    int n_all = 0;
+    for (int r = 0; r < n_regions; ++r) n_all += coarse_count[r * n_super + sup];
+    if (threadIdx.x < n_regions) {
+        const int r = threadIdx.x;
+        s_ncand[r] = coarse_count[r * n_super + sup];
+        s_cand[r] = coarse_list + (size_t)n_super * (rr.begin[r] - rr.begin[0]) + (size_t)sup * (rr.begin[r + 1] - rr.begin[r]);
+    }
+    if (n_all > UAM_IV_CAP) {          // (CTA-uniform)
+        uam_layers_rows_sampled(acc_all, edges, shapes, psic, rr, n_regions, H, W, x0, dx, y0, dy, e, coarse_list, coarse_count, n_super, layers);
+        return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j0 = blockIdx.x * UAM_SUPER, i0 = blockIdx.y * UAM_SUPER;
+    const int ncols = min(UAM_SUPER, W - j0);
+    const size_t plane = (size_t)H * W;
+    // phase A: thread = row
+    {
+        const int i = i0 + threadIdx.x;
+        const double y = uam_cell_centre(i, y0, dy);
+        int base = 0;
+        for (int r = 0; r < n_regions; ++r) {
+            const int* cand = coarse_list + (size_t)n_super * (rr.begin[r] - rr.begin[0]) + (size_t)sup * (rr.begin[r + 1] - rr.begin[r]);
+            const int n_cand = coarse_count[r * n_super + sup];
+            for (int c = 0; c < n_cand; ++c) {
+                const int s = __ldg(cand + c);
+                const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
+                int lo = 0, hi = i < H ? ncols : 0;
+                bool every = false;                                   // psi(centre) = 0 / NaN reaches every cell: never skipped
+                if (meta.w) {
+                    const double pc = __ldg(psic + s);
+                    every = pc == 0.0 || pc != pc;
+                }
+                if (!every) {
+                    for (int ed = meta.x; ed < meta.y && lo < hi; ++ed) {
+                        const UamEdge rcd = uam_load_edge(edges + ed);
+                        uam_row_interval_edge<1>(rcd, y, x0, dx, j0, ncols, e, lo, hi);
+                    }
+                }
+                iv[base + c][threadIdx.x] = (unsigned short)(lo < hi ? (unsigned)lo | ((unsigned)(hi - 1) << 8) : UAM_IV_EMPTY);
+            }
+            base += n_cand;
+        }
+    }
+    __syncthreads();
+    // phase B: warp = row
+    double* acc = acc_all[warp];
+    const bool vec = (W & 3) == 0 && (ncols & 3) == 0 && ((((uintptr_t)layers) & 15) == 0);
+    for (int row = warp; row < UAM_SUPER; row += 8) {
+        const int i = i0 + row;
+        if (i >= H) break;
+        const double y = uam_cell_centre(i, y0, dy);
+        float* out = layers + (size_t)i * W + j0;
+        int base = 0;
+        for (int r = 0; r < n_regions; ++r, out += plane) {
+            const int* cand = s_cand[r];
+            const int n_cand = s_ncand[r];
+            bool dirty = false;
+            for (int c = 0; c < n_cand; ++c) {
+                const unsigned v = iv[base + c][row];
+                const int lo = (int)(v & 255u), hi = (int)(v >> 8) + 1;
+                if (hi <= lo) continue;
+                if (!dirty) {
+#pragma unroll
+                    for (int k = 0; k < UAM_SUPER / 32; ++k) acc[lane + 32 * k] = 0.0;
+                    dirty = true;
+                }
+                __syncwarp();                  // (the lane that owns a column changes from shape to shape: lane = (j - lo) mod 32)
+                const int s = __ldg(cand + c);
+                const int4 meta = __ldg(reinterpret_cast<const int4*>(&shapes[s].e0));
+                const double pc = meta.w ? __ldg(psic + s) : 1.0;
+                const bool always = pc == 0.0 || pc != pc;          // (psi / pc is added even when psi == 0: 0/0 = NaN)
+                const int ne = meta.y - meta.x;
+                if (ne == 4) {
+                    if (uam_layers_cells_lines<4>(edges + meta.x, acc, lane, lo, hi, j0, x0, dx, y, e, meta.w != 0, pc, always)) continue;
+                } else if (ne == 3) {
+                    if (uam_layers_cells_lines<3>(edges + meta.x, acc, lane, lo, hi, j0, x0, dx, y, e, meta.w != 0, pc, always)) continue;
+                }
+                for (int j = lo + lane; j < hi; j += 32) {
+                    const double x = uam_cell_centre(j0 + j, x0, dx);
+                    double psi = 1.0;
+                    for (int ed = meta.x; ed < meta.y; ++ed) {
+                        const UamEdge rcd = uam_load_edge(edges + ed);
+                        const double m = fmin(__dsub_rn(uam_h_exact(rcd, x, y), e), 0.0);
+                        psi = __dmul_rn(psi, __dmul_rn(m, m));
+                    }
+                    if (meta.w) {
+                        if (psi != 0.0 || always) acc[j] = __dadd_rn(acc[j], __ddiv_rn(psi, pc));
+                    } else {
+                        acc[j] = __dadd_rn(acc[j], psi);
+                    }
+                }
+            }
+            base += n_cand;
+            if (!dirty) {                      // (warp-uniform) no shape of the region on this row
+                if (vec) {
+#pragma unroll
+                    for (int k = 0; k < UAM_SUPER / 128; ++k)
+                        if (4 * (lane + 32 * k) < ncols) __stcs(reinterpret_cast<float4*>(out) + lane + 32 * k, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < UAM_SUPER / 32; ++k)
+                        if (lane + 32 * k < ncols) __stcs(out + lane + 32 * k, 0.0f);
+                }
+                continue;
+            }
+            __syncwarp();
+            if (vec) {
+#pragma unroll
+                for (int k = 0; k < UAM_SUPER / 128; ++k) {
+                    const int j = 4 * (lane + 32 * k);
+                    if (j < ncols) {
+                        const double2 a = *reinterpret_cast<const double2*>(acc + j), b2 = *reinterpret_cast<const double2*>(acc + j + 2);
+                        __stcs(reinterpret_cast<float4*>(out) + lane + 32 * k, make_float4((float)a.x, (float)a.y, (float)b2.x, (float)b2.y));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < UAM_SUPER / 32; ++k) {
+                    const int j = lane + 32 * k;
+                    if (j < ncols) __stcs(out + j, (float)acc[j]);
+                }
+            }
+            __syncwarp();
         }
     }
 }
@@ -1081,10 +1299,21 @@ extern "C" int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, doubl
         UAM_CHECK_LAUNCH(ctx, "uam_k_layers_scan");
         return UAM_OK;
     }
-    if (scan) {
+    if (scan && ctx->rasterizer_scan == 3) {         // the sampled row form (round 2's first scanline kernel: kept for comparison)
         uam_k_layers_rows<<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
                                                  y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
         UAM_CHECK_LAUNCH(ctx, "uam_k_layers_rows");
+        return UAM_OK;
+    }
+    if (scan) {
+        static const int minb = getenv("UAM_LAYERS_MINB") ? atoi(getenv("UAM_LAYERS_MINB")) : 2;      // (A/B runs only)
+        if (minb == 3) uam_k_layers_iv<3><<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
+                                                                  y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
+        else if (minb == 2) uam_k_layers_iv<2><<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
+                                                                       y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
+        else uam_k_layers_iv<4><<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
+                                                       y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
+        UAM_CHECK_LAUNCH(ctx, "uam_k_layers_iv");
         return UAM_OK;
     }
     uam_k_rasterize_layers<<<grid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
