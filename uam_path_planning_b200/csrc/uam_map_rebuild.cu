@@ -938,19 +938,19 @@ __device__ __forceinline__ float uam_clearance_of(int d2, float cellf) { return 
 // column-by-column search was issue-bound, 4.5 ms at 16384^2.
 #define UAM_EDT_SPAN 4096
 #define UAM_EDT_WIN (UAM_EDT_SPAN + 2 * UAM_EDT_R)
-// one group of 8 columns against cell c: sq holds g^2 (2^30 = "no occupied cell in this column")
+// one group of 8 columns against cell c.  sq holds g^2 + k^2 for column 8 q + k (2^30 + k^2 = "no occupied cell in this
+// column"): with b = 8 q - c the candidate (b + k)^2 + g^2 is b^2 + (2 b) k + sq -- one multiply-add with a constant k and
+// half a three-way minimum per column, b^2 added once at the end
 __device__ __forceinline__ void uam_edt_scan_group(const int* sq, int q, int c, int& best) {
     const int4 a = *reinterpret_cast<const int4*>(&sq[q * 8]);
     const int4 b4 = *reinterpret_cast<const int4*>(&sq[q * 8 + 4]);
     const int b = q * 8 - c;                       // column offset of the group's first cell
-    best = min(best, b * b + a.x);
-    best = min(best, (b + 1) * (b + 1) + a.y);
-    best = min(best, (b + 2) * (b + 2) + a.z);
-    best = min(best, (b + 3) * (b + 3) + a.w);
-    best = min(best, (b + 4) * (b + 4) + b4.x);
-    best = min(best, (b + 5) * (b + 5) + b4.y);
-    best = min(best, (b + 6) * (b + 6) + b4.z);
-    best = min(best, (b + 7) * (b + 7) + b4.w);
+    const int t = 2 * b;
+    int m = min(a.x, t + a.y);
+    m = min(min(m, t * 2 + a.z), t * 3 + a.w);
+    m = min(min(m, t * 4 + b4.x), t * 5 + b4.y);
+    m = min(min(m, t * 6 + b4.z), t * 7 + b4.w);
+    best = min(best, b * b + m);
 }
 
 // Staging the window and the divergence of per-lane searches are what the earlier versions of this kernel spent their time
@@ -969,7 +969,7 @@ __global__ void __launch_bounds__(256)
 uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __restrict__ d2, float* __restrict__ clearance,
                     float cellf, uint8_t* __restrict__ row_flag, int* __restrict__ any_flag) {
     __shared__ __align__(16) int sq[UAM_EDT_WIN];                      // g^2
-    __shared__ int sm[UAM_EDT_WIN / 8];                                // min of g^2 per group of 8 columns
+    __shared__ __align__(16) int sm[UAM_EDT_WIN / 8];                                // min of g^2 per group of 8 columns
     __shared__ int sm64[UAM_EDT_WIN / UAM_EDT_BLK];                    // ... per block of 64
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.y;
@@ -1000,8 +1000,8 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
             s8[2 * k] = g0 * g0;
             s8[2 * k + 1] = g1 * g1;
         }
-        *reinterpret_cast<int4*>(&sq[q * 8]) = make_int4(s8[0], s8[1], s8[2], s8[3]);
-        *reinterpret_cast<int4*>(&sq[q * 8 + 4]) = make_int4(s8[4], s8[5], s8[6], s8[7]);
+        *reinterpret_cast<int4*>(&sq[q * 8]) = make_int4(s8[0], s8[1] + 1, s8[2] + 4, s8[3] + 9);
+        *reinterpret_cast<int4*>(&sq[q * 8 + 4]) = make_int4(s8[4] + 16, s8[5] + 25, s8[6] + 36, s8[7] + 49);
         int m = min(min(min(s8[0], s8[1]), min(s8[2], s8[3])), min(min(s8[4], s8[5]), min(s8[6], s8[7])));
         sm[q] = m;
         // 8 consecutive groups = one 64-column block: consecutive lanes hold them (q = threadIdx.x + 256 k, 8 | 256)
@@ -1012,20 +1012,22 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
     }
     __syncthreads();
     bool unresolved = false;
+    int* d2row = d2 + (size_t)i * W + u0;
+    float* clrow = clearance ? clearance + (size_t)i * W + u0 : nullptr;
+    const int ncell = min(UAM_EDT_SPAN, W - u0);              // cells of this span inside the raster
 #pragma unroll 1
     for (int k = 0; k < UAM_EDT_SPAN / 256; ++k) {
         const int off0 = k * 256 + warp * 32;                 // the warp's first cell (a multiple of 32)
-        if (u0 + off0 >= W) break;                            // (warp-uniform)
+        if (off0 >= ncell) break;                             // (warp-uniform)
         const int c = UAM_EDT_R + off0 + lane;
-        const int qa = (UAM_EDT_R + off0) >> 3;               // the warp's four own groups: qa .. qa + 3
-        const bool live = u0 + off0 + lane < W;
+        const int qa = (UAM_EDT_R + off0) >> 3;               // the warp's four own groups: qa .. qa + 3 (qa is a multiple of 4)
+        const bool live = off0 + lane < ncell;
         // start: the own column; radii exchanged between the lanes (r >= the true distance, r + |l - k| bounds the neighbour's)
-        int best = sq[c];
+        int best = sq[c] - (lane & 7) * (lane & 7);           // g^2 of the own column (c = 8 q + (lane & 7))
         if (__all_sync(0xffffffffu, !live || best == 0)) {    // a warp inside an obstacle: nothing to search
             if (live) {
-                const size_t o = (size_t)i * W + u0 + off0 + lane;
-                d2[o] = 0;
-                if (clearance) clearance[o] = 0.0f;
+                d2row[off0 + lane] = 0;
+                if (clrow) clrow[off0 + lane] = 0.0f;
             }
             continue;
         }
@@ -1033,48 +1035,54 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, o) + o);
         best = live ? min(best, r * r) + 1 : 0;               // strictly above the minimum; a lane past the row's end wants nothing
-        // the warp's own groups, then outwards, one group on either side per step: left qa - d, right qa + 3 + d
+        // the warp's own 32 columns: groups qa .. qa + 3
+        {
+            const int4 m = *reinterpret_cast<const int4*>(&sm[qa]);
+            const int mm[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int q = qa + t;
-            const int D = max(max(q * 8 - c, c - (q * 8 + 7)), 0);
-            if (__any_sync(0xffffffffu, D * D + sm[q] < best)) uam_edt_scan_group(sq, q, c, best);
+            for (int t = 0; t < 4; ++t) {
+                const int D = max(max(8 * t - lane, lane - (8 * t + 7)), 0);
+                if (__any_sync(0xffffffffu, D * D + mm[t] < best)) uam_edt_scan_group(sq, qa + t, c, best);
+            }
         }
-        bool hit_edge = false;
-        constexpr int NQ = UAM_EDT_WIN / 8;
-        // hot loop: while both sides are inside the window there is nothing to check but the two votes per side
-        const int d_in = min(qa, NQ - 4 - qa);                // steps d = 1 .. d_in keep qa - d >= 0 and qa + 3 + d < NQ
-        int d = 1;
+        // outwards, one BLOCK of 32 columns (4 groups) on either side per step: left block t = groups qa - 4t .. qa - 4t + 3,
+        // right block t = groups qa + 4t .. qa + 4t + 3; both stay inside the window for t <= UAM_EDT_R / 32.  A step is one
+        // termination vote, two 16-byte loads of group minima and ONE vote whether any lane can gain from any of the 8 groups;
+        // only then are the groups looked at one by one, nearest first (ncu r02: the walk group by group spent 35 instructions per
+        // 8 columns and side on votes and addresses, 63 % of the kernel).
         bool done = false;
 #pragma unroll 1
-        for (; d <= d_in; ++d) {
-            const int ql = qa - d, qr = qa + 3 + d;
-            const int Dl = c - (ql * 8 + 7), Dr = qr * 8 - c;                       // both >= 1
-            const int Dm = min(Dl, Dr);
-            if (__all_sync(0xffffffffu, Dm * Dm >= best)) { done = true; break; }    // no farther group can win
-            if (__any_sync(0xffffffffu, Dl * Dl + sm[ql] < best)) uam_edt_scan_group(sq, ql, c, best);
-            if (__any_sync(0xffffffffu, Dr * Dr + sm[qr] < best)) uam_edt_scan_group(sq, qr, c, best);
+        for (int t = 1; t <= UAM_EDT_R / 32; ++t) {
+            const int DL = lane + 1 + 32 * (t - 1), DR = 32 * t - lane;       // distance to the nearest column of the left / right block
+            const int Dm = min(DL, DR);
+            if (__all_sync(0xffffffffu, Dm * Dm >= best)) { done = true; break; }    // no farther column can win
+            const int qL = qa - 4 * t, qR = qa + 4 * t;
+            const int4 mL = *reinterpret_cast<const int4*>(&sm[qL]);
+            const int4 mR = *reinterpret_cast<const int4*>(&sm[qR]);
+            // group g of the left block is 8 (3 - g) columns farther than DL, group g of the right block 8 g farther than DR
+            const int vL3 = DL * DL + mL.w, vL2 = (DL + 8) * (DL + 8) + mL.z, vL1 = (DL + 16) * (DL + 16) + mL.y, vL0 = (DL + 24) * (DL + 24) + mL.x;
+            const int vR0 = DR * DR + mR.x, vR1 = (DR + 8) * (DR + 8) + mR.y, vR2 = (DR + 16) * (DR + 16) + mR.z, vR3 = (DR + 24) * (DR + 24) + mR.w;
+            const int vmin = min(min(min(vL0, vL1), min(vL2, vL3)), min(min(vR0, vR1), min(vR2, vR3)));
+            if (!__any_sync(0xffffffffu, vmin < best)) continue;
+            if (__any_sync(0xffffffffu, vL3 < best)) uam_edt_scan_group(sq, qL + 3, c, best);
+            if (__any_sync(0xffffffffu, vR0 < best)) uam_edt_scan_group(sq, qR, c, best);
+            if (__any_sync(0xffffffffu, vL2 < best)) uam_edt_scan_group(sq, qL + 2, c, best);
+            if (__any_sync(0xffffffffu, vR1 < best)) uam_edt_scan_group(sq, qR + 1, c, best);
+            if (__any_sync(0xffffffffu, vL1 < best)) uam_edt_scan_group(sq, qL + 1, c, best);
+            if (__any_sync(0xffffffffu, vR2 < best)) uam_edt_scan_group(sq, qR + 2, c, best);
+            if (__any_sync(0xffffffffu, vL0 < best)) uam_edt_scan_group(sq, qL, c, best);
+            if (__any_sync(0xffffffffu, vR3 < best)) uam_edt_scan_group(sq, qR + 3, c, best);
         }
-        // rare: one side of the window is used up.  The other side is searched on (the clamped index rescans the last group,
-        // which is harmless); unresolved if some lane could still gain beyond the window and the raster goes on there
-#pragma unroll 1
-        for (; !done; ++d) {
-            const int ql = qa - d, qr = qa + 3 + d;
-            const int Dl = c - (ql * 8 + 7), Dr = qr * 8 - c;
-            const int Dm = min(Dl, Dr);
-            if (__all_sync(0xffffffffu, Dm * Dm >= best)) break;
-            if (ql < 0 && qr >= NQ) { hit_edge = true; break; }
-            if (ql < 0 && u0 - UAM_EDT_R > 0 && __any_sync(0xffffffffu, Dl * Dl < best)) hit_edge = true;
-            if (qr >= NQ && u0 + UAM_EDT_SPAN + UAM_EDT_R < W && __any_sync(0xffffffffu, Dr * Dr < best)) hit_edge = true;
-            const int qlc = max(ql, 0), qrc = min(qr, NQ - 1);
-            if (__any_sync(0xffffffffu, Dl * Dl + sm[qlc] < best)) uam_edt_scan_group(sq, qlc, c, best);
-            if (__any_sync(0xffffffffu, Dr * Dr + sm[qrc] < best)) uam_edt_scan_group(sq, qrc, c, best);
+        if (!done) {
+            // the window is used up on both sides (UAM_EDT_R columns): unresolved if some lane could still gain from a column
+            // beyond it and the raster goes on there
+            const int DL = lane + 1 + UAM_EDT_R, DR = UAM_EDT_R + 32 - lane;
+            const bool left_open = u0 + off0 - UAM_EDT_R > 0, right_open = u0 + off0 + 32 + UAM_EDT_R < W;
+            if ((left_open && __any_sync(0xffffffffu, DL * DL < best)) || (right_open && __any_sync(0xffffffffu, DR * DR < best))) unresolved = true;
         }
-        unresolved = unresolved || hit_edge;
         if (live) {
-            const size_t o = (size_t)i * W + u0 + off0 + lane;
-            d2[o] = best;
-            if (clearance) clearance[o] = uam_clearance_of(best, cellf);
+            d2row[off0 + lane] = best;
+            if (clrow) clrow[off0 + lane] = uam_clearance_of(best, cellf);
         }
     }
     if (__syncthreads_or(unresolved) && threadIdx.x == 0) {
