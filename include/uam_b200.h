@@ -112,6 +112,10 @@ enum {
                                          form of the layer kernel (coarse spans from 32 sample columns per row).  Same bits in every mode */
     UAM_OPT_CCL_TILES = 11,           /* 1 (default): uam_label_components labels 32 x 32-cell tiles in shared memory first and unites only
                                          the pairs across tile borders in HBM; 0: global union-find over all cells (round 1).  Same labels */
+    UAM_OPT_GRID_GRAPH = 12,          /* 1 (default): the relaxation rounds of uam_grid_search* are looped on the device -- one CUDA graph
+                                         with a WHILE conditional node whose body is a round (min key, selection, tile relaxation) and a
+                                         one-thread kernel that re-arms the loop while tiles are pending; 0: the host enqueues the rounds
+                                         and reads the active count back every 8 rounds.  Same results */
     UAM_OPT_SHAPE_GRID = 9            /* 1 (default): the analytic scorer / point queries look up per-cell candidate lists over
                                          the shapes (a shape with one inequality > max(e, 1e-14) on a whole cell contributes
                                          exact zeros there and is left out; same bits).  0: every shape at every point */
@@ -123,7 +127,9 @@ enum { UAM_STAT_SCORE_KERNEL_MS_MEAN = 1, UAM_STAT_SCORE_KERNEL_COUNT = 2,
           relaxing the 8 in-plane edges of its cells), relaxation rounds */
        UAM_STAT_GRID_ACTIVATIONS = 3, UAM_STAT_GRID_SWEEPS = 4, UAM_STAT_GRID_ROUNDS = 5,
        /* shape grid of the analytic scorer (UAM_OPT_SHAPE_GRID) as last built: cells (0 = none) and list entries in all */
-       UAM_STAT_SHAPE_GRID_CELLS = 6, UAM_STAT_SHAPE_GRID_ITEMS = 7 };
+       UAM_STAT_SHAPE_GRID_CELLS = 6, UAM_STAT_SHAPE_GRID_ITEMS = 7,
+       /* what the host enqueued for the last uam_grid_search*: kernel launches + memsets + graph launches (UAM_OPT_GRID_GRAPH) */
+       UAM_STAT_GRID_HOST_SUBMISSIONS = 8 };
 int uam_ctx_get_stat(uam_ctx* ctx, int stat, double* value);
 int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value);
 

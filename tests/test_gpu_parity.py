@@ -679,6 +679,16 @@ def test_grid_search_exact(uam, torch, H, W, wall):
     assert (dist[3] == 2 ** 62).all() and (parent[3] == -1).all()
     d2, _ = uam.Engine().grid_search(torch.from_numpy(cost).cuda(), srcs[:1], None, want_parent=False)
     assert np.array_equal(d2[0].cpu().numpy(), orc.grid_search(cost, tuple(srcs[0]), None)[0])
+    # the round loop on the device (one CUDA graph with a WHILE node: the default) against the host-driven loop: same bits,
+    # and the host enqueues a handful of items instead of five per round
+    subs = {}
+    for graph in (1, 0):
+        eng = uam.Engine()
+        eng.set_option('grid_graph', graph)
+        dg, pg = eng.grid_search(torch.from_numpy(cost).cuda(), srcs, torch.from_numpy(blocked).cuda())
+        assert np.array_equal(dg.cpu().numpy(), dist) and np.array_equal(pg.cpu().numpy(), parent)
+        subs[graph] = (eng.get_stat('grid_host_submissions'), eng.get_stat('grid_rounds'))
+    assert subs[1][0] <= 7 and subs[1][1] >= 1 and subs[0][0] >= 5 * subs[0][1]
 
 
 def test_grid_search_zero_cost_plateaus(uam, torch):

@@ -107,6 +107,7 @@ extern "C" int uam_ctx_create(int device, uam_ctx** out) {
     // tuning knobs from the environment (bench A/B runs); uam_ctx_set_option overrides
     if (const char* e = getenv("UAM_RASTER_LAYOUT")) ctx->raster_layout = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = std::min(3, std::max(-1, atoi(e)));
+    if (const char* e = getenv("UAM_GRID_GRAPH")) ctx->grid_graph = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_GRID_DELTA")) ctx->grid_delta = std::max(0ll, atoll(e));
     if (const char* e = getenv("UAM_BIN_CHUNK")) ctx->bin_chunk = std::min(1 << 20, std::max(1024, atoi(e)));
     if (const char* e = getenv("UAM_BIN_PT")) ctx->bin_pt = atoi(e);
@@ -139,6 +140,10 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
         case UAM_OPT_GRID_DELTA:
             if (value < 0) return uam_fail(ctx, UAM_ERR_INVALID, "grid delta must be >= 0");
             ctx->grid_delta = (long long)value;
+            return UAM_OK;
+        case UAM_OPT_GRID_GRAPH:
+            if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "grid graph must be 0 or 1");
+            ctx->grid_graph = (int)value;
             return UAM_OK;
         case UAM_OPT_COMBINE_LAYERS:
             if (value < 0 || value > 2) return uam_fail(ctx, UAM_ERR_INVALID, "combine_layers must be 0, 1 or 2");
@@ -223,6 +228,7 @@ extern "C" int uam_ctx_get_stat(uam_ctx* ctx, int stat, double* value) {
         case UAM_STAT_GRID_ACTIVATIONS: *value = ctx->grid_activations; return UAM_OK;
         case UAM_STAT_GRID_SWEEPS: *value = ctx->grid_sweeps; return UAM_OK;
         case UAM_STAT_GRID_ROUNDS: *value = ctx->grid_rounds; return UAM_OK;
+        case UAM_STAT_GRID_HOST_SUBMISSIONS: *value = ctx->grid_host_submissions; return UAM_OK;
         case UAM_STAT_SHAPE_GRID_CELLS: *value = (double)ctx->shape_grid.G * ctx->shape_grid.G; return UAM_OK;
         case UAM_STAT_SHAPE_GRID_ITEMS: *value = ctx->shape_grid.G ? (double)ctx->grid_items_total : 0.0; return UAM_OK;
         default:

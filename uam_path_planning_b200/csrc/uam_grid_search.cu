@@ -502,6 +502,15 @@ int uam_grid_mean_cost(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_bl
     return UAM_OK;
 }
 
+// Tail of one relaxation round inside the CUDA-graph WHILE loop: another round unless the selection found no tile (or the
+// safety cap is hit).  stats[2] counts the rounds.
+__global__ void uam_k_grid_loop_cond(cudaGraphConditionalHandle handle, const unsigned* __restrict__ count,
+                                     unsigned long long* __restrict__ stats, unsigned long long max_rounds) {
+    const unsigned long long r = stats[2] + 1ull;
+    stats[2] = r;
+    cudaGraphSetConditional(handle, (*count != 0u && r < max_rounds) ? 1u : 0u);
+}
+
 int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int bands, int H, int W,
                          const int32_t* d_sources, int src_stride, int Q, int64_t* d_dist, int32_t* d_parent, void* stream,
                          const int32_t* d_goals = nullptr) {
@@ -520,7 +529,7 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     const size_t tiles = (size_t)g.tiles_x * g.tiles_y;
     const size_t n_flags = tiles * bands * Q;
     if (n_flags >= 0xffffffffull) return uam_fail(ctx, UAM_ERR_UNSUPPORTED, "too many (query, band, tile) triples");
-    // scratch: keys (u64) | list_key (u64) | minkey (u64 x Q) | stats (u64 x 2) | goal_at (i64 x Q) | list (u32) | count (u32 x 2)
+    // scratch: keys (u64) | list_key (u64) | minkey (u64 x Q) | stats (u64 x 4) | goal_at (i64 x Q) | list (u32) | count (u32 x 2)
     UAM_TRY(uam_reserve(ctx, &ctx->d_scratch, &ctx->scratch_bytes, n_flags * 20 + (size_t)Q * 16 + 256));
     unsigned long long* keys = (unsigned long long*)ctx->d_scratch;
     // delta = cost of crossing about two tiles at the grid's mean cell cost (ordering only: any value gives the same result)
@@ -542,10 +551,10 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     unsigned long long* list_key = keys + n_flags;
     unsigned long long* minkey = list_key + n_flags;
     unsigned long long* stats = minkey + Q;
-    long long* goal_at = (long long*)(stats + 2);
+    long long* goal_at = (long long*)(stats + 4);
     unsigned* list = (unsigned*)(goal_at + Q);
     unsigned* count = list + n_flags;
-    UAM_CUDA(ctx, cudaMemsetAsync(stats, 0, 16, st));
+    UAM_CUDA(ctx, cudaMemsetAsync(stats, 0, 32, st));
     const int grid_fill = ctx->sm_count * 16;
     uam_k_grid_init<<<grid_fill, 256, 0, st>>>((long long*)d_dist, (size_t)H * W * bands * Q);
     UAM_CHECK_LAUNCH(ctx, "uam_k_grid_init");
@@ -565,17 +574,80 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     const long long max_rounds = 1ll << 40;      // the loop ends when no key is pending
     unsigned h_count = 1;
     long long rounds_done = 0;
-    for (long long round = 0; round < max_rounds && h_count; ++round) {
-        rounds_done = round + 1;
-        UAM_CUDA(ctx, cudaMemsetAsync(count, 0, 4, st));
-        UAM_CUDA(ctx, cudaMemsetAsync(minkey, 0xff, (size_t)Q * 8, st));
-        uam_k_grid_minkey<<<Q * parts, 256, 0, st>>>(keys, per_q, parts, minkey);
+    // one relaxation round: every argument lives in device memory and none changes from round to round
+    auto enqueue_round = [&](cudaStream_t s) -> int {
+        UAM_CUDA(ctx, cudaMemsetAsync(count, 0, 4, s));
+        UAM_CUDA(ctx, cudaMemsetAsync(minkey, 0xff, (size_t)Q * 8, s));
+        uam_k_grid_minkey<<<Q * parts, 256, 0, s>>>(keys, per_q, parts, minkey);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_minkey");
-        uam_k_grid_select<<<ctx->sm_count * 4, 256, 0, st>>>(keys, n_flags, per_q, minkey, delta, list, list_key, count,
-                                                             (const long long*)d_dist, d_goals ? goal_at : nullptr);
+        uam_k_grid_select<<<ctx->sm_count * 4, 256, 0, s>>>(keys, n_flags, per_q, minkey, delta, list, list_key, count,
+                                                            (const long long*)d_dist, d_goals ? goal_at : nullptr);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_select");
-        uam_k_grid_relax<<<grid_relax, UAM_GRID_WARPS * 32, smem, st>>>(d_cost, d_blocked, g, list, list_key, count, (long long*)d_dist, keys, stats);
+        uam_k_grid_relax<<<grid_relax, UAM_GRID_WARPS * 32, smem, s>>>(d_cost, d_blocked, g, list, list_key, count, (long long*)d_dist, keys, stats);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_relax");
+        return UAM_OK;
+    };
+    // The round loop runs ON THE DEVICE: a CUDA graph whose only top-level node is a WHILE conditional node; its body is one
+    // round (captured from the launches above) + a one-thread kernel that keeps the loop going while the selection still finds
+    // tiles.  One graph launch per call instead of ~5 launches per round and a host read-back of the active count every 8 rounds
+    // (round 1: 5 496 launches and 472 host-synchronised rounds for one 64-query call).  Falls back to the host loop if the
+    // graph cannot be built (UAM_OPT_GRID_GRAPH = 0 forces that).
+    bool looped = false;
+    if (ctx->grid_graph) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaStream_t cap = nullptr;
+        bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess;
+        cudaGraphConditionalHandle handle = 0;
+        ok = ok && cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+        cudaGraph_t body = nullptr;
+        if (ok) {
+            cudaGraphNodeParams np = {};
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = handle;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            cudaGraphNode_t node;
+            ok = cudaGraphAddNode(&node, graph, nullptr, 0, &np) == cudaSuccess;
+            if (ok) body = np.conditional.phGraph_out[0];
+        }
+        ok = ok && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess;
+        if (ok) {
+            ok = cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok) {
+                const int rc = enqueue_round(cap);
+                uam_k_grid_loop_cond<<<1, 1, 0, cap>>>(handle, count, stats, 1ull << 24);
+                cudaGraph_t captured = nullptr;
+                ok = cudaStreamEndCapture(cap, &captured) == cudaSuccess && rc == UAM_OK;
+            }
+        }
+        ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (ok) {
+            ok = cudaGraphLaunch(exec, st) == cudaSuccess;
+            if (ok) {
+                unsigned long long h_rounds = 0;
+                ok = cudaMemcpyAsync(&h_count, count, 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                     cudaMemcpyAsync(&h_rounds, stats + 2, 8, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                     cudaStreamSynchronize(st) == cudaSuccess;
+                rounds_done = (long long)h_rounds;
+                if (h_rounds) ctx->launches += 4ull * h_rounds - 3ull;      // kernels the loop ran (3 were counted during the capture)
+                if (!ok) {                      // the loop itself failed: nothing to fall back to
+                    if (exec) cudaGraphExecDestroy(exec);
+                    if (graph) cudaGraphDestroy(graph);
+                    if (cap) cudaStreamDestroy(cap);
+                    return uam_fail(ctx, UAM_ERR_CUDA, "grid search graph loop failed: %s", cudaGetErrorString(cudaGetLastError()));
+                }
+                looped = true;
+            }
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (cap) cudaStreamDestroy(cap);
+        if (!looped) (void)cudaGetLastError();      // graph not available: clear the error, run the host loop
+    }
+    for (long long round = 0; !looped && round < max_rounds && h_count; ++round) {
+        rounds_done = round + 1;
+        UAM_TRY(enqueue_round(st));
         if ((round & 7) == 7) {     // termination check every 8 rounds: rounds with an empty list are no-ops
             UAM_CUDA(ctx, cudaMemcpyAsync(&h_count, count, 4, cudaMemcpyDeviceToHost, st));
             UAM_CUDA(ctx, cudaStreamSynchronize(st));
@@ -589,6 +661,8 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
         ctx->grid_activations = (double)h_stats[0];
         ctx->grid_sweeps = (double)h_stats[1];
         ctx->grid_rounds = (double)rounds_done;
+        // set-up (memset, 2 x init, seed [, goal index]) + the rounds (one graph launch, or 2 memsets + 3 kernels per round) [+ parent]
+        ctx->grid_host_submissions = 4.0 + (d_goals ? 1.0 : 0.0) + (looped ? 1.0 : 5.0 * (double)rounds_done) + (d_parent ? 1.0 : 0.0);
     }
     if (d_parent) {
         uam_k_grid_parent<<<grid_fill, 256, 0, st>>>(d_cost, g, (const long long*)d_dist, d_sources, d_parent);

@@ -152,10 +152,12 @@ struct uam_ctx {
     double time_sum_ms = 0.0;
     uint64_t time_count = 0;
     long long grid_delta = 0;           // UAM_OPT_GRID_DELTA (0 = automatic)
+    int grid_graph = 1;                 // UAM_OPT_GRID_GRAPH: relaxation rounds looped on the device (CUDA graph WHILE node)
     int bin_chunk = 8192;               // ... segments per CTA of the histogram / scatter kernels (UAM_BIN_CHUNK, A/B runs only)
     int bin_pt = 2;                     // ... paths a warp of the histogram kernel works on at a time (UAM_BIN_PT: 1, 2, 4)
     int bin_shift = 7;                  // binned raster scorer: bin side = 2^bin_shift cells (UAM_BIN_SHIFT, A/B runs only)
     double grid_activations = 0, grid_sweeps = 0, grid_rounds = 0;   // counted work of the last uam_grid_search*
+    double grid_host_submissions = 0;   // ... and what the host enqueued for it (kernel launches + memsets + graph launches)
     void* d_bin_scratch[UAM_HOST_PIPE_DEPTH + 1] = {};   // binned raster scorer: [0] caller stream, [1..] pipeline stages
     size_t bin_scratch_bytes[UAM_HOST_PIPE_DEPTH + 1] = {};
     // tile-staged raster scorer (variant 3): tile-major copy of the texels (built on first use) + piece scratch
