@@ -466,7 +466,7 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
 
     def e2e_loop(submit):
-        for i in range(2):                                               # warm-up (staging allocation)
+        for i in range(4):                                               # warm-up: every slot of the 3-deep ring allocates its staging / scratch once
             rm.wait(submit(i))
         torch.cuda.synchronize()
         if world > 1:
