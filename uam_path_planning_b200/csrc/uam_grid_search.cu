@@ -188,7 +188,7 @@ __device__ __forceinline__ bool uam_grid_row_step(int* __restrict__ D, const int
 __global__ void __launch_bounds__(UAM_GRID_WARPS * 32)
 uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ blocked, UamGridGeo g,
                  const unsigned* __restrict__ list, const unsigned long long* __restrict__ list_key,
-                 const unsigned* __restrict__ count, long long* __restrict__ dist, unsigned long long* __restrict__ keys,
+                 unsigned* __restrict__ count, long long* __restrict__ dist, unsigned long long* __restrict__ keys,
                  unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char uam_grid_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -208,7 +208,13 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
         span_l[s] = lane >= o ? (below & ~((2u << (lane - o)) - 1u)) : 0xffffffffu;
         span_r[s] = lane + o < 32 ? (((2u << (lane + o)) - 1u) & ~below) : 0xffffffffu;
     }
-    for (unsigned w = blockIdx.x * UAM_GRID_WARPS + warp; w < n; w += gridDim.x * UAM_GRID_WARPS) {
+    // the entries are handed out through a counter (count[1], zeroed with the list length): activations differ widely in
+    // length (1 .. a dozen double sweeps), a fixed share per warp would leave the round waiting for the unluckiest warp
+    for (;;) {
+        unsigned w = 0;
+        if (lane == 0) w = atomicAdd(count + 1, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n) break;
         const unsigned ent = list[w];
         long long key = (long long)list_key[w];
         const unsigned qb = ent / tiles, tile = ent - qb * tiles;
@@ -576,7 +582,7 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     long long rounds_done = 0;
     // one relaxation round: every argument lives in device memory and none changes from round to round
     auto enqueue_round = [&](cudaStream_t s) -> int {
-        UAM_CUDA(ctx, cudaMemsetAsync(count, 0, 4, s));
+        UAM_CUDA(ctx, cudaMemsetAsync(count, 0, 8, s));
         UAM_CUDA(ctx, cudaMemsetAsync(minkey, 0xff, (size_t)Q * 8, s));
         uam_k_grid_minkey<<<Q * parts, 256, 0, s>>>(keys, per_q, parts, minkey);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_minkey");
