@@ -971,6 +971,8 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
     __shared__ __align__(16) int sq[UAM_EDT_WIN];                      // g^2
     __shared__ __align__(16) int sm[UAM_EDT_WIN / 8];                                // min of g^2 per group of 8 columns
     __shared__ int sm64[UAM_EDT_WIN / UAM_EDT_BLK];                    // ... per block of 64
+    __shared__ int s_next;                                             // next 32-cell chunk of the span
+    if (threadIdx.x == 0) s_next = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.y;
     const int u0 = blockIdx.x * UAM_EDT_SPAN;
@@ -1015,9 +1017,12 @@ uam_k_edt_rows_fast(const unsigned short* __restrict__ g, int H, int W, int* __r
     int* d2row = d2 + (size_t)i * W + u0;
     float* clrow = clearance ? clearance + (size_t)i * W + u0 : nullptr;
     const int ncell = min(UAM_EDT_SPAN, W - u0);              // cells of this span inside the raster
+    // the 32-cell chunks of the span are handed out through a shared-memory counter: the warps inside obstacles are done at once
 #pragma unroll 1
-    for (int k = 0; k < UAM_EDT_SPAN / 256; ++k) {
-        const int off0 = k * 256 + warp * 32;                 // the warp's first cell (a multiple of 32)
+    for (;;) {
+        int kk = 0;
+        if (lane == 0) kk = atomicAdd(&s_next, 1);
+        const int off0 = __shfl_sync(0xffffffffu, kk, 0) * 32;     // the warp's first cell (a multiple of 32)
         if (off0 >= ncell) break;                             // (warp-uniform)
         const int c = UAM_EDT_R + off0 + lane;
         const int qa = (UAM_EDT_R + off0) >> 3;               // the warp's four own groups: qa .. qa + 3 (qa is a multiple of 4)
