@@ -518,11 +518,11 @@ __device__ __noinline__ void uam_layers_rows_sampled(double (*acc_all)[UAM_SUPER
                                                         const UamRegionRanges2& rr, int n_regions, int H, int W, double x0,
                                                         double dx, double y0, double dy, double e,
                                                         const int* __restrict__ coarse_list, const int* __restrict__ coarse_count,
-                                                        int n_super, float* __restrict__ layers) {
+                                                        int n_super, float* __restrict__ layers, int sup, int i0, int rows) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
     double* acc = acc_all[warp];
-    const int sup = blockIdx.y * gridDim.x + blockIdx.x;
-    const int j0 = blockIdx.x * UAM_SUPER, i0 = blockIdx.y * UAM_SUPER;
+    const int j0 = blockIdx.x * UAM_SUPER;
     const int ncols = min(UAM_SUPER, W - j0);
     const size_t plane = (size_t)H * W;
     // sample columns: 0 .. ncols - 1 inclusive
@@ -530,7 +530,7 @@ __device__ __noinline__ void uam_layers_rows_sampled(double (*acc_all)[UAM_SUPER
     const int sj_prev = lane > 0 ? ((lane - 1) * (ncols - 1)) / 31 : -1;
     const int sj_next = lane < 31 ? ((lane + 1) * (ncols - 1)) / 31 : ncols;
     const double xs = uam_cell_centre(j0 + sj, x0, dx);
-    for (int row = warp; row < UAM_SUPER; row += 8) {
+    for (int row = warp; row < rows; row += nwarps) {
         const int i = i0 + row;
         if (i >= H) break;
         const double y = uam_cell_centre(i, y0, dy);
@@ -602,7 +602,8 @@ uam_k_layers_rows(const UamEdge* __restrict__ edges, const UamShape* __restrict_
                   const int* __restrict__ coarse_list, const int* __restrict__ coarse_count, int n_super,
                   float* __restrict__ layers) {
     __shared__ double acc_all[8][UAM_SUPER];
-    uam_layers_rows_sampled(acc_all, edges, shapes, psic, rr, n_regions, H, W, x0, dx, y0, dy, e, coarse_list, coarse_count, n_super, layers);
+    uam_layers_rows_sampled(acc_all, edges, shapes, psic, rr, n_regions, H, W, x0, dx, y0, dy, e, coarse_list, coarse_count, n_super, layers,
+                            blockIdx.y * gridDim.x + blockIdx.x, blockIdx.y * UAM_SUPER, UAM_SUPER);
 }
 
 // Cells [lo, hi) of one raster row against a shape of NE straight edges (records at ed[0 .. NE)): the row constants of every
@@ -676,17 +677,18 @@ __device__ __forceinline__ bool uam_layers_cells_lines(const UamEdge* __restrict
 // regions (their intervals would not fit) runs the sampled form.
 #define UAM_IV_CAP 60
 #define UAM_IV_EMPTY 1u          // lo | (hi - 1) << 8 with hi - 1 < lo
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <int MINB, int ROWS>          // ROWS rows of a supertile per CTA (256 or 128), one thread per row in phase A
+__global__ void __launch_bounds__(ROWS, MINB)
 uam_k_layers_iv(const UamEdge* __restrict__ edges, const UamShape* __restrict__ shapes, const double* __restrict__ psic,
                 const __grid_constant__ UamRegionRanges2 rr, int n_regions, int H, int W, double x0, double dx, double y0, double dy, double e,
                 const int* __restrict__ coarse_list, const int* __restrict__ coarse_count, int n_super,
                 float* __restrict__ layers) {
-    __shared__ double acc_all[8][UAM_SUPER];
-    __shared__ unsigned short iv[UAM_IV_CAP][UAM_SUPER];
+    __shared__ double acc_all[ROWS / 32][UAM_SUPER];
+    __shared__ unsigned short iv[UAM_IV_CAP][ROWS];
     __shared__ int s_ncand[UAM_MAX_REGIONS];
     __shared__ const int* s_cand[UAM_MAX_REGIONS];
-    const int sup = blockIdx.y * gridDim.x + blockIdx.x;
+    const int i0 = blockIdx.y * ROWS;
+    const int sup = (i0 / UAM_SUPER) * gridDim.x + blockIdx.x;
     int n_all = 0;
     for (int r = 0; r < n_regions; ++r) n_all += coarse_count[r * n_super + sup];
     if (threadIdx.x < n_regions) {
@@ -695,11 +697,12 @@ uam_k_layers_iv(const UamEdge* __restrict__ edges, const UamShape* __restrict__ 
         s_cand[r] = coarse_list + (size_t)n_super * (rr.begin[r] - rr.begin[0]) + (size_t)sup * (rr.begin[r + 1] - rr.begin[r]);
     }
     if (n_all > UAM_IV_CAP) {          // (CTA-uniform)
-        uam_layers_rows_sampled(acc_all, edges, shapes, psic, rr, n_regions, H, W, x0, dx, y0, dy, e, coarse_list, coarse_count, n_super, layers);
+        uam_layers_rows_sampled(acc_all, edges, shapes, psic, rr, n_regions, H, W, x0, dx, y0, dy, e, coarse_list, coarse_count, n_super, layers,
+                                sup, i0, ROWS);
         return;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j0 = blockIdx.x * UAM_SUPER, i0 = blockIdx.y * UAM_SUPER;
+    const int j0 = blockIdx.x * UAM_SUPER;
     const int ncols = min(UAM_SUPER, W - j0);
     const size_t plane = (size_t)H * W;
     // phase A: thread = row
@@ -734,7 +737,7 @@ uam_k_layers_iv(const UamEdge* __restrict__ edges, const UamShape* __restrict__ 
     // phase B: warp = row
     double* acc = acc_all[warp];
     const bool vec = (W & 3) == 0 && (ncols & 3) == 0 && ((((uintptr_t)layers) & 15) == 0);
-    for (int row = warp; row < UAM_SUPER; row += 8) {
+    for (int row = warp; row < ROWS; row += ROWS / 32) {
         const int i = i0 + row;
         if (i >= H) break;
         const double y = uam_cell_centre(i, y0, dy);
@@ -1319,13 +1322,17 @@ extern "C" int uam_rasterize_layers(uam_ctx* ctx, int H, int W, double x0, doubl
         return UAM_OK;
     }
     if (scan) {
-        static const int minb = getenv("UAM_LAYERS_MINB") ? atoi(getenv("UAM_LAYERS_MINB")) : 2;      // (A/B runs only)
-        if (minb == 3) uam_k_layers_iv<3><<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
-                                                                  y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
-        else if (minb == 2) uam_k_layers_iv<2><<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
-                                                                       y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
-        else uam_k_layers_iv<4><<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
-                                                       y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
+        // half supertiles (128 rows, 128 threads) per CTA: twice the CTAs of half the length -- the kernel ends with the last heavy
+        // supertile, ncu r02: the SMs were busy 90 % of its time with whole supertiles.  (UAM_LAYERS_ROWS = 256: A/B runs only)
+        static const int rows = getenv("UAM_LAYERS_ROWS") ? atoi(getenv("UAM_LAYERS_ROWS")) : 128;
+        if (rows == 256) {
+            uam_k_layers_iv<2, 256><<<sgrid, 256, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
+                                                           y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
+        } else {
+            dim3 hgrid(sgrid.x, (H + 127) / 128);
+            uam_k_layers_iv<4, 128><<<hgrid, 128, 0, st>>>(ctx->d_edges, ctx->d_shapes, ctx->d_psic, rr, ctx->n_regions, H, W, x0, dx,
+                                                           y0, dy, enlargement, clist, ccount, (int)n_super, d_layers);
+        }
         UAM_CHECK_LAUNCH(ctx, "uam_k_layers_iv");
         return UAM_OK;
     }
