@@ -340,6 +340,47 @@ def test_scanline_rasterisers_equal_per_cell_evaluation(uam, torch, H, W, geo):
     assert not bool(torch.isnan(res[1][3]).any()) and bool(torch.isnan(res[1][4][1]).all())        # the slivers are in region B
 
 
+def test_layer_rasteriser_crowded_supertile(uam, torch):
+    """More candidate shapes on one 256 x 256-cell supertile than the interval form keeps row intervals for (60 over all
+    regions): those supertiles run the sampled row form inside the same launch.  Bits equal to the per-cell kernel, with
+    rectangles, triangles (3 straight edges), pentagons (generic loop), ellipses and boxes mixed, for both CTA shapes."""
+    rng = np.random.default_rng(4242)
+    m = uam.RegionMap()
+    for r in ('A', 'B'):
+        m.new_region(r, 'r')
+    for k in range(150):
+        c = rng.uniform(1.0, 9.0, 2)
+        t = k % 5
+        if t == 0:
+            a = rng.uniform(0, np.pi)
+            R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+            hw, hh = rng.uniform(0.2, 2.0, 2)
+            sh = uam.polygon(*(c + np.array([[-hw, -hh], [hw, -hh], [hw, hh], [-hw, hh]]) @ R.T).tolist())
+        elif t == 1:
+            sh = uam.polygon(*(c + rng.uniform(-1.5, 1.5, (3, 2))).tolist())
+        elif t == 2:
+            ang = np.sort(rng.uniform(0, 2 * np.pi, 5))
+            sh = uam.polygon(*(c + 1.2 * np.stack([np.cos(ang), np.sin(ang)], 1)).tolist())
+        elif t == 3:
+            sh = uam.ball(c.tolist(), float(rng.uniform(0.2, 2.0)), float(rng.uniform(0.2, 2.0)))
+        else:
+            sh = uam.square(c.tolist(), float(rng.uniform(0.2, 1.5)), float(rng.uniform(0.2, 1.5)))
+        m.add_obstacle(sh)
+        m.add_shape_to_region('AB'[k % 2], sh)
+    eng = m.engine()
+    for H, W, geo in [(300, 300, (0.0, 10.0 / 300, 0.0, 10.0 / 300)), (520, 700, (0.0, 10.0 / 700, 10.0, -10.0 / 520))]:
+        ref = None
+        for mode in (0, 1, 3):
+            eng.set_option('rasterizer', mode)
+            lay = [eng.rasterize_layers(H, W, geo, e) for e in (0.0, 0.05)]
+            if ref is None:
+                ref = lay
+                assert float((lay[0] != 0).float().mean()) > 0.5
+            else:
+                for a, b in zip(ref, lay):
+                    assert torch.equal(a.view(torch.int32), b.view(torch.int32)), mode
+
+
 def test_dem_mask(uam, torch):
     rng = np.random.default_rng(3)
     eng = uam.Engine()

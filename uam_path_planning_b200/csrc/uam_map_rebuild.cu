@@ -669,7 +669,7 @@ __device__ __forceinline__ bool uam_layers_cells_lines(const UamEdge* __restrict
 // or not (ncu r02: 2.8 ms at 16384^2, issue-bound, the fp64 pipe a quarter busy) -- is done here the way the occupancy
 // kernel does it: phase A, THREAD per row of the supertile: for every candidate shape of every region the thread finds the
 // row's exact interval of cells with all h_i - e < 0 by bisection with the exact predicate (uam_row_interval_edge<1>, ~9
-// evaluations per inequality, 32 rows per warp instruction) and leaves it in shared memory (2 bytes per (row, candidate));
+// evaluations per inequality, 32 rows per warp instruction) and leaves it in shared memory (2 bytes per (row, candidate), up to UAM_IV_CAP x 256 / ROWS candidates);
 // phase B, WARP per row: only the cells of the interval are evaluated (they are exactly the cells where psi != 0), lanes =
 // columns, same per-cell arithmetic and shape order as every other form, so the same bits.  Shapes of up to 4 straight edges
 // (rectangular footprints, triangles) keep their row constants {Ax, By - Ay, (Bx - Ax)(y - Ay), -sgn} in registers: no
@@ -684,7 +684,8 @@ uam_k_layers_iv(const UamEdge* __restrict__ edges, const UamShape* __restrict__ 
                 const int* __restrict__ coarse_list, const int* __restrict__ coarse_count, int n_super,
                 float* __restrict__ layers) {
     __shared__ double acc_all[ROWS / 32][UAM_SUPER];
-    __shared__ unsigned short iv[UAM_IV_CAP][ROWS];
+    constexpr int CAP = UAM_IV_CAP * (UAM_SUPER / ROWS);               // 60 candidates with whole supertiles, 120 with halves
+    __shared__ unsigned short iv[CAP][ROWS];
     __shared__ int s_ncand[UAM_MAX_REGIONS];
     __shared__ const int* s_cand[UAM_MAX_REGIONS];
     const int i0 = blockIdx.y * ROWS;
@@ -696,7 +697,7 @@ uam_k_layers_iv(const UamEdge* __restrict__ edges, const UamShape* __restrict__ 
         s_ncand[r] = coarse_count[r * n_super + sup];
         s_cand[r] = coarse_list + (size_t)n_super * (rr.begin[r] - rr.begin[0]) + (size_t)sup * (rr.begin[r + 1] - rr.begin[r]);
     }
-    if (n_all > UAM_IV_CAP) {          // (CTA-uniform)
+    if (n_all > CAP) {                 // (CTA-uniform)
         uam_layers_rows_sampled(acc_all, edges, shapes, psic, rr, n_regions, H, W, x0, dx, y0, dy, e, coarse_list, coarse_count, n_super, layers,
                                 sup, i0, ROWS);
         return;
