@@ -225,7 +225,7 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
         const uint16_t* cb = cost + (size_t)b * cells;
         const uint8_t* bb = blocked ? blocked + (size_t)b * cells : nullptr;
         long long m_all = UAM_GRID_INF, m_top = UAM_GRID_INF, m_bot = UAM_GRID_INF, m_side = UAM_GRID_INF;   // m_side: this lane's column
-        unsigned n_sweeps = 0;
+        unsigned n_half = 0;                      // half sweeps (32 row steps each)
         for (;;) {                               // one trip unless some cell sits 10^9 above the key (see above)
             long long far_min = UAM_GRID_INF;
             __syncwarp();
@@ -298,20 +298,31 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
             }
             __syncwarp();
             // ---- Gauss-Seidel sweeps to the local fixed point -----------------------------------------------------------
-            bool changed;
-            do {
-                bool ch = false;
-                ++n_sweeps;
-                for (int li = 1; li <= GT; ++li) {
-                    ch |= uam_grid_row_step(D, C, li, li - 1, lane, below, span_l, span_r);
-                    __syncwarp();
+            // The tile is at its fixed point when a top-down and a bottom-up sweep IN A ROW move nothing (the first leaves the
+            // state as it was, so the second has checked the same state): the loop ends after two quiet half sweeps, whichever
+            // direction comes last -- not only after a quiet top-down + bottom-up pair, which cost half a double sweep more per
+            // activation on average.
+            {
+                int quiet = 0;
+                for (;;) {
+                    bool ch = false;
+                    ++n_half;
+                    for (int li = 1; li <= GT; ++li) {
+                        ch |= uam_grid_row_step(D, C, li, li - 1, lane, below, span_l, span_r);
+                        __syncwarp();
+                    }
+                    quiet = __any_sync(0xffffffffu, ch) ? 0 : quiet + 1;
+                    if (quiet >= 2) break;
+                    ch = false;
+                    ++n_half;
+                    for (int li = GT; li >= 1; --li) {
+                        ch |= uam_grid_row_step(D, C, li, li + 1, lane, below, span_l, span_r);
+                        __syncwarp();
+                    }
+                    quiet = __any_sync(0xffffffffu, ch) ? 0 : quiet + 1;
+                    if (quiet >= 2) break;
                 }
-                for (int li = GT; li >= 1; --li) {
-                    ch |= uam_grid_row_step(D, C, li, li + 1, lane, below, span_l, span_r);
-                    __syncwarp();
-                }
-                changed = __any_sync(0xffffffffu, ch);
-            } while (changed);
+            }
             // ---- write back the cells that dropped; smallest dropped value per side ------------------------------------
             {
                 const int lj = lane + 1;
@@ -364,7 +375,7 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
         }
         if (lane == 0) {                      // counted work: tile activations, double sweeps
             atomicAdd(&stats[0], 1ull);
-            atomicAdd(&stats[1], (unsigned long long)n_sweeps);
+            atomicAdd(&stats[1], (unsigned long long)n_half);
         }
         if (m_all < UAM_GRID_INF) {
             unsigned long long* kq = keys + (size_t)q * g.bands * tiles;
@@ -665,7 +676,7 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
         UAM_CUDA(ctx, cudaMemcpyAsync(h_stats, stats, 16, cudaMemcpyDeviceToHost, st));
         UAM_CUDA(ctx, cudaStreamSynchronize(st));
         ctx->grid_activations = (double)h_stats[0];
-        ctx->grid_sweeps = (double)h_stats[1];
+        ctx->grid_sweeps = 0.5 * (double)h_stats[1];          // counted in half sweeps, reported in double sweeps
         ctx->grid_rounds = (double)rounds_done;
         // set-up (memset, 2 x init, seed [, goal index]) + the rounds (one graph launch, or 2 memsets + 3 kernels per round) [+ parent]
         ctx->grid_host_submissions = 4.0 + (d_goals ? 1.0 : 0.0) + (looped ? 1.0 : 5.0 * (double)rounds_done) + (d_parent ? 1.0 : 0.0);
