@@ -139,23 +139,46 @@ uam_k_grid_select(unsigned long long* __restrict__ keys, size_t n, size_t per_q,
 // d_k + |S_j - S_k| and is valid iff no dead edge lies between them -- checked on the ballot of dead edges, so the two
 // min-scans (from the left, from the right) need no sentinel weights.  span_l[s] / span_r[s]: the edges between this
 // lane and the lane 2^s to its left / right (all ones when there is no such lane).
-__device__ __forceinline__ bool uam_grid_row_step(int* __restrict__ D, const int* __restrict__ C, int li, int ln, int lane,
-                                                  const unsigned below, const unsigned (&span_l)[5], const unsigned (&span_r)[5]) {
+// Per activation and tile row (the costs do not change while a tile is relaxed): prefix sums S of the horizontal edge
+// weights, the ballot of dead edges and S_33 (-1: the edge to the right halo column is dead).  uam_grid_row_step used to
+// rebuild them in every one of the ~160 row steps of an activation -- a five-step shuffle scan on the critical path in front of
+// the two closure scans.
+__device__ __forceinline__ void uam_grid_row_tables(const int* __restrict__ C, int* __restrict__ Srow, unsigned* __restrict__ deadm,
+                                                    int* __restrict__ S33v, int lane) {
+    for (int li = 1; li <= GT; ++li) {
+        const int cv = C[li * GH + lane + 1];
+        const int cl = C[li * GH + lane];                 // column to the left (lane 0: halo column 0)
+        const bool dead_l = cv < 0 || cl < 0;             // e_lane
+        const unsigned dead = __ballot_sync(0xffffffffu, dead_l);
+        int S = dead_l ? 0 : 2 * (cv + cl);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, S, o);
+            if (lane >= o) S += t;
+        }
+        const int c32 = C[li * GH + GT], c33 = C[li * GH + GT + 1];
+        const bool dead32 = c32 < 0 || c33 < 0;
+        const int S33 = __shfl_sync(0xffffffffu, S, 31) + (dead32 ? 0 : 2 * (c32 + c33));
+        Srow[(li - 1) * 32 + lane] = S;
+        if (lane == 0) {
+            deadm[li - 1] = dead;
+            S33v[li - 1] = dead32 ? -1 : S33;
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ bool uam_grid_row_step(int* __restrict__ D, const int* __restrict__ C, const int* __restrict__ Srow,
+                                                  const unsigned* __restrict__ deadm, const int* __restrict__ S33v, int li, int ln,
+                                                  int lane, const unsigned below, const unsigned (&span_l)[5],
+                                                  const unsigned (&span_r)[5]) {
     const int lj = lane + 1;
     const int cv = C[li * GH + lj];
-    const int cl = C[li * GH + lane];                 // column to the left (lane 0: halo column 0)
     const int d0 = D[li * GH + lj];
-    const bool dead_l = cv < 0 || cl < 0;             // e_lane
-    const unsigned dead = __ballot_sync(0xffffffffu, dead_l);
-    int S = dead_l ? 0 : 2 * (cv + cl);
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, S, o);
-        if (lane >= o) S += t;
-    }
-    const int c32 = C[li * GH + GT], c33 = C[li * GH + GT + 1];
-    const bool dead32 = c32 < 0 || c33 < 0;
-    const int S33 = __shfl_sync(0xffffffffu, S, 31) + (dead32 ? 0 : 2 * (c32 + c33));
+    const unsigned dead = deadm[li - 1];
+    const int S = Srow[(li - 1) * 32 + lane];
+    const int S33 = S33v[li - 1];
+    const bool dead32 = S33 < 0;
     // candidates from the previous row
     int d = d0;
     if (cv >= 0) {
@@ -183,7 +206,7 @@ __device__ __forceinline__ bool uam_grid_row_step(int* __restrict__ D, const int
     return drop;
 }
 
-#define UAM_GRID_WARP_SMEM (GH * GH * 4 + GH * GH * 4)
+#define UAM_GRID_WARP_SMEM (GH * GH * 4 + GH * GH * 4 + GT * 32 * 4 + GT * 4 + GT * 4)      // D | C | S | dead | S33: 13 600 B
 
 __global__ void __launch_bounds__(UAM_GRID_WARPS * 32)
 uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ blocked, UamGridGeo g,
@@ -194,6 +217,9 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int* D = reinterpret_cast<int*>(uam_grid_smem + (size_t)warp * UAM_GRID_WARP_SMEM);      // distance - key
     int* C = D + GH * GH;                                                                      // cell cost, -1 = blocked / outside / frozen
+    int* Srow = C + GH * GH;                                                                   // per-row tables of the row step
+    unsigned* deadm = reinterpret_cast<unsigned*>(Srow + GT * 32);
+    int* S33v = reinterpret_cast<int*>(deadm + GT);
     const int H = g.H, W = g.W;
     const size_t cells = (size_t)H * W;
     const unsigned tiles = (unsigned)(g.tiles_x * g.tiles_y);
@@ -303,12 +329,13 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
             // direction comes last -- not only after a quiet top-down + bottom-up pair, which cost half a double sweep more per
             // activation on average.
             {
+                uam_grid_row_tables(C, Srow, deadm, S33v, lane);
                 int quiet = 0;
                 for (;;) {
                     bool ch = false;
                     ++n_half;
                     for (int li = 1; li <= GT; ++li) {
-                        ch |= uam_grid_row_step(D, C, li, li - 1, lane, below, span_l, span_r);
+                        ch |= uam_grid_row_step(D, C, Srow, deadm, S33v, li, li - 1, lane, below, span_l, span_r);
                         __syncwarp();
                     }
                     quiet = __any_sync(0xffffffffu, ch) ? 0 : quiet + 1;
@@ -316,7 +343,7 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
                     ch = false;
                     ++n_half;
                     for (int li = GT; li >= 1; --li) {
-                        ch |= uam_grid_row_step(D, C, li, li + 1, lane, below, span_l, span_r);
+                        ch |= uam_grid_row_step(D, C, Srow, deadm, S33v, li, li + 1, lane, below, span_l, span_r);
                         __syncwarp();
                     }
                     quiet = __any_sync(0xffffffffu, ch) ? 0 : quiet + 1;
@@ -587,7 +614,7 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     const int parts = (int)std::max<size_t>(1, std::min<size_t>(64, per_q / 2048));
     const size_t smem = (size_t)UAM_GRID_WARP_SMEM * UAM_GRID_WARPS;
     UAM_CUDA(ctx, cudaFuncSetAttribute(uam_k_grid_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid_relax = ctx->sm_count * 3;
+    const int grid_relax = ctx->sm_count * 2;      // 2 CTAs of 8 warps per SM (13.6 KB of shared memory per warp)
     const long long max_rounds = 1ll << 40;      // the loop ends when no key is pending
     unsigned h_count = 1;
     long long rounds_done = 0;
