@@ -107,6 +107,7 @@ extern "C" int uam_ctx_create(int device, uam_ctx** out) {
     // tuning knobs from the environment (bench A/B runs); uam_ctx_set_option overrides
     if (const char* e = getenv("UAM_RASTER_LAYOUT")) ctx->raster_layout = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_INT_VARIANT")) ctx->int_variant = std::min(3, std::max(-1, atoi(e)));
+    if (const char* e = getenv("UAM_GRID_HALF_CAP")) ctx->grid_half_cap = std::max(0, atoi(e));
     if (const char* e = getenv("UAM_GRID_GRAPH")) ctx->grid_graph = atoi(e) ? 1 : 0;
     if (const char* e = getenv("UAM_GRID_DELTA")) ctx->grid_delta = std::max(0ll, atoll(e));
     if (const char* e = getenv("UAM_BIN_CHUNK")) ctx->bin_chunk = std::min(1 << 20, std::max(1024, atoi(e)));

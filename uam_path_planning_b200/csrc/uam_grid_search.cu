@@ -46,6 +46,7 @@ struct UamGridGeo {
     int H, W, bands, Q;
     int tiles_x, tiles_y;
     int src_stride;          // 2: sources are (row, col) in band 0; 3: (band, row, col)
+    int half_cap;            // half sweeps per activation before the tile is handed to the next round (0: to the fixed point)
 };
 
 __global__ void __launch_bounds__(256)
@@ -252,6 +253,7 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
         const uint8_t* bb = blocked ? blocked + (size_t)b * cells : nullptr;
         long long m_all = UAM_GRID_INF, m_top = UAM_GRID_INF, m_bot = UAM_GRID_INF, m_side = UAM_GRID_INF;   // m_side: this lane's column
         unsigned n_half = 0;                      // half sweeps (32 row steps each)
+        long long repost = UAM_GRID_INF;          // the sweeps were cut off at g.half_cap under this key: the tile is not at its fixed point yet
         for (;;) {                               // one trip unless some cell sits 10^9 above the key (see above)
             long long far_min = UAM_GRID_INF;
             __syncwarp();
@@ -331,6 +333,7 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
             {
                 uam_grid_row_tables(C, Srow, deadm, S33v, lane);
                 int quiet = 0;
+                const unsigned cap = g.half_cap > 0 ? n_half + (unsigned)g.half_cap : 0xffffffffu;
                 for (;;) {
                     bool ch = false;
                     ++n_half;
@@ -348,6 +351,7 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
                     }
                     quiet = __any_sync(0xffffffffu, ch) ? 0 : quiet + 1;
                     if (quiet >= 2) break;
+                    if (n_half >= cap) { repost = key < repost ? key : repost; break; }      // (warp-uniform) continue in the next round
                 }
             }
             // ---- write back the cells that dropped; smallest dropped value per side ------------------------------------
@@ -419,6 +423,10 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
                 atomicMin(&kq[(size_t)(b + 1) * tiles + tile], (unsigned long long)m_all);
             }
         }
+        // cut off before the fixed point: the tile stays pending with the key it was relaxed with (what it wrote back are valid
+        // upper bounds; the next round goes on from them)
+        if (repost < UAM_GRID_INF && lane == 10)
+            atomicMin(&keys[((size_t)q * g.bands + b) * tiles + tile], (unsigned long long)repost);
     }
 }
 
@@ -568,6 +576,7 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     cudaStream_t st = uam_pick_stream(ctx, stream);
     UamGridGeo g;
     g.H = H; g.W = W; g.bands = bands; g.Q = Q; g.src_stride = src_stride;
+    g.half_cap = ctx->grid_half_cap;
     g.tiles_x = (W + GT - 1) / GT;
     g.tiles_y = (H + GT - 1) / GT;
     const size_t tiles = (size_t)g.tiles_x * g.tiles_y;

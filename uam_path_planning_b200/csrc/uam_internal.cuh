@@ -152,6 +152,7 @@ struct uam_ctx {
     double time_sum_ms = 0.0;
     uint64_t time_count = 0;
     long long grid_delta = 0;           // UAM_OPT_GRID_DELTA (0 = automatic)
+    int grid_half_cap = 4;              // half sweeps per activation before a tile is handed to the next round (UAM_GRID_HALF_CAP; 0: none)
     int grid_graph = 1;                 // UAM_OPT_GRID_GRAPH: relaxation rounds looped on the device (CUDA graph WHILE node)
     int bin_chunk = 8192;               // ... segments per CTA of the histogram / scatter kernels (UAM_BIN_CHUNK, A/B runs only)
     int bin_pt = 2;                     // ... paths a warp of the histogram kernel works on at a time (UAM_BIN_PT: 1, 2, 4)
