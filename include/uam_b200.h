@@ -116,6 +116,9 @@ enum {
                                          with a WHILE conditional node whose body is a round (min key, selection, tile relaxation) and a
                                          one-thread kernel that re-arms the loop while tiles are pending; 0: the host enqueues the rounds
                                          and reads the active count back every 8 rounds.  Same results */
+    UAM_OPT_GRID_HALF_CAP = 13,       /* grid search: half sweeps (32 row steps) a tile activation may run before the tile is handed to the
+                                         next round with what it has (default 4 = two double sweeps; 0: to the fixed point).  Scheduling
+                                         only, same results */
     UAM_OPT_SHAPE_GRID = 9            /* 1 (default): the analytic scorer / point queries look up per-cell candidate lists over
                                          the shapes (a shape with one inequality > max(e, 1e-14) on a whole cell contributes
                                          exact zeros there and is left out; same bits).  0: every shape at every point */

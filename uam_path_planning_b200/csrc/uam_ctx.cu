@@ -142,6 +142,10 @@ extern "C" int uam_ctx_set_option(uam_ctx* ctx, int option, int64_t value) {
             if (value < 0) return uam_fail(ctx, UAM_ERR_INVALID, "grid delta must be >= 0");
             ctx->grid_delta = (long long)value;
             return UAM_OK;
+        case UAM_OPT_GRID_HALF_CAP:
+            if (value < 0 || value > 1000000) return uam_fail(ctx, UAM_ERR_INVALID, "grid half-sweep cap must be 0 (none) .. 1000000");
+            ctx->grid_half_cap = (int)value;
+            return UAM_OK;
         case UAM_OPT_GRID_GRAPH:
             if (value != 0 && value != 1) return uam_fail(ctx, UAM_ERR_INVALID, "grid graph must be 0 or 1");
             ctx->grid_graph = (int)value;

@@ -79,7 +79,7 @@ class Engine:
         self._check(self._lib.uam_sync(self._h))
 
     OPTIONS = {'raster_layout': 1, 'integral_variant': 2, 'l2_fetch_granularity': 3, 'time_kernels': 4,
-               'combine_layers': 5, 'grid_delta': 6, 'host_chunks': 7, 'host_taper': 8, 'shape_grid': 9, 'rasterizer': 10, 'ccl_tiles': 11, 'grid_graph': 12}
+               'combine_layers': 5, 'grid_delta': 6, 'host_chunks': 7, 'host_taper': 8, 'shape_grid': 9, 'rasterizer': 10, 'ccl_tiles': 11, 'grid_graph': 12, 'grid_half_cap': 13}
     STATS = {'score_kernel_ms_mean': 1, 'score_kernel_count': 2, 'grid_activations': 3, 'grid_sweeps': 4, 'grid_rounds': 5,
              'shape_grid_cells': 6, 'shape_grid_items': 7, 'grid_host_submissions': 8}
 
