@@ -209,7 +209,7 @@ __device__ __forceinline__ bool uam_grid_row_step(int* __restrict__ D, const int
 
 #define UAM_GRID_WARP_SMEM (GH * GH * 4 + GH * GH * 4 + GT * 32 * 4 + GT * 4 + GT * 4)      // D | C | S | dead | S33: 13 600 B
 
-__global__ void __launch_bounds__(UAM_GRID_WARPS * 32)
+__global__ void __launch_bounds__(UAM_GRID_WARPS * 32, 2)
 uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ blocked, UamGridGeo g,
                  const unsigned* __restrict__ list, const unsigned long long* __restrict__ list_key,
                  unsigned* __restrict__ count, long long* __restrict__ dist, unsigned long long* __restrict__ keys,
@@ -259,6 +259,71 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
             __syncwarp();
             // ---- load tile + halo (34 rows x 34 columns: lanes cover columns 0..31, lanes 0..1 also 32..33); the loads of
             //      several rows are issued together (the activation's latency is what bounds a round) ------------------
+            // a tile whose halo lies inside the raster (all but the border tiles) needs no bounds tests and 32-bit offsets from
+            // the tile's corner; its two right halo columns are read with the lanes down the rows (4 strided loads per lane
+            // instead of 34 trips with two active lanes) -- the load was 5.7 k of the ~30 k instructions of an activation
+            const bool interior = i0 >= 0 && j0 >= 0 && i0 + GH <= H && j0 + GH <= W;          // (warp-uniform)
+            if (interior) {
+                const long long* dp = dq + (size_t)i0 * W + j0;
+                const uint16_t* cp = cb + (size_t)i0 * W + j0;
+                const uint8_t* bp = bb ? bb + (size_t)i0 * W + j0 : nullptr;
+                auto put = [&](int r, int c, long long dv, int cv, uint8_t bl) {
+                    const long long rel = dv - key;
+                    const bool frozen = bl || rel < 0;
+                    const bool far = !frozen && rel >= UAM_GRID_LIM;
+                    if (far && dv < UAM_GRID_INF) far_min = dv < far_min ? dv : far_min;
+                    D[r * GH + c] = (frozen || far) ? UAM_GRID_INF32 : (int)rel;
+                    C[r * GH + c] = frozen ? -1 : cv;
+                };
+#pragma unroll 1
+                for (int r0 = 0; r0 < 30; r0 += 6) {          // rows 0 .. 29, six at a time
+                    long long dv[6];
+                    int cvv[6];
+                    uint8_t bl[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const unsigned o = (unsigned)(r0 + k) * (unsigned)W + (unsigned)lane;
+                        dv[k] = dp[o];
+                        cvv[k] = (int)cp[o];
+                        bl[k] = bp ? bp[o] : 0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) put(r0 + k, lane, dv[k], cvv[k], bl[k]);
+                }
+                {                                             // rows 30 .. 33
+                    long long dv[4];
+                    int cvv[4];
+                    uint8_t bl[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned o = (unsigned)(30 + k) * (unsigned)W + (unsigned)lane;
+                        dv[k] = dp[o];
+                        cvv[k] = (int)cp[o];
+                        bl[k] = bp ? bp[o] : 0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) put(30 + k, lane, dv[k], cvv[k], bl[k]);
+                }
+                {   // columns 32 and 33: element (row, column) = (lane + 32 a, 32 + c)
+                    long long dv[4];
+                    int cvv[4];
+                    uint8_t bl[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int r = lane + 32 * (t >> 1), c = 32 + (t & 1);
+                        const bool ok = r < GH;
+                        const unsigned o = ok ? (unsigned)r * (unsigned)W + (unsigned)c : 0u;
+                        dv[t] = ok ? dp[o] : UAM_GRID_INF;
+                        cvv[t] = ok ? (int)cp[o] : -1;
+                        bl[t] = (ok && bp) ? bp[o] : 0;
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int r = lane + 32 * (t >> 1), c = 32 + (t & 1);
+                        if (r < GH) put(r, c, dv[t], cvv[t], bl[t]);
+                    }
+                }
+            } else {
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 const int lj = lane + 32 * pass;
@@ -289,6 +354,7 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
                         }
                     }
                 }
+            }
             }
             __syncwarp();
             // ---- candidates from the bands below / above (fixed during this activation) ------------------------------
@@ -355,7 +421,27 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
                 }
             }
             // ---- write back the cells that dropped; smallest dropped value per side ------------------------------------
-            {
+            if (interior) {
+                long long* dp = dq + (size_t)i0 * W + j0 + lane + 1;
+                for (int r0 = 1; r0 <= GT; r0 += 8) {
+                    long long old[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) old[k] = dp[(unsigned)(r0 + k) * (unsigned)W];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int li = r0 + k;
+                        const int rel = D[li * GH + lane + 1];
+                        const long long now = key + (long long)rel;
+                        if (rel < UAM_GRID_INF32 && now < old[k]) {
+                            dp[(unsigned)li * (unsigned)W] = now;
+                            m_all = now < m_all ? now : m_all;
+                            m_side = now < m_side ? now : m_side;
+                            if (li == 1) m_top = now < m_top ? now : m_top;
+                            if (li == GT) m_bot = now < m_bot ? now : m_bot;
+                        }
+                    }
+                }
+            } else {
                 const int lj = lane + 1;
                 const int j = j0 + lj;
                 for (int r0 = 1; r0 <= GT; r0 += 8) {
@@ -376,8 +462,6 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
                             m_side = now < m_side ? now : m_side;
                             if (li == 1) m_top = now < m_top ? now : m_top;
                             if (li == GT) m_bot = now < m_bot ? now : m_bot;
-                        } else if (rel >= UAM_GRID_INF32 && old[k] < UAM_GRID_INF && old[k] - key >= UAM_GRID_LIM) {
-                            // still too far above this key: its own arrivals are handled by the next trip
                         }
                     }
                 }
