@@ -365,18 +365,29 @@ uam_k_grid_relax(const uint16_t* __restrict__ cost, const uint8_t* __restrict__ 
                 const uint16_t* c2 = cost + (size_t)b2 * cells;
                 const uint8_t* bl2 = blocked ? blocked + (size_t)b2 * cells : nullptr;
                 const int j = j0 + lane + 1;
+                const size_t corner = interior ? (size_t)i0 * W + j : 0;
                 for (int r0 = 1; r0 <= GT; r0 += 8) {
                     long long dv[8];
                     int cvv[8];
                     uint8_t bl[8];
+                    if (interior) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int i = i0 + r0 + k;
-                        const bool ok = i < H && j < W;
-                        const size_t gi = ok ? (size_t)i * W + j : 0;
-                        dv[k] = ok ? d2[gi] : UAM_GRID_INF;
-                        cvv[k] = ok ? (int)c2[gi] : 0;
-                        bl[k] = (ok && bl2) ? bl2[gi] : 0;
+                        for (int k = 0; k < 8; ++k) {
+                            const unsigned o = (unsigned)(r0 + k) * (unsigned)W;
+                            dv[k] = d2[corner + o];
+                            cvv[k] = (int)c2[corner + o];
+                            bl[k] = bl2 ? bl2[corner + o] : 0;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int i = i0 + r0 + k;
+                            const bool ok = i < H && j < W;
+                            const size_t gi = ok ? (size_t)i * W + j : 0;
+                            dv[k] = ok ? d2[gi] : UAM_GRID_INF;
+                            cvv[k] = ok ? (int)c2[gi] : 0;
+                            bl[k] = (ok && bl2) ? bl2[gi] : 0;
+                        }
                     }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
