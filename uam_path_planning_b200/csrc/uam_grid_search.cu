@@ -12,10 +12,10 @@
 //                               clears their keys (the others wait: relaxing them now would be redone when the
 //                               shorter fronts arrive -- measured 32 activations per tile without the ordering);
 //           uam_k_grid_relax    one WARP per active triple: loads the tile + 1-cell halo of dist (as 32-bit offsets
-//                               from the tile's key; cells below the key are frozen) / cost into its 9 KB slice
+//                               from the tile's key; cells below the key are frozen) / cost into its 13.6 KB slice
 //                               of shared memory, folds in the candidates from the bands above / below (those do
 //                               not change during the activation), then alternates a top-down and a bottom-up
-//                               Gauss-Seidel sweep until nothing moves.  A sweep step handles one row: the three
+//                               Gauss-Seidel sweep until a sweep in each direction moves nothing.  A sweep step handles one row: the three
 //                               neighbours in the previous row, then the exact closure along the row in both
 //                               directions as two (min,+) warp scans -- with S the prefix sum of the horizontal
 //                               edge weights, min_k<=j (d_k + S_j - S_k) = S_j + prefixmin(d - S) and
@@ -24,7 +24,12 @@
 //                               and the smallest dropped value on each side goes into the key of the neighbour
 //                               tile behind that side (atomicMin), the smallest overall into the keys of the same
 //                               tile in the bands above / below.
-//   rounds repeat until no tile is active (the active count is read back every few rounds).
+//   rounds repeat until the selection finds no tile.  The loop runs on the device: one CUDA graph whose WHILE conditional node has
+//   a round as its body (uam_k_grid_loop_cond re-arms it); UAM_OPT_GRID_GRAPH = 0 is the host-driven loop (active count read
+//   back every 8 rounds).  Inside a round the warps take list entries through a work counter; an activation builds its per-row
+//   tables once (prefix sums of the horizontal edge weights, dead-edge ballots), runs at most UAM_OPT_GRID_HALF_CAP half sweeps
+//   (default: two double sweeps) and, if the tile is not at its fixed point by then, leaves it pending for the next round --
+//   a round is bulk-synchronous, so it must not wait for its longest activation.
 //   uam_k_grid_parent then picks each cell's predecessor: argmin over the neighbours in a fixed slot order with a
 //   strict '<' -- deterministic, identical to the oracle's post-pass.
 #include <algorithm>
