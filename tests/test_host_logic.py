@@ -247,6 +247,21 @@ def test_c_abi_exports_every_declared_symbol():
 
 
 @pytest.mark.skipif(have_gpu(), reason='checks the behaviour WITHOUT a CUDA device')
+def test_option_and_stat_tables_match_the_header():
+    """Engine.OPTIONS / Engine.STATS are the enum values of include/uam_b200.h (UAM_OPT_* / UAM_STAT_*): every enumerator has
+    its name in the Python table with the same number, and nothing else is in the tables."""
+    import re
+    from uam_path_planning_b200.engine import Engine
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'uam_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', ' ', hdr, flags=re.S)
+    opts = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r'UAM_OPT_([A-Z0-9_]+)\s*=\s*(\d+)', hdr)}
+    stats = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r'UAM_STAT_([A-Z0-9_]+)\s*=\s*(\d+)', hdr)}
+    assert opts == Engine.OPTIONS, set(opts.items()) ^ set(Engine.OPTIONS.items())
+    assert {k.replace('score_kernel_ms_mean', 'score_kernel_ms_mean'): v for k, v in stats.items()} == Engine.STATS, \
+        set(stats.items()) ^ set(Engine.STATS.items())
+    assert len(set(opts.values())) == len(opts) and len(set(stats.values())) == len(stats)
+
+
 def test_no_cpu_fallback():
     """Without a GPU the product refuses to work: ctx creation fails and every evaluation raises."""
     lib = _lib.load()
