@@ -729,7 +729,7 @@ def test_grid_search_exact(uam, torch, H, W, wall):
         dg, pg = eng.grid_search(torch.from_numpy(cost).cuda(), srcs, torch.from_numpy(blocked).cuda())
         assert np.array_equal(dg.cpu().numpy(), dist) and np.array_equal(pg.cpu().numpy(), parent)
         subs[graph] = (eng.get_stat('grid_host_submissions'), eng.get_stat('grid_rounds'))
-    assert subs[1][0] <= 7 and subs[1][1] >= 1 and subs[0][0] >= 5 * subs[0][1]
+    assert subs[1][0] <= 9 and subs[1][1] >= 1 and subs[0][0] >= 5 * subs[0][1]
     # the cap on the sweeps of one activation (an unfinished tile stays pending for the next round) only changes the schedule
     for cap in (0, 2, 7):
         eng = uam.Engine()

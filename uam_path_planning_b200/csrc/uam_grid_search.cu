@@ -655,12 +655,22 @@ int uam_grid_mean_cost(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_bl
 }
 
 // Tail of one relaxation round inside the CUDA-graph WHILE loop: another round unless the selection found no tile (or the
-// safety cap is hit).  stats[2] counts the rounds.
-__global__ void uam_k_grid_loop_cond(cudaGraphConditionalHandle handle, const unsigned* __restrict__ count,
-                                     unsigned long long* __restrict__ stats, unsigned long long max_rounds) {
-    const unsigned long long r = stats[2] + 1ull;
-    stats[2] = r;
-    cudaGraphSetConditional(handle, (*count != 0u && r < max_rounds) ? 1u : 0u);
+// safety cap is hit).  stats[2] counts the rounds, stats[3] keeps the last round's active count.  The kernel also resets what the
+// next round starts from (the list length / work counter and the per-query minima), so a round is three kernels and this one --
+// no memset nodes.
+__global__ void uam_k_grid_loop_cond(cudaGraphConditionalHandle handle, unsigned* __restrict__ count,
+                                     unsigned long long* __restrict__ minkey, int Q, unsigned long long* __restrict__ stats,
+                                     unsigned long long max_rounds) {
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) minkey[q] = ~0ull;
+    if (threadIdx.x == 0) {
+        const unsigned long long r = stats[2] + 1ull;
+        const unsigned n = count[0];
+        stats[2] = r;
+        stats[3] = n;
+        count[0] = 0u;
+        count[1] = 0u;
+        cudaGraphSetConditional(handle, (n != 0u && r < max_rounds) ? 1u : 0u);
+    }
 }
 
 int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_blocked, int bands, int H, int W,
@@ -728,9 +738,11 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     unsigned h_count = 1;
     long long rounds_done = 0;
     // one relaxation round: every argument lives in device memory and none changes from round to round
-    auto enqueue_round = [&](cudaStream_t s) -> int {
-        UAM_CUDA(ctx, cudaMemsetAsync(count, 0, 8, s));
-        UAM_CUDA(ctx, cudaMemsetAsync(minkey, 0xff, (size_t)Q * 8, s));
+    auto enqueue_round = [&](cudaStream_t s, bool resets) -> int {
+        if (resets) {                    // (the graph loop's tail kernel does them for the next round)
+            UAM_CUDA(ctx, cudaMemsetAsync(count, 0, 8, s));
+            UAM_CUDA(ctx, cudaMemsetAsync(minkey, 0xff, (size_t)Q * 8, s));
+        }
         uam_k_grid_minkey<<<Q * parts, 256, 0, s>>>(keys, per_q, parts, minkey);
         UAM_CHECK_LAUNCH(ctx, "uam_k_grid_minkey");
         uam_k_grid_select<<<ctx->sm_count * 4, 256, 0, s>>>(keys, n_flags, per_q, minkey, delta, list, list_key, count,
@@ -768,20 +780,22 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
         if (ok) {
             ok = cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
             if (ok) {
-                const int rc = enqueue_round(cap);
-                uam_k_grid_loop_cond<<<1, 1, 0, cap>>>(handle, count, stats, 1ull << 24);
+                const int rc = enqueue_round(cap, false);
+                uam_k_grid_loop_cond<<<1, 256, 0, cap>>>(handle, count, minkey, Q, stats, 1ull << 24);
                 cudaGraph_t captured = nullptr;
                 ok = cudaStreamEndCapture(cap, &captured) == cudaSuccess && rc == UAM_OK;
             }
         }
         ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
         if (ok) {
-            ok = cudaGraphLaunch(exec, st) == cudaSuccess;
+            ok = cudaMemsetAsync(count, 0, 8, st) == cudaSuccess && cudaMemsetAsync(minkey, 0xff, (size_t)Q * 8, st) == cudaSuccess &&
+                 cudaGraphLaunch(exec, st) == cudaSuccess;
             if (ok) {
-                unsigned long long h_rounds = 0;
-                ok = cudaMemcpyAsync(&h_count, count, 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-                     cudaMemcpyAsync(&h_rounds, stats + 2, 8, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                unsigned long long h_tail[2] = {0, 0};      // rounds, active count of the last round
+                ok = cudaMemcpyAsync(h_tail, stats + 2, 16, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
                      cudaStreamSynchronize(st) == cudaSuccess;
+                const unsigned long long h_rounds = h_tail[0];
+                h_count = (unsigned)h_tail[1];
                 rounds_done = (long long)h_rounds;
                 if (h_rounds) ctx->launches += 4ull * h_rounds - 3ull;      // kernels the loop ran (3 were counted during the capture)
                 if (!ok) {                      // the loop itself failed: nothing to fall back to
@@ -800,7 +814,7 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
     }
     for (long long round = 0; !looped && round < max_rounds && h_count; ++round) {
         rounds_done = round + 1;
-        UAM_TRY(enqueue_round(st));
+        UAM_TRY(enqueue_round(st, true));
         if ((round & 7) == 7) {     // termination check every 8 rounds: rounds with an empty list are no-ops
             UAM_CUDA(ctx, cudaMemcpyAsync(&h_count, count, 4, cudaMemcpyDeviceToHost, st));
             UAM_CUDA(ctx, cudaStreamSynchronize(st));
@@ -814,8 +828,8 @@ int uam_grid_search_impl(uam_ctx* ctx, const uint16_t* d_cost, const uint8_t* d_
         ctx->grid_activations = (double)h_stats[0];
         ctx->grid_sweeps = 0.5 * (double)h_stats[1];          // counted in half sweeps, reported in double sweeps
         ctx->grid_rounds = (double)rounds_done;
-        // set-up (memset, 2 x init, seed [, goal index]) + the rounds (one graph launch, or 2 memsets + 3 kernels per round) [+ parent]
-        ctx->grid_host_submissions = 4.0 + (d_goals ? 1.0 : 0.0) + (looped ? 1.0 : 5.0 * (double)rounds_done) + (d_parent ? 1.0 : 0.0);
+        // set-up (memset, 2 x init, seed [, goal index]) + the rounds (2 memsets + one graph launch, or 2 memsets + 3 kernels per round) [+ parent]
+        ctx->grid_host_submissions = 4.0 + (d_goals ? 1.0 : 0.0) + (looped ? 3.0 : 5.0 * (double)rounds_done) + (d_parent ? 1.0 : 0.0);
     }
     if (d_parent) {
         uam_k_grid_parent<<<grid_fill, 256, 0, st>>>(d_cost, g, (const long long*)d_dist, d_sources, d_parent);
